@@ -1,0 +1,343 @@
+// Generic bf16 x bf16 -> fp32 GEMM on tcgen05 tensor cores (sm_100a), operands fed by TMA.
+//
+//   C[M,N] = epilogue( sum_k A(m,k) * B(n,k) )
+//
+// Replaces the tf.keras.layers.Dense MatMul+BiasAdd call sites of the reference
+// (clickstream_transformer/transformer.py:112-116,139-141,158,163-167; head.py:35-45) and
+// their autodiff transposes.  Operands may be K-major (k contiguous in memory) or MN-major
+// (m / n contiguous), which covers X*W, dY*W^T and X^T*dY without materialised transposes.
+//
+// One CTA = one 128 x BN output tile (x one K split).  Warp roles: warp 0 = TMA producer and
+// TMEM allocator, warp 1 = single-thread tcgen05.mma issuer, warps 2..5 = epilogue
+// (TMEM -> registers -> global).  A `stages`-deep mbarrier ring connects producer and issuer.
+#include "common.cuh"
+#include "../../include/b4cp.h"
+
+namespace b4cp {
+
+static constexpr int BM = 128;
+static constexpr int BK = 64;  // bf16 elements = one 128-byte swizzle row
+static constexpr int A_STAGE_BYTES = BM * BK * 2;
+
+struct GemmKernelParams {
+  int M, N, K;
+  int BN;
+  int a_mn, b_mn;
+  int stages;
+  int k_tiles_total;
+  int k_tiles_per_split;
+  b4cp_gemm_epilogue ep;
+};
+
+__global__ void __launch_bounds__(192, 1)
+gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const GemmKernelParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // 1024-byte alignment is required by the 128B swizzle atoms.
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  const int BN = p.BN;
+  const int b_stage_bytes = BN * BK * 2;
+  const int stage_bytes = A_STAGE_BYTES + b_stage_bytes;
+  uint8_t* tiles = smem;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tiles + (size_t)p.stages * stage_bytes);
+  uint64_t* empty_bar = full_bar + p.stages;
+  uint64_t* tmem_full_bar = empty_bar + p.stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
+  const int kt_begin = blockIdx.z * p.k_tiles_per_split;
+  const int kt_end = min(p.k_tiles_total, kt_begin + p.k_tiles_per_split);
+  uint32_t tmem_cols = 32;
+  while ((int)tmem_cols < BN) tmem_cols <<= 1;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmA);
+      tma_prefetch_desc(&tmB);
+    }
+    tmem_alloc(tmem_slot, tmem_cols);
+    tmem_relinquish();
+  } else if (warp == 1 && lane == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kt = kt_begin; kt < kt_end; ++kt) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sA = tiles + (size_t)stage * stage_bytes;
+        uint8_t* sB = sA + A_STAGE_BYTES;
+        mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
+        if (!p.a_mn) {
+          tma_load_2d(sA, &tmA, &full_bar[stage], kt * BK, m0);
+        } else {
+          for (int h = 0; h < BM / 64; ++h)
+            tma_load_2d(sA + h * (64 * BK * 2), &tmA, &full_bar[stage], m0 + h * 64, kt * BK);
+        }
+        if (!p.b_mn) {
+          tma_load_2d(sB, &tmB, &full_bar[stage], kt * BK, n0);
+        } else {
+          for (int h = 0; h < BN / 64; ++h)
+            tma_load_2d(sB + h * (64 * BK * 2), &tmB, &full_bar[stage], n0 + h * 64, kt * BK);
+        }
+        if (++stage == p.stages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(BM, BN, p.a_mn, p.b_mn);
+      // K-major: 8-row groups 1024 B apart; one UMMA_K (16 bf16) = 32 B along the row.
+      // MN-major: 8 K-rows per 1024-B group, 64-wide M/N blocks one full box (64 x BK) apart;
+      //           one UMMA_K = two groups = 2048 B.
+      const uint32_t a_lbo = p.a_mn ? 64 * BK * 2 : 16, a_sbo = 1024;
+      const uint32_t b_lbo = p.b_mn ? 64 * BK * 2 : 16, b_sbo = 1024;
+      const uint32_t a_kstep = p.a_mn ? 2048 : 32;
+      const uint32_t b_kstep = p.b_mn ? 2048 : 32;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kt = kt_begin; kt < kt_end; ++kt) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sA = smem_u32(tiles + (size_t)stage * stage_bytes);
+        const uint32_t sB = sA + A_STAGE_BYTES;
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          const uint64_t da = umma_smem_desc(sA + k * a_kstep, a_lbo, a_sbo);
+          const uint64_t db = umma_smem_desc(sB + k * b_kstep, b_lbo, b_sbo);
+          umma_bf16(tmem_base, da, db, idesc, (kt > kt_begin || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+        if (++stage == p.stages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      umma_commit(tmem_full_bar);
+    }
+  } else {
+    // ---- epilogue: warp w may only touch TMEM lanes [32*(w%4), 32*(w%4)+32)
+    const int q = warp & 3;
+    const int row = m0 + q * 32 + lane;
+    const bool row_ok = row < p.M;
+    const b4cp_gemm_epilogue& ep = p.ep;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    float* out_f32 = ep.out_f32 ? ep.out_f32 + (size_t)blockIdx.z * ep.split_stride : nullptr;
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+      tmem_ld_wait();
+      const int col0 = n0 + c0;
+      if (!row_ok || col0 >= p.N) continue;
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * ep.alpha;
+      const int ncol = min(32, p.N - col0);
+      if (ep.bias) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j < ncol) v[j] += __ldg(ep.bias + col0 + j);
+      }
+      if (ep.relu) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+      }
+      if (ep.gate) {  // dY * [gate > 0]  (ReLU backward)
+        const __nv_bfloat16* g =
+            reinterpret_cast<const __nv_bfloat16*>(ep.gate) + (size_t)row * ep.ld_gate + col0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j < ncol && !(__bfloat162float(g[j]) > 0.f)) v[j] = 0.f;
+      }
+      if (ep.addend) {
+        const float* a = ep.addend + (size_t)row * ep.ld_addend + col0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j < ncol) v[j] += a[j];
+      }
+      if (out_f32) {
+        float* o = out_f32 + (size_t)row * ep.ld_f32 + col0;
+        if (ncol == 32 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        } else {
+          for (int j = 0; j < ncol; ++j) o[j] = v[j];
+        }
+      }
+      if (ep.out_bf16) {
+        __nv_bfloat16* o =
+            reinterpret_cast<__nv_bfloat16*>(ep.out_bf16) + (size_t)row * ep.ld_bf16 + col0;
+        if (ncol == 32 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(v[j], v[j + 1]);
+            __nv_bfloat162 h1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]);
+            __nv_bfloat162 h3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
+            uint4 pk;
+            pk.x = *reinterpret_cast<uint32_t*>(&h0);
+            pk.y = *reinterpret_cast<uint32_t*>(&h1);
+            pk.z = *reinterpret_cast<uint32_t*>(&h2);
+            pk.w = *reinterpret_cast<uint32_t*>(&h3);
+            *reinterpret_cast<uint4*>(o + j) = pk;
+          }
+        } else {
+          for (int j = 0; j < ncol; ++j) o[j] = __float2bfloat16_rn(v[j]);
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) ==
+            cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2-D bf16 tensor map, 128B swizzle, zero fill out of bounds.
+int make_tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer,
+                      uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    set_last_error("cuTensorMapEncodeTiled entry point not available");
+    return -2;
+  }
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {row_stride_bytes};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims,
+                  strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled failed (%d): base=%p inner=%llu outer=%llu stride=%llu",
+                   (int)r, base, (unsigned long long)inner, (unsigned long long)outer,
+                   (unsigned long long)row_stride_bytes);
+    return -3;
+  }
+  return 0;
+}
+
+static int pick_bn(int N, int b_mn) {
+  int bn;
+  if (N > 128) bn = 256;
+  else if (N > 64) bn = 128;
+  else if (N > 32) bn = 64;
+  else if (N > 16) bn = 32;
+  else bn = 16;
+  if (b_mn && bn < 64) bn = 64;
+  return bn;
+}
+
+}  // namespace b4cp
+
+using namespace b4cp;
+
+extern "C" int b4cp_gemm_bf16(const void* A, int a_mn, long lda, const void* B, int b_mn,
+                              long ldb, int M, int N, int K, int splits,
+                              const b4cp_gemm_epilogue* ep, void* stream) {
+  B4CP_CHECK_ARG(A && B && ep, "gemm: null operand");
+  B4CP_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm: bad shape M=%d N=%d K=%d", M, N, K);
+  B4CP_CHECK_ARG((lda * 2) % 16 == 0 && (ldb * 2) % 16 == 0,
+                 "gemm: leading dimensions must be multiples of 8 elements (lda=%ld ldb=%ld)", lda,
+                 ldb);
+  B4CP_CHECK_ARG(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0,
+                 "gemm: operands must be 16-byte aligned");
+  B4CP_CHECK_ARG(ep->out_f32 || ep->out_bf16, "gemm: no output requested");
+  GemmKernelParams p;
+  p.M = M;
+  p.N = N;
+  p.K = K;
+  p.a_mn = a_mn ? 1 : 0;
+  p.b_mn = b_mn ? 1 : 0;
+  p.BN = pick_bn(N, p.b_mn);
+  p.k_tiles_total = ceil_div(K, BK);
+  if (splits < 1) splits = 1;
+  if (splits > p.k_tiles_total) splits = p.k_tiles_total;
+  p.k_tiles_per_split = ceil_div(p.k_tiles_total, splits);
+  splits = ceil_div(p.k_tiles_total, p.k_tiles_per_split);
+  B4CP_CHECK_ARG(splits == 1 || (ep->out_f32 && !ep->out_bf16 && !ep->bias && !ep->relu &&
+                                 !ep->gate && !ep->addend),
+                 "gemm: split-K writes raw fp32 partials only");
+  p.ep = *ep;
+  const int stage_bytes = A_STAGE_BYTES + p.BN * BK * 2;
+  int stages = (200 * 1024) / stage_bytes;
+  if (stages > 6) stages = 6;
+  if (stages > p.k_tiles_per_split) stages = p.k_tiles_per_split < 2 ? 2 : p.k_tiles_per_split;
+  p.stages = stages;
+  const size_t smem = (size_t)stages * stage_bytes + (2 * stages + 1) * 8 + 16 + 1024;
+
+  CUtensorMap tmA, tmB;
+  int rc;
+  if (!p.a_mn)
+    rc = make_tmap_bf16_2d(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, BK, BM);
+  else
+    rc = make_tmap_bf16_2d(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda * 2, 64, BK);
+  if (rc) return rc;
+  if (!p.b_mn)
+    rc = make_tmap_bf16_2d(&tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, BK, p.BN);
+  else
+    rc = make_tmap_bf16_2d(&tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb * 2, 64, BK);
+  if (rc) return rc;
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    B4CP_CUDA(cudaFuncSetAttribute(gemm_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   227 * 1024));
+    attr_set = true;
+  }
+  dim3 grid(ceil_div(M, BM), ceil_div(N, p.BN), splits);
+  gemm_umma_kernel<<<grid, 192, smem, (cudaStream_t)stream>>>(tmA, tmB, p);
+  B4CP_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int b4cp_gemm_splits_for(int M, int N, int K) {
+  // enough K-splits to put roughly one wave of CTAs on 148 SMs
+  const int bn = pick_bn(N, 1);
+  const long tiles = (long)ceil_div(M, BM) * ceil_div(N, bn);
+  const int kt = ceil_div(K, BK);
+  long s = (148 + tiles - 1) / tiles;
+  if (s > kt) s = kt;
+  if (s < 1) s = 1;
+  return (int)s;
+}

@@ -1,0 +1,210 @@
+"""Pins the CPU oracle: the reference's two known answers, its docstring example, and an
+independent torch-autograd restatement of the whole Cloze model (forward and backward)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import clickpath_oracle as O
+
+
+def test_kat_masked_loss_reference_main_block():
+    # clickstream_transformer/losses.py:101-123: expected -log(0.05) = 2.9957323
+    y_true = np.array([[1, -1], [2, -1]], dtype=np.float32)
+    y_pred = np.array([[[0.9, 0.05, 0.05], [0.5, 0.3, 0.2]]] * 2, dtype=np.float32)
+    for mode in ("exact_tf23", "logits"):
+        loss = O.cloze_masked_loss(y_true, y_pred, ce_mode=mode)
+        assert abs(float(loss) - 2.9957323) < 1e-5
+    # plain MaskedLoss on the unflattened tensors gives the same mean over the 2 valid items
+    ml = O.masked_loss(
+        y_true, y_pred,
+        lambda y, p: O.sparse_categorical_crossentropy_probs(
+            y.reshape(-1), p.reshape(-1, 3)).reshape(y.shape))
+    assert abs(float(ml) - 2.9957323) < 1e-5
+
+
+def test_kat_ndcg_reference_main_block():
+    # examples/BERT4Rec/source/utils.py:262-272: expected 0.81546488 (= sklearn ndcg_score)
+    y_true = np.array([[1, 0]], dtype=np.float32)
+    y_pred = np.array([[[0.9, 0.1, 0.01], [0.5, 0.3, 0.01]]], dtype=np.float32)
+    s, n = O.cloze_ndcg_update(y_true, y_pred, k=3)
+    assert abs(float(s / n) - 0.81546488) < 1e-6
+    from sklearn.metrics import ndcg_score
+    sk = ndcg_score([[0, 1, 0], [1, 0, 0]], [[0.9, 0.1, 0.01], [0.5, 0.3, 0.01]], k=3)
+    assert abs(float(s / n) - sk) < 1e-6
+    r, n = O.cloze_recall_update(y_true, y_pred, k=1)
+    assert float(r / n) == 0.5
+
+
+def test_segment_markers_docstring_example():
+    # clickstream_transformer/transformer.py:8-19
+    seq = np.array([[3, 4, 1, 444, 1, 903, 186, 1, 947, 1, 798, 0, 0, 0, 0, 0, 0, 4, 814, 706,
+                     959, 537, 4]])
+    want = [0, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 2, 2, 2, 2, 2, 3]
+    assert O.create_segment_markers(seq)[0].tolist() == want
+
+
+def test_positional_encoding_check_value():
+    pe = O.positional_encoding(10000, 64)
+    assert pe.dtype == np.float32 and pe.shape == (10000, 64)
+    np.testing.assert_allclose(pe[1, :4], [0.84147096, 0.5403023, 0.68156135, 0.731761],
+                               rtol=0, atol=1e-7)
+
+
+def test_chaining_and_segments():
+    a = np.array([[11, 12, 0], [13, 0, 0]])
+    b = np.array([[21, 22], [23, 24]])
+    ch = O.chain_sequences([a, b])
+    assert ch.tolist() == [[3, 4, 11, 12, 0, 4, 21, 22, 4], [3, 4, 13, 0, 0, 4, 23, 24, 4]]
+    st, en = O.segment_bounds(ch[0])
+    assert st.tolist() == [0, 2, 6] and en.tolist() == [1, 5, 8]
+
+
+def test_lookup_ids_and_n_masked():
+    ids = O.lookup_ids([["[PAD]", "[MASK]", "b", "zzz", "[SEP]"]], ["a", "b"])
+    assert ids.tolist() == [[0, 1, 11, 12, 4]]
+    assert O.n_masked_for(49, 0.15, 10) == 7
+    assert O.n_masked_for(49, 0.4, 10) == 10
+    assert O.n_masked_for(5, 0.15, 10) == 0
+
+
+def test_topk_ties_lowest_id_first():
+    s = np.array([[0.5, 0.9, 0.5, 0.9, 0.1]], dtype=np.float32)
+    assert O.top_k_ids(s, 4).tolist() == [[1, 3, 0, 2]]
+
+
+def test_exact_tf23_equals_logits_mode_without_clipping():
+    rng = np.random.default_rng(0)
+    z = rng.normal(size=(7, 50))
+    p = np.exp(z) / np.exp(z).sum(-1, keepdims=True)
+    lab = rng.integers(0, 50, size=7)
+    a = O.sparse_categorical_crossentropy_probs(lab, p, "exact_tf23")
+    b = O.sparse_categorical_crossentropy_probs(lab, p, "logits")
+    np.testing.assert_allclose(a, b, rtol=1e-6)
+
+
+def test_empty_batch_loss_is_zero():
+    assert float(O.cloze_masked_loss(np.zeros((0, 3), np.float32),
+                                     np.zeros((0, 3, 5), np.float32))) == 0.0
+    loss, dz, n = O.cloze_ce_from_logits(np.zeros((4, 5)), np.full(4, -1))
+    assert float(loss) == 0.0 and n == 0 and not dz.any()
+
+
+def test_adam_first_step_is_lr_sign():
+    th, m, v = O.adam_step(np.zeros(3), np.array([1.0, -2.0, 0.5]), np.zeros(3), np.zeros(3), 1)
+    np.testing.assert_allclose(th, [-1e-3, 1e-3, -1e-3], rtol=1e-6)
+
+
+# ------------------------------------------------------------------ torch-autograd cross-check
+def _torch_model_loss(ids_list, labels, P, L, H, pe, masks=None):
+    tp = {k: torch.tensor(v, dtype=torch.float64, requires_grad=True) for k, v in P.items()}
+    F = len(ids_list)
+    d = sum(P[f"emb.{f}"].shape[1] for f in range(F))
+    emb = torch.cat([tp[f"emb.{f}"][torch.tensor(ids)] for f, ids in enumerate(ids_list)], -1)
+    S = emb.shape[1]
+    x = emb * float(np.float32(math.sqrt(d))) + torch.tensor(pe[:S], dtype=torch.float64)
+    if masks and masks.get("in") is not None:
+        x = x * torch.tensor(masks["in"])
+    pad = torch.tensor(ids_list[0] == 0)
+    B = x.shape[0]
+    dh = d // H
+    for l in range(L):
+        g = lambda n: tp[f"enc.{l}.{n}"]
+        q = (x @ g("wq") + g("bq")).view(B, S, H, dh).transpose(1, 2)
+        k = (x @ g("wk") + g("bk")).view(B, S, H, dh).transpose(1, 2)
+        v = (x @ g("wv") + g("bv")).view(B, S, H, dh).transpose(1, 2)
+        z = q @ k.transpose(-1, -2) / float(np.float32(math.sqrt(dh)))
+        z = z + pad[:, None, None, :].double() * -1e9
+        a = torch.softmax(z, -1)
+        o = (a @ v).transpose(1, 2).reshape(B, S, d)
+        y = o @ g("wo") + g("bo")
+        if masks and masks.get((l, 1)) is not None:
+            y = y * torch.tensor(masks[(l, 1)])
+        x1 = torch.nn.functional.layer_norm(x + y, (d,), g("ln1_g"), g("ln1_b"), eps=1e-6)
+        ff = torch.relu(x1 @ g("w1") + g("b1")) @ g("w2") + g("b2")
+        if masks and masks.get((l, 2)) is not None:
+            ff = ff * torch.tensor(masks[(l, 2)])
+        x = torch.nn.functional.layer_norm(x1 + ff, (d,), g("ln2_g"), g("ln2_b"), eps=1e-6)
+    hit = torch.tensor(ids_list[0] == 1)
+    rows = x[hit]  # row-major (b, s) order, like tf.where
+    h = rows
+    i = 0
+    while f"head.{i}.w" in tp:
+        h = torch.relu(h @ tp[f"head.{i}.w"] + tp[f"head.{i}.b"])
+        i += 1
+    logits = h @ tp["head.out.w"] + tp["head.out.b"]
+    lab = torch.tensor(np.asarray(labels).reshape(-1))
+    lab = lab[lab >= 0].long()
+    loss = torch.nn.functional.cross_entropy(logits, lab, reduction="mean")
+    loss.backward()
+    return loss.item(), {k: v.grad.numpy() if v.grad is not None else np.zeros_like(P[k])
+                         for k, v in tp.items()}, logits.detach().numpy()
+
+
+def make_tiny_problem(seed=0, B=5, Lmax=7, V=40, dims=(8,), L=2, H=2, dff=12, head=(16, 8),
+                      with_dropout=False):
+    rng = np.random.default_rng(seed)
+    rows = [V + 11] + [9 + 11] * (len(dims) - 1)
+    P = O.init_params(rng, rows, dims, L, dff, head, V, dtype=np.float64)
+    for k in P:  # non-trivial biases / LN params so their gradients are exercised
+        if k.endswith((".bq", ".bk", ".bv", ".bo", ".b1", ".b2", ".b", "_b")):
+            P[k] = rng.normal(scale=0.1, size=P[k].shape)
+        if k.endswith("_g"):
+            P[k] = 1 + rng.normal(scale=0.1, size=P[k].shape)
+    seqs, labels = [], []
+    lens = rng.integers(2, Lmax + 1, size=B)
+    lens[0] = Lmax
+    items = np.zeros((B, Lmax), dtype=np.int64)
+    lab = []
+    for b in range(B):
+        row = rng.integers(10, V + 10, size=lens[b])
+        nm = 0 if b == 1 else max(1, int(lens[b] * 0.4))  # one zero-mask row
+        pos = np.sort(rng.choice(lens[b], size=nm, replace=False))
+        lab.append((row[pos] - 10).tolist())
+        row[pos] = 1
+        items[b, :lens[b]] = row
+    mmax = max(len(l) for l in lab)
+    labels = np.full((B, mmax), -1.0)
+    for b, l in enumerate(lab):
+        labels[b, :len(l)] = l
+    ids_list = [O.chain_sequences([items])]
+    for f in range(1, len(dims)):
+        ev = rng.integers(10, 19, size=(B, Lmax))
+        ev[items == 0] = 0
+        ids_list.append(O.chain_sequences([ev]))
+    pe = O.positional_encoding(10000, sum(dims))
+    masks = None
+    if with_dropout:
+        S = ids_list[0].shape[1]
+        d = sum(dims)
+        mk = lambda: (rng.random((B, S, d)) >= 0.1) / 0.9
+        masks = {"in": mk()}
+        for l in range(L):
+            masks[(l, 1)] = mk()
+            masks[(l, 2)] = mk()
+    return ids_list, labels, P, L, H, pe, masks
+
+
+@pytest.mark.parametrize("dims,with_dropout", [((8,), False), ((8, 4), False), ((8,), True)])
+def test_oracle_matches_torch_autograd(dims, with_dropout):
+    ids_list, labels, P, L, H, pe, masks = make_tiny_problem(dims=dims, with_dropout=with_dropout)
+    loss, G, ex = O.cloze_train_step(ids_list, labels, P, L, H, pe, np.float64, masks)
+    tloss, TG, tlogits = _torch_model_loss(ids_list, labels, P, L, H, pe, masks)
+    # the oracle embeds in fp32 (reference rounding) before the float64 encoder
+    assert abs(loss - tloss) < 1e-7
+    lab = labels.reshape(-1)
+    np.testing.assert_allclose(ex["logits"][lab >= 0], tlogits, rtol=1e-6, atol=1e-7)
+    for k in P:
+        np.testing.assert_allclose(G[k], TG[k], rtol=1e-5, atol=1e-8, err_msg=k)
+    # pad rows and the [PAD] embedding row receive exactly zero gradient only through masking:
+    assert ex["n_valid"] == int((lab >= 0).sum())
+
+
+def test_pad_rows_are_dead_compute():
+    # a PAD key gets exactly zero attention weight
+    ids_list, labels, P, L, H, pe, _ = make_tiny_problem()
+    x, caches = O.encoder_fwd(ids_list, P, L, H, pe, np.float32)
+    pad = ids_list[0] == 0
+    a = caches[0][0]["a"]
+    assert (a[np.broadcast_to(pad[:, None, None, :], a.shape)] == 0).all()
