@@ -1,0 +1,602 @@
+// Encoder-layer kernels that are not GEMMs (the Dense layers go through gemm_umma.cu):
+//   - fused short-sequence masked self-attention, forward and backward
+//     (transformer.py:64-97 scaled_dot_product_attention, :130-156 split/merge heads);
+//   - residual + dropout + LayerNormalization(eps=1e-6), forward and backward
+//     (transformer.py:202-213, LayerNormalization non-fused path: biased variance);
+//   - column sums (bias gradients) and partial-sum reductions.
+// Sequences are short (S <= 256): one CTA owns one (sequence, head); Q/K/V/dO live in shared
+// memory as bf16 with an odd word stride, scores never touch HBM.
+#include <algorithm>
+
+#include "common.cuh"
+#include "../../include/b4cp.h"
+
+namespace b4cp {
+
+static constexpr int MAX_S = 256;
+
+__device__ __forceinline__ float bf2f(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+// cooperative load of one head's [S x dh] slice (row stride ld in global) into smem [S][dh+2]
+__device__ __forceinline__ void load_head_tile(__nv_bfloat16* dst, const __nv_bfloat16* src, int S,
+                                               int dh, long ld) {
+  const int words = dh / 2;
+  for (int i = threadIdx.x; i < S * words; i += blockDim.x) {
+    const int r = i / words, w = i - r * words;
+    reinterpret_cast<uint32_t*>(dst + (size_t)r * (dh + 2))[w] =
+        reinterpret_cast<const uint32_t*>(src + (size_t)r * ld)[w];
+  }
+}
+
+// ------------------------------------------------------------------------- attention forward
+// grid = B*H, block = 128 or 256.  qkv: [T][3d] bf16 (q | k | v), out: [T][d] bf16, lse: [B][H][S].
+__global__ void __launch_bounds__(256)
+attention_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __restrict__ ids,
+                     int S, int H, int dh, __nv_bfloat16* __restrict__ out,
+                     float* __restrict__ lse_out) {
+  extern __shared__ __align__(16) uint8_t sm[];
+  const int d = H * dh;
+  const int b = blockIdx.x / H, h = blockIdx.x % H;
+  const int st = dh + 2;
+  __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(sm);
+  __nv_bfloat16* sK = sQ + (size_t)S * st;
+  __nv_bfloat16* sV = sK + (size_t)S * st;
+  float* sPad = reinterpret_cast<float*>(sV + (size_t)S * st);
+  const int nwarps = blockDim.x >> 5;
+  float* sP = sPad + S;  // [nwarps][S]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const __nv_bfloat16* base = qkv + (size_t)b * S * 3 * d + h * dh;
+  load_head_tile(sQ, base, S, dh, 3L * d);
+  load_head_tile(sK, base + d, S, dh, 3L * d);
+  load_head_tile(sV, base + 2 * d, S, dh, 3L * d);
+  for (int j = threadIdx.x; j < S; j += blockDim.x)
+    sPad[j] = (ids[(size_t)b * S + j] == 0) ? -1e9f : 0.f;  // create_padding_mask * -1e9
+  __syncthreads();
+  const float sqrt_dh = sqrtf((float)dh);
+  float* myP = sP + (size_t)warp * S;
+  for (int i = warp; i < S; i += nwarps) {
+    float z[MAX_S / 32];
+    float m = -INFINITY;
+#pragma unroll
+    for (int t = 0; t < MAX_S / 32; ++t) {
+      const int j = lane + 32 * t;
+      z[t] = -INFINITY;
+      if (j < S) {
+        float acc = 0.f;
+        const __nv_bfloat162* qr = reinterpret_cast<const __nv_bfloat162*>(sQ + (size_t)i * st);
+        const __nv_bfloat162* kr = reinterpret_cast<const __nv_bfloat162*>(sK + (size_t)j * st);
+        for (int c = 0; c < dh / 2; ++c) {
+          const float2 qv = __bfloat1622float2(qr[c]);
+          const float2 kv = __bfloat1622float2(kr[c]);
+          acc = fmaf(qv.x, kv.x, acc);
+          acc = fmaf(qv.y, kv.y, acc);
+        }
+        z[t] = __fdiv_rn(acc, sqrt_dh) + sPad[j];
+        m = fmaxf(m, z[t]);
+      }
+    }
+    m = warp_max(m);
+    float sum = 0.f;
+#pragma unroll
+    for (int t = 0; t < MAX_S / 32; ++t) {
+      const int j = lane + 32 * t;
+      if (j < S) {
+        z[t] = expf(z[t] - m);
+        sum += z[t];
+      }
+    }
+    sum = warp_sum(sum);
+    const float inv = 1.f / sum;
+#pragma unroll
+    for (int t = 0; t < MAX_S / 32; ++t) {
+      const int j = lane + 32 * t;
+      if (j < S) myP[j] = z[t] * inv;
+    }
+    if (lane == 0 && lse_out) lse_out[((size_t)b * H + h) * S + i] = m + logf(sum);
+    __syncwarp();
+    for (int c = lane; c < dh; c += 32) {
+      float acc = 0.f;
+      for (int j = 0; j < S; ++j) acc = fmaf(myP[j], bf2f(sV[(size_t)j * st + c]), acc);
+      out[((size_t)b * S + i) * d + h * dh + c] = __float2bfloat16_rn(acc);
+    }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------- attention backward
+// dqkv: [T][3d] bf16.  Phase 1 (warp per query row): delta_i and dQ_i.  Phase 2 (warp per key
+// row): dK_j, dV_j.  Probabilities are recomputed from the saved log-sum-exp.
+__global__ void __launch_bounds__(256)
+attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ dout,
+                     const float* __restrict__ lse_in, const int32_t* __restrict__ ids, int S,
+                     int H, int dh, __nv_bfloat16* __restrict__ dqkv) {
+  extern __shared__ __align__(16) uint8_t sm[];
+  const int d = H * dh;
+  const int b = blockIdx.x / H, h = blockIdx.x % H;
+  const int st = dh + 2;
+  __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(sm);
+  __nv_bfloat16* sK = sQ + (size_t)S * st;
+  __nv_bfloat16* sV = sK + (size_t)S * st;
+  __nv_bfloat16* sDO = sV + (size_t)S * st;
+  float* sPad = reinterpret_cast<float*>(sDO + (size_t)S * st);
+  float* sLse = sPad + S;
+  float* sDelta = sLse + S;
+  const int nwarps = blockDim.x >> 5;
+  float* sP = sDelta + S;             // [nwarps][S]
+  float* sDZ = sP + (size_t)nwarps * S;  // [nwarps][S]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const __nv_bfloat16* base = qkv + (size_t)b * S * 3 * d + h * dh;
+  load_head_tile(sQ, base, S, dh, 3L * d);
+  load_head_tile(sK, base + d, S, dh, 3L * d);
+  load_head_tile(sV, base + 2 * d, S, dh, 3L * d);
+  load_head_tile(sDO, dout + (size_t)b * S * d + h * dh, S, dh, (long)d);
+  for (int j = threadIdx.x; j < S; j += blockDim.x) {
+    sPad[j] = (ids[(size_t)b * S + j] == 0) ? -1e9f : 0.f;
+    sLse[j] = lse_in[((size_t)b * H + h) * S + j];
+  }
+  __syncthreads();
+  const float sqrt_dh = sqrtf((float)dh);
+  const float inv_sqrt = 1.f / sqrt_dh;
+  float* myP = sP + (size_t)warp * S;
+  float* myDZ = sDZ + (size_t)warp * S;
+  __nv_bfloat16* dq_out = dqkv + (size_t)b * S * 3 * d + h * dh;
+
+  // ---- phase 1: rows of the score matrix
+  for (int i = warp; i < S; i += nwarps) {
+    float p[MAX_S / 32], da[MAX_S / 32];
+    float delta = 0.f;
+    const float lse_i = sLse[i];
+#pragma unroll
+    for (int t = 0; t < MAX_S / 32; ++t) {
+      const int j = lane + 32 * t;
+      p[t] = 0.f;
+      da[t] = 0.f;
+      if (j < S) {
+        float acc = 0.f, acc2 = 0.f;
+        const __nv_bfloat162* qr = reinterpret_cast<const __nv_bfloat162*>(sQ + (size_t)i * st);
+        const __nv_bfloat162* kr = reinterpret_cast<const __nv_bfloat162*>(sK + (size_t)j * st);
+        const __nv_bfloat162* gr = reinterpret_cast<const __nv_bfloat162*>(sDO + (size_t)i * st);
+        const __nv_bfloat162* vr = reinterpret_cast<const __nv_bfloat162*>(sV + (size_t)j * st);
+        for (int c = 0; c < dh / 2; ++c) {
+          const float2 qv = __bfloat1622float2(qr[c]), kv = __bfloat1622float2(kr[c]);
+          const float2 gv = __bfloat1622float2(gr[c]), vv = __bfloat1622float2(vr[c]);
+          acc = fmaf(qv.x, kv.x, acc);
+          acc = fmaf(qv.y, kv.y, acc);
+          acc2 = fmaf(gv.x, vv.x, acc2);
+          acc2 = fmaf(gv.y, vv.y, acc2);
+        }
+        p[t] = expf(__fdiv_rn(acc, sqrt_dh) + sPad[j] - lse_i);
+        da[t] = acc2;
+        delta = fmaf(p[t], da[t], delta);
+      }
+    }
+    delta = warp_sum(delta);
+    if (lane == 0) sDelta[i] = delta;
+#pragma unroll
+    for (int t = 0; t < MAX_S / 32; ++t) {
+      const int j = lane + 32 * t;
+      if (j < S) myDZ[j] = p[t] * (da[t] - delta);
+    }
+    __syncwarp();
+    for (int c = lane; c < dh; c += 32) {
+      float acc = 0.f;
+      for (int j = 0; j < S; ++j) acc = fmaf(myDZ[j], bf2f(sK[(size_t)j * st + c]), acc);
+      dq_out[(size_t)i * 3 * d + c] = __float2bfloat16_rn(acc * inv_sqrt);
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+
+  // ---- phase 2: columns of the score matrix
+  for (int j = warp; j < S; j += nwarps) {
+    const bool key_is_pad = sPad[j] != 0.f;  // uniform per warp
+    if (!key_is_pad) {
+#pragma unroll
+      for (int t = 0; t < MAX_S / 32; ++t) {
+        const int i = lane + 32 * t;
+        if (i < S) {
+          float acc = 0.f, acc2 = 0.f;
+          const __nv_bfloat162* qr = reinterpret_cast<const __nv_bfloat162*>(sQ + (size_t)i * st);
+          const __nv_bfloat162* kr = reinterpret_cast<const __nv_bfloat162*>(sK + (size_t)j * st);
+          const __nv_bfloat162* gr = reinterpret_cast<const __nv_bfloat162*>(sDO + (size_t)i * st);
+          const __nv_bfloat162* vr = reinterpret_cast<const __nv_bfloat162*>(sV + (size_t)j * st);
+          for (int c = 0; c < dh / 2; ++c) {
+            const float2 qv = __bfloat1622float2(qr[c]), kv = __bfloat1622float2(kr[c]);
+            const float2 gv = __bfloat1622float2(gr[c]), vv = __bfloat1622float2(vr[c]);
+            acc = fmaf(qv.x, kv.x, acc);
+            acc = fmaf(qv.y, kv.y, acc);
+            acc2 = fmaf(gv.x, vv.x, acc2);
+            acc2 = fmaf(gv.y, vv.y, acc2);
+          }
+          const float pij = expf(__fdiv_rn(acc, sqrt_dh) - sLse[i]);
+          myP[i] = pij;
+          myDZ[i] = pij * (acc2 - sDelta[i]);
+        }
+      }
+    }
+    __syncwarp();
+    for (int c = lane; c < dh; c += 32) {
+      float dk = 0.f, dv = 0.f;
+      if (!key_is_pad) {
+        for (int i = 0; i < S; ++i) {
+          dv = fmaf(myP[i], bf2f(sDO[(size_t)i * st + c]), dv);
+          dk = fmaf(myDZ[i], bf2f(sQ[(size_t)i * st + c]), dk);
+        }
+      }
+      dq_out[(size_t)j * 3 * d + d + c] = __float2bfloat16_rn(dk * inv_sqrt);
+      dq_out[(size_t)j * 3 * d + 2 * d + c] = __float2bfloat16_rn(dv);
+    }
+    __syncwarp();
+  }
+}
+
+// --------------------------------------------------------------- residual + dropout + LayerNorm
+// y = LN(x + dropout(r)) * gamma + beta ; one warp per row, d <= 256.
+static constexpr int LN_MAX_PER_LANE = 8;
+
+struct DropSpec {
+  float inv_keep;
+  uint32_t thresh24;
+  uint64_t seed;
+  uint32_t site;
+};
+
+__global__ void __launch_bounds__(256)
+residual_ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ r, long T, int d,
+                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                       DropSpec dp, float eps, float* __restrict__ y_f32,
+                       __nv_bfloat16* __restrict__ y_bf16, long ld_bf16) {
+  const int lane = threadIdx.x & 31;
+  const long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= T) return;
+  float v[LN_MAX_PER_LANE];
+  float sum = 0.f;
+#pragma unroll
+  for (int t = 0; t < LN_MAX_PER_LANE; ++t) {
+    const int c = lane + 32 * t;
+    v[t] = 0.f;
+    if (c < d) {
+      float rv = r[row * d + c];
+      if (dp.thresh24)
+        rv = dropout_keep(dp.seed, dp.site, (uint64_t)(row * d + c), dp.thresh24) ? rv * dp.inv_keep : 0.f;
+      v[t] = x[row * d + c] + rv;
+      sum += v[t];
+    }
+  }
+  const float mean = warp_sum(sum) / (float)d;
+  float var = 0.f;
+#pragma unroll
+  for (int t = 0; t < LN_MAX_PER_LANE; ++t) {
+    const int c = lane + 32 * t;
+    if (c < d) {
+      const float dv = v[t] - mean;
+      var = fmaf(dv, dv, var);
+    }
+  }
+  var = warp_sum(var) / (float)d;
+  const float rstd = rsqrtf(var + eps);
+#pragma unroll
+  for (int t = 0; t < LN_MAX_PER_LANE; ++t) {
+    const int c = lane + 32 * t;
+    if (c < d) {
+      const float o = (v[t] - mean) * rstd * gamma[c] + beta[c];
+      if (y_f32) y_f32[row * d + c] = o;
+      if (y_bf16) y_bf16[row * ld_bf16 + c] = __float2bfloat16_rn(o);
+    }
+  }
+}
+
+// Backward.  Outputs: dx (fp32, the residual branch), dr (bf16 and/or fp32: gradient w.r.t. the
+// un-dropped Dense output r), and per-block partial column sums [gridDim.x][3][d] of
+// (dy*xhat, dy, dr) = (dgamma, dbeta, bias gradient of the Dense that produced r).
+__global__ void __launch_bounds__(256)
+residual_ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                       const float* __restrict__ r, long T, int d,
+                       const float* __restrict__ gamma, DropSpec dp, float eps,
+                       float* __restrict__ dx, __nv_bfloat16* __restrict__ dr_bf16, long ld_bf16,
+                       float* __restrict__ partial) {
+  __shared__ float red[8][3][LN_MAX_PER_LANE * 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nwarps = blockDim.x >> 5;
+  float pg[LN_MAX_PER_LANE], pb[LN_MAX_PER_LANE], pr[LN_MAX_PER_LANE];
+#pragma unroll
+  for (int t = 0; t < LN_MAX_PER_LANE; ++t) pg[t] = pb[t] = pr[t] = 0.f;
+  for (long row = (long)blockIdx.x * nwarps + warp; row < T; row += (long)gridDim.x * nwarps) {
+    float v[LN_MAX_PER_LANE], g[LN_MAX_PER_LANE], keepf[LN_MAX_PER_LANE];
+    float sum = 0.f;
+#pragma unroll
+    for (int t = 0; t < LN_MAX_PER_LANE; ++t) {
+      const int c = lane + 32 * t;
+      v[t] = 0.f;
+      keepf[t] = 0.f;
+      if (c < d) {
+        float rv = r[row * d + c];
+        keepf[t] = 1.f;
+        if (dp.thresh24) {
+          const bool keep = dropout_keep(dp.seed, dp.site, (uint64_t)(row * d + c), dp.thresh24);
+          keepf[t] = keep ? dp.inv_keep : 0.f;
+          rv *= keepf[t];
+        }
+        v[t] = x[row * d + c] + rv;
+        sum += v[t];
+      }
+    }
+    const float mean = warp_sum(sum) / (float)d;
+    float var = 0.f;
+#pragma unroll
+    for (int t = 0; t < LN_MAX_PER_LANE; ++t) {
+      const int c = lane + 32 * t;
+      if (c < d) {
+        const float dv = v[t] - mean;
+        var = fmaf(dv, dv, var);
+      }
+    }
+    var = warp_sum(var) / (float)d;
+    const float rstd = rsqrtf(var + eps);
+    float m1 = 0.f, m2 = 0.f;
+#pragma unroll
+    for (int t = 0; t < LN_MAX_PER_LANE; ++t) {
+      const int c = lane + 32 * t;
+      g[t] = 0.f;
+      if (c < d) {
+        const float dyv = dy[row * d + c];
+        v[t] = (v[t] - mean) * rstd;  // xhat
+        g[t] = dyv * gamma[c];
+        m1 += g[t];
+        m2 = fmaf(g[t], v[t], m2);
+        pg[t] = fmaf(dyv, v[t], pg[t]);
+        pb[t] += dyv;
+      }
+    }
+    m1 = warp_sum(m1) / (float)d;
+    m2 = warp_sum(m2) / (float)d;
+#pragma unroll
+    for (int t = 0; t < LN_MAX_PER_LANE; ++t) {
+      const int c = lane + 32 * t;
+      if (c < d) {
+        const float dres = rstd * (g[t] - m1 - v[t] * m2);
+        const float drv = dres * keepf[t];
+        if (dx) dx[row * d + c] = dres;
+        if (dr_bf16) dr_bf16[row * ld_bf16 + c] = __float2bfloat16_rn(drv);
+        pr[t] += drv;
+      }
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < LN_MAX_PER_LANE; ++t) {
+    red[warp][0][lane + 32 * t] = pg[t];
+    red[warp][1][lane + 32 * t] = pb[t];
+    red[warp][2][lane + 32 * t] = pr[t];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 3 * d; i += blockDim.x) {
+    const int k = i / d, c = i - k * d;
+    float s = 0.f;
+    for (int w = 0; w < nwarps; ++w) s += red[w][k][c];
+    partial[((size_t)blockIdx.x * 3 + k) * d + c] = s;
+  }
+}
+
+// out[c] = sum_p partial[p][c] (fixed order -> deterministic)
+__global__ void __launch_bounds__(256)
+reduce_partials_kernel(const float* __restrict__ partial, int P, long n, long stride,
+                       float* __restrict__ out) {
+  const long c = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (c >= n) return;
+  float s = 0.f;
+  for (int p = 0; p < P; ++p) s += partial[(size_t)p * stride + c];
+  out[c] = s;
+}
+
+// column sums of a bf16 matrix [T][ld] over rows -> partial[chunk][n]
+static constexpr int CS_ROWS = 512;
+__global__ void __launch_bounds__(256)
+colsum_partial_kernel(const __nv_bfloat16* __restrict__ in, long T, int n, long ld,
+                      float* __restrict__ partial) {
+  __shared__ float red[4][64];
+  const int cx = threadIdx.x & 63, ry = threadIdx.x >> 6;
+  const int c = blockIdx.y * 64 + cx;
+  const long r0 = (long)blockIdx.x * CS_ROWS;
+  const long r1 = min(T, r0 + CS_ROWS);
+  float s = 0.f;
+  if (c < n)
+    for (long r = r0 + ry; r < r1; r += 4) s += bf2f(in[r * ld + c]);
+  red[ry][cx] = s;
+  __syncthreads();
+  if (ry == 0 && c < n)
+    partial[(size_t)blockIdx.x * n + c] = red[0][cx] + red[1][cx] + red[2][cx] + red[3][cx];
+}
+
+__global__ void __launch_bounds__(256)
+cast_f32_bf16_kernel(const float* __restrict__ in, long rows, int cols, long ld_in,
+                     __nv_bfloat16* __restrict__ out, long ld_out) {
+  const long total = rows * ld_out;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total;
+       i += (long)gridDim.x * blockDim.x) {
+    const long r = i / ld_out;
+    const int c = (int)(i - r * ld_out);
+    out[i] = __float2bfloat16_rn(c < cols ? in[r * ld_in + c] : 0.f);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+dropout_mask_kernel(float* __restrict__ out, long n, DropSpec dp) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n;
+       i += (long)gridDim.x * blockDim.x)
+    out[i] = (!dp.thresh24 || dropout_keep(dp.seed, dp.site, (uint64_t)i, dp.thresh24)) ? dp.inv_keep : 0.f;
+}
+
+static DropSpec make_drop(float rate, uint64_t seed, uint32_t site) {
+  DropSpec d;
+  d.inv_keep = 1.0f / (1.0f - rate);
+  d.thresh24 = (uint32_t)((double)rate * 16777216.0);
+  d.seed = seed;
+  d.site = site;
+  return d;
+}
+
+static size_t attn_smem_fwd(int S, int dh, int threads) {
+  return (size_t)3 * S * (dh + 2) * 2 + (size_t)S * 4 + (size_t)(threads / 32) * S * 4;
+}
+static size_t attn_smem_bwd(int S, int dh, int threads) {
+  return (size_t)4 * S * (dh + 2) * 2 + (size_t)3 * S * 4 + (size_t)2 * (threads / 32) * S * 4;
+}
+
+}  // namespace b4cp
+
+using namespace b4cp;
+
+extern "C" int b4cp_attention_fwd(const void* qkv, const int32_t* ids_first, int B, int S, int H,
+                                  int dh, void* out, float* lse, void* stream) {
+  B4CP_CHECK_ARG(S >= 1 && S <= MAX_S, "attention: S=%d must be in [1,%d]", S, MAX_S);
+  B4CP_CHECK_ARG(dh % 2 == 0 && dh >= 2 && dh <= 128, "attention: head depth %d unsupported", dh);
+  if (B == 0) return 0;
+  const int threads = S <= 64 ? 128 : 256;
+  const size_t smem = attn_smem_fwd(S, dh, threads);
+  B4CP_CHECK_ARG(smem <= 227 * 1024, "attention: S=%d dh=%d needs %zu B smem", S, dh, smem);
+  B4CP_CUDA(cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 227 * 1024));
+  attention_fwd_kernel<<<B * H, threads, smem, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)qkv, ids_first, S, H, dh, (__nv_bfloat16*)out, lse);
+  B4CP_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int b4cp_attention_bwd(const void* qkv, const void* dout, const float* lse,
+                                  const int32_t* ids_first, int B, int S, int H, int dh,
+                                  void* dqkv, void* stream) {
+  B4CP_CHECK_ARG(S >= 1 && S <= MAX_S, "attention: S=%d must be in [1,%d]", S, MAX_S);
+  B4CP_CHECK_ARG(dh % 2 == 0 && dh >= 2 && dh <= 128, "attention: head depth %d unsupported", dh);
+  if (B == 0) return 0;
+  const int threads = S <= 64 ? 128 : 256;
+  const size_t smem = attn_smem_bwd(S, dh, threads);
+  B4CP_CHECK_ARG(smem <= 227 * 1024, "attention bwd: S=%d dh=%d needs %zu B smem", S, dh, smem);
+  B4CP_CUDA(cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 227 * 1024));
+  attention_bwd_kernel<<<B * H, threads, smem, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)qkv, (const __nv_bfloat16*)dout, lse, ids_first, S, H, dh,
+      (__nv_bfloat16*)dqkv);
+  B4CP_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int b4cp_residual_ln_fwd(const float* x, const float* r, long T, int d,
+                                    const float* gamma, const float* beta, float dropout_rate,
+                                    uint64_t seed, uint32_t site, float* y_f32, void* y_bf16,
+                                    long ld_bf16, void* stream) {
+  B4CP_CHECK_ARG(d >= 1 && d <= LN_MAX_PER_LANE * 32, "layernorm: d=%d must be <= 256", d);
+  if (T == 0) return 0;
+  residual_ln_fwd_kernel<<<ceil_div(T, 8), 256, 0, (cudaStream_t)stream>>>(
+      x, r, T, d, gamma, beta, make_drop(dropout_rate, seed, site), 1e-6f, y_f32,
+      (__nv_bfloat16*)y_bf16, ld_bf16);
+  B4CP_LAUNCH_CHECK();
+  return 0;
+}
+
+static constexpr int LN_BWD_BLOCKS = 148 * 4;
+
+extern "C" long b4cp_residual_ln_bwd_workspace_bytes(int d) {
+  return (long)LN_BWD_BLOCKS * 3 * d * sizeof(float);
+}
+
+extern "C" int b4cp_residual_ln_bwd(const float* dy, const float* x, const float* r, long T,
+                                    int d, const float* gamma, float dropout_rate, uint64_t seed,
+                                    uint32_t site, float* dx, void* dr_bf16, long ld_bf16,
+                                    float* dgamma, float* dbeta, float* dbias, void* workspace,
+                                    void* stream) {
+  B4CP_CHECK_ARG(d >= 1 && d <= LN_MAX_PER_LANE * 32, "layernorm: d=%d must be <= 256", d);
+  B4CP_CHECK_ARG(workspace, "layernorm bwd: workspace required");
+  cudaStream_t st = (cudaStream_t)stream;
+  float* partial = (float*)workspace;
+  const int blocks = (int)std::min<long>(LN_BWD_BLOCKS, std::max<long>(1, ceil_div(T, 8)));
+  residual_ln_bwd_kernel<<<blocks, 256, 0, st>>>(dy, x, r, T, d, gamma,
+                                                 make_drop(dropout_rate, seed, site), 1e-6f, dx,
+                                                 (__nv_bfloat16*)dr_bf16, ld_bf16, partial);
+  const int rb = ceil_div(d, 256);
+  if (dgamma) reduce_partials_kernel<<<rb, 256, 0, st>>>(partial, blocks, d, 3L * d, dgamma);
+  if (dbeta) reduce_partials_kernel<<<rb, 256, 0, st>>>(partial + d, blocks, d, 3L * d, dbeta);
+  if (dbias) reduce_partials_kernel<<<rb, 256, 0, st>>>(partial + 2 * d, blocks, d, 3L * d, dbias);
+  B4CP_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" long b4cp_colsum_workspace_bytes(long T, int n) {
+  return (long)ceil_div(T, CS_ROWS) * n * sizeof(float);
+}
+
+extern "C" int b4cp_colsum_bf16(const void* in, long T, int n, long ld, float* out,
+                                void* workspace, void* stream) {
+  B4CP_CHECK_ARG(workspace, "colsum: workspace required");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (T == 0) {
+    B4CP_CUDA(cudaMemsetAsync(out, 0, (size_t)n * 4, st));
+    return 0;
+  }
+  const int chunks = ceil_div(T, CS_ROWS);
+  dim3 grid(chunks, ceil_div(n, 64));
+  colsum_partial_kernel<<<grid, 256, 0, st>>>((const __nv_bfloat16*)in, T, n, ld, (float*)workspace);
+  reduce_partials_kernel<<<ceil_div(n, 256), 256, 0, st>>>((const float*)workspace, chunks, n, n, out);
+  B4CP_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int b4cp_reduce_splits(const float* partials, int splits, long n, long split_stride,
+                                  float* out, void* stream) {
+  reduce_partials_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(partials, splits, n,
+                                                                             split_stride, out);
+  B4CP_LAUNCH_CHECK();
+  return 0;
+}
+
+namespace b4cp {
+// sum of split-K partials + optional ReLU-backward gate, fp32 and/or bf16 outputs
+__global__ void __launch_bounds__(256)
+reduce_splits_ex_kernel(const float* __restrict__ partials, int splits, long M, int N,
+                        long split_stride, const __nv_bfloat16* __restrict__ gate, long ld_gate,
+                        float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16,
+                        long ld_bf16) {
+  const long total = M * N;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total;
+       i += (long)gridDim.x * blockDim.x) {
+    const long r = i / N;
+    const int c = (int)(i - r * N);
+    float s = 0.f;
+    for (int p = 0; p < splits; ++p) s += partials[(size_t)p * split_stride + i];
+    if (gate && !(bf2f(gate[r * ld_gate + c]) > 0.f)) s = 0.f;
+    if (out_f32) out_f32[i] = s;
+    if (out_bf16) out_bf16[r * ld_bf16 + c] = __float2bfloat16_rn(s);
+  }
+}
+}  // namespace b4cp
+
+extern "C" int b4cp_reduce_splits_ex(const float* partials, int splits, long M, int N,
+                                     long split_stride, const void* gate, long ld_gate,
+                                     float* out_f32, void* out_bf16, long ld_bf16, void* stream) {
+  if (M * N == 0) return 0;
+  const int blocks = (int)std::min<long>(ceil_div(M * N, 256), 148L * 16);
+  reduce_splits_ex_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
+      partials, splits, M, N, split_stride, (const __nv_bfloat16*)gate, ld_gate, out_f32,
+      (__nv_bfloat16*)out_bf16, ld_bf16);
+  B4CP_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int b4cp_cast_f32_bf16(const float* in, long rows, int cols, long ld_in, void* out,
+                                  long ld_out, void* stream) {
+  if (rows * ld_out == 0) return 0;
+  const int blocks = (int)std::min<long>(ceil_div(rows * ld_out, 256), 148L * 16);
+  cast_f32_bf16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(in, rows, cols, ld_in,
+                                                                  (__nv_bfloat16*)out, ld_out);
+  B4CP_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int b4cp_dropout_mask(float* out, long n, float dropout_rate, uint64_t seed,
+                                 uint32_t site, void* stream) {
+  if (n == 0) return 0;
+  const int blocks = (int)std::min<long>(ceil_div(n, 256), 148L * 16);
+  dropout_mask_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(out, n,
+                                                                 make_drop(dropout_rate, seed, site));
+  B4CP_LAUNCH_CHECK();
+  return 0;
+}

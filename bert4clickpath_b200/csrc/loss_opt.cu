@@ -1,0 +1,235 @@
+// Row-wise softmax cross-entropy over MATERIALISED logits (small-vocabulary / validation path of
+// the Cloze loss: examples/BERT4Rec/source/utils.py:56-134 + losses.py:31-98 in logits mode),
+// the masked-mean reduction, recall@k / NDCG@k counters (utils.py:137-259) and Keras-semantics
+// Adam (examples/BERT4Rec/source/main.py:87).  The large-vocabulary training path is the fused
+// tcgen05 kernel in vocab_ce.cu; both share ce_loss_reduce / the metric counters.
+#include <algorithm>
+
+#include "common.cuh"
+#include "../../include/b4cp.h"
+
+namespace b4cp {
+
+__device__ __forceinline__ void online_merge(float& m, float& s, float m2, float s2) {
+  const float nm = fmaxf(m, m2);
+  if (nm == -INFINITY) {
+    s = 0.f;
+  } else {
+    s = s * expf(m - nm) + s2 * expf(m2 - nm);
+  }
+  m = nm;
+}
+
+__global__ void __launch_bounds__(256)
+ce_rows_stats_kernel(const float* __restrict__ logits, long ld, int V,
+                     const int32_t* __restrict__ labels, float* __restrict__ lse,
+                     float* __restrict__ tgt) {
+  __shared__ float sm_m[8], sm_s[8];
+  const long row = blockIdx.x;
+  const float* z = logits + row * ld;
+  float m = -INFINITY, s = 0.f;
+  for (int v = threadIdx.x; v < V; v += blockDim.x) {
+    const float x = z[v];
+    if (x > m) {
+      s = s * expf(m - x) + 1.f;
+      m = x;
+    } else {
+      s += expf(x - m);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float m2 = __shfl_xor_sync(0xffffffffu, m, o);
+    const float s2 = __shfl_xor_sync(0xffffffffu, s, o);
+    online_merge(m, s, m2, s2);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) {
+    sm_m[warp] = m;
+    sm_s[warp] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float M = sm_m[0], S = sm_s[0];
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) online_merge(M, S, sm_m[w], sm_s[w]);
+    lse[row] = M + logf(S);
+    const int t = labels[row];
+    tgt[row] = (t >= 0 && t < V) ? z[t] : 0.f;
+  }
+}
+
+// out[0] += 0 ; writes out[0] = sum over valid rows of (lse - tgt), out[1] = number of valid rows
+__global__ void __launch_bounds__(1024)
+ce_loss_reduce_kernel(const float* __restrict__ lse, const float* __restrict__ tgt,
+                      const int32_t* __restrict__ labels, long M, float* __restrict__ out) {
+  __shared__ double s_loss[1024];
+  __shared__ int s_n[1024];
+  double a = 0.0;
+  int n = 0;
+  for (long i = threadIdx.x; i < M; i += blockDim.x) {
+    if (labels[i] >= 0) {
+      a += (double)(lse[i] - tgt[i]);
+      ++n;
+    }
+  }
+  s_loss[threadIdx.x] = a;
+  s_n[threadIdx.x] = n;
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) {
+      s_loss[threadIdx.x] += s_loss[threadIdx.x + o];
+      s_n[threadIdx.x] += s_n[threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    out[0] = (float)s_loss[0];
+    out[1] = (float)s_n[0];
+  }
+}
+
+// dz = (softmax(z) - onehot(label)) / n_valid for valid rows, 0 otherwise; bf16 [M][ld_dz]
+__global__ void __launch_bounds__(256)
+ce_rows_grad_kernel(const float* __restrict__ logits, long ld, int V,
+                    const int32_t* __restrict__ labels, const float* __restrict__ lse,
+                    const float* __restrict__ loss_stats, __nv_bfloat16* __restrict__ dz,
+                    long ld_dz, float* __restrict__ probs, long ld_probs) {
+  const long row = blockIdx.x;
+  const float n = loss_stats ? loss_stats[1] : 1.f;
+  const int t = labels ? labels[row] : 0;
+  const float scale = (t >= 0 && n > 0.f) ? 1.f / n : 0.f;
+  const float l = lse[row];
+  const float* z = logits + row * ld;
+  const long span = dz ? ld_dz : V;
+  for (long v = threadIdx.x; v < span; v += blockDim.x) {
+    float p = 0.f;
+    if (v < V) p = expf(z[v] - l);
+    if (probs && v < V) probs[row * ld_probs + v] = p;
+    if (dz) {
+      float g = 0.f;
+      if (v < V) g = (p - (v == t ? 1.f : 0.f)) * scale;
+      dz[row * ld_dz + v] = __float2bfloat16_rn(g);
+    }
+  }
+}
+
+// counters[0] += hits, counters[1] += sum of 1/log2(rank+2) at the hit, counters[2] += n valid
+__global__ void __launch_bounds__(256)
+rank_metrics_kernel(const int32_t* __restrict__ topk_ids, long M, int k, long ld,
+                    const int32_t* __restrict__ labels, float* __restrict__ counters) {
+  __shared__ float s_h[256], s_g[256], s_n[256];
+  float h = 0.f, g = 0.f, n = 0.f;
+  for (long i = threadIdx.x; i < M; i += blockDim.x) {
+    const int t = labels[i];
+    if (t < 0) continue;
+    n += 1.f;
+    for (int r = 0; r < k; ++r) {
+      if (topk_ids[i * ld + r] == t) {
+        h += 1.f;
+        g += 1.f / (logf((float)(r + 2)) / logf(2.0f));  // utils.py:211, :221-223
+      }
+    }
+  }
+  s_h[threadIdx.x] = h;
+  s_g[threadIdx.x] = g;
+  s_n[threadIdx.x] = n;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) {
+      s_h[threadIdx.x] += s_h[threadIdx.x + o];
+      s_g[threadIdx.x] += s_g[threadIdx.x + o];
+      s_n[threadIdx.x] += s_n[threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    counters[0] += s_h[0];
+    counters[1] += s_g[0];
+    counters[2] += s_n[0];
+  }
+}
+
+// Keras Adam: lr_t = lr*sqrt(1-b2^t)/(1-b1^t); theta -= lr_t*m/(sqrt(v)+eps)
+__global__ void __launch_bounds__(256)
+adam_kernel(float* __restrict__ theta, const float* __restrict__ grad, float* __restrict__ m,
+            float* __restrict__ v, long n, float lr, float b1, float b2, float eps,
+            const int* __restrict__ step_dev, int step_host, float grad_scale,
+            __nv_bfloat16* __restrict__ shadow, int cols, long ld_shadow) {
+  const int t = step_dev ? *step_dev : step_host;
+  const float lr_t = lr * sqrtf(1.f - powf(b2, (float)t)) / (1.f - powf(b1, (float)t));
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n;
+       i += (long)gridDim.x * blockDim.x) {
+    const float g = grad[i] * grad_scale;
+    const float mi = b1 * m[i] + (1.f - b1) * g;
+    const float vi = b2 * v[i] + (1.f - b2) * g * g;
+    const float th = theta[i] - lr_t * mi / (sqrtf(vi) + eps);
+    m[i] = mi;
+    v[i] = vi;
+    theta[i] = th;
+    if (shadow) {
+      const long r = i / cols;
+      const int c = (int)(i - r * cols);
+      shadow[r * ld_shadow + c] = __float2bfloat16_rn(th);
+    }
+  }
+}
+
+__global__ void step_increment_kernel(int* step) { *step += 1; }
+
+}  // namespace b4cp
+
+using namespace b4cp;
+
+extern "C" int b4cp_ce_rows_stats(const float* logits, long ld, long M, int V,
+                                  const int32_t* labels, float* lse, float* tgt, void* stream) {
+  if (M == 0) return 0;
+  ce_rows_stats_kernel<<<(unsigned)M, 256, 0, (cudaStream_t)stream>>>(logits, ld, V, labels, lse, tgt);
+  B4CP_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int b4cp_ce_loss_reduce(const float* lse, const float* tgt, const int32_t* labels,
+                                   long M, float* loss_stats, void* stream) {
+  ce_loss_reduce_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(lse, tgt, labels, M, loss_stats);
+  B4CP_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int b4cp_ce_rows_grad(const float* logits, long ld, long M, int V,
+                                 const int32_t* labels, const float* lse, const float* loss_stats,
+                                 void* dz_bf16, long ld_dz, float* probs, long ld_probs,
+                                 void* stream) {
+  if (M == 0) return 0;
+  ce_rows_grad_kernel<<<(unsigned)M, 256, 0, (cudaStream_t)stream>>>(
+      logits, ld, V, labels, lse, loss_stats, (__nv_bfloat16*)dz_bf16, ld_dz, probs, ld_probs);
+  B4CP_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int b4cp_rank_metrics(const int32_t* topk_ids, long M, int k, long ld,
+                                 const int32_t* labels, float* counters, void* stream) {
+  rank_metrics_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(topk_ids, M, k, ld, labels, counters);
+  B4CP_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int b4cp_adam_step(float* theta, const float* grad, float* m, float* v, long n,
+                              float lr, float beta1, float beta2, float eps, const int* step_dev,
+                              int step_host, float grad_scale, void* shadow_bf16, int cols,
+                              long ld_shadow, void* stream) {
+  if (n == 0) return 0;
+  B4CP_CHECK_ARG(step_dev || step_host >= 1, "adam: step must be >= 1");
+  B4CP_CHECK_ARG(!shadow_bf16 || cols > 0, "adam: shadow needs cols");
+  const int blocks = (int)std::min<long>(ceil_div(n, 256), 148L * 16);
+  adam_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(theta, grad, m, v, n, lr, beta1, beta2,
+                                                        eps, step_dev, step_host, grad_scale,
+                                                        (__nv_bfloat16*)shadow_bf16, cols, ld_shadow);
+  B4CP_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int b4cp_step_increment(int* step_dev, void* stream) {
+  step_increment_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev);
+  B4CP_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,278 @@
+"""Thin Python wrappers over the libb4cp C ABI.
+
+torch is used only for device memory and streams: every function here launches hand-written
+sm_100a kernels on torch's current stream and returns torch tensors that alias plain device
+buffers.  Nothing in this module computes with torch operators.
+"""
+import ctypes
+
+import torch
+
+from . import _lib as L
+
+BF16 = torch.bfloat16
+F32 = torch.float32
+I32 = torch.int32
+
+
+def ld8(n):
+    """Leading dimension of a bf16 matrix: TMA needs 16-byte row strides."""
+    return (int(n) + 7) // 8 * 8
+
+
+def _dev(t):
+    assert t.is_cuda and t.is_contiguous(), "device-resident contiguous tensor required"
+    return t
+
+
+def empty(shape, dtype=F32):
+    return torch.empty(shape, dtype=dtype, device="cuda")
+
+
+def zeros(shape, dtype=F32):
+    return torch.zeros(shape, dtype=dtype, device="cuda")
+
+
+class Workspace:
+    """Grow-only byte buffers keyed by name (the C ABI never allocates)."""
+
+    def __init__(self):
+        self._bufs = {}
+
+    def get(self, name, nbytes):
+        nbytes = max(int(nbytes), 256)
+        buf = self._bufs.get(name)
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+            self._bufs[name] = buf
+        return buf
+
+
+WS = Workspace()
+
+
+# ------------------------------------------------------------------------------------ GEMM
+def gemm(A, a_mn, B, b_mn, M, N, K, *, bias=None, relu=False, gate=None, addend=None,
+         out_f32=None, out_bf16=None, alpha=1.0, splits=1, lda=None, ldb=None):
+    """C[M,N] = epilogue(alpha * sum_k A(m,k) B(n,k)); see include/b4cp.h."""
+    ep = L.GemmEpilogue()
+    ep.alpha = alpha
+    ep.bias = bias.data_ptr() if bias is not None else None
+    ep.relu = 1 if relu else 0
+    if gate is not None:
+        ep.gate = gate.data_ptr()
+        ep.ld_gate = gate.stride(0)
+    if addend is not None:
+        ep.addend = addend.data_ptr()
+        ep.ld_addend = addend.stride(0)
+    if out_f32 is not None:
+        ep.out_f32 = out_f32.data_ptr()
+        ep.ld_f32 = out_f32.stride(-2)
+        ep.split_stride = out_f32.stride(0) if out_f32.dim() == 3 else 0
+    if out_bf16 is not None:
+        ep.out_bf16 = out_bf16.data_ptr()
+        ep.ld_bf16 = out_bf16.stride(0)
+    lda = A.stride(0) if lda is None else lda
+    ldb = B.stride(0) if ldb is None else ldb
+    L.call("b4cp_gemm_bf16", L.ptr(A), L.c_int(a_mn), L.c_long(lda), L.ptr(B), L.c_int(b_mn),
+           L.c_long(ldb), L.c_int(M), L.c_int(N), L.c_int(K), L.c_int(splits), ctypes.byref(ep),
+           L.stream_ptr())
+
+
+def gemm_splits_for(M, N, K):
+    return L.lib().b4cp_gemm_splits_for(int(M), int(N), int(K))
+
+
+def reduce_splits(partials, out):
+    splits = partials.shape[0]
+    n = out.numel()
+    L.call("b4cp_reduce_splits", L.ptr(partials), L.c_int(splits), L.c_long(n),
+           L.c_long(partials.stride(0)), L.ptr(out), L.stream_ptr())
+
+
+def gemm_splitk(A, a_mn, B, b_mn, M, N, K, out_f32, ws_name="splitk"):
+    """Deterministic split-K product into out_f32 [M,N] (used for weight gradients)."""
+    splits = gemm_splits_for(M, N, K)
+    if splits <= 1:
+        gemm(A, a_mn, B, b_mn, M, N, K, out_f32=out_f32)
+        return
+    buf = WS.get(ws_name, splits * M * N * 4).view(F32)[: splits * M * N].view(splits, M, N)
+    gemm(A, a_mn, B, b_mn, M, N, K, out_f32=buf, splits=splits)
+    reduce_splits(buf, out_f32)
+
+
+def cast_bf16(x_f32, cols=None, out=None):
+    """fp32 [rows, cols] -> bf16 [rows, ld8(cols)] (zero padded)."""
+    rows = x_f32.shape[0]
+    cols = x_f32.shape[1] if cols is None else cols
+    if out is None:
+        out = empty((rows, ld8(cols)), BF16)
+    L.call("b4cp_cast_f32_bf16", L.ptr(x_f32), L.c_long(rows), L.c_int(cols),
+           L.c_long(x_f32.stride(0)), L.ptr(out), L.c_long(out.stride(0)), L.stream_ptr())
+    return out
+
+
+# ------------------------------------------------------------------------------- embedding
+def _ptr_array(tensors):
+    arr = (ctypes.c_void_p * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = t.data_ptr()
+    return arr
+
+
+def _int_array(vals):
+    arr = (ctypes.c_int * len(vals))()
+    for i, v in enumerate(vals):
+        arr[i] = int(v)
+    return arr
+
+
+def embed_fwd(ids_list, tables, pe, B, S, *, dropout_rate=0.0, seed=0, site=0, out_f32=None,
+              out_bf16=None):
+    F = len(ids_list)
+    dims = [t.shape[1] for t in tables]
+    rows = [t.shape[0] for t in tables]
+    d = sum(dims)
+    assert pe.shape[0] >= S and pe.shape[1] == d
+    if out_f32 is None and out_bf16 is None:
+        out_f32 = empty((B * S, d))
+    L.call("b4cp_embed_fwd", _ptr_array(ids_list), _ptr_array(tables), _int_array(dims),
+           _int_array(rows), L.c_int(F), L.ptr(pe), L.c_int(B), L.c_int(S),
+           L.c_float(dropout_rate), L.c_u64(seed), ctypes.c_uint32(site), L.ptr(out_f32),
+           L.ptr(out_bf16), L.stream_ptr())
+    return out_f32, out_bf16
+
+
+def embed_bwd(dout, d_model, col_offset, dim, ids, rows, table_grad, *, dropout_rate=0.0, seed=0,
+              site=0, uniq_ids=None, n_unique=None):
+    tokens = ids.numel()
+    nbytes = L.lib().b4cp_embed_bwd_workspace_bytes
+    nbytes.restype = ctypes.c_long
+    need = nbytes(ctypes.c_long(tokens), ctypes.c_int(dim))
+    ws = WS.get("embed_bwd", need)
+    L.call("b4cp_embed_bwd", L.ptr(dout), L.c_int(d_model), L.c_int(col_offset), L.c_int(dim),
+           L.ptr(ids), L.c_long(tokens), L.c_int(rows), L.c_float(dropout_rate), L.c_u64(seed),
+           ctypes.c_uint32(site), L.ptr(table_grad), L.ptr(uniq_ids), L.ptr(n_unique), L.ptr(ws),
+           L.c_long(ws.numel()), L.stream_ptr())
+
+
+# --------------------------------------------------------------------------------- encoder
+def attention_fwd(qkv, ids_first, B, S, H, dh, out, lse):
+    L.call("b4cp_attention_fwd", L.ptr(qkv), L.ptr(ids_first), L.c_int(B), L.c_int(S), L.c_int(H),
+           L.c_int(dh), L.ptr(out), L.ptr(lse), L.stream_ptr())
+
+
+def attention_bwd(qkv, dout, lse, ids_first, B, S, H, dh, dqkv):
+    L.call("b4cp_attention_bwd", L.ptr(qkv), L.ptr(dout), L.ptr(lse), L.ptr(ids_first),
+           L.c_int(B), L.c_int(S), L.c_int(H), L.c_int(dh), L.ptr(dqkv), L.stream_ptr())
+
+
+def residual_ln_fwd(x, r, gamma, beta, y_f32, y_bf16, *, dropout_rate=0.0, seed=0, site=0):
+    T, d = x.shape
+    L.call("b4cp_residual_ln_fwd", L.ptr(x), L.ptr(r), L.c_long(T), L.c_int(d), L.ptr(gamma),
+           L.ptr(beta), L.c_float(dropout_rate), L.c_u64(seed), ctypes.c_uint32(site),
+           L.ptr(y_f32), L.ptr(y_bf16), L.c_long(y_bf16.stride(0) if y_bf16 is not None else 0),
+           L.stream_ptr())
+
+
+def residual_ln_bwd(dy, x, r, gamma, dx, dr_bf16, dgamma, dbeta, dbias, *, dropout_rate=0.0,
+                    seed=0, site=0):
+    T, d = x.shape
+    fn = L.lib().b4cp_residual_ln_bwd_workspace_bytes
+    fn.restype = ctypes.c_long
+    ws = WS.get("ln_bwd", fn(ctypes.c_int(d)))
+    L.call("b4cp_residual_ln_bwd", L.ptr(dy), L.ptr(x), L.ptr(r), L.c_long(T), L.c_int(d),
+           L.ptr(gamma), L.c_float(dropout_rate), L.c_u64(seed), ctypes.c_uint32(site), L.ptr(dx),
+           L.ptr(dr_bf16), L.c_long(dr_bf16.stride(0) if dr_bf16 is not None else 0),
+           L.ptr(dgamma), L.ptr(dbeta), L.ptr(dbias), L.ptr(ws), L.stream_ptr())
+
+
+def colsum_bf16(x_bf16, T, n, out):
+    fn = L.lib().b4cp_colsum_workspace_bytes
+    fn.restype = ctypes.c_long
+    ws = WS.get("colsum", fn(ctypes.c_long(T), ctypes.c_int(n)))
+    L.call("b4cp_colsum_bf16", L.ptr(x_bf16), L.c_long(T), L.c_int(n),
+           L.c_long(x_bf16.stride(0)), L.ptr(out), L.ptr(ws), L.stream_ptr())
+
+
+def dropout_mask(n, rate, seed, site):
+    out = empty((n,))
+    L.call("b4cp_dropout_mask", L.ptr(out), L.c_long(n), L.c_float(rate), L.c_u64(seed),
+           ctypes.c_uint32(site), L.stream_ptr())
+    return out
+
+
+# ------------------------------------------------------------------------------- selection
+def select_masked(ids_first, value, capacity):
+    tokens = ids_first.numel()
+    fn = L.lib().b4cp_select_workspace_bytes
+    fn.restype = ctypes.c_long
+    ws = WS.get("select", fn(ctypes.c_long(tokens)))
+    row_index = empty((max(capacity, 1),), I32)
+    count = empty((1,), I32)
+    L.call("b4cp_select_masked", L.ptr(ids_first), L.c_long(tokens), L.c_int(value),
+           L.ptr(row_index), L.c_long(capacity), L.ptr(count), L.ptr(ws), L.stream_ptr())
+    return row_index[:capacity], count
+
+
+def gather_rows(x, row_index, out_f32=None, out_bf16=None):
+    M = row_index.numel()
+    d = x.shape[1]
+    L.call("b4cp_gather_rows", L.ptr(x), L.c_int(d), L.ptr(row_index), L.c_long(M), L.ptr(out_f32),
+           L.ptr(out_bf16), L.c_long(out_bf16.stride(0) if out_bf16 is not None else 0),
+           L.stream_ptr())
+
+
+def scatter_rows(src, row_index, dst):
+    M = row_index.numel()
+    L.call("b4cp_scatter_rows", L.ptr(src), L.c_int(src.shape[1]), L.ptr(row_index), L.c_long(M),
+           L.ptr(dst), L.stream_ptr())
+
+
+# ------------------------------------------------------------------------- loss and metrics
+def ce_rows_stats(logits, V, labels, lse, tgt):
+    M = logits.shape[0]
+    L.call("b4cp_ce_rows_stats", L.ptr(logits), L.c_long(logits.stride(0)), L.c_long(M),
+           L.c_int(V), L.ptr(labels), L.ptr(lse), L.ptr(tgt), L.stream_ptr())
+
+
+def ce_loss_reduce(lse, tgt, labels, loss_stats):
+    L.call("b4cp_ce_loss_reduce", L.ptr(lse), L.ptr(tgt), L.ptr(labels), L.c_long(labels.numel()),
+           L.ptr(loss_stats), L.stream_ptr())
+
+
+def ce_rows_grad(logits, V, labels, lse, loss_stats, dz_bf16=None, probs=None):
+    M = logits.shape[0]
+    L.call("b4cp_ce_rows_grad", L.ptr(logits), L.c_long(logits.stride(0)), L.c_long(M), L.c_int(V),
+           L.ptr(labels), L.ptr(lse), L.ptr(loss_stats), L.ptr(dz_bf16),
+           L.c_long(dz_bf16.stride(0) if dz_bf16 is not None else 0), L.ptr(probs),
+           L.c_long(probs.stride(0) if probs is not None else 0), L.stream_ptr())
+
+
+def topk_rows(scores, V, k, out_ids=None, out_scores=None):
+    rows = scores.shape[0]
+    if out_ids is None:
+        out_ids = empty((rows, k), I32)
+    L.call("b4cp_topk_rows", L.ptr(scores), L.c_long(scores.stride(0)), L.c_long(rows), L.c_int(V),
+           L.c_int(k), L.ptr(out_ids), L.ptr(out_scores), L.c_long(out_ids.stride(0)),
+           L.stream_ptr())
+    return out_ids, out_scores
+
+
+def rank_metrics(topk_ids, k, labels, counters):
+    L.call("b4cp_rank_metrics", L.ptr(topk_ids), L.c_long(topk_ids.shape[0]), L.c_int(k),
+           L.c_long(topk_ids.stride(0)), L.ptr(labels), L.ptr(counters), L.stream_ptr())
+
+
+# ------------------------------------------------------------------------------- optimizer
+def adam_step(theta, grad, m, v, *, lr, beta1=0.9, beta2=0.999, eps=1e-9, step_dev=None,
+              step_host=0, grad_scale=1.0, shadow=None, cols=0):
+    n = theta.numel()
+    L.call("b4cp_adam_step", L.ptr(theta), L.ptr(grad), L.ptr(m), L.ptr(v), L.c_long(n),
+           L.c_float(lr), L.c_float(beta1), L.c_float(beta2), L.c_float(eps), L.ptr(step_dev),
+           L.c_int(step_host), L.c_float(grad_scale), L.ptr(shadow), L.c_int(cols),
+           L.c_long(shadow.stride(0) if shadow is not None else 0), L.stream_ptr())
+
+
+def step_increment(step_dev):
+    L.call("b4cp_step_increment", L.ptr(step_dev), L.stream_ptr())

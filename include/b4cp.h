@@ -64,6 +64,131 @@ int b4cp_gemm_bf16(const void* A, int a_mn, long lda, const void* B, int b_mn, l
 /* number of K splits that fills the GPU for an M x N output */
 int b4cp_gemm_splits_for(int M, int N, int K);
 
+/* sums `splits` partial matrices (n elements each, split_stride apart) in fixed order */
+int b4cp_reduce_splits(const float* partials, int splits, long n, long split_stride, float* out,
+                       void* stream);
+/* same, over a dense [M][N] matrix, with an optional ReLU-backward gate (bf16, zero where
+ * gate <= 0) and fp32 and/or bf16 outputs */
+int b4cp_reduce_splits_ex(const float* partials, int splits, long M, int N, long split_stride,
+                          const void* gate, long ld_gate, float* out_f32, void* out_bf16,
+                          long ld_bf16, void* stream);
+/* fp32 [rows][ld_in] -> bf16 [rows][ld_out], columns >= cols are zero-filled */
+int b4cp_cast_f32_bf16(const float* in, long rows, int cols, long ld_in, void* out, long ld_out,
+                       void* stream);
+
+/* ------------------------------------------------------------------ input embedding
+ * Replaces Embedding gather x F, tf.concat, * sqrt(d_model), + pos_encoding[:, :S] and the
+ * encoder's input Dropout: clickstream_transformer/transformer.py:376-398, :263.
+ *   out[b,s,off_f+j] = fl32(fl32(E_f[ids_f[b,s], j] * fl32(sqrt(d_model))) + PE[s, off_f+j])
+ * h_ids / h_tables / h_dims / h_rows are HOST arrays of length F (device pointers inside).
+ * `pe` is the fp32 [>=S][d_model] sinusoid table.  dropout_rate = 0 disables dropout; otherwise
+ * kept values are scaled by 1/(1-rate) and the keep bit of element i is the one
+ * b4cp_dropout_mask(seed, site) reports.  Bit-exact against the oracle when dropout is off.
+ */
+int b4cp_embed_fwd(const int32_t* const* h_ids, const float* const* h_tables, const int* h_dims,
+                   const int* h_rows, int F, const float* pe, int B, int S, float dropout_rate,
+                   uint64_t seed, uint32_t site, float* out_f32, void* out_bf16, void* stream);
+
+/* Backward of the gather for ONE feature (TF autodiff IndexedSlices + UnsortedSegmentSum,
+ * implied by transformer.py:347-355): table_grad[r, :] = sqrt(d_model) * sum over tokens with
+ * id r of dout[token, col_offset : col_offset+dim] (after the input-dropout mask).  Deterministic:
+ * stable radix sort of (id, token), one segment per unique id, fixed summation order.
+ * table_grad (rows x dim, fp32) is zero-filled by the call.  uniq_ids / n_unique are optional.
+ */
+long b4cp_embed_bwd_workspace_bytes(long tokens, int max_dim);
+int b4cp_embed_bwd(const float* dout, int d_model, int col_offset, int dim, const int32_t* ids,
+                   long tokens, int rows, float dropout_rate, uint64_t seed, uint32_t site,
+                   float* table_grad, int32_t* uniq_ids, int32_t* n_unique, void* workspace,
+                   long workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------ encoder layer pieces
+ * Fused short-sequence masked self-attention (S <= 256), one CTA per (sequence, head):
+ * clickstream_transformer/transformer.py:64-97 (scaled_dot_product_attention, additive -1e9 key
+ * padding mask from create_padding_mask :38-41) and :130-156 (split/merge heads).
+ * qkv: bf16 [B*S][3*d] = (q | k | v) with head h in columns h*dh..; out: bf16 [B*S][d];
+ * lse: fp32 [B][H][S] log-sum-exp of each score row (saved for the backward).
+ */
+int b4cp_attention_fwd(const void* qkv, const int32_t* ids_first, int B, int S, int H, int dh,
+                       void* out, float* lse, void* stream);
+int b4cp_attention_bwd(const void* qkv, const void* dout, const float* lse,
+                       const int32_t* ids_first, int B, int S, int H, int dh, void* dqkv,
+                       void* stream);
+
+/* y = LayerNormalization(eps=1e-6)(x + Dropout(r)): transformer.py:204-206, :209-211.
+ * Backward returns dx (residual branch, fp32), dr (gradient of the Dense output r, bf16) and the
+ * reduced dgamma, dbeta and dbias = column sums of dr.  d <= 256.
+ */
+int b4cp_residual_ln_fwd(const float* x, const float* r, long T, int d, const float* gamma,
+                         const float* beta, float dropout_rate, uint64_t seed, uint32_t site,
+                         float* y_f32, void* y_bf16, long ld_bf16, void* stream);
+long b4cp_residual_ln_bwd_workspace_bytes(int d);
+int b4cp_residual_ln_bwd(const float* dy, const float* x, const float* r, long T, int d,
+                         const float* gamma, float dropout_rate, uint64_t seed, uint32_t site,
+                         float* dx, void* dr_bf16, long ld_bf16, float* dgamma, float* dbeta,
+                         float* dbias, void* workspace, void* stream);
+
+/* bias gradients: out[c] = sum over rows of a bf16 [T][ld] matrix (deterministic two-stage) */
+long b4cp_colsum_workspace_bytes(long T, int n);
+int b4cp_colsum_bf16(const void* in, long T, int n, long ld, float* out, void* workspace,
+                     void* stream);
+
+/* fills out[i] with 1/(1-rate) (kept) or 0 (dropped) for the n elements of a dropout site */
+int b4cp_dropout_mask(float* out, long n, float dropout_rate, uint64_t seed, uint32_t site,
+                      void* stream);
+
+/* ------------------------------------------------------------------ output selection
+ * clickstream_transformer/clickstream_transformer.py:260-297 (_gather_output_by_raw_value):
+ * token indices whose first-feature id == value, in (b, s) order.  row_index[i] = -1 for
+ * count <= i < capacity.  gather_rows writes zero vectors for -1 (the reference's zero padding).
+ */
+long b4cp_select_workspace_bytes(long tokens);
+int b4cp_select_masked(const int32_t* ids_first, long tokens, int value, int32_t* row_index,
+                       long capacity, int32_t* count, void* workspace, void* stream);
+/* reference label matrix (B, max_n_masked) float32 padded with -1.0 (input_pipeline.py:95-97,
+ * :198-214) -> int32 labels of the valid entries in row-major order (= [MASK] order) */
+int b4cp_compact_labels(const float* labels, long n, float label_pad, int32_t* out, long capacity,
+                        int32_t* count, void* workspace, void* stream);
+int b4cp_gather_rows(const float* x, int d, const int32_t* row_index, long M, float* out_f32,
+                     void* out_bf16, long ld_bf16, void* stream);
+int b4cp_scatter_rows(const float* src, int d, const int32_t* row_index, long M, float* dst,
+                      void* stream);
+
+/* ------------------------------------------------------------------ Cloze loss, materialised
+ * Small-vocabulary path of SoftMaxHead + ClozeMaskedLoss (head.py:38-47;
+ * examples/BERT4Rec/source/utils.py:56-134; losses.py:31-98) in logits mode.
+ * labels: int32 [M], -1 = padded row.  loss_stats[0] = sum of (lse - z_t) over valid rows,
+ * loss_stats[1] = number of valid rows (the loss is their ratio, 0 when there are none).
+ */
+int b4cp_ce_rows_stats(const float* logits, long ld, long M, int V, const int32_t* labels,
+                       float* lse, float* tgt, void* stream);
+int b4cp_ce_loss_reduce(const float* lse, const float* tgt, const int32_t* labels, long M,
+                        float* loss_stats, void* stream);
+/* dz = (softmax - onehot) / loss_stats[1] (bf16, optional) and/or probabilities (fp32, optional) */
+int b4cp_ce_rows_grad(const float* logits, long ld, long M, int V, const int32_t* labels,
+                      const float* lse, const float* loss_stats, void* dz_bf16, long ld_dz,
+                      float* probs, long ld_probs, void* stream);
+
+/* ------------------------------------------------------------------ ranking metrics
+ * tf.math.top_k order (score desc, ties -> lower id): utils.py:176, :245.  k <= 256.
+ * rank_metrics accumulates counters += (hits, sum 1/log2(rank+2), n_valid): utils.py:176-187,
+ * :211, :225-252.
+ */
+int b4cp_topk_rows(const float* scores, long ld, long rows, int V, int k, int32_t* out_ids,
+                   float* out_scores, long ld_out, void* stream);
+int b4cp_rank_metrics(const int32_t* topk_ids, long M, int k, long ld, const int32_t* labels,
+                      float* counters, void* stream);
+
+/* ------------------------------------------------------------------ optimizer
+ * tf.keras.optimizers.Adam(lr, 0.9, 0.999, epsilon=1e-9) (examples/BERT4Rec/source/main.py:87):
+ *   lr_t = lr*sqrt(1-b2^t)/(1-b1^t); m,v updates; theta -= lr_t * m / (sqrt(v) + eps).
+ * t comes from *step_dev when given (graph-friendly) else step_host (1-based).  grad is scaled by
+ * grad_scale first.  Optionally refreshes a bf16 shadow [n/cols][ld_shadow] of the parameter.
+ */
+int b4cp_adam_step(float* theta, const float* grad, float* m, float* v, long n, float lr,
+                   float beta1, float beta2, float eps, const int* step_dev, int step_host,
+                   float grad_scale, void* shadow_bf16, int cols, long ld_shadow, void* stream);
+int b4cp_step_increment(int* step_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -133,6 +133,45 @@ def _softmax(z):
     return e / e.sum(axis=-1, keepdims=True)
 
 
+def mha_core_fwd(q, k, v, pad, H):
+    """split_heads + scaled_dot_product_attention + merge (transformer.py:130-156, :64-97).
+    q,k,v (B,S,d) after the Dense projections; pad (B,S) bool; returns merged (B,S,d)."""
+    B, S, d = q.shape
+    dh = d // H
+    dt = q.dtype.type
+
+    def split(t):
+        return t.reshape(B, S, H, dh).transpose(0, 2, 1, 3)
+
+    qh, kh, vh = split(q), split(k), split(v)
+    z = (qh @ kh.transpose(0, 1, 3, 2)) / dt(np.sqrt(np.float32(dh)))
+    z = z + pad[:, None, None, :].astype(q.dtype) * dt(-1e9)
+    a = _softmax(z)
+    o = (a @ vh).transpose(0, 2, 1, 3).reshape(B, S, d)
+    m = z.max(-1)
+    lse = m + np.log(np.exp(z - m[..., None]).sum(-1))
+    return o, dict(qh=qh, kh=kh, vh=vh, a=a, H=H, lse=lse)
+
+
+def mha_core_bwd(do_merged, att):
+    a, qh, kh, vh, H = att["a"], att["qh"], att["kh"], att["vh"], att["H"]
+    B, _, S, dh = qh.shape
+    d = H * dh
+    dt = qh.dtype.type
+    do = do_merged.reshape(B, S, H, dh).transpose(0, 2, 1, 3)
+    dv = a.transpose(0, 1, 3, 2) @ do
+    da = do @ vh.transpose(0, 1, 3, 2)
+    dz = a * (da - (da * a).sum(-1, keepdims=True))
+    inv = dt(1.0) / dt(np.sqrt(np.float32(dh)))
+    dq = (dz @ kh) * inv
+    dk = (dz.transpose(0, 1, 3, 2) @ qh) * inv
+
+    def merge(t):
+        return t.transpose(0, 2, 1, 3).reshape(B, S, d)
+
+    return merge(dq), merge(dk), merge(dv)
+
+
 def encoder_layer_fwd(x, pad, p, num_heads, drop1=None, drop2=None):
     """transformer.py:202-213 (EncoderLayer), :137-160 (MHA), :64-97 (SDPA), :163-167 (FFN).
 
@@ -146,15 +185,7 @@ def encoder_layer_fwd(x, pad, p, num_heads, drop1=None, drop2=None):
     q = x @ p["wq"] + p["bq"]
     k = x @ p["wk"] + p["bk"]
     v = x @ p["wv"] + p["bv"]
-
-    def split(t):
-        return t.reshape(B, S, H, dh).transpose(0, 2, 1, 3)
-
-    qh, kh, vh = split(q), split(k), split(v)
-    z = (qh @ kh.transpose(0, 1, 3, 2)) / dt(np.sqrt(np.float32(dh)))
-    z = z + pad[:, None, None, :].astype(x.dtype) * dt(-1e9)
-    a = _softmax(z)
-    o = (a @ vh).transpose(0, 2, 1, 3).reshape(B, S, d)
+    o, att = mha_core_fwd(q, k, v, pad, H)
     y = o @ p["wo"] + p["bo"]
     if drop1 is not None:
         y_d = y * drop1
@@ -168,7 +199,7 @@ def encoder_layer_fwd(x, pad, p, num_heads, drop1=None, drop2=None):
     g_d = g * drop2 if drop2 is not None else g
     r2 = x1 + g_d
     x2, ln2 = layer_norm_fwd(r2, p["ln2_g"], p["ln2_b"])
-    cache = dict(x=x, qh=qh, kh=kh, vh=vh, a=a, o=o, ln1=ln1, x1=x1, pre=pre, hdn=hdn, ln2=ln2,
+    cache = dict(x=x, att=att, a=att["a"], o=o, ln1=ln1, x1=x1, pre=pre, hdn=hdn, ln2=ln2,
                  drop1=drop1, drop2=drop2, H=H)
     return x2, cache
 
@@ -195,19 +226,7 @@ def encoder_layer_bwd(dx2, c, p):
     dy = dr1 * c["drop1"] if c["drop1"] is not None else dr1
     g["wo"] = c["o"].reshape(-1, d).T @ dy.reshape(-1, d)
     g["bo"] = dy.reshape(-1, d).sum(0)
-    do = (dy @ p["wo"].T).reshape(B, S, H, dh).transpose(0, 2, 1, 3)
-    a, qh, kh, vh = c["a"], c["qh"], c["kh"], c["vh"]
-    dv = a.transpose(0, 1, 3, 2) @ do
-    da = do @ vh.transpose(0, 1, 3, 2)
-    dz = a * (da - (da * a).sum(-1, keepdims=True))
-    inv = dt(1.0) / dt(np.sqrt(np.float32(dh)))
-    dq = (dz @ kh) * inv
-    dk = (dz.transpose(0, 1, 3, 2) @ qh) * inv
-
-    def merge(t):
-        return t.transpose(0, 2, 1, 3).reshape(B, S, d)
-
-    dq, dk, dv = merge(dq), merge(dk), merge(dv)
+    dq, dk, dv = mha_core_bwd(dy @ p["wo"].T, c["att"])
     x2d = x.reshape(-1, d)
     for nm, dd in (("q", dq), ("k", dk), ("v", dv)):
         g["w" + nm] = x2d.T @ dd.reshape(-1, d)

@@ -1,0 +1,325 @@
+"""Kernel-level parity: every libb4cp export against the CPU oracle on the same seeded inputs.
+Bit-exact for integer / index / gather work; stated tolerances for floating point."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import clickpath_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def dev(a, dtype=None):
+    t = torch.as_tensor(np.ascontiguousarray(a)).cuda()
+    return t.to(dtype) if dtype is not None else t
+
+
+def bf16_round(a):
+    return torch.as_tensor(np.asarray(a, dtype=np.float32)).to(torch.bfloat16).float().numpy()
+
+
+# ------------------------------------------------------------------------------------ GEMM
+@pytest.mark.parametrize("a_mn", [0, 1])
+@pytest.mark.parametrize("b_mn", [0, 1])
+@pytest.mark.parametrize("shape", [(128, 64, 64), (300, 200, 136), (77, 104, 72), (512, 1024, 512),
+                                   (1000, 100, 64), (130, 54293 % 1000 + 8, 128)])
+def test_gemm_all_majors(cuda_lib, a_mn, b_mn, shape):
+    from bert4clickpath_b200 import ops
+    M, N, K = shape
+    rng = np.random.default_rng(M + N + K)
+    A = bf16_round(rng.normal(size=(M, K)))
+    B = bf16_round(rng.normal(size=(N, K)))
+    ref = A.astype(np.float64) @ B.astype(np.float64).T
+    pad = lambda a: np.pad(a, ((0, 0), (0, (-a.shape[1]) % 8)))
+    A_st = dev(pad(A.T) if a_mn else pad(A), torch.bfloat16)
+    B_st = dev(pad(B.T) if b_mn else pad(B), torch.bfloat16)
+    out = torch.full((M, N), float("nan"), device="cuda")
+    ops.gemm(A_st, a_mn, B_st, b_mn, M, N, K, out_f32=out)
+    torch.cuda.synchronize()
+    # fp32 accumulation of exactly representable bf16 products: 1e-5 relative to the row scale
+    np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=0, atol=2e-5 * np.abs(ref).max())
+
+
+def test_gemm_epilogues_and_splitk(cuda_lib):
+    from bert4clickpath_b200 import ops
+    rng = np.random.default_rng(3)
+    M, N, K = 300, 200, 1024
+    A = bf16_round(rng.normal(size=(M, K)))
+    B = bf16_round(rng.normal(size=(K, N)))  # Keras (in, out) kernel = MN-major B
+    bias = rng.normal(size=N).astype(np.float32)
+    gate = bf16_round(rng.normal(size=(M, N)))
+    add = rng.normal(size=(M, N)).astype(np.float32)
+    ref = A.astype(np.float64) @ B.astype(np.float64)
+    Ad, Bd = dev(A, torch.bfloat16), dev(B, torch.bfloat16)
+    out = torch.empty((M, N), device="cuda")
+    outb = torch.zeros((M, ops.ld8(N)), device="cuda", dtype=torch.bfloat16)
+    ops.gemm(Ad, 0, Bd, 1, M, N, K, bias=dev(bias), relu=True, out_f32=out, out_bf16=outb)
+    want = np.maximum(ref + bias, 0)
+    np.testing.assert_allclose(out.cpu().numpy(), want, atol=3e-5 * np.abs(ref).max())
+    np.testing.assert_allclose(outb.float().cpu().numpy()[:, :N], want, rtol=1e-2, atol=1e-2)
+    ops.gemm(Ad, 0, Bd, 1, M, N, K, gate=dev(gate, torch.bfloat16), addend=dev(add), out_f32=out)
+    want = ref * (gate > 0) + add
+    np.testing.assert_allclose(out.cpu().numpy(), want, atol=3e-5 * np.abs(ref).max())
+    out2 = torch.empty((M, N), device="cuda")
+    ops.gemm_splitk(Ad, 0, Bd, 1, M, N, K, out2)
+    np.testing.assert_allclose(out2.cpu().numpy(), ref, atol=3e-5 * np.abs(ref).max())
+    out3 = torch.empty((M, N), device="cuda")
+    ops.gemm_splitk(Ad, 0, Bd, 1, M, N, K, out3)
+    assert torch.equal(out2, out3)  # split-K reduction order is fixed
+
+
+# ------------------------------------------------------------------------------- embedding
+@pytest.mark.parametrize("dims", [(64,), (20, 4), (112, 16), (6, 3)])
+def test_embed_fwd_bit_exact(cuda_lib, dims):
+    from bert4clickpath_b200 import ops
+    rng = np.random.default_rng(sum(dims))
+    B, S = 9, 23
+    rows = [500 + 11] + [50 + 11] * (len(dims) - 1)
+    tables = [rng.uniform(-0.05, 0.05, size=(r, d)).astype(np.float32) for r, d in zip(rows, dims)]
+    ids = [rng.integers(0, r, size=(B, S)).astype(np.int32) for r in rows]
+    ids[0][0, :3] = [0, rows[0] - 1, 1]  # pad row, OOV row, [MASK]
+    d = sum(dims)
+    pe = O.positional_encoding(10000, d)
+    want = O.embed_fwd(ids, tables, pe, np.float32)
+    out, _ = ops.embed_fwd([dev(i) for i in ids], [dev(t) for t in tables], dev(pe), B, S)
+    torch.cuda.synchronize()
+    got = out.cpu().numpy().reshape(B, S, d)
+    assert got.tobytes() == want.tobytes()  # bit-exact, including d=128 where sqrt(d) is inexact
+
+
+def test_embed_fwd_dropout_matches_exported_mask(cuda_lib):
+    from bert4clickpath_b200 import ops
+    rng = np.random.default_rng(0)
+    B, S, d = 7, 11, 64
+    table = rng.uniform(-0.05, 0.05, size=(111, d)).astype(np.float32)
+    ids = rng.integers(0, 111, size=(B, S)).astype(np.int32)
+    pe = O.positional_encoding(10000, d)
+    base = O.embed_fwd([ids], [table], pe, np.float32)
+    mask = ops.dropout_mask(B * S * d, 0.1, 1234, 7).cpu().numpy().reshape(B, S, d)
+    keep_frac = (mask > 0).mean()
+    assert 0.85 < keep_frac < 0.95 and np.allclose(mask[mask > 0], 1 / 0.9)
+    out, _ = ops.embed_fwd([dev(ids)], [dev(table)], dev(pe), B, S, dropout_rate=0.1, seed=1234,
+                           site=7)
+    np.testing.assert_allclose(out.cpu().numpy().reshape(B, S, d), base * mask, rtol=1e-6)
+
+
+@pytest.mark.parametrize("B,S,rows", [(64, 52, 311), (512, 52, 54304), (3, 5, 70000)])
+def test_embed_bwd_sorted_scatter_add(cuda_lib, B, S, rows):
+    from bert4clickpath_b200 import ops
+    rng = np.random.default_rng(B)
+    dims = (48, 16)
+    d = sum(dims)
+    zipf = np.minimum(rng.zipf(1.3, size=(B, S)) + 9, rows - 1).astype(np.int32)
+    zipf[:, 0] = 3
+    zipf[:, 1] = 4
+    zipf[rng.random((B, S)) < 0.15] = 1  # many duplicates of [MASK], CLS, SEP
+    ids2 = rng.integers(0, 61, size=(B, S)).astype(np.int32)
+    dout = rng.normal(size=(B, S, d)).astype(np.float32)
+    want = O.embed_bwd(dout.astype(np.float64), [zipf, ids2], dims, [rows, 61], np.float64)
+    dd = dev(dout.reshape(B * S, d))
+    outs = []
+    for rep in range(2):
+        g0 = torch.empty((rows, dims[0]), device="cuda")
+        g1 = torch.empty((61, dims[1]), device="cuda")
+        uniq = torch.empty(B * S, dtype=torch.int32, device="cuda")
+        nuniq = torch.zeros(1, dtype=torch.int32, device="cuda")
+        ops.embed_bwd(dd, d, 0, dims[0], dev(zipf.reshape(-1)), rows, g0, uniq_ids=uniq,
+                      n_unique=nuniq)
+        ops.embed_bwd(dd, d, dims[0], dims[1], dev(ids2.reshape(-1)), 61, g1)
+        torch.cuda.synchronize()
+        outs.append((g0.clone(), g1.clone()))
+        nu = int(nuniq.item())
+        assert uniq[:nu].cpu().numpy().tolist() == np.unique(zipf).tolist()  # sorted, deduplicated
+    for got, w in zip(outs[0], want):
+        scale = np.abs(w).max()
+        np.testing.assert_allclose(got.cpu().numpy(), w, rtol=0, atol=2e-6 * scale)
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])  # reproducible
+
+
+# ------------------------------------------------------------------------------- attention
+@pytest.mark.parametrize("B,S,H,dh", [(4, 53, 2, 32), (3, 5, 1, 8), (2, 103, 4, 32), (2, 203, 4, 64),
+                                      (2, 114, 2, 64)])
+def test_attention_fwd_bwd(cuda_lib, B, S, H, dh):
+    from bert4clickpath_b200 import ops
+    rng = np.random.default_rng(S)
+    d = H * dh
+    q, k, v, do = (bf16_round(rng.normal(size=(B, S, d))) for _ in range(4))
+    ids = rng.integers(10, 50, size=(B, S)).astype(np.int32)
+    ids[0, S // 2: S - 1] = 0  # interior pad run, trailing token kept
+    ids[-1, 2:4] = 0
+    pad = ids == 0
+    o, att = O.mha_core_fwd(q.astype(np.float64), k.astype(np.float64), v.astype(np.float64), pad, H)
+    dq, dk, dv = O.mha_core_bwd(do.astype(np.float64), att)
+    qkv = dev(np.concatenate([q, k, v], -1).reshape(B * S, 3 * d), torch.bfloat16)
+    out = torch.empty((B * S, d), dtype=torch.bfloat16, device="cuda")
+    lse = torch.empty((B, H, S), device="cuda")
+    ops.attention_fwd(qkv, dev(ids), B, S, H, dh, out, lse)
+    dqkv = torch.empty((B * S, 3 * d), dtype=torch.bfloat16, device="cuda")
+    ops.attention_bwd(qkv, dev(do.reshape(B * S, d), torch.bfloat16), lse, dev(ids), B, S, H, dh, dqkv)
+    torch.cuda.synchronize()
+    # bf16 outputs: 2^-8 relative rounding on top of fp32 math
+    np.testing.assert_allclose(out.float().cpu().numpy().reshape(B, S, d), o, rtol=1e-2, atol=1e-2)
+    np.testing.assert_allclose(lse.cpu().numpy(), att["lse"], rtol=1e-5, atol=1e-5)
+    got = dqkv.float().cpu().numpy().reshape(B, S, 3 * d)
+    for name, g, w in (("dq", got[..., :d], dq), ("dk", got[..., d:2 * d], dk), ("dv", got[..., 2 * d:], dv)):
+        np.testing.assert_allclose(g, w, rtol=2e-2, atol=2e-2 * np.abs(w).max(), err_msg=name)
+    # padded keys receive exactly zero gradient
+    assert not got[..., d:][np.broadcast_to(pad[..., None], got[..., d:].shape)].any()
+
+
+# ------------------------------------------------------------------------------- LayerNorm
+@pytest.mark.parametrize("d,rate", [(64, 0.0), (128, 0.1), (256, 0.1), (24, 0.0)])
+def test_residual_ln_fwd_bwd(cuda_lib, d, rate):
+    from bert4clickpath_b200 import ops
+    rng = np.random.default_rng(d)
+    T = 777
+    x, r, dy = (rng.normal(size=(T, d)).astype(np.float32) for _ in range(3))
+    gamma = (1 + 0.1 * rng.normal(size=d)).astype(np.float32)
+    beta = (0.1 * rng.normal(size=d)).astype(np.float32)
+    mask = ops.dropout_mask(T * d, rate, 99, 3).cpu().numpy().reshape(T, d).astype(np.float64)
+    rr = x.astype(np.float64) + r.astype(np.float64) * mask
+    y, cache = O.layer_norm_fwd(rr, gamma.astype(np.float64), beta.astype(np.float64))
+    dr, dg, db = O.layer_norm_bwd(dy.astype(np.float64), cache, gamma.astype(np.float64))
+    yf = torch.empty((T, d), device="cuda")
+    yb = torch.empty((T, ops.ld8(d)), dtype=torch.bfloat16, device="cuda")
+    ops.residual_ln_fwd(dev(x), dev(r), dev(gamma), dev(beta), yf, yb, dropout_rate=rate, seed=99, site=3)
+    dx = torch.empty((T, d), device="cuda")
+    drb = torch.empty((T, ops.ld8(d)), dtype=torch.bfloat16, device="cuda")
+    dgd, dbd, dbias = (torch.empty(d, device="cuda") for _ in range(3))
+    ops.residual_ln_bwd(dev(dy), dev(x), dev(r), dev(gamma), dx, drb, dgd, dbd, dbias,
+                        dropout_rate=rate, seed=99, site=3)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(yf.cpu().numpy(), y, rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(dx.cpu().numpy(), dr, rtol=1e-3, atol=1e-5)
+    np.testing.assert_allclose(drb.float().cpu().numpy()[:, :d], dr * mask, rtol=1e-2, atol=1e-2)
+    np.testing.assert_allclose(dgd.cpu().numpy(), dg, rtol=1e-4, atol=1e-3)
+    np.testing.assert_allclose(dbd.cpu().numpy(), db, rtol=1e-4, atol=1e-3)
+    np.testing.assert_allclose(dbias.cpu().numpy(), (dr * mask).sum(0), rtol=1e-3, atol=2e-3)
+
+
+def test_colsum_and_cast(cuda_lib):
+    from bert4clickpath_b200 import ops
+    rng = np.random.default_rng(5)
+    T, n = 3001, 100
+    a = rng.normal(size=(T, n)).astype(np.float32)
+    ab = ops.cast_bf16(dev(a))
+    assert ab.shape == (T, 104) and not ab[:, n:].float().abs().sum().item()
+    np.testing.assert_array_equal(ab[:, :n].float().cpu().numpy(), bf16_round(a))
+    out = torch.empty(n, device="cuda")
+    ops.colsum_bf16(ab, T, n, out)
+    np.testing.assert_allclose(out.cpu().numpy(), bf16_round(a).astype(np.float64).sum(0), rtol=1e-4, atol=1e-3)
+
+
+# ------------------------------------------------------------------------------- selection
+def test_select_gather_scatter(cuda_lib):
+    from bert4clickpath_b200 import ops
+    rng = np.random.default_rng(1)
+    B, S, d = 37, 52, 64
+    ids = rng.integers(10, 90, size=(B, S)).astype(np.int32)
+    ids[rng.random((B, S)) < 0.13] = 1
+    ids[5] = 7  # a sequence without any [MASK]
+    x = rng.normal(size=(B * S, d)).astype(np.float32)
+    want_idx = np.nonzero(ids.reshape(-1) == 1)[0]
+    cap = len(want_idx) + 9
+    row_index, count = ops.select_masked(dev(ids.reshape(-1)), 1, cap)
+    torch.cuda.synchronize()
+    assert int(count.item()) == len(want_idx)
+    got = row_index.cpu().numpy()
+    assert got[:len(want_idx)].tolist() == want_idx.tolist() and (got[len(want_idx):] == -1).all()
+    sel = torch.empty((cap, d), device="cuda")
+    selb = torch.empty((cap, d), dtype=torch.bfloat16, device="cuda")
+    ops.gather_rows(dev(x), row_index, sel, selb)
+    np.testing.assert_array_equal(sel.cpu().numpy()[:len(want_idx)], x[want_idx])
+    assert not sel[len(want_idx):].abs().sum().item()
+    back = torch.zeros((B * S, d), device="cuda")
+    ops.scatter_rows(sel, row_index, back)
+    want = np.zeros_like(x)
+    want[want_idx] = x[want_idx]
+    np.testing.assert_array_equal(back.cpu().numpy(), want)
+    # oracle agreement on the padded (B, Mmax, d) layout
+    o_sel, o_index = O.select_masked(ids, x.reshape(B, S, d))
+    assert [b * S + s for b, s in o_index] == want_idx.tolist()
+
+
+# -------------------------------------------------------------------- loss, top-k, metrics
+def test_ce_rows_matches_oracle(cuda_lib):
+    from bert4clickpath_b200 import ops
+    rng = np.random.default_rng(2)
+    M, V = 41, 1237
+    z = (3 * rng.normal(size=(M, V))).astype(np.float32)
+    labels = rng.integers(0, V, size=M).astype(np.int32)
+    labels[[3, 17]] = -1
+    loss, dz, n = O.cloze_ce_from_logits(z.astype(np.float64), labels)
+    zd, ld = dev(z), dev(labels)
+    lse, tgt, stats = torch.empty(M, device="cuda"), torch.empty(M, device="cuda"), torch.empty(2, device="cuda")
+    ops.ce_rows_stats(zd, V, ld, lse, tgt)
+    ops.ce_loss_reduce(lse, tgt, ld, stats)
+    dzb = torch.empty((M, ops.ld8(V)), dtype=torch.bfloat16, device="cuda")
+    probs = torch.empty((M, V), device="cuda")
+    ops.ce_rows_grad(zd, V, ld, lse, stats, dzb, probs)
+    torch.cuda.synchronize()
+    s = stats.cpu().numpy()
+    assert s[1] == n and abs(s[0] / s[1] - loss) < 1e-5 * abs(loss)
+    np.testing.assert_allclose(dzb.float().cpu().numpy()[:, :V], dz, rtol=1e-2, atol=1e-6)
+    e = np.exp(z.astype(np.float64) - z.max(-1, keepdims=True))
+    np.testing.assert_allclose(probs.cpu().numpy(), e / e.sum(-1, keepdims=True), rtol=1e-4, atol=1e-9)
+    # empty / all-pad batch -> loss_sum 0, n 0, zero gradient (losses.py:89-91 guard)
+    allpad = torch.full((M,), -1, dtype=torch.int32, device="cuda")
+    ops.ce_loss_reduce(lse, tgt, allpad, stats)
+    ops.ce_rows_grad(zd, V, allpad, lse, stats, dzb, None)
+    assert stats.cpu().numpy().tolist() == [0.0, 0.0] and not dzb.float().abs().sum().item()
+
+
+@pytest.mark.parametrize("V,k", [(1237, 10), (54293, 100), (1000000, 100), (50, 100), (3, 3)])
+def test_topk_exact_with_ties(cuda_lib, V, k):
+    from bert4clickpath_b200 import ops
+    rng = np.random.default_rng(V)
+    rows = 5
+    s = rng.normal(size=(rows, V)).astype(np.float32)
+    s[1] = np.round(s[1] * 8) / 8          # 8-bit-ish quantised: thousands of exact ties
+    s[2] = 0.25                            # all ties -> ids 0..k-1
+    s[3, ::2] = -0.0                       # signed zeros compare equal
+    s[3, 1::2] = 0.0
+    ids, sc = ops.topk_rows(dev(s), V, k, out_scores=torch.empty((rows, k), device="cuda"))
+    torch.cuda.synchronize()
+    want = O.top_k_ids(s, k)
+    kk = min(k, V)
+    assert ids.cpu().numpy()[:, :kk].tolist() == want[:, :kk].tolist()  # bit-exact ids
+    assert (ids.cpu().numpy()[:, kk:] == -1).all()
+    np.testing.assert_array_equal(sc.cpu().numpy()[:, :kk], np.take_along_axis(s, want[:, :kk], 1))
+
+
+def test_rank_metrics_kat(cuda_lib):
+    from bert4clickpath_b200 import ops
+    # examples/BERT4Rec/source/utils.py:262-272 known answer 0.81546488
+    probs = np.array([[0.9, 0.1, 0.01], [0.5, 0.3, 0.01]], dtype=np.float32)
+    labels = np.array([1, 0], dtype=np.int32)
+    ids, _ = ops.topk_rows(dev(probs), 3, 3)
+    counters = torch.zeros(3, device="cuda")
+    ops.rank_metrics(ids, 3, dev(labels), counters)
+    ops.rank_metrics(ids, 3, dev(np.array([-1, 2], dtype=np.int32)), counters)  # accumulates; pad skipped
+    c = counters.cpu().numpy()
+    h, g, n = O.rank_metrics_from_topk(O.top_k_ids(probs, 3), labels, 3)
+    assert abs(g / n - 0.81546488) < 1e-6
+    assert c[2] == 3 and c[0] == 3 and abs(c[1] - (g + 0.5)) < 1e-6
+
+
+def test_adam_matches_oracle_10_steps(cuda_lib):
+    from bert4clickpath_b200 import ops
+    rng = np.random.default_rng(4)
+    n, cols = 1000, 100
+    th = rng.normal(size=n).astype(np.float32)
+    m, v = np.zeros(n), np.zeros(n)
+    th64 = th.astype(np.float64)
+    thd, md, vd = dev(th), torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    shadow = torch.zeros((n // cols, ops.ld8(cols)), dtype=torch.bfloat16, device="cuda")
+    step = torch.ones(1, dtype=torch.int32, device="cuda")
+    for t in range(1, 11):
+        g = rng.normal(size=n).astype(np.float32)
+        th64, m, v = O.adam_step(th64, g.astype(np.float64), m, v, t)
+        ops.adam_step(thd, dev(g), md, vd, lr=1e-3, step_dev=step, shadow=shadow, cols=cols)
+        ops.step_increment(step)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(thd.cpu().numpy(), th64, rtol=1e-5, atol=1e-6)
+    np.testing.assert_array_equal(shadow[:, :cols].float().cpu().numpy().reshape(-1),
+                                  bf16_round(thd.cpu().numpy()))
