@@ -1,0 +1,346 @@
+"""ClickstreamTransformer with the reference's construction surface
+(clickstream_transformer/clickstream_transformer.py:8-375) on the libb4cp hot path.
+
+Host side (this file): token chaining `[CLS] [SEP] seq_1 [SEP] seq_2 [SEP] ...`, vocabulary
+lookup (10 reserved tokens + vocab + 1 OOV bucket), segment bookkeeping.  Device side: everything
+from int ids to the head output / loss / gradients / metrics.
+"""
+import numpy as np
+import torch
+
+from . import ops
+from .constants import (CLASSIFICATION_TOKEN, CLS, INPUT_MASKING_TOKEN, LABEL_PAD, RESERVED_TOKENS,
+                        SEP, SEPARATOR_TOKEN)
+from .engine import BufferPool, ParamStore
+from .head import ClozeOutput, SoftMaxHead
+from .ops import BF16, F32, I32, ld8
+from .transformer import Transformer
+
+
+def load_vocabulary(vocab_file):
+    """One token per line, stripped (clickstream_transformer/training_utils.py:5-12)."""
+    with open(vocab_file, 'r') as f:
+        return [line.strip() for line in f if line.strip() != '']
+
+
+class StaticVocabularyTable:
+    """tf.lookup.StaticVocabularyTable(KeyValueTensorInitializer(keys, range), num_oov_buckets=1)
+    as used at clickstream_transformer.py:247-258: known keys -> their index, anything else ->
+    len(keys); size() counts the OOV bucket."""
+
+    def __init__(self, keys):
+        self.keys = list(keys)
+        self.table = {}
+        for i, k in enumerate(self.keys):
+            self.table.setdefault(k, i)
+        self.oov = len(self.keys)
+
+    def size(self):
+        return len(self.keys) + 1
+
+    def lookup(self, tokens):
+        arr = np.asarray(tokens)
+        if arr.dtype.kind in "iu":
+            return arr.astype(np.int32)  # already ids
+        if arr.dtype.kind == "S":
+            arr = np.char.decode(arr, "utf-8")
+        flat = np.fromiter((self.table.get(t, self.oov) for t in arr.reshape(-1).tolist()),
+                           dtype=np.int32, count=arr.size)
+        return flat.reshape(arr.shape)
+
+
+class TransformerInputPrep:
+    """Chains raw sequences into `[CLS] [SEP] seq_1 [SEP] seq_2 [SEP] ...` and reports segment
+    starts / ends from the SEP positions of sample 0 (clickstream_transformer.py:8-103).
+    Works on string arrays (reference behaviour) or on integer id arrays."""
+
+    def __init__(self, seq_chain_mapping):
+        self.seq_chain_mapping = seq_chain_mapping
+
+    @staticmethod
+    def _chain_sequences(sequences):
+        first = np.asarray(sequences[0])
+        is_str = first.dtype.kind in "USO"
+        cls_v = CLASSIFICATION_TOKEN if is_str else CLS
+        sep_v = SEPARATOR_TOKEN if is_str else SEP
+        shape = (first.shape[0], 1) + tuple(first.shape[2:])
+        dtype = object if is_str else first.dtype
+        cls_token = np.full(shape, cls_v, dtype=dtype)
+        sep_token = np.full(shape, sep_v, dtype=dtype)
+        seqs = [cls_token] + [np.asarray(s).astype(dtype) for s in sequences]
+        concat_list = [seqs[i // 2] if i % 2 == 0 else sep_token for i in range(2 * len(seqs))]
+        return np.concatenate(concat_list, axis=1)
+
+    def __call__(self, features, keep_features=False):
+        features = dict(features)
+        for new_feature, seq_pair in self.seq_chain_mapping.items():
+            features[new_feature] = self._chain_sequences([features[name] for name in seq_pair])
+        some = features[list(self.seq_chain_mapping.keys())[0]]
+        sample = some[0, :] if some.shape[0] > 0 else np.asarray([])
+        sep_v = SEPARATOR_TOKEN if np.asarray(some).dtype.kind in "USO" else SEP
+        segment_ends = np.nonzero(sample == sep_v)[0]
+        segment_starts = np.concatenate([[0], segment_ends[:-1] + 1]).astype(np.int64)
+        if not keep_features:
+            drop = set()
+            for seq_pair in self.seq_chain_mapping.values():
+                drop |= set(seq_pair)
+            drop -= set(self.seq_chain_mapping.keys())
+            features = {k: v for k, v in features.items() if k not in drop}
+        return features, segment_starts, segment_ends
+
+
+class Adam:
+    """tf.keras.optimizers.Adam(learning_rate, beta_1, beta_2, epsilon) hyper-parameters
+    (examples/BERT4Rec/source/main.py:87); the update itself is b4cp_adam_step."""
+
+    def __init__(self, learning_rate=1e-3, beta_1=0.9, beta_2=0.999, epsilon=1e-9):
+        self.learning_rate, self.beta_1, self.beta_2, self.epsilon = (learning_rate, beta_1, beta_2,
+                                                                      epsilon)
+
+
+class ClickstreamTransformer:
+    """ClickstreamTransformer(sequential_input_config, feature_vocabs, embedding_dims, head_unit,
+    segment_to_head=None, value_to_head=None, num_encoder_layers=1, num_attention_heads=1,
+    dropout_rate=0.1) — clickstream_transformer.py:160-227.
+
+    feature_vocabs values may be a vocabulary file path (reference), a list of tokens, or an int
+    vocabulary size (inputs are then integer ids 10..V+9 already).  `encoder_ff_dim` defaults to
+    the reference's hard-coded 100 (clickstream_transformer.py:225).
+    """
+
+    def __init__(self, sequential_input_config, feature_vocabs, embedding_dims, head_unit,
+                 segment_to_head=None, value_to_head=None, num_encoder_layers=1,
+                 num_attention_heads=1, dropout_rate=0.1, *, encoder_ff_dim=100, seed=0, **kwargs):
+        self.sequential_input_config = sequential_input_config
+        self.feature_vocabs = feature_vocabs
+        self.embedding_dims = embedding_dims
+        self.head = head_unit
+        self.num_encoder_layers = num_encoder_layers
+        self.num_attention_heads = num_attention_heads
+        self.dropout_rate = dropout_rate
+        assert (segment_to_head is not None or value_to_head is not None) and \
+               (segment_to_head is None or value_to_head is None), \
+            "Exactly one of segment_to_head and value_to_head must be provided."
+        self.segment_to_head = segment_to_head
+        self.value_to_head = value_to_head
+        self.transformer_input_prep = TransformerInputPrep(self.sequential_input_config)
+        self.vocab_lookup_tables = self._create_lookup_tables(self.feature_vocabs, RESERVED_TOKENS)
+        self.embedding_sizes = {f: self.vocab_lookup_tables[f].size() for f in self.feature_vocabs}
+        seq_keys = list(self.sequential_input_config.keys())
+        self.store = ParamStore()
+        self.transformer = Transformer(
+            embedding_sizes={k: self.embedding_sizes[k] for k in seq_keys},
+            embedding_dims={k: self.embedding_dims[k] for k in seq_keys},
+            num_layers=num_encoder_layers, num_attention_heads=num_attention_heads,
+            encoder_ff_dim=encoder_ff_dim, dropout_rate=dropout_rate, store=self.store, seed=seed)
+        self.d_model = self.transformer.d_model
+        self.head.build(self.store, self.d_model, np.random.default_rng(seed + 1))
+        self.store.finalize()
+        if self.value_to_head is not None:
+            v = self.value_to_head
+            self._value_id = int(v) if isinstance(v, (int, np.integer)) else \
+                int(self.vocab_lookup_tables[seq_keys[0]].lookup(np.asarray([v]))[0])
+        self.pool = BufferPool()
+        self.optimizer = self.loss = None
+        self.metrics = []
+        self.process_group = None
+        self._step_seed = 0
+
+    # ------------------------------------------------------------------ construction helpers
+    @staticmethod
+    def _create_lookup_tables(vocabularies, tokens_to_prepend=None):
+        tables = {}
+        for name, vocab in vocabularies.items():
+            if isinstance(vocab, (int, np.integer)):
+                keys = [f"item_{j}" for j in range(int(vocab))]
+            elif isinstance(vocab, str):
+                keys = load_vocabulary(vocab)
+            else:
+                keys = list(vocab)
+            if tokens_to_prepend is not None:
+                keys = list(tokens_to_prepend) + keys
+            tables[name] = StaticVocabularyTable(keys)
+        return tables
+
+    def get_config(self):
+        return {
+            'sequential_input_config': self.sequential_input_config,
+            'feature_vocabs': self.feature_vocabs,
+            'embedding_dims': self.embedding_dims,
+            'head_unit': self.head,
+            'segment_to_head': self.segment_to_head,
+            'value_to_head': self.value_to_head,
+            'num_encoder_layers': self.num_encoder_layers,
+            'num_attention_heads': self.num_attention_heads,
+            'dropout_rate': self.dropout_rate,
+        }
+
+    def get_serving_signature(self):
+        """{raw sequence feature: ([None, None], 'string')} (clickstream_transformer.py:354-375)."""
+        feats = []
+        for chain in self.sequential_input_config.values():
+            feats.extend(chain)
+        return {f: ([None, None], 'string') for f in feats}
+
+    # ------------------------------------------------------------------ input preparation
+    def prepare_inputs(self, inputs):
+        """dict of raw (B, L_i) string / id arrays -> chained device ids per sequential feature."""
+        host = {}
+        for k, v in inputs.items():
+            host[k] = v.cpu().numpy() if torch.is_tensor(v) else np.asarray(v)
+        raw, starts, ends = self.transformer_input_prep(features=host)
+        ids_list, shape = [], None
+        for name in self.sequential_input_config.keys():
+            ids = self.vocab_lookup_tables[name].lookup(raw[name])
+            if shape is None:
+                self._host_ids_first = ids
+            shape = ids.shape
+            ids_list.append(torch.from_numpy(np.ascontiguousarray(ids, dtype=np.int32)).cuda().view(-1))
+        B, S = shape
+        return ids_list, B, S, starts, ends
+
+    # ------------------------------------------------------------------ forward
+    def _encode(self, ids_list, B, S, training, seed):
+        x, _ = self.transformer.engine.forward(ids_list, B, S, training, seed)
+        return x
+
+    def forward_ids(self, ids_list, B, S, training=False, seed=0, n_masked=None,
+                    segment_bounds=None):
+        """Hot-path entry on already-chained device ids (int32 [B*S] per feature)."""
+        x = self._encode(ids_list, B, S, training, seed)
+        state = dict(x=x, ids_first=ids_list[0], B=B, S=S)
+        if self.segment_to_head is not None:
+            starts, ends = segment_bounds
+            s0, s1 = int(starts[self.segment_to_head]), int(ends[self.segment_to_head])
+            head_input = x.view(B, S, self.d_model)[:, s0:s1, :]
+            return self.head(head_input)
+        cap = int(n_masked) if n_masked is not None else B * S
+        row_index, count = ops.select_masked(ids_list[0], self._value_id, cap)
+        hsel = self.pool.get("hsel", (cap, ld8(self.d_model)), BF16)
+        ops.gather_rows(x, row_index, None, hsel)
+        state["value_id"] = self._value_id
+        if isinstance(self.head, SoftMaxHead):
+            ab = self.head.hidden(hsel, cap)
+            return ClozeOutput(self.head, ab, cap, row_index, count, state)
+        # other heads consume the reference's padded (B, max_n_masked, d) tensor
+        idx = row_index.cpu().numpy()
+        n = int(count.item())
+        b_of = idx[:n] // S
+        counts = np.bincount(b_of, minlength=B)
+        mmax = int(counts.max()) if n else 0
+        padded = torch.zeros((B, mmax, self.d_model), dtype=F32, device="cuda")
+        if n:
+            j = np.arange(n) - np.repeat(np.cumsum(counts) - counts, counts)
+            padded[torch.from_numpy(b_of).cuda(), torch.from_numpy(j).cuda()] = x[row_index[:n].long()]
+        return self.head(padded)
+
+    def call(self, inputs, training=None, mask=None):
+        """inputs: dict of raw features -> head output (a lazy ClozeOutput for SoftMaxHead in
+        value_to_head mode), or {'instance_id', 'logits'} when 'instance_id' is given."""
+        feats = {k: v for k, v in inputs.items() if k != 'instance_id'}
+        ids_list, B, S, starts, ends = self.prepare_inputs(feats)
+        if self.segment_to_head is None and self.value_to_head is None:
+            raise ValueError("One of value_to_head and segment_to_head must be provided.")
+        n_masked = None
+        if self.value_to_head is not None:
+            n_masked = int((self._host_ids_first == self._value_id).sum())
+        out = self.forward_ids(ids_list, B, S, bool(training), self._next_seed() if training else 0,
+                               n_masked=n_masked, segment_bounds=(starts, ends))
+        if 'instance_id' in inputs:
+            return {'instance_id': inputs['instance_id'], 'logits': out}
+        return out
+
+    __call__ = call
+
+    def _next_seed(self):
+        self._step_seed += 1
+        return self._step_seed
+
+    # ------------------------------------------------------------------ training (Keras-like)
+    def compile(self, optimizer=None, loss=None, metrics=None):
+        self.optimizer = optimizer if optimizer is not None else Adam()
+        self.loss = loss
+        self.metrics = list(metrics or [])
+
+    def set_process_group(self, group):
+        """Data-parallel training: gradients / loss statistics are all-reduced over `group`."""
+        self.process_group = group
+
+    def _allreduce(self, t):
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.process_group) > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.process_group)
+
+    def cloze_forward_backward(self, ids_list, labels_f32, B, S, n_masked=None, training=True,
+                               seed=0):
+        """One Cloze forward + backward on device-resident inputs.  labels_f32: (B, Mmax) float32
+        padded with -1 (the reference contract).  Gradients land in store.flat_g; returns the
+        device tensor loss_stats = (sum of per-position losses, valid positions) — already
+        all-reduced when a process group is set, so loss = stats[0] / stats[1] is the GLOBAL
+        masked mean."""
+        assert isinstance(self.head, SoftMaxHead) and self.value_to_head is not None
+        out = self.forward_ids(ids_list, B, S, training, seed, n_masked=n_masked)
+        cap = out.M
+        labels, _ = ops.compact_labels(labels_f32, cap)
+        stats = self.pool.get("loss_stats", (2,))
+        vocab, mlp = self.head.vocab, self.head.mlp
+        vocab.loss_forward(out.ab, cap, labels, stats)
+        self._allreduce(stats)
+        d = self.d_model
+        dsel = self.pool.get("dsel", (cap, d))
+        if mlp.dims:
+            dzb = self.pool.get("dz_head", (cap, ld8(mlp.out_dim)), BF16)
+            vocab.loss_backward(stats, out.ab, out_bf16=dzb)
+            mlp.backward(dzb, dsel)
+        else:
+            vocab.loss_backward(stats, None, out_f32=dsel)
+        dx = self.pool.get("dx_top", (B * S, d), zero=True)
+        ops.scatter_rows(dsel, out.row_index, dx)
+        self.transformer.engine.backward(dx)
+        self._allreduce(self.store.flat_g)
+        self._last_output = out
+        self._last_labels = labels
+        return stats
+
+    def train_step(self, data, n_masked=None):
+        """Keras Model.train_step: data = (inputs dict, labels (B, max_n_masked) float32).
+        Returns {'loss': float} (+ metric results)."""
+        inputs, y = data
+        ids_list, B, S, _, _ = self.prepare_inputs(inputs)
+        y = torch.as_tensor(np.ascontiguousarray(y, dtype=np.float32)) if not torch.is_tensor(y) else y
+        n_host = int((y != LABEL_PAD).sum().item())
+        y = y.to(device="cuda", dtype=F32).contiguous()
+        stats = self.cloze_forward_backward(ids_list, y, B, S, n_masked=n_host,
+                                            seed=self._next_seed())
+        opt = self.optimizer or Adam()
+        self.store.adam(opt.learning_rate, opt.beta_1, opt.beta_2, opt.epsilon)
+        s = stats.cpu().numpy()
+        logs = {'loss': float(s[0] / s[1]) if s[1] > 0 else 0.0}
+        for m in self.metrics:
+            m.update_state(y, self._last_output)
+            logs[m.name] = float(m.result())
+        return logs
+
+    def test_step(self, data):
+        inputs, y = data
+        out = self.call(inputs, training=False)
+        logs = {}
+        if self.loss is not None:
+            logs['loss'] = float(self.loss(y, out))
+        for m in self.metrics:
+            m.update_state(y, out)
+            logs[m.name] = float(m.result())
+        return logs
+
+    def fit(self, dataset, steps_per_epoch, epochs=1, verbose=0):
+        """Minimal stand-in for Keras Model.fit over an iterator of (inputs, labels)."""
+        history = []
+        it = iter(dataset)
+        for _ in range(epochs):
+            logs = {}
+            for _ in range(steps_per_epoch):
+                logs = self.train_step(next(it))
+            history.append(logs)
+            if verbose:
+                print(logs)
+        return history

@@ -176,6 +176,55 @@ adam_kernel(float* __restrict__ theta, const float* __restrict__ grad, float* __
 
 __global__ void step_increment_kernel(int* step) { *step += 1; }
 
+__global__ void __launch_bounds__(256)
+sigmoid_kernel(const float* __restrict__ z, float* __restrict__ out, long n) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n;
+       i += (long)gridDim.x * blockDim.x)
+    out[i] = 1.f / (1.f + expf(-z[i]));
+}
+
+// z = log(clip(p, lo, hi)) : the first half of K.sparse_categorical_crossentropy(from_logits=False)
+__global__ void __launch_bounds__(256)
+clip_log_kernel(const float* __restrict__ p, float* __restrict__ out, long n, float lo, float hi) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n;
+       i += (long)gridDim.x * blockDim.x)
+    out[i] = logf(fminf(fmaxf(p[i], lo), hi));
+}
+
+// MaskedLoss with K.binary_crossentropy (losses.py:31-98): stats = (sum of weighted masked
+// item losses, number of unmasked items)
+__global__ void __launch_bounds__(1024)
+masked_bce_kernel(const float* __restrict__ y_true, const float* __restrict__ p, long n,
+                  float label_pad, float pos_weight, int use_pos_weight, float* __restrict__ stats) {
+  __shared__ double s_l[1024];
+  __shared__ double s_n[1024];
+  double a = 0.0, c = 0.0;
+  const float eps = 1e-7f;
+  for (long i = threadIdx.x; i < n; i += blockDim.x) {
+    const float yt = y_true[i];
+    if (yt == label_pad) continue;
+    const float pc = fminf(fmaxf(p[i], eps), 1.f - eps);
+    float l = -(yt * logf(pc + eps) + (1.f - yt) * logf(1.f - pc + eps));
+    if (use_pos_weight && yt == 1.f) l *= pos_weight;
+    a += (double)l;
+    c += 1.0;
+  }
+  s_l[threadIdx.x] = a;
+  s_n[threadIdx.x] = c;
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) {
+      s_l[threadIdx.x] += s_l[threadIdx.x + o];
+      s_n[threadIdx.x] += s_n[threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    stats[0] = (float)s_l[0];
+    stats[1] = (float)s_n[0];
+  }
+}
+
 }  // namespace b4cp
 
 using namespace b4cp;
@@ -230,6 +279,30 @@ extern "C" int b4cp_adam_step(float* theta, const float* grad, float* m, float* 
 
 extern "C" int b4cp_step_increment(int* step_dev, void* stream) {
   step_increment_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev);
+  B4CP_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int b4cp_sigmoid(const float* z, float* out, long n, void* stream) {
+  if (n == 0) return 0;
+  const int blocks = (int)std::min<long>(ceil_div(n, 256), 148L * 16);
+  sigmoid_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(z, out, n);
+  B4CP_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int b4cp_clip_log(const float* p, float* out, long n, float lo, float hi, void* stream) {
+  if (n == 0) return 0;
+  const int blocks = (int)std::min<long>(ceil_div(n, 256), 148L * 16);
+  clip_log_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(p, out, n, lo, hi);
+  B4CP_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int b4cp_masked_bce(const float* y_true, const float* probs, long n, float label_pad,
+                               float pos_weight, int use_pos_weight, float* stats, void* stream) {
+  masked_bce_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(y_true, probs, n, label_pad, pos_weight,
+                                                          use_pos_weight, stats);
   B4CP_LAUNCH_CHECK();
   return 0;
 }

@@ -1,0 +1,402 @@
+"""Explicit forward / backward / optimizer schedule of the clickstream transformer on libb4cp.
+
+This is the runtime under the reference-named classes (transformer.py, head.py,
+clickstream_transformer.py): parameters live in flat fp32 buffers (one all-reduce, one Adam
+sweep), every activation buffer is allocated once per shape and reused, and each step is a fixed
+sequence of kernel launches on one stream (CUDA-graph capturable: no host sync, no allocation).
+
+Numerics: fp32 master weights and residual stream; Dense layers run on tcgen05 tensor cores with
+bf16 operands and fp32 accumulation (bf16 shadows of the weights are refreshed by the Adam
+kernel); attention / LayerNorm / softmax math is fp32.
+"""
+import math
+
+import numpy as np
+import torch
+
+from . import ops
+from .ops import BF16, F32, I32, ld8
+
+SITE_INPUT = 1  # dropout site ids (site = 16*layer + k for encoder layers)
+
+
+def site(layer, k):
+    return 16 * (layer + 1) + k
+
+
+class Param:
+    __slots__ = ("name", "shape", "w", "g", "m", "v", "wb", "offset", "numel")
+
+    def __init__(self, name, shape):
+        self.name, self.shape = name, tuple(shape)
+        self.numel = int(np.prod(shape))
+        self.w = self.g = self.m = self.v = self.wb = None
+        self.offset = 0
+
+
+class ParamStore:
+    """Flat fp32 parameter / gradient / Adam-moment buffers with named views."""
+
+    def __init__(self):
+        self.params = {}
+        self._init = {}
+        self._shadow = set()
+        self.flat_w = self.flat_g = self.flat_m = self.flat_v = None
+        self.step_dev = None
+
+    def add(self, name, init, shadow=False):
+        init = np.ascontiguousarray(init, dtype=np.float32)
+        assert name not in self.params, name
+        self.params[name] = Param(name, init.shape)
+        self._init[name] = init
+        if shadow:
+            self._shadow.add(name)
+        return self.params[name]
+
+    def finalize(self):
+        total = 0
+        for p in self.params.values():
+            p.offset = total
+            total += (p.numel + 63) // 64 * 64  # keep every view 256-byte aligned
+        self.flat_w = torch.zeros(total, dtype=F32, device="cuda")
+        self.flat_g = torch.zeros(total, dtype=F32, device="cuda")
+        self.flat_m = torch.zeros(total, dtype=F32, device="cuda")
+        self.flat_v = torch.zeros(total, dtype=F32, device="cuda")
+        self.step_dev = torch.ones(1, dtype=I32, device="cuda")
+        for p in self.params.values():
+            sl = slice(p.offset, p.offset + p.numel)
+            p.w = self.flat_w[sl].view(p.shape)
+            p.g = self.flat_g[sl].view(p.shape)
+            p.m = self.flat_m[sl].view(p.shape)
+            p.v = self.flat_v[sl].view(p.shape)
+            p.w.copy_(torch.from_numpy(self._init[p.name]))
+            if p.name in self._shadow:
+                rows, cols = p.shape
+                p.wb = torch.zeros((rows, ld8(cols)), dtype=BF16, device="cuda")
+                ops.cast_bf16(p.w, cols, out=p.wb)
+        self._init = None
+        torch.cuda.synchronize()
+
+    def __getitem__(self, name):
+        return self.params[name]
+
+    def set_weights(self, arrays):
+        """Load {name: ndarray} (Keras layouts) and refresh the bf16 shadows."""
+        for name, arr in arrays.items():
+            p = self.params[name]
+            p.w.copy_(torch.as_tensor(np.ascontiguousarray(arr, dtype=np.float32)).view(p.shape))
+            if p.wb is not None:
+                ops.cast_bf16(p.w, p.shape[1], out=p.wb)
+        torch.cuda.synchronize()
+
+    def get_weights(self):
+        return {n: p.w.detach().cpu().numpy().copy() for n, p in self.params.items()}
+
+    def get_grads(self):
+        return {n: p.g.detach().cpu().numpy().copy() for n, p in self.params.items()}
+
+    def adam(self, lr, beta1=0.9, beta2=0.999, eps=1e-9, grad_scale=1.0):
+        """Keras-semantics Adam over every parameter (tables dense-equivalent), then t += 1."""
+        plain = [p for p in self.params.values() if p.wb is None]
+        # parameters without shadows are swept in maximal contiguous runs of the flat buffers
+        runs = []
+        for p in sorted(plain, key=lambda q: q.offset):
+            end = p.offset + (p.numel + 63) // 64 * 64
+            if runs and runs[-1][1] == p.offset:
+                runs[-1][1] = end
+            else:
+                runs.append([p.offset, end])
+        for a, b in runs:
+            ops.adam_step(self.flat_w[a:b], self.flat_g[a:b], self.flat_m[a:b], self.flat_v[a:b],
+                          lr=lr, beta1=beta1, beta2=beta2, eps=eps, step_dev=self.step_dev,
+                          grad_scale=grad_scale)
+        for p in self.params.values():
+            if p.wb is not None:
+                ops.adam_step(p.w, p.g, p.m, p.v, lr=lr, beta1=beta1, beta2=beta2, eps=eps,
+                              step_dev=self.step_dev, grad_scale=grad_scale, shadow=p.wb,
+                              cols=p.shape[1])
+        ops.step_increment(self.step_dev)
+
+
+class BufferPool:
+    """Named device buffers allocated once per (name, shape, dtype)."""
+
+    def __init__(self):
+        self._b = {}
+
+    def get(self, name, shape, dtype=F32, zero=False):
+        key = (name, tuple(shape), dtype)
+        t = self._b.get(key)
+        if t is None:
+            t = torch.zeros(shape, dtype=dtype, device="cuda")
+            self._b[key] = t
+        elif zero:
+            t.zero_()
+        return t
+
+
+def glorot_uniform(rng, fan_in, fan_out):
+    lim = math.sqrt(6.0 / (fan_in + fan_out))
+    return rng.uniform(-lim, lim, size=(fan_in, fan_out)).astype(np.float32)
+
+
+# =============================================================================== dense layer
+def dense_fwd(xb, K, W, bias, M, *, relu=False, out_f32=None, out_bf16=None):
+    """y = act(x W + b).  xb bf16 [M, ld8(K)], W: Param with Keras (K, N) kernel + shadow."""
+    N = W.shape[1]
+    ops.gemm(xb, 0, W.wb, 1, M, N, K, bias=bias.w if bias is not None else None, relu=relu,
+             out_f32=out_f32, out_bf16=out_bf16)
+
+
+def dense_bwd_weights(xb, dyb, W, bias, M, *, db_from=None):
+    """dW = x^T dy (split-K, deterministic), db = column sums of dy (unless already reduced)."""
+    K, N = W.shape
+    ops.gemm_splitk(xb, 1, dyb, 1, K, N, M, W.g)
+    if bias is not None and db_from is None:
+        ops.colsum_bf16(dyb, M, N, bias.g)
+
+
+def dense_bwd_input(dyb, W, M, *, gate=None, addend=None, out_f32=None, out_bf16=None):
+    """dx = dy W^T, optionally gated by the ReLU of the layer that produced x / accumulated."""
+    K, N = W.shape
+    ops.gemm(dyb, 0, W.wb, 0, M, K, N, gate=gate, addend=addend, out_f32=out_f32,
+             out_bf16=out_bf16)
+
+
+# =============================================================================== encoder
+class EncoderEngine:
+    """Embedding + encoder stack (clickstream_transformer/transformer.py:271-402)."""
+
+    def __init__(self, store, embedding_sizes, embedding_dims, num_layers, num_heads, dff,
+                 dropout_rate, rng, max_pos=10000):
+        from .transformer import positional_encoding
+        self.store = store
+        self.features = list(embedding_dims.keys())
+        self.rows = [int(embedding_sizes[f]) for f in self.features]
+        self.dims = [int(embedding_dims[f]) for f in self.features]
+        self.d = sum(self.dims)
+        assert self.d % num_heads == 0
+        assert self.d % 8 == 0, "d_model must be a multiple of 8 (16-byte bf16 rows for TMA)"
+        self.L, self.H, self.dff, self.rate = num_layers, num_heads, dff, float(dropout_rate)
+        self.dh = self.d // num_heads
+        d = self.d
+        for f, (R, df) in enumerate(zip(self.rows, self.dims)):
+            store.add(f"emb.{f}", rng.uniform(-0.05, 0.05, size=(R, df)))
+        for l in range(num_layers):
+            wq, wk, wv = (glorot_uniform(rng, d, d) for _ in range(3))
+            store.add(f"enc.{l}.wqkv", np.concatenate([wq, wk, wv], axis=1), shadow=True)
+            store.add(f"enc.{l}.bqkv", np.zeros(3 * d))
+            store.add(f"enc.{l}.wo", glorot_uniform(rng, d, d), shadow=True)
+            store.add(f"enc.{l}.bo", np.zeros(d))
+            store.add(f"enc.{l}.w1", glorot_uniform(rng, d, dff), shadow=True)
+            store.add(f"enc.{l}.b1", np.zeros(dff))
+            store.add(f"enc.{l}.w2", glorot_uniform(rng, dff, d), shadow=True)
+            store.add(f"enc.{l}.b2", np.zeros(d))
+            for k in ("ln1", "ln2"):
+                store.add(f"enc.{l}.{k}_g", np.ones(d))
+                store.add(f"enc.{l}.{k}_b", np.zeros(d))
+        self.pe_host = positional_encoding(max_pos, d)
+        self.pe = None
+        self.pool = BufferPool()
+        self.saved = None
+
+    def _pe(self):
+        if self.pe is None:
+            self.pe = torch.from_numpy(self.pe_host).cuda()
+        return self.pe
+
+    def forward(self, ids_list, B, S, training, seed=0):
+        """ids_list: per-feature int32 [B*S] device tensors.  Returns fp32 [B*S, d] (+ bf16)."""
+        st, pool, d, T = self.store, self.pool, self.d, B * S
+        rate = self.rate if training else 0.0
+        tables = [st[f"emb.{f}"].w for f in range(len(self.features))]
+        x = pool.get("x0", (T, d))
+        xb = pool.get("x0b", (T, d), BF16)
+        ops.embed_fwd(ids_list, tables, self._pe(), B, S, dropout_rate=rate, seed=seed,
+                      site=SITE_INPUT, out_f32=x, out_bf16=xb)
+        acts = []
+        dffp = ld8(self.dff)
+        for l in range(self.L):
+            g = lambda n: st[f"enc.{l}.{n}"]
+            a = dict(x=x, xb=xb)
+            a["qkvb"] = pool.get(f"qkvb{l}", (T, 3 * d), BF16)
+            dense_fwd(xb, d, g("wqkv"), g("bqkv"), T, out_bf16=a["qkvb"])
+            a["ob"] = pool.get(f"ob{l}", (T, d), BF16)
+            a["lse"] = pool.get(f"lse{l}", (B, self.H, S))
+            ops.attention_fwd(a["qkvb"], ids_list[0], B, S, self.H, self.dh, a["ob"], a["lse"])
+            a["y1"] = pool.get(f"y1_{l}", (T, d))
+            dense_fwd(a["ob"], d, g("wo"), g("bo"), T, out_f32=a["y1"])
+            a["x1"] = pool.get(f"x1_{l}", (T, d))
+            a["x1b"] = pool.get(f"x1b{l}", (T, d), BF16)
+            ops.residual_ln_fwd(x, a["y1"], g("ln1_g").w, g("ln1_b").w, a["x1"], a["x1b"],
+                                dropout_rate=rate, seed=seed, site=site(l, 1))
+            a["hb"] = pool.get(f"hb{l}", (T, dffp), BF16)
+            dense_fwd(a["x1b"], d, g("w1"), g("b1"), T, relu=True, out_bf16=a["hb"])
+            a["y2"] = pool.get(f"y2_{l}", (T, d))
+            dense_fwd(a["hb"], self.dff, g("w2"), g("b2"), T, out_f32=a["y2"])
+            x2 = pool.get(f"x2_{l}", (T, d))
+            x2b = pool.get(f"x2b{l}", (T, d), BF16)
+            ops.residual_ln_fwd(a["x1"], a["y2"], g("ln2_g").w, g("ln2_b").w, x2, x2b,
+                                dropout_rate=rate, seed=seed, site=site(l, 2))
+            acts.append(a)
+            x, xb = x2, x2b
+        self.saved = dict(acts=acts, ids=ids_list, B=B, S=S, rate=rate, seed=seed)
+        return x, xb
+
+    def backward(self, dx):
+        """dx: fp32 [T, d] gradient of the encoder output.  Fills every encoder / table .g"""
+        sv, st, pool, d = self.saved, self.store, self.pool, self.d
+        B, S, rate, seed = sv["B"], sv["S"], sv["rate"], sv["seed"]
+        T = B * S
+        dffp = ld8(self.dff)
+        for l in reversed(range(self.L)):
+            g = lambda n: st[f"enc.{l}.{n}"]
+            a = sv["acts"][l]
+            # LN2: dx -> dx1 (residual), dy2 (FFN output grad, bf16) + dgamma/dbeta/db2
+            dx1 = pool.get("dxa", (T, d))
+            dy2b = pool.get("dyb", (T, d), BF16)
+            ops.residual_ln_bwd(dx, a["x1"], a["y2"], g("ln2_g").w, dx1, dy2b, g("ln2_g").g,
+                                g("ln2_b").g, g("b2").g, dropout_rate=rate, seed=seed,
+                                site=site(l, 2))
+            dense_bwd_weights(a["hb"], dy2b, g("w2"), None, T)
+            dhb = pool.get("dhb", (T, dffp), BF16, zero=(dffp != self.dff))
+            dense_bwd_input(dy2b, g("w2"), T, gate=a["hb"], out_bf16=dhb)
+            dense_bwd_weights(a["x1b"], dhb, g("w1"), g("b1"), T)
+            dx1b = pool.get("dxb", (T, d))
+            dense_bwd_input(dhb, g("w1"), T, addend=dx1, out_f32=dx1b)
+            # LN1
+            dxr = pool.get("dxa", (T, d))
+            dy1b = pool.get("dyb", (T, d), BF16)
+            ops.residual_ln_bwd(dx1b, a["x"], a["y1"], g("ln1_g").w, dxr, dy1b, g("ln1_g").g,
+                                g("ln1_b").g, g("bo").g, dropout_rate=rate, seed=seed,
+                                site=site(l, 1))
+            dense_bwd_weights(a["ob"], dy1b, g("wo"), None, T)
+            dob = pool.get("dob", (T, d), BF16)
+            dense_bwd_input(dy1b, g("wo"), T, out_bf16=dob)
+            dqkvb = pool.get("dqkvb", (T, 3 * d), BF16)
+            ops.attention_bwd(a["qkvb"], dob, a["lse"], sv["ids"][0], B, S, self.H, self.dh, dqkvb)
+            dense_bwd_weights(a["xb"], dqkvb, g("wqkv"), g("bqkv"), T)
+            dx = pool.get("dxb", (T, d))
+            dense_bwd_input(dqkvb, g("wqkv"), T, addend=dxr, out_f32=dx)
+        off = 0
+        for f, (R, df) in enumerate(zip(self.rows, self.dims)):
+            ops.embed_bwd(dx, d, off, df, sv["ids"][f], R, st[f"emb.{f}"].g, dropout_rate=rate,
+                          seed=seed, site=SITE_INPUT)
+            off += df
+        return dx
+
+
+# =============================================================================== head MLP
+class MlpEngine:
+    """ReLU Dense stack shared by every Head unit (clickstream_transformer/head.py:10,35,56)."""
+
+    def __init__(self, store, prefix, in_dim, dims, rng):
+        self.store, self.prefix, self.in_dim, self.dims = store, prefix, int(in_dim), list(dims)
+        prev = self.in_dim
+        for i, hd in enumerate(self.dims):
+            store.add(f"{prefix}.{i}.w", glorot_uniform(rng, prev, hd), shadow=True)
+            store.add(f"{prefix}.{i}.b", np.zeros(hd))
+            prev = hd
+        self.out_dim = prev
+        self.pool = BufferPool()
+        self.saved = None
+
+    def forward(self, xb, M):
+        """xb bf16 [M, ld8(in)] -> bf16 [M, ld8(out)] (post-ReLU of the last layer)."""
+        acts = [xb]
+        prev = self.in_dim
+        for i, hd in enumerate(self.dims):
+            W, b = self.store[f"{self.prefix}.{i}.w"], self.store[f"{self.prefix}.{i}.b"]
+            out = self.pool.get(f"a{i}", (M, ld8(hd)), BF16)
+            dense_fwd(acts[-1], prev, W, b, M, relu=True, out_bf16=out)
+            acts.append(out)
+            prev = hd
+        self.saved = dict(acts=acts, M=M)
+        return acts[-1]
+
+    def backward(self, dzb, out_f32):
+        """dzb: bf16 [M, ld8(out)] gradient w.r.t. the last layer's PRE-activation (already
+        gated).  Writes the gradient w.r.t. the MLP input (fp32 [M, in]) into out_f32."""
+        acts, M = self.saved["acts"], self.saved["M"]
+        for i in reversed(range(len(self.dims))):
+            W, b = self.store[f"{self.prefix}.{i}.w"], self.store[f"{self.prefix}.{i}.b"]
+            dense_bwd_weights(acts[i], dzb, W, b, M)
+            if i > 0:
+                prev = self.pool.get(f"da{i}", (M, ld8(self.dims[i - 1])), BF16)
+                dense_bwd_input(dzb, W, M, gate=acts[i], out_bf16=prev)
+                dzb = prev
+            else:
+                dense_bwd_input(dzb, W, M, out_f32=out_f32)
+
+
+# =============================================================================== vocab output
+class VocabOutputEngine:
+    """Dense(V) output layer of SoftMaxHead (head.py:36,45) fused with the Cloze loss
+    (examples/BERT4Rec/source/utils.py:116-134, losses.py:31-98) and the ranking metrics."""
+
+    MATERIALIZE_LIMIT_BYTES = 12 << 30
+
+    def __init__(self, store, prefix, in_dim, vocab, rng):
+        self.store, self.prefix, self.h, self.V = store, prefix, int(in_dim), int(vocab)
+        store.add(f"{prefix}.out.w", glorot_uniform(rng, self.h, self.V), shadow=True)
+        store.add(f"{prefix}.out.b", np.zeros(self.V))
+        self.pool = BufferPool()
+        self.saved = None
+
+    @property
+    def W(self):
+        return self.store[f"{self.prefix}.out.w"]
+
+    @property
+    def b(self):
+        return self.store[f"{self.prefix}.out.b"]
+
+    def logits(self, ab, M):
+        """fp32 [M, ld8(V)] logits (materialised; validation / small-V path)."""
+        Vp = ld8(self.V)
+        if M * Vp * 4 > self.MATERIALIZE_LIMIT_BYTES:
+            raise MemoryError(f"refusing to materialise {M}x{self.V} logits; use the fused path")
+        z = self.pool.get("logits", (M, Vp))
+        dense_fwd(ab, self.h, self.W, self.b, M, out_f32=z)
+        return z
+
+    def probabilities(self, ab, M):
+        z = self.logits(ab, M)
+        lse = self.pool.get("lse", (M,))
+        tgt = self.pool.get("tgt", (M,))
+        nolabel = self.pool.get("nolabel", (M,), I32, zero=True)
+        ops.ce_rows_stats(z, self.V, nolabel, lse, tgt)
+        probs = torch.empty((M, self.V), dtype=F32, device="cuda")
+        ops.ce_rows_grad(z, self.V, None, lse, None, None, probs)
+        return probs
+
+    def loss_forward(self, ab, M, labels, loss_stats):
+        """loss_stats <- (sum over valid rows of lse - z_t, number of valid rows)."""
+        z = self.logits(ab, M)
+        lse = self.pool.get("lse", (M,))
+        tgt = self.pool.get("tgt", (M,))
+        ops.ce_rows_stats(z, self.V, labels, lse, tgt)
+        ops.ce_loss_reduce(lse, tgt, labels, loss_stats)
+        self.saved = dict(ab=ab, M=M, labels=labels, z=z, lse=lse)
+
+    def loss_backward(self, loss_stats, gate, out_f32=None, out_bf16=None):
+        """Gradients of mean CE (normalised by loss_stats[1], which may already be the global
+        count): fills W.g, b.g and returns d(loss)/d(ab) gated by `gate` (the ReLU output that
+        produced ab, or None) as fp32 and/or bf16."""
+        sv = self.saved
+        ab, M, V, h = sv["ab"], sv["M"], self.V, self.h
+        dz = self.pool.get("dz", (M, ld8(V)), BF16)
+        ops.ce_rows_grad(sv["z"], V, sv["labels"], sv["lse"], loss_stats, dz, None)
+        ops.gemm_splitk(ab, 1, dz, 1, h, V, M, self.W.g, ws_name="splitk_vocab")
+        ops.colsum_bf16(dz, M, V, self.b.g)
+        # dx = dz W^T : K = V is long and M x h is small -> split-K with a gated reduce
+        splits = ops.gemm_splits_for(M, h, V)
+        part = ops.WS.get("splitk_dx", splits * M * h * 4).view(F32)[: splits * M * h].view(splits, M, h)
+        ops.gemm(dz, 0, self.W.wb, 0, M, h, V, out_f32=part, splits=splits)
+        ops.reduce_splits_ex(part, M, h, gate, out_f32, out_bf16)
+
+    def topk(self, ab, M, k):
+        z = self.logits(ab, M)
+        ids = self.pool.get(f"topk{k}", (M, k), I32)
+        ops.topk_rows(z, self.V, k, out_ids=ids)
+        return ids

@@ -101,6 +101,14 @@ def gemm_splitk(A, a_mn, B, b_mn, M, N, K, out_f32, ws_name="splitk"):
     reduce_splits(buf, out_f32)
 
 
+def reduce_splits_ex(partials, M, N, gate=None, out_f32=None, out_bf16=None):
+    splits = partials.shape[0]
+    L.call("b4cp_reduce_splits_ex", L.ptr(partials), L.c_int(splits), L.c_long(M), L.c_int(N),
+           L.c_long(partials.stride(0)), L.ptr(gate),
+           L.c_long(gate.stride(0) if gate is not None else 0), L.ptr(out_f32), L.ptr(out_bf16),
+           L.c_long(out_bf16.stride(0) if out_bf16 is not None else 0), L.stream_ptr())
+
+
 def cast_bf16(x_f32, cols=None, out=None):
     """fp32 [rows, cols] -> bf16 [rows, ld8(cols)] (zero padded)."""
     rows = x_f32.shape[0]
@@ -215,6 +223,19 @@ def select_masked(ids_first, value, capacity):
     return row_index[:capacity], count
 
 
+def compact_labels(labels_f32, capacity, label_pad=-1.0):
+    """(B, Mmax) float32 labels padded with -1 -> int32 [capacity] valid labels, -1 padded."""
+    n = labels_f32.numel()
+    fn = L.lib().b4cp_select_workspace_bytes
+    fn.restype = ctypes.c_long
+    ws = WS.get("select", fn(ctypes.c_long(max(n, 1))))
+    out = empty((max(capacity, 1),), I32)
+    count = empty((1,), I32)
+    L.call("b4cp_compact_labels", L.ptr(labels_f32), L.c_long(n), L.c_float(label_pad), L.ptr(out),
+           L.c_long(capacity), L.ptr(count), L.ptr(ws), L.stream_ptr())
+    return out[:capacity], count
+
+
 def gather_rows(x, row_index, out_f32=None, out_bf16=None):
     M = row_index.numel()
     d = x.shape[1]
@@ -276,3 +297,25 @@ def adam_step(theta, grad, m, v, *, lr, beta1=0.9, beta2=0.999, eps=1e-9, step_d
 
 def step_increment(step_dev):
     L.call("b4cp_step_increment", L.ptr(step_dev), L.stream_ptr())
+
+
+def sigmoid(z, out=None):
+    if out is None:
+        out = torch.empty_like(z)
+    L.call("b4cp_sigmoid", L.ptr(z), L.ptr(out), L.c_long(z.numel()), L.stream_ptr())
+    return out
+
+
+def clip_log(p, lo=1e-7, hi=1.0 - 1e-7):
+    out = torch.empty_like(p)
+    L.call("b4cp_clip_log", L.ptr(p), L.ptr(out), L.c_long(p.numel()), L.c_float(lo), L.c_float(hi),
+           L.stream_ptr())
+    return out
+
+
+def masked_bce(y_true, probs, label_pad, pos_weight=None):
+    stats = empty((2,))
+    L.call("b4cp_masked_bce", L.ptr(y_true), L.ptr(probs), L.c_long(y_true.numel()),
+           L.c_float(label_pad), L.c_float(pos_weight if pos_weight is not None else 1.0),
+           L.c_int(0 if pos_weight is None else 1), L.ptr(stats), L.stream_ptr())
+    return stats

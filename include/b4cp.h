@@ -168,6 +168,19 @@ int b4cp_ce_rows_grad(const float* logits, long ld, long M, int V, const int32_t
                       const float* lse, const float* loss_stats, void* dz_bf16, long ld_dz,
                       float* probs, long ld_probs, void* stream);
 
+/* Probability inputs (a materialised SoftMaxHead output): z = log(clip(p, lo, hi)) reproduces
+ * K.sparse_categorical_crossentropy(from_logits=False) of TF 2.3 when followed by
+ * b4cp_ce_rows_stats (losses.py:60 via examples/BERT4Rec/source/main.py:89). */
+int b4cp_clip_log(const float* p, float* out, long n, float lo, float hi, void* stream);
+/* MaskedLoss with K.binary_crossentropy and optional pos_weight (losses.py:31-98):
+ * stats[0] = sum of weighted item losses over labels != label_pad, stats[1] = their count */
+int b4cp_masked_bce(const float* y_true, const float* probs, long n, float label_pad,
+                    float pos_weight, int use_pos_weight, float* stats, void* stream);
+
+/* sigmoid output activation of BinaryClassificationHead / MultiLabel_MultiClass_classification
+ * (head.py:11, :57) */
+int b4cp_sigmoid(const float* z, float* out, long n, void* stream);
+
 /* ------------------------------------------------------------------ ranking metrics
  * tf.math.top_k order (score desc, ties -> lower id): utils.py:176, :245.  k <= 256.
  * rank_metrics accumulates counters += (hits, sum 1/log2(rank+2), n_valid): utils.py:176-187,
