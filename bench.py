@@ -1,0 +1,308 @@
+#!/usr/bin/env python
+"""Benchmark of the clickstream-transformer hot path (BASELINE.json metric: Cloze train seqs/s).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+  python bench.py --impl reference --gpus N ...             # the reference's CPU restatement
+  torchrun --nproc-per-node N bench.py --gpus N ...         # one rank per GPU (NCCL)
+
+A "step" is one full Cloze training step (forward, backward, gradient all-reduce, Adam) of the
+BERT4Rec configuration (V_out=54,293, L=50 -> TRAIN S=52, d=64, 2 layers,
+2 heads, dff=100, head [1024,512,256,128], 7 masks / sequence, dropout 0.1) on synthetic
+Zipf clickstreams.  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CFG = dict(vocab=54293, max_len=50, d_model=64, layers=2, heads=2, dff=100,
+           head_dims=[1024, 512, 256, 128], mask_rate=0.15, max_masked=10, dropout=0.1)
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(bf16_burst=p["bf16_tflops"], bf16_sustained=p["bf16_tflops_sustained"],
+                    hbm=p["hbm_gbs"], source="measured")
+    return dict(bf16_burst=1590.0, bf16_sustained=1400.0, hbm=6650.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except Exception:
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------ CPU reference
+def cpu_reference_step_fn(B):
+    """One full training step of the oracle (fp32 NumPy restatement of the reference: forward,
+    backward, Keras-Adam over every parameter) at the bench configuration with batch B."""
+    from oracle import clickpath_oracle as O
+    from bert4clickpath_b200.synthetic import make_cloze_batch
+    rng = np.random.default_rng(1234)
+    V, d = CFG["vocab"], CFG["d_model"]
+    P = O.init_params(rng, [V + 11], [d], CFG["layers"], CFG["dff"], CFG["head_dims"], V,
+                      dtype=np.float32)
+    pe = O.positional_encoding(10000, d)
+    batch = make_cloze_batch(rng, B, V, CFG["max_len"], "train", CFG["mask_rate"], CFG["max_masked"])
+    ids, labels = [batch["ids"].astype(np.int64)], batch["labels"]
+    Mm = {k: np.zeros_like(v) for k, v in P.items()}
+    Vv = {k: np.zeros_like(v) for k, v in P.items()}
+    state = dict(t=0)
+
+    def step():
+        state["t"] += 1
+        loss, G, _ = O.cloze_train_step(ids, labels, P, CFG["layers"], CFG["heads"], pe, np.float32)
+        for k in P:
+            P[k], Mm[k], Vv[k] = O.adam_step(P[k], G[k].astype(np.float32), Mm[k], Vv[k], state["t"])
+        return float(loss)
+
+    return step
+
+
+def time_cpu_reference(B, steps, warmup, budget_s=25.0):
+    step = cpu_reference_step_fn(B)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    n = 0
+    while n < steps and (n == 0 or time.perf_counter() - t0 < budget_s):
+        step()
+        n += 1
+    dt = time.perf_counter() - t0
+    return B * n / dt, n, dt
+
+
+def blas_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        return max([i.get("num_threads", 1) for i in threadpool_info()] + [1])
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    B = args.cpu_batch
+    seqs, n, dt = time_cpu_reference(B, args.steps, min(args.warmup, 1))
+    cores = blas_threads()
+    line = {
+        "impl": "reference", "metric": "cloze_train_seqs_per_sec", "value": seqs, "unit": "seqs/s",
+        "n_gpus": args.gpus, "steps": n, "warmup": min(args.warmup, 1),
+        "ms_per_step": 1e3 * dt / n, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(B), "per_gpu_batch": B,
+                   "note": "reference TF 2.3.1 stack cannot run here; oracle/ NumPy restatement "
+                           "of the same step on the host cores"},
+        "cpu_baseline": {"value": seqs, "unit": "seqs/s", "cores": cores, "kind": "port",
+                         "sample": f"{n} full training steps at batch {B} (bounded sample of the "
+                                   f"same workload)"},
+        "e2e": {"value": seqs, "unit": "seqs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_name(B):
+    return (f"C2/C1 BERT4Rec Cloze train step: V_out={CFG['vocab']}, S=52, d=64, 2 layers, 2 heads, "
+            f"dff=100, head {CFG['head_dims']}, 7 masks/seq, per-GPU batch {B}")
+
+
+# ------------------------------------------------------------------------------------- ours
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    import bert4clickpath_b200 as bc
+    from bert4clickpath_b200 import _lib, ops
+    from bert4clickpath_b200.synthetic import make_cloze_batch
+    from bert4clickpath_b200.training import ClozeTrainStep
+    _lib.call("b4cp_device_check")
+    V, d, B = CFG["vocab"], CFG["d_model"], args.batch
+    head = bc.SoftMaxHead(dense_layer_dims=CFG["head_dims"], output_vocab_size=V)
+    model = bc.ClickstreamTransformer(
+        sequential_input_config={"items": ["asin"]}, feature_vocabs={"items": V},
+        embedding_dims={"items": d}, head_unit=head, value_to_head=bc.INPUT_MASKING_TOKEN,
+        num_encoder_layers=CFG["layers"], num_attention_heads=CFG["heads"],
+        dropout_rate=CFG["dropout"], encoder_ff_dim=CFG["dff"], seed=0)
+    trainer = ClozeTrainStep(model, bc.Adam(1e-3, 0.9, 0.999, 1e-9))
+    rng = np.random.default_rng(1234 + rank)
+    n_ring = 4
+    host = [make_cloze_batch(rng, B, V, CFG["max_len"], "train", CFG["mask_rate"], CFG["max_masked"])
+            for _ in range(n_ring)]
+    dev = [trainer.to_device(b) for b in host]
+    pinned = [(torch.from_numpy(b["ids"]).pin_memory(), torch.from_numpy(b["labels"]).pin_memory(),
+               b["n_masked"]) for b in host]
+    S = host[0]["ids"].shape[1]
+    M = host[0]["n_masked"]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+
+    # ---- device-resident timing
+    for i in range(args.warmup):
+        trainer.step_device(dev[i % n_ring])
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ops.TIMER.reset()
+    ops.TIMER.enabled = True
+    launches0 = _lib.lib().b4cp_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        stats = trainer.step_device(dev[i % n_ring])
+    e1.record()
+    barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop() if rank == 0 else None
+    launches = _lib.lib().b4cp_launch_count() - launches0
+    ops.TIMER.enabled = False
+    kt = ops.TIMER.totals_ms()
+    loss_stats = stats.cpu().numpy()
+
+    # ---- end-to-end timing through the public API (pinned host buffers in, loss out)
+    trainer.step_host(*pinned[0])
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    for i in range(args.steps):
+        loss = trainer.step_host(*pinned[i % n_ring])
+    e1.record()
+    barrier()
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+    h2d = ClozeTrainStep.h2d_bytes(pinned[0][0], pinned[0][1])
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    pk = peaks()
+    seqs = world * B * args.steps / (ms_total * 1e-3)
+    seqs_e2e = world * B * args.steps / (ms_e2e * 1e-3)
+    # roofline of the dominant kernel(s): the vocab projection (fwd + dW + dX), 6*M*h*V flops
+    h = CFG["head_dims"][-1]
+    flops = 6.0 * M * h * V
+    tag = "vocab_ce" if "vocab_ce" in kt else "vocab_gemm"
+    k_ms, k_n = kt.get(tag, (0.0, 0))
+    per_step_ms = k_ms / max(args.steps, 1)
+    achieved = flops / (per_step_ms * 1e-3) / 1e12 if per_step_ms > 0 else 0.0
+    roof = {"bound": "tensor", "kernel": tag, "achieved": achieved, "peak": pk["bf16_sustained"],
+            "unit": "TFLOP/s", "frac": achieved / pk["bf16_sustained"], "traffic": None,
+            "peak_source": pk["source"] + " (sustained: kernel timed inside a long step)",
+            "algorithmic_flops_per_step": flops, "kernel_ms_per_step": per_step_ms,
+            "kernel_share_of_step": per_step_ms / (ms_total / args.steps)}
+    cpu_seqs, cpu_n, cpu_dt = time_cpu_reference(args.cpu_batch, 6, 1, budget_s=20.0)
+    line = {
+        "metric": "cloze_train_seqs_per_sec", "value": seqs, "unit": "seqs/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic",
+        "config": {"workload": workload_name(B), "per_gpu_batch": B, "global_batch": B * world,
+                   "seq_len": S, "masked_per_step_per_gpu": M, "parallelism": f"dp{world}",
+                   "l2": "per-step working set (activations + 28 MB output kernel + logits) "
+                         "exceeds the 126 MB L2; 4 distinct batches cycle",
+                   "precision": "bf16 tensor-core operands, fp32 accumulate / master weights"},
+        "clocks": clocks,
+        "e2e": {"value": seqs_e2e, "unit": "seqs/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": 8, "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches),
+        "roofline": roof,
+        "cpu_baseline": {"value": cpu_seqs, "unit": "seqs/s", "cores": blas_threads(),
+                         "kind": "port",
+                         "sample": f"{cpu_n} full oracle training steps at batch {args.cpu_batch}"},
+        "loss": float(loss_stats[0] / max(loss_stats[1], 1.0)), "e2e_last_loss": loss,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=1024, help="per-GPU batch (sequences)")
+    ap.add_argument("--cpu-batch", type=int, default=64, help="batch of the CPU reference sample")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        if args.warmup < 3:
+            args.warmup = 3
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -10,6 +10,7 @@ namespace b4cp {
 
 // ---------------------------------------------------------------- host errors
 void set_last_error(const char* fmt, ...);
+void note_launches(int n);  // kernel-launch accounting (b4cp_launch_count)
 int check_cuda(cudaError_t e, const char* what);
 
 #define B4CP_CHECK_ARG(cond, ...)            \

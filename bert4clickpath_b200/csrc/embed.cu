@@ -185,6 +185,7 @@ static int exclusive_scan(const int* in, int* out, long n, int* scratch, int* to
   scan_tile_sums_kernel<<<tiles, SCAN_THREADS, 0, st>>>(in, n, scratch);
   scan_small_kernel<<<1, SCAN_THREADS, 0, st>>>(scratch, tiles, total_out);
   scan_apply_kernel<<<tiles, SCAN_THREADS, 0, st>>>(in, out, n, scratch);
+  note_launches(3);
   B4CP_LAUNCH_CHECK();
   return 0;
 }
@@ -444,6 +445,7 @@ extern "C" int b4cp_embed_fwd(const int32_t* const* h_ids, const float* const* h
     embed_fwd_kernel<4><<<blocks, 256, 0, (cudaStream_t)stream>>>(p, out_f32, (__nv_bfloat16*)out_bf16);
   else
     embed_fwd_kernel<1><<<blocks, 256, 0, (cudaStream_t)stream>>>(p, out_f32, (__nv_bfloat16*)out_bf16);
+  note_launches(1);
   B4CP_LAUNCH_CHECK();
   return 0;
 }
@@ -479,6 +481,7 @@ extern "C" int b4cp_embed_bwd(const float* dout, int d_model, int col_offset, in
     if (exclusive_scan(w.hist, w.hist, 256L * nblocks, w.scan_scratch, nullptr, st)) return -1;
     radix_pass_kernel<true><<<nblocks, SORT_THREADS, 0, st>>>(kin, vin, kout, vout, T, ps * 8,
                                                                w.hist, nblocks);
+    note_launches(2);
     kin = kout;
     vin = vout;
     kout = (kout == w.keys0) ? w.keys1 : w.keys0;
@@ -507,6 +510,7 @@ extern "C" int b4cp_embed_bwd(const float* dout, int d_model, int col_offset, in
                                            inv_keep, thresh24, seed, site, table_grad, w.partial);
   segment_combine_kernel<<<grid, 256, 0, st>>>(dim, skeys, w.seg_start, w.mchunk_off, rows,
                                                n_unique, scale, w.partial, table_grad);
+  note_launches(5);
   if (uniq_ids) export_unique_kernel<<<tb, 256, 0, st>>>(skeys, w.seg_start, n_unique, uniq_ids, T);
   if (n_unique_out)
     B4CP_CUDA(cudaMemcpyAsync(n_unique_out, n_unique, sizeof(int), cudaMemcpyDeviceToDevice, st));
@@ -583,6 +587,7 @@ extern "C" int b4cp_select_masked(const int32_t* ids_first, long tokens, int val
   if (exclusive_scan(flags, pos, tokens, scratch, count_out, st)) return -1;
   select_write_kernel<<<ceil_div(span, 256), 256, 0, st>>>(flags, pos, tokens, row_index, capacity,
                                                            count_out);
+  note_launches(2);
   B4CP_LAUNCH_CHECK();
   return 0;
 }
@@ -593,6 +598,7 @@ extern "C" int b4cp_gather_rows(const float* x, int d, const int32_t* row_index,
   const int blocks = (int)std::min<long>(ceil_div(M * d, 256), 148L * 16);
   gather_rows_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, d, row_index, M, out_f32,
                                                                 (__nv_bfloat16*)out_bf16, ld_bf16);
+  note_launches(1);
   B4CP_LAUNCH_CHECK();
   return 0;
 }
@@ -603,6 +609,7 @@ extern "C" int b4cp_scatter_rows(const float* src, int d, const int32_t* row_ind
   if (M == 0) return 0;
   const int blocks = (int)std::min<long>(ceil_div(M * d, 256), 148L * 16);
   scatter_rows_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, d, row_index, M, dst);
+  note_launches(1);
   B4CP_LAUNCH_CHECK();
   return 0;
 }
@@ -644,6 +651,7 @@ extern "C" int b4cp_compact_labels(const float* labels, long n, float label_pad,
   if (exclusive_scan(flags, pos, n, scratch, count_out, st)) return -1;
   label_write_kernel<<<ceil_div(std::max(n, capacity), 256), 256, 0, st>>>(labels, flags, pos, n,
                                                                            out, capacity, count_out);
+  note_launches(2);
   B4CP_LAUNCH_CHECK();
   return 0;
 }

@@ -458,6 +458,7 @@ extern "C" int b4cp_attention_fwd(const void* qkv, const int32_t* ids_first, int
                                  227 * 1024));
   attention_fwd_kernel<<<B * H, threads, smem, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)qkv, ids_first, S, H, dh, (__nv_bfloat16*)out, lse);
+  note_launches(1);
   B4CP_LAUNCH_CHECK();
   return 0;
 }
@@ -476,6 +477,7 @@ extern "C" int b4cp_attention_bwd(const void* qkv, const void* dout, const float
   attention_bwd_kernel<<<B * H, threads, smem, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)qkv, (const __nv_bfloat16*)dout, lse, ids_first, S, H, dh,
       (__nv_bfloat16*)dqkv);
+  note_launches(1);
   B4CP_LAUNCH_CHECK();
   return 0;
 }
@@ -489,6 +491,7 @@ extern "C" int b4cp_residual_ln_fwd(const float* x, const float* r, long T, int 
   residual_ln_fwd_kernel<<<ceil_div(T, 8), 256, 0, (cudaStream_t)stream>>>(
       x, r, T, d, gamma, beta, make_drop(dropout_rate, seed, site), 1e-6f, y_f32,
       (__nv_bfloat16*)y_bf16, ld_bf16);
+  note_launches(1);
   B4CP_LAUNCH_CHECK();
   return 0;
 }
@@ -513,6 +516,7 @@ extern "C" int b4cp_residual_ln_bwd(const float* dy, const float* x, const float
                                                  make_drop(dropout_rate, seed, site), 1e-6f, dx,
                                                  (__nv_bfloat16*)dr_bf16, ld_bf16, partial);
   const int rb = ceil_div(d, 256);
+  note_launches(1 + (dgamma ? 1 : 0) + (dbeta ? 1 : 0) + (dbias ? 1 : 0));
   if (dgamma) reduce_partials_kernel<<<rb, 256, 0, st>>>(partial, blocks, d, 3L * d, dgamma);
   if (dbeta) reduce_partials_kernel<<<rb, 256, 0, st>>>(partial + d, blocks, d, 3L * d, dbeta);
   if (dbias) reduce_partials_kernel<<<rb, 256, 0, st>>>(partial + 2 * d, blocks, d, 3L * d, dbias);
@@ -536,6 +540,7 @@ extern "C" int b4cp_colsum_bf16(const void* in, long T, int n, long ld, float* o
   dim3 grid(chunks, ceil_div(n, 64));
   colsum_partial_kernel<<<grid, 256, 0, st>>>((const __nv_bfloat16*)in, T, n, ld, (float*)workspace);
   reduce_partials_kernel<<<ceil_div(n, 256), 256, 0, st>>>((const float*)workspace, chunks, n, n, out);
+  note_launches(2);
   B4CP_LAUNCH_CHECK();
   return 0;
 }
@@ -544,6 +549,7 @@ extern "C" int b4cp_reduce_splits(const float* partials, int splits, long n, lon
                                   float* out, void* stream) {
   reduce_partials_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(partials, splits, n,
                                                                              split_stride, out);
+  note_launches(1);
   B4CP_LAUNCH_CHECK();
   return 0;
 }
@@ -577,6 +583,7 @@ extern "C" int b4cp_reduce_splits_ex(const float* partials, int splits, long M, 
   reduce_splits_ex_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
       partials, splits, M, N, split_stride, (const __nv_bfloat16*)gate, ld_gate, out_f32,
       (__nv_bfloat16*)out_bf16, ld_bf16);
+  note_launches(1);
   B4CP_LAUNCH_CHECK();
   return 0;
 }
@@ -587,6 +594,7 @@ extern "C" int b4cp_cast_f32_bf16(const float* in, long rows, int cols, long ld_
   const int blocks = (int)std::min<long>(ceil_div(rows * ld_out, 256), 148L * 16);
   cast_f32_bf16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(in, rows, cols, ld_in,
                                                                   (__nv_bfloat16*)out, ld_out);
+  note_launches(1);
   B4CP_LAUNCH_CHECK();
   return 0;
 }
@@ -597,6 +605,7 @@ extern "C" int b4cp_dropout_mask(float* out, long n, float dropout_rate, uint64_
   const int blocks = (int)std::min<long>(ceil_div(n, 256), 148L * 16);
   dropout_mask_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(out, n,
                                                                  make_drop(dropout_rate, seed, site));
+  note_launches(1);
   B4CP_LAUNCH_CHECK();
   return 0;
 }

@@ -1,5 +1,6 @@
 // Error reporting for the C ABI: every export returns 0 on success, <0 for a bad argument,
 // >0 for a cudaError_t; b4cp_last_error() returns the thread-local message.
+#include <atomic>
 #include <stdarg.h>
 #include <stdio.h>
 
@@ -9,6 +10,9 @@
 namespace b4cp {
 
 static thread_local char g_err[512] = "";
+static std::atomic<long> g_launches{0};
+
+void note_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 void set_last_error(const char* fmt, ...) {
   va_list ap;
@@ -26,6 +30,8 @@ int check_cuda(cudaError_t e, const char* what) {
 }  // namespace b4cp
 
 extern "C" const char* b4cp_last_error(void) { return b4cp::g_err; }
+
+extern "C" long b4cp_launch_count(void) { return b4cp::g_launches.load(); }
 
 extern "C" int b4cp_version(void) { return B4CP_VERSION; }
 

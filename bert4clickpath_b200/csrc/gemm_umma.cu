@@ -327,6 +327,7 @@ extern "C" int b4cp_gemm_bf16(const void* A, int a_mn, long lda, const void* B, 
   }
   dim3 grid(ceil_div(M, BM), ceil_div(N, p.BN), splits);
   gemm_umma_kernel<<<grid, 192, smem, (cudaStream_t)stream>>>(tmA, tmB, p);
+  note_launches(1);
   B4CP_LAUNCH_CHECK();
   return 0;
 }

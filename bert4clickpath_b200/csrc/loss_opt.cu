@@ -233,6 +233,7 @@ extern "C" int b4cp_ce_rows_stats(const float* logits, long ld, long M, int V,
                                   const int32_t* labels, float* lse, float* tgt, void* stream) {
   if (M == 0) return 0;
   ce_rows_stats_kernel<<<(unsigned)M, 256, 0, (cudaStream_t)stream>>>(logits, ld, V, labels, lse, tgt);
+  note_launches(1);
   B4CP_LAUNCH_CHECK();
   return 0;
 }
@@ -240,6 +241,7 @@ extern "C" int b4cp_ce_rows_stats(const float* logits, long ld, long M, int V,
 extern "C" int b4cp_ce_loss_reduce(const float* lse, const float* tgt, const int32_t* labels,
                                    long M, float* loss_stats, void* stream) {
   ce_loss_reduce_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(lse, tgt, labels, M, loss_stats);
+  note_launches(1);
   B4CP_LAUNCH_CHECK();
   return 0;
 }
@@ -251,6 +253,7 @@ extern "C" int b4cp_ce_rows_grad(const float* logits, long ld, long M, int V,
   if (M == 0) return 0;
   ce_rows_grad_kernel<<<(unsigned)M, 256, 0, (cudaStream_t)stream>>>(
       logits, ld, V, labels, lse, loss_stats, (__nv_bfloat16*)dz_bf16, ld_dz, probs, ld_probs);
+  note_launches(1);
   B4CP_LAUNCH_CHECK();
   return 0;
 }
@@ -258,6 +261,7 @@ extern "C" int b4cp_ce_rows_grad(const float* logits, long ld, long M, int V,
 extern "C" int b4cp_rank_metrics(const int32_t* topk_ids, long M, int k, long ld,
                                  const int32_t* labels, float* counters, void* stream) {
   rank_metrics_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(topk_ids, M, k, ld, labels, counters);
+  note_launches(1);
   B4CP_LAUNCH_CHECK();
   return 0;
 }
@@ -273,12 +277,14 @@ extern "C" int b4cp_adam_step(float* theta, const float* grad, float* m, float* 
   adam_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(theta, grad, m, v, n, lr, beta1, beta2,
                                                         eps, step_dev, step_host, grad_scale,
                                                         (__nv_bfloat16*)shadow_bf16, cols, ld_shadow);
+  note_launches(1);
   B4CP_LAUNCH_CHECK();
   return 0;
 }
 
 extern "C" int b4cp_step_increment(int* step_dev, void* stream) {
   step_increment_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev);
+  note_launches(1);
   B4CP_LAUNCH_CHECK();
   return 0;
 }
@@ -287,6 +293,7 @@ extern "C" int b4cp_sigmoid(const float* z, float* out, long n, void* stream) {
   if (n == 0) return 0;
   const int blocks = (int)std::min<long>(ceil_div(n, 256), 148L * 16);
   sigmoid_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(z, out, n);
+  note_launches(1);
   B4CP_LAUNCH_CHECK();
   return 0;
 }
@@ -295,6 +302,7 @@ extern "C" int b4cp_clip_log(const float* p, float* out, long n, float lo, float
   if (n == 0) return 0;
   const int blocks = (int)std::min<long>(ceil_div(n, 256), 148L * 16);
   clip_log_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(p, out, n, lo, hi);
+  note_launches(1);
   B4CP_LAUNCH_CHECK();
   return 0;
 }
@@ -303,6 +311,7 @@ extern "C" int b4cp_masked_bce(const float* y_true, const float* probs, long n, 
                                float pos_weight, int use_pos_weight, float* stats, void* stream) {
   masked_bce_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(y_true, probs, n, label_pad, pos_weight,
                                                           use_pos_weight, stats);
+  note_launches(1);
   B4CP_LAUNCH_CHECK();
   return 0;
 }

@@ -153,6 +153,7 @@ extern "C" int b4cp_topk_rows(const float* scores, long ld, long rows, int V, in
   while ((1L << idbits) < V) ++idbits;
   topk_rows_kernel<<<(unsigned)rows, TK_THREADS, 0, (cudaStream_t)stream>>>(
       scores, ld, V, k, idbits, out_ids, out_scores, ld_out);
+  note_launches(1);
   B4CP_LAUNCH_CHECK();
   return 0;
 }

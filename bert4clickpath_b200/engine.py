@@ -357,7 +357,9 @@ class VocabOutputEngine:
         if M * Vp * 4 > self.MATERIALIZE_LIMIT_BYTES:
             raise MemoryError(f"refusing to materialise {M}x{self.V} logits; use the fused path")
         z = self.pool.get("logits", (M, Vp))
+        t0 = ops.TIMER.begin("vocab_gemm")
         dense_fwd(ab, self.h, self.W, self.b, M, out_f32=z)
+        ops.TIMER.end("vocab_gemm", t0)
         return z
 
     def probabilities(self, ab, M):
@@ -387,12 +389,16 @@ class VocabOutputEngine:
         ab, M, V, h = sv["ab"], sv["M"], self.V, self.h
         dz = self.pool.get("dz", (M, ld8(V)), BF16)
         ops.ce_rows_grad(sv["z"], V, sv["labels"], sv["lse"], loss_stats, dz, None)
+        t0 = ops.TIMER.begin("vocab_gemm")
         ops.gemm_splitk(ab, 1, dz, 1, h, V, M, self.W.g, ws_name="splitk_vocab")
+        ops.TIMER.end("vocab_gemm", t0)
         ops.colsum_bf16(dz, M, V, self.b.g)
         # dx = dz W^T : K = V is long and M x h is small -> split-K with a gated reduce
         splits = ops.gemm_splits_for(M, h, V)
         part = ops.WS.get("splitk_dx", splits * M * h * 4).view(F32)[: splits * M * h].view(splits, M, h)
+        t0 = ops.TIMER.begin("vocab_gemm")
         ops.gemm(dz, 0, self.W.wb, 0, M, h, V, out_f32=part, splits=splits)
+        ops.TIMER.end("vocab_gemm", t0)
         ops.reduce_splits_ex(part, M, h, gate, out_f32, out_bf16)
 
     def topk(self, ab, M, k):

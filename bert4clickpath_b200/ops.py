@@ -51,6 +51,38 @@ class Workspace:
 WS = Workspace()
 
 
+class KernelTimer:
+    """CUDA-event brackets around selected launches on the current stream (bench.py roofline)."""
+
+    def __init__(self):
+        self.enabled = False
+        self.events = {}
+
+    def begin(self, tag):
+        if not self.enabled:
+            return None
+        e0 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        return e0
+
+    def end(self, tag, e0):
+        if e0 is None:
+            return
+        e1 = torch.cuda.Event(enable_timing=True)
+        e1.record()
+        self.events.setdefault(tag, []).append((e0, e1))
+
+    def totals_ms(self):
+        """{tag: (total ms, launches)} — call after a synchronize."""
+        return {t: (sum(a.elapsed_time(b) for a, b in ev), len(ev)) for t, ev in self.events.items()}
+
+    def reset(self):
+        self.events = {}
+
+
+TIMER = KernelTimer()
+
+
 # ------------------------------------------------------------------------------------ GEMM
 def gemm(A, a_mn, B, b_mn, M, N, K, *, bias=None, relu=False, gate=None, addend=None,
          out_f32=None, out_bf16=None, alpha=1.0, splits=1, lda=None, ldb=None):

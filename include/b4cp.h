@@ -29,6 +29,8 @@ extern "C" {
 
 const char* b4cp_last_error(void);
 int b4cp_version(void);
+/* number of CUDA kernels launched by this library since load (all threads) */
+long b4cp_launch_count(void);
 /* fails (<0) unless the current device is compute capability 10.x */
 int b4cp_device_check(void);
 

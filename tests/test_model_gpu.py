@@ -5,13 +5,23 @@ import pytest
 import torch
 
 from oracle import clickpath_oracle as O
+from oracle.mixed_precision import cloze_train_step_bf16
 from tests.test_oracle import make_tiny_problem
 
 pytestmark = pytest.mark.gpu
 
-# bf16 tensor-core operands with fp32 accumulation: gradients are compared on the max-norm of
-# each tensor; 3e-2 covers two encoder layers + a 3-layer head at d_model = 8..64.
-BF16_TOL = 3e-2
+# Two bars (DESIGN.md "Numerics"):
+#  * KERNEL_TOL — CUDA vs the oracle with bf16 rounding applied at the points where the pipeline
+#    stores bf16 (oracle/mixed_precision.py): the kernels compute what they claim.  The only
+#    differences are fp32-vs-float64 accumulation and rare 1-ulp bf16 rounding flips.
+#  * BF16_TOL — CUDA vs the exact float64 oracle: the bf16-operand approximation itself, on the
+#    max-norm of each gradient tensor (tiny batches at random init are the worst case because the
+#    gradients are sums with heavy cancellation).
+#    A 1-ulp bf16 flip upstream can flip a ReLU gate downstream, which changes single gradient
+#    entries discontinuously in ANY two implementations; the kernel bar is therefore measured in
+#    the Frobenius norm (kernel-by-kernel max-norm parity is in test_kernels_gpu.py).
+KERNEL_TOL = 2e-2
+BF16_TOL = 6e-2
 
 
 def build_model(P, dims, L, H, dff, head_dims, V, dropout=0.0, rows2=20):
@@ -30,13 +40,14 @@ def build_model(P, dims, L, H, dff, head_dims, V, dropout=0.0, rows2=20):
 
 
 def rel_err(got, want, floor=0.0):
-    """max-norm error relative to the tensor's own scale (or `floor` for tensors whose true
-    gradient is ~0, e.g. the key bias, to which softmax attention is invariant)."""
-    return np.abs(got - want).max() / max(np.abs(want).max(), floor, 1e-12)
+    """Frobenius-norm error relative to the tensor's own RMS scale (or `floor` for tensors whose
+    true gradient is ~0, e.g. the key bias, to which softmax attention is invariant)."""
+    n = np.sqrt(got.size)
+    return (np.linalg.norm(got - want) / n) / max(np.linalg.norm(want) / n, floor, 1e-12)
 
 
 def grad_floor(G):
-    return 1e-2 * max(np.abs(v).max() for v in G.values())
+    return 1e-2 * max(np.linalg.norm(v) / np.sqrt(v.size) for v in G.values())
 
 
 @pytest.mark.parametrize("dims", [(8,), (8, 8)])
@@ -52,11 +63,14 @@ def test_cloze_forward_backward_matches_oracle(cuda_lib, dims):
     stats = model.cloze_forward_backward(dev_ids, lab, B, S, n_masked=n_masked, training=False)
     torch.cuda.synchronize()
     loss, G, ex = O.cloze_train_step(ids_list, labels, P, L, H, pe, np.float64)
+    eloss, EG, _ = cloze_train_step_bf16(ids_list, labels, P, L, H, pe)
     s = stats.cpu().numpy()
     assert s[1] == ex["n_valid"]
     assert abs(s[0] / s[1] - loss) < 2e-2 * abs(loss)
+    assert abs(s[0] / s[1] - eloss) < 1e-4 * abs(eloss)
     got = to_reference_layout(model.store.get_grads())
     for k in sorted(G):
+        assert rel_err(got[k], EG[k], grad_floor(G)) < KERNEL_TOL, (k, rel_err(got[k], EG[k], grad_floor(G)))
         assert rel_err(got[k], G[k], grad_floor(G)) < BF16_TOL, (k, rel_err(got[k], G[k], grad_floor(G)))
     # PAD rows of the item table get exactly zero gradient (dead compute)
     assert not np.abs(got["emb.0"][0]).any() or (ids_list[0] == 0).any()
@@ -113,10 +127,13 @@ def test_dropout_training_step_matches_oracle_with_exported_masks(cuda_lib):
     stats = model.cloze_forward_backward(dev_ids, lab, B, S, n_masked=int((labels >= 0).sum()),
                                          training=True, seed=seed)
     loss, G, ex = O.cloze_train_step(ids_list, labels, P, L, H, pe, np.float64, masks)
+    eloss, EG, _ = cloze_train_step_bf16(ids_list, labels, P, L, H, pe, masks)
     s = stats.cpu().numpy()
     assert abs(s[0] / s[1] - loss) < 2e-2 * abs(loss)
+    assert abs(s[0] / s[1] - eloss) < 1e-4 * abs(eloss)
     got = to_reference_layout(model.store.get_grads())
     for k in sorted(G):
+        assert rel_err(got[k], EG[k], grad_floor(G)) < KERNEL_TOL, (k, rel_err(got[k], EG[k], grad_floor(G)))
         assert rel_err(got[k], G[k], grad_floor(G)) < BF16_TOL, (k, rel_err(got[k], G[k], grad_floor(G)))
 
 
@@ -147,3 +164,37 @@ def test_three_adam_steps_track_oracle(cuda_lib):
         big = np.abs(want) > 2e-3
         if big.any():
             assert (np.sign(moved[big]) == np.sign(want[big])).mean() > 0.97, k
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(V=300, d=32, L=2, H=2, dff=100, hd=[64, 32], B=16, max_len=20, lengths="beauty", mp=0.4),
+    dict(V=1000, d=64, L=2, H=2, dff=100, hd=[128, 64], B=64, max_len=50, lengths="dense", mp=0.15),
+    dict(V=500, d=128, L=1, H=4, dff=100, hd=[], B=32, max_len=30, lengths="beauty", mp=0.4),
+])
+def test_kernels_match_bf16_emulation_on_c1_like_shapes(cuda_lib, cfg):
+    """Ragged (beauty-shaped) and dense sessions, dff=100 (not a multiple of 8), heads with and
+    without an MLP: CUDA == oracle-with-bf16-rounding to KERNEL_TOL on every gradient tensor."""
+    import bert4clickpath_b200 as bc
+    from bert4clickpath_b200.synthetic import make_cloze_batch
+    from bert4clickpath_b200.weights import to_reference_layout
+    V, d, L, H = cfg["V"], cfg["d"], cfg["L"], cfg["H"]
+    head = bc.SoftMaxHead(dense_layer_dims=cfg["hd"], output_vocab_size=V)
+    model = bc.ClickstreamTransformer(
+        sequential_input_config={"items": ["asin"]}, feature_vocabs={"items": V},
+        embedding_dims={"items": d}, head_unit=head, value_to_head=bc.INPUT_MASKING_TOKEN,
+        num_encoder_layers=L, num_attention_heads=H, dropout_rate=0.0, encoder_ff_dim=cfg["dff"])
+    batch = make_cloze_batch(np.random.default_rng(0), cfg["B"], V, max_len=cfg["max_len"],
+                             mode="train", masked_percentage=cfg["mp"], lengths=cfg["lengths"])
+    ids = torch.from_numpy(batch["ids"]).cuda().view(-1)
+    labels = torch.from_numpy(batch["labels"]).cuda()
+    B, S = batch["ids"].shape
+    stats = model.cloze_forward_backward([ids], labels, B, S, n_masked=batch["n_masked"],
+                                         training=False).cpu().numpy()
+    P = {k: v.astype(np.float64) for k, v in to_reference_layout(model.store.get_weights()).items()}
+    pe = O.positional_encoding(10000, d)
+    eloss, EG, _ = cloze_train_step_bf16([batch["ids"].astype(np.int64)], batch["labels"], P, L, H, pe)
+    assert abs(stats[0] / stats[1] - eloss) < 1e-4 * abs(eloss)
+    got = to_reference_layout(model.store.get_grads())
+    floor = grad_floor(EG)
+    for k in sorted(EG):
+        assert rel_err(got[k], EG[k], floor) < KERNEL_TOL, (k, rel_err(got[k], EG[k], floor))
