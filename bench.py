@@ -50,7 +50,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -289,7 +289,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=1024, help="per-GPU batch (sequences)")
+    ap.add_argument("--batch", type=int, default=4096, help="per-GPU batch (sequences)")
     ap.add_argument("--cpu-batch", type=int, default=64, help="batch of the CPU reference sample")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

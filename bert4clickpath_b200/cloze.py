@@ -51,7 +51,7 @@ class ClozeMaskedLoss:
         if isinstance(y_pred, ClozeOutput):
             labels, _, _ = _compact(y_true, y_pred)
             stats = torch.empty(2, dtype=F32, device="cuda")
-            y_pred.head.vocab.loss_forward(y_pred.ab, y_pred.M, labels, stats)
+            y_pred.head.vocab.loss_forward(y_pred.ab, y_pred.M, labels, stats, need_grad=False)
             s = stats.cpu().numpy()
             return float(s[0] / s[1]) if s[1] > 0 else 0.0
         yt, yp = cloze_output_adaptor(y_true, y_pred)

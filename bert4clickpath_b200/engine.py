@@ -372,12 +372,26 @@ class VocabOutputEngine:
         ops.ce_rows_grad(z, self.V, None, lse, None, None, probs)
         return probs
 
-    def loss_forward(self, ab, M, labels, loss_stats):
+    @property
+    def fused(self):
+        """The tcgen05 fused projection + CE kernels cover h = 128 (forward and backward)."""
+        return self.h == 128 and not self.force_materialized
+
+    force_materialized = False
+
+    def loss_forward(self, ab, M, labels, loss_stats, need_grad=True):
         """loss_stats <- (sum over valid rows of lse - z_t, number of valid rows)."""
-        z = self.logits(ab, M)
         lse = self.pool.get("lse", (M,))
         tgt = self.pool.get("tgt", (M,))
-        ops.ce_rows_stats(z, self.V, labels, lse, tgt)
+        if self.fused:
+            t0 = ops.TIMER.begin("vocab_ce")
+            ops.vocab_ce_fwd(ab, M, self.h, self.W.wb, self.b.w, self.V, labels, lse, tgt,
+                             want_dx=need_grad)
+            ops.TIMER.end("vocab_ce", t0)
+            z = None
+        else:
+            z = self.logits(ab, M)
+            ops.ce_rows_stats(z, self.V, labels, lse, tgt)
         ops.ce_loss_reduce(lse, tgt, labels, loss_stats)
         self.saved = dict(ab=ab, M=M, labels=labels, z=z, lse=lse)
 
@@ -387,6 +401,13 @@ class VocabOutputEngine:
         produced ab, or None) as fp32 and/or bf16."""
         sv = self.saved
         ab, M, V, h = sv["ab"], sv["M"], self.V, self.h
+        if sv["z"] is None:  # fused: logits are recomputed tile by tile, never materialised
+            t0 = ops.TIMER.begin("vocab_ce")
+            ops.vocab_ce_dx(M, h, V, sv["labels"], loss_stats, self.W.wb, gate, out_f32, out_bf16)
+            ops.vocab_ce_bwd(ab, M, h, self.W.wb, self.b.w, V, sv["labels"], sv["lse"], loss_stats,
+                             self.W.g, self.b.g)
+            ops.TIMER.end("vocab_ce", t0)
+            return
         dz = self.pool.get("dz", (M, ld8(V)), BF16)
         ops.ce_rows_grad(sv["z"], V, sv["labels"], sv["lse"], loss_stats, dz, None)
         t0 = ops.TIMER.begin("vocab_gemm")

@@ -351,3 +351,30 @@ def masked_bce(y_true, probs, label_pad, pos_weight=None):
            L.c_float(label_pad), L.c_float(pos_weight if pos_weight is not None else 1.0),
            L.c_int(0 if pos_weight is None else 1), L.ptr(stats), L.stream_ptr())
     return stats
+
+
+def _vocab_ws(M, V, h):
+    fn = L.lib().b4cp_vocab_ce_workspace_bytes
+    fn.restype = ctypes.c_long
+    return WS.get("vocab_ce", fn(ctypes.c_long(M), ctypes.c_int(V), ctypes.c_int(h)))
+
+
+def vocab_ce_fwd(xb, M, h, wb, bias, V, labels, lse, tgt, want_dx=False):
+    ws = _vocab_ws(M, V, h)
+    L.call("b4cp_vocab_ce_fwd", L.ptr(xb), L.c_long(xb.stride(0)), L.c_long(M), L.c_int(h),
+           L.ptr(wb), L.c_long(wb.stride(0)), L.ptr(bias), L.c_int(V), L.ptr(labels),
+           L.c_int(1 if want_dx else 0), L.ptr(lse), L.ptr(tgt), L.ptr(ws), L.stream_ptr())
+
+
+def vocab_ce_dx(M, h, V, labels, loss_stats, wb, gate=None, out_f32=None, out_bf16=None):
+    ws = _vocab_ws(M, V, h)
+    L.call("b4cp_vocab_ce_dx", L.c_long(M), L.c_int(h), L.c_int(V), L.ptr(labels),
+           L.ptr(loss_stats), L.ptr(wb), L.c_long(wb.stride(0)), L.ptr(gate),
+           L.c_long(gate.stride(0) if gate is not None else 0), L.ptr(out_f32), L.ptr(out_bf16),
+           L.c_long(out_bf16.stride(0) if out_bf16 is not None else 0), L.ptr(ws), L.stream_ptr())
+
+
+def vocab_ce_bwd(xb, M, h, wb, bias, V, labels, lse, loss_stats, dW, db):
+    L.call("b4cp_vocab_ce_bwd", L.ptr(xb), L.c_long(xb.stride(0)), L.c_long(M), L.c_int(h),
+           L.ptr(wb), L.c_long(wb.stride(0)), L.ptr(bias), L.c_int(V), L.ptr(labels), L.ptr(lse),
+           L.ptr(loss_stats), L.ptr(dW), L.ptr(db), L.stream_ptr())

@@ -170,6 +170,34 @@ int b4cp_ce_rows_grad(const float* logits, long ld, long M, int V, const int32_t
                       const float* lse, const float* loss_stats, void* dz_bf16, long ld_dz,
                       float* probs, long ld_probs, void* stream);
 
+/* ------------------------------------------------------------------ Cloze loss, FUSED (tcgen05)
+ * SoftMaxHead's Dense(V) + softmax + sparse categorical cross-entropy and its gradient without
+ * ever writing logits / probabilities / dlogits to HBM (head.py:36,45;
+ * examples/BERT4Rec/source/utils.py:116-134; losses.py:31-98, logits mode).
+ *   x_bf16: bf16 [M][ldx] head hidden states; w_bf16: bf16 [h][ldw] Keras (in, out) kernel;
+ *   bias: fp32 [V]; labels: int32 [M], -1 = padded row.
+ * fwd: lse[M] = log sum_v exp(x W + b), tgt[M] = logit of the label (0 for padded rows); feed
+ *      them to b4cp_ce_loss_reduce.  h in {64,128,192,256}.  With want_dx (h = 128) the kernel
+ *      also accumulates, flash-attention style, U = sum_v exp(z_v - max) W[:, v] per row with a
+ *      second tensor-core product per tile; the partials stay in `workspace`.
+ * dx : d(loss)/dx[M][h] = gate * (U / sum - W[:, label]) / n from the forward's workspace, with
+ *      n = loss_stats[1] (the global valid count); gate (bf16 [M][ld_gate], zero where <= 0) is
+ *      the ReLU output that produced x, or NULL.  Deterministic, no atomics.
+ * bwd: dW[h][V] = X^T dZ (fp32, accumulated in TMEM in a fixed order), db[V] = column sums of
+ *      dZ, with dZ = (softmax - onehot)/n on valid rows recomputed tile by tile.  h must be 128.
+ */
+long b4cp_vocab_ce_workspace_bytes(long M, int V, int h);
+int b4cp_vocab_ce_fwd(const void* x_bf16, long ldx, long M, int h, const void* w_bf16, long ldw,
+                      const float* bias, int V, const int32_t* labels, int want_dx, float* lse,
+                      float* tgt, void* workspace, void* stream);
+int b4cp_vocab_ce_dx(long M, int h, int V, const int32_t* labels, const float* loss_stats,
+                     const void* w_bf16, long ldw, const void* gate_bf16, long ld_gate,
+                     float* out_f32, void* out_bf16, long ld_bf16, const void* workspace,
+                     void* stream);
+int b4cp_vocab_ce_bwd(const void* x_bf16, long ldx, long M, int h, const void* w_bf16, long ldw,
+                      const float* bias, int V, const int32_t* labels, const float* lse,
+                      const float* loss_stats, float* dW, float* db, void* stream);
+
 /* Probability inputs (a materialised SoftMaxHead output): z = log(clip(p, lo, hi)) reproduces
  * K.sparse_categorical_crossentropy(from_logits=False) of TF 2.3 when followed by
  * b4cp_ce_rows_stats (losses.py:60 via examples/BERT4Rec/source/main.py:89). */
