@@ -1,0 +1,203 @@
+"""CPU-only checks (`-m "not gpu"`): the oracle against the committed golden vectors, the C-ABI
+library's exported symbols, host-side input preparation, synthetic data rules, and the
+data-parallel loss/gradient normalisation on a 2-rank gloo group."""
+import ctypes
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from oracle import clickpath_oracle as O
+from oracle.mixed_precision import bf16, cloze_train_step_bf16
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _load(name):
+    z = np.load(os.path.join(GOLD, name))
+    P = {k[2:]: z[k] for k in z.files if k.startswith("P/")}
+    G = {k[2:]: z[k] for k in z.files if k.startswith("G/")}
+    masks = None
+    mk = [k for k in z.files if k.startswith("mask/")]
+    if mk:
+        masks = {}
+        for k in mk:
+            n = k[5:]
+            masks["in" if n == "in" else tuple(int(t) for t in n.split("_"))] = z[k]
+    ids = [z[k] for k in sorted(f for f in z.files if f.startswith("ids"))]
+    return z, ids, P, G, masks
+
+
+@pytest.mark.parametrize("name", ["cloze_tiny_1feat.npz", "cloze_tiny_2feat_dropout.npz"])
+def test_oracle_reproduces_golden_cloze_step(name):
+    z, ids, P, G, masks = _load(name)
+    L, H = (int(v) for v in z["meta"])
+    pe = O.positional_encoding(10000, sum(P[f"emb.{f}"].shape[1] for f in range(len(ids))))
+    loss, G2, ex = O.cloze_train_step(ids, z["labels"], P, L, H, pe, np.float64, masks)
+    assert abs(loss - float(z["loss"])) < 1e-12
+    np.testing.assert_allclose(ex["enc_out"], z["enc_out"], rtol=1e-12, atol=1e-14)
+    for k in G:
+        np.testing.assert_allclose(G2[k], G[k], rtol=1e-10, atol=1e-14, err_msg=k)
+    x, _ = O.encoder_fwd(ids, P, L, H, pe, np.float64, masks)
+    sel, _ = O.select_masked(ids[0], x)
+    probs, _, _ = O.softmax_head_fwd(sel, O.head_layers(P), P["head.out.w"], P["head.out.b"])
+    np.testing.assert_allclose(probs, z["probs"], rtol=1e-12)
+    assert O.cloze_ndcg_update(z["labels"], probs.astype(np.float32), 5) == tuple(z["ndcg5"])
+    assert O.cloze_recall_update(z["labels"], probs.astype(np.float32), 5) == tuple(z["recall5"])
+    # the bf16-emulating variant stays within the stated bf16 tolerance of the exact oracle
+    eloss, EG, _ = cloze_train_step_bf16(ids, z["labels"], P, L, H, pe, masks)
+    assert abs(eloss - loss) < 2e-2 * abs(loss)
+
+
+def test_oracle_reproduces_golden_embed_and_topk():
+    z = np.load(os.path.join(GOLD, "embed_topk.npz"))
+    pe = O.positional_encoding(10000, 24)
+    assert pe[:9].tobytes() == z["pe_rows"].tobytes()
+    out = O.embed_fwd([z["ids0"], z["ids1"]], [z["t0"], z["t1"]], pe, np.float32)
+    assert out.tobytes() == z["out"].tobytes()  # bit-exact gather + scale + PE
+    assert O.top_k_ids(z["scores"], 10).tolist() == z["top10"].tolist()
+    assert z["top10"][2].tolist() == list(range(10))  # all-ties row: lowest ids first
+
+
+def test_bf16_rounding_helper_matches_torch():
+    import torch
+    a = np.random.default_rng(0).normal(size=1000).astype(np.float32) * 37
+    want = torch.from_numpy(a).to(torch.bfloat16).float().numpy()
+    np.testing.assert_array_equal(bf16(a).astype(np.float32), want)
+
+
+# --------------------------------------------------------------------------- C ABI
+def test_library_exports_every_declared_symbol():
+    from bert4clickpath_b200 import _lib
+    from bert4clickpath_b200.build import build_lib
+    build_lib(verbose=False)
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    names = _lib.declared_symbols()
+    assert len(names) >= 38
+    missing = [n for n in names if not hasattr(L, n)]
+    assert not missing, missing
+    L.b4cp_version.restype = ctypes.c_int
+    assert L.b4cp_version() == 1
+    L.b4cp_last_error.restype = ctypes.c_char_p
+    assert isinstance(L.b4cp_last_error(), bytes)
+    # pure host-side queries work without a GPU
+    L.b4cp_embed_bwd_workspace_bytes.restype = ctypes.c_long
+    assert L.b4cp_embed_bwd_workspace_bytes(ctypes.c_long(1000), ctypes.c_int(64)) > 0
+    L.b4cp_vocab_ce_workspace_bytes.restype = ctypes.c_long
+    assert L.b4cp_vocab_ce_workspace_bytes(ctypes.c_long(7168), ctypes.c_int(54293), ctypes.c_int(128)) > 0
+    assert L.b4cp_gemm_splits_for(64, 100, 200000) > 1
+
+
+def test_product_path_fails_loudly_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    import bert4clickpath_b200 as bc
+    with pytest.raises(Exception):
+        bc.ClickstreamTransformer(
+            sequential_input_config={"items": ["asin"]}, feature_vocabs={"items": 50},
+            embedding_dims={"items": 8}, head_unit=bc.SoftMaxHead([8], 50),
+            value_to_head=bc.INPUT_MASKING_TOKEN)
+
+
+# --------------------------------------------------------------------------- host logic
+def test_input_prep_chains_strings_and_ids_like_the_reference():
+    from bert4clickpath_b200.clickstream_transformer import StaticVocabularyTable, TransformerInputPrep
+    from bert4clickpath_b200.constants import RESERVED_TOKENS
+    prep = TransformerInputPrep({"items": ["s_items", "b_items"], "events": ["s_ev", "b_ev"]})
+    feats = {
+        "s_items": np.array([["a", "b", "[PAD]"], ["c", "[MASK]", "zzz"]], dtype=object),
+        "b_items": np.array([["d"], ["[PAD]"]], dtype=object),
+        "s_ev": np.array([["v", "v", "[PAD]"], ["v", "w", "v"]], dtype=object),
+        "b_ev": np.array([["w"], ["[PAD]"]], dtype=object),
+        "instance": np.array([1, 2]),
+    }
+    out, starts, ends = prep(feats)
+    assert set(out) == {"items", "events", "instance"}
+    assert out["items"][0].tolist() == ["[CLS]", "[SEP]", "a", "b", "[PAD]", "[SEP]", "d", "[SEP]"]
+    assert starts.tolist() == [0, 2, 6] and ends.tolist() == [1, 5, 7]
+    table = StaticVocabularyTable(RESERVED_TOKENS + ["a", "b", "c", "d"])
+    assert table.size() == 15
+    ids = table.lookup(out["items"])
+    assert ids[1].tolist() == [3, 4, 12, 1, 14, 4, 0, 4]  # zzz -> OOV bucket 14, [MASK] -> 1
+    want = O.chain_sequences([O.lookup_ids(feats["s_items"], ["a", "b", "c", "d"]),
+                              O.lookup_ids(feats["b_items"], ["a", "b", "c", "d"])])
+    assert ids.tolist() == want.tolist()
+
+
+def test_model_constructor_contract():
+    import bert4clickpath_b200 as bc
+    with pytest.raises(AssertionError):
+        bc.ClickstreamTransformer({"items": ["a"]}, {"items": 10}, {"items": 8}, bc.SoftMaxHead([], 10))
+    with pytest.raises(AssertionError):
+        bc.ClickstreamTransformer({"items": ["a"]}, {"items": 10}, {"items": 8}, bc.SoftMaxHead([], 10),
+                                  segment_to_head=0, value_to_head="[MASK]")
+    with pytest.raises(AssertionError):
+        bc.MaskedLoss(bc.binary_crossentropy, label_pad=1.0)
+    assert bc.ClozeMaskedNDCG(5).name == "NDCG_at_5" and bc.ClozeMaskedRecall(10).name == "Recall_at_10"
+
+
+def test_synthetic_cloze_batches_follow_the_reference_rules():
+    from bert4clickpath_b200.synthetic import make_cloze_batch, n_masked_for
+    assert n_masked_for(49, 0.15, 10) == 7 and n_masked_for(49, 0.4, 10) == 10
+    rng = np.random.default_rng(0)
+    b = make_cloze_batch(rng, 64, 1000, max_len=50, mode="train", masked_percentage=0.15)
+    assert b["ids"].shape == (64, 52) and b["labels"].shape == (64, 7) and b["n_masked"] == 64 * 7
+    assert (b["ids"][:, 0] == 3).all() and (b["ids"][:, 1] == 4).all() and (b["ids"][:, -1] == 4).all()
+    assert ((b["ids"] == 1).sum(1) == 7).all()
+    r = make_cloze_batch(rng, 200, 1000, max_len=50, mode="train", masked_percentage=0.4, lengths="beauty")
+    nmask = (r["ids"] == 1).sum(1)
+    assert ((r["labels"] >= 0).sum(1) == nmask).all() and nmask.max() <= 10
+    assert (r["ids"] == 0).any()  # interior pads before the trailing [SEP]
+    assert (r["ids"][np.arange(200), -1] == 4).all()
+    e = make_cloze_batch(rng, 32, 1000, max_len=50, mode="eval", lengths="beauty")
+    assert ((e["ids"] == 1).sum(1) == 1).all() and e["labels"].shape == (32, 1)
+
+
+# --------------------------------------------------------------------------- data parallel
+def _dp_worker(rank, world, port, q):
+    import torch.distributed as dist
+    import torch
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from tests.test_oracle import make_tiny_problem
+    ids_list, labels, P, L, H, pe, _ = make_tiny_problem(seed=3, B=6)
+    sl = slice(rank * 3, rank * 3 + 3)  # uneven numbers of masked positions per rank
+    ids_r, lab_r = [i[sl] for i in ids_list], labels[sl]
+    # local statistics, then the exchange ClickstreamTransformer.cloze_forward_backward performs:
+    # all-reduce (loss_sum, n_valid) BEFORE the backward so gradients are of the GLOBAL masked mean
+    loss_r, G_r, ex = O.cloze_train_step(ids_r, lab_r, P, L, H, pe, np.float64)
+    n_r = ex["n_valid"]
+    stats = torch.tensor([loss_r * n_r, float(n_r)], dtype=torch.float64)
+    dist.all_reduce(stats)
+    n_glob = stats[1].item()
+    flat = torch.from_numpy(np.concatenate([(G_r[k] * n_r / n_glob).reshape(-1) for k in sorted(G_r)]))
+    dist.all_reduce(flat)
+    if rank == 0:
+        q.put((stats[0].item() / n_glob, flat.numpy()))
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_data_parallel_equals_single_process():
+    import torch.multiprocessing as mp
+    from tests.test_oracle import make_tiny_problem
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    loss_dp, flat_dp = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    ids_list, labels, P, L, H, pe, _ = make_tiny_problem(seed=3, B=6)
+    loss, G, _ = O.cloze_train_step(ids_list, labels, P, L, H, pe, np.float64)
+    flat = np.concatenate([G[k].reshape(-1) for k in sorted(G)])
+    assert abs(loss_dp - loss) < 1e-12
+    np.testing.assert_allclose(flat_dp, flat, rtol=1e-9, atol=1e-13)
