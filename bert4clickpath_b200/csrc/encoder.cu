@@ -15,6 +15,13 @@ namespace b4cp {
 
 static constexpr int MAX_S = 256;
 
+// tensor-core path for S <= 128 and head depth 32 / 64 (attention_mma.cu)
+bool attention_mma_supported(int S, int dh);
+int attention_mma_fwd(const void* qkv, const int32_t* ids, int B, int S, int H, int dh, void* out,
+                      float* lse, cudaStream_t st);
+int attention_mma_bwd(const void* qkv, const void* dout, const float* lse, const int32_t* ids, int B,
+                      int S, int H, int dh, void* dqkv, cudaStream_t st);
+
 __device__ __forceinline__ float bf2f(__nv_bfloat16 v) { return __bfloat162float(v); }
 
 // cooperative load of one head's [S x dh] slice (row stride ld in global) into smem [S][dh+2]
@@ -388,6 +395,28 @@ reduce_partials_kernel(const float* __restrict__ partial, int P, long n, long st
   out[c] = s;
 }
 
+// same sum for MANY partials of FEW columns: one warp per column, lane l adds partials
+// l, l+32, ... in order, then a fixed-shape shuffle tree (still deterministic)
+__global__ void __launch_bounds__(256)
+reduce_partials_wide_kernel(const float* __restrict__ partial, int P, long n, long stride,
+                            float* __restrict__ out) {
+  const long c = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (c >= n) return;
+  const int lane = threadIdx.x & 31;
+  float s = 0.f;
+  for (int p = lane; p < P; p += 32) s += partial[(size_t)p * stride + c];
+  s = warp_sum(s);
+  if (lane == 0) out[c] = s;
+}
+
+static void launch_reduce_partials(const float* partial, int P, long n, long stride, float* out,
+                                   cudaStream_t st) {
+  if (P >= 64 && n <= 4096)
+    reduce_partials_wide_kernel<<<ceil_div(n, 8), 256, 0, st>>>(partial, P, n, stride, out);
+  else
+    reduce_partials_kernel<<<ceil_div(n, 256), 256, 0, st>>>(partial, P, n, stride, out);
+}
+
 // column sums of a bf16 matrix [T][ld] over rows -> partial[chunk][n]
 static constexpr int CS_ROWS = 512;
 __global__ void __launch_bounds__(256)
@@ -451,6 +480,13 @@ extern "C" int b4cp_attention_fwd(const void* qkv, const int32_t* ids_first, int
   B4CP_CHECK_ARG(S >= 1 && S <= MAX_S, "attention: S=%d must be in [1,%d]", S, MAX_S);
   B4CP_CHECK_ARG(dh % 2 == 0 && dh >= 2 && dh <= 128, "attention: head depth %d unsupported", dh);
   if (B == 0) return 0;
+  if (attention_mma_supported(S, dh)) {
+    int rc = attention_mma_fwd(qkv, ids_first, B, S, H, dh, out, lse, (cudaStream_t)stream);
+    if (rc) return rc;
+    note_launches(1);
+    B4CP_LAUNCH_CHECK();
+    return 0;
+  }
   const int threads = S <= 64 ? 128 : 256;
   const size_t smem = attn_smem_fwd(S, dh, threads);
   B4CP_CHECK_ARG(smem <= 227 * 1024, "attention: S=%d dh=%d needs %zu B smem", S, dh, smem);
@@ -469,6 +505,13 @@ extern "C" int b4cp_attention_bwd(const void* qkv, const void* dout, const float
   B4CP_CHECK_ARG(S >= 1 && S <= MAX_S, "attention: S=%d must be in [1,%d]", S, MAX_S);
   B4CP_CHECK_ARG(dh % 2 == 0 && dh >= 2 && dh <= 128, "attention: head depth %d unsupported", dh);
   if (B == 0) return 0;
+  if (attention_mma_supported(S, dh)) {
+    int rc = attention_mma_bwd(qkv, dout, lse, ids_first, B, S, H, dh, dqkv, (cudaStream_t)stream);
+    if (rc) return rc;
+    note_launches(1);
+    B4CP_LAUNCH_CHECK();
+    return 0;
+  }
   const int threads = S <= 64 ? 128 : 256;
   const size_t smem = attn_smem_bwd(S, dh, threads);
   B4CP_CHECK_ARG(smem <= 227 * 1024, "attention bwd: S=%d dh=%d needs %zu B smem", S, dh, smem);
@@ -496,7 +539,7 @@ extern "C" int b4cp_residual_ln_fwd(const float* x, const float* r, long T, int 
   return 0;
 }
 
-static constexpr int LN_BWD_BLOCKS = 148 * 4;
+static constexpr int LN_BWD_BLOCKS = 148 * 16;
 
 extern "C" long b4cp_residual_ln_bwd_workspace_bytes(int d) {
   return (long)LN_BWD_BLOCKS * 3 * d * sizeof(float);
@@ -515,11 +558,10 @@ extern "C" int b4cp_residual_ln_bwd(const float* dy, const float* x, const float
   residual_ln_bwd_kernel<<<blocks, 256, 0, st>>>(dy, x, r, T, d, gamma,
                                                  make_drop(dropout_rate, seed, site), 1e-6f, dx,
                                                  (__nv_bfloat16*)dr_bf16, ld_bf16, partial);
-  const int rb = ceil_div(d, 256);
   note_launches(1 + (dgamma ? 1 : 0) + (dbeta ? 1 : 0) + (dbias ? 1 : 0));
-  if (dgamma) reduce_partials_kernel<<<rb, 256, 0, st>>>(partial, blocks, d, 3L * d, dgamma);
-  if (dbeta) reduce_partials_kernel<<<rb, 256, 0, st>>>(partial + d, blocks, d, 3L * d, dbeta);
-  if (dbias) reduce_partials_kernel<<<rb, 256, 0, st>>>(partial + 2 * d, blocks, d, 3L * d, dbias);
+  if (dgamma) launch_reduce_partials(partial, blocks, d, 3L * d, dgamma, st);
+  if (dbeta) launch_reduce_partials(partial + d, blocks, d, 3L * d, dbeta, st);
+  if (dbias) launch_reduce_partials(partial + 2 * d, blocks, d, 3L * d, dbias, st);
   B4CP_LAUNCH_CHECK();
   return 0;
 }
@@ -539,7 +581,7 @@ extern "C" int b4cp_colsum_bf16(const void* in, long T, int n, long ld, float* o
   const int chunks = ceil_div(T, CS_ROWS);
   dim3 grid(chunks, ceil_div(n, 64));
   colsum_partial_kernel<<<grid, 256, 0, st>>>((const __nv_bfloat16*)in, T, n, ld, (float*)workspace);
-  reduce_partials_kernel<<<ceil_div(n, 256), 256, 0, st>>>((const float*)workspace, chunks, n, n, out);
+  launch_reduce_partials((const float*)workspace, chunks, n, n, out, st);
   note_launches(2);
   B4CP_LAUNCH_CHECK();
   return 0;
@@ -547,8 +589,7 @@ extern "C" int b4cp_colsum_bf16(const void* in, long T, int n, long ld, float* o
 
 extern "C" int b4cp_reduce_splits(const float* partials, int splits, long n, long split_stride,
                                   float* out, void* stream) {
-  reduce_partials_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(partials, splits, n,
-                                                                             split_stride, out);
+  launch_reduce_partials(partials, splits, n, split_stride, out, (cudaStream_t)stream);
   note_launches(1);
   B4CP_LAUNCH_CHECK();
   return 0;

@@ -20,6 +20,38 @@ def bf16(a):
     return rounded.view(np.float32).astype(np.float64).reshape(np.shape(a))
 
 
+def _tensor_core_attention(S, dh):
+    """The CUDA attention uses mma.sync (bf16 P / dZ fragments) for S <= 128 and head depth
+    32 or 64, and fp32 SIMT math otherwise (csrc/attention_mma.cu vs csrc/encoder.cu)."""
+    return S <= 128 and dh in (32, 64)
+
+
+def _mha_fwd(qm, km, vm, pad, H):
+    o, att = O.mha_core_fwd(qm, km, vm, pad, H)
+    B, S, d = qm.shape
+    if _tensor_core_attention(S, d // H):
+        dh = d // H
+        o = (bf16(att["a"]) @ att["vh"]).transpose(0, 2, 1, 3).reshape(B, S, d)
+    return o, att
+
+
+def _mha_bwd(do_merged, att):
+    a, qh, kh, vh, H = att["a"], att["qh"], att["kh"], att["vh"], att["H"]
+    B, _, S, dh = qh.shape
+    if not _tensor_core_attention(S, dh):
+        return O.mha_core_bwd(do_merged, att)
+    d = H * dh
+    do = do_merged.reshape(B, S, H, dh).transpose(0, 2, 1, 3)
+    dv = bf16(a).transpose(0, 1, 3, 2) @ do
+    da = do @ vh.transpose(0, 1, 3, 2)
+    dz = bf16(a * (da - (da * a).sum(-1, keepdims=True)))
+    inv = 1.0 / np.sqrt(np.float32(dh)).astype(np.float64)
+    dq = (dz @ kh) * inv
+    dk = (dz.transpose(0, 1, 3, 2) @ qh) * inv
+    merge = lambda t: t.transpose(0, 2, 1, 3).reshape(B, S, d)
+    return merge(dq), merge(dk), merge(dv)
+
+
 def _layer_fwd(x, pad, p, H, drop1, drop2):
     q = bf16
     B, S, d = x.shape
@@ -27,7 +59,7 @@ def _layer_fwd(x, pad, p, H, drop1, drop2):
     wq = np.concatenate([p["wq"], p["wk"], p["wv"]], axis=1)
     bq = np.concatenate([p["bq"], p["bk"], p["bv"]])
     qkv = q(xb @ q(wq) + bq)
-    o, att = O.mha_core_fwd(qkv[..., :d], qkv[..., d:2 * d], qkv[..., 2 * d:], pad, H)
+    o, att = _mha_fwd(qkv[..., :d], qkv[..., d:2 * d], qkv[..., 2 * d:], pad, H)
     ob = q(o)
     y1 = ob @ q(p["wo"]) + p["bo"]
     r1 = x + (y1 * drop1 if drop1 is not None else y1)
@@ -61,7 +93,7 @@ def _layer_bwd(dx2, c, p):
     dy1b = q(dy1)
     g["wo"] = f2(c["ob"]).T @ f2(dy1b)
     dob = q(dy1b @ q(p["wo"]).T)
-    dq, dk, dv = O.mha_core_bwd(dob, c["att"])
+    dq, dk, dv = _mha_bwd(dob, c["att"])
     dqkvb = q(np.concatenate([dq, dk, dv], axis=-1))
     wqkv = np.concatenate([p["wq"], p["wk"], p["wv"]], axis=1)
     gw = f2(c["xb"]).T @ f2(dqkvb)
