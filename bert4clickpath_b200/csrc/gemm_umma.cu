@@ -10,6 +10,8 @@
 // One CTA = one 128 x BN output tile (x one K split).  Warp roles: warp 0 = TMA producer and
 // TMEM allocator, warp 1 = single-thread tcgen05.mma issuer, warps 2..5 = epilogue
 // (TMEM -> registers -> global).  A `stages`-deep mbarrier ring connects producer and issuer.
+#include <algorithm>
+
 #include "common.cuh"
 #include "../../include/b4cp.h"
 
@@ -29,6 +31,98 @@ struct GemmKernelParams {
   b4cp_gemm_epilogue ep;
 };
 
+// One 32-column chunk of one accumulator row: scale, bias, ReLU, ReLU-gate, residual add, stores.
+// `sbias` points at this chunk's 32 bias values staged in shared memory (zero past N), or NULL.
+__device__ __forceinline__ void epilogue_chunk(const b4cp_gemm_epilogue& ep, float* out_f32,
+                                               int row, int col0, int N, const uint32_t (&r)[32],
+                                               const float* sbias) {
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * ep.alpha;
+  const int ncol = min(32, N - col0);
+  if (sbias) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 b4 = *reinterpret_cast<const float4*>(sbias + j);
+      v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+    }
+  }
+  if (ep.relu) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+  }
+  if (ep.gate) {  // dY * [gate > 0]  (ReLU backward)
+    const __nv_bfloat16* g =
+        reinterpret_cast<const __nv_bfloat16*>(ep.gate) + (size_t)row * ep.ld_gate + col0;
+    if (ncol == 32 && ((reinterpret_cast<uintptr_t>(g) & 15) == 0)) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(g + j));
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          // bf16 > 0  <=>  sign bit clear and magnitude bits non-zero
+          if (!((w[k] & 0x8000u) == 0 && (w[k] & 0x7FFFu) != 0)) v[j + 2 * k] = 0.f;
+          if (!((w[k] & 0x80000000u) == 0 && (w[k] & 0x7FFF0000u) != 0)) v[j + 2 * k + 1] = 0.f;
+        }
+      }
+    } else {
+      for (int j = 0; j < ncol; ++j)
+        if (!(__bfloat162float(g[j]) > 0.f)) v[j] = 0.f;
+    }
+  }
+  if (ep.addend) {
+    const float* a = ep.addend + (size_t)row * ep.ld_addend + col0;
+    if (ncol == 32 && ((reinterpret_cast<uintptr_t>(a) & 15) == 0)) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 a4 = __ldg(reinterpret_cast<const float4*>(a + j));
+        v[j] += a4.x; v[j + 1] += a4.y; v[j + 2] += a4.z; v[j + 3] += a4.w;
+      }
+    } else {
+      for (int j = 0; j < ncol; ++j) v[j] += a[j];
+    }
+  }
+  if (out_f32) {
+    float* o = out_f32 + (size_t)row * ep.ld_f32 + col0;
+    if (ncol == 32 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4)
+        *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    } else {
+      for (int j = 0; j < ncol; ++j) o[j] = v[j];
+    }
+  }
+  if (ep.out_bf16) {
+    __nv_bfloat16* o =
+        reinterpret_cast<__nv_bfloat16*>(ep.out_bf16) + (size_t)row * ep.ld_bf16 + col0;
+    if (ncol == 32 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(v[j], v[j + 1]);
+        __nv_bfloat162 h1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
+        __nv_bfloat162 h2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]);
+        __nv_bfloat162 h3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
+        uint4 pk;
+        pk.x = *reinterpret_cast<uint32_t*>(&h0);
+        pk.y = *reinterpret_cast<uint32_t*>(&h1);
+        pk.z = *reinterpret_cast<uint32_t*>(&h2);
+        pk.w = *reinterpret_cast<uint32_t*>(&h3);
+        *reinterpret_cast<uint4*>(o + j) = pk;
+      }
+    } else {
+      for (int j = 0; j < ncol; ++j) o[j] = __float2bfloat16_rn(v[j]);
+    }
+  }
+}
+
+// bias of the CTA's N tile staged in shared memory (zero beyond N) by `nthreads` threads
+__device__ __forceinline__ void stage_bias_tile(float* sbias, const float* bias, int n0, int BN,
+                                                int N, int tid, int nthreads) {
+  for (int j = tid; j < BN; j += nthreads)
+    sbias[j] = (bias && n0 + j < N) ? __ldg(bias + n0 + j) : 0.f;
+}
+
 __global__ void __launch_bounds__(192, 1)
 gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const GemmKernelParams p) {
@@ -44,6 +138,8 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* empty_bar = full_bar + p.stages;
   uint64_t* tmem_full_bar = empty_bar + p.stages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  float* sbias = reinterpret_cast<float*>(
+      (reinterpret_cast<uintptr_t>(tmem_slot + 1) + 15) & ~static_cast<uintptr_t>(15));  // [BN]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -69,6 +165,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     mbar_init(tmem_full_bar, 1);
     fence_barrier_init();
   }
+  if (warp >= 2) stage_bias_tile(sbias, p.ep.bias, n0, BN, p.N, threadIdx.x - 64, 128);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -147,68 +244,156 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tmem_ld_wait();
       const int col0 = n0 + c0;
       if (!row_ok || col0 >= p.N) continue;
-      float v[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * ep.alpha;
-      const int ncol = min(32, p.N - col0);
-      if (ep.bias) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (j < ncol) v[j] += __ldg(ep.bias + col0 + j);
-      }
-      if (ep.relu) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-      }
-      if (ep.gate) {  // dY * [gate > 0]  (ReLU backward)
-        const __nv_bfloat16* g =
-            reinterpret_cast<const __nv_bfloat16*>(ep.gate) + (size_t)row * ep.ld_gate + col0;
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (j < ncol && !(__bfloat162float(g[j]) > 0.f)) v[j] = 0.f;
-      }
-      if (ep.addend) {
-        const float* a = ep.addend + (size_t)row * ep.ld_addend + col0;
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (j < ncol) v[j] += a[j];
-      }
-      if (out_f32) {
-        float* o = out_f32 + (size_t)row * ep.ld_f32 + col0;
-        if (ncol == 32 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        } else {
-          for (int j = 0; j < ncol; ++j) o[j] = v[j];
-        }
-      }
-      if (ep.out_bf16) {
-        __nv_bfloat16* o =
-            reinterpret_cast<__nv_bfloat16*>(ep.out_bf16) + (size_t)row * ep.ld_bf16 + col0;
-        if (ncol == 32 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            __nv_bfloat162 h0 = __floats2bfloat162_rn(v[j], v[j + 1]);
-            __nv_bfloat162 h1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
-            __nv_bfloat162 h2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]);
-            __nv_bfloat162 h3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
-            uint4 pk;
-            pk.x = *reinterpret_cast<uint32_t*>(&h0);
-            pk.y = *reinterpret_cast<uint32_t*>(&h1);
-            pk.z = *reinterpret_cast<uint32_t*>(&h2);
-            pk.w = *reinterpret_cast<uint32_t*>(&h3);
-            *reinterpret_cast<uint4*>(o + j) = pk;
-          }
-        } else {
-          for (int j = 0; j < ncol; ++j) o[j] = __float2bfloat16_rn(v[j]);
-        }
-      }
+      epilogue_chunk(ep, out_f32, row, col0, p.N, r, ep.bias ? sbias + c0 : nullptr);
     }
     tc_fence_before();
   }
   __syncthreads();
   if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------ persistent variant
+// Skinny products (one N tile, K <= 192: every Dense of the encoder and most of the head MLP at
+// large row counts) are HBM-bound and, one tile per CTA, dominated by per-CTA set-up.  Here a CTA
+// keeps the whole B operand resident in shared memory, streams 128-row A tiles through a 2-stage
+// ring and ping-pongs two TMEM accumulators so the epilogue of tile i overlaps the loads and MMAs
+// of tile i+1.  8 epilogue warps: warp w drains TMEM lanes 32*(w%4).. and column half w/4.
+static constexpr int PERSIST_MAX_KT = 3;
+
+__global__ void __launch_bounds__(320, 1)
+gemm_umma_persistent_kernel(const __grid_constant__ CUtensorMap tmA,
+                            const __grid_constant__ CUtensorMap tmB, const GemmKernelParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  const int BN = p.BN, KT = p.k_tiles_total;
+  const int b_kt_bytes = BN * BK * 2;
+  const int a_stage_bytes = KT * A_STAGE_BYTES;
+  uint8_t* sB = smem;
+  uint8_t* sA = sB + (size_t)KT * b_kt_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sA + 2 * (size_t)a_stage_bytes);
+  uint64_t* b_full = bars;
+  uint64_t* a_full = bars + 1;    // [2]
+  uint64_t* a_empty = bars + 3;   // [2]
+  uint64_t* t_full = bars + 5;    // [2]
+  uint64_t* t_empty = bars + 7;   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  float* sbias = reinterpret_cast<float*>(bars + 12);  // [BN]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_mtiles = (p.M + BM - 1) / BM;
+  const int n_my = (n_mtiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  uint32_t tmem_cols = 32;
+  while ((int)tmem_cols < 2 * BN) tmem_cols <<= 1;
+  constexpr int WARP_TMA = 8, WARP_MMA = 9;  // single-thread roles at the highest warp ids
+
+  if (warp == WARP_TMA) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmA);
+      tma_prefetch_desc(&tmB);
+    }
+    tmem_alloc(tmem_slot, tmem_cols);
+    tmem_relinquish();
+  } else if (warp == WARP_MMA && lane == 0) {
+    mbar_init(b_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&a_full[i], 1);
+      mbar_init(&a_empty[i], 1);
+      mbar_init(&t_full[i], 1);
+      mbar_init(&t_empty[i], 256);
+    }
+    fence_barrier_init();
+  }
+  if (warp < 8) stage_bias_tile(sbias, p.ep.bias, 0, BN, p.N, threadIdx.x, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == WARP_TMA) {
+    if (lane == 0) {
+      mbar_expect_tx(b_full, (uint32_t)(KT * b_kt_bytes));
+      for (int kt = 0; kt < KT; ++kt) {
+        uint8_t* dst = sB + (size_t)kt * b_kt_bytes;
+        if (!p.b_mn) {
+          tma_load_2d(dst, &tmB, b_full, kt * BK, 0);
+        } else {
+          for (int h = 0; h < BN / 64; ++h)
+            tma_load_2d(dst + h * (64 * BK * 2), &tmB, b_full, h * 64, kt * BK);
+        }
+      }
+      for (int i = 0; i < n_my; ++i) {
+        const int st = i & 1;
+        const int m0 = ((int)blockIdx.x + i * (int)gridDim.x) * BM;
+        mbar_wait(&a_empty[st], ((i >> 1) & 1) ^ 1);
+        mbar_expect_tx(&a_full[st], (uint32_t)a_stage_bytes);
+        for (int kt = 0; kt < KT; ++kt) {
+          uint8_t* dst = sA + (size_t)st * a_stage_bytes + (size_t)kt * A_STAGE_BYTES;
+          if (!p.a_mn) {
+            tma_load_2d(dst, &tmA, &a_full[st], kt * BK, m0);
+          } else {
+            for (int h = 0; h < BM / 64; ++h)
+              tma_load_2d(dst + h * (64 * BK * 2), &tmA, &a_full[st], m0 + h * 64, kt * BK);
+          }
+        }
+      }
+    }
+  } else if (warp == WARP_MMA) {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(BM, BN, p.a_mn, p.b_mn);
+      const uint32_t a_lbo = p.a_mn ? 64 * BK * 2 : 16, b_lbo = p.b_mn ? 64 * BK * 2 : 16;
+      const uint32_t a_kstep = p.a_mn ? 2048 : 32, b_kstep = p.b_mn ? 2048 : 32;
+      mbar_wait(b_full, 0);
+      for (int i = 0; i < n_my; ++i) {
+        const int st = i & 1;
+        mbar_wait(&a_full[st], (i >> 1) & 1);
+        mbar_wait(&t_empty[st], ((i >> 1) & 1) ^ 1);
+        tc_fence_after();
+        for (int kt = 0; kt < KT; ++kt) {
+          const uint32_t aA = smem_u32(sA + (size_t)st * a_stage_bytes + (size_t)kt * A_STAGE_BYTES);
+          const uint32_t aB = smem_u32(sB + (size_t)kt * b_kt_bytes);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t da = umma_smem_desc(aA + k * a_kstep, a_lbo, 1024);
+            const uint64_t db = umma_smem_desc(aB + k * b_kstep, b_lbo, 1024);
+            umma_bf16(tmem_base + st * BN, da, db, idesc, (kt | k) ? 1u : 0u);
+          }
+        }
+        umma_commit(&a_empty[st]);
+        umma_commit(&t_full[st]);
+      }
+    }
+  } else {
+    const int q = warp & 3, half = warp >> 2;  // 8 epilogue warps
+    const b4cp_gemm_epilogue& ep = p.ep;
+    const int chunks = BN / 32;
+    const int c_begin = half * ((chunks + 1) / 2), c_end = half ? chunks : (chunks + 1) / 2;
+    for (int i = 0; i < n_my; ++i) {
+      const int st = i & 1;
+      const int row = ((int)blockIdx.x + i * (int)gridDim.x) * BM + q * 32 + lane;
+      mbar_wait(&t_full[st], (i >> 1) & 1);
+      tc_fence_after();
+      for (int c = c_begin; c < c_end; ++c) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(st * BN + c * 32), r);
+        tmem_ld_wait();
+        if (c == c_end - 1) {  // accumulator fully read: hand the TMEM buffer back early
+          tc_fence_before();
+          mbar_arrive(&t_empty[st]);
+        }
+        if (row < p.M && c * 32 < p.N)
+          epilogue_chunk(ep, ep.out_f32, row, c * 32, p.N, r, ep.bias ? sbias + c * 32 : nullptr);
+      }
+      if (c_begin >= c_end) {
+        tc_fence_before();
+        mbar_arrive(&t_empty[st]);
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == WARP_TMA) {
     tc_fence_after();
     tmem_dealloc(tmem_base, tmem_cols);
   }
@@ -304,7 +489,7 @@ extern "C" int b4cp_gemm_bf16(const void* A, int a_mn, long lda, const void* B, 
   if (stages > 6) stages = 6;
   if (stages > p.k_tiles_per_split) stages = p.k_tiles_per_split < 2 ? 2 : p.k_tiles_per_split;
   p.stages = stages;
-  const size_t smem = (size_t)stages * stage_bytes + (2 * stages + 1) * 8 + 16 + 1024;
+  const size_t smem = (size_t)stages * stage_bytes + (2 * stages + 1) * 8 + 64 + p.BN * 4 + 1024;
 
   CUtensorMap tmA, tmB;
   int rc;
@@ -319,6 +504,28 @@ extern "C" int b4cp_gemm_bf16(const void* A, int a_mn, long lda, const void* B, 
     rc = make_tmap_bf16_2d(&tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb * 2, 64, BK);
   if (rc) return rc;
 
+  // persistent row-streaming variant for skinny products
+  const int n_mtiles = ceil_div(M, BM);
+  if (splits == 1 && N <= p.BN && p.k_tiles_total <= PERSIST_MAX_KT && n_mtiles >= 148 &&
+      p.BN >= 32) {
+    const size_t psmem = (size_t)p.k_tiles_total * (p.BN * BK * 2) +
+                         2 * (size_t)p.k_tiles_total * A_STAGE_BYTES + 128 + p.BN * 4 + 1024;
+    if (psmem <= 227 * 1024) {
+      static bool pattr = false;
+      if (!pattr) {
+        B4CP_CUDA(cudaFuncSetAttribute(gemm_umma_persistent_kernel,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        pattr = true;
+      }
+      // two CTAs per SM when shared memory and TMEM (2*BN columns each) allow it
+      const int per_sm = (psmem <= 110 * 1024 && p.BN <= 128) ? 2 : 1;
+      const int grid = std::min(n_mtiles, 148 * per_sm);
+      gemm_umma_persistent_kernel<<<grid, 320, psmem, (cudaStream_t)stream>>>(tmA, tmB, p);
+      note_launches(1);
+      B4CP_LAUNCH_CHECK();
+      return 0;
+    }
+  }
   static bool attr_set = false;
   if (!attr_set) {
     B4CP_CUDA(cudaFuncSetAttribute(gemm_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -22,7 +22,10 @@ def bf16_round(a):
 @pytest.mark.parametrize("a_mn", [0, 1])
 @pytest.mark.parametrize("b_mn", [0, 1])
 @pytest.mark.parametrize("shape", [(128, 64, 64), (300, 200, 136), (77, 104, 72), (512, 1024, 512),
-                                   (1000, 100, 64), (130, 54293 % 1000 + 8, 128)])
+                                   (1000, 100, 64), (130, 54293 % 1000 + 8, 128),
+                                   # >= 148 row tiles and K <= 192: the persistent row-streaming kernel
+                                   (20000, 192, 64), (19001, 100, 64), (19000, 64, 104), (19500, 128, 192),
+                                   (19000, 24, 64)])
 def test_gemm_all_majors(cuda_lib, a_mn, b_mn, shape):
     from bert4clickpath_b200 import ops
     M, N, K = shape
@@ -66,6 +69,25 @@ def test_gemm_epilogues_and_splitk(cuda_lib):
     out3 = torch.empty((M, N), device="cuda")
     ops.gemm_splitk(Ad, 0, Bd, 1, M, N, K, out3)
     assert torch.equal(out2, out3)  # split-K reduction order is fixed
+    # the same epilogues through the persistent kernel (many row tiles, short K)
+    M, N, K = 19500, 100, 64
+    A = bf16_round(rng.normal(size=(M, K)))
+    B = bf16_round(rng.normal(size=(K, N)))
+    Bp = np.pad(B, ((0, 0), (0, 4)))
+    bias = rng.normal(size=N).astype(np.float32)
+    gate = bf16_round(rng.normal(size=(M, N)))
+    add = rng.normal(size=(M, N)).astype(np.float32)
+    ref = A.astype(np.float64) @ B.astype(np.float64)
+    Ad, Bd = dev(A, torch.bfloat16), dev(Bp, torch.bfloat16)
+    out = torch.empty((M, N), device="cuda")
+    outb = torch.zeros((M, ops.ld8(N)), device="cuda", dtype=torch.bfloat16)
+    ops.gemm(Ad, 0, Bd, 1, M, N, K, bias=dev(bias), relu=True, out_f32=out, out_bf16=outb)
+    want = np.maximum(ref + bias, 0)
+    np.testing.assert_allclose(out.cpu().numpy(), want, atol=3e-5 * np.abs(ref).max())
+    np.testing.assert_allclose(outb.float().cpu().numpy()[:, :N], want, rtol=1e-2, atol=1e-2)
+    gpad = np.pad(gate, ((0, 0), (0, 4)))
+    ops.gemm(Ad, 0, Bd, 1, M, N, K, gate=dev(gpad, torch.bfloat16), addend=dev(add), out_f32=out)
+    np.testing.assert_allclose(out.cpu().numpy(), ref * (gate > 0) + add, atol=3e-5 * np.abs(ref).max())
 
 
 # ------------------------------------------------------------------------------- embedding
