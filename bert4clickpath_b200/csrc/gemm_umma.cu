@@ -11,6 +11,7 @@
 // TMEM allocator, warp 1 = single-thread tcgen05.mma issuer, warps 2..5 = epilogue
 // (TMEM -> registers -> global).  A `stages`-deep mbarrier ring connects producer and issuer.
 #include <algorithm>
+#include <cstring>
 
 #include "common.cuh"
 #include "../../include/b4cp.h"
@@ -28,15 +29,15 @@ struct GemmKernelParams {
   int stages;
   int k_tiles_total;
   int k_tiles_per_split;
+  int tma_out_bf16, tma_out_f32;  // persistent kernel: outputs leave through TMA stores
   b4cp_gemm_epilogue ep;
 };
 
 // One 32-column chunk of one accumulator row: scale, bias, ReLU, ReLU-gate, residual add, stores.
 // `sbias` points at this chunk's 32 bias values staged in shared memory (zero past N), or NULL.
-__device__ __forceinline__ void epilogue_chunk(const b4cp_gemm_epilogue& ep, float* out_f32,
-                                               int row, int col0, int N, const uint32_t (&r)[32],
-                                               const float* sbias) {
-  float v[32];
+__device__ __forceinline__ void epilogue_math(const b4cp_gemm_epilogue& ep, int row, int col0,
+                                              int N, const uint32_t (&r)[32], const float* sbias,
+                                              float (&v)[32]) {
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * ep.alpha;
   const int ncol = min(32, N - col0);
@@ -83,6 +84,13 @@ __device__ __forceinline__ void epilogue_chunk(const b4cp_gemm_epilogue& ep, flo
       for (int j = 0; j < ncol; ++j) v[j] += a[j];
     }
   }
+}
+
+// direct (per-thread row) stores of one finished chunk
+__device__ __forceinline__ void epilogue_store_direct(const b4cp_gemm_epilogue& ep, float* out_f32,
+                                                      int row, int col0, int N,
+                                                      const float (&v)[32]) {
+  const int ncol = min(32, N - col0);
   if (out_f32) {
     float* o = out_f32 + (size_t)row * ep.ld_f32 + col0;
     if (ncol == 32 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
@@ -114,6 +122,14 @@ __device__ __forceinline__ void epilogue_chunk(const b4cp_gemm_epilogue& ep, flo
       for (int j = 0; j < ncol; ++j) o[j] = __float2bfloat16_rn(v[j]);
     }
   }
+}
+
+__device__ __forceinline__ void epilogue_chunk(const b4cp_gemm_epilogue& ep, float* out_f32,
+                                               int row, int col0, int N, const uint32_t (&r)[32],
+                                               const float* sbias) {
+  float v[32];
+  epilogue_math(ep, row, col0, N, r, sbias, v);
+  epilogue_store_direct(ep, out_f32, row, col0, N, v);
 }
 
 // bias of the CTA's N tile staged in shared memory (zero beyond N) by `nthreads` threads
@@ -263,9 +279,25 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 // of tile i+1.  8 epilogue warps: warp w drains TMEM lanes 32*(w%4).. and column half w/4.
 static constexpr int PERSIST_MAX_KT = 3;
 
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0,
+                                             int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
 __global__ void __launch_bounds__(320, 1)
 gemm_umma_persistent_kernel(const __grid_constant__ CUtensorMap tmA,
-                            const __grid_constant__ CUtensorMap tmB, const GemmKernelParams p) {
+                            const __grid_constant__ CUtensorMap tmB,
+                            const __grid_constant__ CUtensorMap tmOutB,
+                            const __grid_constant__ CUtensorMap tmOutF, const GemmKernelParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -274,7 +306,11 @@ gemm_umma_persistent_kernel(const __grid_constant__ CUtensorMap tmA,
   const int a_stage_bytes = KT * A_STAGE_BYTES;
   uint8_t* sB = smem;
   uint8_t* sA = sB + (size_t)KT * b_kt_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sA + 2 * (size_t)a_stage_bytes);
+  // per-epilogue-warp staging tiles for the TMA stores: fp32 32x32 (4 KB, 128B swizzle) and bf16
+  // 32x32 (2 KB, 64B swizzle)
+  uint8_t* sStageF = sA + 2 * (size_t)a_stage_bytes;
+  uint8_t* sStageB = sStageF + (p.tma_out_f32 ? 8 * 4096 : 0);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStageB + (p.tma_out_bf16 ? 8 * 2048 : 0));
   uint64_t* b_full = bars;
   uint64_t* a_full = bars + 1;    // [2]
   uint64_t* a_empty = bars + 3;   // [2]
@@ -370,9 +406,17 @@ gemm_umma_persistent_kernel(const __grid_constant__ CUtensorMap tmA,
     const b4cp_gemm_epilogue& ep = p.ep;
     const int chunks = BN / 32;
     const int c_begin = half * ((chunks + 1) / 2), c_end = half ? chunks : (chunks + 1) / 2;
+    uint8_t* stgF = sStageF + warp * 4096;
+    uint8_t* stgB = sStageB + warp * 2048;
+    const bool staged = p.tma_out_bf16 || p.tma_out_f32;
+    if (staged && lane == 0) {
+      if (p.tma_out_bf16) tma_prefetch_desc(&tmOutB);
+      if (p.tma_out_f32) tma_prefetch_desc(&tmOutF);
+    }
     for (int i = 0; i < n_my; ++i) {
       const int st = i & 1;
-      const int row = ((int)blockIdx.x + i * (int)gridDim.x) * BM + q * 32 + lane;
+      const int row0 = ((int)blockIdx.x + i * (int)gridDim.x) * BM + q * 32;
+      const int row = row0 + lane;
       mbar_wait(&t_full[st], (i >> 1) & 1);
       tc_fence_after();
       for (int c = c_begin; c < c_end; ++c) {
@@ -383,14 +427,64 @@ gemm_umma_persistent_kernel(const __grid_constant__ CUtensorMap tmA,
           tc_fence_before();
           mbar_arrive(&t_empty[st]);
         }
-        if (row < p.M && c * 32 < p.N)
-          epilogue_chunk(ep, ep.out_f32, row, c * 32, p.N, r, ep.bias ? sbias + c * 32 : nullptr);
+        if (c * 32 >= p.N || row0 >= p.M) continue;  // warp-uniform
+        const float* sb = ep.bias ? sbias + c * 32 : nullptr;
+        if (!staged) {
+          if (row < p.M) epilogue_chunk(ep, ep.out_f32, row, c * 32, p.N, r, sb);
+          continue;
+        }
+        float v[32];
+        if (row < p.M) {
+          epilogue_math(ep, row, c * 32, p.N, r, sb, v);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0.f;  // clipped by the TMA store anyway
+        }
+        // the previous store of this warp must have finished READING the staging tiles
+        if (lane == 0) tma_store_wait_read();
+        __syncwarp();
+        if (p.tma_out_f32) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k)  // 16-byte chunk k of the 128-byte row, 128B swizzle
+            *reinterpret_cast<float4*>(stgF + lane * 128 + ((k ^ (lane & 7)) << 4)) =
+                make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+        } else if (ep.out_f32 && row < p.M) {
+          b4cp_gemm_epilogue e2 = ep;
+          e2.out_bf16 = nullptr;
+          epilogue_store_direct(e2, ep.out_f32, row, c * 32, p.N, v);
+        }
+        if (p.tma_out_bf16) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {  // 16-byte chunk k of the 64-byte row, 64B swizzle
+            uint4 pk;
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(v[8 * k + 0], v[8 * k + 1]);
+            __nv_bfloat162 h1 = __floats2bfloat162_rn(v[8 * k + 2], v[8 * k + 3]);
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * k + 4], v[8 * k + 5]);
+            __nv_bfloat162 h3 = __floats2bfloat162_rn(v[8 * k + 6], v[8 * k + 7]);
+            pk.x = *reinterpret_cast<uint32_t*>(&h0);
+            pk.y = *reinterpret_cast<uint32_t*>(&h1);
+            pk.z = *reinterpret_cast<uint32_t*>(&h2);
+            pk.w = *reinterpret_cast<uint32_t*>(&h3);
+            *reinterpret_cast<uint4*>(stgB + lane * 64 + ((k ^ ((lane >> 1) & 3)) << 4)) = pk;
+          }
+        } else if (ep.out_bf16 && row < p.M) {
+          b4cp_gemm_epilogue e2 = ep;
+          epilogue_store_direct(e2, nullptr, row, c * 32, p.N, v);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          if (p.tma_out_f32) tma_store_2d(&tmOutF, stgF, c * 32, row0);
+          if (p.tma_out_bf16) tma_store_2d(&tmOutB, stgB, c * 32, row0);
+          tma_store_commit();
+        }
       }
       if (c_begin >= c_end) {
         tc_fence_before();
         mbar_arrive(&t_empty[st]);
       }
     }
+    if (staged && lane == 0) tma_store_wait_read();  // smem must outlive the last store's read
   }
   __syncthreads();
   if (warp == WARP_TMA) {
@@ -418,9 +512,20 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+int make_tmap_2d(CUtensorMap* map, CUtensorMapDataType dtype, CUtensorMapSwizzle swz,
+                 const void* base, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
+                 uint32_t box_inner, uint32_t box_outer);
+
 // 2-D bf16 tensor map, 128B swizzle, zero fill out of bounds.
 int make_tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer,
                       uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer) {
+  return make_tmap_2d(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_128B, base, inner,
+                      outer, row_stride_bytes, box_inner, box_outer);
+}
+
+int make_tmap_2d(CUtensorMap* map, CUtensorMapDataType dtype, CUtensorMapSwizzle swz,
+                 const void* base, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
+                 uint32_t box_inner, uint32_t box_outer) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) {
     set_last_error("cuTensorMapEncodeTiled entry point not available");
@@ -430,9 +535,9 @@ int make_tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64
   cuuint64_t strides[1] = {row_stride_bytes};
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims,
-                  strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = fn(map, dtype, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_last_error("cuTensorMapEncodeTiled failed (%d): base=%p inner=%llu outer=%llu stride=%llu",
                    (int)r, base, (unsigned long long)inner, (unsigned long long)outer,
@@ -508,8 +613,27 @@ extern "C" int b4cp_gemm_bf16(const void* A, int a_mn, long lda, const void* B, 
   const int n_mtiles = ceil_div(M, BM);
   if (splits == 1 && N <= p.BN && p.k_tiles_total <= PERSIST_MAX_KT && n_mtiles >= 148 &&
       p.BN >= 32) {
+    // outputs through TMA stores when their row strides / bases allow it (16-byte multiples)
+    CUtensorMap tmOutB, tmOutF;
+    memset(&tmOutB, 0, sizeof(tmOutB));
+    memset(&tmOutF, 0, sizeof(tmOutF));
+    p.tma_out_bf16 = p.tma_out_f32 = 0;
+    if (ep->out_bf16 && (ep->ld_bf16 * 2) % 16 == 0 && ((uintptr_t)ep->out_bf16 & 15) == 0) {
+      rc = make_tmap_2d(&tmOutB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_64B,
+                        ep->out_bf16, (uint64_t)N, (uint64_t)M, (uint64_t)ep->ld_bf16 * 2, 32, 32);
+      if (rc) return rc;
+      p.tma_out_bf16 = 1;
+    }
+    if (ep->out_f32 && (ep->ld_f32 * 4) % 16 == 0 && ((uintptr_t)ep->out_f32 & 15) == 0) {
+      rc = make_tmap_2d(&tmOutF, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, CU_TENSOR_MAP_SWIZZLE_128B,
+                        ep->out_f32, (uint64_t)N, (uint64_t)M, (uint64_t)ep->ld_f32 * 4, 32, 32);
+      if (rc) return rc;
+      p.tma_out_f32 = 1;
+    }
     const size_t psmem = (size_t)p.k_tiles_total * (p.BN * BK * 2) +
-                         2 * (size_t)p.k_tiles_total * A_STAGE_BYTES + 128 + p.BN * 4 + 1024;
+                         2 * (size_t)p.k_tiles_total * A_STAGE_BYTES +
+                         (p.tma_out_f32 ? 8 * 4096 : 0) + (p.tma_out_bf16 ? 8 * 2048 : 0) + 128 +
+                         p.BN * 4 + 1024;
     if (psmem <= 227 * 1024) {
       static bool pattr = false;
       if (!pattr) {
@@ -517,10 +641,9 @@ extern "C" int b4cp_gemm_bf16(const void* A, int a_mn, long lda, const void* B, 
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         pattr = true;
       }
-      // two CTAs per SM when shared memory and TMEM (2*BN columns each) allow it
-      const int per_sm = (psmem <= 110 * 1024 && p.BN <= 128) ? 2 : 1;
-      const int grid = std::min(n_mtiles, 148 * per_sm);
-      gemm_umma_persistent_kernel<<<grid, 320, psmem, (cudaStream_t)stream>>>(tmA, tmB, p);
+      const int grid = std::min(n_mtiles, 148);
+      gemm_umma_persistent_kernel<<<grid, 320, psmem, (cudaStream_t)stream>>>(tmA, tmB, tmOutB,
+                                                                              tmOutF, p);
       note_launches(1);
       B4CP_LAUNCH_CHECK();
       return 0;
