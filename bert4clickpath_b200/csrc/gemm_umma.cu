@@ -44,7 +44,7 @@ __device__ __forceinline__ void epilogue_math(const b4cp_gemm_epilogue& ep, int 
   if (sbias) {
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
-      const float4 b4 = *reinterpret_cast<const float4*>(sbias + j);
+      const float4 b4 = lds128f(smem_u32(sbias) + j * 4);
       v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
     }
   }
@@ -338,7 +338,7 @@ gemm_umma_persistent_kernel(const __grid_constant__ CUtensorMap tmA,
       mbar_init(&a_full[i], 1);
       mbar_init(&a_empty[i], 1);
       mbar_init(&t_full[i], 1);
-      mbar_init(&t_empty[i], 256);
+      mbar_init(&t_empty[i], 8);
     }
     fence_barrier_init();
   }
@@ -425,7 +425,7 @@ gemm_umma_persistent_kernel(const __grid_constant__ CUtensorMap tmA,
         tmem_ld_wait();
         if (c == c_end - 1) {  // accumulator fully read: hand the TMEM buffer back early
           tc_fence_before();
-          mbar_arrive(&t_empty[st]);
+          mbar_arrive_warp(&t_empty[st]);
         }
         if (c * 32 >= p.N || row0 >= p.M) continue;  // warp-uniform
         const float* sb = ep.bias ? sbias + c * 32 : nullptr;
@@ -446,8 +446,9 @@ gemm_umma_persistent_kernel(const __grid_constant__ CUtensorMap tmA,
         if (p.tma_out_f32) {
 #pragma unroll
           for (int k = 0; k < 8; ++k)  // 16-byte chunk k of the 128-byte row, 128B swizzle
-            *reinterpret_cast<float4*>(stgF + lane * 128 + ((k ^ (lane & 7)) << 4)) =
-                make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+            sts128(smem_u32(stgF) + lane * 128 + ((k ^ (lane & 7)) << 4), __float_as_uint(v[4 * k]),
+                   __float_as_uint(v[4 * k + 1]), __float_as_uint(v[4 * k + 2]),
+                   __float_as_uint(v[4 * k + 3]));
         } else if (ep.out_f32 && row < p.M) {
           b4cp_gemm_epilogue e2 = ep;
           e2.out_bf16 = nullptr;
@@ -456,16 +457,13 @@ gemm_umma_persistent_kernel(const __grid_constant__ CUtensorMap tmA,
         if (p.tma_out_bf16) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) {  // 16-byte chunk k of the 64-byte row, 64B swizzle
-            uint4 pk;
             __nv_bfloat162 h0 = __floats2bfloat162_rn(v[8 * k + 0], v[8 * k + 1]);
             __nv_bfloat162 h1 = __floats2bfloat162_rn(v[8 * k + 2], v[8 * k + 3]);
             __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * k + 4], v[8 * k + 5]);
             __nv_bfloat162 h3 = __floats2bfloat162_rn(v[8 * k + 6], v[8 * k + 7]);
-            pk.x = *reinterpret_cast<uint32_t*>(&h0);
-            pk.y = *reinterpret_cast<uint32_t*>(&h1);
-            pk.z = *reinterpret_cast<uint32_t*>(&h2);
-            pk.w = *reinterpret_cast<uint32_t*>(&h3);
-            *reinterpret_cast<uint4*>(stgB + lane * 64 + ((k ^ ((lane >> 1) & 3)) << 4)) = pk;
+            sts128(smem_u32(stgB) + lane * 64 + ((k ^ ((lane >> 1) & 3)) << 4),
+                   *reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
+                   *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
           }
         } else if (ep.out_bf16 && row < p.M) {
           b4cp_gemm_epilogue e2 = ep;
@@ -481,7 +479,7 @@ gemm_umma_persistent_kernel(const __grid_constant__ CUtensorMap tmA,
       }
       if (c_begin >= c_end) {
         tc_fence_before();
-        mbar_arrive(&t_empty[st]);
+        mbar_arrive_warp(&t_empty[st]);
       }
     }
     if (staged && lane == 0) tma_store_wait_read();  // smem must outlive the last store's read

@@ -136,11 +136,11 @@ vocab_ce_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&s_full[b], 1);
-      mbar_init(&s_empty[b], NUM_EPI_THREADS);
-      mbar_init(&p_full[b], NUM_EPI_THREADS);
+      mbar_init(&s_empty[b], NUM_EPI_WARPS);
+      mbar_init(&p_full[b], NUM_EPI_WARPS);
       mbar_init(&p_empty[b], 1);
       mbar_init(&u_full[b], 1);
-      mbar_init(&u_empty[b], NUM_EPI_THREADS);
+      mbar_init(&u_empty[b], NUM_EPI_WARPS);
     }
     fence_barrier_init();
   }
@@ -219,7 +219,8 @@ vocab_ce_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     const int row = m0 + r_in_tile;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     const int label = row < p.M ? p.labels[row] : -1;
-    float* sb = sBias + warp * 32;
+    const uint32_t sb = smem_u32(sBias + warp * 32);
+    const uint32_t aMax = smem_u32(sMax), aP = smem_u32(sP);
     // running (max, sum) in the log2 domain: z2 = (x.w + b) * log2(e)
     float m_run = -INFINITY, s_run = 0.f, tgt2 = 0.f, alpha_prev = 1.f;
     bool have_tgt = false;
@@ -234,7 +235,7 @@ vocab_ce_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       tmem_ld32(T_U + lane_base + (uint32_t)(ub * VB_N + cg * 32), u);
       tmem_ld_wait();
       tc_fence_before();
-      mbar_arrive(&u_empty[ub]);
+      mbar_arrive_warp(&u_empty[ub]);
 #pragma unroll
       for (int j = 0; j < 32; ++j) acc_u[j] = fmaf(acc_u[j], alpha_prev, __uint_as_float(u[j]));
     };
@@ -246,7 +247,7 @@ vocab_ce_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     for (int t = 0; t < ntiles; ++t) {
       const int buf = t & 1;
       const int vbase = (t_begin + t) * VB_N + cg * 32;
-      sb[lane] = bias_next;
+      sts32f(sb + lane * 4, bias_next);
       __syncwarp();
       bias_next = load_bias(t + 1);  // in flight while this tile is processed
       mbar_wait(&s_full[buf], (t >> 1) & 1);
@@ -255,12 +256,12 @@ vocab_ce_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       tmem_ld32(tmem_base + lane_base + (uint32_t)(buf * VB_N + cg * 32), r);
       tmem_ld_wait();
       tc_fence_before();
-      mbar_arrive(&s_empty[buf]);  // the accumulator is in registers: release the TMEM buffer
+      mbar_arrive_warp(&s_empty[buf]);  // the accumulator is in registers: release the TMEM buffer
       float z[32];
       float cmax = -INFINITY;
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
-        const float4 b4 = *reinterpret_cast<const float4*>(sb + j);
+        const float4 b4 = lds128f(sb + j * 4);
         z[j + 0] = fmaf(__uint_as_float(r[j + 0]), LOG2E, b4.x);
         z[j + 1] = fmaf(__uint_as_float(r[j + 1]), LOG2E, b4.y);
         z[j + 2] = fmaf(__uint_as_float(r[j + 2]), LOG2E, b4.z);
@@ -276,11 +277,11 @@ vocab_ce_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       }
       if (with_dx) {
         // the 4 warps that share these rows must agree on one running maximum per row
-        float* mx = sMax + buf * (4 * VB_M);
-        mx[cg * VB_M + r_in_tile] = cmax;
+        const uint32_t mx = aMax + (uint32_t)(buf * (4 * VB_M) + r_in_tile) * 4;
+        sts32f(mx + cg * VB_M * 4, cmax);
         asm volatile("bar.sync %0, 128;" ::"r"(2 + q) : "memory");
-        cmax = fmaxf(fmaxf(mx[r_in_tile], mx[VB_M + r_in_tile]),
-                     fmaxf(mx[2 * VB_M + r_in_tile], mx[3 * VB_M + r_in_tile]));
+        cmax = fmaxf(fmaxf(lds32f(mx), lds32f(mx + VB_M * 4)),
+                     fmaxf(lds32f(mx + 2 * VB_M * 4), lds32f(mx + 3 * VB_M * 4)));
       }
       const float m_new = fmaxf(m_run, cmax);
       const float alpha = m_new > -INFINITY ? ex2(m_run - m_new) : 1.f;  // ex2(-inf) = 0 at start
@@ -301,23 +302,20 @@ vocab_ce_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       m_run = m_new;
       if (with_dx) {
         mbar_wait(&p_empty[buf], ((t >> 1) & 1) ^ 1);
-        uint8_t* blk = sP + (size_t)buf * p_bytes + (cg >> 1) * (VB_M * 128) + r_in_tile * 128;
+        const uint32_t blk = aP + (uint32_t)(buf * p_bytes + (cg >> 1) * (VB_M * 128) + r_in_tile * 128);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           __nv_bfloat162 h0 = __floats2bfloat162_rn(z[8 * k + 0], z[8 * k + 1]);
           __nv_bfloat162 h1 = __floats2bfloat162_rn(z[8 * k + 2], z[8 * k + 3]);
           __nv_bfloat162 h2 = __floats2bfloat162_rn(z[8 * k + 4], z[8 * k + 5]);
           __nv_bfloat162 h3 = __floats2bfloat162_rn(z[8 * k + 6], z[8 * k + 7]);
-          uint4 pk;
-          pk.x = *reinterpret_cast<uint32_t*>(&h0);
-          pk.y = *reinterpret_cast<uint32_t*>(&h1);
-          pk.z = *reinterpret_cast<uint32_t*>(&h2);
-          pk.w = *reinterpret_cast<uint32_t*>(&h3);
           const int chunk16 = ((cg & 1) * 4 + k) ^ (r_in_tile & 7);
-          *reinterpret_cast<uint4*>(blk + chunk16 * 16) = pk;
+          sts128(blk + chunk16 * 16, *reinterpret_cast<uint32_t*>(&h0),
+                 *reinterpret_cast<uint32_t*>(&h1), *reinterpret_cast<uint32_t*>(&h2),
+                 *reinterpret_cast<uint32_t*>(&h3));
         }
         fence_proxy_async_smem();
-        mbar_arrive(&p_full[buf]);
+        mbar_arrive_warp(&p_full[buf]);
         if (t > 0) fold_u(t - 1);  // alpha_prev still holds the rescale of tile t-1
         alpha_prev = alpha;
       }
@@ -456,14 +454,14 @@ vocab_ce_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&s_empty[i], NUM_EPI_THREADS);
-      mbar_init(&dz_full[i], NUM_EPI_THREADS);
+      mbar_init(&s_empty[i], NUM_EPI_WARPS);
+      mbar_init(&dz_full[i], NUM_EPI_WARPS);
       mbar_init(&dz_empty[i], 3);  // tcgen05.commit + the two column-sum warps
     }
     mbar_init(dx_full, 1);
-    mbar_init(dx_empty, NUM_EPI_THREADS);
+    mbar_init(dx_empty, NUM_EPI_WARPS);
     mbar_init(dw_full, 1);
-    mbar_init(dw_empty, NUM_EPI_THREADS);
+    mbar_init(dw_empty, NUM_EPI_WARPS);
     fence_barrier_init();
   }
   tc_fence_before();
@@ -557,11 +555,11 @@ vocab_ce_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       for (int i = 0; i < nm; ++i, ++it) {
         const int zb = (int)(it & 1);
         mbar_wait(&dz_full[zb], (uint32_t)((it >> 1) & 1));
-        const uint8_t* blk = sDZ + (size_t)zb * dz_bytes + vb * (VB_M * 128);
+        const uint32_t blk = smem_u32(sDZ) + (uint32_t)(zb * dz_bytes + vb * (VB_M * 128));
 #pragma unroll 8
         for (int rr = 0; rr < 64; ++rr) {
           const int r = half * 64 + rr;
-          const uint2 u = *reinterpret_cast<const uint2*>(blk + r * 128 + ((chunk16 ^ (r & 7)) << 4) + sub);
+          const uint2 u = lds64(blk + r * 128 + ((chunk16 ^ (r & 7)) << 4) + sub);
           a0 += __uint_as_float(u.x << 16);
           a1 += __uint_as_float(u.x & 0xFFFF0000u);
           a2 += __uint_as_float(u.y << 16);
@@ -588,18 +586,23 @@ vocab_ce_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     const int cg = warp >> 2;
     const int r_in_tile = q * 32 + lane;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-    float* sb = sBias + warp * 32;
+    const uint32_t sb = smem_u32(sBias + warp * 32);
+    const uint32_t aDZs = smem_u32(sDZ);
     const float n_valid = p.loss_stats[1];
     const float inv_n = n_valid > 0.f ? 1.f / n_valid : 0.f;
     long it = 0;
     for (int vt = 0; vt < n_my; ++vt) {
       const int v0 = ((int)blockIdx.x + vt * (int)gridDim.x) * VB_N;
       const int vbase = v0 + cg * 32;
-      stage_bias(sb, p.bias, vbase, p.V, lane);
+      {
+        const int v = vbase + lane;
+        sts32f(sb + lane * 4, v < p.V ? __ldg(p.bias + v) * LOG2E : -INFINITY);
+        __syncwarp();
+      }
       float b2[32];
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
-        const float4 b4 = *reinterpret_cast<const float4*>(sb + j);
+        const float4 b4 = lds128f(sb + j * 4);
         b2[j] = b4.x; b2[j + 1] = b4.y; b2[j + 2] = b4.z; b2[j + 3] = b4.w;
       }
       __syncwarp();
@@ -622,7 +625,7 @@ vocab_ce_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         tmem_ld32(T_S + lane_base + (uint32_t)(sbuf * VB_N + cg * 32), r);
         tmem_ld_wait();
         tc_fence_before();
-        mbar_arrive(&s_empty[sbuf]);
+        mbar_arrive_warp(&s_empty[sbuf]);
         float g[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j)
@@ -634,23 +637,20 @@ vocab_ce_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         }
         mbar_wait(&dz_empty[zb], (uint32_t)((it >> 1) & 1) ^ 1);
         // bf16 pack + swizzled store: 16-byte chunk index XOR (row & 7) inside the 128-B row
-        uint8_t* blk = sDZ + (size_t)zb * dz_bytes + (cg >> 1) * (VB_M * 128) + r_in_tile * 128;
+        const uint32_t blk = aDZs + (uint32_t)(zb * dz_bytes + (cg >> 1) * (VB_M * 128) + r_in_tile * 128);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           __nv_bfloat162 h0 = __floats2bfloat162_rn(g[8 * k + 0], g[8 * k + 1]);
           __nv_bfloat162 h1 = __floats2bfloat162_rn(g[8 * k + 2], g[8 * k + 3]);
           __nv_bfloat162 h2 = __floats2bfloat162_rn(g[8 * k + 4], g[8 * k + 5]);
           __nv_bfloat162 h3 = __floats2bfloat162_rn(g[8 * k + 6], g[8 * k + 7]);
-          uint4 pk;
-          pk.x = *reinterpret_cast<uint32_t*>(&h0);
-          pk.y = *reinterpret_cast<uint32_t*>(&h1);
-          pk.z = *reinterpret_cast<uint32_t*>(&h2);
-          pk.w = *reinterpret_cast<uint32_t*>(&h3);
           const int chunk16 = ((cg & 1) * 4 + k) ^ (r_in_tile & 7);
-          *reinterpret_cast<uint4*>(blk + chunk16 * 16) = pk;
+          sts128(blk + chunk16 * 16, *reinterpret_cast<uint32_t*>(&h0),
+                 *reinterpret_cast<uint32_t*>(&h1), *reinterpret_cast<uint32_t*>(&h2),
+                 *reinterpret_cast<uint32_t*>(&h3));
         }
         fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the UMMA async proxy
-        mbar_arrive(&dz_full[zb]);
+        mbar_arrive_warp(&dz_full[zb]);
       }
       // dW tile: TMEM lane = input feature, columns = vocabulary entries of this tile
       mbar_wait(dw_full, vt & 1);
@@ -660,7 +660,7 @@ vocab_ce_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         tmem_ld32(T_DW + lane_base + (uint32_t)(cg * 32), r);
         tmem_ld_wait();
         tc_fence_before();
-        mbar_arrive(dw_empty);
+        mbar_arrive_warp(dw_empty);
         if (r_in_tile < h) {
           float* dst = p.dW + (size_t)r_in_tile * p.V + vbase;
           const int ncol = min(32, p.V - vbase);
