@@ -239,7 +239,7 @@ attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16*
 
 // --------------------------------------------------------------- residual + dropout + LayerNorm
 // y = LN(x + dropout(r)) * gamma + beta ; one warp per row, d <= 256.
-static constexpr int LN_MAX_PER_LANE = 8;
+static constexpr int LN_MAX_PER_LANE = 8;  // d <= 256; kernels are templated on ceil(d/32)
 
 struct DropSpec {
   float inv_keep;
@@ -248,6 +248,7 @@ struct DropSpec {
   uint32_t site;
 };
 
+template <int NPL>
 __global__ void __launch_bounds__(256)
 residual_ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ r, long T, int d,
                        const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -256,10 +257,10 @@ residual_ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ r,
   const int lane = threadIdx.x & 31;
   const long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= T) return;
-  float v[LN_MAX_PER_LANE];
+  float v[NPL];
   float sum = 0.f;
 #pragma unroll
-  for (int t = 0; t < LN_MAX_PER_LANE; ++t) {
+  for (int t = 0; t < NPL; ++t) {
     const int c = lane + 32 * t;
     v[t] = 0.f;
     if (c < d) {
@@ -273,7 +274,7 @@ residual_ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ r,
   const float mean = warp_sum(sum) / (float)d;
   float var = 0.f;
 #pragma unroll
-  for (int t = 0; t < LN_MAX_PER_LANE; ++t) {
+  for (int t = 0; t < NPL; ++t) {
     const int c = lane + 32 * t;
     if (c < d) {
       const float dv = v[t] - mean;
@@ -283,7 +284,7 @@ residual_ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ r,
   var = warp_sum(var) / (float)d;
   const float rstd = rsqrtf(var + eps);
 #pragma unroll
-  for (int t = 0; t < LN_MAX_PER_LANE; ++t) {
+  for (int t = 0; t < NPL; ++t) {
     const int c = lane + 32 * t;
     if (c < d) {
       const float o = (v[t] - mean) * rstd * gamma[c] + beta[c];
@@ -296,23 +297,24 @@ residual_ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ r,
 // Backward.  Outputs: dx (fp32, the residual branch), dr (bf16 and/or fp32: gradient w.r.t. the
 // un-dropped Dense output r), and per-block partial column sums [gridDim.x][3][d] of
 // (dy*xhat, dy, dr) = (dgamma, dbeta, bias gradient of the Dense that produced r).
+template <int NPL>
 __global__ void __launch_bounds__(256)
 residual_ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
                        const float* __restrict__ r, long T, int d,
                        const float* __restrict__ gamma, DropSpec dp, float eps,
                        float* __restrict__ dx, __nv_bfloat16* __restrict__ dr_bf16, long ld_bf16,
                        float* __restrict__ partial) {
-  __shared__ float red[8][3][LN_MAX_PER_LANE * 32];
+  __shared__ float red[8][3][NPL * 32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nwarps = blockDim.x >> 5;
-  float pg[LN_MAX_PER_LANE], pb[LN_MAX_PER_LANE], pr[LN_MAX_PER_LANE];
+  float pg[NPL], pb[NPL], pr[NPL];
 #pragma unroll
-  for (int t = 0; t < LN_MAX_PER_LANE; ++t) pg[t] = pb[t] = pr[t] = 0.f;
+  for (int t = 0; t < NPL; ++t) pg[t] = pb[t] = pr[t] = 0.f;
   for (long row = (long)blockIdx.x * nwarps + warp; row < T; row += (long)gridDim.x * nwarps) {
-    float v[LN_MAX_PER_LANE], g[LN_MAX_PER_LANE], keepf[LN_MAX_PER_LANE];
+    float v[NPL], g[NPL], keepf[NPL];
     float sum = 0.f;
 #pragma unroll
-    for (int t = 0; t < LN_MAX_PER_LANE; ++t) {
+    for (int t = 0; t < NPL; ++t) {
       const int c = lane + 32 * t;
       v[t] = 0.f;
       keepf[t] = 0.f;
@@ -331,7 +333,7 @@ residual_ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x
     const float mean = warp_sum(sum) / (float)d;
     float var = 0.f;
 #pragma unroll
-    for (int t = 0; t < LN_MAX_PER_LANE; ++t) {
+    for (int t = 0; t < NPL; ++t) {
       const int c = lane + 32 * t;
       if (c < d) {
         const float dv = v[t] - mean;
@@ -342,7 +344,7 @@ residual_ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x
     const float rstd = rsqrtf(var + eps);
     float m1 = 0.f, m2 = 0.f;
 #pragma unroll
-    for (int t = 0; t < LN_MAX_PER_LANE; ++t) {
+    for (int t = 0; t < NPL; ++t) {
       const int c = lane + 32 * t;
       g[t] = 0.f;
       if (c < d) {
@@ -358,7 +360,7 @@ residual_ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x
     m1 = warp_sum(m1) / (float)d;
     m2 = warp_sum(m2) / (float)d;
 #pragma unroll
-    for (int t = 0; t < LN_MAX_PER_LANE; ++t) {
+    for (int t = 0; t < NPL; ++t) {
       const int c = lane + 32 * t;
       if (c < d) {
         const float dres = rstd * (g[t] - m1 - v[t] * m2);
@@ -370,7 +372,7 @@ residual_ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x
     }
   }
 #pragma unroll
-  for (int t = 0; t < LN_MAX_PER_LANE; ++t) {
+  for (int t = 0; t < NPL; ++t) {
     red[warp][0][lane + 32 * t] = pg[t];
     red[warp][1][lane + 32 * t] = pb[t];
     red[warp][2][lane + 32 * t] = pr[t];
@@ -531,9 +533,14 @@ extern "C" int b4cp_residual_ln_fwd(const float* x, const float* r, long T, int 
                                     long ld_bf16, void* stream) {
   B4CP_CHECK_ARG(d >= 1 && d <= LN_MAX_PER_LANE * 32, "layernorm: d=%d must be <= 256", d);
   if (T == 0) return 0;
-  residual_ln_fwd_kernel<<<ceil_div(T, 8), 256, 0, (cudaStream_t)stream>>>(
-      x, r, T, d, gamma, beta, make_drop(dropout_rate, seed, site), 1e-6f, y_f32,
-      (__nv_bfloat16*)y_bf16, ld_bf16);
+  const DropSpec dsp = make_drop(dropout_rate, seed, site);
+  const int nb = ceil_div(T, 8);
+  cudaStream_t st = (cudaStream_t)stream;
+  __nv_bfloat16* yb = (__nv_bfloat16*)y_bf16;
+  if (d <= 32) residual_ln_fwd_kernel<1><<<nb, 256, 0, st>>>(x, r, T, d, gamma, beta, dsp, 1e-6f, y_f32, yb, ld_bf16);
+  else if (d <= 64) residual_ln_fwd_kernel<2><<<nb, 256, 0, st>>>(x, r, T, d, gamma, beta, dsp, 1e-6f, y_f32, yb, ld_bf16);
+  else if (d <= 128) residual_ln_fwd_kernel<4><<<nb, 256, 0, st>>>(x, r, T, d, gamma, beta, dsp, 1e-6f, y_f32, yb, ld_bf16);
+  else residual_ln_fwd_kernel<8><<<nb, 256, 0, st>>>(x, r, T, d, gamma, beta, dsp, 1e-6f, y_f32, yb, ld_bf16);
   note_launches(1);
   B4CP_LAUNCH_CHECK();
   return 0;
@@ -555,9 +562,12 @@ extern "C" int b4cp_residual_ln_bwd(const float* dy, const float* x, const float
   cudaStream_t st = (cudaStream_t)stream;
   float* partial = (float*)workspace;
   const int blocks = (int)std::min<long>(LN_BWD_BLOCKS, std::max<long>(1, ceil_div(T, 8)));
-  residual_ln_bwd_kernel<<<blocks, 256, 0, st>>>(dy, x, r, T, d, gamma,
-                                                 make_drop(dropout_rate, seed, site), 1e-6f, dx,
-                                                 (__nv_bfloat16*)dr_bf16, ld_bf16, partial);
+  const DropSpec dsp = make_drop(dropout_rate, seed, site);
+  __nv_bfloat16* drb = (__nv_bfloat16*)dr_bf16;
+  if (d <= 32) residual_ln_bwd_kernel<1><<<blocks, 256, 0, st>>>(dy, x, r, T, d, gamma, dsp, 1e-6f, dx, drb, ld_bf16, partial);
+  else if (d <= 64) residual_ln_bwd_kernel<2><<<blocks, 256, 0, st>>>(dy, x, r, T, d, gamma, dsp, 1e-6f, dx, drb, ld_bf16, partial);
+  else if (d <= 128) residual_ln_bwd_kernel<4><<<blocks, 256, 0, st>>>(dy, x, r, T, d, gamma, dsp, 1e-6f, dx, drb, ld_bf16, partial);
+  else residual_ln_bwd_kernel<8><<<blocks, 256, 0, st>>>(dy, x, r, T, d, gamma, dsp, 1e-6f, dx, drb, ld_bf16, partial);
   note_launches(1 + (dgamma ? 1 : 0) + (dbeta ? 1 : 0) + (dbias ? 1 : 0));
   if (dgamma) launch_reduce_partials(partial, blocks, d, 3L * d, dgamma, st);
   if (dbeta) launch_reduce_partials(partial + d, blocks, d, 3L * d, dbeta, st);

@@ -239,15 +239,17 @@ vocab_ce_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
 #pragma unroll
       for (int j = 0; j < 32; ++j) acc_u[j] = fmaf(acc_u[j], alpha_prev, __uint_as_float(u[j]));
     };
-    auto load_bias = [&](int t) -> float {  // bias * log2(e) of this lane's column, -inf past V
+    // raw bias of this lane's column (-inf past V); scaled by log2(e) only when it is consumed so
+    // that the load stays in flight during the whole tile
+    auto load_bias = [&](int t) -> float {
       const int v = (t_begin + t) * VB_N + cg * 32 + lane;
-      return (t < ntiles && v < p.V) ? __ldg(p.bias + v) * LOG2E : -INFINITY;
+      return (t < ntiles && v < p.V) ? __ldg(p.bias + v) : -INFINITY;
     };
     float bias_next = load_bias(0);
     for (int t = 0; t < ntiles; ++t) {
       const int buf = t & 1;
       const int vbase = (t_begin + t) * VB_N + cg * 32;
-      sts32f(sb + lane * 4, bias_next);
+      sts32f(sb + lane * 4, bias_next * LOG2E);
       __syncwarp();
       bias_next = load_bias(t + 1);  // in flight while this tile is processed
       mbar_wait(&s_full[buf], (t >> 1) & 1);
