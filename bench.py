@@ -238,6 +238,39 @@ def run_ours(args, rank, world, local_rank):
     ms_e2e = max_over_ranks(e0.elapsed_time(e1))
     h2d = ClozeTrainStep.h2d_bytes(pinned[0][0], pinned[0][1])
 
+    # ---- next-item top-k inference (EVAL masking: last item of each session), k = 100
+    topk = None
+    if not args.no_topk:
+        K_TOP, QB = 100, args.batch
+        ev_host = [make_cloze_batch(rng, QB, V, CFG["max_len"], "eval") for _ in range(2)]
+        ev = [(torch.from_numpy(b["ids"]).cuda().view(-1), torch.from_numpy(b["labels"]).cuda(),
+               b["ids"].shape[1], b["n_masked"]) for b in ev_host]
+        counters = torch.zeros(3, device="cuda")
+
+        def query(i):
+            ids_d, lab_d, S_e, n_m = ev[i % 2]
+            top, out = model.topk_ids([ids_d], QB, S_e, K_TOP, n_masked=n_m)
+            labels_c, _ = ops.compact_labels(lab_d, n_m)
+            ops.rank_metrics(top, K_TOP, labels_c, counters)
+
+        for i in range(3):
+            query(i)
+        barrier()
+        n_q = max(5, args.steps // 2)
+        q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        q0.record()
+        for i in range(n_q):
+            query(i)
+        q1.record()
+        barrier()
+        q_ms = max_over_ranks(q0.elapsed_time(q1))
+        c = counters.cpu().numpy()
+        topk = {"metric": "next_item_topk_queries_per_sec", "value": world * QB * n_q / (q_ms * 1e-3),
+                "unit": "queries/s", "k": K_TOP, "queries_per_step_per_gpu": QB, "steps": n_q,
+                "ms_per_step": q_ms / n_q, "vocab": V,
+                "includes": "encoder forward + head MLP + fused scoring/top-k + recall/NDCG counters",
+                "recall_at_k": float(c[0] / max(c[2], 1)), "ndcg_at_k": float(c[1] / max(c[2], 1))}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -257,7 +290,12 @@ def run_ours(args, rank, world, local_rank):
             "peak_source": pk["source"] + " (sustained: kernel timed inside a long step)",
             "algorithmic_flops_per_step": flops, "kernel_ms_per_step": per_step_ms,
             "kernel_share_of_step": per_step_ms / (ms_total / args.steps)}
-    cpu_seqs, cpu_n, cpu_dt = time_cpu_reference(args.cpu_batch, 6, 1, budget_s=20.0)
+    if world == 1:
+        cpu_seqs, cpu_n, cpu_dt = time_cpu_reference(args.cpu_batch, 6, 1, budget_s=20.0)
+        cpu_base = {"value": cpu_seqs, "unit": "seqs/s", "cores": blas_threads(), "kind": "port",
+                    "sample": f"{cpu_n} full oracle training steps at batch {args.cpu_batch}"}
+    else:
+        cpu_base = None  # reported at N=1 only (torchrun pins OMP_NUM_THREADS=1)
     line = {
         "metric": "cloze_train_seqs_per_sec", "value": seqs, "unit": "seqs/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
@@ -273,9 +311,8 @@ def run_ours(args, rank, world, local_rank):
                 "d2h_bytes_per_step": 8, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
         "roofline": roof,
-        "cpu_baseline": {"value": cpu_seqs, "unit": "seqs/s", "cores": blas_threads(),
-                         "kind": "port",
-                         "sample": f"{cpu_n} full oracle training steps at batch {args.cpu_batch}"},
+        "cpu_baseline": cpu_base,
+        "topk": topk,
         "loss": float(loss_stats[0] / max(loss_stats[1], 1.0)), "e2e_last_loss": loss,
     }
     print(json.dumps(line), flush=True)
@@ -291,6 +328,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=4096, help="per-GPU batch (sequences)")
     ap.add_argument("--cpu-batch", type=int, default=64, help="batch of the CPU reference sample")
+    ap.add_argument("--no-topk", action="store_true", help="skip the top-k inference leg")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

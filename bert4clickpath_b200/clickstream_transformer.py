@@ -252,6 +252,12 @@ class ClickstreamTransformer:
 
     __call__ = call
 
+    def topk_ids(self, ids_list, B, S, k, n_masked=None):
+        """Next-item inference on chained device ids: the k best label-vocabulary ids for every
+        [MASK] position, in (b, s) order -> int32 (n_masked, k).  Scores never reach HBM."""
+        out = self.forward_ids(ids_list, B, S, training=False, n_masked=n_masked)
+        return out.head.vocab.topk(out.ab, out.M, k), out
+
     def _next_seed(self):
         self._step_seed += 1
         return self._step_seed

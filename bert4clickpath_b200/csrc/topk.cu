@@ -33,16 +33,37 @@ __device__ __forceinline__ float from_ordered_desc(uint32_t d) {
 }
 
 __global__ void __launch_bounds__(TK_THREADS)
-topk_rows_kernel(const float* __restrict__ scores, long ld, int V, int k, int idbits,
-                 int32_t* __restrict__ out_ids, float* __restrict__ out_scores, long ld_out) {
+topk_rows_kernel(const float* __restrict__ scores, const int32_t* __restrict__ cand_ids, long ld,
+                 int V, int k, int idbits, int32_t* __restrict__ out_ids,
+                 float* __restrict__ out_scores, long ld_out) {
   __shared__ int hist[TK_BINS];
   __shared__ unsigned long long buf[TK_SORT];
   __shared__ int scan_tmp[40];
   __shared__ int s_bin, s_below, s_nsel;
   const long row = blockIdx.x;
   const float* z = scores + row * ld;
+  // candidate mode: element v carries the id cand[v] (negative = empty slot, skipped)
+  const int32_t* cand = cand_ids ? cand_ids + row * ld : nullptr;
   const int total_bits = 32 + idbits;
-  int need = min(k, V);
+  int n_valid = V;
+  if (cand) {
+    if (threadIdx.x == 0) s_nsel = 0;
+    __syncthreads();
+    int c = 0;
+    for (int v = threadIdx.x; v < V; v += TK_THREADS) c += cand[v] >= 0 ? 1 : 0;
+    if (c) atomicAdd(&s_nsel, c);
+    __syncthreads();
+    n_valid = s_nsel;
+    __syncthreads();
+  }
+  int need = min(k, n_valid);
+  if (need == 0) {  // nothing to rank
+    for (int r = threadIdx.x; r < k; r += TK_THREADS) {
+      out_ids[row * ld_out + r] = -1;
+      if (out_scores) out_scores[row * ld_out + r] = -INFINITY;
+    }
+    return;
+  }
   unsigned long long prefix = 0;
   int consumed = 0;
   int bin_count = V;
@@ -52,7 +73,9 @@ topk_rows_kernel(const float* __restrict__ scores, long ld, int V, int k, int id
     for (int i = threadIdx.x; i < TK_BINS; i += TK_THREADS) hist[i] = 0;
     __syncthreads();
     for (int v = threadIdx.x; v < V; v += TK_THREADS) {
-      const unsigned long long K = ((unsigned long long)ordered_desc(z[v]) << idbits) | (unsigned)v;
+      const int id = cand ? cand[v] : v;
+      if (id < 0) continue;
+      const unsigned long long K = ((unsigned long long)ordered_desc(z[v]) << idbits) | (unsigned)id;
       if (consumed == 0 || (K >> (shift + bits)) == prefix)
         atomicAdd(&hist[(int)((K >> shift) & ((1u << bits) - 1u))], 1);
     }
@@ -106,7 +129,9 @@ topk_rows_kernel(const float* __restrict__ scores, long ld, int V, int k, int id
   __syncthreads();
   const int rem = total_bits - consumed;
   for (int v = threadIdx.x; v < V; v += TK_THREADS) {
-    const unsigned long long K = ((unsigned long long)ordered_desc(z[v]) << idbits) | (unsigned)v;
+    const int id = cand ? cand[v] : v;
+    if (id < 0) continue;
+    const unsigned long long K = ((unsigned long long)ordered_desc(z[v]) << idbits) | (unsigned)id;
     if ((K >> rem) <= prefix) {
       const int slot = atomicAdd(&s_nsel, 1);
       if (slot < TK_SORT) buf[slot] = K;
@@ -132,7 +157,7 @@ topk_rows_kernel(const float* __restrict__ scores, long ld, int V, int k, int id
   const unsigned long long idmask = (1ull << idbits) - 1ull;
   for (int r = threadIdx.x; r < k; r += TK_THREADS) {
     const unsigned long long K = buf[r];
-    const bool ok = r < V && K != ~0ull;
+    const bool ok = r < n_valid && K != ~0ull;
     out_ids[row * ld_out + r] = ok ? (int32_t)(K & idmask) : -1;
     if (out_scores)
       out_scores[row * ld_out + r] = ok ? from_ordered_desc((uint32_t)(K >> idbits)) : -INFINITY;
@@ -152,7 +177,25 @@ extern "C" int b4cp_topk_rows(const float* scores, long ld, long rows, int V, in
   int idbits = 1;
   while ((1L << idbits) < V) ++idbits;
   topk_rows_kernel<<<(unsigned)rows, TK_THREADS, 0, (cudaStream_t)stream>>>(
-      scores, ld, V, k, idbits, out_ids, out_scores, ld_out);
+      scores, nullptr, ld, V, k, idbits, out_ids, out_scores, ld_out);
+  note_launches(1);
+  B4CP_LAUNCH_CHECK();
+  return 0;
+}
+
+/* top-k over explicit (score, id) candidate lists: row r ranks cand_scores[r*ld .. +n_cand) whose
+ * ids are cand_ids[...] (negative = empty).  Same order as b4cp_topk_rows; ids < V. */
+extern "C" int b4cp_topk_candidates(const float* cand_scores, const int32_t* cand_ids, long ld,
+                                    long rows, int n_cand, int V, int k, int32_t* out_ids,
+                                    float* out_scores, long ld_out, void* stream) {
+  B4CP_CHECK_ARG(k >= 1 && k <= TK_MAXK, "topk: k=%d must be in [1,%d]", k, TK_MAXK);
+  B4CP_CHECK_ARG(cand_scores && cand_ids && out_ids, "topk_candidates: null argument");
+  B4CP_CHECK_ARG(ld_out >= k, "topk: ld_out < k");
+  if (rows == 0) return 0;
+  int idbits = 1;
+  while ((1L << idbits) < V) ++idbits;
+  topk_rows_kernel<<<(unsigned)rows, TK_THREADS, 0, (cudaStream_t)stream>>>(
+      cand_scores, cand_ids, ld, n_cand, k, idbits, out_ids, out_scores, ld_out);
   note_launches(1);
   B4CP_LAUNCH_CHECK();
   return 0;

@@ -423,7 +423,15 @@ class VocabOutputEngine:
         ops.reduce_splits_ex(part, M, h, gate, out_f32, out_bf16)
 
     def topk(self, ab, M, k):
-        z = self.logits(ab, M)
+        """(M, k) int32 ids of the k highest scores per row, ties -> lower id.  Fused scoring +
+        heap top-k on the tensor cores when the head width allows it (scores never reach HBM),
+        otherwise materialised logits + radix-select top-k."""
         ids = self.pool.get(f"topk{k}", (M, k), I32)
+        if self.h in (64, 128) and k <= 104 and not self.force_materialized:
+            t0 = ops.TIMER.begin("score_topk")
+            ops.score_topk(ab, M, self.h, self.W.wb, self.b.w, self.V, k, out_ids=ids)
+            ops.TIMER.end("score_topk", t0)
+            return ids
+        z = self.logits(ab, M)
         ops.topk_rows(z, self.V, k, out_ids=ids)
         return ids

@@ -378,3 +378,16 @@ def vocab_ce_bwd(xb, M, h, wb, bias, V, labels, lse, loss_stats, dW, db):
     L.call("b4cp_vocab_ce_bwd", L.ptr(xb), L.c_long(xb.stride(0)), L.c_long(M), L.c_int(h),
            L.ptr(wb), L.c_long(wb.stride(0)), L.ptr(bias), L.c_int(V), L.ptr(labels), L.ptr(lse),
            L.ptr(loss_stats), L.ptr(dW), L.ptr(db), L.stream_ptr())
+
+
+def score_topk(xb, M, h, wb, bias, V, k, out_ids=None, out_scores=None):
+    """Fused scoring + exact top-k (scores never written to HBM)."""
+    fn = L.lib().b4cp_score_topk_workspace_bytes
+    fn.restype = ctypes.c_long
+    ws = WS.get("score_topk", fn(ctypes.c_long(M), ctypes.c_int(V), ctypes.c_int(k)))
+    if out_ids is None:
+        out_ids = empty((M, k), I32)
+    L.call("b4cp_score_topk", L.ptr(xb), L.c_long(xb.stride(0)), L.c_long(M), L.c_int(h), L.ptr(wb),
+           L.c_long(wb.stride(0)), L.ptr(bias), L.c_int(V), L.c_int(k), L.ptr(out_ids),
+           L.ptr(out_scores), L.c_long(out_ids.stride(0)), L.ptr(ws), L.stream_ptr())
+    return out_ids, out_scores

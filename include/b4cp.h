@@ -218,6 +218,18 @@ int b4cp_sigmoid(const float* z, float* out, long n, void* stream);
  */
 int b4cp_topk_rows(const float* scores, long ld, long rows, int V, int k, int32_t* out_ids,
                    float* out_scores, long ld_out, void* stream);
+/* same ranking over explicit candidate lists: row r ranks cand_scores[r*ld .. r*ld+n_cand) with
+ * ids cand_ids[...] (negative = empty slot); ids < V */
+int b4cp_topk_candidates(const float* cand_scores, const int32_t* cand_ids, long ld, long rows,
+                         int n_cand, int V, int k, int32_t* out_ids, float* out_scores,
+                         long ld_out, void* stream);
+/* FUSED inference scoring + top-k: ranks x W + b over the whole vocabulary without writing the
+ * (M x V) scores (head.py:36,45 + examples/BERT4Rec/source/utils.py:176,:245).  x_bf16: bf16
+ * [M][ldx]; w_bf16: bf16 [h][ldw] Keras kernel; h in {64,128}; k <= 104.  Exact, ties -> lower id. */
+long b4cp_score_topk_workspace_bytes(long M, int V, int k);
+int b4cp_score_topk(const void* x_bf16, long ldx, long M, int h, const void* w_bf16, long ldw,
+                    const float* bias, int V, int k, int32_t* out_ids, float* out_scores,
+                    long ld_out, void* workspace, void* stream);
 int b4cp_rank_metrics(const int32_t* topk_ids, long M, int k, long ld, const int32_t* labels,
                       float* counters, void* stream);
 

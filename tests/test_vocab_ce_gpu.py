@@ -111,3 +111,31 @@ def test_fused_all_rows_padded(cuda_lib):
     torch.cuda.synchronize()
     assert stats.cpu().numpy().tolist() == [0.0, 0.0]
     assert not dX.any().item() and not dW.any().item() and not db.any().item()
+
+
+# ------------------------------------------------------------------ fused scoring + top-k
+@pytest.mark.parametrize("M,h,V,k", [(5, 128, 54293, 100), (300, 128, 5000, 10), (1, 64, 1237, 5),
+                                     (130, 128, 200, 100), (700, 128, 100000, 100)])
+def test_fused_score_topk_is_exact(cuda_lib, M, h, V, k):
+    """ids bit-exact against the oracle's tf.math.top_k order applied to the same tensor-core
+    scores, including exact ties across tiles and vocabulary chunks (duplicated W columns)."""
+    from bert4clickpath_b200 import ops
+    x, w, b, _ = make(M, h, V, 3 * M + V)
+    w[:, V // 3:] = w[:, (np.arange(V - V // 3) % 53)]   # thousands of exactly tied scores
+    b[V // 3:] = b[np.arange(V - V // 3) % 53]
+    labels = np.zeros(M, dtype=np.int32)
+    xb, wb, bd, _ = to_dev(x, w, b, labels)
+    logits = torch.empty((M, ops.ld8(V)), device="cuda")
+    ops.gemm(xb, 0, wb, 1, M, V, h, bias=bd, out_f32=logits)
+    ids, scores = ops.score_topk(xb, M, h, wb, bd, V, k, out_scores=torch.empty((M, k), device="cuda"))
+    torch.cuda.synchronize()
+    z = logits.cpu().numpy()[:, :V]
+    want = O.top_k_ids(z, k)
+    kk = min(k, V)
+    got = ids.cpu().numpy()
+    assert got[:, :kk].tolist() == want[:, :kk].tolist()
+    assert (got[:, kk:] == -1).all()
+    np.testing.assert_array_equal(scores.cpu().numpy()[:, :kk], np.take_along_axis(z, want[:, :kk], 1))
+    # and the materialised top-k kernel agrees
+    ids2, _ = ops.topk_rows(logits, V, k)
+    assert torch.equal(ids, ids2)
