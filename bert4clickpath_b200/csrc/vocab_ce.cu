@@ -55,6 +55,7 @@ struct VocabParams {
   const float* loss_stats;  // [2]: (sum, n_valid)
   float* dW;                // [h][V]
   float* db;                // [V]
+  int debug;                // timing experiments only (B4CP_DEBUG_BWD bitmask)
 };
 
 // Warp roles (both kernels, 640 threads): warps 0-15 = epilogue, warp 16 = TMA producer + TMEM
@@ -530,7 +531,7 @@ vocab_ce_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
           tc_fence_after();
           // dW[h x 128] (+)= X^T dZ : K = 128 rows, 8 steps of 16
 #pragma unroll
-          for (int kk = 0; kk < 8; ++kk) {
+          for (int kk = 0; kk < ((p.debug & 4) ? 0 : 8); ++kk) {
             const uint64_t da = umma_smem_desc(aX + kk * 2048, VB_M * 128, 1024);
             const uint64_t db = umma_smem_desc(aZ + kk * 2048, VB_M * 128, 1024);
             umma_bf16(T_DW, da, db, id_dw, (i | kk) ? 1u : 0u);
@@ -559,7 +560,7 @@ vocab_ce_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         mbar_wait(&dz_full[zb], (uint32_t)((it >> 1) & 1));
         const uint32_t blk = smem_u32(sDZ) + (uint32_t)(zb * dz_bytes + vb * (VB_M * 128));
 #pragma unroll 8
-        for (int rr = 0; rr < 64; ++rr) {
+        for (int rr = 0; rr < ((p.debug & 1) ? 0 : 64); ++rr) {
           const int r = half * 64 + rr;
           const uint2 u = lds64(blk + r * 128 + ((chunk16 ^ (r & 7)) << 4) + sub);
           a0 += __uint_as_float(u.x << 16);
@@ -592,6 +593,7 @@ vocab_ce_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     const uint32_t aDZs = smem_u32(sDZ);
     const float n_valid = p.loss_stats[1];
     const float inv_n = n_valid > 0.f ? 1.f / n_valid : 0.f;
+    const float log2_inv_n = n_valid > 0.f ? -log2f(n_valid) : 0.f;
     long it = 0;
     for (int vt = 0; vt < n_my; ++vt) {
       const int v0 = ((int)blockIdx.x + vt * (int)gridDim.x) * VB_N;
@@ -614,13 +616,9 @@ vocab_ce_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         const int sbuf = (int)(it & 1), zb = sbuf;
         const int label = label_next;
         const float scale = label >= 0 ? inv_n : 0.f;
-        const float lneg = -lse_next * LOG2E;  // -inf for rows past M: they contribute exactly 0
-        {
-          const int nrow = (i + 1) * VB_M + r_in_tile;  // prefetch the next row tile's statistics
-          const bool ok = (i + 1 < nm) && nrow < p.M;
-          label_next = ok ? __ldg(p.labels + nrow) : -1;
-          lse_next = ok ? __ldg(p.lse + nrow) : INFINITY;
-        }
+        // dZ = exp2(z2 - lse2 + log2(scale)): the 1/n_valid factor rides in the exponent.
+        // -inf for padded rows and rows past M: they contribute exactly 0.
+        const float lneg = scale > 0.f ? log2_inv_n - lse_next * LOG2E : -INFINITY;
         mbar_wait(&s_full[sbuf], (uint32_t)((it >> 1) & 1));
         tc_fence_after();
         uint32_t r[32];
@@ -631,7 +629,7 @@ vocab_ce_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         float g[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j)
-          g[j] = ex2(fmaf(__uint_as_float(r[j]), LOG2E, b2[j] + lneg)) * scale;
+          g[j] = (p.debug & 2) ? __uint_as_float(r[j]) : ex2(fmaf(__uint_as_float(r[j]), LOG2E, b2[j] + lneg));
         if (label >= vbase && label < vbase + 32) {
 #pragma unroll
           for (int j = 0; j < 32; ++j)
@@ -653,6 +651,13 @@ vocab_ce_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         }
         fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the UMMA async proxy
         mbar_arrive_warp(&dz_full[zb]);
+        {
+          // prefetch the next row tile's statistics
+          const int nrow = (i + 1) * VB_M + r_in_tile;
+          const bool ok = (i + 1 < nm) && nrow < p.M;
+          label_next = ok ? __ldg(p.labels + nrow) : -1;
+          lse_next = ok ? __ldg(p.lse + nrow) : INFINITY;
+        }
       }
       // dW tile: TMEM lane = input feature, columns = vocabulary entries of this tile
       mbar_wait(dw_full, vt & 1);
@@ -795,6 +800,7 @@ extern "C" int b4cp_vocab_ce_bwd(const void* x_bf16, long ldx, long M, int h, co
   p.loss_stats = loss_stats;
   p.dW = dW;
   p.db = db;
+  p.debug = getenv("B4CP_DEBUG_BWD") ? atoi(getenv("B4CP_DEBUG_BWD")) : 0;
   CUtensorMap tmX, tmW;
   rc = make_tmap_bf16_2d(&tmX, x_bf16, (uint64_t)h, (uint64_t)M, (uint64_t)ldx * 2, 64, VB_M);
   if (rc) return rc;
