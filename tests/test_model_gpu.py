@@ -248,3 +248,53 @@ def test_gpu_matches_committed_golden_cloze_step(cuda_lib, name, dims):
         assert rel_err(got[k], G[k], grad_floor(G)) < BF16_TOL, (k, rel_err(got[k], G[k], grad_floor(G)))
     out = model.forward_ids(dev_ids, B, S, training=False, n_masked=n_masked)
     np.testing.assert_allclose(out.materialize().cpu().numpy(), z["probs"], rtol=5e-2, atol=1e-4)
+
+
+# ------------------------------------------------------------------ C3: multi-variable, segment mode
+@pytest.mark.parametrize("segment", [0, 2])
+def test_multivariable_segment_head_forward_matches_oracle(cuda_lib, segment):
+    """(action, item) click-path encoder with a sigmoid classification head fed from a segment
+    slice (clickstream_transformer.py:317-322): segment 0 = [CLS] (purchase intention),
+    segment 2 = the basket sequence (return prediction).  String inputs, two chained sequences."""
+    import bert4clickpath_b200 as bc
+    from bert4clickpath_b200.weights import to_reference_layout
+    rng = np.random.default_rng(7)
+    items_vocab = [f"it{j}" for j in range(60)]
+    ev_vocab = [f"ev{j}" for j in range(7)]
+    B, L1, L2 = 6, 9, 4
+    def draw(vocab, L):
+        a = rng.choice(vocab, size=(B, L)).astype(object)
+        for b in range(B):
+            n = rng.integers(1, L + 1)
+            a[b, n:] = "[PAD]"
+        return a
+    feats = {"s_items": draw(items_vocab, L1), "b_items": draw(items_vocab, L2)}
+    feats["s_ev"] = np.where(feats["s_items"] == "[PAD]", "[PAD]", rng.choice(ev_vocab, size=(B, L1)).astype(object))
+    feats["b_ev"] = np.where(feats["b_items"] == "[PAD]", "[PAD]", rng.choice(ev_vocab, size=(B, L2)).astype(object))
+    feats["s_items"][0, 1] = "never-seen-item"  # OOV bucket
+    head = bc.BinaryClassificationHead(dense_layer_dims=[32, 16])
+    model = bc.ClickstreamTransformer(
+        sequential_input_config={"items": ["s_items", "b_items"], "events": ["s_ev", "b_ev"]},
+        feature_vocabs={"items": items_vocab, "events": ev_vocab},
+        embedding_dims={"items": 24, "events": 8}, head_unit=head, segment_to_head=segment,
+        num_encoder_layers=2, num_attention_heads=4, dropout_rate=0.1)
+    probs = model.call(feats, training=False).cpu().numpy()
+    # oracle on the same weights
+    P = {k: v.astype(np.float64) for k, v in to_reference_layout(model.store.get_weights()).items()}
+    ids_items = O.chain_sequences([O.lookup_ids(feats["s_items"], items_vocab), O.lookup_ids(feats["b_items"], items_vocab)])
+    ids_ev = O.chain_sequences([O.lookup_ids(feats["s_ev"], ev_vocab), O.lookup_ids(feats["b_ev"], ev_vocab)])
+    assert ids_items[0, 3] == 10 + 60  # OOV id = len(reserved) + len(vocab)
+    pe = O.positional_encoding(10000, 32)
+    x, _ = O.encoder_fwd([ids_items, ids_ev], P, 2, 4, pe, np.float64)
+    starts, ends = O.segment_bounds(ids_items[0])
+    seg = O.select_segment(x, starts, ends, segment)
+    want, _, _ = O.binary_head_fwd(seg, O.head_layers(P), P["head.out.w"], P["head.out.b"])
+    assert probs.shape == want.shape == (B, 1 if segment == 0 else L2)
+    np.testing.assert_allclose(probs, want, rtol=3e-2, atol=3e-3)
+    # MaskedLoss with binary cross-entropy and pos_weight on the materialised probabilities
+    y = rng.integers(0, 2, size=want.shape).astype(np.float32)
+    if segment == 2:
+        y[feats["b_items"] == "[PAD]"] = -1.0
+    loss = bc.MaskedLoss(bc.binary_crossentropy, pos_weight=3.0)(y, probs)
+    want_loss = O.masked_loss(y, probs.astype(np.float64), O.binary_crossentropy_probs, pos_weight=3.0)
+    assert abs(loss - want_loss) < 1e-4 * abs(want_loss)
