@@ -215,6 +215,9 @@ class ClickstreamTransformer:
             head_input = x.view(B, S, self.d_model)[:, s0:s1, :]
             return self.head(head_input)
         cap = int(n_masked) if n_masked is not None else B * S
+        vocab = getattr(self.head, "vocab", None)
+        if hasattr(vocab, "common_rows"):
+            cap = vocab.common_rows(cap)  # vocabulary-parallel: every rank presents the same rows
         row_index, count = ops.select_masked(ids_list[0], self._value_id, cap)
         hsel = self.pool.get("hsel", (cap, ld8(self.d_model)), BF16)
         ops.gather_rows(x, row_index, None, hsel)
@@ -291,7 +294,8 @@ class ClickstreamTransformer:
         stats = self.pool.get("loss_stats", (2,))
         vocab, mlp = self.head.vocab, self.head.mlp
         vocab.loss_forward(out.ab, cap, labels, stats)
-        self._allreduce(stats)
+        if not getattr(vocab, "stats_are_global", False):
+            self._allreduce(stats)
         d = self.d_model
         dsel = self.pool.get("dsel", (cap, d))
         if mlp.dims:
@@ -303,7 +307,8 @@ class ClickstreamTransformer:
         dx = self.pool.get("dx_top", (B * S, d), zero=True)
         ops.scatter_rows(dsel, out.row_index, dx)
         self.transformer.engine.backward(dx)
-        self._allreduce(self.store.flat_g)
+        for run in self.store.replicated_grad_runs():
+            self._allreduce(run)
         self._last_output = out
         self._last_labels = labels
         return stats

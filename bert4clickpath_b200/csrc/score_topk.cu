@@ -30,6 +30,7 @@ static constexpr int ST_MAXK = 104;
 struct ScoreParams {
   int M, V, h, HB, k;
   int n_vtiles, tiles_per_chunk, n_chunks;
+  int id_base;  // added to every reported id (vocabulary shards)
   const float* bias;
   float* part_scores;  // [M][n_chunks][k]
   int32_t* part_ids;   // [M][n_chunks][k]
@@ -207,7 +208,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         int id;
         asm volatile("ld.shared.s32 %0, [%1];" : "=r"(id) : "r"(aI + s * SLOT) : "memory");
         os[s] = lds32f(aS + s * SLOT);
-        oi[s] = id == INT_MAX ? -1 : id;
+        oi[s] = id == INT_MAX ? -1 : id + p.id_base;
       }
     }
   }
@@ -240,8 +241,9 @@ extern "C" long b4cp_score_topk_workspace_bytes(long M, int V, int k) {
 }
 
 extern "C" int b4cp_score_topk(const void* x_bf16, long ldx, long M, int h, const void* w_bf16,
-                               long ldw, const float* bias, int V, int k, int32_t* out_ids,
-                               float* out_scores, long ld_out, void* workspace, void* stream) {
+                               long ldw, const float* bias, int V, int k, int id_base, int V_total,
+                               int32_t* out_ids, float* out_scores, long ld_out, void* workspace,
+                               void* stream) {
   B4CP_CHECK_ARG(x_bf16 && w_bf16 && bias && out_ids && workspace, "score_topk: null argument");
   B4CP_CHECK_ARG(M > 0 && V > 0, "score_topk: empty problem");
   B4CP_CHECK_ARG(h == 64 || h == 128, "score_topk: head width h=%d unsupported (64 or 128)", h);
@@ -257,6 +259,7 @@ extern "C" int b4cp_score_topk(const void* x_bf16, long ldx, long M, int h, cons
   p.n_vtiles = ceil_div(V, ST_N);
   p.n_chunks = score_chunks(ceil_div(M, ST_M), p.n_vtiles, &p.tiles_per_chunk);
   p.bias = bias;
+  p.id_base = id_base;
   p.part_scores = (float*)workspace;
   p.part_ids = (int32_t*)(p.part_scores + (size_t)p.n_chunks * M * k);
   CUtensorMap tmX, tmW;
@@ -273,6 +276,6 @@ extern "C" int b4cp_score_topk(const void* x_bf16, long ldx, long M, int h, cons
   score_topk_kernel<<<grid, 192, smem, st>>>(tmX, tmW, p);
   note_launches(1);
   B4CP_LAUNCH_CHECK();
-  return b4cp_topk_candidates(p.part_scores, p.part_ids, (long)p.n_chunks * k, M, p.n_chunks * k, V,
-                              k, out_ids, out_scores, ld_out, stream);
+  return b4cp_topk_candidates(p.part_scores, p.part_ids, (long)p.n_chunks * k, M, p.n_chunks * k,
+                              V_total > 0 ? V_total : V, k, out_ids, out_scores, ld_out, stream);
 }

@@ -348,7 +348,7 @@ vocab_ce_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
 // partials are (max, sum) in the log2 domain; lse is returned in natural units
 __global__ void __launch_bounds__(256)
 vocab_ce_merge_kernel(const float* __restrict__ part_max, const float* __restrict__ part_sum,
-                      int n_parts, int M, const int32_t* __restrict__ labels,
+                      int n_parts, int M, int V, const int32_t* __restrict__ labels,
                       float* __restrict__ lse, float* __restrict__ tgt) {
   const int row = blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= M) return;
@@ -360,7 +360,8 @@ vocab_ce_merge_kernel(const float* __restrict__ part_max, const float* __restric
     if (pm > -INFINITY) s += part_sum[(size_t)c * M + row] * exp2f(pm - m);
   }
   lse[row] = (m + log2f(s)) * LN2;
-  if (labels[row] < 0) tgt[row] = 0.f;
+  // padded rows, and rows whose label another vocabulary shard owns, have no local target
+  if (labels[row] < 0 || labels[row] >= V) tgt[row] = 0.f;
 }
 
 // dX[row][j] = gate * ( sum_c U_c[row][j] 2^(m_c - m) / s  -  W[j][label] ) / n_valid
@@ -369,6 +370,7 @@ __global__ void __launch_bounds__(256)
 vocab_ce_dx_kernel(const float* __restrict__ part_max, const float* __restrict__ part_sum,
                    const float* __restrict__ part_u, int n_chunks, int M, int h,
                    const int32_t* __restrict__ labels, const float* __restrict__ loss_stats,
+                   const float* __restrict__ lse_global, int V,
                    const __nv_bfloat16* __restrict__ w, long ldw,
                    const __nv_bfloat16* __restrict__ gate, long ld_gate,
                    float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16, long ld_bf16) {
@@ -391,7 +393,11 @@ vocab_ce_dx_kernel(const float* __restrict__ part_max, const float* __restrict__
       const float pm = part_max[(size_t)(c * 4) * M + row];  // the 4 column groups share one max
       if (pm > -INFINITY) u += part_u[((size_t)c * M + row) * h + j] * exp2f(pm - m);
     }
-    val = (u / ssum - __bfloat162float(w[(size_t)j * ldw + label])) / n_valid;
+    // vocabulary-parallel: normalise by the GLOBAL log-sum-exp; the one-hot term belongs to the
+    // shard that owns the label (labels of other shards are remapped to >= V)
+    const float pexp = lse_global ? u * exp2f(m - lse_global[row] * LOG2E) : u / ssum;
+    const float wt = label < V ? __bfloat162float(w[(size_t)j * ldw + label]) : 0.f;
+    val = (pexp - wt) / n_valid;
   }
   if (gate && !(__bfloat162float(gate[(size_t)row * ld_gate + j]) > 0.f)) val = 0.f;
   if (out_f32) out_f32[(size_t)row * h + j] = val;
@@ -750,14 +756,15 @@ extern "C" int b4cp_vocab_ce_fwd(const void* x_bf16, long ldx, long M, int h, co
   dim3 grid(p.n_mtiles, p.n_chunks);
   vocab_ce_fwd_kernel<<<grid, NUM_THREADS, smem, st>>>(tmX, tmW, p);
   vocab_ce_merge_kernel<<<ceil_div(M, 256), 256, 0, st>>>(p.part_max, p.part_sum, 4 * p.n_chunks,
-                                                          (int)M, labels, lse, tgt);
+                                                          (int)M, V, labels, lse, tgt);
   note_launches(2);
   B4CP_LAUNCH_CHECK();
   return 0;
 }
 
 extern "C" int b4cp_vocab_ce_dx(long M, int h, int V, const int32_t* labels,
-                                const float* loss_stats, const void* w_bf16, long ldw,
+                                const float* loss_stats, const float* lse_global,
+                                const void* w_bf16, long ldw,
                                 const void* gate_bf16, long ld_gate, float* out_f32, void* out_bf16,
                                 long ld_bf16, const void* workspace, void* stream) {
   B4CP_CHECK_ARG(h == 128, "vocab_ce_dx: h=%d unsupported", h);
@@ -770,7 +777,7 @@ extern "C" int b4cp_vocab_ce_dx(long M, int h, int V, const int32_t* labels,
   const float* part_sum = part_max + (size_t)4 * chunks * M;
   const float* part_u = part_sum + (size_t)4 * chunks * M;
   vocab_ce_dx_kernel<<<ceil_div(M, 2), 256, 0, (cudaStream_t)stream>>>(
-      part_max, part_sum, part_u, chunks, (int)M, h, labels, loss_stats,
+      part_max, part_sum, part_u, chunks, (int)M, h, labels, loss_stats, lse_global, V,
       (const __nv_bfloat16*)w_bf16, ldw, (const __nv_bfloat16*)gate_bf16, ld_gate, out_f32,
       (__nv_bfloat16*)out_bf16, ld_bf16);
   note_launches(1);
@@ -812,6 +819,48 @@ extern "C" int b4cp_vocab_ce_bwd(const void* x_bf16, long ldx, long M, int h, co
                                  227 * 1024));
   const int grid = std::min(148, p.n_vtiles);
   vocab_ce_bwd_kernel<<<grid, NUM_THREADS, smem, st>>>(tmX, tmW, p);
+  note_launches(1);
+  B4CP_LAUNCH_CHECK();
+  return 0;
+}
+
+namespace b4cp {
+// labels of a vocabulary shard [v_begin, v_begin + v_count): padded rows stay -1, labels owned by
+// the shard become local ids, labels owned elsewhere become a value >= v_count (row is valid, but
+// no local column is its target)
+__global__ void __launch_bounds__(256)
+shard_labels_kernel(const int32_t* __restrict__ labels, long M, int v_begin, int v_count,
+                    int32_t* __restrict__ out) {
+  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (i >= M) return;
+  const int t = labels[i];
+  out[i] = t < 0 ? -1 : ((t >= v_begin && t < v_begin + v_count) ? t - v_begin : 0x3FFFFFFF);
+}
+// out[m] = log sum_r exp(parts[r][m])
+__global__ void __launch_bounds__(256)
+lse_merge_kernel(const float* __restrict__ parts, int R, long M, float* __restrict__ out) {
+  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (i >= M) return;
+  float m = -INFINITY;
+  for (int r = 0; r < R; ++r) m = fmaxf(m, parts[(size_t)r * M + i]);
+  float s = 0.f;
+  for (int r = 0; r < R; ++r) s += expf(parts[(size_t)r * M + i] - m);
+  out[i] = m + logf(s);
+}
+}  // namespace b4cp
+
+extern "C" int b4cp_shard_labels(const int32_t* labels, long M, int v_begin, int v_count,
+                                 int32_t* out, void* stream) {
+  if (M == 0) return 0;
+  shard_labels_kernel<<<ceil_div(M, 256), 256, 0, (cudaStream_t)stream>>>(labels, M, v_begin, v_count, out);
+  note_launches(1);
+  B4CP_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int b4cp_lse_merge(const float* parts, int n_parts, long M, float* out, void* stream) {
+  if (M == 0) return 0;
+  lse_merge_kernel<<<ceil_div(M, 256), 256, 0, (cudaStream_t)stream>>>(parts, n_parts, M, out);
   note_launches(1);
   B4CP_LAUNCH_CHECK();
   return 0;

@@ -25,13 +25,14 @@ def site(layer, k):
 
 
 class Param:
-    __slots__ = ("name", "shape", "w", "g", "m", "v", "wb", "offset", "numel")
+    __slots__ = ("name", "shape", "w", "g", "m", "v", "wb", "offset", "numel", "replicated")
 
     def __init__(self, name, shape):
         self.name, self.shape = name, tuple(shape)
         self.numel = int(np.prod(shape))
         self.w = self.g = self.m = self.v = self.wb = None
         self.offset = 0
+        self.replicated = True  # False: a per-rank shard, excluded from the data-parallel all-reduce
 
 
 class ParamStore:
@@ -44,10 +45,11 @@ class ParamStore:
         self.flat_w = self.flat_g = self.flat_m = self.flat_v = None
         self.step_dev = None
 
-    def add(self, name, init, shadow=False):
+    def add(self, name, init, shadow=False, replicated=True):
         init = np.ascontiguousarray(init, dtype=np.float32)
         assert name not in self.params, name
         self.params[name] = Param(name, init.shape)
+        self.params[name].replicated = replicated
         self._init[name] = init
         if shadow:
             self._shadow.add(name)
@@ -91,6 +93,20 @@ class ParamStore:
 
     def get_weights(self):
         return {n: p.w.detach().cpu().numpy().copy() for n, p in self.params.items()}
+
+    def replicated_grad_runs(self):
+        """Maximal contiguous slices of flat_g that hold replicated parameters (what data
+        parallelism all-reduces; vocabulary-parallel shards are already complete per rank)."""
+        runs = []
+        for p in sorted(self.params.values(), key=lambda q: q.offset):
+            if not p.replicated:
+                continue
+            end = p.offset + (p.numel + 63) // 64 * 64
+            if runs and runs[-1][1] == p.offset:
+                runs[-1][1] = end
+            else:
+                runs.append([p.offset, end])
+        return [self.flat_g[a:b] for a, b in runs]
 
     def get_grads(self):
         return {n: p.g.detach().cpu().numpy().copy() for n, p in self.params.items()}
@@ -435,3 +451,128 @@ class VocabOutputEngine:
         z = self.logits(ab, M)
         ops.topk_rows(z, self.V, k, out_ids=ids)
         return ids
+
+
+class VocabParallelOutputEngine(VocabOutputEngine):
+    """The Dense(V) output layer sharded by contiguous vocabulary ranges over a process group
+    (the reference only replicates head.py:36's kernel under MirroredStrategy).
+
+    Rank r owns columns [v_begin, v_end) of the kernel and bias.  Per step: all-gather the head
+    hidden rows and labels of every rank, run the fused projection + online-softmax kernels on the
+    local shard for ALL rows, all-gather the per-shard log-sum-exps and merge them, all-reduce the
+    target logits, and - in backward - reduce-scatter the per-shard dX partials back to the rank
+    that owns each row.  dW / db of the shard are complete locally (they saw every row) and are
+    excluded from the data-parallel gradient all-reduce.  Loss statistics are global by
+    construction.  Every rank must present the same row capacity M."""
+
+    stats_are_global = True
+
+    def __init__(self, store, prefix, in_dim, vocab, rng, group=None):
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("vocabulary-parallel output layer needs torch.distributed initialised")
+        self.group = group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.store, self.prefix, self.h, self.V_total = store, prefix, int(in_dim), int(vocab)
+        if self.h != 128:
+            raise ValueError("vocabulary-parallel output layer needs a 128-wide head (fused kernels)")
+        # contiguous shards whose boundaries are multiples of 8 (bf16 leading-dimension rule)
+        per = ld8((self.V_total + self.world - 1) // self.world)
+        self.v_begin = min(self.rank * per, self.V_total)
+        self.v_end = min(self.v_begin + per, self.V_total)
+        self.V = self.v_end - self.v_begin
+        if self.V <= 0:
+            raise ValueError(f"rank {self.rank} would own an empty vocabulary shard")
+        full = glorot_uniform(rng, self.h, self.V_total)  # same draw as the replicated layer
+        store.add(f"{prefix}.out.w", full[:, self.v_begin:self.v_end], shadow=True, replicated=False)
+        store.add(f"{prefix}.out.b", np.zeros(self.V), replicated=False)
+        self.pool = BufferPool()
+        self.saved = None
+
+    def common_rows(self, M):
+        """Row capacity shared by all ranks (max over the group); extra rows are padding."""
+        import torch.distributed as dist
+        t = torch.tensor([int(M)], dtype=torch.int64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        return int(t.item())
+
+    def _gather_rows(self, ab, M, labels):
+        import torch.distributed as dist
+        W_ = self.world
+        ab_all = self.pool.get("ab_all", (W_ * M, ab.shape[1]), BF16)
+        dist.all_gather_into_tensor(ab_all, ab[:M], group=self.group)
+        lab_all = None
+        if labels is not None:
+            lab_all = self.pool.get("labels_all", (W_ * M,), I32)
+            dist.all_gather_into_tensor(lab_all, labels[:M], group=self.group)
+        return ab_all, lab_all
+
+    def loss_forward(self, ab, M, labels, loss_stats, need_grad=True):
+        import torch.distributed as dist
+        W_ = self.world
+        ab_all, lab_all = self._gather_rows(ab, M, labels)
+        Ma = W_ * M
+        lab_sh = ops.shard_labels(lab_all, self.v_begin, self.V, out=self.pool.get("labels_shard", (Ma,), I32))
+        lse_parts = self.pool.get("lse_parts", (W_, Ma))
+        lse_loc = self.pool.get("lse_local", (Ma,))
+        tgt = self.pool.get("tgt", (Ma,))
+        t0 = ops.TIMER.begin("vocab_ce")
+        ops.vocab_ce_fwd(ab_all, Ma, self.h, self.W.wb, self.b.w, self.V, lab_sh, lse_loc, tgt,
+                         want_dx=need_grad)
+        ops.TIMER.end("vocab_ce", t0)
+        dist.all_gather_into_tensor(lse_parts.view(-1), lse_loc, group=self.group)
+        dist.all_reduce(tgt, op=dist.ReduceOp.SUM, group=self.group)
+        lse = ops.lse_merge(lse_parts, out=self.pool.get("lse", (Ma,)))
+        ops.ce_loss_reduce(lse, tgt, lab_all, loss_stats)  # global sum and count, same on all ranks
+        self.saved = dict(ab=ab_all, M=M, Ma=Ma, labels=lab_sh, lse=lse, z=None)
+
+    def loss_backward(self, loss_stats, gate, out_f32=None, out_bf16=None):
+        import torch.distributed as dist
+        sv = self.saved
+        M, Ma, h = sv["M"], sv["Ma"], self.h
+        dx_all = self.pool.get("dx_all", (Ma, h))
+        t0 = ops.TIMER.begin("vocab_ce")
+        ops.vocab_ce_dx(Ma, h, self.V, sv["labels"], loss_stats, self.W.wb, None, out_f32=dx_all,
+                        lse_global=sv["lse"])
+        ops.vocab_ce_bwd(sv["ab"], Ma, h, self.W.wb, self.b.w, self.V, sv["labels"], sv["lse"],
+                         loss_stats, self.W.g, self.b.g)
+        ops.TIMER.end("vocab_ce", t0)
+        dx_loc = self.pool.get("dx_local", (1, M, h))
+        dist.reduce_scatter_tensor(dx_loc.view(-1), dx_all.view(-1), op=dist.ReduceOp.SUM,
+                                   group=self.group)
+        ops.reduce_splits_ex(dx_loc, M, h, gate, out_f32, out_bf16)  # ReLU gate + casts
+
+    def topk(self, ab, M, k):
+        """Global (M, k) top-k: per-shard fused scoring + top-k with global ids, all-gather of the
+        world * k candidates per row, exact merge (ties -> lower id, as on one GPU)."""
+        import torch.distributed as dist
+        if k > 104:
+            raise ValueError("vocabulary-parallel top-k supports k <= 104")
+        W_ = self.world
+        ab_all, _ = self._gather_rows(ab, M, None)
+        Ma = W_ * M
+        kk = min(k, self.V)
+        ids_l = self.pool.get(f"vp_ids{k}", (Ma, k), I32)
+        sc_l = self.pool.get(f"vp_sc{k}", (Ma, k))
+        if kk < k:
+            ids_l.fill_(-1)
+            sc_l.fill_(float("-inf"))
+        t0 = ops.TIMER.begin("score_topk")
+        ops.score_topk(ab_all, Ma, self.h, self.W.wb, self.b.w, self.V, kk, out_ids=ids_l,
+                       out_scores=sc_l, id_base=self.v_begin, V_total=self.V_total)
+        ops.TIMER.end("score_topk", t0)
+        # exchange: rank r needs the candidates of ITS rows from every shard -> all-to-all
+        ids_x = self.pool.get(f"vp_idsx{k}", (W_, M, k), I32)
+        sc_x = self.pool.get(f"vp_scx{k}", (W_, M, k))
+        dist.all_to_all_single(ids_x.view(-1), ids_l.view(-1), group=self.group)
+        dist.all_to_all_single(sc_x.view(-1), sc_l.view(-1), group=self.group)
+        cand_ids = ids_x.permute(1, 0, 2).contiguous().view(M, W_ * k)
+        cand_sc = sc_x.permute(1, 0, 2).contiguous().view(M, W_ * k)
+        ids = self.pool.get(f"topk{k}", (M, k), I32)
+        ops.topk_candidates(cand_sc, cand_ids, self.V_total, k, out_ids=ids)
+        return ids
+
+    def logits(self, ab, M):
+        raise NotImplementedError("vocabulary-parallel output layer never materialises logits")
+
+    probabilities = logits

@@ -5,7 +5,7 @@ import numpy as np
 import torch
 
 from . import ops
-from .engine import MlpEngine, VocabOutputEngine, glorot_uniform
+from .engine import MlpEngine, VocabOutputEngine, VocabParallelOutputEngine, glorot_uniform
 from .ops import BF16, F32, I32, ld8
 
 
@@ -67,12 +67,21 @@ class ClozeOutput:
 class SoftMaxHead(_Head):
     """SoftMaxHead(dense_layer_dims, output_vocab_size) — head.py:29-47."""
 
-    def __init__(self, dense_layer_dims, output_vocab_size, **kwargs):
+    def __init__(self, dense_layer_dims, output_vocab_size, vocab_parallel=False,
+                 vocab_parallel_group=None, **kwargs):
+        """vocab_parallel=True (an extension; the reference only replicates) shards the output
+        kernel by vocabulary ranges over `vocab_parallel_group` (default: the world)."""
         super().__init__(dense_layer_dims, **kwargs)
         self.output_vocab_size = int(output_vocab_size)
+        self.vocab_parallel = bool(vocab_parallel)
+        self.vocab_parallel_group = vocab_parallel_group
 
     def _build_output(self, store, h, rng):
-        self.vocab = VocabOutputEngine(store, self.prefix, h, self.output_vocab_size, rng)
+        if self.vocab_parallel:
+            self.vocab = VocabParallelOutputEngine(store, self.prefix, h, self.output_vocab_size,
+                                                   rng, group=self.vocab_parallel_group)
+        else:
+            self.vocab = VocabOutputEngine(store, self.prefix, h, self.output_vocab_size, rng)
 
     def call(self, inputs, **kwargs):
         """inputs: fp32 (..., in_dim) device tensor -> (..., V) probabilities (materialised)."""

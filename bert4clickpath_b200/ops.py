@@ -366,10 +366,11 @@ def vocab_ce_fwd(xb, M, h, wb, bias, V, labels, lse, tgt, want_dx=False):
            L.c_int(1 if want_dx else 0), L.ptr(lse), L.ptr(tgt), L.ptr(ws), L.stream_ptr())
 
 
-def vocab_ce_dx(M, h, V, labels, loss_stats, wb, gate=None, out_f32=None, out_bf16=None):
+def vocab_ce_dx(M, h, V, labels, loss_stats, wb, gate=None, out_f32=None, out_bf16=None,
+                lse_global=None):
     ws = _vocab_ws(M, V, h)
     L.call("b4cp_vocab_ce_dx", L.c_long(M), L.c_int(h), L.c_int(V), L.ptr(labels),
-           L.ptr(loss_stats), L.ptr(wb), L.c_long(wb.stride(0)), L.ptr(gate),
+           L.ptr(loss_stats), L.ptr(lse_global), L.ptr(wb), L.c_long(wb.stride(0)), L.ptr(gate),
            L.c_long(gate.stride(0) if gate is not None else 0), L.ptr(out_f32), L.ptr(out_bf16),
            L.c_long(out_bf16.stride(0) if out_bf16 is not None else 0), L.ptr(ws), L.stream_ptr())
 
@@ -380,7 +381,24 @@ def vocab_ce_bwd(xb, M, h, wb, bias, V, labels, lse, loss_stats, dW, db):
            L.ptr(loss_stats), L.ptr(dW), L.ptr(db), L.stream_ptr())
 
 
-def score_topk(xb, M, h, wb, bias, V, k, out_ids=None, out_scores=None):
+def shard_labels(labels, v_begin, v_count, out=None):
+    M = labels.numel()
+    if out is None:
+        out = empty((M,), I32)
+    L.call("b4cp_shard_labels", L.ptr(labels), L.c_long(M), L.c_int(v_begin), L.c_int(v_count),
+           L.ptr(out), L.stream_ptr())
+    return out
+
+
+def lse_merge(parts, out=None):
+    R, M = parts.shape
+    if out is None:
+        out = empty((M,))
+    L.call("b4cp_lse_merge", L.ptr(parts), L.c_int(R), L.c_long(M), L.ptr(out), L.stream_ptr())
+    return out
+
+
+def score_topk(xb, M, h, wb, bias, V, k, out_ids=None, out_scores=None, id_base=0, V_total=0):
     """Fused scoring + exact top-k (scores never written to HBM)."""
     fn = L.lib().b4cp_score_topk_workspace_bytes
     fn.restype = ctypes.c_long
@@ -388,6 +406,18 @@ def score_topk(xb, M, h, wb, bias, V, k, out_ids=None, out_scores=None):
     if out_ids is None:
         out_ids = empty((M, k), I32)
     L.call("b4cp_score_topk", L.ptr(xb), L.c_long(xb.stride(0)), L.c_long(M), L.c_int(h), L.ptr(wb),
-           L.c_long(wb.stride(0)), L.ptr(bias), L.c_int(V), L.c_int(k), L.ptr(out_ids),
-           L.ptr(out_scores), L.c_long(out_ids.stride(0)), L.ptr(ws), L.stream_ptr())
+           L.c_long(wb.stride(0)), L.ptr(bias), L.c_int(V), L.c_int(k), L.c_int(id_base),
+           L.c_int(V_total), L.ptr(out_ids), L.ptr(out_scores), L.c_long(out_ids.stride(0)),
+           L.ptr(ws), L.stream_ptr())
+    return out_ids, out_scores
+
+
+def topk_candidates(cand_scores, cand_ids, V, k, out_ids=None, out_scores=None):
+    """Exact top-k over explicit (score, id) candidate rows [rows, n_cand] (ids < V, -1 = empty)."""
+    rows, n_cand = cand_scores.shape
+    if out_ids is None:
+        out_ids = empty((rows, k), I32)
+    L.call("b4cp_topk_candidates", L.ptr(cand_scores), L.ptr(cand_ids),
+           L.c_long(cand_scores.stride(0)), L.c_long(rows), L.c_int(n_cand), L.c_int(V), L.c_int(k),
+           L.ptr(out_ids), L.ptr(out_scores), L.c_long(out_ids.stride(0)), L.stream_ptr())
     return out_ids, out_scores

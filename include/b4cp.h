@@ -190,13 +190,24 @@ long b4cp_vocab_ce_workspace_bytes(long M, int V, int h);
 int b4cp_vocab_ce_fwd(const void* x_bf16, long ldx, long M, int h, const void* w_bf16, long ldw,
                       const float* bias, int V, const int32_t* labels, int want_dx, float* lse,
                       float* tgt, void* workspace, void* stream);
+/* dx with lse_global != NULL is the vocabulary-parallel form: the shard's partial contribution
+ * gate * (U * exp(max - lse_global) - [label < V] W[:, label]) / n, to be summed over shards. */
 int b4cp_vocab_ce_dx(long M, int h, int V, const int32_t* labels, const float* loss_stats,
-                     const void* w_bf16, long ldw, const void* gate_bf16, long ld_gate,
+                     const float* lse_global, const void* w_bf16, long ldw, const void* gate_bf16,
+                     long ld_gate,
                      float* out_f32, void* out_bf16, long ld_bf16, const void* workspace,
                      void* stream);
 int b4cp_vocab_ce_bwd(const void* x_bf16, long ldx, long M, int h, const void* w_bf16, long ldw,
                       const float* bias, int V, const int32_t* labels, const float* lse,
                       const float* loss_stats, float* dW, float* db, void* stream);
+
+/* Vocabulary-parallel helpers (the output kernel sharded by contiguous vocabulary ranges across
+ * GPUs; the reference has no such mode - its MirroredStrategy replicates head.py:36's kernel):
+ * remap labels for a shard (-1 stays, owned -> local id, others -> a valid id >= v_count), and
+ * merge per-shard log-sum-exps: out[m] = log sum_r exp(parts[r][m]). */
+int b4cp_shard_labels(const int32_t* labels, long M, int v_begin, int v_count, int32_t* out,
+                      void* stream);
+int b4cp_lse_merge(const float* parts, int n_parts, long M, float* out, void* stream);
 
 /* Probability inputs (a materialised SoftMaxHead output): z = log(clip(p, lo, hi)) reproduces
  * K.sparse_categorical_crossentropy(from_logits=False) of TF 2.3 when followed by
@@ -227,9 +238,11 @@ int b4cp_topk_candidates(const float* cand_scores, const int32_t* cand_ids, long
  * (M x V) scores (head.py:36,45 + examples/BERT4Rec/source/utils.py:176,:245).  x_bf16: bf16
  * [M][ldx]; w_bf16: bf16 [h][ldw] Keras kernel; h in {64,128}; k <= 104.  Exact, ties -> lower id. */
 long b4cp_score_topk_workspace_bytes(long M, int V, int k);
+/* id_base is added to every reported id and V_total (0 = V) bounds the reported ids: a vocabulary
+ * shard [id_base, id_base + V) of a V_total-wide output layer reports global ids */
 int b4cp_score_topk(const void* x_bf16, long ldx, long M, int h, const void* w_bf16, long ldw,
-                    const float* bias, int V, int k, int32_t* out_ids, float* out_scores,
-                    long ld_out, void* workspace, void* stream);
+                    const float* bias, int V, int k, int id_base, int V_total, int32_t* out_ids,
+                    float* out_scores, long ld_out, void* workspace, void* stream);
 int b4cp_rank_metrics(const int32_t* topk_ids, long M, int k, long ld, const int32_t* labels,
                       float* counters, void* stream);
 

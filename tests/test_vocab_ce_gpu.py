@@ -139,3 +139,109 @@ def test_fused_score_topk_is_exact(cuda_lib, M, h, V, k):
     # and the materialised top-k kernel agrees
     ids2, _ = ops.topk_rows(logits, V, k)
     assert torch.equal(ids, ids2)
+
+
+# ------------------------------------------------------------------ vocabulary-parallel pieces
+def _shards(V, R):
+    per = (V + R - 1) // R
+    per = (per + 7) // 8 * 8
+    return [(min(r * per, V), min(r * per + per, V)) for r in range(R)]
+
+
+@pytest.mark.parametrize("M,V,R", [(300, 1237, 2), (77, 54293, 3), (1000, 5000, 4)])
+def test_vocab_shards_merge_to_the_unsharded_result(cuda_lib, M, V, R):
+    """The vocabulary-parallel algebra on one GPU: per-shard fused kernels (labels remapped by
+    b4cp_shard_labels), b4cp_lse_merge, dx with the global lse summed over shards, shard-local
+    dW/db — against the unsharded kernels and the oracle.  (The NCCL exchanges of
+    VocabParallelOutputEngine are replaced by sums / concatenation here.)"""
+    from bert4clickpath_b200 import ops
+    h = 128
+    x, w, b, labels = make(M, h, V, 11 * M + V)
+    z = x @ w + b.astype(np.float64)
+    loss, dz, n = O.cloze_ce_from_logits(z, labels)
+    xb, wb, bd, ld = to_dev(x, w, b, labels)
+    # unsharded reference run of the same kernels
+    lse0, tgt0, stats0 = (torch.empty(M, device="cuda"), torch.empty(M, device="cuda"),
+                          torch.empty(2, device="cuda"))
+    ops.vocab_ce_fwd(xb, M, h, wb, bd, V, ld, lse0, tgt0, want_dx=True)
+    ops.ce_loss_reduce(lse0, tgt0, ld, stats0)
+    dX0, dW0, db0 = (torch.empty((M, h), device="cuda"), torch.empty((h, V), device="cuda"),
+                     torch.empty(V, device="cuda"))
+    ops.vocab_ce_dx(M, h, V, ld, stats0, wb, None, dX0, None)
+    ops.vocab_ce_bwd(xb, M, h, wb, bd, V, ld, lse0, stats0, dW0, db0)
+
+    shards = _shards(V, R)
+    lse_parts = torch.empty((R, M), device="cuda")
+    tgt_sum = torch.zeros(M, device="cuda")
+    lab_sh, w_sh, b_sh = [], [], []
+    for r, (v0, v1) in enumerate(shards):
+        xs, ws, bs, _ = to_dev(x, w[:, v0:v1], b[v0:v1], labels)
+        ls = ops.shard_labels(ld, v0, v1 - v0)
+        want = np.where(labels < 0, -1, np.where((labels >= v0) & (labels < v1), labels - v0, 0x3FFFFFFF))
+        assert ls.cpu().numpy().tolist() == want.tolist()
+        lab_sh.append(ls); w_sh.append(ws); b_sh.append(bs)
+    stats = torch.empty(2, device="cuda")
+    # forward of every shard, then the merge
+    for r, (v0, v1) in enumerate(shards):
+        tgt = torch.full((M,), float("nan"), device="cuda")
+        ops.vocab_ce_fwd(xb, M, h, w_sh[r], b_sh[r], v1 - v0, lab_sh[r], lse_parts[r], tgt, want_dx=False)
+        tgt_sum += tgt
+    lse = ops.lse_merge(lse_parts)
+    ops.ce_loss_reduce(lse, tgt_sum, ld, stats)
+    torch.cuda.synchronize()
+    m = z.max(-1)
+    np.testing.assert_allclose(lse.cpu().numpy(), m + np.log(np.exp(z - m[:, None]).sum(-1)), rtol=2e-5, atol=2e-5)
+    s = stats.cpu().numpy()
+    assert s[1] == n and abs(s[0] / s[1] - loss) < 1e-5 * abs(loss)
+    np.testing.assert_allclose(s, stats0.cpu().numpy(), rtol=2e-6)
+    # backward: the workspace holds one shard's forward at a time
+    dX = torch.zeros((M, h), device="cuda")
+    for r, (v0, v1) in enumerate(shards):
+        Vs = v1 - v0
+        scratch_lse, scratch_tgt = torch.empty(M, device="cuda"), torch.empty(M, device="cuda")
+        ops.vocab_ce_fwd(xb, M, h, w_sh[r], b_sh[r], Vs, lab_sh[r], scratch_lse, scratch_tgt, want_dx=True)
+        part = torch.full((M, h), float("nan"), device="cuda")
+        ops.vocab_ce_dx(M, h, Vs, lab_sh[r], stats, w_sh[r], None, part, None, lse_global=lse)
+        dX += part
+        dW = torch.full((h, Vs), float("nan"), device="cuda")
+        db = torch.full((Vs,), float("nan"), device="cuda")
+        ops.vocab_ce_bwd(xb, M, h, w_sh[r], b_sh[r], Vs, lab_sh[r], lse, stats, dW, db)
+        torch.cuda.synchronize()
+        for name, got, ref in (("dW", dW, dW0[:, v0:v1]), ("db", db, db0[v0:v1])):
+            g, f = got.cpu().numpy(), ref.cpu().numpy()
+            assert np.isfinite(g).all()
+            assert np.abs(g - f).max() <= 2e-3 * max(np.abs(f).max(), 1e-12), (name, r)
+    torch.cuda.synchronize()
+    g = dX.cpu().numpy()
+    dX_exact = dz @ w.T
+    assert np.abs(g - dX_exact).max() <= 4e-3 * np.abs(dX_exact).max()
+    assert np.abs(g - dX0.cpu().numpy()).max() <= 4e-3 * np.abs(dX_exact).max()
+    assert not g[labels < 0].any()
+
+
+@pytest.mark.parametrize("M,V,R,k", [(200, 5000, 2, 10), (64, 54293, 4, 100), (33, 300, 3, 100)])
+def test_vocab_shards_topk_merge_is_exact(cuda_lib, M, V, R, k):
+    """Per-shard fused top-k with global ids (id_base) + candidate merge == unsharded top-k,
+    including exact score ties that straddle shard boundaries."""
+    from bert4clickpath_b200 import ops
+    h = 128
+    x, w, b, _ = make(M, h, V, 5 * M + V)
+    w[:, V // 4:] = w[:, (np.arange(V - V // 4) % 37)]
+    b[V // 4:] = b[np.arange(V - V // 4) % 37]
+    labels = np.zeros(M, dtype=np.int32)
+    xb, wb, bd, _ = to_dev(x, w, b, labels)
+    ids0, sc0 = ops.score_topk(xb, M, h, wb, bd, V, k, out_scores=torch.empty((M, k), device="cuda"))
+    cand_i, cand_s = [], []
+    for v0, v1 in _shards(V, R):
+        _, ws, bs, _ = to_dev(x, w[:, v0:v1], b[v0:v1], labels)
+        kk = min(k, v1 - v0)
+        i = torch.full((M, k), -1, dtype=torch.int32, device="cuda")
+        s = torch.full((M, k), float("-inf"), device="cuda")
+        ops.score_topk(xb, M, h, ws, bs, v1 - v0, kk, out_ids=i, out_scores=s, id_base=v0, V_total=V)
+        cand_i.append(i); cand_s.append(s)
+    ci, cs = torch.cat(cand_i, 1).contiguous(), torch.cat(cand_s, 1).contiguous()
+    ids, sc = ops.topk_candidates(cs, ci, V, k, out_scores=torch.empty((M, k), device="cuda"))
+    torch.cuda.synchronize()
+    assert torch.equal(ids, ids0)
+    kk = min(k, V)
+    assert torch.equal(sc[:, :kk], sc0[:, :kk])
