@@ -580,9 +580,17 @@ extern "C" int b4cp_gemm_bf16(const void* A, int a_mn, long lda, const void* B, 
   p.BN = pick_bn(N, p.b_mn);
   p.k_tiles_total = ceil_div(K, BK);
   if (splits < 1) splits = 1;
+  const int splits_requested = splits;
   if (splits > p.k_tiles_total) splits = p.k_tiles_total;
   p.k_tiles_per_split = ceil_div(p.k_tiles_total, splits);
-  splits = ceil_div(p.k_tiles_total, p.k_tiles_per_split);
+  splits = ceil_div(p.k_tiles_total, p.k_tiles_per_split);  // no empty K ranges
+  if (splits < splits_requested && ep->out_f32) {
+    // the caller will sum `splits_requested` partials: the ones no CTA writes must read as zero
+    for (int z = splits; z < splits_requested; ++z)
+      B4CP_CUDA(cudaMemsetAsync(ep->out_f32 + (size_t)z * ep->split_stride, 0,
+                                ((size_t)(M - 1) * ep->ld_f32 + N) * sizeof(float),
+                                (cudaStream_t)stream));
+  }
   B4CP_CHECK_ARG(splits == 1 || (ep->out_f32 && !ep->out_bf16 && !ep->bias && !ep->relu &&
                                  !ep->gate && !ep->addend),
                  "gemm: split-K writes raw fp32 partials only");
@@ -668,5 +676,7 @@ extern "C" int b4cp_gemm_splits_for(int M, int N, int K) {
   long s = (148 + tiles - 1) / tiles;
   if (s > kt) s = kt;
   if (s < 1) s = 1;
-  return (int)s;
+  // the count b4cp_gemm_bf16 launches: equal K-tile ranges, none empty
+  const int per = ceil_div(kt, (int)s);
+  return ceil_div(kt, per);
 }

@@ -77,12 +77,23 @@ def main():
     out["loss_replicated"], out["loss_vocab_parallel"] = float(sa[0] / sa[1]), float(sb[0] / sb[1])
     ok &= sa[1] == sb[1] and abs(sa[0] - sb[0]) <= 2e-5 * abs(sa[0])
     ga, gb = A.store.get_grads(), Bm.store.get_grads()
-    worst = 0.0
+    # parameters whose gradient is analytically zero (attention key biases) hold rounding noise
+    # only: measure every error against at least 1e-3 of the largest gradient norm
+    floor = 1e-3 * max(np.linalg.norm(ga[n]) for n in ga)
+    worst, worst_name = 0.0, None
     for n in ga:
         if n in (name_w, name_b):
             continue
-        worst = max(worst, rel(gb[n], ga[n]))
+        e = float(np.linalg.norm(gb[n].astype(np.float64) - ga[n]) / max(np.linalg.norm(ga[n]), floor))
+        if e > worst:
+            worst, worst_name = e, n
+    if os.environ.get("VP_VERBOSE"):
+        for n in ga:
+            if n not in (name_w, name_b):
+                print(f"[rank {rank}] {n:28s} |A|={np.linalg.norm(ga[n]):.3e} |B|={np.linalg.norm(gb[n]):.3e} "
+                      f"|B-A|={np.linalg.norm(gb[n].astype(np.float64) - ga[n]):.3e}", flush=True)
     out["grad_rel_replicated_params_max"] = worst
+    out["grad_rel_replicated_params_argmax"] = worst_name
     out["grad_rel_out_w_shard"] = rel(gb[name_w], ga[name_w][:, vp.v_begin:vp.v_end])
     out["grad_rel_out_b_shard"] = rel(gb[name_b], ga[name_b][vp.v_begin:vp.v_end])
     ok &= worst < 5e-3 and out["grad_rel_out_w_shard"] < 5e-3 and out["grad_rel_out_b_shard"] < 5e-3

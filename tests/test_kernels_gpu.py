@@ -43,6 +43,37 @@ def test_gemm_all_majors(cuda_lib, a_mn, b_mn, shape):
     np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=0, atol=2e-5 * np.abs(ref).max())
 
 
+@pytest.mark.parametrize("K", [58 * 64, 57 * 64 + 5, 64, 200])
+@pytest.mark.parametrize("requested", [19, 7, 64])
+def test_splitk_partials_never_stale(cuda_lib, K, requested):
+    """Regression: the launcher evens out K ranges and may run fewer splits than requested; the
+    partials nobody writes must read as zero (they used to keep the workspace's old contents, so a
+    weight gradient silently picked up a previous GEMM's partial sums)."""
+    from bert4clickpath_b200 import ops
+    rng = np.random.default_rng(K + requested)
+    M, N = 512, 256
+    A = bf16_round(rng.normal(size=(K, M)))   # a^T dy: both operands MN-major
+    B = bf16_round(rng.normal(size=(K, N)))
+    ref = A.astype(np.float64).T @ B.astype(np.float64)
+    Ad, Bd = dev(A, torch.bfloat16), dev(B, torch.bfloat16)
+    part = torch.full((requested, M, N), float("nan"), device="cuda")
+    ops.gemm(Ad, 1, Bd, 1, M, N, K, out_f32=part, splits=requested)
+    out = torch.empty((M, N), device="cuda")
+    ops.reduce_splits(part, out)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=0, atol=3e-5 * np.abs(ref).max())
+    # the planner returns exactly the number of K ranges the launcher runs
+    s = ops.gemm_splits_for(M, N, K)
+    kt = -(-K // 64)
+    assert -(-kt // -(-kt // s)) == s
+    dirty = ops.WS.get("splitk", s * M * N * 4).view(torch.float32)
+    dirty.fill_(float("nan"))
+    out2 = torch.empty((M, N), device="cuda")
+    ops.gemm_splitk(Ad, 1, Bd, 1, M, N, K, out2)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(out2.cpu().numpy(), ref, rtol=0, atol=3e-5 * np.abs(ref).max())
+
+
 def test_gemm_epilogues_and_splitk(cuda_lib):
     from bert4clickpath_b200 import ops
     rng = np.random.default_rng(3)
