@@ -361,9 +361,11 @@ def _vocab_ws(M, V, h):
 
 def vocab_ce_fwd(xb, M, h, wb, bias, V, labels, lse, tgt, want_dx=False):
     ws = _vocab_ws(M, V, h)
+    t0 = TIMER.begin("k:vocab_ce_fwd")
     L.call("b4cp_vocab_ce_fwd", L.ptr(xb), L.c_long(xb.stride(0)), L.c_long(M), L.c_int(h),
            L.ptr(wb), L.c_long(wb.stride(0)), L.ptr(bias), L.c_int(V), L.ptr(labels),
            L.c_int(1 if want_dx else 0), L.ptr(lse), L.ptr(tgt), L.ptr(ws), L.stream_ptr())
+    TIMER.end("k:vocab_ce_fwd", t0)
 
 
 def vocab_ce_dx(M, h, V, labels, loss_stats, wb, gate=None, out_f32=None, out_bf16=None,
@@ -376,9 +378,11 @@ def vocab_ce_dx(M, h, V, labels, loss_stats, wb, gate=None, out_f32=None, out_bf
 
 
 def vocab_ce_bwd(xb, M, h, wb, bias, V, labels, lse, loss_stats, dW, db):
+    t0 = TIMER.begin("k:vocab_ce_bwd")
     L.call("b4cp_vocab_ce_bwd", L.ptr(xb), L.c_long(xb.stride(0)), L.c_long(M), L.c_int(h),
            L.ptr(wb), L.c_long(wb.stride(0)), L.ptr(bias), L.c_int(V), L.ptr(labels), L.ptr(lse),
            L.ptr(loss_stats), L.ptr(dW), L.ptr(db), L.stream_ptr())
+    TIMER.end("k:vocab_ce_bwd", t0)
 
 
 def shard_labels(labels, v_begin, v_count, out=None):

@@ -201,3 +201,104 @@ def test_two_rank_gloo_data_parallel_equals_single_process():
     flat = np.concatenate([G[k].reshape(-1) for k in sorted(G)])
     assert abs(loss_dp - loss) < 1e-12
     np.testing.assert_allclose(flat_dp, flat, rtol=1e-9, atol=1e-13)
+
+
+# --------------------------------------------------------------------------- vocabulary parallel
+def _vp_problem(world, M=7, h=16, V=53, seed=5):
+    rng = np.random.default_rng(seed)
+    X = rng.normal(size=(world, M, h))
+    W = rng.normal(size=(h, V)) * 0.4
+    b = rng.normal(size=V) * 0.2
+    labels = rng.integers(0, V, size=(world, M)).astype(np.int32)
+    labels[0, 2] = -1
+    labels[world - 1, 0] = -1
+    return X, W, b, labels
+
+
+def _vp_worker(rank, world, port, q):
+    """The exchange schedule of engine.VocabParallelOutputEngine with NumPy arithmetic."""
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    X, W, b, labels = _vp_problem(world)
+    M, h = X.shape[1:]
+    V = W.shape[1]
+    per = -(-(-(-V // world)) // 8) * 8
+    v0, v1 = min(rank * per, V), min(rank * per + per, V)
+    Ws, bs = W[:, v0:v1], b[v0:v1]
+    # all-gather rows and labels
+    x_all = [torch.empty(M, h, dtype=torch.float64) for _ in range(world)]
+    dist.all_gather(x_all, torch.from_numpy(X[rank]))
+    l_all = [torch.empty(M, dtype=torch.int32) for _ in range(world)]
+    dist.all_gather(l_all, torch.from_numpy(labels[rank]))
+    xa, la = torch.cat(x_all).numpy(), torch.cat(l_all).numpy()
+    lsh = np.where(la < 0, -1, np.where((la >= v0) & (la < v1), la - v0, 0x3FFFFFFF))  # b4cp_shard_labels
+    z = xa @ Ws + bs
+    m = z.max(-1)
+    lse_loc = m + np.log(np.exp(z - m[:, None]).sum(-1))
+    owned = (lsh >= 0) & (lsh < v1 - v0)
+    tgt = np.where(owned, z[np.arange(len(la)), np.where(owned, lsh, 0)], 0.0)
+    parts = [torch.empty(len(la), dtype=torch.float64) for _ in range(world)]
+    dist.all_gather(parts, torch.from_numpy(lse_loc))
+    P = torch.stack(parts).numpy()
+    pm = P.max(0)
+    lse = pm + np.log(np.exp(P - pm).sum(0))                       # b4cp_lse_merge
+    tg = torch.from_numpy(tgt)
+    dist.all_reduce(tg)
+    valid = la >= 0
+    n = valid.sum()
+    loss = float(((lse - tg.numpy()) * valid).sum() / n)
+    # backward: shard-local dZ with the global lse; dX partial -> reduce-scatter; dW local
+    dz = np.exp(z - lse[:, None]) * valid[:, None] / n
+    dz[np.nonzero(owned)[0], lsh[owned]] -= 1.0 / n
+    dx_all = torch.from_numpy(dz @ Ws.T)
+    dx_loc = torch.empty(M, h, dtype=torch.float64)
+    dist.reduce_scatter(dx_loc, list(dx_all.view(world, M, h).unbind(0)))
+    dW, db = xa.T @ dz, dz.sum(0)
+    # top-k: per-shard candidates with global ids, all-to-all so each rank merges its own rows
+    k = 5
+    order = np.lexsort((np.broadcast_to(np.arange(v1 - v0), z.shape), -z), axis=-1)[:, :k]
+    cs = torch.from_numpy(np.take_along_axis(z, order, 1).copy())
+    ci = torch.from_numpy((order + v0).astype(np.int64))
+    cs_x, ci_x = torch.empty_like(cs), torch.empty_like(ci)
+    dist.all_to_all_single(cs_x, cs)
+    dist.all_to_all_single(ci_x, ci)
+    cs_m = cs_x.view(world, M, k).permute(1, 0, 2).reshape(M, world * k).numpy()
+    ci_m = ci_x.view(world, M, k).permute(1, 0, 2).reshape(M, world * k).numpy()
+    sel = np.lexsort((ci_m, -cs_m), axis=-1)[:, :k]
+    top = np.take_along_axis(ci_m, sel, 1)
+    q.put((rank, loss, dx_loc.numpy(), (v0, v1), dW, db, top))
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_vocab_parallel_equals_single_process():
+    import torch.multiprocessing as mp
+    world = 2
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_vp_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted((q.get(timeout=120) for _ in range(world)), key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    X, W, b, labels = _vp_problem(world)
+    M, h = X.shape[1:]
+    xa, la = X.reshape(-1, h), labels.reshape(-1)
+    z = xa @ W + b
+    loss, dz, n = O.cloze_ce_from_logits(z, la)
+    dX, dW, db = dz @ W.T, xa.T @ dz, dz.sum(0)
+    want_top = O.top_k_ids(z, 5)
+    for rank, loss_r, dx_loc, (v0, v1), dW_r, db_r, top in res:
+        assert abs(loss_r - loss) < 1e-12
+        np.testing.assert_allclose(dx_loc, dX[rank * M:(rank + 1) * M], rtol=1e-10, atol=1e-14)
+        np.testing.assert_allclose(dW_r, dW[:, v0:v1], rtol=1e-10, atol=1e-14)
+        np.testing.assert_allclose(db_r, db[v0:v1], rtol=1e-10, atol=1e-14)
+        assert top.tolist() == want_top[rank * M:(rank + 1) * M].tolist()
