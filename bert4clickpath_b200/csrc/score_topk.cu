@@ -219,11 +219,21 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   }
 }
 
+// Vocabulary chunks per row tile: one CTA per SM is resident, so the critical path is
+// waves-of-148 x tiles-per-chunk; each chunk adds k candidates per row to the merge.
 static int score_chunks(int n_mtiles, int n_vtiles, int* tiles_per_chunk) {
-  int chunks = std::max(1, (148 + n_mtiles - 1) / n_mtiles);
-  chunks = std::min(chunks, n_vtiles);
-  *tiles_per_chunk = (n_vtiles + chunks - 1) / chunks;
-  return (n_vtiles + *tiles_per_chunk - 1) / *tiles_per_chunk;
+  int best = 1;
+  double best_cost = 1e30;
+  for (int c = 1; c <= std::min(n_vtiles, 148); ++c) {
+    const int tpc = (n_vtiles + c - 1) / c;
+    const int real = (n_vtiles + tpc - 1) / tpc;
+    if (real != c) continue;
+    const long waves = ((long)n_mtiles * c + 147) / 148;
+    const double cost = (double)waves * tpc + 1.0 * c;
+    if (cost < best_cost) best_cost = cost, best = c;
+  }
+  *tiles_per_chunk = (n_vtiles + best - 1) / best;
+  return best;
 }
 
 }  // namespace b4cp

@@ -365,8 +365,13 @@ vocab_ce_merge_kernel(const float* __restrict__ part_max, const float* __restric
 }
 
 // dX[row][j] = gate * ( sum_c U_c[row][j] 2^(m_c - m) / s  -  W[j][label] ) / n_valid
-// (h = 128: thread j of a 128-thread group owns one column; two rows per block)
-__global__ void __launch_bounds__(256)
+// h = 128: one warp per row, lane l owns columns 4l..4l+3 (128-bit loads of the U partials, all
+// chunk loads independent); the (max, sum) partials of the row (4 per chunk, <= 96) are spread
+// over the lanes and combined with warp reductions.
+static constexpr int DX_ROWS_PER_BLOCK = 8;
+static constexpr int MAX_FWD_CHUNKS = 24;
+
+__global__ void __launch_bounds__(32 * DX_ROWS_PER_BLOCK)
 vocab_ce_dx_kernel(const float* __restrict__ part_max, const float* __restrict__ part_sum,
                    const float* __restrict__ part_u, int n_chunks, int M, int h,
                    const int32_t* __restrict__ labels, const float* __restrict__ loss_stats,
@@ -374,34 +379,73 @@ vocab_ce_dx_kernel(const float* __restrict__ part_max, const float* __restrict__
                    const __nv_bfloat16* __restrict__ w, long ldw,
                    const __nv_bfloat16* __restrict__ gate, long ld_gate,
                    float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16, long ld_bf16) {
-  const int row = blockIdx.x * 2 + (threadIdx.x >> 7);
-  const int j = threadIdx.x & 127;
-  if (row >= M || j >= h) return;
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * DX_ROWS_PER_BLOCK + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const int j = lane * 4;
   const int label = labels[row];
   const float n_valid = loss_stats[1];
-  float val = 0.f;
+  float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
   if (label >= 0 && n_valid > 0.f) {
+    const int n_parts = 4 * n_chunks;
+    float pmx[3], psm[3];
     float m = -INFINITY;
-    for (int c = 0; c < 4 * n_chunks; ++c) m = fmaxf(m, part_max[(size_t)c * M + row]);
-    float ssum = 0.f;
-    for (int c = 0; c < 4 * n_chunks; ++c) {
-      const float pm = part_max[(size_t)c * M + row];
-      if (pm > -INFINITY) ssum += part_sum[(size_t)c * M + row] * exp2f(pm - m);
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+      const int c = lane + 32 * t;
+      pmx[t] = c < n_parts ? __ldg(part_max + (size_t)c * M + row) : -INFINITY;
+      psm[t] = c < n_parts ? __ldg(part_sum + (size_t)c * M + row) : 0.f;
+      m = fmaxf(m, pmx[t]);
     }
-    float u = 0.f;
+    m = warp_max(m);
+    float ssum = 0.f;
+#pragma unroll
+    for (int t = 0; t < 3; ++t)
+      if (pmx[t] > -INFINITY) ssum += psm[t] * exp2f(pmx[t] - m);
+    ssum = warp_sum(ssum);
+    float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
     for (int c = 0; c < n_chunks; ++c) {
-      const float pm = part_max[(size_t)(c * 4) * M + row];  // the 4 column groups share one max
-      if (pm > -INFINITY) u += part_u[((size_t)c * M + row) * h + j] * exp2f(pm - m);
+      const int pc = c * 4;  // the 4 column groups of a chunk share one max
+      const float mine = (pc >> 5) == 0 ? pmx[0] : ((pc >> 5) == 1 ? pmx[1] : pmx[2]);
+      const float pm = __shfl_sync(0xffffffffu, mine, pc & 31);
+      const float sc = pm > -INFINITY ? exp2f(pm - m) : 0.f;
+      const float4 v = __ldg(reinterpret_cast<const float4*>(part_u + ((size_t)c * M + row) * h + j));
+      u.x = fmaf(v.x, sc, u.x); u.y = fmaf(v.y, sc, u.y);
+      u.z = fmaf(v.z, sc, u.z); u.w = fmaf(v.w, sc, u.w);
     }
     // vocabulary-parallel: normalise by the GLOBAL log-sum-exp; the one-hot term belongs to the
     // shard that owns the label (labels of other shards are remapped to >= V)
-    const float pexp = lse_global ? u * exp2f(m - lse_global[row] * LOG2E) : u / ssum;
-    const float wt = label < V ? __bfloat162float(w[(size_t)j * ldw + label]) : 0.f;
-    val = (pexp - wt) / n_valid;
+    const float norm = lse_global ? exp2f(m - __ldg(lse_global + row) * LOG2E) : 1.f / ssum;
+    float wt[4] = {0.f, 0.f, 0.f, 0.f};
+    if (label < V) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) wt[i] = __bfloat162float(w[(size_t)(j + i) * ldw + label]);
+    }
+    const float inv_n = 1.f / n_valid;
+    val.x = (u.x * norm - wt[0]) * inv_n;
+    val.y = (u.y * norm - wt[1]) * inv_n;
+    val.z = (u.z * norm - wt[2]) * inv_n;
+    val.w = (u.w * norm - wt[3]) * inv_n;
   }
-  if (gate && !(__bfloat162float(gate[(size_t)row * ld_gate + j]) > 0.f)) val = 0.f;
-  if (out_f32) out_f32[(size_t)row * h + j] = val;
-  if (out_bf16) out_bf16[(size_t)row * ld_bf16 + j] = __float2bfloat16_rn(val);
+  if (gate) {
+    const uint2 g = *reinterpret_cast<const uint2*>(gate + (size_t)row * ld_gate + j);
+    const __nv_bfloat162 g0 = *reinterpret_cast<const __nv_bfloat162*>(&g.x);
+    const __nv_bfloat162 g1 = *reinterpret_cast<const __nv_bfloat162*>(&g.y);
+    if (!(__bfloat162float(g0.x) > 0.f)) val.x = 0.f;
+    if (!(__bfloat162float(g0.y) > 0.f)) val.y = 0.f;
+    if (!(__bfloat162float(g1.x) > 0.f)) val.z = 0.f;
+    if (!(__bfloat162float(g1.y) > 0.f)) val.w = 0.f;
+  }
+  if (out_f32) *reinterpret_cast<float4*>(out_f32 + (size_t)row * h + j) = val;
+  if (out_bf16) {
+    __nv_bfloat162 o0 = __floats2bfloat162_rn(val.x, val.y);
+    __nv_bfloat162 o1 = __floats2bfloat162_rn(val.z, val.w);
+    uint2 o;
+    o.x = *reinterpret_cast<uint32_t*>(&o0);
+    o.y = *reinterpret_cast<uint32_t*>(&o1);
+    *reinterpret_cast<uint2*>(out_bf16 + (size_t)row * ld_bf16 + j) = o;
+  }
 }
 
 // =============================================================================== backward
@@ -691,11 +735,24 @@ vocab_ce_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   }
 }
 
+// Vocabulary chunks per row tile.  One CTA per SM is resident, so the launch runs in waves of 148
+// CTAs and its critical path is waves x tiles-per-chunk tile iterations; every extra chunk adds
+// one more (max, sum, U) partial per row for vocab_ce_dx_kernel to read (~2.5 tile iterations of
+// HBM time).  Pick the count that minimises the sum instead of "about two waves" (448 CTAs = 3.03
+// waves at the bench shape cost a whole extra wave).
 static int fwd_chunks(int n_mtiles, int n_vtiles, int* tiles_per_chunk) {
-  int chunks = std::max(1, (2 * 148 + n_mtiles - 1) / n_mtiles);
-  chunks = std::min(chunks, n_vtiles);
-  *tiles_per_chunk = (n_vtiles + chunks - 1) / chunks;
-  return (n_vtiles + *tiles_per_chunk - 1) / *tiles_per_chunk;
+  int best = 1;
+  double best_cost = 1e30;
+  for (int c = 1; c <= std::min(n_vtiles, MAX_FWD_CHUNKS); ++c) {
+    const int tpc = (n_vtiles + c - 1) / c;
+    const int real = (n_vtiles + tpc - 1) / tpc;
+    if (real != c) continue;
+    const long waves = ((long)n_mtiles * c + 147) / 148;
+    const double cost = (double)waves * tpc + 2.5 * c;
+    if (cost < best_cost) best_cost = cost, best = c;
+  }
+  *tiles_per_chunk = (n_vtiles + best - 1) / best;
+  return best;
 }
 
 }  // namespace b4cp
@@ -776,7 +833,8 @@ extern "C" int b4cp_vocab_ce_dx(long M, int h, int V, const int32_t* labels,
   const float* part_max = (const float*)workspace;
   const float* part_sum = part_max + (size_t)4 * chunks * M;
   const float* part_u = part_sum + (size_t)4 * chunks * M;
-  vocab_ce_dx_kernel<<<ceil_div(M, 2), 256, 0, (cudaStream_t)stream>>>(
+  B4CP_CHECK_ARG(ld_gate % 4 == 0 && ld_bf16 % 4 == 0, "vocab_ce_dx: leading dimensions must be multiples of 4");
+  vocab_ce_dx_kernel<<<ceil_div(M, DX_ROWS_PER_BLOCK), 32 * DX_ROWS_PER_BLOCK, 0, (cudaStream_t)stream>>>(
       part_max, part_sum, part_u, chunks, (int)M, h, labels, loss_stats, lse_global, V,
       (const __nv_bfloat16*)w_bf16, ldw, (const __nv_bfloat16*)gate_bf16, ld_gate, out_f32,
       (__nv_bfloat16*)out_bf16, ld_bf16);
