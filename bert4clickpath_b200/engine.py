@@ -367,16 +367,24 @@ class VocabOutputEngine:
     def b(self):
         return self.store[f"{self.prefix}.out.b"]
 
-    def logits(self, ab, M):
-        """fp32 [M, ld8(V)] logits (materialised; validation / small-V path)."""
+    def _row_chunks(self, M):
+        """Row ranges whose fp32 logits fit MATERIALIZE_LIMIT_BYTES (multiples of 128 rows)."""
+        rows = max(128, self.MATERIALIZE_LIMIT_BYTES // (ld8(self.V) * 4) // 128 * 128)
+        return [(a, min(a + rows, M)) for a in range(0, M, rows)]
+
+    def logits(self, ab, M, chunk=None):
+        """fp32 [rows, ld8(V)] logits of rows `chunk` = (a, b) of ab (default: all M rows, which
+        must fit the limit).  Materialised; validation / small-V / h != 128 path."""
         Vp = ld8(self.V)
-        if M * Vp * 4 > self.MATERIALIZE_LIMIT_BYTES:
-            raise MemoryError(f"refusing to materialise {M}x{self.V} logits; use the fused path")
-        z = self.pool.get("logits", (M, Vp))
+        a, b = chunk if chunk is not None else (0, M)
+        if (b - a) * Vp * 4 > max(self.MATERIALIZE_LIMIT_BYTES, 128 * Vp * 4):
+            raise MemoryError(f"refusing to materialise {b - a}x{self.V} logits; use the fused path")
+        cap = min(M, self._row_chunks(M)[0][1])
+        z = self.pool.get("logits", (cap, Vp))
         t0 = ops.TIMER.begin("vocab_gemm")
-        dense_fwd(ab, self.h, self.W, self.b, M, out_f32=z)
+        dense_fwd(ab[a:b], self.h, self.W, self.b, b - a, out_f32=z)
         ops.TIMER.end("vocab_gemm", t0)
-        return z
+        return z[: b - a]
 
     def probabilities(self, ab, M):
         z = self.logits(ab, M)
@@ -399,17 +407,24 @@ class VocabOutputEngine:
         """loss_stats <- (sum over valid rows of lse - z_t, number of valid rows)."""
         lse = self.pool.get("lse", (M,))
         tgt = self.pool.get("tgt", (M,))
+        z = None
         if self.fused:
             t0 = ops.TIMER.begin("vocab_ce")
             ops.vocab_ce_fwd(ab, M, self.h, self.W.wb, self.b.w, self.V, labels, lse, tgt,
                              want_dx=need_grad)
             ops.TIMER.end("vocab_ce", t0)
-            z = None
+            chunks = None
         else:
-            z = self.logits(ab, M)
-            ops.ce_rows_stats(z, self.V, labels, lse, tgt)
+            # materialised path (head widths the fused kernels do not cover): logits exist for one
+            # bounded row range at a time; with several ranges the backward recomputes them
+            chunks = self._row_chunks(M)
+            for a, b in chunks:
+                z = self.logits(ab, M, (a, b))
+                ops.ce_rows_stats(z, self.V, labels[a:b], lse[a:b], tgt[a:b])
+            if len(chunks) > 1:
+                z = None
         ops.ce_loss_reduce(lse, tgt, labels, loss_stats)
-        self.saved = dict(ab=ab, M=M, labels=labels, z=z, lse=lse)
+        self.saved = dict(ab=ab, M=M, labels=labels, z=z, lse=lse, chunks=chunks)
 
     def loss_backward(self, loss_stats, gate, out_f32=None, out_bf16=None):
         """Gradients of mean CE (normalised by loss_stats[1], which may already be the global
@@ -417,39 +432,56 @@ class VocabOutputEngine:
         produced ab, or None) as fp32 and/or bf16."""
         sv = self.saved
         ab, M, V, h = sv["ab"], sv["M"], self.V, self.h
-        if sv["z"] is None:  # fused: logits are recomputed tile by tile, never materialised
+        if sv["chunks"] is None:  # fused: logits are recomputed tile by tile, never materialised
             t0 = ops.TIMER.begin("vocab_ce")
             ops.vocab_ce_dx(M, h, V, sv["labels"], loss_stats, self.W.wb, gate, out_f32, out_bf16)
             ops.vocab_ce_bwd(ab, M, h, self.W.wb, self.b.w, V, sv["labels"], sv["lse"], loss_stats,
                              self.W.g, self.b.g)
             ops.TIMER.end("vocab_ce", t0)
             return
-        dz = self.pool.get("dz", (M, ld8(V)), BF16)
-        ops.ce_rows_grad(sv["z"], V, sv["labels"], sv["lse"], loss_stats, dz, None)
-        t0 = ops.TIMER.begin("vocab_gemm")
-        ops.gemm_splitk(ab, 1, dz, 1, h, V, M, self.W.g, ws_name="splitk_vocab")
-        ops.TIMER.end("vocab_gemm", t0)
-        ops.colsum_bf16(dz, M, V, self.b.g)
-        # dx = dz W^T : K = V is long and M x h is small -> split-K with a gated reduce
-        splits = ops.gemm_splits_for(M, h, V)
-        part = ops.WS.get("splitk_dx", splits * M * h * 4).view(F32)[: splits * M * h].view(splits, M, h)
-        t0 = ops.TIMER.begin("vocab_gemm")
-        ops.gemm(dz, 0, self.W.wb, 0, M, h, V, out_f32=part, splits=splits)
-        ops.TIMER.end("vocab_gemm", t0)
-        ops.reduce_splits_ex(part, M, h, gate, out_f32, out_bf16)
+        chunks = sv["chunks"]
+        rows_cap = chunks[0][1] - chunks[0][0]
+        dz_all = self.pool.get("dz", (rows_cap, ld8(V)), BF16)
+        db_parts = self.pool.get("db_parts", (len(chunks), V)) if len(chunks) > 1 else None
+        for ci, (a, b) in enumerate(chunks):
+            rows = b - a
+            z = sv["z"] if sv["z"] is not None else self.logits(ab, M, (a, b))
+            dz = dz_all[:rows]
+            ops.ce_rows_grad(z, V, sv["labels"][a:b], sv["lse"][a:b], loss_stats, dz, None)
+            t0 = ops.TIMER.begin("vocab_gemm")
+            if len(chunks) == 1:
+                ops.gemm_splitk(ab, 1, dz, 1, h, V, rows, self.W.g, ws_name="splitk_vocab")
+            else:  # dW accumulates over the row ranges in a fixed order (in-place addend)
+                ops.gemm(ab[a:b], 1, dz, 1, h, V, rows, addend=self.W.g if ci else None,
+                         out_f32=self.W.g)
+            ops.TIMER.end("vocab_gemm", t0)
+            ops.colsum_bf16(dz, rows, V, self.b.g if db_parts is None else db_parts[ci])
+            # dx = dz W^T : K = V is long and rows x h is small -> split-K with a gated reduce
+            splits = ops.gemm_splits_for(rows, h, V)
+            part = ops.WS.get("splitk_dx", splits * rows * h * 4).view(F32)[: splits * rows * h]
+            part = part.view(splits, rows, h)
+            t0 = ops.TIMER.begin("vocab_gemm")
+            ops.gemm(dz, 0, self.W.wb, 0, rows, h, V, out_f32=part, splits=splits)
+            ops.TIMER.end("vocab_gemm", t0)
+            ops.reduce_splits_ex(part, rows, h, gate[a:b] if gate is not None else None,
+                                 out_f32[a:b] if out_f32 is not None else None,
+                                 out_bf16[a:b] if out_bf16 is not None else None)
+        if db_parts is not None:
+            ops.reduce_splits(db_parts, self.b.g)
 
     def topk(self, ab, M, k):
         """(M, k) int32 ids of the k highest scores per row, ties -> lower id.  Fused scoring +
         heap top-k on the tensor cores when the head width allows it (scores never reach HBM),
-        otherwise materialised logits + radix-select top-k."""
+        otherwise logits materialised for a bounded row range at a time + radix-select top-k."""
         ids = self.pool.get(f"topk{k}", (M, k), I32)
         if self.h in (64, 128) and k <= 104 and not self.force_materialized:
             t0 = ops.TIMER.begin("score_topk")
             ops.score_topk(ab, M, self.h, self.W.wb, self.b.w, self.V, k, out_ids=ids)
             ops.TIMER.end("score_topk", t0)
             return ids
-        z = self.logits(ab, M)
-        ops.topk_rows(z, self.V, k, out_ids=ids)
+        for a, b in self._row_chunks(M):
+            z = self.logits(ab, M, (a, b))
+            ops.topk_rows(z, self.V, k, out_ids=ids[a:b])
         return ids
 
 

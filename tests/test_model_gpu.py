@@ -170,6 +170,8 @@ def test_three_adam_steps_track_oracle(cuda_lib):
     dict(V=300, d=32, L=2, H=2, dff=100, hd=[64, 32], B=16, max_len=20, lengths="beauty", mp=0.4),
     dict(V=1000, d=64, L=2, H=2, dff=100, hd=[128, 64], B=64, max_len=50, lengths="dense", mp=0.15),
     dict(V=500, d=128, L=1, H=4, dff=100, hd=[], B=32, max_len=30, lengths="beauty", mp=0.4),
+    # C4-shaped: d_model 256, 4 heads of depth 64, head [] -> V (h = 256: materialised vocabulary path)
+    dict(V=2000, d=256, L=2, H=4, dff=100, hd=[], B=8, max_len=40, lengths="beauty", mp=0.15),
 ])
 def test_kernels_match_bf16_emulation_on_c1_like_shapes(cuda_lib, cfg):
     """Ragged (beauty-shaped) and dense sessions, dff=100 (not a multiple of 8), heads with and
@@ -298,3 +300,45 @@ def test_multivariable_segment_head_forward_matches_oracle(cuda_lib, segment):
     loss = bc.MaskedLoss(bc.binary_crossentropy, pos_weight=3.0)(y, probs)
     want_loss = O.masked_loss(y, probs.astype(np.float64), O.binary_crossentropy_probs, pos_weight=3.0)
     assert abs(loss - want_loss) < 1e-4 * abs(want_loss)
+
+
+def test_h256_vocabulary_stage_in_bounded_row_ranges(cuda_lib):
+    """C4 / C5 head width (h = 256, head [] -> V): the vocabulary stage materialises logits for a
+    bounded row range at a time.  Forcing 128-row ranges must reproduce the single-range loss,
+    gradients (dW accumulated over ranges) and top-k ids."""
+    import bert4clickpath_b200 as bc
+    from bert4clickpath_b200.synthetic import make_cloze_batch
+    V, d = 3001, 256
+
+    def build():
+        head = bc.SoftMaxHead(dense_layer_dims=[], output_vocab_size=V)
+        return bc.ClickstreamTransformer(
+            sequential_input_config={"items": ["asin"]}, feature_vocabs={"items": V},
+            embedding_dims={"items": d}, head_unit=head, value_to_head=bc.INPUT_MASKING_TOKEN,
+            num_encoder_layers=1, num_attention_heads=4, dropout_rate=0.0, seed=3)
+
+    batch = make_cloze_batch(np.random.default_rng(1), 64, V, max_len=50, mode="train",
+                             masked_percentage=0.15)
+    ids = torch.from_numpy(batch["ids"]).cuda().view(-1)
+    labels = torch.from_numpy(batch["labels"]).cuda()
+    B, S = batch["ids"].shape
+    ev = make_cloze_batch(np.random.default_rng(2), 300, V, max_len=50, mode="eval")
+    ev_ids = torch.from_numpy(ev["ids"]).cuda().view(-1)
+    res = []
+    for limit in (None, 1):
+        m = build()
+        assert not m.head.vocab.fused
+        if limit is not None:
+            m.head.vocab.MATERIALIZE_LIMIT_BYTES = limit      # -> 128-row ranges
+            assert len(m.head.vocab._row_chunks(batch["n_masked"])) == -(-batch["n_masked"] // 128) > 2
+        st = m.cloze_forward_backward([ids], labels, B, S, n_masked=batch["n_masked"],
+                                      training=False).cpu().numpy()
+        top, _ = m.topk_ids([ev_ids], 300, ev["ids"].shape[1], 10, n_masked=300)
+        res.append((st, m.store.get_grads(), top.cpu().numpy().copy()))
+    (s0, g0, t0), (s1, g1, t1) = res
+    np.testing.assert_allclose(s1, s0, rtol=1e-6)
+    assert (t0 == t1).all()
+    floor = 1e-3 * max(np.linalg.norm(v) for v in g0.values())
+    for k in g0:
+        e = np.linalg.norm(g1[k].astype(np.float64) - g0[k]) / max(np.linalg.norm(g0[k]), floor)
+        assert e < 2e-3, (k, e)  # split-K order differs per range -> bf16 rounding of dX differs
