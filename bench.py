@@ -179,7 +179,7 @@ def run_ours(args, rank, world, local_rank):
         embedding_dims={"items": d}, head_unit=head, value_to_head=bc.INPUT_MASKING_TOKEN,
         num_encoder_layers=CFG["layers"], num_attention_heads=CFG["heads"],
         dropout_rate=CFG["dropout"], encoder_ff_dim=CFG["dff"], seed=0)
-    trainer = ClozeTrainStep(model, bc.Adam(1e-3, 0.9, 0.999, 1e-9))
+    trainer = ClozeTrainStep(model, bc.Adam(1e-3, 0.9, 0.999, 1e-9), use_graph=not args.no_graph)
     rng = np.random.default_rng(1234 + rank)
     n_ring = 4
     host = [make_cloze_batch(rng, B, V, CFG["max_len"], "train", CFG["mask_rate"], CFG["max_masked"])
@@ -202,16 +202,14 @@ def run_ours(args, rank, world, local_rank):
             return float(t.item())
         return ms
 
-    # ---- device-resident timing
-    for i in range(args.warmup):
+    # ---- device-resident timing (the step is one CUDA graph replay unless --no-graph; the first
+    # ClozeTrainStep.GRAPH_WARMUP_STEPS + 1 calls run eagerly / capture, so warm up past them)
+    for i in range(max(args.warmup, ClozeTrainStep.GRAPH_WARMUP_STEPS + 2)):
         trainer.step_device(dev[i % n_ring])
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ops.TIMER.reset()
-    ops.TIMER.enabled = True
-    launches0 = _lib.lib().b4cp_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
@@ -221,10 +219,29 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     clocks = sampler.stop() if rank == 0 else None
-    launches = _lib.lib().b4cp_launch_count() - launches0
+    loss_stats = stats.cpu().numpy()
+
+    # ---- per-kernel timing and launch count: the same step launched eagerly with CUDA-event
+    # brackets around the vocabulary-stage kernels (events cannot be read back from a graph)
+    graph_mode, trainer.use_graph = trainer.use_graph, False
+    n_kt = min(args.steps, 10)
+    trainer.step_device(dev[0])
+    barrier()
+    ops.TIMER.reset()
+    ops.TIMER.enabled = True
+    launches0 = _lib.lib().b4cp_launch_count()
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k0.record()
+    for i in range(n_kt):
+        trainer.step_device(dev[i % n_ring])
+    k1.record()
+    barrier()
+    launches_per_step = (_lib.lib().b4cp_launch_count() - launches0) // n_kt
+    launches = launches_per_step * args.steps
+    eager_ms_per_step = k0.elapsed_time(k1) / n_kt
     ops.TIMER.enabled = False
     kt = ops.TIMER.totals_ms()
-    loss_stats = stats.cpu().numpy()
+    trainer.use_graph = graph_mode
 
     # ---- end-to-end timing through the public API (pinned host buffers in, loss out)
     trainer.step_host(*pinned[0])
@@ -287,11 +304,11 @@ def run_ours(args, rank, world, local_rank):
 
     def kernel_line(tag, flops, per_step=False):
         k_ms, k_n = kt.get(tag, (0.0, 0))
-        per = k_ms / max(args.steps if per_step else k_n, 1)
+        per = k_ms / max(n_kt if per_step else k_n, 1)
         ach = flops / (per * 1e-3) / 1e12 if per > 0 else 0.0
         return {"achieved": ach, "frac": ach / peak, "algorithmic_flops_per_launch": flops,
                 "ms_per_launch": per, "launches": k_n,
-                "kernel_share_of_step": (k_ms / max(args.steps, 1)) / step_ms}
+                "kernel_share_of_step": (k_ms / max(n_kt, 1)) / step_ms}
 
     mhv = float(M) * h * V
     traffic = None
@@ -332,6 +349,10 @@ def run_ours(args, rank, world, local_rank):
         "e2e": {"value": seqs_e2e, "unit": "seqs/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 8, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
+        "launch_mode": {"cuda_graph": bool(graph_mode), "kernels_per_step": int(launches_per_step),
+                        "eager_ms_per_step_with_event_brackets": eager_ms_per_step,
+                        "note": "value/e2e replay one captured graph per step; gpu_launches = "
+                                "kernels per step (counted on eagerly launched steps) x steps"},
         "roofline": roof,
         "cpu_baseline": cpu_base,
         "topk": topk,
@@ -345,6 +366,7 @@ def run_ours(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host")
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])

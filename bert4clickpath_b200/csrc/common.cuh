@@ -238,6 +238,15 @@ __device__ __host__ __forceinline__ uint32_t mix32(uint32_t x) {
   x ^= x >> 16;
   return x;
 }
+// A dropout seed argument is either the seed itself or, with bit 63 set, the address of an int32 in
+// device memory read when the kernel RUNS (B4CP_SEED_FROM_DEVICE in b4cp.h): a captured CUDA graph
+// then draws fresh masks on every replay from a counter a kernel of the same graph increments.
+__device__ __forceinline__ uint64_t resolve_seed(uint64_t seed) {
+  if (seed >> 63)
+    return (uint64_t)(uint32_t)__ldg(reinterpret_cast<const int32_t*>(seed & 0x00FFFFFFFFFFFFFFull));
+  return seed;
+}
+
 __device__ __host__ __forceinline__ bool dropout_keep(uint64_t seed, uint32_t site, uint64_t idx,
                                                       uint32_t thresh24) {
   uint32_t lo = (uint32_t)idx, hi = (uint32_t)(idx >> 32);

@@ -38,6 +38,7 @@ struct EmbedParams {
 template <int VEC>
 __global__ void __launch_bounds__(256)
 embed_fwd_kernel(const EmbedParams p, float* __restrict__ out, __nv_bfloat16* __restrict__ out_bf16) {
+  const uint64_t seed_v = resolve_seed(p.seed);
   const long per_tok = p.d_model / VEC;
   const long total = p.T * per_tok;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total;
@@ -70,7 +71,7 @@ embed_fwd_kernel(const EmbedParams p, float* __restrict__ out, __nv_bfloat16* __
     for (int j = 0; j < VEC; ++j) {
       o[j] = __fadd_rn(__fmul_rn(e[j], p.scale), pe[j]);
       if (p.thresh24) {
-        const bool keep = dropout_keep(p.seed, p.site, (uint64_t)(t * p.d_model + c + j), p.thresh24);
+        const bool keep = dropout_keep(seed_v, p.site, (uint64_t)(t * p.d_model + c + j), p.thresh24);
         o[j] = keep ? __fmul_rn(o[j], p.inv_keep) : 0.f;
       }
     }
@@ -293,6 +294,7 @@ segment_sum_kernel(const float* __restrict__ dout, int d_model, int off, int dim
                    const int* __restrict__ n_unique, const int* __restrict__ total_chunks,
                    float scale, float inv_keep, uint32_t thresh24, uint64_t seed, uint32_t site,
                    float* __restrict__ table_grad, float* __restrict__ partial) {
+  seed = resolve_seed(seed);
   const int warps_per_block = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
   const int U = *n_unique;

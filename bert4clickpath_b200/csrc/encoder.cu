@@ -257,6 +257,7 @@ residual_ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ r,
   const int lane = threadIdx.x & 31;
   const long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= T) return;
+  if (dp.thresh24) dp.seed = resolve_seed(dp.seed);
   float v[NPL];
   float sum = 0.f;
 #pragma unroll
@@ -305,6 +306,7 @@ residual_ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x
                        float* __restrict__ dx, __nv_bfloat16* __restrict__ dr_bf16, long ld_bf16,
                        float* __restrict__ partial) {
   __shared__ float red[8][3][NPL * 32];
+  if (dp.thresh24) dp.seed = resolve_seed(dp.seed);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nwarps = blockDim.x >> 5;
   float pg[NPL], pb[NPL], pr[NPL];
@@ -452,6 +454,7 @@ cast_f32_bf16_kernel(const float* __restrict__ in, long rows, int cols, long ld_
 
 __global__ void __launch_bounds__(256)
 dropout_mask_kernel(float* __restrict__ out, long n, DropSpec dp) {
+  if (dp.thresh24) dp.seed = resolve_seed(dp.seed);
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n;
        i += (long)gridDim.x * blockDim.x)
     out[i] = (!dp.thresh24 || dropout_keep(dp.seed, dp.site, (uint64_t)i, dp.thresh24)) ? dp.inv_keep : 0.f;

@@ -235,6 +235,12 @@ def colsum_bf16(x_bf16, T, n, out):
            L.c_long(x_bf16.stride(0)), L.ptr(out), L.ptr(ws), L.stream_ptr())
 
 
+def device_seed(counter_i32):
+    """Seed argument that makes kernels read the seed from a device int32 at run time
+    (B4CP_SEED_FROM_DEVICE): used by CUDA-graph replays."""
+    return (1 << 63) | int(counter_i32.data_ptr())
+
+
 def dropout_mask(n, rate, seed, site):
     out = empty((n,))
     L.call("b4cp_dropout_mask", L.ptr(out), L.c_long(n), L.c_float(rate), L.c_u64(seed),

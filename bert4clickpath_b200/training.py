@@ -20,10 +20,19 @@ class DeviceBatch:
 
 
 class ClozeTrainStep:
-    def __init__(self, model, optimizer=None):
+    """use_graph=True captures the whole step (forward, backward, NCCL gradient all-reduce, Adam)
+    into one CUDA graph per (B, S, masked-row capacity) after two eager steps, and replays it: the
+    ~160 kernel launches of a step cost one host call.  Dropout seeds are then read on the device
+    from the Adam step counter (B4CP_SEED_FROM_DEVICE), so every replay draws new masks."""
+
+    GRAPH_WARMUP_STEPS = 2
+
+    def __init__(self, model, optimizer=None, use_graph=False):
         self.model = model
         self.opt = optimizer or Adam()
         self.seed = 0
+        self.use_graph = bool(use_graph)
+        self._graphs = {}
         self._dev_ids = self._dev_labels = None
         self._host_stats = torch.empty(2, dtype=F32).pin_memory() if torch.cuda.is_available() else None
 
@@ -34,8 +43,45 @@ class ClozeTrainStep:
         B, S = batch["ids"].shape
         return DeviceBatch(ids, labels, B, S, batch["n_masked"])
 
+    def _eager(self, db, seed):
+        stats = self.model.cloze_forward_backward(db.ids, db.labels, db.B, db.S,
+                                                  n_masked=db.n_masked, training=True, seed=seed)
+        self.model.store.adam(self.opt.learning_rate, self.opt.beta_1, self.opt.beta_2,
+                              self.opt.epsilon)
+        return stats
+
+    def _step_graph(self, db):
+        from . import ops
+        key = (db.B, db.S, int(db.n_masked), len(db.ids))
+        st = self._graphs.get(key)
+        if st is None:
+            st = self._graphs[key] = dict(calls=0, graph=None)
+        seed = ops.device_seed(self.model.store.step_dev)
+        if st["graph"] is None:
+            st["calls"] += 1
+            if st["calls"] <= self.GRAPH_WARMUP_STEPS:   # real steps; they also size every buffer
+                return self._eager(db, seed)
+            st["ids"] = [torch.empty_like(t) for t in db.ids]
+            st["labels"] = torch.empty_like(db.labels)
+            sdb = DeviceBatch(st["ids"], st["labels"], db.B, db.S, db.n_masked)
+            timer_was, ops.TIMER.enabled = ops.TIMER.enabled, False
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                st["stats"] = self._eager(sdb, seed)
+            ops.TIMER.enabled = timer_was
+            st["graph"] = g
+        for dst, src in zip(st["ids"], db.ids):
+            if dst.data_ptr() != src.data_ptr():
+                dst.copy_(src, non_blocking=True)
+        if st["labels"].data_ptr() != db.labels.data_ptr():
+            st["labels"].copy_(db.labels, non_blocking=True)
+        st["graph"].replay()
+        return st["stats"]
+
     def step_device(self, db):
         """forward + backward + all-reduce + Adam; returns the device loss statistics."""
+        if self.use_graph:
+            return self._step_graph(db)
         self.seed += 1
         stats = self.model.cloze_forward_backward(db.ids, db.labels, db.B, db.S,
                                                   n_masked=db.n_masked, training=True,
@@ -52,9 +98,14 @@ class ClozeTrainStep:
             self._dev_ids = torch.empty(ids_pinned.shape, dtype=I32, device="cuda")
         if self._dev_labels is None or self._dev_labels.shape != labels_pinned.shape:
             self._dev_labels = torch.empty(labels_pinned.shape, dtype=F32, device="cuda")
-        self._dev_ids.copy_(ids_pinned, non_blocking=True)
-        self._dev_labels.copy_(labels_pinned, non_blocking=True)
-        db = DeviceBatch([self._dev_ids.view(-1)], self._dev_labels, B, S, n_masked)
+        dev_ids, dev_labels = self._dev_ids.view(-1), self._dev_labels
+        if self.use_graph:  # copy straight into the captured graph's input buffers
+            st = self._graphs.get((B, S, int(n_masked), 1))
+            if st is not None and st.get("graph") is not None:
+                dev_ids, dev_labels = st["ids"][0], st["labels"]
+        dev_ids.view(B, S).copy_(ids_pinned, non_blocking=True)
+        dev_labels.copy_(labels_pinned, non_blocking=True)
+        db = DeviceBatch([dev_ids], dev_labels, B, S, n_masked)
         stats = self.step_device(db)
         self._host_stats.copy_(stats, non_blocking=True)
         torch.cuda.current_stream().synchronize()

@@ -86,7 +86,11 @@ int b4cp_cast_f32_bf16(const float* in, long rows, int cols, long ld_in, void* o
  * `pe` is the fp32 [>=S][d_model] sinusoid table.  dropout_rate = 0 disables dropout; otherwise
  * kept values are scaled by 1/(1-rate) and the keep bit of element i is the one
  * b4cp_dropout_mask(seed, site) reports.  Bit-exact against the oracle when dropout is off.
+ * Every `seed` argument of this library is either the seed value (< 2^63) or
+ * B4CP_SEED_FROM_DEVICE(ptr): the seed is the int32 at device address `ptr` when the kernel runs,
+ * so a captured CUDA graph draws new masks on every replay.
  */
+#define B4CP_SEED_FROM_DEVICE(ptr) ((uint64_t)1 << 63 | (uint64_t)(uintptr_t)(ptr))
 int b4cp_embed_fwd(const int32_t* const* h_ids, const float* const* h_tables, const int* h_dims,
                    const int* h_rows, int F, const float* pe, int B, int S, float dropout_rate,
                    uint64_t seed, uint32_t site, float* out_f32, void* out_bf16, void* stream);

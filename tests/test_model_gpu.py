@@ -342,3 +342,47 @@ def test_h256_vocabulary_stage_in_bounded_row_ranges(cuda_lib):
     for k in g0:
         e = np.linalg.norm(g1[k].astype(np.float64) - g0[k]) / max(np.linalg.norm(g0[k]), floor)
         assert e < 2e-3, (k, e)  # split-K order differs per range -> bf16 rounding of dX differs
+
+
+def test_cuda_graph_replay_is_bit_identical_to_eager_steps(cuda_lib):
+    """ClozeTrainStep(use_graph=True): two eager steps, capture, replays.  With dropout seeds read
+    on the device from the Adam step counter the replayed steps must reproduce the eagerly
+    launched ones bit for bit (same kernels, same order, deterministic reductions)."""
+    import bert4clickpath_b200 as bc
+    from bert4clickpath_b200 import ops
+    from bert4clickpath_b200.synthetic import make_cloze_batch
+    from bert4clickpath_b200.training import ClozeTrainStep
+    V = 1237
+
+    def build():
+        head = bc.SoftMaxHead(dense_layer_dims=[64, 128], output_vocab_size=V)
+        return bc.ClickstreamTransformer(
+            sequential_input_config={"items": ["asin"]}, feature_vocabs={"items": V},
+            embedding_dims={"items": 64}, head_unit=head, value_to_head=bc.INPUT_MASKING_TOKEN,
+            num_encoder_layers=2, num_attention_heads=2, dropout_rate=0.1, seed=5)
+
+    rng = np.random.default_rng(0)
+    batches = [make_cloze_batch(rng, 32, V, max_len=30, mode="train") for _ in range(3)]
+    mg, me = build(), build()
+    tg = ClozeTrainStep(mg, bc.Adam(1e-3), use_graph=True)
+    te = ClozeTrainStep(me, bc.Adam(1e-3))
+    losses = []
+    for i in range(7):
+        b = batches[i % 3]
+        sg = tg.step_device(tg.to_device(b)).clone()
+        se = te._eager(te.to_device(b), ops.device_seed(me.store.step_dev)).clone()
+        torch.cuda.synchronize()
+        assert torch.equal(sg, se), i
+        losses.append(float(sg[0] / sg[1]))
+    assert len(tg._graphs) == 1 and next(iter(tg._graphs.values()))["graph"] is not None
+    wg, we = mg.store.get_weights(), me.store.get_weights()
+    for k in wg:
+        assert np.array_equal(wg[k], we[k]), k
+    assert int(mg.store.step_dev.item()) == 8
+    assert losses[-1] < losses[0]
+    # dropout masks differ from step to step (the seed is the step counter)
+    m1 = ops.dropout_mask(1000, 0.1, ops.device_seed(mg.store.step_dev), 1).clone()
+    ops.step_increment(mg.store.step_dev)
+    m2 = ops.dropout_mask(1000, 0.1, ops.device_seed(mg.store.step_dev), 1)
+    assert not torch.equal(m1, m2)
+    assert torch.equal(m2, ops.dropout_mask(1000, 0.1, 9, 1))  # device seed == same host seed
