@@ -388,6 +388,226 @@ residual_ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x
   }
 }
 
+// ---- vectorised variants for d in {64, 128, 256}: 128-bit accesses, d/4 (<= 32) lanes per row so
+// a warp covers 32 / LPR rows per pass and the statistics reduce over sub-warps.  Same math and the
+// same dropout bits (element index row * d + column) as the generic kernels above.
+template <int D>
+struct LnVec {
+  static constexpr int LPR = (D / 4) < 32 ? (D / 4) : 32;  // lanes per row
+  static constexpr int VPL = D / (4 * LPR);                // float4 per lane
+  static constexpr int RPW = 32 / LPR;                     // rows per warp
+};
+
+template <int LPR>
+__device__ __forceinline__ float subwarp_sum(float v) {
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ void store_bf16x4(__nv_bfloat16* dst, const float* v) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]);
+  __nv_bfloat162 b = __floats2bfloat162_rn(v[2], v[3]);
+  uint2 o;
+  o.x = *reinterpret_cast<uint32_t*>(&a);
+  o.y = *reinterpret_cast<uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(dst) = o;
+}
+
+template <int D>
+__global__ void __launch_bounds__(256)
+residual_ln_fwd_vec_kernel(const float* __restrict__ x, const float* __restrict__ r, long T,
+                           const float* __restrict__ gamma, const float* __restrict__ beta,
+                           DropSpec dp, float eps, float* __restrict__ y_f32,
+                           __nv_bfloat16* __restrict__ y_bf16, long ld_bf16) {
+  using C = LnVec<D>;
+  const int lane = threadIdx.x & 31;
+  const int lr = lane % C::LPR;
+  const long row = ((long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * C::RPW + lane / C::LPR;
+  const bool live = row < T;  // dead sub-rows still join the shuffles
+  if (dp.thresh24) dp.seed = resolve_seed(dp.seed);
+  float v[C::VPL][4];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < C::VPL; ++i) {
+    const int c = (lr + i * C::LPR) * 4;
+    float4 xv = make_float4(0.f, 0.f, 0.f, 0.f), rv = xv;
+    if (live) {
+      xv = *reinterpret_cast<const float4*>(x + row * D + c);
+      rv = *reinterpret_cast<const float4*>(r + row * D + c);
+    }
+    float rr[4] = {rv.x, rv.y, rv.z, rv.w};
+    const float xx[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (dp.thresh24)
+        rr[j] = dropout_keep(dp.seed, dp.site, (uint64_t)(row * D + c + j), dp.thresh24) ? rr[j] * dp.inv_keep : 0.f;
+      v[i][j] = xx[j] + rr[j];
+      sum += v[i][j];
+    }
+  }
+  const float mean = subwarp_sum<C::LPR>(sum) / (float)D;
+  float var = 0.f;
+#pragma unroll
+  for (int i = 0; i < C::VPL; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float dv = v[i][j] - mean;
+      var = fmaf(dv, dv, var);
+    }
+  var = subwarp_sum<C::LPR>(var) / (float)D;
+  const float rstd = rsqrtf(var + eps);
+  if (!live) return;
+#pragma unroll
+  for (int i = 0; i < C::VPL; ++i) {
+    const int c = (lr + i * C::LPR) * 4;
+    const float4 gv = __ldg(reinterpret_cast<const float4*>(gamma + c));
+    const float4 bv = __ldg(reinterpret_cast<const float4*>(beta + c));
+    const float gg[4] = {gv.x, gv.y, gv.z, gv.w}, bb[4] = {bv.x, bv.y, bv.z, bv.w};
+    float o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[j] = (v[i][j] - mean) * rstd * gg[j] + bb[j];
+    if (y_f32) *reinterpret_cast<float4*>(y_f32 + row * D + c) = make_float4(o[0], o[1], o[2], o[3]);
+    if (y_bf16) store_bf16x4(y_bf16 + row * ld_bf16 + c, o);
+  }
+}
+
+template <int D>
+__global__ void __launch_bounds__(256)
+residual_ln_bwd_vec_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                           const float* __restrict__ r, long T, const float* __restrict__ gamma,
+                           DropSpec dp, float eps, float* __restrict__ dx,
+                           __nv_bfloat16* __restrict__ dr_bf16, long ld_bf16,
+                           float* __restrict__ partial) {
+  using C = LnVec<D>;
+  __shared__ float red[8][3][D];
+  if (dp.thresh24) dp.seed = resolve_seed(dp.seed);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nwarps = blockDim.x >> 5;
+  const int lr = lane % C::LPR, sub = lane / C::LPR;
+  float pg[C::VPL][4], pb[C::VPL][4], pr[C::VPL][4], gam[C::VPL][4];
+#pragma unroll
+  for (int i = 0; i < C::VPL; ++i) {
+    const float4 gv = __ldg(reinterpret_cast<const float4*>(gamma + (lr + i * C::LPR) * 4));
+    gam[i][0] = gv.x; gam[i][1] = gv.y; gam[i][2] = gv.z; gam[i][3] = gv.w;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) pg[i][j] = pb[i][j] = pr[i][j] = 0.f;
+  }
+  const long groups = (T + C::RPW - 1) / C::RPW;
+  for (long grp = (long)blockIdx.x * nwarps + warp; grp < groups; grp += (long)gridDim.x * nwarps) {
+    const long row = grp * C::RPW + sub;
+    const bool live = row < T;
+    float v[C::VPL][4], g[C::VPL][4], keepf[C::VPL][4], dyv[C::VPL][4];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < C::VPL; ++i) {
+      const int c = (lr + i * C::LPR) * 4;
+      float4 xv = make_float4(0.f, 0.f, 0.f, 0.f), rv = xv, dv = xv;
+      if (live) {
+        xv = *reinterpret_cast<const float4*>(x + row * D + c);
+        rv = *reinterpret_cast<const float4*>(r + row * D + c);
+        dv = *reinterpret_cast<const float4*>(dy + row * D + c);
+      }
+      const float xx[4] = {xv.x, xv.y, xv.z, xv.w}, rr[4] = {rv.x, rv.y, rv.z, rv.w};
+      dyv[i][0] = dv.x; dyv[i][1] = dv.y; dyv[i][2] = dv.z; dyv[i][3] = dv.w;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        keepf[i][j] = live ? 1.f : 0.f;
+        if (dp.thresh24 && live)
+          keepf[i][j] = dropout_keep(dp.seed, dp.site, (uint64_t)(row * D + c + j), dp.thresh24) ? dp.inv_keep : 0.f;
+        v[i][j] = xx[j] + rr[j] * keepf[i][j];
+        sum += v[i][j];
+      }
+    }
+    const float mean = subwarp_sum<C::LPR>(sum) / (float)D;
+    float var = 0.f;
+#pragma unroll
+    for (int i = 0; i < C::VPL; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float dv = v[i][j] - mean;
+        var = fmaf(dv, dv, var);
+      }
+    var = subwarp_sum<C::LPR>(var) / (float)D;
+    const float rstd = rsqrtf(var + eps);
+    float m1 = 0.f, m2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < C::VPL; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        v[i][j] = (v[i][j] - mean) * rstd;  // xhat
+        g[i][j] = dyv[i][j] * gam[i][j];
+        m1 += g[i][j];
+        m2 = fmaf(g[i][j], v[i][j], m2);
+        if (live) {
+          pg[i][j] = fmaf(dyv[i][j], v[i][j], pg[i][j]);
+          pb[i][j] += dyv[i][j];
+        }
+      }
+    m1 = subwarp_sum<C::LPR>(m1) / (float)D;
+    m2 = subwarp_sum<C::LPR>(m2) / (float)D;
+    if (live) {
+#pragma unroll
+      for (int i = 0; i < C::VPL; ++i) {
+        const int c = (lr + i * C::LPR) * 4;
+        float dres[4], drv[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          dres[j] = rstd * (g[i][j] - m1 - v[i][j] * m2);
+          drv[j] = dres[j] * keepf[i][j];
+          pr[i][j] += drv[j];
+        }
+        if (dx) *reinterpret_cast<float4*>(dx + row * D + c) = make_float4(dres[0], dres[1], dres[2], dres[3]);
+        if (dr_bf16) store_bf16x4(dr_bf16 + row * ld_bf16 + c, drv);
+      }
+    }
+  }
+  // sub-rows of a warp hold the same columns: fold them (fixed order), then one writer per column
+#pragma unroll
+  for (int i = 0; i < C::VPL; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+      for (int o = C::LPR; o < 32; o <<= 1) {
+        pg[i][j] += __shfl_xor_sync(0xffffffffu, pg[i][j], o);
+        pb[i][j] += __shfl_xor_sync(0xffffffffu, pb[i][j], o);
+        pr[i][j] += __shfl_xor_sync(0xffffffffu, pr[i][j], o);
+      }
+      if (sub == 0) {
+        const int c = (lr + i * C::LPR) * 4 + j;
+        red[warp][0][c] = pg[i][j];
+        red[warp][1][c] = pb[i][j];
+        red[warp][2][c] = pr[i][j];
+      }
+    }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 3 * D; i += blockDim.x) {
+    const int k = i / D, c = i - k * D;
+    float s = 0.f;
+    for (int w = 0; w < nwarps; ++w) s += red[w][k][c];
+    partial[((size_t)blockIdx.x * 3 + k) * D + c] = s;
+  }
+}
+
+// (dgamma | dbeta | dbias)[c] = sum over blocks of partial[block][k][c]: one warp per column of
+// the 3*d, lanes stride the blocks, fixed shuffle tree (deterministic)
+__global__ void __launch_bounds__(256)
+reduce_ln_partials_kernel(const float* __restrict__ partial, int P, int d,
+                          float* __restrict__ dgamma, float* __restrict__ dbeta,
+                          float* __restrict__ dbias) {
+  const int col = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (col >= 3 * d) return;
+  const int lane = threadIdx.x & 31;
+  float s = 0.f;
+  for (int p = lane; p < P; p += 32) s += partial[(size_t)p * 3 * d + col];
+  s = warp_sum(s);
+  if (lane == 0) {
+    const int k = col / d, c = col - k * d;
+    float* out = k == 0 ? dgamma : (k == 1 ? dbeta : dbias);
+    if (out) out[c] = s;
+  }
+}
+
 // out[c] = sum_p partial[p][c] (fixed order -> deterministic)
 __global__ void __launch_bounds__(256)
 reduce_partials_kernel(const float* __restrict__ partial, int P, long n, long stride,
@@ -540,7 +760,12 @@ extern "C" int b4cp_residual_ln_fwd(const float* x, const float* r, long T, int 
   const int nb = ceil_div(T, 8);
   cudaStream_t st = (cudaStream_t)stream;
   __nv_bfloat16* yb = (__nv_bfloat16*)y_bf16;
-  if (d <= 32) residual_ln_fwd_kernel<1><<<nb, 256, 0, st>>>(x, r, T, d, gamma, beta, dsp, 1e-6f, y_f32, yb, ld_bf16);
+  const bool vec_ok = (((uintptr_t)x | (uintptr_t)r | (uintptr_t)y_f32 | (uintptr_t)gamma | (uintptr_t)beta) & 15) == 0 &&
+                      ((uintptr_t)y_bf16 & 7) == 0 && ld_bf16 % 4 == 0;
+  if (vec_ok && d == 64) residual_ln_fwd_vec_kernel<64><<<ceil_div(T, 8 * LnVec<64>::RPW), 256, 0, st>>>(x, r, T, gamma, beta, dsp, 1e-6f, y_f32, yb, ld_bf16);
+  else if (vec_ok && d == 128) residual_ln_fwd_vec_kernel<128><<<ceil_div(T, 8), 256, 0, st>>>(x, r, T, gamma, beta, dsp, 1e-6f, y_f32, yb, ld_bf16);
+  else if (vec_ok && d == 256) residual_ln_fwd_vec_kernel<256><<<ceil_div(T, 8), 256, 0, st>>>(x, r, T, gamma, beta, dsp, 1e-6f, y_f32, yb, ld_bf16);
+  else if (d <= 32) residual_ln_fwd_kernel<1><<<nb, 256, 0, st>>>(x, r, T, d, gamma, beta, dsp, 1e-6f, y_f32, yb, ld_bf16);
   else if (d <= 64) residual_ln_fwd_kernel<2><<<nb, 256, 0, st>>>(x, r, T, d, gamma, beta, dsp, 1e-6f, y_f32, yb, ld_bf16);
   else if (d <= 128) residual_ln_fwd_kernel<4><<<nb, 256, 0, st>>>(x, r, T, d, gamma, beta, dsp, 1e-6f, y_f32, yb, ld_bf16);
   else residual_ln_fwd_kernel<8><<<nb, 256, 0, st>>>(x, r, T, d, gamma, beta, dsp, 1e-6f, y_f32, yb, ld_bf16);
@@ -567,14 +792,18 @@ extern "C" int b4cp_residual_ln_bwd(const float* dy, const float* x, const float
   const int blocks = (int)std::min<long>(LN_BWD_BLOCKS, std::max<long>(1, ceil_div(T, 8)));
   const DropSpec dsp = make_drop(dropout_rate, seed, site);
   __nv_bfloat16* drb = (__nv_bfloat16*)dr_bf16;
-  if (d <= 32) residual_ln_bwd_kernel<1><<<blocks, 256, 0, st>>>(dy, x, r, T, d, gamma, dsp, 1e-6f, dx, drb, ld_bf16, partial);
+  const bool vec_ok = (((uintptr_t)x | (uintptr_t)r | (uintptr_t)dy | (uintptr_t)dx | (uintptr_t)gamma) & 15) == 0 &&
+                      ((uintptr_t)dr_bf16 & 7) == 0 && ld_bf16 % 4 == 0;
+  if (vec_ok && d == 64) residual_ln_bwd_vec_kernel<64><<<blocks, 256, 0, st>>>(dy, x, r, T, gamma, dsp, 1e-6f, dx, drb, ld_bf16, partial);
+  else if (vec_ok && d == 128) residual_ln_bwd_vec_kernel<128><<<blocks, 256, 0, st>>>(dy, x, r, T, gamma, dsp, 1e-6f, dx, drb, ld_bf16, partial);
+  else if (vec_ok && d == 256) residual_ln_bwd_vec_kernel<256><<<blocks, 256, 0, st>>>(dy, x, r, T, gamma, dsp, 1e-6f, dx, drb, ld_bf16, partial);
+  else if (d <= 32) residual_ln_bwd_kernel<1><<<blocks, 256, 0, st>>>(dy, x, r, T, d, gamma, dsp, 1e-6f, dx, drb, ld_bf16, partial);
   else if (d <= 64) residual_ln_bwd_kernel<2><<<blocks, 256, 0, st>>>(dy, x, r, T, d, gamma, dsp, 1e-6f, dx, drb, ld_bf16, partial);
   else if (d <= 128) residual_ln_bwd_kernel<4><<<blocks, 256, 0, st>>>(dy, x, r, T, d, gamma, dsp, 1e-6f, dx, drb, ld_bf16, partial);
   else residual_ln_bwd_kernel<8><<<blocks, 256, 0, st>>>(dy, x, r, T, d, gamma, dsp, 1e-6f, dx, drb, ld_bf16, partial);
-  note_launches(1 + (dgamma ? 1 : 0) + (dbeta ? 1 : 0) + (dbias ? 1 : 0));
-  if (dgamma) launch_reduce_partials(partial, blocks, d, 3L * d, dgamma, st);
-  if (dbeta) launch_reduce_partials(partial + d, blocks, d, 3L * d, dbeta, st);
-  if (dbias) launch_reduce_partials(partial + 2 * d, blocks, d, 3L * d, dbias, st);
+  if (dgamma || dbeta || dbias)
+    reduce_ln_partials_kernel<<<ceil_div(3 * d, 8), 256, 0, st>>>(partial, blocks, d, dgamma, dbeta, dbias);
+  note_launches(1 + ((dgamma || dbeta || dbias) ? 1 : 0));
   B4CP_LAUNCH_CHECK();
   return 0;
 }
