@@ -660,6 +660,42 @@ colsum_partial_kernel(const __nv_bfloat16* __restrict__ in, long T, int n, long 
     partial[(size_t)blockIdx.x * n + c] = red[0][cx] + red[1][cx] + red[2][cx] + red[3][cx];
 }
 
+// same partials with 128-bit loads: thread = 8 consecutive columns x every 8th row of the chunk
+__global__ void __launch_bounds__(256)
+colsum_partial_vec_kernel(const __nv_bfloat16* __restrict__ in, long T, int n, long ld,
+                          float* __restrict__ partial) {
+  __shared__ float red[8][32][9];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int c0 = (blockIdx.y * 32 + cx) * 8;
+  const long r0 = (long)blockIdx.x * CS_ROWS;
+  const long r1 = min(T, r0 + CS_ROWS);
+  float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (c0 < n) {
+#pragma unroll 4
+    for (long r = r0 + ry; r < r1; r += 8) {
+      const uint4 q = __ldg(reinterpret_cast<const uint4*>(in + r * ld + c0));
+      const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        s[2 * k] += __uint_as_float(w[k] << 16);            // low half = even column
+        s[2 * k + 1] += __uint_as_float(w[k] & 0xFFFF0000u);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) red[ry][cx][k] = s[k];
+  __syncthreads();
+  // 256 threads = 32 column groups x 8 columns: fixed-order sum over the 8 row lanes
+  const int g = threadIdx.x >> 3, k = threadIdx.x & 7;
+  const int c = (blockIdx.y * 32 + g) * 8 + k;
+  if (c < n) {
+    float t = 0.f;
+#pragma unroll
+    for (int y = 0; y < 8; ++y) t += red[y][g][k];
+    partial[(size_t)blockIdx.x * n + c] = t;
+  }
+}
+
 __global__ void __launch_bounds__(256)
 cast_f32_bf16_kernel(const float* __restrict__ in, long rows, int cols, long ld_in,
                      __nv_bfloat16* __restrict__ out, long ld_out) {
@@ -821,8 +857,13 @@ extern "C" int b4cp_colsum_bf16(const void* in, long T, int n, long ld, float* o
     return 0;
   }
   const int chunks = ceil_div(T, CS_ROWS);
-  dim3 grid(chunks, ceil_div(n, 64));
-  colsum_partial_kernel<<<grid, 256, 0, st>>>((const __nv_bfloat16*)in, T, n, ld, (float*)workspace);
+  if (ld % 8 == 0 && ((uintptr_t)in & 15) == 0 && ld >= (long)ceil_div(n, 8) * 8) {
+    dim3 grid(chunks, ceil_div(n, 256));
+    colsum_partial_vec_kernel<<<grid, 256, 0, st>>>((const __nv_bfloat16*)in, T, n, ld, (float*)workspace);
+  } else {
+    dim3 grid(chunks, ceil_div(n, 64));
+    colsum_partial_kernel<<<grid, 256, 0, st>>>((const __nv_bfloat16*)in, T, n, ld, (float*)workspace);
+  }
   launch_reduce_partials((const float*)workspace, chunks, n, n, out, st);
   note_launches(2);
   B4CP_LAUNCH_CHECK();

@@ -221,7 +221,7 @@ def test_attention_fwd_bwd(cuda_lib, B, S, H, dh):
 
 
 # ------------------------------------------------------------------------------- LayerNorm
-@pytest.mark.parametrize("d,rate", [(64, 0.0), (128, 0.1), (256, 0.1), (24, 0.0)])
+@pytest.mark.parametrize("d,rate", [(64, 0.0), (64, 0.1), (128, 0.1), (256, 0.1), (24, 0.0)])
 def test_residual_ln_fwd_bwd(cuda_lib, d, rate):
     from bert4clickpath_b200 import ops
     rng = np.random.default_rng(d)
@@ -261,6 +261,19 @@ def test_colsum_and_cast(cuda_lib):
     out = torch.empty(n, device="cuda")
     ops.colsum_bf16(ab, T, n, out)
     np.testing.assert_allclose(out.cpu().numpy(), bf16_round(a).astype(np.float64).sum(0), rtol=1e-4, atol=1e-3)
+    # wide / ragged shapes through the 128-bit kernel, and an unaligned view through the scalar one
+    for T2, n2 in ((5000, 1024), (700, 192), (513, 8), (1, 300)):
+        a2 = rng.normal(size=(T2, n2)).astype(np.float32)
+        ab2 = ops.cast_bf16(dev(a2))
+        out2 = torch.full((n2,), float("nan"), device="cuda")
+        ops.colsum_bf16(ab2, T2, n2, out2)
+        np.testing.assert_allclose(out2.cpu().numpy(), bf16_round(a2).astype(np.float64).sum(0),
+                                   rtol=1e-4, atol=2e-3)
+    view = ab[:, 1:]   # base no longer 16-byte aligned
+    out3 = torch.empty(n - 1, device="cuda")
+    ops.colsum_bf16(view, T, n - 1, out3)
+    np.testing.assert_allclose(out3.cpu().numpy(), bf16_round(a)[:, 1:].astype(np.float64).sum(0),
+                               rtol=1e-4, atol=1e-3)
 
 
 # ------------------------------------------------------------------------------- selection
