@@ -1,6 +1,7 @@
 // Tensor-core path of the fused short-sequence masked self-attention (S <= 128, head depth 32
 // or 64): transformer.py:64-97 (scaled_dot_product_attention) and :130-156 (split / merge heads).
-// One CTA per (sequence, head); Q/K/V (and dO) live in shared memory as bf16, the S x S score
+// One CTA per (sequence, head); Q/K/V (and dO) live in shared memory as row-major bf16 tiles
+// (staged with 128-bit loads; transposed operands come from ldmatrix.trans), the S x S score
 // matrix only ever exists as mma.sync accumulator fragments in registers (these per-head products
 // are 64x64x32: too small for a tcgen05 128-row tile, so the warp-level HMMA path is used here and
 // tcgen05 is kept for the Dense layers and the vocabulary stage).
@@ -46,6 +47,19 @@ __device__ __forceinline__ void load_b(uint32_t& b0, uint32_t& b1, const __nv_bf
   b1 = *reinterpret_cast<const uint32_t*>(p + 8);
 }
 
+// Two B fragments (16 k x 8 n each, n-tiles n0 and n0 + 8) where B[k][n] = tile[k0 + k][n0 + n]
+// (tile row-major, n contiguous): ldmatrix.trans transposes the 8x8 blocks on the way in, so the
+// P.V / dZ.K / P^T.dO / dZ^T.Q products read the row-major tiles directly (no transposed copies).
+__device__ __forceinline__ void load_b_trans2(uint32_t (&b)[4], const __nv_bfloat16* tile, int ld,
+                                              int k0, int n0, int lane) {
+  const int row = k0 + (lane & 7) + ((lane >> 3) & 1) * 8;
+  const int col = n0 + (lane >> 4) * 8;
+  const uint32_t addr = smem_u32(tile + (size_t)row * ld + col);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(b[0]), "=r"(b[1]), "=r"(b[2]), "=r"(b[3])
+               : "r"(addr));
+}
+
 __device__ __forceinline__ float quad_sum(float v) {
   v += __shfl_xor_sync(0xffffffffu, v, 1);
   v += __shfl_xor_sync(0xffffffffu, v, 2);
@@ -57,23 +71,18 @@ __device__ __forceinline__ float quad_max(float v) {
   return v;
 }
 
-// cooperative load of one head slice [S][DH] (global row stride ld) into a row-major smem tile
-// [SP][LDR] (rows >= S zero) and, optionally, its transpose [DH][LDT]
+// cooperative 128-bit load of one head slice [S][DH] (global row stride ld elements, 16-byte
+// aligned rows) into a row-major smem tile [SP][LDR]; rows >= S are zero
 template <int DH, int SP>
 __device__ __forceinline__ void stage_tile(const __nv_bfloat16* __restrict__ src, long ld, int S,
-                                           __nv_bfloat16* rowm, int LDR, __nv_bfloat16* trans,
-                                           int LDT) {
-  constexpr int W = DH / 2;
+                                           __nv_bfloat16* rowm, int LDR) {
+  constexpr int W = DH / 8;
+#pragma unroll 2
   for (int i = threadIdx.x; i < SP * W; i += blockDim.x) {
     const int r = i / W, w = i - r * W;
-    uint32_t v = 0;
-    if (r < S) v = *reinterpret_cast<const uint32_t*>(src + (size_t)r * ld + 2 * w);
-    if (rowm) *reinterpret_cast<uint32_t*>(rowm + (size_t)r * LDR + 2 * w) = v;
-    if (trans) {
-      const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&v);
-      trans[(size_t)(2 * w) * LDT + r] = h.x;
-      trans[(size_t)(2 * w + 1) * LDT + r] = h.y;
-    }
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (r < S) v = __ldg(reinterpret_cast<const uint4*>(src + (size_t)r * ld + 8 * w));
+    *reinterpret_cast<uint4*>(rowm + (size_t)r * LDR + 8 * w) = v;
   }
 }
 
@@ -98,15 +107,15 @@ attention_mma_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* _
   extern __shared__ __align__(16) uint8_t sm[];
   __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(sm);
   __nv_bfloat16* sK = sQ + C::SP * C::LDR;
-  __nv_bfloat16* sVt = sK + C::SP * C::LDR;
-  float* sMask = reinterpret_cast<float*>(sVt + DH * C::LDT);
+  __nv_bfloat16* sV = sK + C::SP * C::LDR;
+  float* sMask = reinterpret_cast<float*>(sV + C::SP * C::LDR);
   const int d = H * DH;
   const int b = blockIdx.x / H, h = blockIdx.x % H;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const __nv_bfloat16* base = qkv + (size_t)b * S * 3 * d + h * DH;
-  stage_tile<DH, C::SP>(base, 3L * d, S, sQ, C::LDR, nullptr, 0);
-  stage_tile<DH, C::SP>(base + d, 3L * d, S, sK, C::LDR, nullptr, 0);
-  stage_tile<DH, C::SP>(base + 2 * d, 3L * d, S, nullptr, 0, sVt, C::LDT);
+  stage_tile<DH, C::SP>(base, 3L * d, S, sQ, C::LDR);
+  stage_tile<DH, C::SP>(base + d, 3L * d, S, sK, C::LDR);
+  stage_tile<DH, C::SP>(base + 2 * d, 3L * d, S, sV, C::LDR);
   for (int j = threadIdx.x; j < C::SP; j += blockDim.x)
     sMask[j] = j >= S ? -INFINITY : (ids[(size_t)b * S + j] == 0 ? -1e9f : 0.f);
   __syncthreads();
@@ -164,10 +173,11 @@ attention_mma_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* _
       a[2] = pack_bf16(sc[2 * ks + 1][0] * i0, sc[2 * ks + 1][1] * i0);
       a[3] = pack_bf16(sc[2 * ks + 1][2] * i1, sc[2 * ks + 1][3] * i1);
 #pragma unroll
-      for (int n2 = 0; n2 < C::NT_D; ++n2) {
-        uint32_t b0, b1;
-        load_b(b0, b1, sVt, C::LDT, n2 * 8, ks * 16, g, t);
-        mma_bf16(o[n2], a, b0, b1);
+      for (int n2 = 0; n2 < C::NT_D; n2 += 2) {
+        uint32_t bb[4];
+        load_b_trans2(bb, sV, C::LDR, ks * 16, n2 * 8, lane);
+        mma_bf16(o[n2], a, bb[0], bb[1]);
+        mma_bf16(o[n2 + 1], a, bb[2], bb[3]);
       }
     }
     const int row0 = r0 + g, row1 = r0 + g + 8;
@@ -198,20 +208,17 @@ attention_mma_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloa
   __nv_bfloat16* sK = sQ + C::SP * C::LDR;
   __nv_bfloat16* sV = sK + C::SP * C::LDR;
   __nv_bfloat16* sDO = sV + C::SP * C::LDR;
-  __nv_bfloat16* sQt = sDO + C::SP * C::LDR;
-  __nv_bfloat16* sKt = sQt + DH * C::LDT;
-  __nv_bfloat16* sDOt = sKt + DH * C::LDT;
-  float* sMask = reinterpret_cast<float*>(sDOt + DH * C::LDT);
+  float* sMask = reinterpret_cast<float*>(sDO + C::SP * C::LDR);
   float* sLse = sMask + C::SP;
   float* sDelta = sLse + C::SP;
   const int d = H * DH;
   const int b = blockIdx.x / H, h = blockIdx.x % H;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const __nv_bfloat16* base = qkv + (size_t)b * S * 3 * d + h * DH;
-  stage_tile<DH, C::SP>(base, 3L * d, S, sQ, C::LDR, sQt, C::LDT);
-  stage_tile<DH, C::SP>(base + d, 3L * d, S, sK, C::LDR, sKt, C::LDT);
-  stage_tile<DH, C::SP>(base + 2 * d, 3L * d, S, sV, C::LDR, nullptr, 0);
-  stage_tile<DH, C::SP>(dout + (size_t)b * S * d + h * DH, (long)d, S, sDO, C::LDR, sDOt, C::LDT);
+  stage_tile<DH, C::SP>(base, 3L * d, S, sQ, C::LDR);
+  stage_tile<DH, C::SP>(base + d, 3L * d, S, sK, C::LDR);
+  stage_tile<DH, C::SP>(base + 2 * d, 3L * d, S, sV, C::LDR);
+  stage_tile<DH, C::SP>(dout + (size_t)b * S * d + h * DH, (long)d, S, sDO, C::LDR);
   for (int j = threadIdx.x; j < C::SP; j += blockDim.x) {
     sMask[j] = j >= S ? -INFINITY : (ids[(size_t)b * S + j] == 0 ? -1e9f : 0.f);
     sLse[j] = j < S ? lse_in[((size_t)b * H + h) * S + j] : INFINITY;  // rows past S: P = 0
@@ -274,10 +281,11 @@ attention_mma_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloa
       a[2] = pack_bf16(p[2 * ks + 1][0] * (dp[2 * ks + 1][0] - d0), p[2 * ks + 1][1] * (dp[2 * ks + 1][1] - d0));
       a[3] = pack_bf16(p[2 * ks + 1][2] * (dp[2 * ks + 1][2] - d1), p[2 * ks + 1][3] * (dp[2 * ks + 1][3] - d1));
 #pragma unroll
-      for (int n2 = 0; n2 < C::NT_D; ++n2) {
-        uint32_t b0, b1;
-        load_b(b0, b1, sKt, C::LDT, n2 * 8, ks * 16, g, t);
-        mma_bf16(dq[n2], a, b0, b1);
+      for (int n2 = 0; n2 < C::NT_D; n2 += 2) {
+        uint32_t bb[4];
+        load_b_trans2(bb, sK, C::LDR, ks * 16, n2 * 8, lane);
+        mma_bf16(dq[n2], a, bb[0], bb[1]);
+        mma_bf16(dq[n2 + 1], a, bb[2], bb[3]);
       }
     }
     const int row0 = r0 + g, row1 = r0 + g + 8;
@@ -350,12 +358,14 @@ attention_mma_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloa
       az[2] = pack_bf16(dp[2 * ks + 1][0], dp[2 * ks + 1][1]);
       az[3] = pack_bf16(dp[2 * ks + 1][2], dp[2 * ks + 1][3]);
 #pragma unroll
-      for (int n2 = 0; n2 < C::NT_D; ++n2) {
-        uint32_t b0, b1;
-        load_b(b0, b1, sDOt, C::LDT, n2 * 8, ks * 16, g, t);
-        mma_bf16(dv[n2], ap, b0, b1);
-        load_b(b0, b1, sQt, C::LDT, n2 * 8, ks * 16, g, t);
-        mma_bf16(dk[n2], az, b0, b1);
+      for (int n2 = 0; n2 < C::NT_D; n2 += 2) {
+        uint32_t bb[4];
+        load_b_trans2(bb, sDO, C::LDR, ks * 16, n2 * 8, lane);
+        mma_bf16(dv[n2], ap, bb[0], bb[1]);
+        mma_bf16(dv[n2 + 1], ap, bb[2], bb[3]);
+        load_b_trans2(bb, sQ, C::LDR, ks * 16, n2 * 8, lane);
+        mma_bf16(dk[n2], az, bb[0], bb[1]);
+        mma_bf16(dk[n2 + 1], az, bb[2], bb[3]);
       }
     }
     const int row0 = j0 + g, row1 = j0 + g + 8;
@@ -380,7 +390,7 @@ template <int NKB, int DH>
 static int launch_fwd(const void* qkv, const int32_t* ids, int B, int S, int H, void* out, float* lse,
                       cudaStream_t st) {
   using C = AttnCfg<NKB, DH>;
-  const size_t smem = (size_t)(2 * C::SP * C::LDR + DH * C::LDT) * 2 + C::SP * 4;
+  const size_t smem = (size_t)(3 * C::SP * C::LDR) * 2 + C::SP * 4;
   B4CP_CUDA(cudaFuncSetAttribute(attention_mma_fwd_kernel<NKB, DH>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   attention_mma_fwd_kernel<NKB, DH><<<B * H, 128, smem, st>>>(
@@ -392,7 +402,7 @@ template <int NKB, int DH>
 static int launch_bwd(const void* qkv, const void* dout, const float* lse, const int32_t* ids, int B,
                       int S, int H, void* dqkv, cudaStream_t st) {
   using C = AttnCfg<NKB, DH>;
-  const size_t smem = (size_t)(4 * C::SP * C::LDR + 3 * DH * C::LDT) * 2 + 3 * C::SP * 4;
+  const size_t smem = (size_t)(4 * C::SP * C::LDR) * 2 + 3 * C::SP * 4;
   B4CP_CUDA(cudaFuncSetAttribute(attention_mma_bwd_kernel<NKB, DH>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   attention_mma_bwd_kernel<NKB, DH><<<B * H, 128, smem, st>>>(
