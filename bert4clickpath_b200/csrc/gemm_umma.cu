@@ -13,6 +13,7 @@
 #include <algorithm>
 #include <cstring>
 
+#include <cstdlib>
 #include "common.cuh"
 #include "../../include/b4cp.h"
 
@@ -68,8 +69,9 @@ __device__ __forceinline__ void epilogue_math(const b4cp_gemm_epilogue& ep, int 
         }
       }
     } else {
-      for (int j = 0; j < ncol; ++j)
-        if (!(__bfloat162float(g[j]) > 0.f)) v[j] = 0.f;
+#pragma unroll
+      for (int j = 0; j < 32; ++j)  // predicated, fully unrolled: v[] stays in registers
+        if (j < ncol && !(__bfloat162float(g[j]) > 0.f)) v[j] = 0.f;
     }
   }
   if (ep.addend) {
@@ -81,7 +83,9 @@ __device__ __forceinline__ void epilogue_math(const b4cp_gemm_epilogue& ep, int 
         v[j] += a4.x; v[j + 1] += a4.y; v[j + 2] += a4.z; v[j + 3] += a4.w;
       }
     } else {
-      for (int j = 0; j < ncol; ++j) v[j] += a[j];
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < ncol) v[j] += a[j];
     }
   }
 }
@@ -98,7 +102,9 @@ __device__ __forceinline__ void epilogue_store_direct(const b4cp_gemm_epilogue& 
       for (int j = 0; j < 32; j += 4)
         *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
     } else {
-      for (int j = 0; j < ncol; ++j) o[j] = v[j];
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < ncol) o[j] = v[j];
     }
   }
   if (ep.out_bf16) {
@@ -119,7 +125,76 @@ __device__ __forceinline__ void epilogue_store_direct(const b4cp_gemm_epilogue& 
         *reinterpret_cast<uint4*>(o + j) = pk;
       }
     } else {
-      for (int j = 0; j < ncol; ++j) o[j] = __float2bfloat16_rn(v[j]);
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < ncol) o[j] = __float2bfloat16_rn(v[j]);
+    }
+  }
+}
+
+// Coalesced stores of one finished 32-row x 32-column chunk of a warp (lane = row): the chunk is
+// transposed through a per-warp swizzled smem tile so that every store instruction writes whole
+// rows segments (8 lanes x 16 B = one 128-byte fp32 row, 4 lanes x 16 B = one 64-byte bf16 row).
+// Per-thread row stores write 16-byte halves of 32-byte sectors in separate instructions, which
+// makes L2 fetch every output sector from DRAM before merging (measured: DRAM reads = output size).
+// `stg` : 4096 B per warp, 128-byte aligned.  Rows >= M and chunks that are not 32 wide / 16-byte
+// aligned take the direct path.
+__device__ __forceinline__ void epilogue_store_coalesced(const b4cp_gemm_epilogue& ep,
+                                                         float* out_f32, int row0, int M, int col0,
+                                                         int N, const float (&v)[32],
+                                                         uint32_t stg, int lane) {
+  const int ncol = min(32, N - col0);
+  const bool f_ok = out_f32 && ncol == 32 &&
+                    ((reinterpret_cast<uintptr_t>(out_f32 + col0) | (uintptr_t)(ep.ld_f32 * 4)) & 15) == 0;
+  __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(ep.out_bf16);
+  const bool b_ok = ob && ncol == 32 &&
+                    ((reinterpret_cast<uintptr_t>(ob + col0) | (uintptr_t)(ep.ld_bf16 * 2)) & 15) == 0;
+  const int row = row0 + lane;
+  if (out_f32) {
+    if (f_ok) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        sts128(stg + lane * 128 + ((k ^ (lane & 7)) << 4), __float_as_uint(v[4 * k]),
+               __float_as_uint(v[4 * k + 1]), __float_as_uint(v[4 * k + 2]),
+               __float_as_uint(v[4 * k + 3]));
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = i * 4 + (lane >> 3), pc = lane & 7;
+        const float4 q = lds128f(stg + r * 128 + ((pc ^ (r & 7)) << 4));
+        if (row0 + r < M)
+          *reinterpret_cast<float4*>(out_f32 + (size_t)(row0 + r) * ep.ld_f32 + col0 + pc * 4) = q;
+      }
+      __syncwarp();
+    } else if (row < M) {
+      b4cp_gemm_epilogue e2 = ep;
+      e2.out_bf16 = nullptr;
+      epilogue_store_direct(e2, out_f32, row, col0, N, v);
+    }
+  }
+  if (ob) {
+    if (b_ok) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(v[8 * k + 0], v[8 * k + 1]);
+        __nv_bfloat162 h1 = __floats2bfloat162_rn(v[8 * k + 2], v[8 * k + 3]);
+        __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * k + 4], v[8 * k + 5]);
+        __nv_bfloat162 h3 = __floats2bfloat162_rn(v[8 * k + 6], v[8 * k + 7]);
+        sts128(stg + lane * 64 + ((k ^ ((lane >> 1) & 3)) << 4), *reinterpret_cast<uint32_t*>(&h0),
+               *reinterpret_cast<uint32_t*>(&h1), *reinterpret_cast<uint32_t*>(&h2),
+               *reinterpret_cast<uint32_t*>(&h3));
+      }
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = i * 8 + (lane >> 2), pc = lane & 3;
+        const float4 q = lds128f(stg + r * 64 + ((pc ^ ((r >> 1) & 3)) << 4));
+        if (row0 + r < M)
+          *reinterpret_cast<float4*>(ob + (size_t)(row0 + r) * ep.ld_bf16 + col0 + pc * 8) = q;
+      }
+      __syncwarp();
+    } else if (row < M) {
+      epilogue_store_direct(ep, nullptr, row, col0, N, v);
     }
   }
 }
@@ -156,6 +231,8 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
   float* sbias = reinterpret_cast<float*>(
       (reinterpret_cast<uintptr_t>(tmem_slot + 1) + 15) & ~static_cast<uintptr_t>(15));  // [BN]
+  uint8_t* sStage = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(sbias + BN) + 127) & ~static_cast<uintptr_t>(127));  // [4][4096]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -248,8 +325,9 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else {
     // ---- epilogue: warp w may only touch TMEM lanes [32*(w%4), 32*(w%4)+32)
     const int q = warp & 3;
-    const int row = m0 + q * 32 + lane;
-    const bool row_ok = row < p.M;
+    const int row0 = m0 + q * 32;
+    const int row = row0 + lane;
+    const uint32_t stg = smem_u32(sStage + (warp - 2) * 4096);
     const b4cp_gemm_epilogue& ep = p.ep;
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
@@ -259,8 +337,210 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
       tmem_ld_wait();
       const int col0 = n0 + c0;
-      if (!row_ok || col0 >= p.N) continue;
-      epilogue_chunk(ep, out_f32, row, col0, p.N, r, ep.bias ? sbias + c0 : nullptr);
+      if (row0 >= p.M || col0 >= p.N) continue;  // warp-uniform
+      float v[32];
+      if (row < p.M) {
+        epilogue_math(ep, row, col0, p.N, r, ep.bias ? sbias + c0 : nullptr, v);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+      }
+      epilogue_store_coalesced(ep, out_f32, row0, p.M, col0, p.N, v, stg, lane);
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------ tile-persistent variant
+// More output tiles than SMs (the head MLP and its gradients): one CTA per SM walks the tiles
+// t, t + grid, ... (row tile fastest, so concurrently running CTAs share the B column tile in
+// L2).  The smem ring runs continuously across tiles and two TMEM accumulators ping-pong, so the
+// epilogue of tile i overlaps the TMA loads and MMAs of tile i + 1 and the per-CTA set-up
+// (TMEM allocation, barrier init, descriptor prefetch) is paid once per SM, not once per tile.
+struct TileCoord {
+  int m0, n0, z, kt_begin, kt_end;
+};
+__device__ __forceinline__ TileCoord tile_coord(const GemmKernelParams& p, int t, int n_m, int n_n) {
+  TileCoord c;
+  c.z = t / (n_m * n_n);
+  const int rem = t - c.z * (n_m * n_n);
+  const int nt = rem / n_m;
+  c.m0 = (rem - nt * n_m) * BM;
+  c.n0 = nt * p.BN;
+  c.kt_begin = c.z * p.k_tiles_per_split;
+  c.kt_end = min(p.k_tiles_total, c.kt_begin + p.k_tiles_per_split);
+  return c;
+}
+
+static constexpr int TILES_EPI_WARPS = 8;  // two per TMEM lane quadrant, interleaved column chunks
+static constexpr int TILES_THREADS = 64 + 32 * TILES_EPI_WARPS;
+
+__global__ void __launch_bounds__(TILES_THREADS, 1)
+gemm_umma_tiles_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                       const GemmKernelParams p, int n_m, int n_n, int total_tiles) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  const int BN = p.BN;
+  const int b_stage_bytes = BN * BK * 2;
+  const int stage_bytes = A_STAGE_BYTES + b_stage_bytes;
+  uint8_t* tiles = smem;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tiles + (size_t)p.stages * stage_bytes);
+  uint64_t* empty_bar = full_bar + p.stages;
+  uint64_t* acc_full = empty_bar + p.stages;   // [2]
+  uint64_t* acc_empty = acc_full + 2;          // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* sbias = reinterpret_cast<float*>(
+      (reinterpret_cast<uintptr_t>(tmem_slot + 1) + 15) & ~static_cast<uintptr_t>(15));  // [2][BN]
+  uint8_t* sStage = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(sbias + 2 * BN) + 127) & ~static_cast<uintptr_t>(127));  // [8][4096]
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  uint32_t tmem_cols = 32;
+  while ((int)tmem_cols < 2 * BN) tmem_cols <<= 1;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmA);
+      tma_prefetch_desc(&tmB);
+    }
+    tmem_alloc(tmem_slot, tmem_cols);
+    tmem_relinquish();
+  } else if (warp == 1 && lane == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&acc_full[a], 1);
+      mbar_init(&acc_empty[a], TILES_EPI_WARPS);  // one arrival per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const TileCoord c = tile_coord(p, t, n_m, n_n);
+        for (int kt = c.kt_begin; kt < c.kt_end; ++kt) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sA = tiles + (size_t)stage * stage_bytes;
+          uint8_t* sB = sA + A_STAGE_BYTES;
+          mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
+          if (!p.a_mn) {
+            tma_load_2d(sA, &tmA, &full_bar[stage], kt * BK, c.m0);
+          } else {
+            for (int h = 0; h < BM / 64; ++h)
+              tma_load_2d(sA + h * (64 * BK * 2), &tmA, &full_bar[stage], c.m0 + h * 64, kt * BK);
+          }
+          if (!p.b_mn) {
+            tma_load_2d(sB, &tmB, &full_bar[stage], kt * BK, c.n0);
+          } else {
+            for (int h = 0; h < BN / 64; ++h)
+              tma_load_2d(sB + h * (64 * BK * 2), &tmB, &full_bar[stage], c.n0 + h * 64, kt * BK);
+          }
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(BM, BN, p.a_mn, p.b_mn);
+      const uint32_t a_lbo = p.a_mn ? 64 * BK * 2 : 16, a_sbo = 1024;
+      const uint32_t b_lbo = p.b_mn ? 64 * BK * 2 : 16, b_sbo = 1024;
+      const uint32_t a_kstep = p.a_mn ? 2048 : 32;
+      const uint32_t b_kstep = p.b_mn ? 2048 : 32;
+      int stage = 0;
+      uint32_t phase = 0;
+      int iter = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++iter) {
+        const TileCoord c = tile_coord(p, t, n_m, n_n);
+        const int acc = iter & 1;
+        mbar_wait(&acc_empty[acc], (uint32_t)((iter >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kt = c.kt_begin; kt < c.kt_end; ++kt) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sA = smem_u32(tiles + (size_t)stage * stage_bytes);
+          const uint32_t sB = sA + A_STAGE_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t da = umma_smem_desc(sA + k * a_kstep, a_lbo, a_sbo);
+            const uint64_t db = umma_smem_desc(sB + k * b_kstep, b_lbo, b_sbo);
+            umma_bf16(d_tmem, da, db, idesc, (kt > c.kt_begin || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&acc_full[acc]);
+      }
+    }
+  } else {
+    // ---- epilogue warps 2..9: TMEM lane quadrant warp % 4, column chunks half, half + 2, ...
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    const int n_chunks = BN / 32;
+    const int etid = threadIdx.x - 64;
+    const b4cp_gemm_epilogue& ep = p.ep;
+    int iter = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++iter) {
+      const TileCoord c = tile_coord(p, t, n_m, n_n);
+      const int acc = iter & 1;
+      float* sb = sbias + acc * BN;
+      if (ep.bias) {
+        stage_bias_tile(sb, ep.bias, c.n0, BN, p.N, etid, 32 * TILES_EPI_WARPS);
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * TILES_EPI_WARPS) : "memory");
+      }
+      mbar_wait(&acc_full[acc], (uint32_t)((iter >> 1) & 1));
+      tc_fence_after();
+      const int row0 = c.m0 + q * 32;
+      const int row = row0 + lane;
+      const uint32_t stg = smem_u32(sStage + (warp - 2) * 4096);
+      float* out_f32 = ep.out_f32 ? ep.out_f32 + (size_t)c.z * ep.split_stride : nullptr;
+      bool released = false;
+      for (int ci = half; ci < n_chunks; ci += 2) {
+        const int c0 = ci * 32;
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), r);
+        tmem_ld_wait();
+        if (ci + 2 >= n_chunks) {  // this warp's last read: hand the accumulator back early
+          tc_fence_before();
+          mbar_arrive_warp(&acc_empty[acc]);
+          released = true;
+        }
+        const int col0 = c.n0 + c0;
+        if (row0 >= p.M || col0 >= p.N) continue;  // warp-uniform
+        float v[32];
+        if (row < p.M) {
+          epilogue_math(ep, row, col0, p.N, r, ep.bias ? sb + c0 : nullptr, v);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0.f;
+        }
+        epilogue_store_coalesced(ep, out_f32, row0, p.M, col0, p.N, v, stg, lane);
+      }
+      if (!released) {  // BN = 32: the second warp of the quadrant has no chunk
+        tc_fence_before();
+        mbar_arrive_warp(&acc_empty[acc]);
+      }
     }
     tc_fence_before();
   }
@@ -596,11 +876,14 @@ extern "C" int b4cp_gemm_bf16(const void* A, int a_mn, long lda, const void* B, 
                  "gemm: split-K writes raw fp32 partials only");
   p.ep = *ep;
   const int stage_bytes = A_STAGE_BYTES + p.BN * BK * 2;
-  int stages = (200 * 1024) / stage_bytes;
+  const int stage_budget = 200 * 1024;
+  int stages = stage_budget / stage_bytes;
+  if (stages < 2) stages = 2;
   if (stages > 6) stages = 6;
   if (stages > p.k_tiles_per_split) stages = p.k_tiles_per_split < 2 ? 2 : p.k_tiles_per_split;
   p.stages = stages;
-  const size_t smem = (size_t)stages * stage_bytes + (2 * stages + 1) * 8 + 64 + p.BN * 4 + 1024;
+  const size_t smem = (size_t)stages * stage_bytes + (2 * stages + 1) * 8 + 64 + p.BN * 4 + 128 +
+                      4 * 4096 + 1024;
 
   CUtensorMap tmA, tmB;
   int rc;
@@ -654,6 +937,31 @@ extern "C" int b4cp_gemm_bf16(const void* A, int a_mn, long lda, const void* B, 
       B4CP_LAUNCH_CHECK();
       return 0;
     }
+  }
+  // more tiles than SMs: tile-persistent kernel with accumulator ping-pong
+  const int n_ntiles = ceil_div(N, p.BN);
+  const long total_tiles = (long)n_mtiles * n_ntiles * splits;
+  if (total_tiles > 148 && total_tiles < (1L << 30) && !getenv("B4CP_GEMM_NO_TILES")) {
+    int tstages = (200 * 1024) / stage_bytes;
+    if (tstages > 6) tstages = 6;
+    if (tstages < 2) tstages = 2;
+    p.stages = tstages;
+    int tstages_fit = (int)((227 * 1024 - (TILES_EPI_WARPS * 4096 + 2 * p.BN * 4 + 1024 + 512)) / stage_bytes);
+    if (tstages > tstages_fit) tstages = tstages_fit;
+    p.stages = tstages;
+    const size_t tsmem = (size_t)tstages * stage_bytes + (2 * tstages + 4) * 8 + 64 + 2 * p.BN * 4 +
+                         128 + TILES_EPI_WARPS * 4096 + 1024;
+    static bool tattr = false;
+    if (!tattr) {
+      B4CP_CUDA(cudaFuncSetAttribute(gemm_umma_tiles_kernel,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      tattr = true;
+    }
+    gemm_umma_tiles_kernel<<<148, TILES_THREADS, tsmem, (cudaStream_t)stream>>>(tmA, tmB, p, n_mtiles, n_ntiles,
+                                                                     (int)total_tiles);
+    note_launches(1);
+    B4CP_LAUNCH_CHECK();
+    return 0;
   }
   static bool attr_set = false;
   if (!attr_set) {
