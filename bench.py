@@ -160,6 +160,30 @@ def workload_name(B):
             f"dff=100, head {CFG['head_dims']}, 7 masks/seq, per-GPU batch {B}")
 
 
+def finish(world):
+    """Flush and exit 0 without interpreter teardown (every rank calls this exactly once)."""
+    sys.stdout.flush()
+    sys.stderr.flush()
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+    os._exit(0)
+
+
+def arm_watchdog(seconds):
+    """A bench that cannot finish must not hold the GPU box: hard exit after `seconds`."""
+    def boom():
+        sys.stderr.write(f"bench.py watchdog: no result after {seconds} s, aborting\n")
+        sys.stderr.flush()
+        os._exit(3)
+    t = threading.Timer(seconds, boom)
+    t.daemon = True
+    t.start()
+
+
 # ------------------------------------------------------------------------------------- ours
 def run_ours(args, rank, world, local_rank):
     import torch
@@ -288,10 +312,12 @@ def run_ours(args, rank, world, local_rank):
                 "includes": "encoder forward + head MLP + fused scoring/top-k + recall/NDCG counters",
                 "recall_at_k": float(c[0] / max(c[2], 1)), "ndcg_at_k": float(c[1] / max(c[2], 1))}
 
+    # Captured CUDA graphs hold NCCL kernels: drop them and quiesce BEFORE any teardown, and leave
+    # through os._exit so that no destructor (process group, graph pool) can block the launcher.
+    trainer._graphs.clear()
+    torch.cuda.synchronize()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        finish(world)
     pk = peaks()
     seqs = world * B * args.steps / (ms_total * 1e-3)
     seqs_e2e = world * B * args.steps / (ms_e2e * 1e-3)
@@ -359,8 +385,7 @@ def run_ours(args, rank, world, local_rank):
         "loss": float(loss_stats[0] / max(loss_stats[1], 1.0)), "e2e_last_loss": loss,
     }
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    finish(world)
 
 
 def main():
@@ -373,7 +398,9 @@ def main():
     ap.add_argument("--batch", type=int, default=4096, help="per-GPU batch (sequences)")
     ap.add_argument("--cpu-batch", type=int, default=64, help="batch of the CPU reference sample")
     ap.add_argument("--no-topk", action="store_true", help="skip the top-k inference leg")
+    ap.add_argument("--max-seconds", type=int, default=1200, help="watchdog: hard exit after this long")
     args = ap.parse_args()
+    arm_watchdog(args.max_seconds)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
