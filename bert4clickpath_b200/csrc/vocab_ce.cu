@@ -18,57 +18,13 @@
 #include <algorithm>
 #include <cstdlib>
 
-#include "common.cuh"
+#include "vocab_ce.cuh"
 #include "../../include/b4cp.h"
 
 namespace b4cp {
 
 int make_tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer,
                       uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer);
-
-static constexpr int VB_M = 128;   // rows per tile
-static constexpr int VB_N = 128;   // vocabulary entries per tile
-static constexpr float LOG2E = 1.4426950408889634f;
-
-__device__ __forceinline__ float ex2(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-
-struct VocabParams {
-  int M, V, h, HB;          // HB = h / 64
-  int n_mtiles, n_vtiles;
-  int tiles_per_chunk;      // forward: vocabulary tiles per CTA
-  int n_chunks;
-  const float* bias;
-  const int32_t* labels;
-  // forward outputs
-  float* part_max;          // [n_chunks][M]
-  float* part_sum;          // [n_chunks][M]
-  float* tgt;               // [M]
-  float* part_u;            // [n_chunks][M][h] un-normalised sum_v exp2(z2 - m) W[:,v] (with_dx)
-  int with_dx;              // forward also accumulates part_u (h = 128)
-  int fwd_stages;
-  // backward inputs / outputs
-  const float* lse;         // [M]
-  const float* loss_stats;  // [2]: (sum, n_valid)
-  float* dW;                // [h][V]
-  float* db;                // [V]
-  int debug;                // timing experiments only (B4CP_DEBUG_BWD bitmask)
-};
-
-// Warp roles (both kernels, 640 threads): warps 0-15 = epilogue, warp 16 = TMA producer + TMEM
-// owner, warp 17 = MMA issuer, warps 18-19 = bias-gradient column sums (backward only).
-// Epilogue warp w reads TMEM lanes [32*(w%4), +32) (hardware restriction) and owns the 32-column
-// group cg = w/4 of every 128-wide tile, so each scheduler has 4 epilogue warps to hide latency.
-// The single-thread roles sit at the HIGHEST warp ids: the issue arbiter favours high warp ids,
-// and a producer / MMA issuer starved by polling epilogue warps stalls the whole pipeline.
-static constexpr int NUM_THREADS = 640;
-static constexpr int NUM_EPI_WARPS = 16;
-static constexpr int NUM_EPI_THREADS = 512;
-static constexpr int WARP_TMA = 16, WARP_MMA = 17, WARP_DB0 = 18;
-static constexpr float LN2 = 0.6931471805599453f;
 
 // bias of this warp's 32 columns, pre-multiplied by log2(e); -inf beyond the vocabulary so that
 // padded columns vanish from the softmax without per-element bound checks
@@ -382,14 +338,14 @@ vocab_ce_dx_kernel(const float* __restrict__ part_max, const float* __restrict__
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * DX_ROWS_PER_BLOCK + (threadIdx.x >> 5);
   if (row >= M) return;
-  const int j = lane * 4;
   const int label = labels[row];
   const float n_valid = loss_stats[1];
-  float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (label >= 0 && n_valid > 0.f) {
+  const bool live = label >= 0 && n_valid > 0.f;
+  float pmx[3] = {-INFINITY, -INFINITY, -INFINITY};
+  float m = -INFINITY, ssum = 1.f;
+  if (live) {
     const int n_parts = 4 * n_chunks;
-    float pmx[3], psm[3];
-    float m = -INFINITY;
+    float psm[3];
 #pragma unroll
     for (int t = 0; t < 3; ++t) {
       const int c = lane + 32 * t;
@@ -398,53 +354,59 @@ vocab_ce_dx_kernel(const float* __restrict__ part_max, const float* __restrict__
       m = fmaxf(m, pmx[t]);
     }
     m = warp_max(m);
-    float ssum = 0.f;
+    ssum = 0.f;
 #pragma unroll
     for (int t = 0; t < 3; ++t)
       if (pmx[t] > -INFINITY) ssum += psm[t] * exp2f(pmx[t] - m);
     ssum = warp_sum(ssum);
-    float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  // vocabulary-parallel: normalise by the GLOBAL log-sum-exp; the one-hot term belongs to the
+  // shard that owns the label (labels of other shards are remapped to >= V)
+  const float norm = live ? (lse_global ? exp2f(m - __ldg(lse_global + row) * LOG2E) : 1.f / ssum) : 0.f;
+  const float inv_n = live ? 1.f / n_valid : 0.f;
+  // lane l owns columns 4l..4l+3 of every 128-column slab (h = 128 or 256)
+  for (int j = lane * 4; j < h; j += 128) {
+    float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (live) {
+      float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 4
-    for (int c = 0; c < n_chunks; ++c) {
-      const int pc = c * 4;  // the 4 column groups of a chunk share one max
-      const float mine = (pc >> 5) == 0 ? pmx[0] : ((pc >> 5) == 1 ? pmx[1] : pmx[2]);
-      const float pm = __shfl_sync(0xffffffffu, mine, pc & 31);
-      const float sc = pm > -INFINITY ? exp2f(pm - m) : 0.f;
-      const float4 v = __ldg(reinterpret_cast<const float4*>(part_u + ((size_t)c * M + row) * h + j));
-      u.x = fmaf(v.x, sc, u.x); u.y = fmaf(v.y, sc, u.y);
-      u.z = fmaf(v.z, sc, u.z); u.w = fmaf(v.w, sc, u.w);
-    }
-    // vocabulary-parallel: normalise by the GLOBAL log-sum-exp; the one-hot term belongs to the
-    // shard that owns the label (labels of other shards are remapped to >= V)
-    const float norm = lse_global ? exp2f(m - __ldg(lse_global + row) * LOG2E) : 1.f / ssum;
-    float wt[4] = {0.f, 0.f, 0.f, 0.f};
-    if (label < V) {
+      for (int c = 0; c < n_chunks; ++c) {
+        const int pc = c * 4;  // the 4 column groups of a chunk share one reference maximum
+        const float mine = (pc >> 5) == 0 ? pmx[0] : ((pc >> 5) == 1 ? pmx[1] : pmx[2]);
+        const float pm = __shfl_sync(0xffffffffu, mine, pc & 31);
+        const float sc = pm > -INFINITY ? exp2f(pm - m) : 0.f;
+        const float4 v = __ldg(reinterpret_cast<const float4*>(part_u + ((size_t)c * M + row) * h + j));
+        u.x = fmaf(v.x, sc, u.x); u.y = fmaf(v.y, sc, u.y);
+        u.z = fmaf(v.z, sc, u.z); u.w = fmaf(v.w, sc, u.w);
+      }
+      float wt[4] = {0.f, 0.f, 0.f, 0.f};
+      if (label < V) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) wt[i] = __bfloat162float(w[(size_t)(j + i) * ldw + label]);
+        for (int i = 0; i < 4; ++i) wt[i] = __bfloat162float(w[(size_t)(j + i) * ldw + label]);
+      }
+      val.x = (u.x * norm - wt[0]) * inv_n;
+      val.y = (u.y * norm - wt[1]) * inv_n;
+      val.z = (u.z * norm - wt[2]) * inv_n;
+      val.w = (u.w * norm - wt[3]) * inv_n;
     }
-    const float inv_n = 1.f / n_valid;
-    val.x = (u.x * norm - wt[0]) * inv_n;
-    val.y = (u.y * norm - wt[1]) * inv_n;
-    val.z = (u.z * norm - wt[2]) * inv_n;
-    val.w = (u.w * norm - wt[3]) * inv_n;
-  }
-  if (gate) {
-    const uint2 g = *reinterpret_cast<const uint2*>(gate + (size_t)row * ld_gate + j);
-    const __nv_bfloat162 g0 = *reinterpret_cast<const __nv_bfloat162*>(&g.x);
-    const __nv_bfloat162 g1 = *reinterpret_cast<const __nv_bfloat162*>(&g.y);
-    if (!(__bfloat162float(g0.x) > 0.f)) val.x = 0.f;
-    if (!(__bfloat162float(g0.y) > 0.f)) val.y = 0.f;
-    if (!(__bfloat162float(g1.x) > 0.f)) val.z = 0.f;
-    if (!(__bfloat162float(g1.y) > 0.f)) val.w = 0.f;
-  }
-  if (out_f32) *reinterpret_cast<float4*>(out_f32 + (size_t)row * h + j) = val;
-  if (out_bf16) {
-    __nv_bfloat162 o0 = __floats2bfloat162_rn(val.x, val.y);
-    __nv_bfloat162 o1 = __floats2bfloat162_rn(val.z, val.w);
-    uint2 o;
-    o.x = *reinterpret_cast<uint32_t*>(&o0);
-    o.y = *reinterpret_cast<uint32_t*>(&o1);
-    *reinterpret_cast<uint2*>(out_bf16 + (size_t)row * ld_bf16 + j) = o;
+    if (gate) {
+      const uint2 g = *reinterpret_cast<const uint2*>(gate + (size_t)row * ld_gate + j);
+      const __nv_bfloat162 g0 = *reinterpret_cast<const __nv_bfloat162*>(&g.x);
+      const __nv_bfloat162 g1 = *reinterpret_cast<const __nv_bfloat162*>(&g.y);
+      if (!(__bfloat162float(g0.x) > 0.f)) val.x = 0.f;
+      if (!(__bfloat162float(g0.y) > 0.f)) val.y = 0.f;
+      if (!(__bfloat162float(g1.x) > 0.f)) val.z = 0.f;
+      if (!(__bfloat162float(g1.y) > 0.f)) val.w = 0.f;
+    }
+    if (out_f32) *reinterpret_cast<float4*>(out_f32 + (size_t)row * h + j) = val;
+    if (out_bf16) {
+      __nv_bfloat162 o0 = __floats2bfloat162_rn(val.x, val.y);
+      __nv_bfloat162 o1 = __floats2bfloat162_rn(val.z, val.w);
+      uint2 o;
+      o.x = *reinterpret_cast<uint32_t*>(&o0);
+      o.y = *reinterpret_cast<uint32_t*>(&o1);
+      *reinterpret_cast<uint2*>(out_bf16 + (size_t)row * ld_bf16 + j) = o;
+    }
   }
 }
 
@@ -765,6 +727,13 @@ extern "C" long b4cp_vocab_ce_workspace_bytes(long M, int V, int h) {
   return (long)(2 * 4 + h) * chunks * M * sizeof(float) + 256;
 }
 
+// B4CP_VOCAB_IMPL=ss selects the first-generation kernels of this file (h = 128 only for the
+// gradient paths); the default is the TS-form generation of vocab_ce_ts.cu.
+static bool use_ts_impl() {
+  const char* e = getenv("B4CP_VOCAB_IMPL");
+  return !(e && e[0] == 's');
+}
+
 static int check_vocab_args(const void* x, long ldx, long M, int h, const void* w, long ldw, int V,
                             int max_h) {
   B4CP_CHECK_ARG(x && w, "vocab_ce: null operand");
@@ -782,7 +751,9 @@ extern "C" int b4cp_vocab_ce_fwd(const void* x_bf16, long ldx, long M, int h, co
                                  void* stream) {
   int rc = check_vocab_args(x_bf16, ldx, M, h, w_bf16, ldw, V, 256);
   if (rc) return rc;
-  B4CP_CHECK_ARG(!want_dx || h == 128, "vocab_ce_fwd: the dX accumulation needs h=128 (got %d)", h);
+  const bool ts = use_ts_impl();
+  B4CP_CHECK_ARG(!want_dx || h == 128 || (ts && h == 256),
+                 "vocab_ce_fwd: the dX accumulation needs h in {128, 256} (got %d)", h);
   B4CP_CHECK_ARG(bias && labels && lse && tgt && workspace, "vocab_ce_fwd: null argument");
   cudaStream_t st = (cudaStream_t)stream;
   VocabParams p = {};
@@ -806,12 +777,17 @@ extern "C" int b4cp_vocab_ce_fwd(const void* x_bf16, long ldx, long M, int h, co
   if (rc) return rc;
   rc = make_tmap_bf16_2d(&tmW, w_bf16, (uint64_t)V, (uint64_t)h, (uint64_t)ldw * 2, 64, 64);
   if (rc) return rc;
-  const size_t smem = (size_t)p.HB * VB_M * 128 + (size_t)p.fwd_stages * 2 * p.HB * 8192 +
-                      (want_dx ? 2 * (2 * VB_M * 128) : 0) + 16 * 32 * 4 + 2 * 4 * VB_M * 4 + 512 + 1024;
-  B4CP_CUDA(cudaFuncSetAttribute(vocab_ce_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 227 * 1024));
-  dim3 grid(p.n_mtiles, p.n_chunks);
-  vocab_ce_fwd_kernel<<<grid, NUM_THREADS, smem, st>>>(tmX, tmW, p);
+  if (ts) {
+    rc = launch_vocab_fwd_ts(tmX, tmW, p, st);
+    if (rc) return rc;
+  } else {
+    const size_t smem = (size_t)p.HB * VB_M * 128 + (size_t)p.fwd_stages * 2 * p.HB * 8192 +
+                        (want_dx ? 2 * (2 * VB_M * 128) : 0) + 16 * 32 * 4 + 2 * 4 * VB_M * 4 + 512 + 1024;
+    B4CP_CUDA(cudaFuncSetAttribute(vocab_ce_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   227 * 1024));
+    dim3 grid(p.n_mtiles, p.n_chunks);
+    vocab_ce_fwd_kernel<<<grid, NUM_THREADS, smem, st>>>(tmX, tmW, p);
+  }
   vocab_ce_merge_kernel<<<ceil_div(M, 256), 256, 0, st>>>(p.part_max, p.part_sum, 4 * p.n_chunks,
                                                           (int)M, V, labels, lse, tgt);
   note_launches(2);
@@ -824,7 +800,7 @@ extern "C" int b4cp_vocab_ce_dx(long M, int h, int V, const int32_t* labels,
                                 const void* w_bf16, long ldw,
                                 const void* gate_bf16, long ld_gate, float* out_f32, void* out_bf16,
                                 long ld_bf16, const void* workspace, void* stream) {
-  B4CP_CHECK_ARG(h == 128, "vocab_ce_dx: h=%d unsupported", h);
+  B4CP_CHECK_ARG(h == 128 || h == 256, "vocab_ce_dx: h=%d unsupported (128 or 256)", h);
   B4CP_CHECK_ARG(labels && loss_stats && w_bf16 && workspace && (out_f32 || out_bf16),
                  "vocab_ce_dx: null argument");
   if (M == 0) return 0;
@@ -847,9 +823,11 @@ extern "C" int b4cp_vocab_ce_bwd(const void* x_bf16, long ldx, long M, int h, co
                                  long ldw, const float* bias, int V, const int32_t* labels,
                                  const float* lse, const float* loss_stats, float* dW, float* db,
                                  void* stream) {
-  int rc = check_vocab_args(x_bf16, ldx, M, h, w_bf16, ldw, V, 128);
+  int rc = check_vocab_args(x_bf16, ldx, M, h, w_bf16, ldw, V, 256);
   if (rc) return rc;
-  B4CP_CHECK_ARG(h == 128, "vocab_ce_bwd: head width h=%d unsupported (the fused backward needs h=128)", h);
+  const bool ts = use_ts_impl();
+  B4CP_CHECK_ARG(h == 128 || (ts && h == 256),
+                 "vocab_ce_bwd: head width h=%d unsupported (the fused backward needs h in {128, 256})", h);
   B4CP_CHECK_ARG(bias && labels && lse && loss_stats && dW && db, "vocab_ce_bwd: null argument");
   cudaStream_t st = (cudaStream_t)stream;
   VocabParams p = {};
@@ -871,12 +849,17 @@ extern "C" int b4cp_vocab_ce_bwd(const void* x_bf16, long ldx, long M, int h, co
   if (rc) return rc;
   rc = make_tmap_bf16_2d(&tmW, w_bf16, (uint64_t)V, (uint64_t)h, (uint64_t)ldw * 2, 64, 64);
   if (rc) return rc;
-  const size_t smem = (size_t)2 * p.HB * 8192 + (size_t)BWD_XBUF * p.HB * VB_M * 128 +
-                      2 * (2 * VB_M * 128) + 2 * VB_N * 4 + 16 * 32 * 4 + 256 + 1024;
-  B4CP_CUDA(cudaFuncSetAttribute(vocab_ce_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 227 * 1024));
-  const int grid = std::min(148, p.n_vtiles);
-  vocab_ce_bwd_kernel<<<grid, NUM_THREADS, smem, st>>>(tmX, tmW, p);
+  if (ts) {
+    rc = launch_vocab_bwd_ts(tmX, tmW, p, st);
+    if (rc) return rc;
+  } else {
+    const size_t smem = (size_t)2 * p.HB * 8192 + (size_t)BWD_XBUF * p.HB * VB_M * 128 +
+                        2 * (2 * VB_M * 128) + 2 * VB_N * 4 + 16 * 32 * 4 + 256 + 1024;
+    B4CP_CUDA(cudaFuncSetAttribute(vocab_ce_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   227 * 1024));
+    const int grid = std::min(148, p.n_vtiles);
+    vocab_ce_bwd_kernel<<<grid, NUM_THREADS, smem, st>>>(tmX, tmW, p);
+  }
   note_launches(1);
   B4CP_LAUNCH_CHECK();
   return 0;

@@ -1,0 +1,637 @@
+// TS-form generation of the fused output stage (see vocab_ce.cu for the mathematics and the
+// reference citations: head.py:36,45; examples/BERT4Rec/source/utils.py:116-134; losses.py:31-98).
+//
+// What changes against the SS-form kernels of vocab_ce.cu: the bf16 tile that feeds the SECOND
+// tensor-core product of each kernel (P' = exp2(z2 - m) in the forward, dZ^T in the backward) is
+// written by the epilogue warps straight into TMEM, over the fp32 accumulator columns they have
+// just read, and is consumed as the TMEM A operand of `tcgen05.mma` (A from TMEM, B from shared
+// memory).  It never touches shared memory, so the 128 B/clk shared-memory port only serves the
+// B operands, and the 64 KB of staging buffers are gone - which is what lets a 256-wide head
+// (V = 1M, h = 256) fit: X tile 64 KB + two 64 KB W stages.
+//
+//   forward : S = X W in TMEM (lanes = rows).  U = sum_v P'_v W_v^T accumulates IN TMEM over the
+//             whole vocabulary chunk (no per-tile fold into registers): P' is taken relative to a
+//             per-row reference maximum m_ref that only moves when the running maximum exceeds
+//             it by more than 2^8 ("lazy rescale"; bf16 keeps fp32's exponent range, so P' <= 256
+//             loses nothing); on that rare event the owning warps rescale their U columns in TMEM.
+//   backward: the transposed problem.  S^T = W^T X^T (lanes = vocabulary entries, columns = rows),
+//             dZ^T = exp2(z2 - lse2)/n - onehot goes back to TMEM, dW^T[v][:] += dZ^T X accumulates
+//             in TMEM over the sweep of all row tiles (N = h up to 256 in one instruction).  The
+//             bias gradient is a per-thread register sum (lane = vocabulary entry), and dW is
+//             written with 128-byte coalesced rows.
+#include <algorithm>
+#include <cstdlib>
+
+#include "vocab_ce.cuh"
+
+namespace b4cp {
+
+static constexpr int TS_THREADS = 576;  // 16 epilogue warps + TMA warp + MMA warp
+static constexpr float RESCALE_TH = 8.f;
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// =============================================================================== forward
+// TMEM columns: S0 [0,128) S1 [128,256) U [256, 256+h).  P'(t) overwrites S(t&1): epilogue warp
+// (q, cg) owns lanes [32q,+32) x columns [32cg,+32) of S and writes its 32 probabilities as 16
+// packed columns at [32cg, 32cg+16) - inside its own region, so no warp overwrites columns another
+// warp still has to read.  K step k8 (vocabulary entries 16k8..16k8+15 of the tile) therefore
+// reads A at column 32*(k8>>1) + 8*(k8&1).
+__global__ void __launch_bounds__(TS_THREADS, 1)
+vocab_ce_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmX,
+                       const __grid_constant__ CUtensorMap tmW, const VocabParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  const int HB = p.HB;
+  const int NST = p.fwd_stages;
+  const bool with_dx = p.with_dx != 0;
+  const int x_bytes = HB * VB_M * 128;
+  const int w_bytes = 2 * HB * 64 * 128;
+  uint8_t* sX = smem;
+  uint8_t* sW = sX + x_bytes;
+  float* sBias = reinterpret_cast<float*>(sW + (size_t)NST * w_bytes);  // [16 warps][32]
+  float* sMax = sBias + 16 * 32;                                         // [2][4 cg][128 rows]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sMax + 2 * 4 * VB_M);
+  uint64_t* x_full = bars;
+  uint64_t* w_full = bars + 1;          // [4]
+  uint64_t* w_empty = w_full + 4;       // [4]
+  uint64_t* s_full = w_empty + 4;       // [2]
+  uint64_t* s_empty = s_full + 2;       // [2]
+  uint64_t* p_full = s_empty + 2;       // [2]
+  uint64_t* u_full = p_full + 2;        // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(u_full + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * VB_M;
+  const int chunk = blockIdx.y;
+  const int t_begin = chunk * p.tiles_per_chunk;
+  const int t_end = min(p.n_vtiles, t_begin + p.tiles_per_chunk);
+  const int ntiles = t_end - t_begin;
+
+  if (warp == WARP_TMA) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmX);
+      tma_prefetch_desc(&tmW);
+    }
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  } else if (warp == WARP_MMA && lane == 0) {
+    mbar_init(x_full, 1);
+    for (int s = 0; s < 4; ++s) {
+      mbar_init(&w_full[s], 1);
+      mbar_init(&w_empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&s_full[b], 1);
+      mbar_init(&s_empty[b], NUM_EPI_WARPS);
+      mbar_init(&p_full[b], NUM_EPI_WARPS);
+      mbar_init(&u_full[b], 1);
+    }
+    fence_barrier_init();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t T_U = tmem_base + 256;
+
+  if (warp == WARP_TMA) {
+    if (lane == 0) {
+      mbar_expect_tx(x_full, (uint32_t)x_bytes);
+      for (int hb = 0; hb < HB; ++hb)
+        tma_load_2d(sX + hb * (VB_M * 128), &tmX, x_full, hb * 64, m0);
+      for (int t = 0; t < ntiles; ++t) {
+        const int st = t % NST;
+        mbar_wait(&w_empty[st], ((t / NST) & 1) ^ 1);
+        mbar_expect_tx(&w_full[st], (uint32_t)w_bytes);
+        const int v0 = (t_begin + t) * VB_N;
+        uint8_t* dst = sW + (size_t)st * w_bytes;
+        for (int vb = 0; vb < 2; ++vb)
+          for (int hb = 0; hb < HB; ++hb)
+            tma_load_2d(dst + (vb * HB + hb) * 8192, &tmW, &w_full[st], v0 + vb * 64, hb * 64);
+      }
+    }
+  } else if (warp == WARP_MMA) {
+    if (lane == 0) {
+      const uint32_t id_s = umma_idesc_bf16(VB_M, VB_N, 0, 1);
+      const uint32_t id_u = umma_idesc_bf16(VB_M, p.h, 0, 0);
+      const uint32_t aX = smem_u32(sX);
+      auto s_ready = [&](int t) -> bool {
+        return mbar_test(&w_full[t % NST], (t / NST) & 1) &&
+               mbar_test(&s_empty[t & 1], ((t >> 1) & 1) ^ 1);
+      };
+      auto issue_s = [&](int t) {
+        const int st = t % NST, buf = t & 1;
+        tc_fence_after();
+        const uint32_t aW = smem_u32(sW + (size_t)st * w_bytes);
+        for (int hb = 0; hb < HB; ++hb) {
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            const uint64_t da = umma_smem_desc(aX + hb * (VB_M * 128) + kk * 32, 16, 1024);
+            const uint64_t db = umma_smem_desc(aW + hb * 8192 + kk * 2048, HB * 8192, 1024);
+            umma_bf16(tmem_base + buf * VB_N, da, db, id_s, (hb | kk) ? 1u : 0u);
+          }
+        }
+        umma_commit(&s_full[buf]);
+      };
+      auto issue_u = [&](int t) {
+        const int st = t % NST, buf = t & 1;
+        tc_fence_after();
+        const uint32_t aW = smem_u32(sW + (size_t)st * w_bytes);
+        const uint32_t tP = tmem_base + buf * VB_N;
+#pragma unroll
+        for (int k8 = 0; k8 < 8; ++k8) {
+          const int vb = k8 >> 2, kk = k8 & 3;
+          const uint64_t db = umma_smem_desc(aW + vb * HB * 8192 + kk * 32, 16, 1024);
+          umma_bf16_ts(T_U, tP + (k8 >> 1) * 32 + (k8 & 1) * 8, db, id_u, (t | k8) ? 1u : 0u);
+        }
+        umma_commit(&u_full[buf]);
+        umma_commit(&w_empty[st]);
+      };
+      mbar_wait(x_full, 0);
+      if (!with_dx) {
+        for (int t = 0; t < ntiles; ++t) {
+          mbar_wait(&w_full[t % NST], (t / NST) & 1);
+          mbar_wait(&s_empty[t & 1], ((t >> 1) & 1) ^ 1);
+          issue_s(t);
+          umma_commit(&w_empty[t % NST]);
+        }
+      } else {
+        // Two queues, one issuing thread: S(ts) needs its W stage and a free accumulator, U(tu)
+        // needs P'(tu).  Neither may hold the other up (a blocking wait for W(t+1) would delay
+        // U(t), hence the release of W(t)'s stage, hence the load of W(t+2): loads and tensor
+        // work would serialise).  Order constraint: S(t+2) after U(t) - the tensor pipe executes
+        // in issue order, so S(t+2) then cannot overwrite P'(t) before U(t) has read it.
+        int ts = 0, tu = 0;
+        while (tu < ntiles) {
+          bool progressed = false;
+          if (tu < ts && mbar_test(&p_full[tu & 1], (tu >> 1) & 1)) {
+            issue_u(tu);
+            ++tu;
+            progressed = true;
+          }
+          if (ts < ntiles && ts <= tu + 1 && s_ready(ts)) {
+            issue_s(ts);
+            ++ts;
+            progressed = true;
+          }
+          if (!progressed) __nanosleep(20);
+        }
+      }
+    }
+  } else if (warp < NUM_EPI_WARPS) {
+    const int q = warp & 3;
+    const int cg = warp >> 2;
+    const int r_in_tile = q * 32 + lane;
+    const int row = m0 + r_in_tile;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    const int label = row < p.M ? p.labels[row] : -1;
+    const uint32_t sb = smem_u32(sBias + warp * 32);
+    const uint32_t aMax = smem_u32(sMax);
+    const int uw = p.h >> 2;  // U columns owned by this warp: [cg*uw, +uw), 32 or 64
+    // statistics in the log2 domain: z2 = (x.w + b) * log2(e); s_run is relative to m_ref
+    float m_run = -INFINITY, m_ref = -INFINITY, s_run = 0.f, tgt2 = 0.f;
+    bool have_tgt = false;
+    auto load_bias = [&](int t) -> float {
+      const int v = (t_begin + t) * VB_N + cg * 32 + lane;
+      return (t < ntiles && v < p.V) ? __ldg(p.bias + v) : -INFINITY;
+    };
+    float bias_next = load_bias(0);
+    for (int t = 0; t < ntiles; ++t) {
+      const int buf = t & 1;
+      const int vbase = (t_begin + t) * VB_N + cg * 32;
+      sts32f(sb + lane * 4, bias_next * LOG2E);
+      __syncwarp();
+      bias_next = load_bias(t + 1);  // in flight while this tile is processed
+      mbar_wait(&s_full[buf], (t >> 1) & 1);
+      tc_fence_after();
+      const uint32_t tS = tmem_base + lane_base + (uint32_t)(buf * VB_N + cg * 32);
+      uint32_t r[32];
+      tmem_ld32(tS, r);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive_warp(&s_empty[buf]);
+      float z[32];
+      float cmax = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 b4 = lds128f(sb + j * 4);
+        z[j + 0] = fmaf(__uint_as_float(r[j + 0]), LOG2E, b4.x);
+        z[j + 1] = fmaf(__uint_as_float(r[j + 1]), LOG2E, b4.y);
+        z[j + 2] = fmaf(__uint_as_float(r[j + 2]), LOG2E, b4.z);
+        z[j + 3] = fmaf(__uint_as_float(r[j + 3]), LOG2E, b4.w);
+        cmax = fmaxf(cmax, fmaxf(fmaxf(z[j], z[j + 1]), fmaxf(z[j + 2], z[j + 3])));
+      }
+      __syncwarp();  // sb is rewritten for the next tile
+      if (label >= vbase && label < vbase + 32) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (vbase + j == label) tgt2 = z[j];
+        have_tgt = true;
+      }
+      if (with_dx) {
+        // the 4 warps that share these rows agree on one running maximum per row
+        const uint32_t mx = aMax + (uint32_t)(buf * (4 * VB_M) + r_in_tile) * 4;
+        sts32f(mx + cg * VB_M * 4, cmax);
+        asm volatile("bar.sync %0, 128;" ::"r"(2 + q) : "memory");
+        cmax = fmaxf(fmaxf(lds32f(mx), lds32f(mx + VB_M * 4)),
+                     fmaxf(lds32f(mx + 2 * VB_M * 4), lds32f(mx + 3 * VB_M * 4)));
+      }
+      const float m_new = fmaxf(m_run, cmax);
+      if (!with_dx) {
+        const float alpha = m_ref > -INFINITY ? ex2(m_ref - m_new) : 0.f;
+        s_run *= alpha;
+        m_ref = m_new;
+      } else if (t == 0) {
+        m_ref = m_new;  // nothing accumulated yet
+      } else {
+        const bool jump = m_new > m_ref + RESCALE_TH;
+        if (__any_sync(0xffffffffu, jump)) {
+          // rare: U(0..t-1) must have retired before its columns are rescaled in TMEM; U(t)
+          // cannot start before p_full(t), which this warp only signals after the rescale
+          mbar_wait(&u_full[(t - 1) & 1], ((t - 1) >> 1) & 1);
+          tc_fence_after();
+          const float f = jump ? ex2(m_ref - m_new) : 1.f;
+#pragma unroll 1
+          for (int c = 0; c < uw; c += 8) {  // 8 columns at a time: keeps z[] in registers
+            const uint32_t tU = T_U + lane_base + (uint32_t)(cg * uw + c);
+            uint32_t u[8];
+            tmem_ld8(tU, u);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 8; ++j) u[j] = __float_as_uint(__uint_as_float(u[j]) * f);
+            tmem_st8(tU, u);
+          }
+          tmem_st_wait();
+          s_run *= f;
+          if (jump) m_ref = m_new;
+        }
+      }
+      m_run = m_new;
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        z[j + 0] = ex2(z[j + 0] - m_ref);
+        z[j + 1] = ex2(z[j + 1] - m_ref);
+        z[j + 2] = ex2(z[j + 2] - m_ref);
+        z[j + 3] = ex2(z[j + 3] - m_ref);
+        a0 += z[j + 0];
+        a1 += z[j + 1];
+        a2 += z[j + 2];
+        a3 += z[j + 3];
+      }
+      s_run += (a0 + a1) + (a2 + a3);
+      if (with_dx) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(z[2 * j], z[2 * j + 1]);
+        tmem_st16(tS, pk);
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive_warp(&p_full[buf]);
+      }
+    }
+    if (with_dx && ntiles > 0) {
+      mbar_wait(&u_full[(ntiles - 1) & 1], ((ntiles - 1) >> 1) & 1);
+      tc_fence_after();
+    }
+    if (row < p.M) {
+      const size_t slot = ((size_t)chunk * 4 + cg) * p.M + row;
+      p.part_max[slot] = m_ref;   // log2 domain; the reference the sums are relative to
+      p.part_sum[slot] = s_run;
+      if (have_tgt) p.tgt[row] = tgt2 * LN2;
+    }
+    if (with_dx) {
+      for (int c = 0; c < uw; c += 32) {
+        uint32_t u[32];
+        tmem_ld32(T_U + lane_base + (uint32_t)(cg * uw + c), u);
+        tmem_ld_wait();
+        if (row < p.M) {
+          float* dst = p.part_u + ((size_t)chunk * p.M + row) * p.h + cg * uw + c;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(dst + j) =
+                make_float4(__uint_as_float(u[j]), __uint_as_float(u[j + 1]),
+                            __uint_as_float(u[j + 2]), __uint_as_float(u[j + 3]));
+        }
+      }
+      tc_fence_before();
+    }
+  }
+  __syncthreads();
+  if (warp == WARP_TMA) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// =============================================================================== backward
+// One CTA owns vocabulary tiles c, c+grid, ... and sweeps every row tile for each of them.
+// Shared memory: sW one vocabulary tile [vb 2][hb HB][64 h-rows][128 B]; sX a ring of row tiles
+// [hb HB][128 rows][128 B].  TMEM columns: S^T0 [0,128) S^T1 [128,256) dW^T [256, 256+h).
+// Epilogue warp (q, cg): lanes = vocabulary entries [32q,+32) of the tile, columns = rows
+// [32cg,+32) of the row tile; dZ^T goes back packed into columns [32cg, 32cg+16) of the S^T buffer.
+__global__ void __launch_bounds__(TS_THREADS, 1)
+vocab_ce_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmX,
+                       const __grid_constant__ CUtensorMap tmW, const VocabParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  const int HB = p.HB, h = p.h;
+  const int XBUF = p.fwd_stages;
+  const int w_bytes = 2 * HB * 8192;
+  const int x_bytes = HB * VB_M * 128;
+  uint8_t* sW = smem;
+  uint8_t* sX = sW + w_bytes;
+  float* sNeg = reinterpret_cast<float*>(sX + (size_t)XBUF * x_bytes);  // [16 warps][32]
+  int32_t* sLab = reinterpret_cast<int32_t*>(sNeg + 16 * 32);           // [16 warps][32]
+  float* sDB = reinterpret_cast<float*>(sLab + 16 * 32);                // [4 cg][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sDB + 4 * VB_N);
+  uint64_t* w_full = bars;            // 1
+  uint64_t* w_empty = bars + 1;       // 1
+  uint64_t* x_full = bars + 2;        // 4
+  uint64_t* x_empty = x_full + 4;     // 4
+  uint64_t* s_full = x_empty + 4;     // 2
+  uint64_t* s_empty = s_full + 2;     // 2
+  uint64_t* dz_full = s_empty + 2;    // 2
+  uint64_t* dw_full = dz_full + 2;    // 1
+  uint64_t* dw_empty = dw_full + 1;   // 1
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dw_empty + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nm = p.n_mtiles;
+  const int n_my = (p.n_vtiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (warp == WARP_TMA) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmX);
+      tma_prefetch_desc(&tmW);
+    }
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  } else if (warp == WARP_MMA && lane == 0) {
+    mbar_init(w_full, 1);
+    mbar_init(w_empty, 1);
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&x_full[i], 1);
+      mbar_init(&x_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_empty[i], NUM_EPI_WARPS);
+      mbar_init(&dz_full[i], NUM_EPI_WARPS);
+    }
+    mbar_init(dw_full, 1);
+    mbar_init(dw_empty, NUM_EPI_WARPS);
+    fence_barrier_init();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t T_S = tmem_base, T_DW = tmem_base + 256;
+
+  if (warp == WARP_TMA) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      long it = 0;
+      for (int vt = 0; vt < n_my; ++vt) {
+        const int v0 = ((int)blockIdx.x + vt * (int)gridDim.x) * VB_N;
+        mbar_wait(w_empty, (vt & 1) ^ 1);
+        mbar_expect_tx(w_full, (uint32_t)w_bytes);
+        for (int vb = 0; vb < 2; ++vb)
+          for (int hb = 0; hb < HB; ++hb)
+            tma_load_2d(sW + (vb * HB + hb) * 8192, &tmW, w_full, v0 + vb * 64, hb * 64);
+        for (int i = 0; i < nm; ++i, ++it) {
+          const int xb = (int)(it % XBUF);
+          mbar_wait(&x_empty[xb], (uint32_t)((it / XBUF) & 1) ^ 1);
+          mbar_expect_tx(&x_full[xb], (uint32_t)x_bytes);
+          for (int hb = 0; hb < HB; ++hb)
+            tma_load_2d(sX + (size_t)xb * x_bytes + hb * (VB_M * 128), &tmX, &x_full[xb], hb * 64,
+                        i * VB_M);
+        }
+      }
+    }
+  } else if (warp == WARP_MMA) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t id_s = umma_idesc_bf16(VB_N, VB_M, 1, 0);  // S^T = W^T (MN-major) X^T (K-major)
+      const uint32_t id_dw = umma_idesc_bf16(VB_N, h, 0, 1);    // dW^T = dZ^T (TMEM) X (MN-major)
+      const uint32_t aW = smem_u32(sW);
+      auto s_ready = [&](long it) -> bool {
+        return mbar_test(&x_full[it % XBUF], (uint32_t)((it / XBUF) & 1)) &&
+               mbar_test(&s_empty[it & 1], (uint32_t)((it >> 1) & 1) ^ 1);
+      };
+      auto issue_s = [&](long it) {
+        const int xb = (int)(it % XBUF), sb = (int)(it & 1);
+        tc_fence_after();
+        const uint32_t aX = smem_u32(sX + (size_t)xb * x_bytes);
+        for (int hb = 0; hb < HB; ++hb) {
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            const uint64_t da = umma_smem_desc(aW + hb * 8192 + kk * 2048, HB * 8192, 1024);
+            const uint64_t db = umma_smem_desc(aX + hb * (VB_M * 128) + kk * 32, 16, 1024);
+            umma_bf16(T_S + sb * VB_M, da, db, id_s, (hb | kk) ? 1u : 0u);
+          }
+        }
+        umma_commit(&s_full[sb]);
+      };
+      // dW^T[128 v x h] (+)= dZ^T[128 v x 128 rows] X[128 rows x h]: 8 K steps of 16 rows
+      auto issue_dw = [&](long it, int i) {
+        const int xb = (int)(it % XBUF), zb = (int)(it & 1);
+        tc_fence_after();
+        const uint32_t aX = smem_u32(sX + (size_t)xb * x_bytes);
+        const uint32_t tZ = T_S + zb * VB_M;
+#pragma unroll
+        for (int k8 = 0; k8 < 8; ++k8) {
+          const uint64_t db = umma_smem_desc(aX + k8 * 2048, VB_M * 128, 1024);
+          umma_bf16_ts(T_DW, tZ + (k8 >> 1) * 32 + (k8 & 1) * 8, db, id_dw, (i | k8) ? 1u : 0u);
+        }
+        umma_commit(&x_empty[xb]);
+      };
+      long it0 = 0;
+      for (int vt = 0; vt < n_my; ++vt, it0 += nm) {
+        mbar_wait(w_full, vt & 1);
+        // two queues (see the forward kernel): S^T(is) needs its X tile and a free accumulator,
+        // dW(iu) needs dZ^T(iu); S^T(i+2) is only issued after dW(i)
+        int is = 0, iu = 0;
+        while (iu < nm) {
+          bool progressed = false;
+          if (iu < is && mbar_test(&dz_full[(it0 + iu) & 1], (uint32_t)(((it0 + iu) >> 1) & 1))) {
+            if (iu == 0) mbar_wait(dw_empty, (vt & 1) ^ 1);
+            issue_dw(it0 + iu, iu);
+            ++iu;
+            progressed = true;
+          }
+          if (is < nm && is <= iu + 1 && s_ready(it0 + is)) {
+            issue_s(it0 + is);
+            ++is;
+            progressed = true;
+          }
+          if (!progressed) __nanosleep(20);
+        }
+        umma_commit(dw_full);
+        umma_commit(w_empty);
+      }
+    }
+  } else if (warp < NUM_EPI_WARPS) {
+    // ------------------------------------------------------------------ epilogue (16 warps)
+    const int q = warp & 3;
+    const int cg = warp >> 2;
+    const int v_local = q * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    const uint32_t aNeg = smem_u32(sNeg + warp * 32);
+    const uint32_t aLab = smem_u32(sLab + warp * 32);
+    const int uw = h >> 2;
+    const float n_valid = p.loss_stats[1];
+    const float inv_n = n_valid > 0.f ? 1.f / n_valid : 0.f;
+    const float log2_inv_n = n_valid > 0.f ? -log2f(n_valid) : 0.f;
+    long it = 0;
+    for (int vt = 0; vt < n_my; ++vt) {
+      const int v0 = ((int)blockIdx.x + vt * (int)gridDim.x) * VB_N;
+      const int v = v0 + v_local;
+      const float b2 = v < p.V ? __ldg(p.bias + v) * LOG2E : -INFINITY;
+      float db_acc = 0.f;
+      // statistics of row (32cg + lane) of the next row tile, prefetched one tile ahead
+      int label_next = -1;
+      float lse_next = 0.f;
+      {
+        const int r0 = cg * 32 + lane;
+        if (r0 < p.M) {
+          label_next = __ldg(p.labels + r0);
+          lse_next = __ldg(p.lse + r0);
+        }
+      }
+      for (int i = 0; i < nm; ++i, ++it) {
+        const int sbuf = (int)(it & 1);
+        // dZ = exp2(z2 - lse2 - log2 n): the 1/n_valid factor rides in the exponent; -inf for
+        // padded rows and rows past M, which then contribute exactly 0
+        const float lneg = (label_next >= 0 && n_valid > 0.f) ? log2_inv_n - lse_next * LOG2E
+                                                               : -INFINITY;
+        sts32f(aNeg + lane * 4, lneg);
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(aLab + lane * 4), "r"(label_next) : "memory");
+        const bool hit = __any_sync(0xffffffffu, (unsigned)(label_next - v0) < (unsigned)VB_N);
+        __syncwarp();
+        {
+          const int nrow = (i + 1) * VB_M + cg * 32 + lane;
+          const bool ok = (i + 1 < nm) && nrow < p.M;
+          label_next = ok ? __ldg(p.labels + nrow) : -1;
+          lse_next = ok ? __ldg(p.lse + nrow) : 0.f;
+        }
+        mbar_wait(&s_full[sbuf], (uint32_t)((it >> 1) & 1));
+        tc_fence_after();
+        const uint32_t tS = T_S + lane_base + (uint32_t)(sbuf * VB_M + cg * 32);
+        uint32_t r[32];
+        tmem_ld32(tS, r);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive_warp(&s_empty[sbuf]);
+        float g[32];
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 n4 = lds128f(aNeg + j * 4);
+          g[j + 0] = ex2(fmaf(__uint_as_float(r[j + 0]), LOG2E, b2 + n4.x));
+          g[j + 1] = ex2(fmaf(__uint_as_float(r[j + 1]), LOG2E, b2 + n4.y));
+          g[j + 2] = ex2(fmaf(__uint_as_float(r[j + 2]), LOG2E, b2 + n4.z));
+          g[j + 3] = ex2(fmaf(__uint_as_float(r[j + 3]), LOG2E, b2 + n4.w));
+        }
+        if (hit) {  // some row of this 32-row group has its label inside this vocabulary tile
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            int lab;
+            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(lab) : "r"(aLab + j * 4) : "memory");
+            if (lab == v) g[j] -= inv_n;
+          }
+        }
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        uint32_t pk[16];
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          a0 += g[j + 0];
+          a1 += g[j + 1];
+          a2 += g[j + 2];
+          a3 += g[j + 3];
+          pk[j / 2] = pack_bf16x2(g[j], g[j + 1]);
+          pk[j / 2 + 1] = pack_bf16x2(g[j + 2], g[j + 3]);
+        }
+        db_acc += (a0 + a1) + (a2 + a3);
+        tmem_st16(tS, pk);
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive_warp(&dz_full[sbuf]);  // (its __syncwarp also orders the sNeg/sLab reuse)
+      }
+      // bias gradient: the 4 warps that share these vocabulary entries combine their row groups
+      sDB[cg * VB_N + v_local] = db_acc;
+      asm volatile("bar.sync %0, 128;" ::"r"(2 + q) : "memory");
+      if (cg == 0 && v < p.V)
+        p.db[v] = (sDB[v_local] + sDB[VB_N + v_local]) + (sDB[2 * VB_N + v_local] + sDB[3 * VB_N + v_local]);
+      asm volatile("bar.sync %0, 128;" ::"r"(2 + q) : "memory");
+      // dW^T tile: lane = vocabulary entry, columns = input features -> each store instruction of
+      // a warp writes 32 consecutive floats of one dW row
+      mbar_wait(dw_full, vt & 1);
+      tc_fence_after();
+      for (int c = 0; c < uw; c += 32) {
+        uint32_t r[32];
+        tmem_ld32(T_DW + lane_base + (uint32_t)(cg * uw + c), r);
+        tmem_ld_wait();
+        if (v < p.V) {
+          float* dst = p.dW + (size_t)(cg * uw + c) * p.V + v;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) dst[(size_t)j * p.V] = __uint_as_float(r[j]);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive_warp(dw_empty);
+    }
+  }
+  __syncthreads();
+  if (warp == WARP_TMA) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------- launchers
+static size_t fwd_ts_smem(int HB, int stages) {
+  return (size_t)HB * VB_M * 128 + (size_t)stages * 2 * HB * 8192 + 16 * 32 * 4 +
+         2 * 4 * VB_M * 4 + 256 + 1024;
+}
+
+int launch_vocab_fwd_ts(const CUtensorMap& tmX, const CUtensorMap& tmW, const VocabParams& p_in,
+                        cudaStream_t st) {
+  VocabParams p = p_in;
+  int stages = 4;
+  while (stages > 2 && fwd_ts_smem(p.HB, stages) > 227 * 1024) --stages;
+  B4CP_CHECK_ARG(fwd_ts_smem(p.HB, stages) <= 227 * 1024, "vocab_ce_fwd: h=%d does not fit", p.h);
+  p.fwd_stages = stages;
+  B4CP_CUDA(cudaFuncSetAttribute(vocab_ce_fwd_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 227 * 1024));
+  dim3 grid(p.n_mtiles, p.n_chunks);
+  vocab_ce_fwd_ts_kernel<<<grid, TS_THREADS, fwd_ts_smem(p.HB, stages), st>>>(tmX, tmW, p);
+  return 0;
+}
+
+static size_t bwd_ts_smem(int HB, int xbuf) {
+  return (size_t)2 * HB * 8192 + (size_t)xbuf * HB * VB_M * 128 + 2 * 16 * 32 * 4 + 4 * VB_N * 4 +
+         256 + 1024;
+}
+
+int launch_vocab_bwd_ts(const CUtensorMap& tmX, const CUtensorMap& tmW, const VocabParams& p_in,
+                        cudaStream_t st) {
+  VocabParams p = p_in;
+  int xbuf = 4;
+  while (xbuf > 2 && bwd_ts_smem(p.HB, xbuf) > 227 * 1024) --xbuf;
+  B4CP_CHECK_ARG(bwd_ts_smem(p.HB, xbuf) <= 227 * 1024, "vocab_ce_bwd: h=%d does not fit", p.h);
+  p.fwd_stages = xbuf;
+  B4CP_CUDA(cudaFuncSetAttribute(vocab_ce_bwd_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 227 * 1024));
+  const int grid = std::min(148, p.n_vtiles);
+  vocab_ce_bwd_ts_kernel<<<grid, TS_THREADS, bwd_ts_smem(p.HB, xbuf), st>>>(tmX, tmW, p);
+  return 0;
+}
+
+}  // namespace b4cp

@@ -9,7 +9,7 @@ from bert4clickpath_b200 import ops  # noqa: E402
 
 M = int(sys.argv[1]) if len(sys.argv) > 1 else 28672
 V = int(sys.argv[2]) if len(sys.argv) > 2 else 54293
-h = 128
+h = int(sys.argv[3]) if len(sys.argv) > 3 else 128
 torch.manual_seed(0)
 xb = (torch.randn(M, h, device="cuda") * 0.5).to(torch.bfloat16)
 wb = torch.zeros(h, ops.ld8(V), device="cuda", dtype=torch.bfloat16)

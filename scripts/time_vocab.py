@@ -1,7 +1,10 @@
-import sys, torch, numpy as np
+"""Times the fused vocabulary-stage kernels: python scripts/time_vocab.py M [h] [V].
+B4CP_VOCAB_IMPL=ss selects the first-generation (shared-memory staged) kernels."""
+import sys, os, torch, numpy as np
 sys.path.insert(0, ".")
 from bert4clickpath_b200 import ops
-M, h, V = int(sys.argv[1]), 128, 54293
+M = int(sys.argv[1]); h = int(sys.argv[2]) if len(sys.argv) > 2 else 128
+V = int(sys.argv[3]) if len(sys.argv) > 3 else 54293
 xb = (torch.randn(M, h, device="cuda") * 0.5).to(torch.bfloat16)
 wb = torch.zeros(h, ops.ld8(V), device="cuda", dtype=torch.bfloat16); wb[:, :V] = (torch.randn(h, V, device="cuda") * 0.1).to(torch.bfloat16)
 bias = torch.zeros(V, device="cuda"); labels = torch.randint(0, V, (M,), device="cuda", dtype=torch.int32)
@@ -15,10 +18,14 @@ def t(fn, n=10):
     for _ in range(n): fn()
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / n
+dxok = h in (128, 256) and not (h == 256 and os.environ.get("B4CP_VOCAB_IMPL", "").startswith("s"))
 tf0 = t(lambda: ops.vocab_ce_fwd(xb, M, h, wb, bias, V, labels, lse, tgt, want_dx=False))
+fl = 2.0 * M * h * V
+if not dxok:
+    print(f"M={M} h={h} V={V}: fwd(no dx) {tf0:.3f} ms ({fl/tf0/1e9:.0f} TF/s)")
+    sys.exit(0)
 tf = t(lambda: ops.vocab_ce_fwd(xb, M, h, wb, bias, V, labels, lse, tgt, want_dx=True))
 ops.ce_loss_reduce(lse, tgt, labels, stats)
 tb = t(lambda: ops.vocab_ce_bwd(xb, M, h, wb, bias, V, labels, lse, stats, dW, db))
 td = t(lambda: ops.vocab_ce_dx(M, h, V, labels, stats, wb, None, dX, None))
-fl = 2.0 * M * h * V
-print(f"M={M}: fwd(no dx) {tf0:.3f} ms, fwd+U {tf:.3f} ms ({2*fl/tf/1e9:.0f} TF/s of 2 MMAs), dx {td:.3f} ms, bwd {tb:.3f} ms ({2*fl/tb/1e9:.0f} TF/s of 2 MMAs); total {tf+td+tb:.3f} ms = {3*fl/(tf+td+tb)/1e9:.0f} TF/s useful (6MhV)")
+print(f"impl={os.environ.get('B4CP_VOCAB_IMPL','ts')} M={M} h={h} V={V}: fwd(no dx) {tf0:.3f} ms ({fl/tf0/1e9:.0f} TF/s), fwd+U {tf:.3f} ms ({2*fl/tf/1e9:.0f} TF/s of 2 MMAs), dx {td:.3f} ms, bwd {tb:.3f} ms ({2*fl/tb/1e9:.0f} TF/s of 2 MMAs; {fl/tb/1e9:.0f} algorithmic); total {tf+td+tb:.3f} ms = {3*fl/(tf+td+tb)/1e9:.0f} TF/s useful (6MhV)")

@@ -33,7 +33,7 @@ def to_dev(x, w, b, labels):
 @pytest.mark.parametrize("M,h,V", [(300, 128, 1237), (128, 128, 128), (77, 128, 54293),
                                    (1000, 64, 5000), (260, 256, 3001)])
 def test_fused_forward_lse_and_target(cuda_lib, M, h, V, want_dx):
-    want_dx = want_dx and h == 128
+    want_dx = want_dx and h in (128, 256)
     from bert4clickpath_b200 import ops
     x, w, b, labels = make(M, h, V, M + V)
     z = x @ w + b.astype(np.float64)
@@ -54,15 +54,17 @@ def test_fused_forward_lse_and_target(cuda_lib, M, h, V, want_dx):
     assert s[1] == n and abs(s[0] / s[1] - loss) < 1e-5 * abs(loss)
 
 
-@pytest.mark.parametrize("M,V", [(300, 1237), (128, 128), (77, 54293), (1000, 5000), (5, 300)])
-def test_fused_backward_gradients(cuda_lib, M, V):
+@pytest.mark.parametrize("M,V,h", [(300, 1237, 128), (128, 128, 128), (77, 54293, 128),
+                                   (1000, 5000, 128), (5, 300, 128), (300, 1237, 256),
+                                   (129, 54293, 256), (1000, 5000, 256), (5, 300, 256)])
+def test_fused_backward_gradients(cuda_lib, M, V, h):
     from bert4clickpath_b200 import ops
-    h = 128
     x, w, b, labels = make(M, h, V, 7 * M + V)
     z = x @ w + b.astype(np.float64)
     loss, dz, n = O.cloze_ce_from_logits(z, labels)
     dzq = bf16(dz)  # the kernel feeds bf16 dZ to the tensor cores
-    dX_ref, dW_ref, db_ref = dzq @ w.T, x.T @ dzq, dzq.sum(0)
+    # db is a register sum of the unrounded fp32 dZ (lane = vocabulary entry): exact reference
+    dX_ref, dW_ref, db_ref = dzq @ w.T, x.T @ dzq, dz.sum(0)
     xb, wb, bd, ld = to_dev(x, w, b, labels)
     lse = torch.empty(M, device="cuda")
     tgt = torch.empty(M, device="cuda")
@@ -79,7 +81,7 @@ def test_fused_backward_gradients(cuda_lib, M, V):
     # (sum_v bf16(p'_v) W_v) / sum - W_label: compare with the exact softmax expectation
     dX_exact = dz @ w.T
     for name, got, want, tol in (("dX", dX, dX_exact, 4e-3), ("dW", dW, dW_ref, 2e-3),
-                                 ("db", db, db_ref, 2e-3)):
+                                 ("db", db, db_ref, 4e-3)):
         g = got.cpu().numpy()
         assert np.isfinite(g).all(), name
         # fp32 accumulation + bf16 rounding of the probabilities: fraction of the max-norm
@@ -94,9 +96,37 @@ def test_fused_backward_gradients(cuda_lib, M, V):
     assert torch.equal(dW, dW2) and torch.equal(dX, dX2)  # fixed accumulation order: reproducible
 
 
-def test_fused_all_rows_padded(cuda_lib):
+def test_fused_lazy_rescale_of_the_running_maximum(cuda_lib):
+    """The forward keeps U = sum_v exp2(z - m_ref) W_v in TMEM and only rescales it when a row's
+    running maximum jumps by more than 2^8: logits that grow along the vocabulary (so the maximum
+    moves in many tiles, by more and by less than the threshold) must give the same dX."""
     from bert4clickpath_b200 import ops
-    M, h, V = 130, 128, 700
+    M, h, V = 200, 128, 4000
+    x, w, b, labels = make(M, h, V, 99)
+    b = (np.linspace(-60.0, 60.0, V) + np.random.default_rng(5).normal(size=V) * 4).astype(np.float32)
+    b[V // 2] = 90.0    # one big jump in the middle of a chunk
+    z = x @ w + b.astype(np.float64)
+    loss, dz, n = O.cloze_ce_from_logits(z, labels)
+    xb, wb, bd, ld = to_dev(x, w, b, labels)
+    lse, tgt, stats = (torch.empty(M, device="cuda"), torch.empty(M, device="cuda"),
+                       torch.empty(2, device="cuda"))
+    ops.vocab_ce_fwd(xb, M, h, wb, bd, V, ld, lse, tgt, want_dx=True)
+    ops.ce_loss_reduce(lse, tgt, ld, stats)
+    dX = torch.full((M, h), float("nan"), device="cuda")
+    ops.vocab_ce_dx(M, h, V, ld, stats, wb, None, dX, None)
+    torch.cuda.synchronize()
+    m = z.max(-1)
+    np.testing.assert_allclose(lse.cpu().numpy(), m + np.log(np.exp(z - m[:, None]).sum(-1)), rtol=2e-5, atol=2e-5)
+    want = dz @ w.T
+    g = dX.cpu().numpy()
+    assert np.isfinite(g).all()
+    assert np.abs(g - want).max() <= 4e-3 * np.abs(want).max()
+
+
+@pytest.mark.parametrize("h", [128, 256])
+def test_fused_all_rows_padded(cuda_lib, h):
+    from bert4clickpath_b200 import ops
+    M, V = 130, 700
     x, w, b, labels = make(M, h, V, 1)
     labels[:] = -1
     xb, wb, bd, ld = to_dev(x, w, b, labels)
