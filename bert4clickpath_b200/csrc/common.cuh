@@ -208,6 +208,49 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, u
       "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// ---- warp-uniform issue.  `if (lane == 0) { ...tcgen05.mma... }` puts descriptor arithmetic in
+// divergent control flow: ptxas then cannot use the uniform datapath and wraps EVERY UTCHMMA in a
+// waterfall loop (ELECT / R2UR.BROADCAST / BRA.U.ANY, ~20 instructions and several dependent
+// R2UR latencies per MMA), so issuing a 128x128x16 MMA costs as much as executing it.  The *_el
+// variants are executed by the WHOLE warp in uniform control flow (operands derived from kernel
+// parameters, blockIdx, loop counters, votes and shfl-broadcast values) and predicate only the
+// tcgen05 instruction itself on an elected lane.
+__device__ __forceinline__ void umma_bf16_el(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                             uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_ts_el(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc,
+                                                uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_el(uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(
+          smem_u32(bar))
+      : "memory");
+}
+// warp-uniform barrier polls (every lane polls; the vote makes the result provably uniform)
+__device__ __forceinline__ bool mbar_test_all(uint64_t* bar, uint32_t parity) {
+  return __all_sync(0xffffffffu, mbar_test(bar, parity));
+}
+__device__ __forceinline__ void mbar_wait_all(uint64_t* bar, uint32_t parity) {
+  while (!__all_sync(0xffffffffu, mbar_try_wait(bar, parity))) {
+  }
+}
 // registers -> TMEM: 32 lanes x 16 (or 32) consecutive 32-bit columns, thread = lane.
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
   asm volatile(

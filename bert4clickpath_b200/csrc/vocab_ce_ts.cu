@@ -65,7 +65,9 @@ vocab_ce_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmX,
   uint64_t* u_full = p_full + 2;        // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(u_full + 2);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through shfl: provably warp-uniform, so the role branches are uniform control flow
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * VB_M;
   const int chunk = blockIdx.y;
   const int t_begin = chunk * p.tiles_per_chunk;
@@ -96,7 +98,7 @@ vocab_ce_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmX,
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
   const uint32_t T_U = tmem_base + 256;
 
   if (warp == WARP_TMA) {
@@ -116,71 +118,74 @@ vocab_ce_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmX,
       }
     }
   } else if (warp == WARP_MMA) {
-    if (lane == 0) {
-      const uint32_t id_s = umma_idesc_bf16(VB_M, VB_N, 0, 1);
-      const uint32_t id_u = umma_idesc_bf16(VB_M, p.h, 0, 0);
-      const uint32_t aX = smem_u32(sX);
-      auto s_ready = [&](int t) -> bool {
-        return mbar_test(&w_full[t % NST], (t / NST) & 1) &&
-               mbar_test(&s_empty[t & 1], ((t >> 1) & 1) ^ 1);
-      };
-      auto issue_s = [&](int t) {
-        const int st = t % NST, buf = t & 1;
-        tc_fence_after();
-        const uint32_t aW = smem_u32(sW + (size_t)st * w_bytes);
-        for (int hb = 0; hb < HB; ++hb) {
+    // The WHOLE warp runs this loop in uniform control flow; only the tcgen05 instructions are
+    // predicated on an elected lane (see umma_bf16_el in common.cuh).
+    const uint32_t id_s = umma_idesc_bf16(VB_M, VB_N, 0, 1);
+    const uint32_t id_u = umma_idesc_bf16(VB_M, p.h, 0, 0);
+    const uint32_t aX = smem_u32(sX);
+    const uint32_t aW0 = smem_u32(sW);
+    // descriptors differ only in their 14-bit start-address field: build once, add (bytes >> 4)
+    const uint64_t dX = umma_smem_desc(aX, 16, 1024);                // X, K-major (A of S)
+    const uint64_t dWs = umma_smem_desc(aW0, HB * 8192, 1024);       // W, MN-major (B of S)
+    const uint64_t dWu = umma_smem_desc(aW0, 16, 1024);              // W, K-major (B of U)
+    auto s_ready = [&](int t) -> bool {
+      return mbar_test_all(&w_full[t % NST], (t / NST) & 1) &&
+             mbar_test_all(&s_empty[t & 1], ((t >> 1) & 1) ^ 1);
+    };
+    auto issue_s = [&](int t) {
+      const int st = t % NST, buf = t & 1;
+      tc_fence_after();
+      const uint32_t wo = (uint32_t)(st * w_bytes) >> 4;
+      for (int hb = 0; hb < HB; ++hb) {
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
-            const uint64_t da = umma_smem_desc(aX + hb * (VB_M * 128) + kk * 32, 16, 1024);
-            const uint64_t db = umma_smem_desc(aW + hb * 8192 + kk * 2048, HB * 8192, 1024);
-            umma_bf16(tmem_base + buf * VB_N, da, db, id_s, (hb | kk) ? 1u : 0u);
-          }
-        }
-        umma_commit(&s_full[buf]);
-      };
-      auto issue_u = [&](int t) {
-        const int st = t % NST, buf = t & 1;
-        tc_fence_after();
-        const uint32_t aW = smem_u32(sW + (size_t)st * w_bytes);
-        const uint32_t tP = tmem_base + buf * VB_N;
+        for (int kk = 0; kk < 4; ++kk)
+          umma_bf16_el(tmem_base + buf * VB_N, dX + (uint32_t)((hb * (VB_M * 128) + kk * 32) >> 4),
+                       dWs + (wo + (uint32_t)((hb * 8192 + kk * 2048) >> 4)), id_s, (hb | kk) ? 1u : 0u);
+      }
+      umma_commit_el(&s_full[buf]);
+    };
+    auto issue_u = [&](int t) {
+      const int st = t % NST, buf = t & 1;
+      tc_fence_after();
+      const uint32_t wo = (uint32_t)(st * w_bytes) >> 4;
+      const uint32_t tP = tmem_base + buf * VB_N;
 #pragma unroll
-        for (int k8 = 0; k8 < 8; ++k8) {
-          const int vb = k8 >> 2, kk = k8 & 3;
-          const uint64_t db = umma_smem_desc(aW + vb * HB * 8192 + kk * 32, 16, 1024);
-          umma_bf16_ts(T_U, tP + (k8 >> 1) * 32 + (k8 & 1) * 8, db, id_u, (t | k8) ? 1u : 0u);
+      for (int k8 = 0; k8 < 8; ++k8) {
+        const int vb = k8 >> 2, kk = k8 & 3;
+        umma_bf16_ts_el(T_U, tP + (k8 >> 1) * 32 + (k8 & 1) * 8,
+                        dWu + (wo + (uint32_t)((vb * HB * 8192 + kk * 32) >> 4)), id_u, (t | k8) ? 1u : 0u);
+      }
+      umma_commit_el(&u_full[buf]);
+      umma_commit_el(&w_empty[st]);
+    };
+    mbar_wait_all(x_full, 0);
+    if (!with_dx) {
+      for (int t = 0; t < ntiles; ++t) {
+        mbar_wait_all(&w_full[t % NST], (t / NST) & 1);
+        mbar_wait_all(&s_empty[t & 1], ((t >> 1) & 1) ^ 1);
+        issue_s(t);
+        umma_commit_el(&w_empty[t % NST]);
+      }
+    } else {
+      // Two queues, one issuing warp: S(ts) needs its W stage and a free accumulator, U(tu)
+      // needs P'(tu).  Neither may hold the other up (a blocking wait for W(t+1) would delay
+      // U(t), hence the release of W(t)'s stage, hence the load of W(t+2): loads and tensor
+      // work would serialise).  Order constraint: S(t+2) after U(t) - the tensor pipe executes
+      // in issue order, so S(t+2) then cannot overwrite P'(t) before U(t) has read it.
+      int ts = 0, tu = 0;
+      while (tu < ntiles) {
+        bool progressed = false;
+        if (tu < ts && mbar_test_all(&p_full[tu & 1], (tu >> 1) & 1)) {
+          issue_u(tu);
+          ++tu;
+          progressed = true;
         }
-        umma_commit(&u_full[buf]);
-        umma_commit(&w_empty[st]);
-      };
-      mbar_wait(x_full, 0);
-      if (!with_dx) {
-        for (int t = 0; t < ntiles; ++t) {
-          mbar_wait(&w_full[t % NST], (t / NST) & 1);
-          mbar_wait(&s_empty[t & 1], ((t >> 1) & 1) ^ 1);
-          issue_s(t);
-          umma_commit(&w_empty[t % NST]);
+        if (ts < ntiles && ts <= tu + 1 && s_ready(ts)) {
+          issue_s(ts);
+          ++ts;
+          progressed = true;
         }
-      } else {
-        // Two queues, one issuing thread: S(ts) needs its W stage and a free accumulator, U(tu)
-        // needs P'(tu).  Neither may hold the other up (a blocking wait for W(t+1) would delay
-        // U(t), hence the release of W(t)'s stage, hence the load of W(t+2): loads and tensor
-        // work would serialise).  Order constraint: S(t+2) after U(t) - the tensor pipe executes
-        // in issue order, so S(t+2) then cannot overwrite P'(t) before U(t) has read it.
-        int ts = 0, tu = 0;
-        while (tu < ntiles) {
-          bool progressed = false;
-          if (tu < ts && mbar_test(&p_full[tu & 1], (tu >> 1) & 1)) {
-            issue_u(tu);
-            ++tu;
-            progressed = true;
-          }
-          if (ts < ntiles && ts <= tu + 1 && s_ready(ts)) {
-            issue_s(ts);
-            ++ts;
-            progressed = true;
-          }
-          if (!progressed) __nanosleep(20);
-        }
+        if (!progressed) __nanosleep(20);
       }
     }
   } else if (warp < NUM_EPI_WARPS) {
@@ -362,7 +367,9 @@ vocab_ce_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmX,
   uint64_t* dw_empty = dw_full + 1;   // 1
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dw_empty + 1);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through shfl: provably warp-uniform, so the role branches are uniform control flow
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
   const int nm = p.n_mtiles;
   const int n_my = (p.n_vtiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
@@ -392,7 +399,7 @@ vocab_ce_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmX,
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
   const uint32_t T_S = tmem_base, T_DW = tmem_base + 256;
 
   if (warp == WARP_TMA) {
@@ -417,66 +424,66 @@ vocab_ce_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmX,
       }
     }
   } else if (warp == WARP_MMA) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      const uint32_t id_s = umma_idesc_bf16(VB_N, VB_M, 1, 0);  // S^T = W^T (MN-major) X^T (K-major)
-      const uint32_t id_dw = umma_idesc_bf16(VB_N, h, 0, 1);    // dW^T = dZ^T (TMEM) X (MN-major)
-      const uint32_t aW = smem_u32(sW);
-      auto s_ready = [&](long it) -> bool {
-        return mbar_test(&x_full[it % XBUF], (uint32_t)((it / XBUF) & 1)) &&
-               mbar_test(&s_empty[it & 1], (uint32_t)((it >> 1) & 1) ^ 1);
-      };
-      auto issue_s = [&](long it) {
-        const int xb = (int)(it % XBUF), sb = (int)(it & 1);
-        tc_fence_after();
-        const uint32_t aX = smem_u32(sX + (size_t)xb * x_bytes);
-        for (int hb = 0; hb < HB; ++hb) {
+    // ------------------------------------------------------------------ MMA issuer (whole warp,
+    // uniform control flow; tcgen05 instructions predicated on an elected lane)
+    const uint32_t id_s = umma_idesc_bf16(VB_N, VB_M, 1, 0);  // S^T = W^T (MN-major) X^T (K-major)
+    const uint32_t id_dw = umma_idesc_bf16(VB_N, h, 0, 1);    // dW^T = dZ^T (TMEM) X (MN-major)
+    const uint32_t aX0 = smem_u32(sX);
+    const uint64_t dWa = umma_smem_desc(smem_u32(sW), HB * 8192, 1024);   // W^T, MN-major (A of S^T)
+    const uint64_t dXk = umma_smem_desc(aX0, 16, 1024);                   // X, K-major (B of S^T)
+    const uint64_t dXn = umma_smem_desc(aX0, VB_M * 128, 1024);           // X, MN-major (B of dW^T)
+    auto s_ready = [&](long it) -> bool {
+      return mbar_test_all(&x_full[it % XBUF], (uint32_t)((it / XBUF) & 1)) &&
+             mbar_test_all(&s_empty[it & 1], (uint32_t)((it >> 1) & 1) ^ 1);
+    };
+    auto issue_s = [&](long it) {
+      const int xb = (int)(it % XBUF), sb = (int)(it & 1);
+      tc_fence_after();
+      const uint32_t xo = (uint32_t)(xb * x_bytes) >> 4;
+      for (int hb = 0; hb < HB; ++hb) {
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
-            const uint64_t da = umma_smem_desc(aW + hb * 8192 + kk * 2048, HB * 8192, 1024);
-            const uint64_t db = umma_smem_desc(aX + hb * (VB_M * 128) + kk * 32, 16, 1024);
-            umma_bf16(T_S + sb * VB_M, da, db, id_s, (hb | kk) ? 1u : 0u);
-          }
-        }
-        umma_commit(&s_full[sb]);
-      };
-      // dW^T[128 v x h] (+)= dZ^T[128 v x 128 rows] X[128 rows x h]: 8 K steps of 16 rows
-      auto issue_dw = [&](long it, int i) {
-        const int xb = (int)(it % XBUF), zb = (int)(it & 1);
-        tc_fence_after();
-        const uint32_t aX = smem_u32(sX + (size_t)xb * x_bytes);
-        const uint32_t tZ = T_S + zb * VB_M;
-#pragma unroll
-        for (int k8 = 0; k8 < 8; ++k8) {
-          const uint64_t db = umma_smem_desc(aX + k8 * 2048, VB_M * 128, 1024);
-          umma_bf16_ts(T_DW, tZ + (k8 >> 1) * 32 + (k8 & 1) * 8, db, id_dw, (i | k8) ? 1u : 0u);
-        }
-        umma_commit(&x_empty[xb]);
-      };
-      long it0 = 0;
-      for (int vt = 0; vt < n_my; ++vt, it0 += nm) {
-        mbar_wait(w_full, vt & 1);
-        // two queues (see the forward kernel): S^T(is) needs its X tile and a free accumulator,
-        // dW(iu) needs dZ^T(iu); S^T(i+2) is only issued after dW(i)
-        int is = 0, iu = 0;
-        while (iu < nm) {
-          bool progressed = false;
-          if (iu < is && mbar_test(&dz_full[(it0 + iu) & 1], (uint32_t)(((it0 + iu) >> 1) & 1))) {
-            if (iu == 0) mbar_wait(dw_empty, (vt & 1) ^ 1);
-            issue_dw(it0 + iu, iu);
-            ++iu;
-            progressed = true;
-          }
-          if (is < nm && is <= iu + 1 && s_ready(it0 + is)) {
-            issue_s(it0 + is);
-            ++is;
-            progressed = true;
-          }
-          if (!progressed) __nanosleep(20);
-        }
-        umma_commit(dw_full);
-        umma_commit(w_empty);
+        for (int kk = 0; kk < 4; ++kk)
+          umma_bf16_el(T_S + sb * VB_M, dWa + (uint32_t)((hb * 8192 + kk * 2048) >> 4),
+                       dXk + (xo + (uint32_t)((hb * (VB_M * 128) + kk * 32) >> 4)), id_s,
+                       (hb | kk) ? 1u : 0u);
       }
+      umma_commit_el(&s_full[sb]);
+    };
+    // dW^T[128 v x h] (+)= dZ^T[128 v x 128 rows] X[128 rows x h]: 8 K steps of 16 rows
+    auto issue_dw = [&](long it, int i) {
+      const int xb = (int)(it % XBUF), zb = (int)(it & 1);
+      tc_fence_after();
+      const uint32_t xo = (uint32_t)(xb * x_bytes) >> 4;
+      const uint32_t tZ = T_S + zb * VB_M;
+#pragma unroll
+      for (int k8 = 0; k8 < 8; ++k8)
+        umma_bf16_ts_el(T_DW, tZ + (k8 >> 1) * 32 + (k8 & 1) * 8,
+                        dXn + (xo + (uint32_t)((k8 * 2048) >> 4)), id_dw, (i | k8) ? 1u : 0u);
+      umma_commit_el(&x_empty[xb]);
+    };
+    long it0 = 0;
+    for (int vt = 0; vt < n_my; ++vt, it0 += nm) {
+      mbar_wait_all(w_full, vt & 1);
+      // two queues (see the forward kernel): S^T(is) needs its X tile and a free accumulator,
+      // dW(iu) needs dZ^T(iu); S^T(i+2) is only issued after dW(i)
+      int is = 0, iu = 0;
+      while (iu < nm) {
+        bool progressed = false;
+        if (iu < is && mbar_test_all(&dz_full[(it0 + iu) & 1], (uint32_t)(((it0 + iu) >> 1) & 1))) {
+          if (iu == 0) mbar_wait_all(dw_empty, (vt & 1) ^ 1);
+          issue_dw(it0 + iu, iu);
+          ++iu;
+          progressed = true;
+        }
+        if (is < nm && is <= iu + 1 && s_ready(it0 + is)) {
+          issue_s(it0 + is);
+          ++is;
+          progressed = true;
+        }
+        if (!progressed) __nanosleep(20);
+      }
+      umma_commit_el(dw_full);
+      umma_commit_el(w_empty);
     }
   } else if (warp < NUM_EPI_WARPS) {
     // ------------------------------------------------------------------ epilogue (16 warps)
