@@ -243,6 +243,24 @@ __device__ __forceinline__ void umma_commit_el(uint64_t* bar) {
           smem_u32(bar))
       : "memory");
 }
+__device__ __forceinline__ void mbar_expect_tx_el(uint64_t* bar, uint32_t bytes) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}" ::"r"(smem_u32(bar)),
+      "r"(bytes)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_el(uint32_t smem_dst, const CUtensorMap* m,
+                                               uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];\n\t}" ::"r"(smem_dst),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
 // warp-uniform barrier polls (every lane polls; the vote makes the result provably uniform)
 __device__ __forceinline__ bool mbar_test_all(uint64_t* bar, uint32_t parity) {
   return __all_sync(0xffffffffu, mbar_test(bar, parity));

@@ -234,7 +234,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint8_t* sStage = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(sbias + BN) + 127) & ~static_cast<uintptr_t>(127));  // [4][4096]
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // provably warp-uniform
   const int lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * BM;
   const int n0 = blockIdx.y * BN;
@@ -262,28 +262,28 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   if (warp == 0) {
-    if (lane == 0) {
+    {  // whole warp, uniform control flow; TMA instructions predicated on an elected lane
       int stage = 0;
       uint32_t phase = 0;
       for (int kt = kt_begin; kt < kt_end; ++kt) {
-        mbar_wait(&empty_bar[stage], phase ^ 1);
+        mbar_wait_all(&empty_bar[stage], phase ^ 1);
         uint8_t* sA = tiles + (size_t)stage * stage_bytes;
         uint8_t* sB = sA + A_STAGE_BYTES;
-        mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
+        mbar_expect_tx_el(&full_bar[stage], (uint32_t)stage_bytes);
         if (!p.a_mn) {
-          tma_load_2d(sA, &tmA, &full_bar[stage], kt * BK, m0);
+          tma_load_2d_el(smem_u32(sA), &tmA, &full_bar[stage], kt * BK, m0);
         } else {
           for (int h = 0; h < BM / 64; ++h)
-            tma_load_2d(sA + h * (64 * BK * 2), &tmA, &full_bar[stage], m0 + h * 64, kt * BK);
+            tma_load_2d_el(smem_u32(sA + h * (64 * BK * 2)), &tmA, &full_bar[stage], m0 + h * 64, kt * BK);
         }
         if (!p.b_mn) {
-          tma_load_2d(sB, &tmB, &full_bar[stage], kt * BK, n0);
+          tma_load_2d_el(smem_u32(sB), &tmB, &full_bar[stage], kt * BK, n0);
         } else {
           for (int h = 0; h < BN / 64; ++h)
-            tma_load_2d(sB + h * (64 * BK * 2), &tmB, &full_bar[stage], n0 + h * 64, kt * BK);
+            tma_load_2d_el(smem_u32(sB + h * (64 * BK * 2)), &tmB, &full_bar[stage], n0 + h * 64, kt * BK);
         }
         if (++stage == p.stages) {
           stage = 0;
@@ -292,7 +292,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {  // the WHOLE warp issues, in uniform control flow (see umma_bf16_el in common.cuh)
       const uint32_t idesc = umma_idesc_bf16(BM, BN, p.a_mn, p.b_mn);
       // K-major: 8-row groups 1024 B apart; one UMMA_K (16 bf16) = 32 B along the row.
       // MN-major: 8 K-rows per 1024-B group, 64-wide M/N blocks one full box (64 x BK) apart;
@@ -304,7 +304,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0;
       for (int kt = kt_begin; kt < kt_end; ++kt) {
-        mbar_wait(&full_bar[stage], phase);
+        mbar_wait_all(&full_bar[stage], phase);
         tc_fence_after();
         const uint32_t sA = smem_u32(tiles + (size_t)stage * stage_bytes);
         const uint32_t sB = sA + A_STAGE_BYTES;
@@ -312,15 +312,15 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int k = 0; k < BK / 16; ++k) {
           const uint64_t da = umma_smem_desc(sA + k * a_kstep, a_lbo, a_sbo);
           const uint64_t db = umma_smem_desc(sB + k * b_kstep, b_lbo, b_sbo);
-          umma_bf16(tmem_base, da, db, idesc, (kt > kt_begin || k > 0) ? 1u : 0u);
+          umma_bf16_el(tmem_base, da, db, idesc, (kt > kt_begin || k > 0) ? 1u : 0u);
         }
-        umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+        umma_commit_el(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
         if (++stage == p.stages) {
           stage = 0;
           phase ^= 1;
         }
       }
-      umma_commit(tmem_full_bar);
+      umma_commit_el(tmem_full_bar);
     }
   } else {
     // ---- epilogue: warp w may only touch TMEM lanes [32*(w%4), 32*(w%4)+32)
@@ -400,7 +400,7 @@ gemm_umma_tiles_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   uint8_t* sStage = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(sbias + 2 * BN) + 127) & ~static_cast<uintptr_t>(127));  // [8][4096]
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // provably warp-uniform
   const int lane = threadIdx.x & 31;
   uint32_t tmem_cols = 32;
   while ((int)tmem_cols < 2 * BN) tmem_cols <<= 1;
@@ -426,30 +426,30 @@ gemm_umma_tiles_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   if (warp == 0) {
-    if (lane == 0) {
+    {  // whole warp, uniform control flow; TMA instructions predicated on an elected lane
       int stage = 0;
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const TileCoord c = tile_coord(p, t, n_m, n_n);
         for (int kt = c.kt_begin; kt < c.kt_end; ++kt) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_wait_all(&empty_bar[stage], phase ^ 1);
           uint8_t* sA = tiles + (size_t)stage * stage_bytes;
           uint8_t* sB = sA + A_STAGE_BYTES;
-          mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
+          mbar_expect_tx_el(&full_bar[stage], (uint32_t)stage_bytes);
           if (!p.a_mn) {
-            tma_load_2d(sA, &tmA, &full_bar[stage], kt * BK, c.m0);
+            tma_load_2d_el(smem_u32(sA), &tmA, &full_bar[stage], kt * BK, c.m0);
           } else {
             for (int h = 0; h < BM / 64; ++h)
-              tma_load_2d(sA + h * (64 * BK * 2), &tmA, &full_bar[stage], c.m0 + h * 64, kt * BK);
+              tma_load_2d_el(smem_u32(sA + h * (64 * BK * 2)), &tmA, &full_bar[stage], c.m0 + h * 64, kt * BK);
           }
           if (!p.b_mn) {
-            tma_load_2d(sB, &tmB, &full_bar[stage], kt * BK, c.n0);
+            tma_load_2d_el(smem_u32(sB), &tmB, &full_bar[stage], kt * BK, c.n0);
           } else {
             for (int h = 0; h < BN / 64; ++h)
-              tma_load_2d(sB + h * (64 * BK * 2), &tmB, &full_bar[stage], c.n0 + h * 64, kt * BK);
+              tma_load_2d_el(smem_u32(sB + h * (64 * BK * 2)), &tmB, &full_bar[stage], c.n0 + h * 64, kt * BK);
           }
           if (++stage == p.stages) {
             stage = 0;
@@ -459,7 +459,7 @@ gemm_umma_tiles_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {  // the WHOLE warp issues, in uniform control flow (see umma_bf16_el in common.cuh)
       const uint32_t idesc = umma_idesc_bf16(BM, BN, p.a_mn, p.b_mn);
       const uint32_t a_lbo = p.a_mn ? 64 * BK * 2 : 16, a_sbo = 1024;
       const uint32_t b_lbo = p.b_mn ? 64 * BK * 2 : 16, b_sbo = 1024;
@@ -471,11 +471,11 @@ gemm_umma_tiles_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++iter) {
         const TileCoord c = tile_coord(p, t, n_m, n_n);
         const int acc = iter & 1;
-        mbar_wait(&acc_empty[acc], (uint32_t)((iter >> 1) & 1) ^ 1);
+        mbar_wait_all(&acc_empty[acc], (uint32_t)((iter >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
         for (int kt = c.kt_begin; kt < c.kt_end; ++kt) {
-          mbar_wait(&full_bar[stage], phase);
+          mbar_wait_all(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sA = smem_u32(tiles + (size_t)stage * stage_bytes);
           const uint32_t sB = sA + A_STAGE_BYTES;
@@ -483,15 +483,15 @@ gemm_umma_tiles_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           for (int k = 0; k < BK / 16; ++k) {
             const uint64_t da = umma_smem_desc(sA + k * a_kstep, a_lbo, a_sbo);
             const uint64_t db = umma_smem_desc(sB + k * b_kstep, b_lbo, b_sbo);
-            umma_bf16(d_tmem, da, db, idesc, (kt > c.kt_begin || k > 0) ? 1u : 0u);
+            umma_bf16_el(d_tmem, da, db, idesc, (kt > c.kt_begin || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);
+          umma_commit_el(&empty_bar[stage]);
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&acc_full[acc]);
+        umma_commit_el(&acc_full[acc]);
       }
     }
   } else {
@@ -598,7 +598,8 @@ gemm_umma_persistent_kernel(const __grid_constant__ CUtensorMap tmA,
   uint64_t* t_empty = bars + 7;   // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
   float* sbias = reinterpret_cast<float*>(bars + 12);  // [BN]
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // provably warp-uniform
+  const int lane = threadIdx.x & 31;
   const int n_mtiles = (p.M + BM - 1) / BM;
   const int n_my = (n_mtiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   uint32_t tmem_cols = 32;
@@ -626,46 +627,46 @@ gemm_umma_persistent_kernel(const __grid_constant__ CUtensorMap tmA,
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   if (warp == WARP_TMA) {
-    if (lane == 0) {
-      mbar_expect_tx(b_full, (uint32_t)(KT * b_kt_bytes));
+    {  // whole warp, uniform control flow; TMA instructions predicated on an elected lane
+      mbar_expect_tx_el(b_full, (uint32_t)(KT * b_kt_bytes));
       for (int kt = 0; kt < KT; ++kt) {
         uint8_t* dst = sB + (size_t)kt * b_kt_bytes;
         if (!p.b_mn) {
-          tma_load_2d(dst, &tmB, b_full, kt * BK, 0);
+          tma_load_2d_el(smem_u32(dst), &tmB, b_full, kt * BK, 0);
         } else {
           for (int h = 0; h < BN / 64; ++h)
-            tma_load_2d(dst + h * (64 * BK * 2), &tmB, b_full, h * 64, kt * BK);
+            tma_load_2d_el(smem_u32(dst + h * (64 * BK * 2)), &tmB, b_full, h * 64, kt * BK);
         }
       }
       for (int i = 0; i < n_my; ++i) {
         const int st = i & 1;
         const int m0 = ((int)blockIdx.x + i * (int)gridDim.x) * BM;
-        mbar_wait(&a_empty[st], ((i >> 1) & 1) ^ 1);
-        mbar_expect_tx(&a_full[st], (uint32_t)a_stage_bytes);
+        mbar_wait_all(&a_empty[st], ((i >> 1) & 1) ^ 1);
+        mbar_expect_tx_el(&a_full[st], (uint32_t)a_stage_bytes);
         for (int kt = 0; kt < KT; ++kt) {
           uint8_t* dst = sA + (size_t)st * a_stage_bytes + (size_t)kt * A_STAGE_BYTES;
           if (!p.a_mn) {
-            tma_load_2d(dst, &tmA, &a_full[st], kt * BK, m0);
+            tma_load_2d_el(smem_u32(dst), &tmA, &a_full[st], kt * BK, m0);
           } else {
             for (int h = 0; h < BM / 64; ++h)
-              tma_load_2d(dst + h * (64 * BK * 2), &tmA, &a_full[st], m0 + h * 64, kt * BK);
+              tma_load_2d_el(smem_u32(dst + h * (64 * BK * 2)), &tmA, &a_full[st], m0 + h * 64, kt * BK);
           }
         }
       }
     }
   } else if (warp == WARP_MMA) {
-    if (lane == 0) {
+    {  // the WHOLE warp issues, in uniform control flow (see umma_bf16_el in common.cuh)
       const uint32_t idesc = umma_idesc_bf16(BM, BN, p.a_mn, p.b_mn);
       const uint32_t a_lbo = p.a_mn ? 64 * BK * 2 : 16, b_lbo = p.b_mn ? 64 * BK * 2 : 16;
       const uint32_t a_kstep = p.a_mn ? 2048 : 32, b_kstep = p.b_mn ? 2048 : 32;
-      mbar_wait(b_full, 0);
+      mbar_wait_all(b_full, 0);
       for (int i = 0; i < n_my; ++i) {
         const int st = i & 1;
-        mbar_wait(&a_full[st], (i >> 1) & 1);
-        mbar_wait(&t_empty[st], ((i >> 1) & 1) ^ 1);
+        mbar_wait_all(&a_full[st], (i >> 1) & 1);
+        mbar_wait_all(&t_empty[st], ((i >> 1) & 1) ^ 1);
         tc_fence_after();
         for (int kt = 0; kt < KT; ++kt) {
           const uint32_t aA = smem_u32(sA + (size_t)st * a_stage_bytes + (size_t)kt * A_STAGE_BYTES);
@@ -674,11 +675,11 @@ gemm_umma_persistent_kernel(const __grid_constant__ CUtensorMap tmA,
           for (int k = 0; k < BK / 16; ++k) {
             const uint64_t da = umma_smem_desc(aA + k * a_kstep, a_lbo, 1024);
             const uint64_t db = umma_smem_desc(aB + k * b_kstep, b_lbo, 1024);
-            umma_bf16(tmem_base + st * BN, da, db, idesc, (kt | k) ? 1u : 0u);
+            umma_bf16_el(tmem_base + st * BN, da, db, idesc, (kt | k) ? 1u : 0u);
           }
         }
-        umma_commit(&a_empty[st]);
-        umma_commit(&t_full[st]);
+        umma_commit_el(&a_empty[st]);
+        umma_commit_el(&t_full[st]);
       }
     }
   } else {

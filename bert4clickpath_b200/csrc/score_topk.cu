@@ -59,7 +59,8 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_empty + 2);
   constexpr int WARP_TMA = 4, WARP_MMA = 5;
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // provably warp-uniform
+  const int lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * ST_M;
   const int chunk = blockIdx.y;
   const int t_begin = chunk * p.tiles_per_chunk;
@@ -88,32 +89,32 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   if (warp == WARP_TMA) {
-    if (lane == 0) {
-      mbar_expect_tx(x_full, (uint32_t)x_bytes);
-      for (int hb = 0; hb < HB; ++hb) tma_load_2d(sX + hb * (ST_M * 128), &tmX, x_full, hb * 64, m0);
+    {  // whole warp, uniform control flow; TMA instructions predicated on an elected lane
+      mbar_expect_tx_el(x_full, (uint32_t)x_bytes);
+      for (int hb = 0; hb < HB; ++hb) tma_load_2d_el(smem_u32(sX + hb * (ST_M * 128)), &tmX, x_full, hb * 64, m0);
       for (int t = 0; t < ntiles; ++t) {
         const int st = t % ST_STAGES;
-        mbar_wait(&w_empty[st], ((t / ST_STAGES) & 1) ^ 1);
-        mbar_expect_tx(&w_full[st], (uint32_t)w_bytes);
+        mbar_wait_all(&w_empty[st], ((t / ST_STAGES) & 1) ^ 1);
+        mbar_expect_tx_el(&w_full[st], (uint32_t)w_bytes);
         const int v0 = (t_begin + t) * ST_N;
         uint8_t* dst = sW + (size_t)st * w_bytes;
         for (int vb = 0; vb < 2; ++vb)
           for (int hb = 0; hb < HB; ++hb)
-            tma_load_2d(dst + (vb * HB + hb) * 8192, &tmW, &w_full[st], v0 + vb * 64, hb * 64);
+            tma_load_2d_el(smem_u32(dst + (vb * HB + hb) * 8192), &tmW, &w_full[st], v0 + vb * 64, hb * 64);
       }
     }
   } else if (warp == WARP_MMA) {
-    if (lane == 0) {
+    {  // the WHOLE warp issues, in uniform control flow (see umma_bf16_el in common.cuh)
       const uint32_t idesc = umma_idesc_bf16(ST_M, ST_N, 0, 1);
       const uint32_t aX = smem_u32(sX);
-      mbar_wait(x_full, 0);
+      mbar_wait_all(x_full, 0);
       for (int t = 0; t < ntiles; ++t) {
         const int st = t % ST_STAGES, buf = t & 1;
-        mbar_wait(&w_full[st], (t / ST_STAGES) & 1);
-        mbar_wait(&s_empty[buf], ((t >> 1) & 1) ^ 1);
+        mbar_wait_all(&w_full[st], (t / ST_STAGES) & 1);
+        mbar_wait_all(&s_empty[buf], ((t >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t aW = smem_u32(sW + (size_t)st * w_bytes);
         for (int hb = 0; hb < HB; ++hb) {
@@ -121,11 +122,11 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           for (int kk = 0; kk < 4; ++kk) {
             const uint64_t da = umma_smem_desc(aX + hb * (ST_M * 128) + kk * 32, 16, 1024);
             const uint64_t db = umma_smem_desc(aW + hb * 8192 + kk * 2048, HB * 8192, 1024);
-            umma_bf16(tmem_base + buf * ST_N, da, db, idesc, (hb | kk) ? 1u : 0u);
+            umma_bf16_el(tmem_base + buf * ST_N, da, db, idesc, (hb | kk) ? 1u : 0u);
           }
         }
-        umma_commit(&w_empty[st]);
-        umma_commit(&s_full[buf]);
+        umma_commit_el(&w_empty[st]);
+        umma_commit_el(&s_full[buf]);
       }
     }
   } else {

@@ -102,20 +102,20 @@ vocab_ce_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmX,
   const uint32_t T_U = tmem_base + 256;
 
   if (warp == WARP_TMA) {
-    if (lane == 0) {
-      mbar_expect_tx(x_full, (uint32_t)x_bytes);
-      for (int hb = 0; hb < HB; ++hb)
-        tma_load_2d(sX + hb * (VB_M * 128), &tmX, x_full, hb * 64, m0);
-      for (int t = 0; t < ntiles; ++t) {
-        const int st = t % NST;
-        mbar_wait(&w_empty[st], ((t / NST) & 1) ^ 1);
-        mbar_expect_tx(&w_full[st], (uint32_t)w_bytes);
-        const int v0 = (t_begin + t) * VB_N;
-        uint8_t* dst = sW + (size_t)st * w_bytes;
-        for (int vb = 0; vb < 2; ++vb)
-          for (int hb = 0; hb < HB; ++hb)
-            tma_load_2d(dst + (vb * HB + hb) * 8192, &tmW, &w_full[st], v0 + vb * 64, hb * 64);
-      }
+    // whole warp, uniform control flow; the TMA instructions are predicated on an elected lane
+    const uint32_t aX = smem_u32(sX), aW0 = smem_u32(sW);
+    mbar_expect_tx_el(x_full, (uint32_t)x_bytes);
+    for (int hb = 0; hb < HB; ++hb)
+      tma_load_2d_el(aX + hb * (VB_M * 128), &tmX, x_full, hb * 64, m0);
+    for (int t = 0; t < ntiles; ++t) {
+      const int st = t % NST;
+      mbar_wait_all(&w_empty[st], ((t / NST) & 1) ^ 1);
+      mbar_expect_tx_el(&w_full[st], (uint32_t)w_bytes);
+      const int v0 = (t_begin + t) * VB_N;
+      const uint32_t dst = aW0 + (uint32_t)(st * w_bytes);
+      for (int vb = 0; vb < 2; ++vb)
+        for (int hb = 0; hb < HB; ++hb)
+          tma_load_2d_el(dst + (vb * HB + hb) * 8192, &tmW, &w_full[st], v0 + vb * 64, hb * 64);
     }
   } else if (warp == WARP_MMA) {
     // The WHOLE warp runs this loop in uniform control flow; only the tcgen05 instructions are
@@ -403,24 +403,24 @@ vocab_ce_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmX,
   const uint32_t T_S = tmem_base, T_DW = tmem_base + 256;
 
   if (warp == WARP_TMA) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      long it = 0;
-      for (int vt = 0; vt < n_my; ++vt) {
-        const int v0 = ((int)blockIdx.x + vt * (int)gridDim.x) * VB_N;
-        mbar_wait(w_empty, (vt & 1) ^ 1);
-        mbar_expect_tx(w_full, (uint32_t)w_bytes);
-        for (int vb = 0; vb < 2; ++vb)
-          for (int hb = 0; hb < HB; ++hb)
-            tma_load_2d(sW + (vb * HB + hb) * 8192, &tmW, w_full, v0 + vb * 64, hb * 64);
-        for (int i = 0; i < nm; ++i, ++it) {
-          const int xb = (int)(it % XBUF);
-          mbar_wait(&x_empty[xb], (uint32_t)((it / XBUF) & 1) ^ 1);
-          mbar_expect_tx(&x_full[xb], (uint32_t)x_bytes);
-          for (int hb = 0; hb < HB; ++hb)
-            tma_load_2d(sX + (size_t)xb * x_bytes + hb * (VB_M * 128), &tmX, &x_full[xb], hb * 64,
-                        i * VB_M);
-        }
+    // ------------------------------------------------------------------ TMA producer (whole
+    // warp, uniform control flow; TMA instructions predicated on an elected lane)
+    const uint32_t aW = smem_u32(sW), aX0 = smem_u32(sX);
+    long it = 0;
+    for (int vt = 0; vt < n_my; ++vt) {
+      const int v0 = ((int)blockIdx.x + vt * (int)gridDim.x) * VB_N;
+      mbar_wait_all(w_empty, (vt & 1) ^ 1);
+      mbar_expect_tx_el(w_full, (uint32_t)w_bytes);
+      for (int vb = 0; vb < 2; ++vb)
+        for (int hb = 0; hb < HB; ++hb)
+          tma_load_2d_el(aW + (vb * HB + hb) * 8192, &tmW, w_full, v0 + vb * 64, hb * 64);
+      for (int i = 0; i < nm; ++i, ++it) {
+        const int xb = (int)(it % XBUF);
+        mbar_wait_all(&x_empty[xb], (uint32_t)((it / XBUF) & 1) ^ 1);
+        mbar_expect_tx_el(&x_full[xb], (uint32_t)x_bytes);
+        for (int hb = 0; hb < HB; ++hb)
+          tma_load_2d_el(aX0 + (uint32_t)(xb * x_bytes) + hb * (VB_M * 128), &tmX, &x_full[xb],
+                         hb * 64, i * VB_M);
       }
     }
   } else if (warp == WARP_MMA) {
