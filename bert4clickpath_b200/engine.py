@@ -398,8 +398,9 @@ class VocabOutputEngine:
 
     @property
     def fused(self):
-        """The tcgen05 fused projection + CE kernels cover h = 128 (forward and backward)."""
-        return self.h == 128 and not self.force_materialized
+        """The tcgen05 fused projection + CE kernels cover h = 128 and h = 256 (forward and
+        backward; csrc/vocab_ce_ts.cu); other head widths take the materialised path."""
+        return self.h in (128, 256) and not self.force_materialized
 
     force_materialized = False
 
@@ -506,8 +507,8 @@ class VocabParallelOutputEngine(VocabOutputEngine):
         self.group = group
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         self.store, self.prefix, self.h, self.V_total = store, prefix, int(in_dim), int(vocab)
-        if self.h != 128:
-            raise ValueError("vocabulary-parallel output layer needs a 128-wide head (fused kernels)")
+        if self.h not in (128, 256):
+            raise ValueError("vocabulary-parallel output layer needs a 128- or 256-wide head (fused kernels)")
         # contiguous shards whose boundaries are multiples of 8 (bf16 leading-dimension rule)
         per = ld8((self.V_total + self.world - 1) // self.world)
         self.v_begin = min(self.rank * per, self.V_total)

@@ -1,0 +1,84 @@
+"""HBM-roofline check of the memory-bound kernels: embedding gather, its sorted
+scatter-add backward, top-k over materialised scores, Adam, residual+LayerNorm.
+Each iteration is timed on its own with CUDA events after an L2 flush (a 512 MB buffer is
+rewritten); achieved = ALGORITHMIC bytes / median time, against MEASURED_PEAKS.json hbm_gbs.
+Prints one JSON line per kernel/shape."""
+import json, os, sys
+import numpy as np
+import torch
+sys.path.insert(0, ".")
+from bert4clickpath_b200 import ops  # noqa: E402
+
+PEAK = json.load(open("MEASURED_PEAKS.json"))["hbm_gbs"] if os.path.exists("MEASURED_PEAKS.json") else 6650.0
+flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
+
+
+def timed(fn, iters=7):
+    for _ in range(2):
+        fn()
+    ts = []
+    for _ in range(iters):
+        flush.zero_()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return float(np.median(ts))
+
+
+def report(name, shape, nbytes, ms, **extra):
+    gbs = nbytes / (ms * 1e-3) / 1e9
+    print(json.dumps({"kernel": name, "shape": shape, "algorithmic_bytes": int(nbytes), "ms": round(ms, 4),
+                      "achieved_GBps": round(gbs, 1), "peak_GBps": PEAK, "frac": round(gbs / PEAK, 3), **extra}),
+          flush=True)
+
+
+def zipf_ids(n, V, s, g):
+    p = 1.0 / np.arange(1, V + 1) ** s
+    p /= p.sum()
+    return torch.from_numpy(g.choice(V, size=n, p=p).astype(np.int32) + 10).cuda()
+
+
+g = np.random.default_rng(0)
+for name, B, S, V, d in (("C1", 16384, 52, 54293, 64), ("C4", 1024, 202, 1_000_000, 256)):
+    rows = V + 11
+    table = (torch.rand(rows, d, device="cuda") - 0.5) * 0.1
+    pe = torch.randn(S, d, device="cuda")
+    ids = zipf_ids(B * S, V, 0.8, g)
+    out = torch.empty(B * S, d, device="cuda")
+    ms = timed(lambda: ops.embed_fwd([ids], [table], pe, B, S, out_f32=out))
+    report("embed_fwd_kernel", f"{name}: B={B} S={S} d={d} V={V}", B * S * (8 * d + 4), ms)
+    dout = torch.randn(B * S, d, device="cuda")
+    tg = torch.empty(rows, d, device="cuda")
+    nu = torch.zeros(1, dtype=torch.int32, device="cuda")
+    uq = torch.empty(B * S, dtype=torch.int32, device="cuda")
+    ms = timed(lambda: ops.embed_bwd(dout, d, 0, d, ids, rows, tg, uniq_ids=uq, n_unique=nu))
+    U = int(nu.item())
+    alg = B * S * d * 4 + B * S * 4 + U * d * 4 + U * 4
+    report("embed_bwd (radix sort + segment sums + table zero-fill)", f"{name}: N={B*S} U={U} d={d} rows={rows}",
+           alg, ms, bytes_incl_dense_zero_fill=int(alg + rows * d * 4),
+           frac_incl_zero_fill=round((alg + rows * d * 4) / (ms * 1e-3) / 1e9 / PEAK, 3))
+    del table, out, dout, tg
+
+for B, V, k in ((1024, 1_000_000, 100), (8192, 54293, 100), (1024, 1_000_000, 10)):
+    sc = torch.randn(B, ops.ld8(V), device="cuda")
+    ids_o = torch.empty(B, k, dtype=torch.int32, device="cuda")
+    ms = timed(lambda: ops.topk_rows(sc, V, k, out_ids=ids_o))
+    report("topk_rows_kernel", f"B={B} V={V} k={k}", B * V * 4 + B * k * 8, ms)
+    del sc
+
+n = 256 * 1_000_000 // 4
+theta, grad, m, v = (torch.randn(n, device="cuda") for _ in range(4))
+v.abs_()
+step = torch.zeros(1, dtype=torch.int32, device="cuda")
+ms = timed(lambda: ops.adam_step(theta, grad, m, v, lr=1e-3, step_dev=step))
+report("adam_kernel", f"n={n} (no bf16 shadow)", n * 28, ms)
+del theta, grad, m, v
+
+for rows_, d in ((16384 * 52, 64), (1024 * 202, 256)):
+    x, r = torch.randn(rows_, d, device="cuda"), torch.randn(rows_, d, device="cuda")
+    gam, bet = torch.ones(d, device="cuda"), torch.zeros(d, device="cuda")
+    y, yb = torch.empty(rows_, d, device="cuda"), torch.empty(rows_, d, device="cuda", dtype=torch.bfloat16)
+    ms = timed(lambda: ops.residual_ln_fwd(x, r, gam, bet, y, yb))
+    report("residual_ln_fwd_kernel", f"rows={rows_} d={d}", rows_ * d * 14, ms)

@@ -170,7 +170,7 @@ def test_three_adam_steps_track_oracle(cuda_lib):
     dict(V=300, d=32, L=2, H=2, dff=100, hd=[64, 32], B=16, max_len=20, lengths="beauty", mp=0.4),
     dict(V=1000, d=64, L=2, H=2, dff=100, hd=[128, 64], B=64, max_len=50, lengths="dense", mp=0.15),
     dict(V=500, d=128, L=1, H=4, dff=100, hd=[], B=32, max_len=30, lengths="beauty", mp=0.4),
-    # C4-shaped: d_model 256, 4 heads of depth 64, head [] -> V (h = 256: materialised vocabulary path)
+    # C4-shaped: d_model 256, 4 heads of depth 64, head [] -> V (h = 256: fused TS-form vocabulary path)
     dict(V=2000, d=256, L=2, H=4, dff=100, hd=[], B=8, max_len=40, lengths="beauty", mp=0.15),
 ])
 def test_kernels_match_bf16_emulation_on_c1_like_shapes(cuda_lib, cfg):
@@ -302,10 +302,11 @@ def test_multivariable_segment_head_forward_matches_oracle(cuda_lib, segment):
     assert abs(loss - want_loss) < 1e-4 * abs(want_loss)
 
 
-def test_h256_vocabulary_stage_in_bounded_row_ranges(cuda_lib):
-    """C4 / C5 head width (h = 256, head [] -> V): the vocabulary stage materialises logits for a
-    bounded row range at a time.  Forcing 128-row ranges must reproduce the single-range loss,
-    gradients (dW accumulated over ranges) and top-k ids."""
+def test_h256_vocabulary_stage_fused_and_in_bounded_row_ranges(cuda_lib):
+    """C4 / C5 head width (h = 256, head [] -> V).  Default: the fused TS-form kernels (logits never
+    in HBM).  The materialised fallback (`force_materialized`) holds logits for a bounded row range
+    at a time: forcing 128-row ranges must reproduce the single-range loss, gradients (dW
+    accumulated over ranges) and top-k ids, and the fused path must agree with both."""
     import bert4clickpath_b200 as bc
     from bert4clickpath_b200.synthetic import make_cloze_batch
     V, d = 3001, 256
@@ -325,16 +326,26 @@ def test_h256_vocabulary_stage_in_bounded_row_ranges(cuda_lib):
     ev = make_cloze_batch(np.random.default_rng(2), 300, V, max_len=50, mode="eval")
     ev_ids = torch.from_numpy(ev["ids"]).cuda().view(-1)
     res = []
-    for limit in (None, 1):
+    for limit in ("fused", None, 1):
         m = build()
-        assert not m.head.vocab.fused
-        if limit is not None:
+        assert m.head.vocab.fused
+        if limit != "fused":
+            m.head.vocab.force_materialized = True
+            assert not m.head.vocab.fused
+        if limit == 1:
             m.head.vocab.MATERIALIZE_LIMIT_BYTES = limit      # -> 128-row ranges
             assert len(m.head.vocab._row_chunks(batch["n_masked"])) == -(-batch["n_masked"] // 128) > 2
         st = m.cloze_forward_backward([ids], labels, B, S, n_masked=batch["n_masked"],
                                       training=False).cpu().numpy()
         top, _ = m.topk_ids([ev_ids], 300, ev["ids"].shape[1], 10, n_masked=300)
         res.append((st, m.store.get_grads(), top.cpu().numpy().copy()))
+    (sf, gf, _), res = res[0], res[1:]
+    np.testing.assert_allclose(sf, res[0][0], rtol=2e-5)
+    floor_f = 1e-3 * max(np.linalg.norm(v) for v in res[0][1].values())
+    for k in gf:
+        g0k = res[0][1][k].astype(np.float64)
+        e = np.linalg.norm(gf[k].astype(np.float64) - g0k) / max(np.linalg.norm(g0k), floor_f)
+        assert e < 1e-2, ("fused vs materialised", k, e)  # bf16 P' / dZ tiles vs bf16 dZ matrix
     (s0, g0, t0), (s1, g1, t1) = res
     np.testing.assert_allclose(s1, s0, rtol=1e-6)
     assert (t0 == t1).all()
