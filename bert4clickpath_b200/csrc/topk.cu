@@ -6,6 +6,14 @@
 // and the k smallest keys are found by an MSB-first radix select with 11-bit digits that stops
 // as soon as the undecided bucket fits in shared memory; survivors are bitonic-sorted.  The id is
 // part of the key, so any number of exact ties is resolved exactly.
+//
+// Long rows (V >= 16384, the 1M-item catalogue of SURVEY.md C5) take a SINGLE streaming pass
+// instead (topk_stream_kernel): 128-bit loads, a running threshold tau = the k-th best key seen so
+// far, and a shared-memory candidate buffer that is compacted (rank by counting, keep k) whenever
+// it holds more than k + 160 keys.  A random row admits ~k ln(V/256) candidates in total, so the
+// row is read exactly once at HBM speed.  A row that would overflow the buffer
+// (adversarially ordered scores) is flagged and redone by the radix-select kernel - the result is
+// exact either way.
 #include <algorithm>
 
 #include "common.cuh"
@@ -19,6 +27,7 @@ static constexpr int TK_BINS = 1 << TK_BITS;
 static constexpr int TK_MAXK = 256;
 static constexpr int TK_CAP = 2048;               // undecided bucket must shrink below this
 static constexpr int TK_SORT = 4096;              // >= TK_CAP + TK_MAXK, power of two
+static constexpr int TK_REDO = -2;                // out_ids[row][0] marker: redo with radix select
 
 __device__ __forceinline__ uint32_t ordered_desc(float f) {
   if (f == 0.f) f = 0.f;  // -0 == +0 for the comparison TensorFlow does
@@ -35,7 +44,9 @@ __device__ __forceinline__ float from_ordered_desc(uint32_t d) {
 __global__ void __launch_bounds__(TK_THREADS)
 topk_rows_kernel(const float* __restrict__ scores, const int32_t* __restrict__ cand_ids, long ld,
                  int V, int k, int idbits, int32_t* __restrict__ out_ids,
-                 float* __restrict__ out_scores, long ld_out) {
+                 float* __restrict__ out_scores, long ld_out, int only_flagged) {
+  // second launch after topk_stream_kernel: only rows it flagged (out_ids[row][0] == -2)
+  if (only_flagged && out_ids[(long)blockIdx.x * ld_out] != TK_REDO) return;
   __shared__ int hist[TK_BINS];
   __shared__ unsigned long long buf[TK_SORT];
   __shared__ int scan_tmp[40];
@@ -164,6 +175,160 @@ topk_rows_kernel(const float* __restrict__ scores, const int32_t* __restrict__ c
   }
 }
 
+// ------------------------------------------------------------------ single-pass streaming top-k
+static constexpr int ST_THREADS = 512;
+static constexpr int ST_UNROLL = 4;                              // float4 loads in flight per thread
+static constexpr int ST_BATCH = ST_THREADS * ST_UNROLL * 4;      // 8192 elements per full batch
+static constexpr int ST_CAP = 4096;                              // candidate keys (+ ST_CAP scratch)
+static constexpr int ST_SEED = 256;                              // elements that seed the threshold
+static constexpr int ST_SLACK = 160;                             // compact above k + ST_SLACK keys
+static constexpr int ST_RANK_MAX = 1024;                         // rank-by-counting up to this many
+static constexpr int ST_MIN_V = 16384;
+
+// ascending bitonic sort of n = 2^logn 64-bit keys in shared memory, whole block (shifts and
+// masks only).  Only used when a batch admits more than ST_RANK_MAX candidates.
+__device__ __forceinline__ void block_bitonic_sort(unsigned long long* buf, int logn) {
+  const int half = 1 << (logn - 1);
+  for (int ls = 1; ls <= logn; ++ls) {          // size = 2^ls
+    for (int lt = ls - 1; lt >= 0; --lt) {      // stride = 2^lt
+      const int stride = 1 << lt;
+      for (int i = threadIdx.x; i < half; i += blockDim.x) {
+        const int lo = ((i >> lt) << (lt + 1)) | (i & (stride - 1));
+        const int hi = lo | stride;
+        const bool asc = ((lo >> ls) & 1) == 0;
+        const unsigned long long a = buf[lo], c = buf[hi];
+        if ((a > c) == asc) {
+          buf[lo] = c;
+          buf[hi] = a;
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// Keep the min(c, k) smallest of the c keys in buf, sorted ascending in buf[0..); returns the new
+// threshold (the k-th smallest, or "accept everything" while fewer than k keys exist).
+// c <= ST_RANK_MAX: rank by counting - thread t owns keys t and t + 512 and counts the keys below
+// each (all lanes read the same key: a shared-memory broadcast); ~6 c instructions per thread,
+// against ~25 * 4 * log^2 instructions for a sort of the same buffer, which made the sorts
+// 45% of all instructions of the first version of this kernel.
+__device__ __forceinline__ unsigned long long st_compact(unsigned long long* buf, int c, int k,
+                                                         int* s_count) {
+  const int tid = threadIdx.x;
+  const int n = min(c, k);
+  if (c <= ST_RANK_MAX) {
+    unsigned long long* dst = buf + ST_CAP;
+    const unsigned long long my0 = tid < c ? buf[tid] : ~0ull;
+    const unsigned long long my1 = tid + ST_THREADS < c ? buf[tid + ST_THREADS] : ~0ull;
+    int r0 = 0, r1 = 0;
+    if (tid < c) {
+      if (c > ST_THREADS) {
+#pragma unroll 4
+        for (int i = 0; i < c; ++i) {
+          const unsigned long long K = buf[i];
+          r0 += K < my0 ? 1 : 0;
+          r1 += K < my1 ? 1 : 0;
+        }
+      } else {
+#pragma unroll 4
+        for (int i = 0; i < c; ++i) r0 += buf[i] < my0 ? 1 : 0;
+      }
+    }
+    __syncthreads();
+    if (tid < c && r0 < k) dst[r0] = my0;
+    if (tid + ST_THREADS < c && r1 < k) dst[r1] = my1;
+    __syncthreads();
+    for (int i = tid; i < n; i += ST_THREADS) buf[i] = dst[i];
+  } else {
+    int logn = 1;
+    while ((1 << logn) < c) ++logn;
+    for (int i = c + tid; i < (1 << logn); i += ST_THREADS) buf[i] = ~0ull;
+    __syncthreads();
+    block_bitonic_sort(buf, logn);
+  }
+  __syncthreads();
+  const unsigned long long tau = c >= k ? buf[k - 1] : ~0ull;
+  if (tid == 0) *s_count = n;
+  __syncthreads();
+  return tau;
+}
+
+__global__ void __launch_bounds__(ST_THREADS, 2)
+topk_stream_kernel(const float* __restrict__ scores, long ld, int V, int k, int idbits,
+                   int32_t* __restrict__ out_ids, float* __restrict__ out_scores, long ld_out) {
+  extern __shared__ __align__(16) unsigned long long st_buf[];  // [2 * ST_CAP]
+  __shared__ int s_count;
+  const long row = blockIdx.x;
+  const float* z = scores + row * ld;
+  const int tid = threadIdx.x;
+  // the first ST_SEED elements seed the buffer and the threshold
+  if (tid < ST_SEED)
+    st_buf[tid] = ((unsigned long long)ordered_desc(__ldg(z + tid)) << idbits) | (unsigned)tid;
+  __syncthreads();
+  unsigned long long tau = st_compact(st_buf, ST_SEED, k, &s_count);
+  // batches double from ST_SEED to ST_BATCH elements: while little has been seen the threshold is
+  // loose and a batch as large as everything seen so far admits about k candidates
+  auto load_batch = [&](int base, int lim, float (&x)[ST_UNROLL][4]) {
+#pragma unroll
+    for (int u = 0; u < ST_UNROLL; ++u) {
+      const int idx = base + (u * ST_THREADS + tid) * 4;
+      if (idx + 3 < lim) {
+        const float4 v4 = __ldg(reinterpret_cast<const float4*>(z + idx));
+        x[u][0] = v4.x; x[u][1] = v4.y; x[u][2] = v4.z; x[u][3] = v4.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) x[u][j] = idx + j < lim ? __ldg(z + idx + j) : -INFINITY;
+      }
+    }
+  };
+  float x[ST_UNROLL][4], xn[ST_UNROLL][4];
+  int base = ST_SEED, bsz = ST_SEED;
+  load_batch(base, min(V, base + bsz), x);
+  while (base < V) {
+    const int lim = min(V, base + bsz);
+    const int nbsz = min(ST_BATCH, bsz * 2);
+    if (lim < V) load_batch(lim, min(V, lim + nbsz), xn);   // in flight while x is filtered
+    // fast filter on the float value (x >= threshold score; -0 == +0 as in the key), exact
+    // 64-bit key comparison (ties -> lower id) only for the few that pass
+    const float tau_f = from_ordered_desc((uint32_t)(tau >> idbits));
+#pragma unroll
+    for (int u = 0; u < ST_UNROLL; ++u) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (x[u][j] >= tau_f) {
+          const int v = base + (u * ST_THREADS + tid) * 4 + j;
+          const unsigned long long K = ((unsigned long long)ordered_desc(x[u][j]) << idbits) | (unsigned)v;
+          if (K < tau && v < lim) {
+            const int slot = atomicAdd(&s_count, 1);
+            if (slot < ST_CAP) st_buf[slot] = K;
+          }
+        }
+      }
+    }
+    __syncthreads();
+    const int c = s_count;
+    if (c > ST_CAP) {  // would have dropped candidates: hand the row to the radix-select kernel
+      if (tid == 0) out_ids[row * ld_out] = TK_REDO;
+      return;
+    }
+    if (c > k + ST_SLACK) tau = st_compact(st_buf, c, k, &s_count);
+#pragma unroll
+    for (int u = 0; u < ST_UNROLL; ++u)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) x[u][j] = xn[u][j];
+    base = lim;
+    bsz = nbsz;
+  }
+  st_compact(st_buf, s_count, k, &s_count);   // sorted winners in st_buf[0..k)
+  const unsigned long long idmask = (1ull << idbits) - 1ull;
+  for (int r = tid; r < k; r += ST_THREADS) {
+    const unsigned long long K = st_buf[r];
+    out_ids[row * ld_out + r] = (int32_t)(K & idmask);
+    if (out_scores) out_scores[row * ld_out + r] = from_ordered_desc((uint32_t)(K >> idbits));
+  }
+}
+
 }  // namespace b4cp
 
 using namespace b4cp;
@@ -176,8 +341,20 @@ extern "C" int b4cp_topk_rows(const float* scores, long ld, long rows, int V, in
   if (rows == 0) return 0;
   int idbits = 1;
   while ((1L << idbits) < V) ++idbits;
+  if (V >= ST_MIN_V && ld % 4 == 0 && ((uintptr_t)scores & 15) == 0) {
+    const size_t smem = (size_t)2 * ST_CAP * sizeof(unsigned long long);
+    B4CP_CUDA(cudaFuncSetAttribute(topk_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)smem));
+    topk_stream_kernel<<<(unsigned)rows, ST_THREADS, smem, (cudaStream_t)stream>>>(
+        scores, ld, V, k, idbits, out_ids, out_scores, ld_out);
+    topk_rows_kernel<<<(unsigned)rows, TK_THREADS, 0, (cudaStream_t)stream>>>(
+        scores, nullptr, ld, V, k, idbits, out_ids, out_scores, ld_out, 1);
+    note_launches(2);
+    B4CP_LAUNCH_CHECK();
+    return 0;
+  }
   topk_rows_kernel<<<(unsigned)rows, TK_THREADS, 0, (cudaStream_t)stream>>>(
-      scores, nullptr, ld, V, k, idbits, out_ids, out_scores, ld_out);
+      scores, nullptr, ld, V, k, idbits, out_ids, out_scores, ld_out, 0);
   note_launches(1);
   B4CP_LAUNCH_CHECK();
   return 0;
@@ -195,7 +372,7 @@ extern "C" int b4cp_topk_candidates(const float* cand_scores, const int32_t* can
   int idbits = 1;
   while ((1L << idbits) < V) ++idbits;
   topk_rows_kernel<<<(unsigned)rows, TK_THREADS, 0, (cudaStream_t)stream>>>(
-      cand_scores, cand_ids, ld, n_cand, k, idbits, out_ids, out_scores, ld_out);
+      cand_scores, cand_ids, ld, n_cand, k, idbits, out_ids, out_scores, ld_out, 0);
   note_launches(1);
   B4CP_LAUNCH_CHECK();
   return 0;

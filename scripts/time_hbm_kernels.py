@@ -61,7 +61,7 @@ for name, B, S, V, d in (("C1", 16384, 52, 54293, 64), ("C4", 1024, 202, 1_000_0
            frac_incl_zero_fill=round((alg + rows * d * 4) / (ms * 1e-3) / 1e9 / PEAK, 3))
     del table, out, dout, tg
 
-for B, V, k in ((1024, 1_000_000, 100), (8192, 54293, 100), (1024, 1_000_000, 10)):
+for B, V, k in ((1184, 1_000_000, 100), (9472, 54293, 100), (1184, 1_000_000, 10)):  # whole waves of 2 CTAs x 148 SMs
     sc = torch.randn(B, ops.ld8(V), device="cuda")
     ids_o = torch.empty(B, k, dtype=torch.int32, device="cuda")
     ms = timed(lambda: ops.topk_rows(sc, V, k, out_ids=ids_o))

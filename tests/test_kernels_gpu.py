@@ -355,6 +355,30 @@ def test_topk_exact_with_ties(cuda_lib, V, k):
     np.testing.assert_array_equal(sc.cpu().numpy()[:, :kk], np.take_along_axis(s, want[:, :kk], 1))
 
 
+@pytest.mark.parametrize("V,k", [(54293, 100), (300001, 10), (16384, 256)])
+def test_topk_streaming_pass_and_its_radix_fallback(cuda_lib, V, k):
+    """Long rows take the single-pass streaming kernel (running threshold + candidate buffer);
+    rows whose order would overflow the buffer (ascending scores: every element beats the
+    threshold) are flagged and redone by the radix-select kernel.  Ids are exact either way."""
+    from bert4clickpath_b200 import ops
+    rng = np.random.default_rng(V + k)
+    s = rng.normal(size=(7, V)).astype(np.float32)
+    s[0] = np.arange(V, dtype=np.float32)              # ascending: overflow -> fallback
+    s[1] = -np.arange(V, dtype=np.float32)             # descending: nothing after the seed passes
+    s[2] = np.repeat(np.arange((V + 63) // 64, dtype=np.float32), 64)[:V]   # ascending plateaus of ties
+    s[3, rng.choice(V, 50, replace=False)] = np.inf
+    s[3, rng.choice(V, 50, replace=False)] = -np.inf
+    s[4, -k:] = 100.0                                  # the winners are the last k (ties)
+    s[5] = np.sort(s[5])                               # ascending random
+    sd = torch.full((7, ops.ld8(V)), float("nan"), device="cuda")   # padded rows: ld % 8 == 0
+    sd[:, :V] = dev(s)
+    ids, sc = ops.topk_rows(sd, V, k, out_scores=torch.empty((7, k), device="cuda"))
+    torch.cuda.synchronize()
+    want = O.top_k_ids(s, k)
+    assert ids.cpu().numpy().tolist() == want.tolist()
+    np.testing.assert_array_equal(sc.cpu().numpy(), np.take_along_axis(s, want, 1))
+
+
 def test_rank_metrics_kat(cuda_lib):
     from bert4clickpath_b200 import ops
     # examples/BERT4Rec/source/utils.py:262-272 known answer 0.81546488
