@@ -7,9 +7,10 @@
 // two TensorFlow ops.
 //
 // Backward (TF autodiff -> IndexedSlices -> UnsortedSegmentSum): deterministic.  Token ids are
-// stably radix-sorted (key = id, value = token index), each run of equal ids is one segment, and
-// segments are summed in token order by warps (long segments are cut into fixed chunks whose
-// partial sums are combined in chunk order), so results are bit-reproducible run to run.
+// stably radix-sorted (key = id, value = token index); the sorted list is cut into fixed 64-token
+// tiles, one warp per tile sums every run of equal ids in token order, and runs that cross tile
+// boundaries are finished from per-tile partial rows in tile order, so results are
+// bit-reproducible run to run.
 #include <algorithm>
 
 #include "common.cuh"
@@ -267,96 +268,6 @@ segment_starts_kernel(const int* __restrict__ flags, const int* __restrict__ fla
   if (i == 0) seg_start[*n_unique] = (int)n;
 }
 
-static constexpr int SEG_CHUNK = 64;  // tokens summed by one warp task
-
-__global__ void __launch_bounds__(256)
-segment_chunk_counts_kernel(const int* __restrict__ seg_start, const int* __restrict__ n_unique,
-                            int* __restrict__ chunks_per_seg, int* __restrict__ mchunks_per_seg,
-                            long cap) {
-  const long u = blockIdx.x * (long)blockDim.x + threadIdx.x;
-  if (u >= cap) return;
-  int c = 0;
-  if (u < *n_unique) {
-    const int len = seg_start[u + 1] - seg_start[u];
-    c = (len + SEG_CHUNK - 1) / SEG_CHUNK;
-  }
-  chunks_per_seg[u] = c;
-  mchunks_per_seg[u] = c > 1 ? c : 0;  // only multi-chunk segments need partial rows
-}
-
-// One warp per (segment, chunk) task.  Tasks are enumerated as chunk index c in
-// [0, total_chunks); the owning segment is found by binary search in the chunk-offset scan.
-__global__ void __launch_bounds__(256)
-segment_sum_kernel(const float* __restrict__ dout, int d_model, int off, int dim,
-                   const uint32_t* __restrict__ sorted_keys, const uint32_t* __restrict__ sorted_tok,
-                   const int* __restrict__ seg_start, const int* __restrict__ chunk_off,
-                   const int* __restrict__ mchunk_off, int rows,
-                   const int* __restrict__ n_unique, const int* __restrict__ total_chunks,
-                   float scale, float inv_keep, uint32_t thresh24, uint64_t seed, uint32_t site,
-                   float* __restrict__ table_grad, float* __restrict__ partial) {
-  seed = resolve_seed(seed);
-  const int warps_per_block = blockDim.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int U = *n_unique;
-  const int C = *total_chunks;
-  for (long task = (long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); task < C;
-       task += (long)gridDim.x * warps_per_block) {
-    // largest u with chunk_off[u] <= task
-    int lo = 0, hi = U - 1;
-    while (lo < hi) {
-      const int mid = (lo + hi + 1) >> 1;
-      if (chunk_off[mid] <= task) lo = mid; else hi = mid - 1;
-    }
-    const int u = lo;
-    const int c_in_seg = (int)task - chunk_off[u];
-    const int s0 = seg_start[u], s1 = seg_start[u + 1];
-    const int nchunks = (s1 - s0 + SEG_CHUNK - 1) / SEG_CHUNK;
-    const int b = s0 + c_in_seg * SEG_CHUNK;
-    const int e = min(s1, b + SEG_CHUNK);
-    const uint32_t id = sorted_keys[s0];
-    if (id >= (uint32_t)rows) continue;  // out-of-range id: no table row to update
-    const size_t prow = (size_t)(mchunk_off[u] + c_in_seg);
-    for (int c = lane; c < dim; c += 32) {
-      float acc = 0.f;
-      for (int i = b; i < e; ++i) {
-        const uint32_t tok = sorted_tok[i];
-        float g = __ldg(dout + (size_t)tok * d_model + off + c);
-        if (thresh24) {
-          const bool keep = dropout_keep(seed, site, (uint64_t)tok * d_model + off + c, thresh24);
-          g = keep ? __fmul_rn(g, inv_keep) : 0.f;
-        }
-        acc = __fadd_rn(acc, g);
-      }
-      if (nchunks == 1) table_grad[(size_t)id * dim + c] = __fmul_rn(acc, scale);
-      else partial[prow * dim + c] = acc;
-    }
-  }
-}
-
-__global__ void __launch_bounds__(256)
-segment_combine_kernel(int dim, const uint32_t* __restrict__ sorted_keys,
-                       const int* __restrict__ seg_start, const int* __restrict__ mchunk_off,
-                       int rows, const int* __restrict__ n_unique, float scale,
-                       const float* __restrict__ partial, float* __restrict__ table_grad) {
-  const int warps_per_block = blockDim.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int U = *n_unique;
-  for (long u = (long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); u < U;
-       u += (long)gridDim.x * warps_per_block) {
-    const int s0 = seg_start[u], s1 = seg_start[u + 1];
-    const int nchunks = (s1 - s0 + SEG_CHUNK - 1) / SEG_CHUNK;
-    if (nchunks <= 1) continue;
-    const uint32_t id = sorted_keys[s0];
-    if (id >= (uint32_t)rows) continue;
-    const int c0 = mchunk_off[u];
-    for (int c = lane; c < dim; c += 32) {
-      float acc = 0.f;
-      for (int k = 0; k < nchunks; ++k) acc = __fadd_rn(acc, partial[(size_t)(c0 + k) * dim + c]);
-      table_grad[(size_t)id * dim + c] = __fmul_rn(acc, scale);
-    }
-  }
-}
-
 __global__ void __launch_bounds__(256)
 export_unique_kernel(const uint32_t* __restrict__ sorted_keys, const int* __restrict__ seg_start,
                      const int* __restrict__ n_unique, int* __restrict__ uniq_ids, long cap) {
@@ -364,11 +275,210 @@ export_unique_kernel(const uint32_t* __restrict__ sorted_keys, const int* __rest
   if (u < cap && u < *n_unique) uniq_ids[u] = (int)sorted_keys[seg_start[u]];
 }
 
+// ---------------------------------------------------------------------------------------------
+// Tile-based segmented sum (default path).  The sorted token list is cut into fixed tiles of
+// SEG_TILE positions, one warp per tile - no search, uniform work, coalesced key/token reads.  The
+// warp walks its tile in order and keeps one running row (lane = columns lane, lane+32, ...):
+//   * a run of equal ids that begins and ends inside the tile is scaled and written to the table;
+//   * a run that continues from the previous tile (open left) or into the next (open right)
+//     leaves an UNSCALED partial row: slot 0 = the tile's first run, slot 1 = its last run.
+// segment_fixup_kernel then finishes every id whose tokens cross a tile boundary: the warp of the
+// tile where the id BEGINS adds the partials of the following tiles in tile order (= token
+// order), so the sum is bit-reproducible.  Ids spanning more than SEG_LONG tiles ([MASK], [CLS],
+// [SEP], [PAD]: O(batch) duplicates) are queued for segment_long_kernel, where 32 warps sum fixed
+// sub-ranges of the partial rows and the 32 results are added in order.
+static constexpr int SEG_TILE = 64;
+static constexpr int SEG_NV = 8;      // columns per lane: dim <= 256
+static constexpr int SEG_LONG = 16;   // tiles
+
+template <int NV>
+__global__ void __launch_bounds__(256)
+segment_tile_sum_kernel(const float* __restrict__ dout, int d_model, int off, int dim,
+                        const uint32_t* __restrict__ skeys, const uint32_t* __restrict__ stok,
+                        long n, int rows, float scale, float inv_keep, uint32_t thresh24,
+                        uint64_t seed, uint32_t site, float* __restrict__ table_grad,
+                        float* __restrict__ partial) {
+  seed = resolve_seed(seed);
+  const int lane = threadIdx.x & 31;
+  const long n_tiles = (n + SEG_TILE - 1) / SEG_TILE;
+  for (long w = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < n_tiles;
+       w += (long)gridDim.x * (blockDim.x >> 5)) {
+    const long b = w * SEG_TILE;
+    const int cnt = (int)min((long)SEG_TILE, n - b);
+    uint32_t k0 = 0xFFFFFFFFu, k1 = 0xFFFFFFFFu, t0 = 0, t1 = 0;
+    if (lane < cnt) { k0 = skeys[b + lane]; t0 = stok[b + lane]; }
+    if (lane + 32 < cnt) { k1 = skeys[b + 32 + lane]; t1 = stok[b + 32 + lane]; }
+    const uint32_t k_first = __shfl_sync(0xffffffffu, k0, 0);
+    const uint32_t k_last = cnt > 32 ? __shfl_sync(0xffffffffu, k1, cnt - 33)
+                                     : __shfl_sync(0xffffffffu, k0, cnt - 1);
+    const bool open_left = b > 0 && skeys[b - 1] == k_first;
+    const bool open_right = b + cnt < n && skeys[b + cnt] == k_last;
+    float acc[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) acc[v] = 0.f;
+    uint32_t run_key = k_first;
+    bool run_is_first = true;
+    auto flush = [&](bool is_last) {
+      const bool part = (run_is_first && open_left) || (is_last && open_right);
+      if (run_key < (uint32_t)rows) {
+        float* dst = part ? partial + (size_t)(2 * w + (run_is_first ? 0 : 1)) * dim
+                          : table_grad + (size_t)run_key * dim;
+        const float sc = part ? 1.f : scale;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          const int c = lane + 32 * v;
+          if (c < dim) dst[c] = part ? acc[v] : __fmul_rn(acc[v], sc);
+        }
+      }
+#pragma unroll
+      for (int v = 0; v < NV; ++v) acc[v] = 0.f;
+    };
+    // G tokens per step: all their row loads are issued before the first add (one warp keeps
+    // G * NV 128-byte requests in flight instead of one row at a time)
+    constexpr int G = NV <= 4 ? 8 : 4;
+    for (int i0 = 0; i0 < cnt; i0 += G) {
+      uint32_t kk[G];
+      float g[G][NV];
+#pragma unroll
+      for (int j = 0; j < G; ++j) {
+        const int i = i0 + j;   // i0 is a multiple of G, G divides 32: one branch per step
+        kk[j] = i0 < 32 ? __shfl_sync(0xffffffffu, k0, i & 31) : __shfl_sync(0xffffffffu, k1, i & 31);
+        const uint32_t ti = i0 < 32 ? __shfl_sync(0xffffffffu, t0, i & 31) : __shfl_sync(0xffffffffu, t1, i & 31);
+        const float* src = dout + (size_t)ti * d_model + off;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          const int c = lane + 32 * v;
+          float x = 0.f;
+          if (i < cnt && c < dim) {
+            x = __ldg(src + c);
+            if (thresh24) {
+              const bool keep = dropout_keep(seed, site, (uint64_t)ti * d_model + off + c, thresh24);
+              x = keep ? __fmul_rn(x, inv_keep) : 0.f;
+            }
+          }
+          g[j][v] = x;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < G; ++j) {
+        if (i0 + j < cnt) {
+          if (kk[j] != run_key) {
+            flush(false);
+            run_key = kk[j];
+            run_is_first = false;
+          }
+#pragma unroll
+          for (int v = 0; v < NV; ++v) acc[v] = __fadd_rn(acc[v], g[j][v]);
+        }
+      }
+    }
+    flush(true);
+  }
+}
+
+template <int NV>
+__global__ void __launch_bounds__(256)
+segment_fixup_kernel(int dim, const uint32_t* __restrict__ skeys, long n, int rows, float scale,
+                     const float* __restrict__ partial, float* __restrict__ table_grad,
+                     int* __restrict__ long_count, int2* __restrict__ long_list, int long_cap) {
+  const int lane = threadIdx.x & 31;
+  const long n_tiles = (n + SEG_TILE - 1) / SEG_TILE;
+  for (long a = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); a < n_tiles;
+       a += (long)gridDim.x * (blockDim.x >> 5)) {
+    const long b = a * SEG_TILE;
+    const long e = min(n, b + SEG_TILE);
+    if (e >= n) continue;
+    const uint32_t K = skeys[e - 1];
+    if (skeys[e] != K) continue;                                  // last run closed on the right
+    const bool whole = skeys[b] == K;
+    if (whole && b > 0 && skeys[b - 1] == K) continue;            // a continuation, not the start
+    if (K >= (uint32_t)rows) continue;
+    float acc[NV];
+    const float* p0 = partial + (size_t)(2 * a + (whole ? 0 : 1)) * dim;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) acc[v] = lane + 32 * v < dim ? p0[lane + 32 * v] : 0.f;
+    long w = a + 1;
+    bool is_long = false;
+    while (true) {
+      const float* pw = partial + (size_t)(2 * w) * dim;
+#pragma unroll
+      for (int v = 0; v < NV; ++v)
+        if (lane + 32 * v < dim) acc[v] = __fadd_rn(acc[v], pw[lane + 32 * v]);
+      const long we = min(n, (w + 1) * SEG_TILE);
+      const bool cont = we < n && skeys[we - 1] == K && skeys[we] == K;
+      if (!cont) break;
+      ++w;
+      if (w - a > SEG_LONG) { is_long = true; break; }
+    }
+    if (is_long) {  // queue for the block-parallel kernel (queue order does not affect results)
+      if (lane == 0) {
+        const int slot = atomicAdd(long_count, 1);
+        if (slot < long_cap) long_list[slot] = make_int2((int)a, (int)K);
+      }
+      continue;
+    }
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+      if (lane + 32 * v < dim) table_grad[(size_t)K * dim + lane + 32 * v] = __fmul_rn(acc[v], scale);
+  }
+}
+
+// one block per queued id: rows to add, in order: partial[a][slot], partial[a+1][0], ...,
+// partial[b_end][0].  Warp q adds rows [q*per, (q+1)*per) in order; the 32 sums are added in order.
+__global__ void __launch_bounds__(1024)
+segment_long_kernel(int dim, const uint32_t* __restrict__ skeys, long n, float scale,
+                    const float* __restrict__ partial, float* __restrict__ table_grad,
+                    const int* __restrict__ long_count, const int2* __restrict__ long_list,
+                    int long_cap) {
+  __shared__ float part[32][256 + 1];
+  __shared__ long s_end;
+  const int n_long = min(*long_count, long_cap);
+  const int lane = threadIdx.x & 31, q = threadIdx.x >> 5;
+  for (int li = blockIdx.x; li < n_long; li += gridDim.x) {
+    const long a = long_list[li].x;
+    const uint32_t K = (uint32_t)long_list[li].y;
+    {  // upper bound of K in the sorted keys: 1024-ary search, two or three rounds
+      long lo = (a + 1) * SEG_TILE, hi = n;   // skeys[lo] == K is known; answer in (lo, hi]
+      while (hi - lo > 1) {
+        const long step = (hi - lo + blockDim.x - 1) / blockDim.x;
+        const long pos = lo + (long)threadIdx.x * step;
+        const int below = __syncthreads_count(pos < hi && skeys[pos] <= K);   // monotone in pos
+        const long nlo = lo + (long)(below - 1) * step;
+        hi = min(hi, nlo + step);
+        lo = nlo;
+      }
+      if (threadIdx.x == 0) s_end = hi;   // first position whose key is greater than K
+    }
+    __syncthreads();
+    const long b_end = (s_end - 1) / SEG_TILE;
+    const long R = b_end - a + 1;
+    const long per = (R + 31) / 32;
+    const bool whole = skeys[a * SEG_TILE] == K;
+    const long r0 = q * per, r1 = min(R, r0 + per);
+    for (int c = lane; c < dim; c += 32) {
+      float acc = 0.f;
+      for (long r = r0; r < r1; ++r) {
+        const size_t prow = r == 0 ? (size_t)(2 * a + (whole ? 0 : 1)) : (size_t)(2 * (a + r));
+        acc = __fadd_rn(acc, partial[prow * dim + c]);
+      }
+      part[q][c] = acc;
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < dim; c += blockDim.x) {
+      float acc = 0.f;
+#pragma unroll
+      for (int w = 0; w < 32; ++w) acc = __fadd_rn(acc, part[w][c]);
+      table_grad[(size_t)K * dim + c] = __fmul_rn(acc, scale);
+    }
+    __syncthreads();
+  }
+}
+
 struct BwdWorkspace {
   uint32_t *keys0, *keys1, *vals0, *vals1;
-  int *hist, *flags, *flag_scan, *seg_start, *chunks, *chunk_off, *mchunks, *mchunk_off,
-      *scan_scratch, *counters;
+  int *hist, *flags, *flag_scan, *seg_start, *scan_scratch, *counters;
   float* partial;
+  int2* long_list;
   size_t bytes;
 };
 
@@ -392,14 +502,11 @@ static BwdWorkspace carve_ws(void* base, long T, int max_dim) {
   w.flags = (int*)take(T * 4);
   w.flag_scan = (int*)take(T * 4);
   w.seg_start = (int*)take((T + 1) * 4);
-  w.chunks = (int*)take(T * 4);
-  w.chunk_off = (int*)take(T * 4);
-  w.mchunks = (int*)take(T * 4);
-  w.mchunk_off = (int*)take(T * 4);
   w.scan_scratch = (int*)take((size_t)(ceil_div(std::max<long>(T, 256L * nblocks), SCAN_TILE) + 1) * 4);
   w.counters = (int*)take(64);
-  // every segment with > 1 chunk has >= SEG_CHUNK tokens per chunk except its last one
-  w.partial = (float*)take((size_t)(2 * (T / SEG_CHUNK) + 2) * max_dim * 4);
+  // two partial rows (first / last run) per SEG_TILE tile
+  w.partial = (float*)take((size_t)(2 * (T / SEG_TILE) + 4) * max_dim * 4);
+  w.long_list = (int2*)take((size_t)(T / (SEG_TILE * SEG_LONG) + 2) * sizeof(int2));
   w.bytes = o;
   return w;
 }
@@ -493,26 +600,38 @@ extern "C" int b4cp_embed_bwd(const float* dout, int d_model, int col_offset, in
   const uint32_t* skeys = kin;
   const uint32_t* stok = vin;
   int* n_unique = w.counters;
-  int* total_chunks = w.counters + 1;
+  int* long_count = w.counters + 2;
   const int tb = ceil_div(T, 256);
-  segment_flags_kernel<<<tb, 256, 0, st>>>(skeys, T, w.flags);
-  if (exclusive_scan(w.flags, w.flag_scan, T, w.scan_scratch, n_unique, st)) return -1;
-  segment_starts_kernel<<<tb, 256, 0, st>>>(w.flags, w.flag_scan, T, w.seg_start, n_unique);
-  segment_chunk_counts_kernel<<<tb, 256, 0, st>>>(w.seg_start, n_unique, w.chunks, w.mchunks, T);
-  if (exclusive_scan(w.chunks, w.chunk_off, T, w.scan_scratch, total_chunks, st)) return -1;
-  if (exclusive_scan(w.mchunks, w.mchunk_off, T, w.scan_scratch, nullptr, st)) return -1;
+  B4CP_CHECK_ARG(dim <= 32 * SEG_NV, "embed_bwd: feature width %d > %d", dim, 32 * SEG_NV);
   B4CP_CUDA(cudaMemsetAsync(table_grad, 0, (size_t)rows * dim * sizeof(float), st));
+  B4CP_CUDA(cudaMemsetAsync(long_count, 0, sizeof(int), st));
   const float scale = sqrtf((float)d_model);
   const float inv_keep = 1.0f / (1.0f - dropout_rate);
   const uint32_t thresh24 = (uint32_t)((double)dropout_rate * 16777216.0);
-  const int grid = 148 * 8;
-  segment_sum_kernel<<<grid, 256, 0, st>>>(dout, d_model, col_offset, dim, skeys, stok,
-                                           w.seg_start, w.chunk_off, w.mchunk_off, rows, n_unique,
-                                           total_chunks, scale,
-                                           inv_keep, thresh24, seed, site, table_grad, w.partial);
-  segment_combine_kernel<<<grid, 256, 0, st>>>(dim, skeys, w.seg_start, w.mchunk_off, rows,
-                                               n_unique, scale, w.partial, table_grad);
-  note_launches(5);
+  const long n_tiles = (T + SEG_TILE - 1) / SEG_TILE;
+  const int grid = (int)std::min<long>((n_tiles + 7) / 8, 148L * 16);
+  const int long_cap = (int)(T / (SEG_TILE * SEG_LONG) + 2);
+#define B4CP_SEG_LAUNCH(NV)                                                                        \
+  do {                                                                                             \
+    segment_tile_sum_kernel<NV><<<grid, 256, 0, st>>>(dout, d_model, col_offset, dim, skeys, stok, \
+                                                      T, rows, scale, inv_keep, thresh24, seed,    \
+                                                      site, table_grad, w.partial);                \
+    segment_fixup_kernel<NV><<<grid, 256, 0, st>>>(dim, skeys, T, rows, scale, w.partial,          \
+                                                   table_grad, long_count, w.long_list, long_cap); \
+  } while (0)
+  if (dim <= 64) B4CP_SEG_LAUNCH(2);
+  else if (dim <= 128) B4CP_SEG_LAUNCH(4);
+  else B4CP_SEG_LAUNCH(8);
+#undef B4CP_SEG_LAUNCH
+  segment_long_kernel<<<64, 1024, 0, st>>>(dim, skeys, T, scale, w.partial, table_grad, long_count,
+                                           w.long_list, long_cap);
+  note_launches(3);
+  if (uniq_ids || n_unique_out) {  // optional export of the unique ids (not needed for the sums)
+    segment_flags_kernel<<<tb, 256, 0, st>>>(skeys, T, w.flags);
+    if (exclusive_scan(w.flags, w.flag_scan, T, w.scan_scratch, n_unique, st)) return -1;
+    segment_starts_kernel<<<tb, 256, 0, st>>>(w.flags, w.flag_scan, T, w.seg_start, n_unique);
+    note_launches(2);
+  }
   if (uniq_ids) export_unique_kernel<<<tb, 256, 0, st>>>(skeys, w.seg_start, n_unique, uniq_ids, T);
   if (n_unique_out)
     B4CP_CUDA(cudaMemcpyAsync(n_unique_out, n_unique, sizeof(int), cudaMemcpyDeviceToDevice, st));

@@ -156,7 +156,7 @@ def test_embed_fwd_dropout_matches_exported_mask(cuda_lib):
     np.testing.assert_allclose(out.cpu().numpy().reshape(B, S, d), base * mask, rtol=1e-6)
 
 
-@pytest.mark.parametrize("B,S,rows", [(64, 52, 311), (512, 52, 54304), (3, 5, 70000)])
+@pytest.mark.parametrize("B,S,rows", [(64, 52, 311), (512, 52, 54304), (3, 5, 70000), (4096, 20, 500)])
 def test_embed_bwd_sorted_scatter_add(cuda_lib, B, S, rows):
     from bert4clickpath_b200 import ops
     rng = np.random.default_rng(B)
