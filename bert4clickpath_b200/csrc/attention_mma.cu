@@ -1,4 +1,4 @@
-// Tensor-core path of the fused short-sequence masked self-attention (S <= 128, head depth 32
+// Tensor-core path of the fused short-sequence masked self-attention (S <= 256, head depth 32
 // or 64): transformer.py:64-97 (scaled_dot_product_attention) and :130-156 (split / merge heads).
 // One CTA per (sequence, head); Q/K/V (and dO) live in shared memory as row-major bf16 tiles
 // (staged with 128-bit loads; transposed operands come from ldmatrix.trans), the S x S score
@@ -386,6 +386,359 @@ attention_mma_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloa
   }
 }
 
+// =============================================================================== 128 < S <= 256
+// The same products for sequences of up to 256 positions (S = 202 / 203).  The
+// score tile of one 16-row block no longer fits in registers (32 key tiles x 4 accumulators, twice
+// that in the backward), so keys (forward, dQ pass) / queries (dK, dV pass) are walked in two
+// halves of 128: the forward keeps a running (max, sum) and rescales O, flash-attention style; the
+// backward takes delta = rowsum(dO o O) from the saved forward output instead of a sweep over all
+// keys.  256 threads per CTA (16 row blocks, two per warp).
+static constexpr int LSP = 256;   // padded sequence length
+static constexpr int LHALF = 128;
+
+template <int DH>
+__global__ void __launch_bounds__(256)
+attention_mma_fwd_long_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __restrict__ ids,
+                              int S, int H, __nv_bfloat16* __restrict__ out,
+                              float* __restrict__ lse_out) {
+  constexpr int LDR = DH + 8, KS_D = DH / 16, NT_D = DH / 8, NT = LHALF / 8, KS_S = LHALF / 16;
+  extern __shared__ __align__(16) uint8_t sm[];
+  __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(sm);
+  __nv_bfloat16* sK = sQ + LSP * LDR;
+  __nv_bfloat16* sV = sK + LSP * LDR;
+  float* sMask = reinterpret_cast<float*>(sV + LSP * LDR);
+  const int d = H * DH;
+  const int b = blockIdx.x / H, h = blockIdx.x % H;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int nwarps = blockDim.x >> 5;
+  const __nv_bfloat16* base = qkv + (size_t)b * S * 3 * d + h * DH;
+  stage_tile<DH, LSP>(base, 3L * d, S, sQ, LDR);
+  stage_tile<DH, LSP>(base + d, 3L * d, S, sK, LDR);
+  stage_tile<DH, LSP>(base + 2 * d, 3L * d, S, sV, LDR);
+  for (int j = threadIdx.x; j < LSP; j += blockDim.x)
+    sMask[j] = j >= S ? -INFINITY : (ids[(size_t)b * S + j] == 0 ? -1e9f : 0.f);
+  __syncthreads();
+  const float sqrt_dh = sqrtf((float)DH);
+  for (int rb = warp; rb * 16 < S; rb += nwarps) {
+    const int r0 = rb * 16;
+    float o[NT_D][4];
+#pragma unroll
+    for (int n2 = 0; n2 < NT_D; ++n2) o[n2][0] = o[n2][1] = o[n2][2] = o[n2][3] = 0.f;
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+#pragma unroll 1
+    for (int kh = 0; kh < 2; ++kh) {
+      const int kb0 = kh * LHALF;
+      if (kb0 >= S) break;
+      float sc[NT][4];
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < KS_D; ++ks) {
+        uint32_t a[4];
+        load_a(a, sQ, LDR, r0, ks * 16, g, t);
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+          uint32_t b0, b1;
+          load_b(b0, b1, sK, LDR, kb0 + nt * 8, ks * 16, g, t);
+          mma_bf16(sc[nt], a, b0, b1);
+        }
+      }
+      float c0 = -INFINITY, c1 = -INFINITY;
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        const float k0 = sMask[kb0 + nt * 8 + t * 2], k1 = sMask[kb0 + nt * 8 + t * 2 + 1];
+        sc[nt][0] = __fdiv_rn(sc[nt][0], sqrt_dh) + k0;
+        sc[nt][1] = __fdiv_rn(sc[nt][1], sqrt_dh) + k1;
+        sc[nt][2] = __fdiv_rn(sc[nt][2], sqrt_dh) + k0;
+        sc[nt][3] = __fdiv_rn(sc[nt][3], sqrt_dh) + k1;
+        c0 = fmaxf(c0, fmaxf(sc[nt][0], sc[nt][1]));
+        c1 = fmaxf(c1, fmaxf(sc[nt][2], sc[nt][3]));
+      }
+      const float n0 = fmaxf(m0, quad_max(c0)), n1 = fmaxf(m1, quad_max(c1));   // finite: key 0 exists
+      const float a0 = expf(m0 - n0), a1 = expf(m1 - n1);                        // exp(-inf) = 0 at first
+      float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        sc[nt][0] = expf(sc[nt][0] - n0);
+        sc[nt][1] = expf(sc[nt][1] - n0);
+        sc[nt][2] = expf(sc[nt][2] - n1);
+        sc[nt][3] = expf(sc[nt][3] - n1);
+        s0 += sc[nt][0] + sc[nt][1];
+        s1 += sc[nt][2] + sc[nt][3];
+      }
+      l0 = l0 * a0 + quad_sum(s0);
+      l1 = l1 * a1 + quad_sum(s1);
+      m0 = n0;
+      m1 = n1;
+#pragma unroll
+      for (int n2 = 0; n2 < NT_D; ++n2) {
+        o[n2][0] *= a0; o[n2][1] *= a0; o[n2][2] *= a1; o[n2][3] *= a1;
+      }
+#pragma unroll
+      for (int ks = 0; ks < KS_S; ++ks) {
+        uint32_t a[4];
+        a[0] = pack_bf16(sc[2 * ks][0], sc[2 * ks][1]);
+        a[1] = pack_bf16(sc[2 * ks][2], sc[2 * ks][3]);
+        a[2] = pack_bf16(sc[2 * ks + 1][0], sc[2 * ks + 1][1]);
+        a[3] = pack_bf16(sc[2 * ks + 1][2], sc[2 * ks + 1][3]);
+#pragma unroll
+        for (int n2 = 0; n2 < NT_D; n2 += 2) {
+          uint32_t bb[4];
+          load_b_trans2(bb, sV, LDR, kb0 + ks * 16, n2 * 8, lane);
+          mma_bf16(o[n2], a, bb[0], bb[1]);
+          mma_bf16(o[n2 + 1], a, bb[2], bb[3]);
+        }
+      }
+    }
+    const float i0 = 1.f / l0, i1 = 1.f / l1;
+    const int row0 = r0 + g, row1 = r0 + g + 8;
+#pragma unroll
+    for (int n2 = 0; n2 < NT_D; ++n2) {
+      const int col = h * DH + n2 * 8 + t * 2;
+      if (row0 < S)
+        *reinterpret_cast<uint32_t*>(out + ((size_t)b * S + row0) * d + col) =
+            pack_bf16(o[n2][0] * i0, o[n2][1] * i0);
+      if (row1 < S)
+        *reinterpret_cast<uint32_t*>(out + ((size_t)b * S + row1) * d + col) =
+            pack_bf16(o[n2][2] * i1, o[n2][3] * i1);
+    }
+    if (lse_out && t == 0) {
+      if (row0 < S) lse_out[((size_t)b * H + h) * S + row0] = m0 + logf(l0);
+      if (row1 < S) lse_out[((size_t)b * H + h) * S + row1] = m1 + logf(l1);
+    }
+  }
+}
+
+template <int DH>
+__global__ void __launch_bounds__(256)
+attention_mma_bwd_long_kernel(const __nv_bfloat16* __restrict__ qkv,
+                              const __nv_bfloat16* __restrict__ fwd_out,
+                              const __nv_bfloat16* __restrict__ dout,
+                              const float* __restrict__ lse_in, const int32_t* __restrict__ ids,
+                              int S, int H, __nv_bfloat16* __restrict__ dqkv) {
+  constexpr int LDR = DH + 8, KS_D = DH / 16, NT_D = DH / 8, NT = LHALF / 8, KS_S = LHALF / 16;
+  extern __shared__ __align__(16) uint8_t sm[];
+  __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(sm);
+  __nv_bfloat16* sK = sQ + LSP * LDR;
+  __nv_bfloat16* sV = sK + LSP * LDR;
+  __nv_bfloat16* sDO = sV + LSP * LDR;
+  float* sMask = reinterpret_cast<float*>(sDO + LSP * LDR);
+  float* sLse = sMask + LSP;
+  float* sDelta = sLse + LSP;
+  const int d = H * DH;
+  const int b = blockIdx.x / H, h = blockIdx.x % H;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int nwarps = blockDim.x >> 5;
+  const __nv_bfloat16* base = qkv + (size_t)b * S * 3 * d + h * DH;
+  stage_tile<DH, LSP>(base, 3L * d, S, sQ, LDR);
+  stage_tile<DH, LSP>(base + d, 3L * d, S, sK, LDR);
+  stage_tile<DH, LSP>(base + 2 * d, 3L * d, S, sV, LDR);
+  stage_tile<DH, LSP>(dout + (size_t)b * S * d + h * DH, (long)d, S, sDO, LDR);
+  for (int j = threadIdx.x; j < LSP; j += blockDim.x) {
+    sMask[j] = j >= S ? -INFINITY : (ids[(size_t)b * S + j] == 0 ? -1e9f : 0.f);
+    sLse[j] = j < S ? lse_in[((size_t)b * H + h) * S + j] : INFINITY;  // rows past S: P = 0
+  }
+  __syncthreads();
+  // delta[r] = sum_c dO[r][c] * O[r][c]  (= rowsum(P o dP)); one warp per row
+  for (int r = warp; r < LSP; r += nwarps) {
+    float acc = 0.f;
+    if (r < S) {
+      const __nv_bfloat16* orow = fwd_out + ((size_t)b * S + r) * d + h * DH;
+      for (int c = lane * 2; c < DH; c += 64) {
+        const __nv_bfloat162 ov = *reinterpret_cast<const __nv_bfloat162*>(orow + c);
+        const __nv_bfloat162 gv = *reinterpret_cast<const __nv_bfloat162*>(sDO + (size_t)r * LDR + c);
+        acc += __bfloat162float(ov.x) * __bfloat162float(gv.x) + __bfloat162float(ov.y) * __bfloat162float(gv.y);
+      }
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) sDelta[r] = acc;
+  }
+  __syncthreads();
+  const float sqrt_dh = sqrtf((float)DH);
+  const float inv_sqrt = 1.f / sqrt_dh;
+  __nv_bfloat16* dst = dqkv + (size_t)b * S * 3 * d + h * DH;
+
+  // ---- pass A: query row blocks -> dQ (keys in two halves)
+  for (int rb = warp; rb * 16 < S; rb += nwarps) {
+    const int r0 = rb * 16;
+    float dq[NT_D][4];
+#pragma unroll
+    for (int n2 = 0; n2 < NT_D; ++n2) dq[n2][0] = dq[n2][1] = dq[n2][2] = dq[n2][3] = 0.f;
+    const float l0 = sLse[r0 + g], l1 = sLse[r0 + g + 8];
+    const float d0 = sDelta[r0 + g], d1 = sDelta[r0 + g + 8];
+#pragma unroll 1
+    for (int kh = 0; kh < 2; ++kh) {
+      const int kb0 = kh * LHALF;
+      if (kb0 >= S) break;
+      float p[NT][4], dp[NT][4];
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        p[nt][0] = p[nt][1] = p[nt][2] = p[nt][3] = 0.f;
+        dp[nt][0] = dp[nt][1] = dp[nt][2] = dp[nt][3] = 0.f;
+      }
+#pragma unroll
+      for (int ks = 0; ks < KS_D; ++ks) {
+        uint32_t aq[4], ag[4];
+        load_a(aq, sQ, LDR, r0, ks * 16, g, t);
+        load_a(ag, sDO, LDR, r0, ks * 16, g, t);
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+          uint32_t b0, b1;
+          load_b(b0, b1, sK, LDR, kb0 + nt * 8, ks * 16, g, t);
+          mma_bf16(p[nt], aq, b0, b1);
+          load_b(b0, b1, sV, LDR, kb0 + nt * 8, ks * 16, g, t);
+          mma_bf16(dp[nt], ag, b0, b1);
+        }
+      }
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        const float k0 = sMask[kb0 + nt * 8 + t * 2], k1 = sMask[kb0 + nt * 8 + t * 2 + 1];
+        p[nt][0] = expf(__fdiv_rn(p[nt][0], sqrt_dh) + k0 - l0) * (dp[nt][0] - d0);
+        p[nt][1] = expf(__fdiv_rn(p[nt][1], sqrt_dh) + k1 - l0) * (dp[nt][1] - d0);
+        p[nt][2] = expf(__fdiv_rn(p[nt][2], sqrt_dh) + k0 - l1) * (dp[nt][2] - d1);
+        p[nt][3] = expf(__fdiv_rn(p[nt][3], sqrt_dh) + k1 - l1) * (dp[nt][3] - d1);
+      }
+#pragma unroll
+      for (int ks = 0; ks < KS_S; ++ks) {
+        uint32_t a[4];
+        a[0] = pack_bf16(p[2 * ks][0], p[2 * ks][1]);
+        a[1] = pack_bf16(p[2 * ks][2], p[2 * ks][3]);
+        a[2] = pack_bf16(p[2 * ks + 1][0], p[2 * ks + 1][1]);
+        a[3] = pack_bf16(p[2 * ks + 1][2], p[2 * ks + 1][3]);
+#pragma unroll
+        for (int n2 = 0; n2 < NT_D; n2 += 2) {
+          uint32_t bb[4];
+          load_b_trans2(bb, sK, LDR, kb0 + ks * 16, n2 * 8, lane);
+          mma_bf16(dq[n2], a, bb[0], bb[1]);
+          mma_bf16(dq[n2 + 1], a, bb[2], bb[3]);
+        }
+      }
+    }
+    const int row0 = r0 + g, row1 = r0 + g + 8;
+#pragma unroll
+    for (int n2 = 0; n2 < NT_D; ++n2) {
+      const int col = n2 * 8 + t * 2;
+      if (row0 < S)
+        *reinterpret_cast<uint32_t*>(dst + (size_t)row0 * 3 * d + col) =
+            pack_bf16(dq[n2][0] * inv_sqrt, dq[n2][1] * inv_sqrt);
+      if (row1 < S)
+        *reinterpret_cast<uint32_t*>(dst + (size_t)row1 * 3 * d + col) =
+            pack_bf16(dq[n2][2] * inv_sqrt, dq[n2][3] * inv_sqrt);
+    }
+  }
+
+  // ---- pass B: key row blocks -> dK, dV (transposed tiles; queries in two halves)
+  for (int kb = warp; kb * 16 < S; kb += nwarps) {
+    const int j0 = kb * 16;
+    float dk[NT_D][4], dv[NT_D][4];
+#pragma unroll
+    for (int n2 = 0; n2 < NT_D; ++n2) {
+      dk[n2][0] = dk[n2][1] = dk[n2][2] = dk[n2][3] = 0.f;
+      dv[n2][0] = dv[n2][1] = dv[n2][2] = dv[n2][3] = 0.f;
+    }
+    const float k0m = sMask[j0 + g], k1m = sMask[j0 + g + 8];
+#pragma unroll 1
+    for (int qh = 0; qh < 2; ++qh) {
+      const int qb0 = qh * LHALF;
+      if (qb0 >= S) break;
+      float p[NT][4], dp[NT][4];
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        p[nt][0] = p[nt][1] = p[nt][2] = p[nt][3] = 0.f;
+        dp[nt][0] = dp[nt][1] = dp[nt][2] = dp[nt][3] = 0.f;
+      }
+#pragma unroll
+      for (int ks = 0; ks < KS_D; ++ks) {
+        uint32_t ak[4], av[4];
+        load_a(ak, sK, LDR, j0, ks * 16, g, t);
+        load_a(av, sV, LDR, j0, ks * 16, g, t);
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+          uint32_t b0, b1;
+          load_b(b0, b1, sQ, LDR, qb0 + nt * 8, ks * 16, g, t);
+          mma_bf16(p[nt], ak, b0, b1);
+          load_b(b0, b1, sDO, LDR, qb0 + nt * 8, ks * 16, g, t);
+          mma_bf16(dp[nt], av, b0, b1);
+        }
+      }
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        const int q0 = qb0 + nt * 8 + t * 2;
+        const float la = sLse[q0], lb = sLse[q0 + 1];
+        const float da = sDelta[q0], db = sDelta[q0 + 1];
+        p[nt][0] = expf(__fdiv_rn(p[nt][0], sqrt_dh) + k0m - la);
+        p[nt][1] = expf(__fdiv_rn(p[nt][1], sqrt_dh) + k0m - lb);
+        p[nt][2] = expf(__fdiv_rn(p[nt][2], sqrt_dh) + k1m - la);
+        p[nt][3] = expf(__fdiv_rn(p[nt][3], sqrt_dh) + k1m - lb);
+        dp[nt][0] = p[nt][0] * (dp[nt][0] - da);
+        dp[nt][1] = p[nt][1] * (dp[nt][1] - db);
+        dp[nt][2] = p[nt][2] * (dp[nt][2] - da);
+        dp[nt][3] = p[nt][3] * (dp[nt][3] - db);
+      }
+#pragma unroll
+      for (int ks = 0; ks < KS_S; ++ks) {
+        uint32_t ap[4], az[4];
+        ap[0] = pack_bf16(p[2 * ks][0], p[2 * ks][1]);
+        ap[1] = pack_bf16(p[2 * ks][2], p[2 * ks][3]);
+        ap[2] = pack_bf16(p[2 * ks + 1][0], p[2 * ks + 1][1]);
+        ap[3] = pack_bf16(p[2 * ks + 1][2], p[2 * ks + 1][3]);
+        az[0] = pack_bf16(dp[2 * ks][0], dp[2 * ks][1]);
+        az[1] = pack_bf16(dp[2 * ks][2], dp[2 * ks][3]);
+        az[2] = pack_bf16(dp[2 * ks + 1][0], dp[2 * ks + 1][1]);
+        az[3] = pack_bf16(dp[2 * ks + 1][2], dp[2 * ks + 1][3]);
+#pragma unroll
+        for (int n2 = 0; n2 < NT_D; n2 += 2) {
+          uint32_t bb[4];
+          load_b_trans2(bb, sDO, LDR, qb0 + ks * 16, n2 * 8, lane);
+          mma_bf16(dv[n2], ap, bb[0], bb[1]);
+          mma_bf16(dv[n2 + 1], ap, bb[2], bb[3]);
+          load_b_trans2(bb, sQ, LDR, qb0 + ks * 16, n2 * 8, lane);
+          mma_bf16(dk[n2], az, bb[0], bb[1]);
+          mma_bf16(dk[n2 + 1], az, bb[2], bb[3]);
+        }
+      }
+    }
+    const int row0 = j0 + g, row1 = j0 + g + 8;
+#pragma unroll
+    for (int n2 = 0; n2 < NT_D; ++n2) {
+      const int col = n2 * 8 + t * 2;
+      if (row0 < S) {
+        *reinterpret_cast<uint32_t*>(dst + (size_t)row0 * 3 * d + d + col) =
+            pack_bf16(dk[n2][0] * inv_sqrt, dk[n2][1] * inv_sqrt);
+        *reinterpret_cast<uint32_t*>(dst + (size_t)row0 * 3 * d + 2 * d + col) = pack_bf16(dv[n2][0], dv[n2][1]);
+      }
+      if (row1 < S) {
+        *reinterpret_cast<uint32_t*>(dst + (size_t)row1 * 3 * d + d + col) =
+            pack_bf16(dk[n2][2] * inv_sqrt, dk[n2][3] * inv_sqrt);
+        *reinterpret_cast<uint32_t*>(dst + (size_t)row1 * 3 * d + 2 * d + col) = pack_bf16(dv[n2][2], dv[n2][3]);
+      }
+    }
+  }
+}
+
+template <int DH>
+static int launch_fwd_long(const void* qkv, const int32_t* ids, int B, int S, int H, void* out,
+                           float* lse, cudaStream_t st) {
+  const size_t smem = (size_t)(3 * LSP * (DH + 8)) * 2 + LSP * 4;
+  B4CP_CUDA(cudaFuncSetAttribute(attention_mma_fwd_long_kernel<DH>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  attention_mma_fwd_long_kernel<DH><<<B * H, 256, smem, st>>>(
+      (const __nv_bfloat16*)qkv, ids, S, H, (__nv_bfloat16*)out, lse);
+  return 0;
+}
+
+template <int DH>
+static int launch_bwd_long(const void* qkv, const void* fwd_out, const void* dout, const float* lse,
+                           const int32_t* ids, int B, int S, int H, void* dqkv, cudaStream_t st) {
+  const size_t smem = (size_t)(4 * LSP * (DH + 8)) * 2 + 3 * LSP * 4;
+  B4CP_CUDA(cudaFuncSetAttribute(attention_mma_bwd_long_kernel<DH>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  attention_mma_bwd_long_kernel<DH><<<B * H, 256, smem, st>>>(
+      (const __nv_bfloat16*)qkv, (const __nv_bfloat16*)fwd_out, (const __nv_bfloat16*)dout, lse, ids,
+      S, H, (__nv_bfloat16*)dqkv);
+  return 0;
+}
+
 template <int NKB, int DH>
 static int launch_fwd(const void* qkv, const int32_t* ids, int B, int S, int H, void* out, float* lse,
                       cudaStream_t st) {
@@ -410,10 +763,13 @@ static int launch_bwd(const void* qkv, const void* dout, const float* lse, const
   return 0;
 }
 
-bool attention_mma_supported(int S, int dh) { return S <= 128 && (dh == 32 || dh == 64); }
+bool attention_mma_supported(int S, int dh) { return S <= LSP && (dh == 32 || dh == 64); }
 
 int attention_mma_fwd(const void* qkv, const int32_t* ids, int B, int S, int H, int dh, void* out,
                       float* lse, cudaStream_t st) {
+  if (S > 128)
+    return dh == 32 ? launch_fwd_long<32>(qkv, ids, B, S, H, out, lse, st)
+                    : launch_fwd_long<64>(qkv, ids, B, S, H, out, lse, st);
   const int nkb = S <= 64 ? 1 : 2;
   if (nkb == 1 && dh == 32) return launch_fwd<1, 32>(qkv, ids, B, S, H, out, lse, st);
   if (nkb == 1 && dh == 64) return launch_fwd<1, 64>(qkv, ids, B, S, H, out, lse, st);
@@ -421,8 +777,16 @@ int attention_mma_fwd(const void* qkv, const int32_t* ids, int B, int S, int H, 
   return launch_fwd<2, 64>(qkv, ids, B, S, H, out, lse, st);
 }
 
-int attention_mma_bwd(const void* qkv, const void* dout, const float* lse, const int32_t* ids, int B,
-                      int S, int H, int dh, void* dqkv, cudaStream_t st) {
+int attention_mma_bwd(const void* qkv, const void* fwd_out, const void* dout, const float* lse,
+                      const int32_t* ids, int B, int S, int H, int dh, void* dqkv, cudaStream_t st) {
+  if (S > 128) {
+    if (!fwd_out) {
+      set_last_error("attention_bwd: S=%d > 128 needs the forward output (delta = rowsum(dO o O))", S);
+      return -1;
+    }
+    return dh == 32 ? launch_bwd_long<32>(qkv, fwd_out, dout, lse, ids, B, S, H, dqkv, st)
+                    : launch_bwd_long<64>(qkv, fwd_out, dout, lse, ids, B, S, H, dqkv, st);
+  }
   const int nkb = S <= 64 ? 1 : 2;
   if (nkb == 1 && dh == 32) return launch_bwd<1, 32>(qkv, dout, lse, ids, B, S, H, dqkv, st);
   if (nkb == 1 && dh == 64) return launch_bwd<1, 64>(qkv, dout, lse, ids, B, S, H, dqkv, st);

@@ -97,6 +97,75 @@ embed_fwd_kernel(const EmbedParams p, float* __restrict__ out, __nv_bfloat16* __
   }
 }
 
+// 128-bit path with U independent (id -> row) chains per thread: the id load and the row load it
+// feeds are two dependent memory latencies, so one 16-byte load per thread in flight (the generic
+// kernel above) keeps only ~32 KB per SM moving; U = 4 quadruples that.
+template <int U>
+__global__ void __launch_bounds__(256)
+embed_fwd_vec_kernel(const EmbedParams p, int tok_shift, float* __restrict__ out,
+                     __nv_bfloat16* __restrict__ out_bf16) {
+  const uint64_t seed_v = resolve_seed(p.seed);
+  const long per_tok = p.d_model / 4;
+  const long total = p.T * per_tok;
+  const long stride = (long)gridDim.x * blockDim.x;
+  for (long i0 = blockIdx.x * (long)blockDim.x + threadIdx.x; i0 < total; i0 += stride * U) {
+    long t[U];
+    int c[U], f[U], id[U];
+    bool ok[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long i = i0 + u * stride;
+      ok[u] = i < total;
+      t[u] = tok_shift >= 0 ? (i >> tok_shift) : i / per_tok;
+      c[u] = (int)(i - t[u] * per_tok) * 4;
+      f[u] = 0;
+#pragma unroll
+      for (int g = 1; g < B4CP_MAX_FEATURES; ++g)
+        if (g < p.F && c[u] >= p.offs[g]) f[u] = g;
+      id[u] = ok[u] ? __ldg(p.ids[f[u]] + t[u]) : -1;
+    }
+    float4 ev[U], pv[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const bool id_ok = (unsigned)id[u] < (unsigned)p.rows[f[u]];
+      ev[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      pv[u] = ev[u];
+      if (ok[u]) {
+        if (id_ok)
+          ev[u] = __ldg(reinterpret_cast<const float4*>(
+              p.tables[f[u]] + (size_t)id[u] * p.dims[f[u]] + (c[u] - p.offs[f[u]])));
+        const int s = (int)(t[u] % p.S);
+        pv[u] = __ldg(reinterpret_cast<const float4*>(p.pe + (size_t)s * p.d_model + c[u]));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (!ok[u]) continue;
+      float o[4] = {__fadd_rn(__fmul_rn(ev[u].x, p.scale), pv[u].x),
+                    __fadd_rn(__fmul_rn(ev[u].y, p.scale), pv[u].y),
+                    __fadd_rn(__fmul_rn(ev[u].z, p.scale), pv[u].z),
+                    __fadd_rn(__fmul_rn(ev[u].w, p.scale), pv[u].w)};
+      if (p.thresh24) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const bool keep = dropout_keep(seed_v, p.site, (uint64_t)(t[u] * p.d_model + c[u] + j), p.thresh24);
+          o[j] = keep ? __fmul_rn(o[j], p.inv_keep) : 0.f;
+        }
+      }
+      const size_t off = (size_t)t[u] * p.d_model + c[u];
+      if (out) *reinterpret_cast<float4*>(out + off) = make_float4(o[0], o[1], o[2], o[3]);
+      if (out_bf16) {
+        __nv_bfloat162 a = __floats2bfloat162_rn(o[0], o[1]);
+        __nv_bfloat162 b = __floats2bfloat162_rn(o[2], o[3]);
+        uint2 pk;
+        pk.x = *reinterpret_cast<uint32_t*>(&a);
+        pk.y = *reinterpret_cast<uint32_t*>(&b);
+        *reinterpret_cast<uint2*>(out_bf16 + off) = pk;
+      }
+    }
+  }
+}
+
 // =========================================================================== device scans
 static constexpr int SCAN_THREADS = 256;
 static constexpr int SCAN_ITEMS = 8;
@@ -550,9 +619,17 @@ extern "C" int b4cp_embed_fwd(const int32_t* const* h_ids, const float* const* h
          (((uintptr_t)out_bf16 & 7) == 0);
   const long work = p.T * (p.d_model / (vec4 ? 4 : 1));
   const int blocks = (int)std::min<long>(ceil_div(work, 256), 148L * 16);
-  if (vec4)
-    embed_fwd_kernel<4><<<blocks, 256, 0, (cudaStream_t)stream>>>(p, out_f32, (__nv_bfloat16*)out_bf16);
-  else
+  if (vec4) {
+    const int per_tok = p.d_model / 4;
+    int tok_shift = -1;
+    if ((per_tok & (per_tok - 1)) == 0) {
+      tok_shift = 0;
+      while ((1 << tok_shift) < per_tok) ++tok_shift;
+    }
+    const int vblocks = (int)std::min<long>(ceil_div(work, 256L * 4), 148L * 8);
+    embed_fwd_vec_kernel<4><<<vblocks, 256, 0, (cudaStream_t)stream>>>(p, tok_shift, out_f32,
+                                                                       (__nv_bfloat16*)out_bf16);
+  } else
     embed_fwd_kernel<1><<<blocks, 256, 0, (cudaStream_t)stream>>>(p, out_f32, (__nv_bfloat16*)out_bf16);
   note_launches(1);
   B4CP_LAUNCH_CHECK();

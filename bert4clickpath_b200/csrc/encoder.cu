@@ -19,7 +19,8 @@ static constexpr int MAX_S = 256;
 bool attention_mma_supported(int S, int dh);
 int attention_mma_fwd(const void* qkv, const int32_t* ids, int B, int S, int H, int dh, void* out,
                       float* lse, cudaStream_t st);
-int attention_mma_bwd(const void* qkv, const void* dout, const float* lse, const int32_t* ids, int B,
+int attention_mma_bwd(const void* qkv, const void* fwd_out, const void* dout, const float* lse,
+                      const int32_t* ids, int B,
                       int S, int H, int dh, void* dqkv, cudaStream_t st);
 
 __device__ __forceinline__ float bf2f(__nv_bfloat16 v) { return __bfloat162float(v); }
@@ -760,14 +761,16 @@ extern "C" int b4cp_attention_fwd(const void* qkv, const int32_t* ids_first, int
   return 0;
 }
 
-extern "C" int b4cp_attention_bwd(const void* qkv, const void* dout, const float* lse,
-                                  const int32_t* ids_first, int B, int S, int H, int dh,
-                                  void* dqkv, void* stream) {
+extern "C" int b4cp_attention_bwd(const void* qkv, const void* out, const void* dout,
+                                  const float* lse, const int32_t* ids_first, int B, int S, int H,
+                                  int dh, void* dqkv, void* stream) {
   B4CP_CHECK_ARG(S >= 1 && S <= MAX_S, "attention: S=%d must be in [1,%d]", S, MAX_S);
   B4CP_CHECK_ARG(dh % 2 == 0 && dh >= 2 && dh <= 128, "attention: head depth %d unsupported", dh);
   if (B == 0) return 0;
-  if (attention_mma_supported(S, dh)) {
-    int rc = attention_mma_bwd(qkv, dout, lse, ids_first, B, S, H, dh, dqkv, (cudaStream_t)stream);
+  // 128 < S <= 256 on the tensor cores needs the saved forward output (delta = rowsum(dO o O));
+  // without it the SIMT kernel below computes delta from a full sweep
+  if (attention_mma_supported(S, dh) && (S <= 128 || out)) {
+    int rc = attention_mma_bwd(qkv, out, dout, lse, ids_first, B, S, H, dh, dqkv, (cudaStream_t)stream);
     if (rc) return rc;
     note_launches(1);
     B4CP_LAUNCH_CHECK();

@@ -174,6 +174,45 @@ adam_kernel(float* __restrict__ theta, const float* __restrict__ grad, float* __
   }
 }
 
+// 128-bit variant: n % 4 == 0, 16-byte aligned buffers, and (with a shadow) cols % 4 == 0 so that
+// four consecutive parameters never straddle a shadow row.  Same arithmetic, element by element.
+__global__ void __launch_bounds__(256)
+adam_vec4_kernel(float4* __restrict__ theta, const float4* __restrict__ grad, float4* __restrict__ m,
+                 float4* __restrict__ v, long n4, float lr, float b1, float b2, float eps,
+                 const int* __restrict__ step_dev, int step_host, float grad_scale,
+                 __nv_bfloat16* __restrict__ shadow, int cols, long ld_shadow) {
+  const int t = step_dev ? *step_dev : step_host;
+  const float lr_t = lr * sqrtf(1.f - powf(b2, (float)t)) / (1.f - powf(b1, (float)t));
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n4;
+       i += (long)gridDim.x * blockDim.x) {
+    const float4 g4 = grad[i];
+    float4 m4 = m[i], v4 = v[i], th4 = theta[i];
+    const float gs[4] = {g4.x * grad_scale, g4.y * grad_scale, g4.z * grad_scale, g4.w * grad_scale};
+    float mm[4] = {m4.x, m4.y, m4.z, m4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w};
+    float th[4] = {th4.x, th4.y, th4.z, th4.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      mm[j] = b1 * mm[j] + (1.f - b1) * gs[j];
+      vv[j] = b2 * vv[j] + (1.f - b2) * gs[j] * gs[j];
+      th[j] = th[j] - lr_t * mm[j] / (sqrtf(vv[j]) + eps);
+    }
+    m[i] = make_float4(mm[0], mm[1], mm[2], mm[3]);
+    v[i] = make_float4(vv[0], vv[1], vv[2], vv[3]);
+    theta[i] = make_float4(th[0], th[1], th[2], th[3]);
+    if (shadow) {
+      const long e = i * 4;
+      const long r = e / cols;
+      const int c = (int)(e - r * cols);
+      __nv_bfloat162 a = __floats2bfloat162_rn(th[0], th[1]);
+      __nv_bfloat162 b = __floats2bfloat162_rn(th[2], th[3]);
+      uint2 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&a);
+      pk.y = *reinterpret_cast<uint32_t*>(&b);
+      *reinterpret_cast<uint2*>(shadow + r * ld_shadow + c) = pk;
+    }
+  }
+}
+
 __global__ void step_increment_kernel(int* step) { *step += 1; }
 
 __global__ void __launch_bounds__(256)
@@ -273,6 +312,17 @@ extern "C" int b4cp_adam_step(float* theta, const float* grad, float* m, float* 
   if (n == 0) return 0;
   B4CP_CHECK_ARG(step_dev || step_host >= 1, "adam: step must be >= 1");
   B4CP_CHECK_ARG(!shadow_bf16 || cols > 0, "adam: shadow needs cols");
+  const bool vec = n % 4 == 0 && (((uintptr_t)theta | (uintptr_t)grad | (uintptr_t)m | (uintptr_t)v) & 15) == 0 &&
+                   (!shadow_bf16 || (cols % 4 == 0 && ld_shadow % 4 == 0 && ((uintptr_t)shadow_bf16 & 7) == 0));
+  if (vec) {
+    const int vb = (int)std::min<long>(ceil_div(n / 4, 256), 148L * 8);
+    adam_vec4_kernel<<<vb, 256, 0, (cudaStream_t)stream>>>(
+        (float4*)theta, (const float4*)grad, (float4*)m, (float4*)v, n / 4, lr, beta1, beta2, eps,
+        step_dev, step_host, grad_scale, (__nv_bfloat16*)shadow_bf16, cols, ld_shadow);
+    note_launches(1);
+    B4CP_LAUNCH_CHECK();
+    return 0;
+  }
   const int blocks = (int)std::min<long>(ceil_div(n, 256), 148L * 16);
   adam_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(theta, grad, m, v, n, lr, beta1, beta2,
                                                         eps, step_dev, step_host, grad_scale,

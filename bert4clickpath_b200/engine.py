@@ -290,7 +290,8 @@ class EncoderEngine:
             dob = pool.get("dob", (T, d), BF16)
             dense_bwd_input(dy1b, g("wo"), T, out_bf16=dob)
             dqkvb = pool.get("dqkvb", (T, 3 * d), BF16)
-            ops.attention_bwd(a["qkvb"], dob, a["lse"], sv["ids"][0], B, S, self.H, self.dh, dqkvb)
+            ops.attention_bwd(a["qkvb"], dob, a["lse"], sv["ids"][0], B, S, self.H, self.dh, dqkvb,
+                              out=a["ob"])
             dense_bwd_weights(a["xb"], dqkvb, g("wqkv"), g("bqkv"), T)
             dx = pool.get("dxb", (T, d))
             dense_bwd_input(dqkvb, g("wqkv"), T, addend=dxr, out_f32=dx)

@@ -202,8 +202,9 @@ def attention_fwd(qkv, ids_first, B, S, H, dh, out, lse):
            L.c_int(dh), L.ptr(out), L.ptr(lse), L.stream_ptr())
 
 
-def attention_bwd(qkv, dout, lse, ids_first, B, S, H, dh, dqkv):
-    L.call("b4cp_attention_bwd", L.ptr(qkv), L.ptr(dout), L.ptr(lse), L.ptr(ids_first),
+def attention_bwd(qkv, dout, lse, ids_first, B, S, H, dh, dqkv, out=None):
+    """`out`: the forward output; needed by the tensor-core path for 128 < S <= 256."""
+    L.call("b4cp_attention_bwd", L.ptr(qkv), L.ptr(out), L.ptr(dout), L.ptr(lse), L.ptr(ids_first),
            L.c_int(B), L.c_int(S), L.c_int(H), L.c_int(dh), L.ptr(dqkv), L.stream_ptr())
 
 

@@ -116,7 +116,9 @@ int b4cp_embed_bwd(const float* dout, int d_model, int col_offset, int dim, cons
  */
 int b4cp_attention_fwd(const void* qkv, const int32_t* ids_first, int B, int S, int H, int dh,
                        void* out, float* lse, void* stream);
-int b4cp_attention_bwd(const void* qkv, const void* dout, const float* lse,
+/* backward: `out` is the forward output (bf16 [B*S][d]); the tensor-core path for 128 < S <= 256
+ * takes delta = rowsum(dO o O) from it (may be NULL: the SIMT kernel is used for such S then). */
+int b4cp_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse,
                        const int32_t* ids_first, int B, int S, int H, int dh, void* dqkv,
                        void* stream);
 

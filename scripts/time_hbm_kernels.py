@@ -1,7 +1,8 @@
 """HBM-roofline check of the memory-bound kernels: embedding gather, its sorted
 scatter-add backward, top-k over materialised scores, Adam, residual+LayerNorm.
-Each iteration is timed on its own with CUDA events after an L2 flush (a 512 MB buffer is
-rewritten); achieved = ALGORITHMIC bytes / median time, against MEASURED_PEAKS.json hbm_gbs.
+Each measurement replays a CUDA graph of the kernel(s) after an L2 flush (a 512 MB buffer is
+rewritten), timed with CUDA events; achieved = ALGORITHMIC bytes / median time, against
+MEASURED_PEAKS.json hbm_gbs.
 Prints one JSON line per kernel/shape."""
 import json, os, sys
 import numpy as np
@@ -13,17 +14,27 @@ PEAK = json.load(open("MEASURED_PEAKS.json"))["hbm_gbs"] if os.path.exists("MEAS
 flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
 
 
-def timed(fn, iters=7):
-    for _ in range(2):
-        fn()
+def timed(fn, iters=7, sets=1):
+    """fn(j) launches the kernel(s) on buffer set j.  All `sets` calls are captured in ONE CUDA
+    graph (no host launch gaps inside the timed region: several of these kernels run for tens of
+    microseconds, less than a ctypes call); the graph is replayed after an L2 flush and the time
+    is divided by `sets`.  With sets > 1 the buffer sets together exceed L2 as well."""
+    for j in range(sets):
+        fn(j)                      # eager warm-up: workspaces are allocated outside the capture
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        for j in range(sets):
+            fn(j)
+    graph.replay()
     ts = []
     for _ in range(iters):
         flush.zero_()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); fn(); e1.record()
+        e0.record(); graph.replay(); e1.record()
         torch.cuda.synchronize()
-        ts.append(e0.elapsed_time(e1))
+        ts.append(e0.elapsed_time(e1) / sets)
     return float(np.median(ts))
 
 
@@ -46,25 +57,27 @@ for name, B, S, V, d in (("C1", 16384, 52, 54293, 64), ("C4", 1024, 202, 1_000_0
     table = (torch.rand(rows, d, device="cuda") - 0.5) * 0.1
     pe = torch.randn(S, d, device="cuda")
     ids = zipf_ids(B * S, V, 0.8, g)
-    out = torch.empty(B * S, d, device="cuda")
-    ms = timed(lambda: ops.embed_fwd([ids], [table], pe, B, S, out_f32=out))
+    NS = 4
+    outs = [torch.empty(B * S, d, device="cuda") for _ in range(NS)]
+    idss = [ids] + [zipf_ids(B * S, V, 0.8, g) for _ in range(NS - 1)]
+    ms = timed(lambda j: ops.embed_fwd([idss[j]], [table], pe, B, S, out_f32=outs[j]), sets=NS)
     report("embed_fwd_kernel", f"{name}: B={B} S={S} d={d} V={V}", B * S * (8 * d + 4), ms)
-    dout = torch.randn(B * S, d, device="cuda")
+    douts = outs
+    for o in douts:
+        o.normal_()
     tg = torch.empty(rows, d, device="cuda")
-    nu = torch.zeros(1, dtype=torch.int32, device="cuda")
-    uq = torch.empty(B * S, dtype=torch.int32, device="cuda")
-    ms = timed(lambda: ops.embed_bwd(dout, d, 0, d, ids, rows, tg, uniq_ids=uq, n_unique=nu))
-    U = int(nu.item())
+    ms = timed(lambda j: ops.embed_bwd(douts[j], d, 0, d, idss[j], rows, tg), sets=NS)
+    U = int(torch.unique(ids).numel())
     alg = B * S * d * 4 + B * S * 4 + U * d * 4 + U * 4
     report("embed_bwd (radix sort + segment sums + table zero-fill)", f"{name}: N={B*S} U={U} d={d} rows={rows}",
            alg, ms, bytes_incl_dense_zero_fill=int(alg + rows * d * 4),
            frac_incl_zero_fill=round((alg + rows * d * 4) / (ms * 1e-3) / 1e9 / PEAK, 3))
-    del table, out, dout, tg
+    del table, outs, douts, tg
 
 for B, V, k in ((1184, 1_000_000, 100), (9472, 54293, 100), (1184, 1_000_000, 10)):  # whole waves of 2 CTAs x 148 SMs
     sc = torch.randn(B, ops.ld8(V), device="cuda")
     ids_o = torch.empty(B, k, dtype=torch.int32, device="cuda")
-    ms = timed(lambda: ops.topk_rows(sc, V, k, out_ids=ids_o))
+    ms = timed(lambda j: ops.topk_rows(sc, V, k, out_ids=ids_o))
     report("topk_rows_kernel", f"B={B} V={V} k={k}", B * V * 4 + B * k * 8, ms)
     del sc
 
@@ -72,7 +85,7 @@ n = 256 * 1_000_000 // 4
 theta, grad, m, v = (torch.randn(n, device="cuda") for _ in range(4))
 v.abs_()
 step = torch.zeros(1, dtype=torch.int32, device="cuda")
-ms = timed(lambda: ops.adam_step(theta, grad, m, v, lr=1e-3, step_dev=step))
+ms = timed(lambda j: ops.adam_step(theta, grad, m, v, lr=1e-3, step_dev=step))
 report("adam_kernel", f"n={n} (no bf16 shadow)", n * 28, ms)
 del theta, grad, m, v
 
@@ -80,5 +93,5 @@ for rows_, d in ((16384 * 52, 64), (1024 * 202, 256)):
     x, r = torch.randn(rows_, d, device="cuda"), torch.randn(rows_, d, device="cuda")
     gam, bet = torch.ones(d, device="cuda"), torch.zeros(d, device="cuda")
     y, yb = torch.empty(rows_, d, device="cuda"), torch.empty(rows_, d, device="cuda", dtype=torch.bfloat16)
-    ms = timed(lambda: ops.residual_ln_fwd(x, r, gam, bet, y, yb))
+    ms = timed(lambda j: ops.residual_ln_fwd(x, r, gam, bet, y, yb))
     report("residual_ln_fwd_kernel", f"rows={rows_} d={d}", rows_ * d * 14, ms)

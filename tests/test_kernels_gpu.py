@@ -191,6 +191,7 @@ def test_embed_bwd_sorted_scatter_add(cuda_lib, B, S, rows):
 
 # ------------------------------------------------------------------------------- attention
 @pytest.mark.parametrize("B,S,H,dh", [(4, 53, 2, 32), (3, 5, 1, 8), (2, 103, 4, 32), (2, 203, 4, 64),
+                                      (3, 202, 2, 32), (2, 256, 1, 64), (2, 129, 2, 32),
                                       (2, 114, 2, 64)])
 def test_attention_fwd_bwd(cuda_lib, B, S, H, dh):
     from bert4clickpath_b200 import ops
@@ -208,7 +209,8 @@ def test_attention_fwd_bwd(cuda_lib, B, S, H, dh):
     lse = torch.empty((B, H, S), device="cuda")
     ops.attention_fwd(qkv, dev(ids), B, S, H, dh, out, lse)
     dqkv = torch.empty((B * S, 3 * d), dtype=torch.bfloat16, device="cuda")
-    ops.attention_bwd(qkv, dev(do.reshape(B * S, d), torch.bfloat16), lse, dev(ids), B, S, H, dh, dqkv)
+    ops.attention_bwd(qkv, dev(do.reshape(B * S, d), torch.bfloat16), lse, dev(ids), B, S, H, dh, dqkv,
+                      out=out)
     torch.cuda.synchronize()
     # bf16 outputs: 2^-8 relative rounding on top of fp32 math
     np.testing.assert_allclose(out.float().cpu().numpy().reshape(B, S, d), o, rtol=1e-2, atol=1e-2)
