@@ -360,6 +360,23 @@ extern "C" int b4cp_topk_rows(const float* scores, long ld, long rows, int V, in
   return 0;
 }
 
+/* b4cp_topk_candidates for the rows marked for a redo only (out_ids[row][0] == -2): the fallback
+ * leg of the long-vocabulary path of b4cp_score_topk; other rows keep their results. */
+extern "C" int b4cp_topk_candidates_redo(const float* cand_scores, const int32_t* cand_ids, long ld,
+                                         long rows, int n_cand, int V, int k, int32_t* out_ids,
+                                         float* out_scores, long ld_out, void* stream) {
+  B4CP_CHECK_ARG(k >= 1 && k <= TK_MAXK, "topk: k=%d must be in [1,%d]", k, TK_MAXK);
+  B4CP_CHECK_ARG(cand_scores && cand_ids && out_ids, "topk_candidates: null argument");
+  if (rows == 0) return 0;
+  int idbits = 1;
+  while ((1L << idbits) < V) ++idbits;
+  topk_rows_kernel<<<(unsigned)rows, TK_THREADS, 0, (cudaStream_t)stream>>>(
+      cand_scores, cand_ids, ld, n_cand, k, idbits, out_ids, out_scores, ld_out, 1);
+  note_launches(1);
+  B4CP_LAUNCH_CHECK();
+  return 0;
+}
+
 /* top-k over explicit (score, id) candidate lists: row r ranks cand_scores[r*ld .. +n_cand) whose
  * ids are cand_ids[...] (negative = empty).  Same order as b4cp_topk_rows; ids < V. */
 extern "C" int b4cp_topk_candidates(const float* cand_scores, const int32_t* cand_ids, long ld,

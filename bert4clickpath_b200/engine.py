@@ -471,12 +471,18 @@ class VocabOutputEngine:
         if db_parts is not None:
             ops.reduce_splits(db_parts, self.b.g)
 
+    FUSED_TOPK_MAX_V = 262144
+
     def topk(self, ab, M, k):
-        """(M, k) int32 ids of the k highest scores per row, ties -> lower id.  Fused scoring +
-        heap top-k on the tensor cores when the head width allows it (scores never reach HBM),
-        otherwise logits materialised for a bounded row range at a time + radix-select top-k."""
+        """(M, k) int32 ids of the k highest scores per row, ties -> lower id.
+        V < 262144: fused scoring + per-row heaps on the tensor cores (scores never reach HBM).
+        Longer vocabularies (C5: 1M items): logits materialised for a bounded row range at a time
+        + the single-pass streaming top-k, which measures faster there (~500k queries/s at V = 1M,
+        h = 256) than both the heap kernel (~100k) and the library's seed + filter + merge path
+        (~380k, `b4cp_score_topk` above 262144 entries; set `prefer_fused_topk` to use it)."""
         ids = self.pool.get(f"topk{k}", (M, k), I32)
-        if self.h in (64, 128) and k <= 104 and not self.force_materialized:
+        fused_ok = self.h in (64, 128, 256) and k <= 104 and not self.force_materialized
+        if fused_ok and (self.V < self.FUSED_TOPK_MAX_V or self.prefer_fused_topk):
             t0 = ops.TIMER.begin("score_topk")
             ops.score_topk(ab, M, self.h, self.W.wb, self.b.w, self.V, k, out_ids=ids)
             ops.TIMER.end("score_topk", t0)
@@ -485,6 +491,8 @@ class VocabOutputEngine:
             z = self.logits(ab, M, (a, b))
             ops.topk_rows(z, self.V, k, out_ids=ids[a:b])
         return ids
+
+    prefer_fused_topk = False
 
 
 class VocabParallelOutputEngine(VocabOutputEngine):

@@ -240,9 +240,17 @@ int b4cp_topk_rows(const float* scores, long ld, long rows, int V, int k, int32_
 int b4cp_topk_candidates(const float* cand_scores, const int32_t* cand_ids, long ld, long rows,
                          int n_cand, int V, int k, int32_t* out_ids, float* out_scores,
                          long ld_out, void* stream);
+/* b4cp_topk_candidates restricted to the rows whose out_ids[row][0] == -2 (redo marker) */
+int b4cp_topk_candidates_redo(const float* cand_scores, const int32_t* cand_ids, long ld, long rows,
+                              int n_cand, int V, int k, int32_t* out_ids, float* out_scores,
+                              long ld_out, void* stream);
 /* FUSED inference scoring + top-k: ranks x W + b over the whole vocabulary without writing the
  * (M x V) scores (head.py:36,45 + examples/BERT4Rec/source/utils.py:176,:245).  x_bf16: bf16
- * [M][ldx]; w_bf16: bf16 [h][ldw] Keras kernel; h in {64,128}; k <= 104.  Exact, ties -> lower id. */
+ * [M][ldx]; w_bf16: bf16 [h][ldw] Keras kernel; h in {64,128,256}; k <= 104.  Exact, ties -> lower
+ * id.  V < 262144: per-row heaps in shared memory; longer vocabularies: the first 65536 entries
+ * are ranked to give every row a threshold, the tcgen05 product over the rest appends the scores
+ * above it to per-row lists, and an exact merge finishes (rows whose list overflows are redone by
+ * the heap kernel). */
 long b4cp_score_topk_workspace_bytes(long M, int V, int k);
 /* id_base is added to every reported id and V_total (0 = V) bounds the reported ids: a vocabulary
  * shard [id_base, id_base + V) of a V_total-wide output layer reports global ids */

@@ -145,7 +145,8 @@ def test_fused_all_rows_padded(cuda_lib, h):
 
 # ------------------------------------------------------------------ fused scoring + top-k
 @pytest.mark.parametrize("M,h,V,k", [(5, 128, 54293, 100), (300, 128, 5000, 10), (1, 64, 1237, 5),
-                                     (130, 128, 200, 100), (700, 128, 100000, 100)])
+                                     (130, 128, 200, 100), (700, 128, 100000, 100),
+                                     (300, 256, 5000, 10), (131, 256, 100000, 100), (2, 256, 300, 104)])
 def test_fused_score_topk_is_exact(cuda_lib, M, h, V, k):
     """ids bit-exact against the oracle's tf.math.top_k order applied to the same tensor-core
     scores, including exact ties across tiles and vocabulary chunks (duplicated W columns)."""
@@ -169,6 +170,37 @@ def test_fused_score_topk_is_exact(cuda_lib, M, h, V, k):
     # and the materialised top-k kernel agrees
     ids2, _ = ops.topk_rows(logits, V, k)
     assert torch.equal(ids, ids2)
+
+
+@pytest.mark.parametrize("M,h,V,k,adversarial", [(131, 256, 300000, 100, False), (300, 128, 400003, 10, False),
+                                                 (70, 128, 280000, 100, True)])
+def test_fused_score_topk_long_vocabulary(cuda_lib, M, h, V, k, adversarial):
+    """V >= 262144: seed (first 65536 entries ranked exactly) + threshold filter in the tcgen05
+    epilogue + exact merge.  `adversarial`: scores grow along the vocabulary, every later entry
+    beats the seed threshold, the candidate lists overflow and the rows are redone by the heap
+    kernel behind the device-side flag.  Ids are exact either way (ties included)."""
+    from bert4clickpath_b200 import ops
+    x, w, b, _ = make(M, h, V, 17 * M + V)
+    w[:, V // 2:] = w[:, (np.arange(V - V // 2) % 101)]      # exact ties across seed / rest
+    b[V // 2:] = b[np.arange(V - V // 2) % 101]
+    if adversarial:
+        b = (b + np.linspace(0.0, 40.0, V)).astype(np.float32)
+    labels = np.zeros(M, dtype=np.int32)
+    xb, wb, bd, _ = to_dev(x, w, b, labels)
+    ids, scores = ops.score_topk(xb, M, h, wb, bd, V, k, out_scores=torch.empty((M, k), device="cuda"))
+    torch.cuda.synchronize()
+    got = ids.cpu().numpy()
+    want = np.empty((M, k), dtype=np.int64)
+    sc_want = np.empty((M, k), dtype=np.float32)
+    for a in range(0, M, 64):                                  # bounded logits on the device
+        rows = min(64, M - a)
+        logits = torch.empty((rows, ops.ld8(V)), device="cuda")
+        ops.gemm(xb[a:a + rows], 0, wb, 1, rows, V, h, bias=bd, out_f32=logits)
+        z = logits.cpu().numpy()[:, :V]
+        want[a:a + rows] = O.top_k_ids(z, k)
+        sc_want[a:a + rows] = np.take_along_axis(z, want[a:a + rows], 1)
+    assert got.tolist() == want.tolist()
+    np.testing.assert_array_equal(scores.cpu().numpy(), sc_want)
 
 
 # ------------------------------------------------------------------ vocabulary-parallel pieces
