@@ -293,6 +293,53 @@ def c4_vocab_stage(pk, iters=6):
     return out
 
 
+# ------------------------------------------------------------------ C5 next-item top-k (kernel leg)
+def c5_topk(pk, B=4096, iters=5):
+    """top-100 over a 1,000,000-item catalogue from 256-wide hidden states (scoring
+    + exact top-k only; the encoder is the C4 one).  Path = what `VocabOutputEngine.topk` runs
+    above 262,144 entries: logits materialised for 2,048 rows at a time (tcgen05 GEMM, fp32) + the
+    single-pass streaming top-k.  HBM-bound: every score is written once and read once."""
+    import torch
+    from bert4clickpath_b200 import ops
+    V, h, k, RC = 1_000_000, 256, 100, 2048
+    g = torch.Generator(device="cuda").manual_seed(11)
+    wb = torch.zeros(h, ops.ld8(V), device="cuda", dtype=torch.bfloat16)
+    wb[:, :V] = (torch.randn(h, V, device="cuda", generator=g) * 0.05).to(torch.bfloat16)
+    bias = torch.zeros(V, device="cuda")
+    xb = (torch.randn(B, h, device="cuda", generator=g) * 0.5).to(torch.bfloat16)
+    ids = torch.empty(B, k, dtype=torch.int32, device="cuda")
+    z = torch.empty(RC, ops.ld8(V), device="cuda")
+
+    def run():
+        for a in range(0, B, RC):
+            rows = min(RC, B - a)
+            ops.gemm(xb[a:a + rows], 0, wb, 1, rows, V, h, bias=bias, out_f32=z[:rows])
+            ops.topk_rows(z[:rows], V, k, out_ids=ids[a:a + rows])
+
+    for _ in range(2):
+        run()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        run()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    nbytes = 2.0 * B * V * 4 + V * h * 2 * (B / RC) + B * k * 4
+    out = {"workload": f"C5 next-item top-{k}: V={V}, h={h}, {B} queries per call (scoring + top-k)",
+           "value": B / (ms * 1e-3), "unit": "queries/s", "ms_per_call": ms, "bound": "hbm",
+           "achieved": nbytes / (ms * 1e-3) / 1e9, "peak": pk["hbm"], "roofline_unit": "GB/s",
+           "frac": nbytes / (ms * 1e-3) / 1e9 / pk["hbm"],
+           "algorithmic_bytes": nbytes,
+           "note": "bytes = scores written once + read once (fp32) + W per 2048-row range + ids; the "
+                   "fused alternative b4cp_score_topk (scores never in HBM) measures 0.38M queries/s "
+                   "at this shape and is used below 262,144 entries"}
+    del wb, z
+    torch.cuda.empty_cache()
+    return out
+
+
 # ------------------------------------------------------------------------------------- ours
 def run_ours(args, rank, world, local_rank):
     import torch
@@ -421,9 +468,10 @@ def run_ours(args, rank, world, local_rank):
                 "includes": "encoder forward + head MLP + fused scoring/top-k + recall/NDCG counters",
                 "recall_at_k": float(c[0] / max(c[2], 1)), "ndcg_at_k": float(c[1] / max(c[2], 1))}
 
-    c4 = None
+    c4 = c5 = None
     if world == 1 and not args.no_c4:
         c4 = c4_vocab_stage(peaks())
+        c5 = c5_topk(peaks())
 
     # Captured CUDA graphs hold NCCL kernels: drop them and quiesce BEFORE any teardown, and leave
     # through os._exit so that no destructor (process group, graph pool) can block the launcher.
@@ -496,6 +544,7 @@ def run_ours(args, rank, world, local_rank):
         "cpu_baseline": cpu_base,
         "topk": topk,
         "c4_vocab_stage": c4,
+        "c5_topk": c5,
         "loss": float(loss_stats[0] / max(loss_stats[1], 1.0)), "e2e_last_loss": loss,
     }
     print(json.dumps(line), flush=True)
@@ -512,7 +561,7 @@ def main():
     ap.add_argument("--batch", type=int, default=4096, help="per-GPU batch (sequences)")
     ap.add_argument("--cpu-batch", type=int, default=64, help="batch of the CPU reference sample")
     ap.add_argument("--no-topk", action="store_true", help="skip the top-k inference leg")
-    ap.add_argument("--no-c4", action="store_true", help="skip the C4 (V=1M, h=256) vocabulary-stage leg")
+    ap.add_argument("--no-c4", action="store_true", help="skip the C4 / C5 (V=1M, h=256) kernel legs")
     ap.add_argument("--max-seconds", type=int, default=1200, help="watchdog: hard exit after this long")
     args = ap.parse_args()
     arm_watchdog(args.max_seconds)
