@@ -313,14 +313,75 @@ class ClickstreamTransformer:
         self._last_labels = labels
         return stats
 
+    def binary_forward_backward(self, ids_list, y_f32, B, S, segment_bounds, pos_weight=None,
+                                label_pad=LABEL_PAD, training=True, seed=0):
+        """Segment mode with a BinaryClassificationHead (purchase intention / return prediction,
+        SURVEY.md C3): encoder -> rows of segment `segment_to_head` (clickstream_transformer.py:
+        317-322) -> ReLU MLP -> Dense(1, sigmoid) (head.py:4-26) -> MaskedLoss(binary_crossentropy,
+        pos_weight) (losses.py:31-98), and the whole backward.  y_f32: (B, segment length) float32
+        padded with label_pad.  Gradients land in store.flat_g; returns loss_stats = (sum of item
+        losses, valid items), all-reduced when a process group is set."""
+        from .head import BinaryClassificationHead
+        assert isinstance(self.head, BinaryClassificationHead) and self.segment_to_head is not None
+        x = self._encode(ids_list, B, S, training, seed)
+        starts, ends = segment_bounds
+        s0, s1 = int(starts[self.segment_to_head]), int(ends[self.segment_to_head])
+        Ls = s1 - s0
+        M = B * Ls
+        key = (B, S, s0, s1)
+        if getattr(self, "_seg_rows_key", None) != key:
+            idx = (np.arange(B, dtype=np.int64)[:, None] * S + np.arange(s0, s1)[None, :]).reshape(-1)
+            self._seg_rows = torch.from_numpy(idx.astype(np.int32)).cuda()
+            self._seg_rows_key = key
+        row_index = self._seg_rows
+        d = self.d_model
+        hsel = self.pool.get("hsel_bin", (M, ld8(d)), BF16)
+        ops.gather_rows(x, row_index, None, hsel)
+        head = self.head
+        z, ab = head.logits(hsel, M)
+        probs = ops.sigmoid(z.view(-1))
+        y = y_f32.reshape(-1).contiguous()
+        assert y.numel() == M, "labels must be (B, segment length)"
+        stats = ops.masked_bce(y, probs, label_pad, pos_weight)
+        self._allreduce(stats)
+        W, b = self.store[f"{head.prefix}.out.w"], self.store[f"{head.prefix}.out.b"]
+        dz = self.pool.get("dz_bin", (M,))
+        dsel = self.pool.get("dsel_bin", (M, d))
+        mlp = head.mlp
+        if mlp.dims:
+            dab = self.pool.get("dab_bin", (M, ld8(mlp.out_dim)), BF16)
+            ops.binary_head_bwd(y, probs, label_pad, pos_weight, stats, ab, head.h, W.w, True, dz,
+                                dab_bf16=dab, dw=W.g, db=b.g)
+            mlp.backward(dab, dsel)
+        else:
+            ops.binary_head_bwd(y, probs, label_pad, pos_weight, stats, ab, head.h, W.w, False, dz,
+                                dab_f32=dsel, dw=W.g, db=b.g)
+        dx = self.pool.get("dx_top", (B * S, d), zero=True)
+        ops.scatter_rows(dsel, row_index, dx)
+        self.transformer.engine.backward(dx)
+        for run in self.store.replicated_grad_runs():
+            self._allreduce(run)
+        self._last_probs = probs.view(B, Ls)
+        return stats
+
     def train_step(self, data, n_masked=None):
         """Keras Model.train_step: data = (inputs dict, labels (B, max_n_masked) float32).
         Returns {'loss': float} (+ metric results)."""
         inputs, y = data
-        ids_list, B, S, _, _ = self.prepare_inputs(inputs)
+        ids_list, B, S, starts, ends = self.prepare_inputs(inputs)
         y = torch.as_tensor(np.ascontiguousarray(y, dtype=np.float32)) if not torch.is_tensor(y) else y
         n_host = int((y != LABEL_PAD).sum().item())
         y = y.to(device="cuda", dtype=F32).contiguous()
+        from .head import BinaryClassificationHead
+        if isinstance(self.head, BinaryClassificationHead) and self.segment_to_head is not None:
+            pw = getattr(self.loss, "pos_weight", None)
+            stats = self.binary_forward_backward(ids_list, y, B, S, (starts, ends), pos_weight=pw,
+                                                 seed=self._next_seed())
+            opt = self.optimizer or Adam()
+            self.store.adam(opt.learning_rate, opt.beta_1, opt.beta_2, opt.epsilon)
+            s = stats.cpu().numpy()
+            mean = float(s[0] / s[1]) if s[1] > 0 else 0.0
+            return {'loss': mean / ((pw + 1.0) / 2) if pw is not None else mean}
         stats = self.cloze_forward_backward(ids_list, y, B, S, n_masked=n_host,
                                             seed=self._next_seed())
         opt = self.optimizer or Adam()

@@ -357,6 +357,105 @@ extern "C" int b4cp_clip_log(const float* p, float* out, long n, float lo, float
   return 0;
 }
 
+namespace b4cp {
+// ---- backward of BinaryClassificationHead's Dense(1, sigmoid) + MaskedLoss(binary_crossentropy)
+// (head.py:11,24-26; losses.py:31-98 with K.binary_crossentropy on probabilities):
+//   l_i = -w_i (y log(pc + e) + (1 - y) log(1 - pc + e)),  pc = clip(p, e, 1 - e),  e = 1e-7,
+//   w_i = pos_weight where y == 1 (if given), loss = sum l_i / n over labels != label_pad,
+//   divided by (pos_weight + 1) / 2 when pos_weight is given (losses.py:94-96).
+// dz_i = dl/dp * p (1 - p) / n (the clip passes a gradient only strictly inside (e, 1 - e)).
+__global__ void __launch_bounds__(256)
+binary_head_dz_kernel(const float* __restrict__ y_true, const float* __restrict__ p, long n,
+                      float label_pad, float pos_weight, int use_pos_weight,
+                      const float* __restrict__ stats, float* __restrict__ dz) {
+  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float eps = 1e-7f;
+  const float nv = stats[1];
+  const float yt = y_true[i];
+  float g = 0.f;
+  if (yt != label_pad && nv > 0.f) {
+    const float pi = p[i];
+    if (pi > eps && pi < 1.f - eps) {
+      float dl = -(yt / (pi + eps) - (1.f - yt) / (1.f - pi + eps));
+      if (use_pos_weight && yt == 1.f) dl *= pos_weight;
+      g = dl * pi * (1.f - pi) / nv;
+      // MaskedLoss divides the weighted mean by (pos_weight + negative_weight) / 2 (losses.py:94-96)
+      if (use_pos_weight) g *= 2.f / (pos_weight + 1.f);
+    }
+  }
+  dz[i] = g;
+}
+
+// d_ab[i][c] = dz_i * w[c] (zeroed where the ReLU output ab[i][c] <= 0 when `gated`)
+__global__ void __launch_bounds__(256)
+binary_head_dx_kernel(const float* __restrict__ dz, const float* __restrict__ w, long M, int h,
+                      const __nv_bfloat16* __restrict__ ab, long ld_ab, int gated,
+                      float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16, long ld_bf16) {
+  const long idx = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (idx >= M * h) return;
+  const long i = idx / h;
+  const int c = (int)(idx - i * h);
+  float v = dz[i] * w[c];
+  if (gated && !(__bfloat162float(ab[i * ld_ab + c]) > 0.f)) v = 0.f;
+  if (out_f32) out_f32[i * h + c] = v;
+  if (out_bf16) out_bf16[i * ld_bf16 + c] = __float2bfloat16_rn(v);
+}
+
+// dw[c] = sum_i ab[i][c] dz_i, db = sum_i dz_i: one block per 32 columns, warps stride the rows,
+// the 8 warp partials are added in order (deterministic)
+__global__ void __launch_bounds__(256)
+binary_head_dw_kernel(const float* __restrict__ dz, const __nv_bfloat16* __restrict__ ab, long ld_ab,
+                      long M, int h, float* __restrict__ dw, float* __restrict__ db) {
+  __shared__ float part[8][33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
+  float acc = 0.f, accb = 0.f;
+  for (long i = warp; i < M; i += 8) {
+    const float g = dz[i];
+    if (c < h) acc += __bfloat162float(ab[i * ld_ab + c]) * g;
+    if (blockIdx.x == 0 && lane == 0) accb += g;
+  }
+  part[warp][lane] = acc;
+  if (lane == 0) part[warp][32] = accb;
+  __syncthreads();
+  if (warp == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += part[k][lane];
+    if (c < h) dw[c] = t;
+    if (blockIdx.x == 0 && lane == 0) {
+      float tb = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) tb += part[k][32];
+      *db = tb;
+    }
+  }
+}
+}  // namespace b4cp
+
+extern "C" int b4cp_binary_head_bwd(const float* y_true, const float* probs, long M, float label_pad,
+                                    float pos_weight, int use_pos_weight, const float* stats,
+                                    const void* ab_bf16, long ld_ab, int h, const float* w_out,
+                                    int gated, float* dz, float* dab_f32, void* dab_bf16,
+                                    long ld_dab, float* dw, float* db, void* stream) {
+  B4CP_CHECK_ARG(y_true && probs && stats && ab_bf16 && w_out && dz && dw && db && (dab_f32 || dab_bf16),
+                 "binary_head_bwd: null argument");
+  B4CP_CHECK_ARG(h >= 1, "binary_head_bwd: h=%d", h);
+  if (M == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  binary_head_dz_kernel<<<ceil_div(M, 256), 256, 0, st>>>(y_true, probs, M, label_pad, pos_weight,
+                                                          use_pos_weight, stats, dz);
+  binary_head_dx_kernel<<<ceil_div(M * h, 256), 256, 0, st>>>(
+      dz, w_out, M, h, (const __nv_bfloat16*)ab_bf16, ld_ab, gated, dab_f32,
+      (__nv_bfloat16*)dab_bf16, ld_dab);
+  binary_head_dw_kernel<<<ceil_div(h, 32), 256, 0, st>>>(dz, (const __nv_bfloat16*)ab_bf16, ld_ab, M,
+                                                         h, dw, db);
+  note_launches(3);
+  B4CP_LAUNCH_CHECK();
+  return 0;
+}
+
 extern "C" int b4cp_masked_bce(const float* y_true, const float* probs, long n, float label_pad,
                                float pos_weight, int use_pos_weight, float* stats, void* stream) {
   masked_bce_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(y_true, probs, n, label_pad, pos_weight,

@@ -360,6 +360,18 @@ def masked_bce(y_true, probs, label_pad, pos_weight=None):
     return stats
 
 
+def binary_head_bwd(y_true, probs, label_pad, pos_weight, stats, ab, h, w_out, gated, dz,
+                    dab_f32=None, dab_bf16=None, dw=None, db=None):
+    """Backward of Dense(1, sigmoid) + MaskedLoss(binary_crossentropy) (head.py:11, losses.py:31-98)."""
+    M = y_true.numel()
+    L.call("b4cp_binary_head_bwd", L.ptr(y_true), L.ptr(probs), L.c_long(M), L.c_float(label_pad),
+           L.c_float(pos_weight if pos_weight is not None else 1.0),
+           L.c_int(0 if pos_weight is None else 1), L.ptr(stats), L.ptr(ab), L.c_long(ab.stride(0)),
+           L.c_int(h), L.ptr(w_out), L.c_int(1 if gated else 0), L.ptr(dz), L.ptr(dab_f32),
+           L.ptr(dab_bf16), L.c_long(dab_bf16.stride(0) if dab_bf16 is not None else 0), L.ptr(dw),
+           L.ptr(db), L.stream_ptr())
+
+
 def _vocab_ws(M, V, h):
     fn = L.lib().b4cp_vocab_ce_workspace_bytes
     fn.restype = ctypes.c_long

@@ -223,6 +223,17 @@ int b4cp_clip_log(const float* p, float* out, long n, float lo, float hi, void* 
  * stats[0] = sum of weighted item losses over labels != label_pad, stats[1] = their count */
 int b4cp_masked_bce(const float* y_true, const float* probs, long n, float label_pad,
                     float pos_weight, int use_pos_weight, float* stats, void* stream);
+/* Backward of BinaryClassificationHead's Dense(1, sigmoid) + MaskedLoss(binary_crossentropy,
+ * pos_weight) (head.py:11,24-26; losses.py:31-98): y_true / probs [M] (one logit per item),
+ * stats = b4cp_masked_bce's (sum, n) (n may already be the global count).  ab: bf16 [M][ld_ab]
+ * input of the Dense(1) (ReLU output of the head MLP -> gated = 1, or the encoder rows), w_out:
+ * fp32 [h] its kernel.  Writes dz [M], d(loss)/d(ab) as fp32 [M][h] and/or bf16 [M][ld_dab],
+ * dw [h], db [1].  Deterministic. */
+int b4cp_binary_head_bwd(const float* y_true, const float* probs, long M, float label_pad,
+                         float pos_weight, int use_pos_weight, const float* stats,
+                         const void* ab_bf16, long ld_ab, int h, const float* w_out, int gated,
+                         float* dz, float* dab_f32, void* dab_bf16, long ld_dab, float* dw,
+                         float* db, void* stream);
 
 /* sigmoid output activation of BinaryClassificationHead / MultiLabel_MultiClass_classification
  * (head.py:11, :57) */

@@ -302,6 +302,77 @@ def test_multivariable_segment_head_forward_matches_oracle(cuda_lib, segment):
     assert abs(loss - want_loss) < 1e-4 * abs(want_loss)
 
 
+@pytest.mark.parametrize("segment,dims", [(0, [32, 16]), (2, [32, 16]), (2, [])])
+def test_binary_head_training_matches_autograd(cuda_lib, segment, dims):
+    """C3 training path (segment mode + BinaryClassificationHead + MaskedLoss(binary_crossentropy,
+    pos_weight), head.py:4-26, losses.py:31-98): loss and every head gradient against torch
+    autograd (float64, bf16 rounding at the points where the pipeline stores bf16) on the same
+    encoder output; encoder gradients finite and non-zero; Adam steps reduce the loss."""
+    import bert4clickpath_b200 as bc
+    rng = np.random.default_rng(11 + segment)
+    items_vocab = [f"it{j}" for j in range(60)]
+    ev_vocab = [f"ev{j}" for j in range(7)]
+    B, L1, L2, pw = 37, 9, 4, 3.0
+    def draw(vocab, L):
+        a = rng.choice(vocab, size=(B, L)).astype(object)
+        for b in range(B):
+            a[b, rng.integers(1, L + 1):] = "[PAD]"
+        return a
+    feats = {"s_items": draw(items_vocab, L1), "b_items": draw(items_vocab, L2)}
+    feats["s_ev"] = np.where(feats["s_items"] == "[PAD]", "[PAD]", rng.choice(ev_vocab, size=(B, L1)).astype(object))
+    feats["b_ev"] = np.where(feats["b_items"] == "[PAD]", "[PAD]", rng.choice(ev_vocab, size=(B, L2)).astype(object))
+    head = bc.BinaryClassificationHead(dense_layer_dims=dims)
+    model = bc.ClickstreamTransformer(
+        sequential_input_config={"items": ["s_items", "b_items"], "events": ["s_ev", "b_ev"]},
+        feature_vocabs={"items": items_vocab, "events": ev_vocab},
+        embedding_dims={"items": 24, "events": 8}, head_unit=head, segment_to_head=segment,
+        num_encoder_layers=1, num_attention_heads=4, dropout_rate=0.0, seed=5)
+    ids_list, Bq, S, starts, ends = model.prepare_inputs(feats)
+    s0, s1 = int(starts[segment]), int(ends[segment])
+    Ls = s1 - s0
+    y = rng.integers(0, 2, size=(B, Ls)).astype(np.float32)
+    if segment == 2:
+        y[feats["b_items"] == "[PAD]"] = -1.0
+    yd = torch.from_numpy(y).cuda()
+    stats = model.binary_forward_backward(ids_list, yd, B, S, (starts, ends), pos_weight=pw,
+                                          training=False).cpu().numpy()
+    grads = model.store.get_grads()
+    Wts = model.store.get_weights()
+    # ---- reference: torch autograd on the head, fed with the device's encoder output
+    x = model._encode(ids_list, B, S, False, 0).cpu().numpy().reshape(B, S, 32)
+    def q(t):  # straight-through bf16 rounding
+        return t + (t.detach().to(torch.bfloat16).to(torch.float64) - t.detach())
+    a = q(torch.from_numpy(x[:, s0:s1].reshape(B * Ls, 32).astype(np.float64)))
+    params = {}
+    for i in range(len(dims)):
+        params[f"head.{i}.w"] = torch.tensor(Wts[f"head.{i}.w"], dtype=torch.float64, requires_grad=True)
+        params[f"head.{i}.b"] = torch.tensor(Wts[f"head.{i}.b"], dtype=torch.float64, requires_grad=True)
+        a = q(torch.relu(a @ q(params[f"head.{i}.w"]) + params[f"head.{i}.b"]))
+    params["head.out.w"] = torch.tensor(Wts["head.out.w"], dtype=torch.float64, requires_grad=True)
+    params["head.out.b"] = torch.tensor(Wts["head.out.b"], dtype=torch.float64, requires_grad=True)
+    p = torch.sigmoid(a @ q(params["head.out.w"]) + params["head.out.b"]).reshape(-1)
+    yt = torch.from_numpy(y.reshape(-1).astype(np.float64))
+    valid = yt != -1.0
+    eps = 1e-7
+    pc = torch.clamp(p, eps, 1 - eps)
+    item = -(yt * torch.log(pc + eps) + (1 - yt) * torch.log(1 - pc + eps))
+    item = torch.where(yt == 1.0, item * pw, item)
+    loss = (item * valid).sum() / valid.sum() / ((pw + 1) / 2)
+    loss.backward()
+    got_loss = stats[0] / stats[1] / ((pw + 1) / 2)
+    assert stats[1] == float(valid.sum()) and abs(got_loss - loss.item()) < 2e-3 * abs(loss.item())
+    for k, t in params.items():
+        g, w = grads[k].astype(np.float64).reshape(t.shape), t.grad.numpy()
+        e = np.linalg.norm(g - w) / max(np.linalg.norm(w), 1e-12)
+        assert e < 3e-2, (k, e)
+    enc = [k for k in grads if not k.startswith("head.")]
+    assert all(np.isfinite(grads[k]).all() for k in enc) and any(np.abs(grads[k]).max() > 0 for k in enc)
+    # ---- Keras-style training: the loss goes down
+    model.compile(optimizer=bc.Adam(1e-2), loss=bc.MaskedLoss(bc.binary_crossentropy, pos_weight=pw))
+    losses = [model.train_step((feats, y))["loss"] for _ in range(12)]
+    assert losses[-1] < 0.8 * losses[0], losses
+
+
 def test_h256_vocabulary_stage_fused_and_in_bounded_row_ranges(cuda_lib):
     """C4 / C5 head width (h = 256, head [] -> V).  Default: the fused TS-form kernels (logits never
     in HBM).  The materialised fallback (`force_materialized`) holds logits for a bounded row range
