@@ -29,6 +29,10 @@ def __getattr__(name):
         "ClozeMaskedRecall": ".cloze",
         "ClozeMaskedNDCG": ".cloze",
         "cloze_output_adaptor": ".cloze",
+        "PositiveRate": ".metrics",
+        "PredictedPositives": ".metrics",
+        "F1Score": ".metrics",
+        "MaskedMetric": ".metrics",
     }
     if name in table:
         return getattr(importlib.import_module(table[name], __name__), name)

@@ -456,6 +456,50 @@ extern "C" int b4cp_binary_head_bwd(const float* y_true, const float* probs, lon
   return 0;
 }
 
+namespace b4cp {
+// counters += (sum mask, sum y*mask, sum round(p)*mask, tp, condition_true, predicted_true):
+// the accumulators of clickstream_transformer/metrics.py (PositiveRate :12-20, PredictedPositives
+// :36-45, F1Score :63-78).  mask = (y != label_pad); round = round-half-to-even (tf.round);
+// tp / condition_true / predicted_true follow F1Score literally: int32 casts, NO mask (a padded
+// label -1 is never "== 1", but a padded position still counts as predicted-true).
+__global__ void __launch_bounds__(1024)
+binary_metric_counts_kernel(const float* __restrict__ y_true, const float* __restrict__ p, long n,
+                            float label_pad, float* __restrict__ counters) {
+  __shared__ double sh[6][1024];
+  double a[6] = {0, 0, 0, 0, 0, 0};
+  for (long i = threadIdx.x; i < n; i += blockDim.x) {
+    const float yt = y_true[i];
+    const float m = yt != label_pad ? 1.f : 0.f;
+    const float pr = rintf(p[i]);
+    a[0] += m;
+    a[1] += yt * m;
+    a[2] += pr * m;
+    const bool ct = (int)yt == 1, pt = (int)pr == 1;
+    a[3] += (ct && pt) ? 1.0 : 0.0;
+    a[4] += ct ? 1.0 : 0.0;
+    a[5] += pt ? 1.0 : 0.0;
+  }
+  for (int j = 0; j < 6; ++j) sh[j][threadIdx.x] = a[j];
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o)
+      for (int j = 0; j < 6; ++j) sh[j][threadIdx.x] += sh[j][threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x < 6) counters[threadIdx.x] += (float)sh[threadIdx.x][0];
+}
+}  // namespace b4cp
+
+extern "C" int b4cp_binary_metric_counts(const float* y_true, const float* probs, long n,
+                                         float label_pad, float* counters, void* stream) {
+  B4CP_CHECK_ARG(y_true && probs && counters, "binary_metric_counts: null argument");
+  if (n == 0) return 0;
+  binary_metric_counts_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(y_true, probs, n, label_pad, counters);
+  note_launches(1);
+  B4CP_LAUNCH_CHECK();
+  return 0;
+}
+
 extern "C" int b4cp_masked_bce(const float* y_true, const float* probs, long n, float label_pad,
                                float pos_weight, int use_pos_weight, float* stats, void* stream) {
   masked_bce_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(y_true, probs, n, label_pad, pos_weight,

@@ -360,6 +360,11 @@ def masked_bce(y_true, probs, label_pad, pos_weight=None):
     return stats
 
 
+def binary_metric_counts(y_true, probs, label_pad, counters):
+    L.call("b4cp_binary_metric_counts", L.ptr(y_true), L.ptr(probs), L.c_long(y_true.numel()),
+           L.c_float(label_pad), L.ptr(counters), L.stream_ptr())
+
+
 def binary_head_bwd(y_true, probs, label_pad, pos_weight, stats, ab, h, w_out, gated, dz,
                     dab_f32=None, dab_bf16=None, dw=None, db=None):
     """Backward of Dense(1, sigmoid) + MaskedLoss(binary_crossentropy) (head.py:11, losses.py:31-98)."""

@@ -223,6 +223,11 @@ int b4cp_clip_log(const float* p, float* out, long n, float lo, float hi, void* 
  * stats[0] = sum of weighted item losses over labels != label_pad, stats[1] = their count */
 int b4cp_masked_bce(const float* y_true, const float* probs, long n, float label_pad,
                     float pos_weight, int use_pos_weight, float* stats, void* stream);
+/* Accumulators of clickstream_transformer/metrics.py: counters[0..5] += (sum mask, sum y*mask,
+ * sum round(p)*mask, tp, condition_true, predicted_true) with mask = (y != label_pad), tf.round
+ * (half to even) as the 0.5 threshold, and F1Score's unmasked int32 comparisons (metrics.py:63-78). */
+int b4cp_binary_metric_counts(const float* y_true, const float* probs, long n, float label_pad,
+                              float* counters, void* stream);
 /* Backward of BinaryClassificationHead's Dense(1, sigmoid) + MaskedLoss(binary_crossentropy,
  * pos_weight) (head.py:11,24-26; losses.py:31-98): y_true / probs [M] (one logit per item),
  * stats = b4cp_masked_bce's (sum, n) (n may already be the global count).  ab: bf16 [M][ld_ab]

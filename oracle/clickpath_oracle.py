@@ -545,3 +545,19 @@ def cloze_train_step(ids_list, labels, P, num_layers, num_heads, pe, dtype=np.fl
         G[f"emb.{f}"] = g
     extras = dict(logits=logits, hidden=h, enc_out=x, index=index, n_valid=n)
     return loss, G, extras
+
+
+# ------------------------------------------------------------------ binary-task metrics
+def binary_metric_counts(y_true, y_pred, label_pad=-1.0):
+    """Accumulators of clickstream_transformer/metrics.py as one vector:
+    (sum mask, sum y*mask [PositiveRate :12-20], sum round(p)*mask [PredictedPositives :36-45],
+    tp, condition_true, predicted_true [F1Score :63-78: int32 casts, no mask]).  tf.round rounds
+    half to even, as np.rint does."""
+    yt = np.asarray(y_true, dtype=np.float32).reshape(-1)
+    yp = np.asarray(y_pred, dtype=np.float32).reshape(-1)
+    mask = (yt != np.float32(label_pad)).astype(np.float32)
+    pr = np.rint(yp)
+    ct = yt.astype(np.int32) == 1
+    pt = pr.astype(np.int32) == 1
+    return np.array([mask.sum(), (yt * mask).sum(), (pr * mask).sum(), (ct & pt).sum(), ct.sum(), pt.sum()],
+                    dtype=np.float64)

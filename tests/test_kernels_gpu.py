@@ -415,3 +415,30 @@ def test_adam_matches_oracle_10_steps(cuda_lib):
     np.testing.assert_allclose(thd.cpu().numpy(), th64, rtol=1e-5, atol=1e-6)
     np.testing.assert_array_equal(shadow[:, :cols].float().cpu().numpy().reshape(-1),
                                   bf16_round(thd.cpu().numpy()))
+
+
+def test_binary_metrics_match_reference_semantics(cuda_lib):
+    """PositiveRate / PredictedPositives / F1Score / MaskedMetric (clickstream_transformer/
+    metrics.py) against the oracle's restatement, accumulated over two updates."""
+    import bert4clickpath_b200 as bc
+    rng = np.random.default_rng(3)
+    ms = [bc.PositiveRate(), bc.PredictedPositives(), bc.F1Score(), bc.MaskedMetric(bc.F1Score(), "masked_f1")]
+    assert [m.name for m in ms] == ["positive_rate", "pred_positives", "F1Score", "masked_f1"]
+    tot = np.zeros(6)
+    for n in (1000, 37):
+        y = rng.integers(0, 2, size=(n, 7)).astype(np.float32)
+        y[rng.random((n, 7)) < 0.3] = -1.0
+        p = rng.random((n, 7)).astype(np.float32)
+        p[0, :3] = [0.5, 1.5, 2.5]
+        for m in ms:
+            m.update_state(y, p)
+        tot += O.binary_metric_counts(y, p)
+    want = [tot[1] / tot[0], tot[2] / tot[0], 2 * tot[3] / (tot[4] + tot[5]), 2 * tot[3] / (tot[4] + tot[5])]
+    for m, w in zip(ms, want):
+        assert abs(float(m.result()) - w) < 1e-6 * abs(w), m.name
+    with pytest.raises(ValueError):
+        ms[3].update_state(y, p, sample_weight=np.ones_like(y))
+    ms[0].reset_states()
+    ms[0].update_state(y, p)
+    c = O.binary_metric_counts(y, p)
+    assert abs(float(ms[0].result()) - c[1] / c[0]) < 1e-6

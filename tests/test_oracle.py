@@ -208,3 +208,19 @@ def test_pad_rows_are_dead_compute():
     pad = ids_list[0] == 0
     a = caches[0][0]["a"]
     assert (a[np.broadcast_to(pad[:, None, None, :], a.shape)] == 0).all()
+
+
+def test_binary_metric_counts_hand_computed():
+    """metrics.py semantics on a hand-checked example: mask = (y != -1); tf.round halves to even
+    (0.5 -> 0, 1.5 -> 2); F1Score compares int32 casts WITHOUT the mask, so a padded position with
+    round(p) == 1 still counts as predicted-true (the MaskedMetric(F1Score) quirk)."""
+    y = np.array([[1, 0, -1, 1], [0, 1, -1, -1]], dtype=np.float32)
+    p = np.array([[0.9, 0.5, 0.8, 0.2], [0.51, 0.49, 0.1, 1.5]], dtype=np.float32)
+    c = O.binary_metric_counts(y, p)
+    # mask: 5 items; positives among them: 3; round(p)*mask: 1,0,.,0 | 1,0,.,. -> 2
+    # tp: (y==1 & round==1): item 0 only -> 1; condition_true: 3; predicted_true: 0.9,0.8,0.51 -> 3
+    # (round(1.5) = 2, not 1)
+    assert c.tolist() == [5.0, 3.0, 2.0, 1.0, 3.0, 3.0]
+    assert abs(c[1] / c[0] - 0.6) < 1e-12                       # PositiveRate
+    assert abs(c[2] / c[0] - 0.4) < 1e-12                       # PredictedPositives
+    assert abs(2 * c[3] / (c[4] + c[5]) - 1.0 / 3.0) < 1e-12    # F1Score
