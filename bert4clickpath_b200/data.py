@@ -1,0 +1,121 @@
+"""Real-data input side of the Cloze path (host NumPy; the step immediately before the hot path,
+SURVEY.md N2): the BERT4Rec text format reader and session prep of
+examples/BERT4Rec/data_prep/main.py:45-76, and the Cloze example / batch builder of
+examples/BERT4Rec/source/input_pipeline.py:21-32, :59-133, :198-220, producing the same dict as
+`synthetic.make_cloze_batch` (already-chained int32 ids + the reference's padded float32 labels),
+i.e. what `ClozeTrainStep.to_device` / `ClickstreamTransformer.cloze_forward_backward` consume.
+
+Not on the timed path and not a tf.data replacement: no TFRecord I/O, no shuffling buffers.
+"""
+import numpy as np
+
+from .constants import CLS, LABEL_PAD, MASK_ID, NUM_RESERVED_TOKENS, SEP
+from .synthetic import n_masked_for
+
+MASKED_PERCENTAGE = 0.4      # cloze_constants.py:1
+MAX_MASKED_ITEMS = 10        # cloze_constants.py:2
+MAX_SEQ_LEN = 50             # data_prep/main.py:57
+
+
+def read_bert4rec_text_data(path):
+    """`user item` pairs, one per line, in interaction order (data_prep/main.py:45-49).
+    Returns (users, items): two lists of strings of equal length."""
+    users, items = [], []
+    with open(path) as f:
+        for line in f:
+            parts = line.split()
+            if len(parts) >= 2:
+                users.append(parts[0])
+                items.append(parts[1])
+    return users, items
+
+
+def prepare_sessions(users, items, max_seq_len=MAX_SEQ_LEN):
+    """data_prep/main.py:62-76: keep each user's first `max_seq_len` interactions (cumcount <
+    max), item vocabulary = pd.unique over the kept rows (order of first appearance), one session
+    per user in order of first appearance.  Returns (sessions: list of lists of item strings,
+    item_vocab: list of strings, user_ids: list of strings)."""
+    per_user, order = {}, []
+    vocab, seen = [], set()
+    for u, it in zip(users, items):
+        s = per_user.get(u)
+        if s is None:
+            s = per_user[u] = []
+            order.append(u)
+        if len(s) >= max_seq_len:
+            continue
+        s.append(it)
+        if it not in seen:
+            seen.add(it)
+            vocab.append(it)
+    return [per_user[u] for u in order], vocab, order
+
+
+def cloze_example(item_ids, mode, rng, masked_percentage=MASKED_PERCENTAGE, max_masked=MAX_MASKED_ITEMS):
+    """One session of INPUT-vocabulary ids (>= 10) -> (masked ids, labels in the label vocabulary
+    = id - 10, as the reference's separate target lookup table gives: input_pipeline.py:189-192).
+    TRAIN: the last item is held out (:101-104), n = clip(int(len * p), 0, max) (:68-70) distinct
+    positions are replaced by [MASK] and the labels follow in ascending position (:21-32, :77-90).
+    EVAL: only the last item is masked (:118-121)."""
+    ids = np.asarray(item_ids, dtype=np.int32)
+    if mode == "train":
+        ids = ids[:-1].copy()
+        n = n_masked_for(len(ids), masked_percentage, max_masked)
+        pos = np.sort(rng.permutation(len(ids))[:n])
+    elif mode == "eval":
+        ids = ids.copy()
+        pos = np.array([len(ids) - 1])
+    else:
+        raise ValueError(f"Unrecognized mode: {mode}")
+    labels = (ids[pos] - NUM_RESERVED_TOKENS).astype(np.float32)
+    ids[pos] = MASK_ID
+    return ids, labels
+
+
+def cloze_batch(sessions_ids, mode, rng, masked_percentage=MASKED_PERCENTAGE, max_masked=MAX_MASKED_ITEMS):
+    """Batch of sessions (lists of input-vocabulary ids) -> dict(ids (B, S) int32 chained
+    `[CLS] [SEP] items... [PAD]... [SEP]` - every sequence is padded BEFORE chaining, so the trailing
+    [SEP] sits after the pad run (input_pipeline.py:198-214, clickstream_transformer.py:54-61,
+    SURVEY.md T7) -, labels (B, Mmax) float32 padded with -1, n_masked, items (B, L))."""
+    ex = [cloze_example(s, mode, rng, masked_percentage, max_masked) for s in sessions_ids]
+    B = len(ex)
+    L = max(len(e[0]) for e in ex)
+    items = np.zeros((B, L), dtype=np.int32)
+    mmax = max(1, max(len(e[1]) for e in ex))
+    labels = np.full((B, mmax), LABEL_PAD, dtype=np.float32)
+    for b, (ids, lab) in enumerate(ex):
+        items[b, :len(ids)] = ids
+        labels[b, :len(lab)] = lab
+    ids = np.concatenate([np.full((B, 1), CLS, np.int32), np.full((B, 1), SEP, np.int32), items,
+                          np.full((B, 1), SEP, np.int32)], axis=1)
+    return dict(ids=ids, labels=labels, n_masked=int(sum(len(e[1]) for e in ex)), items=items)
+
+
+class ClozeDataset:
+    """Sessions of the BERT4Rec text format as Cloze batches.  `vocab` defaults to the file's own
+    item vocabulary (order of first appearance, as data_prep writes item_vocab.txt); input ids are
+    index + 10 (clickstream_transformer.py:247-258), labels index (no offset)."""
+
+    def __init__(self, path, max_seq_len=MAX_SEQ_LEN, vocab=None):
+        users, items = read_bert4rec_text_data(path)
+        self.sessions, file_vocab, self.users = prepare_sessions(users, items, max_seq_len)
+        self.vocab = list(vocab) if vocab is not None else file_vocab
+        index = {t: i for i, t in enumerate(self.vocab)}
+        oov = len(self.vocab) + NUM_RESERVED_TOKENS   # StaticVocabularyTable's single OOV bucket
+        self.session_ids = [np.array([index[t] + NUM_RESERVED_TOKENS if t in index else oov for t in s],
+                                     dtype=np.int32) for s in self.sessions]
+
+    def __len__(self):
+        return len(self.session_ids)
+
+    def batches(self, batch_size, mode, rng, masked_percentage=MASKED_PERCENTAGE,
+                max_masked=MAX_MASKED_ITEMS, shuffle=None, drop_remainder=False):
+        """Yields batch dicts; TRAIN shuffles the session order by default."""
+        order = np.arange(len(self))
+        if shuffle if shuffle is not None else mode == "train":
+            order = rng.permutation(len(self))
+        for a in range(0, len(order), batch_size):
+            idx = order[a:a + batch_size]
+            if drop_remainder and len(idx) < batch_size:
+                return
+            yield cloze_batch([self.session_ids[i] for i in idx], mode, rng, masked_percentage, max_masked)

@@ -302,3 +302,55 @@ def test_two_rank_gloo_vocab_parallel_equals_single_process():
         np.testing.assert_allclose(dW_r, dW[:, v0:v1], rtol=1e-10, atol=1e-14)
         np.testing.assert_allclose(db_r, db[v0:v1], rtol=1e-10, atol=1e-14)
         assert top.tolist() == want_top[rank * M:(rank + 1) * M].tolist()
+
+
+# ------------------------------------------------------------------ real-data input side (N2)
+def test_bert4rec_text_reader_and_cloze_batches_follow_the_reference_rules():
+    """data.py against the reference's rules: first-50 cut and vocabulary order
+    (data_prep/main.py:62-76), TRAIN drop-last + n = clip(int(len*p),0,max) distinct sorted
+    positions + label ids without the +10 offset, EVAL masks the last item only
+    (input_pipeline.py:21-32,:59-133), and the chained layout with the trailing [SEP] after the
+    pad run (clickstream_transformer.py:54-61)."""
+    import os
+    from bert4clickpath_b200 import data as D
+    from bert4clickpath_b200.constants import CLS, SEP, MASK_ID
+    from oracle import clickpath_oracle as O
+    path = os.path.join(os.path.dirname(__file__), "golden", "tiny_bert4rec.txt")
+    ds = D.ClozeDataset(path)
+    users, items = D.read_bert4rec_text_data(path)
+    assert len(ds) == 12 and max(len(s) for s in ds.sessions) == 50        # user 7: 60 -> 50
+    # vocabulary = order of first appearance over the KEPT rows
+    kept, cnt = [], {}
+    for u, it in zip(users, items):
+        cnt[u] = cnt.get(u, 0) + 1
+        if cnt[u] <= 50:
+            kept.append(it)
+    assert ds.vocab == list(dict.fromkeys(kept))
+    rng = np.random.default_rng(0)
+    tr = D.cloze_batch(ds.session_ids, "train", rng, 0.4, 10)
+    B, S = tr["ids"].shape
+    assert (tr["ids"][:, 0] == CLS).all() and (tr["ids"][:, 1] == SEP).all() and (tr["ids"][:, -1] == SEP).all()
+    tot = 0
+    for b in range(B):
+        full = ds.session_ids[b]
+        n_in = len(full) - 1                                               # last item held out
+        row = tr["ids"][b, 2:2 + n_in]
+        assert (tr["ids"][b, 2 + n_in:-1] == 0).all()                      # pad run BEFORE the final [SEP]
+        pos = np.nonzero(row == MASK_ID)[0]
+        assert len(pos) == min(int(np.float32(n_in) * np.float32(0.4)), 10)
+        lab = tr["labels"][b]
+        assert (lab[:len(pos)] == full[:-1][pos] - 10).all() and (lab[len(pos):] == -1).all()
+        assert (np.delete(row, pos) == np.delete(full[:-1], pos)).all()    # everything else untouched
+        tot += len(pos)
+    assert tr["n_masked"] == tot
+    ev = D.cloze_batch(ds.session_ids, "eval", rng)
+    for b in range(B):
+        full = ds.session_ids[b]
+        assert ev["ids"][b, 2 + len(full) - 1] == MASK_ID and ev["labels"][b, 0] == full[-1] - 10
+        assert (ev["ids"][b, 2:2 + len(full) - 1] == full[:-1]).all()
+    assert ev["labels"].shape == (B, 1) and ev["n_masked"] == B
+    # the oracle's chaining of the same padded item matrix gives the same ids
+    assert (O.chain_sequences([tr["items"]]) == tr["ids"]).all()
+    # batches(): every session exactly once per epoch
+    seen = sum(b["ids"].shape[0] for b in ds.batches(5, "train", rng))
+    assert seen == len(ds)
