@@ -29,41 +29,22 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-// A fragment (16 rows x 16 k) of a row-major bf16 tile with row stride `ld` elements: one
-// ldmatrix.x4 (matrices [r0,k0] [r0+8,k0] [r0,k0+8] [r0+8,k0+8]) instead of four 32-bit loads -
-// these kernels were bound by shared-memory load ISSUE (two LDS per MMA), not by the tensor pipe.
-// Rows are (DH + 8) * 2 bytes apart, a multiple of 16, as ldmatrix requires.
+// A fragment (16 rows x 16 k) of a row-major bf16 tile with row stride `ld` elements
 __device__ __forceinline__ void load_a(uint32_t (&a)[4], const __nv_bfloat16* tile, int ld, int r0,
                                        int k0, int g, int t) {
-  const int lane = g * 4 + t;
-  const int row = r0 + (lane & 7) + ((lane >> 3) & 1) * 8;
-  const int col = k0 + (lane >> 4) * 8;
-  const uint32_t addr = smem_u32(tile + (size_t)row * ld + col);
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
-               : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3])
-               : "r"(addr));
+  const __nv_bfloat16* p0 = tile + (size_t)(r0 + g) * ld + k0 + t * 2;
+  const __nv_bfloat16* p1 = p0 + 8 * ld;
+  a[0] = *reinterpret_cast<const uint32_t*>(p0);
+  a[1] = *reinterpret_cast<const uint32_t*>(p1);
+  a[2] = *reinterpret_cast<const uint32_t*>(p0 + 8);
+  a[3] = *reinterpret_cast<const uint32_t*>(p1 + 8);
 }
 // B fragment (16 k x 8 n) where B[k][n] = tile[n0 + n][k0 + k] (tile row-major, k contiguous)
 __device__ __forceinline__ void load_b(uint32_t& b0, uint32_t& b1, const __nv_bfloat16* tile,
                                        int ld, int n0, int k0, int g, int t) {
-  const int lane = g * 4 + t;
-  const int row = n0 + (lane & 7);
-  const int col = k0 + ((lane >> 3) & 1) * 8;
-  const uint32_t addr = smem_u32(tile + (size_t)row * ld + col);
-  asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];"
-               : "=r"(b0), "=r"(b1)
-               : "r"(addr));
-}
-// B fragments of TWO adjacent n-tiles (n0 and n0 + 8) in one ldmatrix.x4:
-// b[0], b[1] = (b0, b1) of n-tile n0; b[2], b[3] = (b0, b1) of n-tile n0 + 8
-__device__ __forceinline__ void load_b2(uint32_t (&b)[4], const __nv_bfloat16* tile, int ld, int n0,
-                                        int k0, int lane) {
-  const int row = n0 + (lane & 7) + (lane >> 4) * 8;
-  const int col = k0 + ((lane >> 3) & 1) * 8;
-  const uint32_t addr = smem_u32(tile + (size_t)row * ld + col);
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
-               : "=r"(b[0]), "=r"(b[1]), "=r"(b[2]), "=r"(b[3])
-               : "r"(addr));
+  const __nv_bfloat16* p = tile + (size_t)(n0 + g) * ld + k0 + t * 2;
+  b0 = *reinterpret_cast<const uint32_t*>(p);
+  b1 = *reinterpret_cast<const uint32_t*>(p + 8);
 }
 
 // Two B fragments (16 k x 8 n each, n-tiles n0 and n0 + 8) where B[k][n] = tile[k0 + k][n0 + n]
@@ -149,11 +130,10 @@ attention_mma_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* _
       uint32_t a[4];
       load_a(a, sQ, C::LDR, r0, ks * 16, g, t);
 #pragma unroll
-      for (int nt = 0; nt < C::NT; nt += 2) {
-        uint32_t bb[4];
-        load_b2(bb, sK, C::LDR, nt * 8, ks * 16, lane);
-        mma_bf16(sc[nt], a, bb[0], bb[1]);
-        mma_bf16(sc[nt + 1], a, bb[2], bb[3]);
+      for (int nt = 0; nt < C::NT; ++nt) {
+        uint32_t b0, b1;
+        load_b(b0, b1, sK, C::LDR, nt * 8, ks * 16, g, t);
+        mma_bf16(sc[nt], a, b0, b1);
       }
     }
     float m0 = -INFINITY, m1 = -INFINITY;
@@ -264,14 +244,12 @@ attention_mma_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloa
       load_a(aq, sQ, C::LDR, r0, ks * 16, g, t);
       load_a(ag, sDO, C::LDR, r0, ks * 16, g, t);
 #pragma unroll
-      for (int nt = 0; nt < C::NT; nt += 2) {
-        uint32_t bb[4];
-        load_b2(bb, sK, C::LDR, nt * 8, ks * 16, lane);
-        mma_bf16(p[nt], aq, bb[0], bb[1]);
-        mma_bf16(p[nt + 1], aq, bb[2], bb[3]);
-        load_b2(bb, sV, C::LDR, nt * 8, ks * 16, lane);
-        mma_bf16(dp[nt], ag, bb[0], bb[1]);
-        mma_bf16(dp[nt + 1], ag, bb[2], bb[3]);
+      for (int nt = 0; nt < C::NT; ++nt) {
+        uint32_t b0, b1;
+        load_b(b0, b1, sK, C::LDR, nt * 8, ks * 16, g, t);
+        mma_bf16(p[nt], aq, b0, b1);
+        load_b(b0, b1, sV, C::LDR, nt * 8, ks * 16, g, t);
+        mma_bf16(dp[nt], ag, b0, b1);
       }
     }
     const float l0 = sLse[r0 + g], l1 = sLse[r0 + g + 8];
@@ -339,14 +317,12 @@ attention_mma_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloa
       load_a(ak, sK, C::LDR, j0, ks * 16, g, t);
       load_a(av, sV, C::LDR, j0, ks * 16, g, t);
 #pragma unroll
-      for (int nt = 0; nt < C::NT; nt += 2) {
-        uint32_t bb[4];
-        load_b2(bb, sQ, C::LDR, nt * 8, ks * 16, lane);
-        mma_bf16(p[nt], ak, bb[0], bb[1]);
-        mma_bf16(p[nt + 1], ak, bb[2], bb[3]);
-        load_b2(bb, sDO, C::LDR, nt * 8, ks * 16, lane);
-        mma_bf16(dp[nt], av, bb[0], bb[1]);
-        mma_bf16(dp[nt + 1], av, bb[2], bb[3]);
+      for (int nt = 0; nt < C::NT; ++nt) {
+        uint32_t b0, b1;
+        load_b(b0, b1, sQ, C::LDR, nt * 8, ks * 16, g, t);
+        mma_bf16(p[nt], ak, b0, b1);
+        load_b(b0, b1, sDO, C::LDR, nt * 8, ks * 16, g, t);
+        mma_bf16(dp[nt], av, b0, b1);
       }
     }
     const float k0m = sMask[j0 + g], k1m = sMask[j0 + g + 8];
@@ -461,11 +437,10 @@ attention_mma_fwd_long_kernel(const __nv_bfloat16* __restrict__ qkv, const int32
         uint32_t a[4];
         load_a(a, sQ, LDR, r0, ks * 16, g, t);
 #pragma unroll
-        for (int nt = 0; nt < NT; nt += 2) {
-          uint32_t bb[4];
-          load_b2(bb, sK, LDR, kb0 + nt * 8, ks * 16, lane);
-          mma_bf16(sc[nt], a, bb[0], bb[1]);
-          mma_bf16(sc[nt + 1], a, bb[2], bb[3]);
+        for (int nt = 0; nt < NT; ++nt) {
+          uint32_t b0, b1;
+          load_b(b0, b1, sK, LDR, kb0 + nt * 8, ks * 16, g, t);
+          mma_bf16(sc[nt], a, b0, b1);
         }
       }
       float c0 = -INFINITY, c1 = -INFINITY;
@@ -607,14 +582,12 @@ attention_mma_bwd_long_kernel(const __nv_bfloat16* __restrict__ qkv,
         load_a(aq, sQ, LDR, r0, ks * 16, g, t);
         load_a(ag, sDO, LDR, r0, ks * 16, g, t);
 #pragma unroll
-        for (int nt = 0; nt < NT; nt += 2) {
-          uint32_t bb[4];
-          load_b2(bb, sK, LDR, kb0 + nt * 8, ks * 16, lane);
-          mma_bf16(p[nt], aq, bb[0], bb[1]);
-          mma_bf16(p[nt + 1], aq, bb[2], bb[3]);
-          load_b2(bb, sV, LDR, kb0 + nt * 8, ks * 16, lane);
-          mma_bf16(dp[nt], ag, bb[0], bb[1]);
-          mma_bf16(dp[nt + 1], ag, bb[2], bb[3]);
+        for (int nt = 0; nt < NT; ++nt) {
+          uint32_t b0, b1;
+          load_b(b0, b1, sK, LDR, kb0 + nt * 8, ks * 16, g, t);
+          mma_bf16(p[nt], aq, b0, b1);
+          load_b(b0, b1, sV, LDR, kb0 + nt * 8, ks * 16, g, t);
+          mma_bf16(dp[nt], ag, b0, b1);
         }
       }
 #pragma unroll
@@ -680,14 +653,12 @@ attention_mma_bwd_long_kernel(const __nv_bfloat16* __restrict__ qkv,
         load_a(ak, sK, LDR, j0, ks * 16, g, t);
         load_a(av, sV, LDR, j0, ks * 16, g, t);
 #pragma unroll
-        for (int nt = 0; nt < NT; nt += 2) {
-          uint32_t bb[4];
-          load_b2(bb, sQ, LDR, qb0 + nt * 8, ks * 16, lane);
-          mma_bf16(p[nt], ak, bb[0], bb[1]);
-          mma_bf16(p[nt + 1], ak, bb[2], bb[3]);
-          load_b2(bb, sDO, LDR, qb0 + nt * 8, ks * 16, lane);
-          mma_bf16(dp[nt], av, bb[0], bb[1]);
-          mma_bf16(dp[nt + 1], av, bb[2], bb[3]);
+        for (int nt = 0; nt < NT; ++nt) {
+          uint32_t b0, b1;
+          load_b(b0, b1, sQ, LDR, qb0 + nt * 8, ks * 16, g, t);
+          mma_bf16(p[nt], ak, b0, b1);
+          load_b(b0, b1, sDO, LDR, qb0 + nt * 8, ks * 16, g, t);
+          mma_bf16(dp[nt], av, b0, b1);
         }
       }
 #pragma unroll
