@@ -156,10 +156,10 @@ attention_mma_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* _
     float s0 = 0.f, s1 = 0.f;
 #pragma unroll
     for (int nt = 0; nt < C::NT; ++nt) {
-      sc[nt][0] = expf(sc[nt][0] - m0);
-      sc[nt][1] = expf(sc[nt][1] - m0);
-      sc[nt][2] = expf(sc[nt][2] - m1);
-      sc[nt][3] = expf(sc[nt][3] - m1);
+      sc[nt][0] = __expf(sc[nt][0] - m0);
+      sc[nt][1] = __expf(sc[nt][1] - m0);
+      sc[nt][2] = __expf(sc[nt][2] - m1);
+      sc[nt][3] = __expf(sc[nt][3] - m1);
       s0 += sc[nt][0] + sc[nt][1];
       s1 += sc[nt][2] + sc[nt][3];
     }
@@ -265,10 +265,10 @@ attention_mma_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloa
 #pragma unroll
     for (int nt = 0; nt < C::NT; ++nt) {
       const float k0 = sMask[nt * 8 + t * 2], k1 = sMask[nt * 8 + t * 2 + 1];
-      p[nt][0] = expf((p[nt][0] * rsqrt_dh) + k0 - l0);
-      p[nt][1] = expf((p[nt][1] * rsqrt_dh) + k1 - l0);
-      p[nt][2] = expf((p[nt][2] * rsqrt_dh) + k0 - l1);
-      p[nt][3] = expf((p[nt][3] * rsqrt_dh) + k1 - l1);
+      p[nt][0] = __expf((p[nt][0] * rsqrt_dh) + k0 - l0);
+      p[nt][1] = __expf((p[nt][1] * rsqrt_dh) + k1 - l0);
+      p[nt][2] = __expf((p[nt][2] * rsqrt_dh) + k0 - l1);
+      p[nt][3] = __expf((p[nt][3] * rsqrt_dh) + k1 - l1);
       d0 += p[nt][0] * dp[nt][0] + p[nt][1] * dp[nt][1];
       d1 += p[nt][2] * dp[nt][2] + p[nt][3] * dp[nt][3];
     }
@@ -339,10 +339,10 @@ attention_mma_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloa
       const int q0 = nt * 8 + t * 2;
       const float la = sLse[q0], lb = sLse[q0 + 1];
       const float da = sDelta[q0], db = sDelta[q0 + 1];
-      p[nt][0] = expf((p[nt][0] * rsqrt_dh) + k0m - la);
-      p[nt][1] = expf((p[nt][1] * rsqrt_dh) + k0m - lb);
-      p[nt][2] = expf((p[nt][2] * rsqrt_dh) + k1m - la);
-      p[nt][3] = expf((p[nt][3] * rsqrt_dh) + k1m - lb);
+      p[nt][0] = __expf((p[nt][0] * rsqrt_dh) + k0m - la);
+      p[nt][1] = __expf((p[nt][1] * rsqrt_dh) + k0m - lb);
+      p[nt][2] = __expf((p[nt][2] * rsqrt_dh) + k1m - la);
+      p[nt][3] = __expf((p[nt][3] * rsqrt_dh) + k1m - lb);
       dp[nt][0] = p[nt][0] * (dp[nt][0] - da);
       dp[nt][1] = p[nt][1] * (dp[nt][1] - db);
       dp[nt][2] = p[nt][2] * (dp[nt][2] - da);
@@ -467,14 +467,14 @@ attention_mma_fwd_long_kernel(const __nv_bfloat16* __restrict__ qkv, const int32
         c1 = fmaxf(c1, fmaxf(sc[nt][2], sc[nt][3]));
       }
       const float n0 = fmaxf(m0, quad_max(c0)), n1 = fmaxf(m1, quad_max(c1));   // finite: key 0 exists
-      const float a0 = expf(m0 - n0), a1 = expf(m1 - n1);                        // exp(-inf) = 0 at first
+      const float a0 = __expf(m0 - n0), a1 = __expf(m1 - n1);                        // exp(-inf) = 0 at first
       float s0 = 0.f, s1 = 0.f;
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) {
-        sc[nt][0] = expf(sc[nt][0] - n0);
-        sc[nt][1] = expf(sc[nt][1] - n0);
-        sc[nt][2] = expf(sc[nt][2] - n1);
-        sc[nt][3] = expf(sc[nt][3] - n1);
+        sc[nt][0] = __expf(sc[nt][0] - n0);
+        sc[nt][1] = __expf(sc[nt][1] - n0);
+        sc[nt][2] = __expf(sc[nt][2] - n1);
+        sc[nt][3] = __expf(sc[nt][3] - n1);
         s0 += sc[nt][0] + sc[nt][1];
         s1 += sc[nt][2] + sc[nt][3];
       }
@@ -609,10 +609,10 @@ attention_mma_bwd_long_kernel(const __nv_bfloat16* __restrict__ qkv,
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) {
         const float k0 = sMask[kb0 + nt * 8 + t * 2], k1 = sMask[kb0 + nt * 8 + t * 2 + 1];
-        p[nt][0] = expf((p[nt][0] * rsqrt_dh) + k0 - l0) * (dp[nt][0] - d0);
-        p[nt][1] = expf((p[nt][1] * rsqrt_dh) + k1 - l0) * (dp[nt][1] - d0);
-        p[nt][2] = expf((p[nt][2] * rsqrt_dh) + k0 - l1) * (dp[nt][2] - d1);
-        p[nt][3] = expf((p[nt][3] * rsqrt_dh) + k1 - l1) * (dp[nt][3] - d1);
+        p[nt][0] = __expf((p[nt][0] * rsqrt_dh) + k0 - l0) * (dp[nt][0] - d0);
+        p[nt][1] = __expf((p[nt][1] * rsqrt_dh) + k1 - l0) * (dp[nt][1] - d0);
+        p[nt][2] = __expf((p[nt][2] * rsqrt_dh) + k0 - l1) * (dp[nt][2] - d1);
+        p[nt][3] = __expf((p[nt][3] * rsqrt_dh) + k1 - l1) * (dp[nt][3] - d1);
       }
 #pragma unroll
       for (int ks = 0; ks < KS_S; ++ks) {
@@ -682,10 +682,10 @@ attention_mma_bwd_long_kernel(const __nv_bfloat16* __restrict__ qkv,
         const int q0 = qb0 + nt * 8 + t * 2;
         const float la = sLse[q0], lb = sLse[q0 + 1];
         const float da = sDelta[q0], db = sDelta[q0 + 1];
-        p[nt][0] = expf((p[nt][0] * rsqrt_dh) + k0m - la);
-        p[nt][1] = expf((p[nt][1] * rsqrt_dh) + k0m - lb);
-        p[nt][2] = expf((p[nt][2] * rsqrt_dh) + k1m - la);
-        p[nt][3] = expf((p[nt][3] * rsqrt_dh) + k1m - lb);
+        p[nt][0] = __expf((p[nt][0] * rsqrt_dh) + k0m - la);
+        p[nt][1] = __expf((p[nt][1] * rsqrt_dh) + k0m - lb);
+        p[nt][2] = __expf((p[nt][2] * rsqrt_dh) + k1m - la);
+        p[nt][3] = __expf((p[nt][3] * rsqrt_dh) + k1m - lb);
         dp[nt][0] = p[nt][0] * (dp[nt][0] - da);
         dp[nt][1] = p[nt][1] * (dp[nt][1] - db);
         dp[nt][2] = p[nt][2] * (dp[nt][2] - da);
