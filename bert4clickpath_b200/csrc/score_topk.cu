@@ -151,7 +151,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   float* sBias = reinterpret_cast<float*>(
       reinterpret_cast<uint8_t*>(sHeapI) +
       (FILTER ? (size_t)16 * ST_M * 4 : (((size_t)k * ST_M * (WIDE ? 3 : 4) + 15) & ~(size_t)15)));  // [2][128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + 2 * ST_N);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + 4 * 2 * ST_N);   // sBias: [4 warps][2][128]
   uint64_t* x_full = bars;
   uint64_t* w_full = bars + 1;
   uint64_t* w_empty = w_full + ST_STAGES;
@@ -261,7 +261,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     const uint32_t aS = smem_u32(sHeapS) + r * 4;
     const uint32_t aI = smem_u32(sHeapI) + r * (WIDE ? 2 : 4);                      // int32 or u16 low
     const uint32_t aH = smem_u32(sHeapI) + (uint32_t)k * ST_M * 2 + r;              // u8 high (WIDE)
-    const uint32_t aB = smem_u32(sBias);
+    const uint32_t aB = smem_u32(sBias + warp * 2 * ST_N);   // this warp's private copy: no CTA-wide barrier per tile
     constexpr uint32_t SLOT = ST_M * 4;  // byte stride between heap score slots
     constexpr int EMPTY = WIDE ? ID24_EMPTY : INT_MAX;
     auto ld_id = [&](int slot) -> int {
@@ -298,17 +298,30 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     int n_staged = 0;   // FILTER: candidates staged in sHeapS / sHeapI ([slot][row])
     // bias of a tile (one value per thread, -inf past the vocabulary), fetched one tile ahead:
     // a global load per tile in front of the barrier below stalled every tile for a DRAM latency
-    auto load_bias = [&](int t) -> float {
-      const int v = (p.tile0 + t_begin + t) * ST_N + r;
-      return (t < ntiles && v < p.V) ? __ldg(p.bias + v) : -INFINITY;
+    // lane l stages columns 4l..4l+3 of the tile's bias for ITS warp (every thread needs all 128)
+    auto load_bias = [&](int t) -> float4 {
+      const int v = (p.tile0 + t_begin + t) * ST_N + lane * 4;
+      float4 b = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+      if (t < ntiles) {
+        if (v + 3 < p.V && (((uintptr_t)(p.bias + v)) & 15) == 0) {
+          b = __ldg(reinterpret_cast<const float4*>(p.bias + v));
+        } else {
+          if (v < p.V) b.x = __ldg(p.bias + v);
+          if (v + 1 < p.V) b.y = __ldg(p.bias + v + 1);
+          if (v + 2 < p.V) b.z = __ldg(p.bias + v + 2);
+          if (v + 3 < p.V) b.w = __ldg(p.bias + v + 3);
+        }
+      }
+      return b;
     };
-    float bias_next = load_bias(0);
+    float4 bias_next = load_bias(0);
     for (int t = 0; t < ntiles; ++t) {
       const int buf = t & 1;
       const int v0 = (p.tile0 + t_begin + t) * ST_N;
-      sts32f(aB + (buf * ST_N + r) * 4, bias_next);
+      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(aB + (buf * ST_N + lane * 4) * 4),
+                   "f"(bias_next.x), "f"(bias_next.y), "f"(bias_next.z), "f"(bias_next.w) : "memory");
       bias_next = load_bias(t + 1);
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      __syncwarp();
       mbar_wait(&s_full[buf], (t >> 1) & 1);
       tc_fence_after();
 #pragma unroll 1
@@ -486,7 +499,7 @@ static int launch_heap(const void* x_bf16, long ldx, long M, int h, const void* 
   if (rc) return rc;
   const size_t smem = (wide ? 0 : (size_t)p.HB * ST_M * 128) + (size_t)ST_STAGES * 2 * p.HB * 8192 +
                       (size_t)k * ST_M * 4 + (((size_t)k * ST_M * (wide ? 3 : 4) + 15) & ~(size_t)15) +
-                      2 * ST_N * 4 + 256 + 1024;
+                      4 * 2 * ST_N * 4 + 256 + 1024;
   B4CP_CHECK_ARG(smem <= 227 * 1024, "score_topk: k=%d h=%d needs %zu B of shared memory", k, h, smem);
   dim3 grid(ceil_div(M, ST_M), p.n_chunks);
   if (wide) {
@@ -548,7 +561,7 @@ static int score_topk_filter(const void* x_bf16, long ldx, long M, int h, const 
   rc = make_tmap_bf16_2d(&tmW, w_bf16, (uint64_t)V, (uint64_t)h, (uint64_t)ldw * 2, 64, 64);
   if (rc) return rc;
   const size_t smem = (size_t)p.HB * ST_M * 128 + (size_t)ST_STAGES * 2 * p.HB * 8192 +
-                      (size_t)2 * 16 * ST_M * 4 + 2 * ST_N * 4 + 256 + 1024;
+                      (size_t)2 * 16 * ST_M * 4 + 4 * 2 * ST_N * 4 + 256 + 1024;
   B4CP_CUDA(cudaFuncSetAttribute(score_topk_kernel<false, true>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   dim3 grid(ceil_div(M, ST_M), p.n_chunks);
