@@ -333,8 +333,8 @@ def c5_topk(pk, B=4096, iters=5):
            "frac": nbytes / (ms * 1e-3) / 1e9 / pk["hbm"],
            "algorithmic_bytes": nbytes,
            "note": "bytes = scores written once + read once (fp32) + W per 2048-row range + ids; the "
-                   "fused alternative b4cp_score_topk (scores never in HBM) measures 0.38M queries/s "
-                   "at this shape and is used below 262,144 entries"}
+                   "fused alternative b4cp_score_topk (scores never in HBM) measures 0.41M queries/s "
+                   "at this shape"}
     del wb, z
     torch.cuda.empty_cache()
     return out
@@ -465,7 +465,8 @@ def run_ours(args, rank, world, local_rank):
         topk = {"metric": "next_item_topk_queries_per_sec", "value": world * QB * n_q / (q_ms * 1e-3),
                 "unit": "queries/s", "k": K_TOP, "queries_per_step_per_gpu": QB, "steps": n_q,
                 "ms_per_step": q_ms / n_q, "vocab": V,
-                "includes": "encoder forward + head MLP + fused scoring/top-k + recall/NDCG counters",
+                "includes": "encoder forward + head MLP + scoring (tcgen05 GEMM) + streaming top-k + "
+                            "recall/NDCG counters; synthetic ids are NOT in popularity order",
                 "recall_at_k": float(c[0] / max(c[2], 1)), "ndcg_at_k": float(c[1] / max(c[2], 1))}
 
     c4 = c5 = None

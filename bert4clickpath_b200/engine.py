@@ -471,18 +471,18 @@ class VocabOutputEngine:
         if db_parts is not None:
             ops.reduce_splits(db_parts, self.b.g)
 
-    FUSED_TOPK_MAX_V = 262144
-
     def topk(self, ab, M, k):
         """(M, k) int32 ids of the k highest scores per row, ties -> lower id.
-        V < 262144: fused scoring + per-row heaps on the tensor cores (scores never reach HBM).
-        Longer vocabularies (C5: 1M items): logits materialised for a bounded row range at a time
-        + the single-pass streaming top-k, which measures faster there (~500k queries/s at V = 1M,
-        h = 256) than both the heap kernel (~100k) and the library's seed + filter + merge path
-        (~380k, `b4cp_score_topk` above 262144 entries; set `prefer_fused_topk` to use it)."""
+        Default: logits materialised for a bounded row range at a time (tcgen05 GEMM, fp32) + the
+        single-pass streaming top-k (`b4cp_topk_rows`).  On scores in realistic (unsorted) order this
+        measures 3.7 M queries/s at V = 54,293 / h = 128 and 0.5 M at V = 1M / h = 256, against
+        0.67 M / 0.41 M for the fused kernels of `b4cp_score_topk` (scores never in HBM; per-row heaps
+        below 262,144 entries, seed + filter + merge above), whose per-row candidate bookkeeping is
+        the bottleneck.  `prefer_fused_topk = True` selects the fused kernels (they win when HBM
+        capacity, not time, is the constraint, and on near-sorted scores)."""
         ids = self.pool.get(f"topk{k}", (M, k), I32)
         fused_ok = self.h in (64, 128, 256) and k <= 104 and not self.force_materialized
-        if fused_ok and (self.V < self.FUSED_TOPK_MAX_V or self.prefer_fused_topk):
+        if fused_ok and self.prefer_fused_topk:
             t0 = ops.TIMER.begin("score_topk")
             ops.score_topk(ab, M, self.h, self.W.wb, self.b.w, self.V, k, out_ids=ids)
             ops.TIMER.end("score_topk", t0)

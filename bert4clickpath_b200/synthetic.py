@@ -21,12 +21,28 @@ def n_masked_for(length, masked_percentage, max_masked):
     return int(min(max(int(np.float32(length) * np.float32(masked_percentage)), 0), max_masked))
 
 
+def _rank_to_item(vocab):
+    """Multiplier of the bijection rank -> (rank * A) % vocab (golden-ratio hashing, gcd(A, vocab)
+    = 1) that scatters popularity ranks over the id space.  Real catalogues are not sorted by
+    popularity; with ids in popularity order a model that has learned the popularity prior emits
+    scores that DECREASE along the vocabulary, and every threshold-based top-k degenerates to its
+    no-candidate fast path (the first k ids win), which flatters the inference benchmark."""
+    from math import gcd
+    a = max(1, int(0.6180339887498949 * vocab))
+    while gcd(a, vocab) != 1:
+        a += 1
+    return a
+
+
 def zipf_items(rng, size, vocab, s=0.8):
-    """Item ids in [10, vocab+9] with P(rank r) ~ r^-s."""
+    """Item ids in [10, vocab+9] with P(popularity rank r) ~ r^-s; ranks are scattered over the id
+    space by a fixed bijection (see _rank_to_item)."""
     w = 1.0 / np.power(np.arange(1, vocab + 1, dtype=np.float64), s)
     cdf = np.cumsum(w)
     cdf /= cdf[-1]
-    return (np.searchsorted(cdf, rng.random(size)) + NUM_RESERVED_TOKENS).astype(np.int32)
+    rank = np.searchsorted(cdf, rng.random(size)).astype(np.int64)
+    item = (rank * _rank_to_item(vocab)) % vocab
+    return (item + NUM_RESERVED_TOKENS).astype(np.int32)
 
 
 def make_cloze_batch(rng, batch, vocab, max_len=50, mode="train", masked_percentage=0.15,

@@ -3,11 +3,13 @@ python scripts/time_c5_topk.py"""
 import json, sys, torch
 sys.path.insert(0, ".")
 from bert4clickpath_b200 import ops
-V, h, k = 1_000_000, 256, 100
+V = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
+h = int(sys.argv[2]) if len(sys.argv) > 2 else 256
+k = 100
 wb = torch.zeros(h, ops.ld8(V), device="cuda", dtype=torch.bfloat16)
 wb[:, :V] = (torch.randn(h, V, device="cuda") * 0.05).to(torch.bfloat16)
 bias = torch.zeros(V, device="cuda")
-for B in (1, 16, 256, 1024, 4096, 16384):
+for B in ((1, 16, 256, 1024, 4096, 16384) if len(sys.argv) < 4 else tuple(int(a) for a in sys.argv[3:])):
     xb = (torch.randn(B, h, device="cuda") * 0.5).to(torch.bfloat16)
     ids = torch.empty(B, k, dtype=torch.int32, device="cuda")
     fn = lambda: ops.score_topk(xb, B, h, wb, bias, V, k, out_ids=ids)
