@@ -15,6 +15,7 @@
 // (adversarially ordered scores) is flagged and redone by the radix-select kernel - the result is
 // exact either way.
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "../../include/b4cp.h"
@@ -329,6 +330,148 @@ topk_stream_kernel(const float* __restrict__ scores, long ld, int V, int k, int 
   }
 }
 
+// ------------------------------------------------------------------ sampled-threshold streaming top-k
+// One pass with a STATIC threshold taken from a strided sample of the row: the r-th best of n_s
+// sampled scores (r ~ 4 k n_s / V) sits near population rank 4k, so admitting every score at
+// least as good as it leaves ~4k candidates - no compaction and no block-wide barrier during the
+// pass - and the exact top-k of those candidates finishes.  Correctness never depends on the
+// sample: if fewer than k or more than SM_CAP candidates were admitted (astronomically unlikely for
+// random order; certain for e.g. an all-ties row), the row is flagged and redone by the
+// radix-select kernel.  This is the variant for rows of 16K..256K scores, where the running
+// threshold of topk_stream_kernel spends more time compacting than reading.
+static constexpr int SM_THREADS = 512;
+static constexpr int SM_CAP = 4096;
+
+template <int SPT>   // sampled scores per thread: n_s = 512 * SPT
+__global__ void __launch_bounds__(SM_THREADS, 2)
+topk_sample_kernel(const float* __restrict__ scores, long ld, int V, int k, int idbits, int rounds_target,
+                   int32_t* __restrict__ out_ids, float* __restrict__ out_scores, long ld_out) {
+  extern __shared__ __align__(16) unsigned long long sm_buf[];  // [2 * SM_CAP] (second half: scratch)
+  __shared__ uint32_t s_wmin[SM_THREADS / 32];
+  __shared__ int s_count;
+  const long row = blockIdx.x;
+  const float* z = scores + row * ld;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int NS = SM_THREADS * SPT;
+  // ---- 1. threshold = the sample's r-th best distinct key (ordered_desc: smaller = better)
+  uint32_t key[SPT];
+#pragma unroll
+  for (int q = 0; q < SPT; ++q) {
+    const long j = (long)(tid + SM_THREADS * q) * V / NS;
+    key[q] = ordered_desc(__ldg(z + j));
+  }
+  if (tid == 0) s_count = 0;
+  uint32_t tau_od = 0;
+  int removed = 0;
+  while (removed < rounds_target) {
+    uint32_t m = 0xFFFFFFFFu;
+#pragma unroll
+    for (int q = 0; q < SPT; ++q) m = min(m, key[q]);
+    m = __reduce_min_sync(0xffffffffu, m);
+    if (lane == 0) s_wmin[warp] = m;
+    __syncthreads();
+    m = s_wmin[lane & (SM_THREADS / 32 - 1)];
+    m = __reduce_min_sync(0xffffffffu, m);
+    if (m == 0xFFFFFFFFu) break;   // sample exhausted (cannot happen for V >= 16384 real scores)
+    int mine = 0;
+#pragma unroll
+    for (int q = 0; q < SPT; ++q)
+      if (key[q] == m) {
+        key[q] = 0xFFFFFFFFu;
+        ++mine;
+      }
+    removed += __syncthreads_count(mine > 0);   // >= 1 per round; ties at m are removed together
+    tau_od = m;
+  }
+  const float tau_f = from_ordered_desc(tau_od);
+  // ---- 2. one pass: admit every score >= tau
+  auto load_batch = [&](int base, float (&x)[4][4]) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int idx = base + (u * SM_THREADS + tid) * 4;
+      if (idx + 3 < V) {
+        const float4 v4 = __ldg(reinterpret_cast<const float4*>(z + idx));
+        x[u][0] = v4.x; x[u][1] = v4.y; x[u][2] = v4.z; x[u][3] = v4.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) x[u][j] = idx + j < V ? __ldg(z + idx + j) : -INFINITY;
+      }
+    }
+  };
+  constexpr int BATCH = SM_THREADS * 16;
+  float x[4][4], xn[4][4];
+  load_batch(0, x);
+  for (int base = 0; base < V; base += BATCH) {
+    if (base + BATCH < V) load_batch(base + BATCH, xn);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (x[u][j] >= tau_f) {
+          const int v = base + (u * SM_THREADS + tid) * 4 + j;
+          if (v < V) {
+            const int slot = atomicAdd(&s_count, 1);
+            if (slot < SM_CAP)
+              sm_buf[slot] = ((unsigned long long)ordered_desc(x[u][j]) << idbits) | (unsigned)v;
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) x[u][j] = xn[u][j];
+  }
+  __syncthreads();
+  const int c = s_count;
+  if (c > SM_CAP || c < k) {   // threshold too loose / too tight: exact redo by the radix kernel
+    if (tid == 0) out_ids[row * ld_out] = TK_REDO;
+    return;
+  }
+  // ---- 3. exact top-k of the admitted candidates (sorted into sm_buf[0..k))
+  __syncthreads();
+  {
+    unsigned long long* buf = sm_buf;
+    if (c <= ST_RANK_MAX) {
+      unsigned long long* dst = buf + SM_CAP;
+      const unsigned long long my0 = tid < c ? buf[tid] : ~0ull;
+      const unsigned long long my1 = tid + SM_THREADS < c ? buf[tid + SM_THREADS] : ~0ull;
+      int r0 = 0, r1 = 0;
+      if (tid < c) {
+        if (c > SM_THREADS) {
+#pragma unroll 4
+          for (int i = 0; i < c; ++i) {
+            const unsigned long long K = buf[i];
+            r0 += K < my0 ? 1 : 0;
+            r1 += K < my1 ? 1 : 0;
+          }
+        } else {
+#pragma unroll 4
+          for (int i = 0; i < c; ++i) r0 += buf[i] < my0 ? 1 : 0;
+        }
+      }
+      __syncthreads();
+      if (tid < c && r0 < k) dst[r0] = my0;
+      if (tid + SM_THREADS < c && r1 < k) dst[r1] = my1;
+      __syncthreads();
+      for (int i = tid; i < k; i += SM_THREADS) buf[i] = dst[i];
+    } else {
+      int logn = 1;
+      while ((1 << logn) < c) ++logn;
+      for (int i = c + tid; i < (1 << logn); i += SM_THREADS) buf[i] = ~0ull;
+      __syncthreads();
+      block_bitonic_sort(buf, logn);
+    }
+    __syncthreads();
+  }
+  const unsigned long long idmask = (1ull << idbits) - 1ull;
+  for (int r = tid; r < k; r += SM_THREADS) {
+    const unsigned long long K = sm_buf[r];
+    out_ids[row * ld_out + r] = (int32_t)(K & idmask);
+    if (out_scores) out_scores[row * ld_out + r] = from_ordered_desc((uint32_t)(K >> idbits));
+  }
+}
+
 }  // namespace b4cp
 
 using namespace b4cp;
@@ -342,11 +485,35 @@ extern "C" int b4cp_topk_rows(const float* scores, long ld, long rows, int V, in
   int idbits = 1;
   while ((1L << idbits) < V) ++idbits;
   if (V >= ST_MIN_V && ld % 4 == 0 && ((uintptr_t)scores & 15) == 0) {
-    const size_t smem = (size_t)2 * ST_CAP * sizeof(unsigned long long);
-    B4CP_CUDA(cudaFuncSetAttribute(topk_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)smem));
-    topk_stream_kernel<<<(unsigned)rows, ST_THREADS, smem, (cudaStream_t)stream>>>(
-        scores, ld, V, k, idbits, out_ids, out_scores, ld_out);
+    // sampled static threshold (measured faster: 0.34 vs 0.16 of the HBM roofline at V = 54K,
+    // 0.77 vs 0.66 at V = 1M, k = 100) except for very small k on very long rows, where the
+    // running threshold of topk_stream_kernel admits almost nothing (0.79 vs 0.77 at k = 10)
+    const char* mode = getenv("B4CP_TOPK_STREAM");
+    bool sampled = !(V >= 262144 && k <= 16);
+    if (mode && mode[0] == 'a') sampled = false;
+    if (mode && mode[0] == 's') sampled = true;
+    if (sampled) {
+      const bool big = V >= 131072;
+      const int ns = SM_THREADS * (big ? 16 : 4);
+      int r = (int)((4L * k * ns + V - 1) / V);
+      r = std::max(8, std::min(r, 64));
+      const size_t smem = (size_t)2 * SM_CAP * sizeof(unsigned long long);
+      if (big) {
+        B4CP_CUDA(cudaFuncSetAttribute(topk_sample_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        topk_sample_kernel<16><<<(unsigned)rows, SM_THREADS, smem, (cudaStream_t)stream>>>(
+            scores, ld, V, k, idbits, r, out_ids, out_scores, ld_out);
+      } else {
+        B4CP_CUDA(cudaFuncSetAttribute(topk_sample_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        topk_sample_kernel<4><<<(unsigned)rows, SM_THREADS, smem, (cudaStream_t)stream>>>(
+            scores, ld, V, k, idbits, r, out_ids, out_scores, ld_out);
+      }
+    } else {
+      const size_t smem = (size_t)2 * ST_CAP * sizeof(unsigned long long);
+      B4CP_CUDA(cudaFuncSetAttribute(topk_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)smem));
+      topk_stream_kernel<<<(unsigned)rows, ST_THREADS, smem, (cudaStream_t)stream>>>(
+          scores, ld, V, k, idbits, out_ids, out_scores, ld_out);
+    }
     topk_rows_kernel<<<(unsigned)rows, TK_THREADS, 0, (cudaStream_t)stream>>>(
         scores, nullptr, ld, V, k, idbits, out_ids, out_scores, ld_out, 1);
     note_launches(2);
