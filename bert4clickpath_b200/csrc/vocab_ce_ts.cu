@@ -40,6 +40,7 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 // packed columns at [32cg, 32cg+16) - inside its own region, so no warp overwrites columns another
 // warp still has to read.  K step k8 (vocabulary entries 16k8..16k8+15 of the tile) therefore
 // reads A at column 32*(k8>>1) + 8*(k8&1).
+template <int NSB>   // S accumulators in TMEM: 3 at h <= 128, 2 at h = 256
 __global__ void __launch_bounds__(TS_THREADS, 1)
 vocab_ce_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmX,
                        const __grid_constant__ CUtensorMap tmW, const VocabParams p) {
@@ -59,11 +60,14 @@ vocab_ce_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmX,
   uint64_t* x_full = bars;
   uint64_t* w_full = bars + 1;          // [4]
   uint64_t* w_empty = w_full + 4;       // [4]
-  uint64_t* s_full = w_empty + 4;       // [2]
-  uint64_t* s_empty = s_full + 2;       // [2]
-  uint64_t* p_full = s_empty + 2;       // [2]
-  uint64_t* u_full = p_full + 2;        // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(u_full + 2);
+  uint64_t* s_full = w_empty + 4;       // [3]
+  uint64_t* s_empty = s_full + 3;       // [3]
+  uint64_t* p_full = s_empty + 3;       // [3]
+  uint64_t* u_full = p_full + 3;        // [3]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(u_full + 3);
+  // S accumulators: three at h <= 128 (columns 0,128,256; U at 384), two at h = 256 (U at 256).
+  // With three, S runs two tiles ahead of the epilogue: S(t+3) only has to follow U(t), so an
+  // epilogue that takes about as long as the tile's two MMAs no longer stalls on every other tile.
 
   // warp index through shfl: provably warp-uniform, so the role branches are uniform control flow
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
@@ -87,7 +91,7 @@ vocab_ce_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmX,
       mbar_init(&w_full[s], 1);
       mbar_init(&w_empty[s], 1);
     }
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < 3; ++b) {
       mbar_init(&s_full[b], 1);
       mbar_init(&s_empty[b], NUM_EPI_WARPS);
       mbar_init(&p_full[b], NUM_EPI_WARPS);
@@ -99,7 +103,7 @@ vocab_ce_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmX,
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
-  const uint32_t T_U = tmem_base + 256;
+  const uint32_t T_U = tmem_base + (uint32_t)(NSB * VB_N);
 
   if (warp == WARP_TMA) {
     // whole warp, uniform control flow; the TMA instructions are predicated on an elected lane
@@ -130,10 +134,10 @@ vocab_ce_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmX,
     const uint64_t dWu = umma_smem_desc(aW0, 16, 1024);              // W, K-major (B of U)
     auto s_ready = [&](int t) -> bool {
       return mbar_test_all(&w_full[t % NST], (t / NST) & 1) &&
-             mbar_test_all(&s_empty[t & 1], ((t >> 1) & 1) ^ 1);
+             mbar_test_all(&s_empty[t % NSB], ((t / NSB) & 1) ^ 1);
     };
     auto issue_s = [&](int t) {
-      const int st = t % NST, buf = t & 1;
+      const int st = t % NST, buf = t % NSB;
       tc_fence_after();
       const uint32_t wo = (uint32_t)(st * w_bytes) >> 4;
       for (int hb = 0; hb < HB; ++hb) {
@@ -145,7 +149,7 @@ vocab_ce_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmX,
       umma_commit_el(&s_full[buf]);
     };
     auto issue_u = [&](int t) {
-      const int st = t % NST, buf = t & 1;
+      const int st = t % NST, buf = t % NSB;
       tc_fence_after();
       const uint32_t wo = (uint32_t)(st * w_bytes) >> 4;
       const uint32_t tP = tmem_base + buf * VB_N;
@@ -162,7 +166,7 @@ vocab_ce_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmX,
     if (!with_dx) {
       for (int t = 0; t < ntiles; ++t) {
         mbar_wait_all(&w_full[t % NST], (t / NST) & 1);
-        mbar_wait_all(&s_empty[t & 1], ((t >> 1) & 1) ^ 1);
+        mbar_wait_all(&s_empty[t % NSB], ((t / NSB) & 1) ^ 1);
         issue_s(t);
         umma_commit_el(&w_empty[t % NST]);
       }
@@ -171,16 +175,16 @@ vocab_ce_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmX,
       // needs P'(tu).  Neither may hold the other up (a blocking wait for W(t+1) would delay
       // U(t), hence the release of W(t)'s stage, hence the load of W(t+2): loads and tensor
       // work would serialise).  Order constraint: S(t+2) after U(t) - the tensor pipe executes
-      // in issue order, so S(t+2) then cannot overwrite P'(t) before U(t) has read it.
+      // in issue order, so S(t+NSB) then cannot overwrite P'(t) before U(t) has read it.
       int ts = 0, tu = 0;
       while (tu < ntiles) {
         bool progressed = false;
-        if (tu < ts && mbar_test_all(&p_full[tu & 1], (tu >> 1) & 1)) {
+        if (tu < ts && mbar_test_all(&p_full[tu % NSB], (tu / NSB) & 1)) {
           issue_u(tu);
           ++tu;
           progressed = true;
         }
-        if (ts < ntiles && ts <= tu + 1 && s_ready(ts)) {
+        if (ts < ntiles && ts <= tu + NSB - 1 && s_ready(ts)) {
           issue_s(ts);
           ++ts;
           progressed = true;
@@ -207,12 +211,12 @@ vocab_ce_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmX,
     };
     float bias_next = load_bias(0);
     for (int t = 0; t < ntiles; ++t) {
-      const int buf = t & 1;
+      const int buf = t % NSB, sph = (t / NSB) & 1;   // accumulator buffer and its barrier phase
       const int vbase = (t_begin + t) * VB_N + cg * 32;
       sts32f(sb + lane * 4, bias_next * LOG2E);
       __syncwarp();
       bias_next = load_bias(t + 1);  // in flight while this tile is processed
-      mbar_wait(&s_full[buf], (t >> 1) & 1);
+      mbar_wait(&s_full[buf], sph);
       tc_fence_after();
       const uint32_t tS = tmem_base + lane_base + (uint32_t)(buf * VB_N + cg * 32);
       uint32_t r[32];
@@ -240,7 +244,7 @@ vocab_ce_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmX,
       }
       if (with_dx) {
         // the 4 warps that share these rows agree on one running maximum per row
-        const uint32_t mx = aMax + (uint32_t)(buf * (4 * VB_M) + r_in_tile) * 4;
+        const uint32_t mx = aMax + (uint32_t)((t & 1) * (4 * VB_M) + r_in_tile) * 4;
         sts32f(mx + cg * VB_M * 4, cmax);
         asm volatile("bar.sync %0, 128;" ::"r"(2 + q) : "memory");
         cmax = fmaxf(fmaxf(lds32f(mx), lds32f(mx + VB_M * 4)),
@@ -258,7 +262,7 @@ vocab_ce_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmX,
         if (__any_sync(0xffffffffu, jump)) {
           // rare: U(0..t-1) must have retired before its columns are rescaled in TMEM; U(t)
           // cannot start before p_full(t), which this warp only signals after the rescale
-          mbar_wait(&u_full[(t - 1) & 1], ((t - 1) >> 1) & 1);
+          mbar_wait(&u_full[(t - 1) % NSB], ((t - 1) / NSB) & 1);
           tc_fence_after();
           const float f = jump ? ex2(m_ref - m_new) : 1.f;
 #pragma unroll 1
@@ -301,7 +305,7 @@ vocab_ce_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmX,
       }
     }
     if (with_dx && ntiles > 0) {
-      mbar_wait(&u_full[(ntiles - 1) & 1], ((ntiles - 1) >> 1) & 1);
+      mbar_wait(&u_full[(ntiles - 1) % NSB], ((ntiles - 1) / NSB) & 1);
       tc_fence_after();
     }
     if (row < p.M) {
@@ -340,6 +344,7 @@ vocab_ce_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmX,
 // [hb HB][128 rows][128 B].  TMEM columns: S^T0 [0,128) S^T1 [128,256) dW^T [256, 256+h).
 // Epilogue warp (q, cg): lanes = vocabulary entries [32q,+32) of the tile, columns = rows
 // [32cg,+32) of the row tile; dZ^T goes back packed into columns [32cg, 32cg+16) of the S^T buffer.
+template <int NSB>
 __global__ void __launch_bounds__(TS_THREADS, 1)
 vocab_ce_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmX,
                        const __grid_constant__ CUtensorMap tmW, const VocabParams p) {
@@ -360,10 +365,10 @@ vocab_ce_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmX,
   uint64_t* w_empty = bars + 1;       // 1
   uint64_t* x_full = bars + 2;        // 4
   uint64_t* x_empty = x_full + 4;     // 4
-  uint64_t* s_full = x_empty + 4;     // 2
-  uint64_t* s_empty = s_full + 2;     // 2
-  uint64_t* dz_full = s_empty + 2;    // 2
-  uint64_t* dw_full = dz_full + 2;    // 1
+  uint64_t* s_full = x_empty + 4;     // 3
+  uint64_t* s_empty = s_full + 3;     // 3
+  uint64_t* dz_full = s_empty + 3;    // 3
+  uint64_t* dw_full = dz_full + 3;    // 1
   uint64_t* dw_empty = dw_full + 1;   // 1
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dw_empty + 1);
 
@@ -387,7 +392,7 @@ vocab_ce_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmX,
       mbar_init(&x_full[i], 1);
       mbar_init(&x_empty[i], 1);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 3; ++i) {
       mbar_init(&s_full[i], 1);
       mbar_init(&s_empty[i], NUM_EPI_WARPS);
       mbar_init(&dz_full[i], NUM_EPI_WARPS);
@@ -400,7 +405,7 @@ vocab_ce_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmX,
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
-  const uint32_t T_S = tmem_base, T_DW = tmem_base + 256;
+  const uint32_t T_S = tmem_base, T_DW = tmem_base + (uint32_t)(NSB * VB_M);
 
   if (warp == WARP_TMA) {
     // ------------------------------------------------------------------ TMA producer (whole
@@ -434,10 +439,10 @@ vocab_ce_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmX,
     const uint64_t dXn = umma_smem_desc(aX0, VB_M * 128, 1024);           // X, MN-major (B of dW^T)
     auto s_ready = [&](long it) -> bool {
       return mbar_test_all(&x_full[it % XBUF], (uint32_t)((it / XBUF) & 1)) &&
-             mbar_test_all(&s_empty[it & 1], (uint32_t)((it >> 1) & 1) ^ 1);
+             mbar_test_all(&s_empty[it % NSB], (uint32_t)((it / NSB) & 1) ^ 1);
     };
     auto issue_s = [&](long it) {
-      const int xb = (int)(it % XBUF), sb = (int)(it & 1);
+      const int xb = (int)(it % XBUF), sb = (int)(it % NSB);
       tc_fence_after();
       const uint32_t xo = (uint32_t)(xb * x_bytes) >> 4;
       for (int hb = 0; hb < HB; ++hb) {
@@ -451,7 +456,7 @@ vocab_ce_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmX,
     };
     // dW^T[128 v x h] (+)= dZ^T[128 v x 128 rows] X[128 rows x h]: 8 K steps of 16 rows
     auto issue_dw = [&](long it, int i) {
-      const int xb = (int)(it % XBUF), zb = (int)(it & 1);
+      const int xb = (int)(it % XBUF), zb = (int)(it % NSB);
       tc_fence_after();
       const uint32_t xo = (uint32_t)(xb * x_bytes) >> 4;
       const uint32_t tZ = T_S + zb * VB_M;
@@ -469,13 +474,13 @@ vocab_ce_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmX,
       int is = 0, iu = 0;
       while (iu < nm) {
         bool progressed = false;
-        if (iu < is && mbar_test_all(&dz_full[(it0 + iu) & 1], (uint32_t)(((it0 + iu) >> 1) & 1))) {
+        if (iu < is && mbar_test_all(&dz_full[(it0 + iu) % NSB], (uint32_t)(((it0 + iu) / NSB) & 1))) {
           if (iu == 0) mbar_wait_all(dw_empty, (vt & 1) ^ 1);
           issue_dw(it0 + iu, iu);
           ++iu;
           progressed = true;
         }
-        if (is < nm && is <= iu + 1 && s_ready(it0 + is)) {
+        if (is < nm && is <= iu + NSB - 1 && s_ready(it0 + is)) {
           issue_s(it0 + is);
           ++is;
           progressed = true;
@@ -514,7 +519,7 @@ vocab_ce_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmX,
         }
       }
       for (int i = 0; i < nm; ++i, ++it) {
-        const int sbuf = (int)(it & 1);
+        const int sbuf = (int)(it % NSB);
         // dZ = exp2(z2 - lse2 - log2 n): the 1/n_valid factor rides in the exponent; -inf for
         // padded rows and rows past M, which then contribute exactly 0
         const float lneg = (label_next >= 0 && n_valid > 0.f) ? log2_inv_n - lse_next * LOG2E
@@ -529,7 +534,7 @@ vocab_ce_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmX,
           label_next = ok ? __ldg(p.labels + nrow) : -1;
           lse_next = ok ? __ldg(p.lse + nrow) : 0.f;
         }
-        mbar_wait(&s_full[sbuf], (uint32_t)((it >> 1) & 1));
+        mbar_wait(&s_full[sbuf], (uint32_t)((it / NSB) & 1));
         tc_fence_after();
         const uint32_t tS = T_S + lane_base + (uint32_t)(sbuf * VB_M + cg * 32);
         uint32_t r[32];
@@ -615,10 +620,16 @@ int launch_vocab_fwd_ts(const CUtensorMap& tmX, const CUtensorMap& tmW, const Vo
   while (stages > 2 && fwd_ts_smem(p.HB, stages) > 227 * 1024) --stages;
   B4CP_CHECK_ARG(fwd_ts_smem(p.HB, stages) <= 227 * 1024, "vocab_ce_fwd: h=%d does not fit", p.h);
   p.fwd_stages = stages;
-  B4CP_CUDA(cudaFuncSetAttribute(vocab_ce_fwd_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 227 * 1024));
   dim3 grid(p.n_mtiles, p.n_chunks);
-  vocab_ce_fwd_ts_kernel<<<grid, TS_THREADS, fwd_ts_smem(p.HB, stages), st>>>(tmX, tmW, p);
+  if (p.h <= 128) {
+    B4CP_CUDA(cudaFuncSetAttribute(vocab_ce_fwd_ts_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   227 * 1024));
+    vocab_ce_fwd_ts_kernel<3><<<grid, TS_THREADS, fwd_ts_smem(p.HB, stages), st>>>(tmX, tmW, p);
+  } else {
+    B4CP_CUDA(cudaFuncSetAttribute(vocab_ce_fwd_ts_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   227 * 1024));
+    vocab_ce_fwd_ts_kernel<2><<<grid, TS_THREADS, fwd_ts_smem(p.HB, stages), st>>>(tmX, tmW, p);
+  }
   return 0;
 }
 
@@ -634,10 +645,12 @@ int launch_vocab_bwd_ts(const CUtensorMap& tmX, const CUtensorMap& tmW, const Vo
   while (xbuf > 2 && bwd_ts_smem(p.HB, xbuf) > 227 * 1024) --xbuf;
   B4CP_CHECK_ARG(bwd_ts_smem(p.HB, xbuf) <= 227 * 1024, "vocab_ce_bwd: h=%d does not fit", p.h);
   p.fwd_stages = xbuf;
-  B4CP_CUDA(cudaFuncSetAttribute(vocab_ce_bwd_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 227 * 1024));
   const int grid = std::min(148, p.n_vtiles);
-  vocab_ce_bwd_ts_kernel<<<grid, TS_THREADS, bwd_ts_smem(p.HB, xbuf), st>>>(tmX, tmW, p);
+  // two S^T accumulators: a third one (possible at h <= 128) measured slower here (0.84 vs 0.78 ms
+  // at the bench shape) - the backward's epilogue is shorter than its two MMAs
+  B4CP_CUDA(cudaFuncSetAttribute(vocab_ce_bwd_ts_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 227 * 1024));
+  vocab_ce_bwd_ts_kernel<2><<<grid, TS_THREADS, bwd_ts_smem(p.HB, xbuf), st>>>(tmX, tmW, p);
   return 0;
 }
 
