@@ -344,7 +344,11 @@ vocab_ce_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmX,
 // [hb HB][128 rows][128 B].  TMEM columns: S^T0 [0,128) S^T1 [128,256) dW^T [256, 256+h).
 // Epilogue warp (q, cg): lanes = vocabulary entries [32q,+32) of the tile, columns = rows
 // [32cg,+32) of the row tile; dZ^T goes back packed into columns [32cg, 32cg+16) of the S^T buffer.
-template <int NSB>
+// NG = 2: the 16 epilogue warps form two groups of 8 that take ALTERNATE row tiles (group g owns
+// accumulator buffer g; a warp covers 64 columns instead of 32).  With one group all 16 warps wait
+// for the same S^T tile, load it, compute and store in lockstep, so nobody issues during the TMEM
+// load / store latencies; with two groups one computes while the other waits.
+template <int NSB, int NG>
 __global__ void __launch_bounds__(TS_THREADS, 1)
 vocab_ce_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmX,
                        const __grid_constant__ CUtensorMap tmW, const VocabParams p) {
@@ -357,9 +361,9 @@ vocab_ce_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmX,
   const int x_bytes = HB * VB_M * 128;
   uint8_t* sW = smem;
   uint8_t* sX = sW + w_bytes;
-  float* sNeg = reinterpret_cast<float*>(sX + (size_t)XBUF * x_bytes);  // [16 warps][32]
-  int32_t* sLab = reinterpret_cast<int32_t*>(sNeg + 16 * 32);           // [16 warps][32]
-  float* sDB = reinterpret_cast<float*>(sLab + 16 * 32);                // [4 cg][128]
+  float* sNeg = reinterpret_cast<float*>(sX + (size_t)XBUF * x_bytes);  // [16 warps][64]
+  int32_t* sLab = reinterpret_cast<int32_t*>(sNeg + 16 * 64);           // [16 warps][64]
+  float* sDB = reinterpret_cast<float*>(sLab + 16 * 64);                // [4 cg][128]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sDB + 4 * VB_N);
   uint64_t* w_full = bars;            // 1
   uint64_t* w_empty = bars + 1;       // 1
@@ -394,8 +398,8 @@ vocab_ce_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmX,
     }
     for (int i = 0; i < 3; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&s_empty[i], NUM_EPI_WARPS);
-      mbar_init(&dz_full[i], NUM_EPI_WARPS);
+      mbar_init(&s_empty[i], NUM_EPI_WARPS / NG);
+      mbar_init(&dz_full[i], NUM_EPI_WARPS / NG);
     }
     mbar_init(dw_full, 1);
     mbar_init(dw_empty, NUM_EPI_WARPS);
@@ -494,84 +498,102 @@ vocab_ce_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmX,
     // ------------------------------------------------------------------ epilogue (16 warps)
     const int q = warp & 3;
     const int cg = warp >> 2;
+    static_assert(NG == 1 || NSB == 2, "two epilogue groups own one accumulator buffer each");
     const int v_local = q * 32 + lane;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-    const uint32_t aNeg = smem_u32(sNeg + warp * 32);
-    const uint32_t aLab = smem_u32(sLab + warp * 32);
+    const uint32_t aNeg = smem_u32(sNeg + warp * 64);
+    const uint32_t aLab = smem_u32(sLab + warp * 64);
+    constexpr int CW = 32 * NG;                           // columns (rows of the row tile) per warp
+    const int grp = NG == 2 ? (cg & 1) : 0;               // epilogue group
+    const int cb = NG == 2 ? (cg >> 1) * CW : cg * CW;    // first column of this warp
     const int uw = h >> 2;
     const float n_valid = p.loss_stats[1];
     const float inv_n = n_valid > 0.f ? 1.f / n_valid : 0.f;
     const float log2_inv_n = n_valid > 0.f ? -log2f(n_valid) : 0.f;
-    long it = 0;
-    for (int vt = 0; vt < n_my; ++vt) {
+    long it0 = 0;
+    for (int vt = 0; vt < n_my; ++vt, it0 += nm) {
       const int v0 = ((int)blockIdx.x + vt * (int)gridDim.x) * VB_N;
       const int v = v0 + v_local;
       const float b2 = v < p.V ? __ldg(p.bias + v) * LOG2E : -INFINITY;
       float db_acc = 0.f;
-      // statistics of row (32cg + lane) of the next row tile, prefetched one tile ahead
-      int label_next = -1;
-      float lse_next = 0.f;
-      {
-        const int r0 = cg * 32 + lane;
-        if (r0 < p.M) {
-          label_next = __ldg(p.labels + r0);
-          lse_next = __ldg(p.lse + r0);
-        }
+      // this group's first row tile of the vocabulary tile, then every NG-th
+      const int i_first = NG == 2 ? (int)((it0 & 1) != grp) : 0;
+      // statistics of rows (cb + lane [+ 32]) of the group's next row tile, prefetched a tile ahead
+      int label_next[NG];
+      float lse_next[NG];
+#pragma unroll
+      for (int u = 0; u < NG; ++u) {
+        const int r0 = i_first * VB_M + cb + 32 * u + lane;
+        const bool ok = i_first < nm && r0 < p.M;
+        label_next[u] = ok ? __ldg(p.labels + r0) : -1;
+        lse_next[u] = ok ? __ldg(p.lse + r0) : 0.f;
       }
-      for (int i = 0; i < nm; ++i, ++it) {
+      for (int i = i_first; i < nm; i += NG) {
+        const long it = it0 + i;
         const int sbuf = (int)(it % NSB);
         // dZ = exp2(z2 - lse2 - log2 n): the 1/n_valid factor rides in the exponent; -inf for
         // padded rows and rows past M, which then contribute exactly 0
-        const float lneg = (label_next >= 0 && n_valid > 0.f) ? log2_inv_n - lse_next * LOG2E
-                                                               : -INFINITY;
-        sts32f(aNeg + lane * 4, lneg);
-        asm volatile("st.shared.b32 [%0], %1;" ::"r"(aLab + lane * 4), "r"(label_next) : "memory");
-        const bool hit = __any_sync(0xffffffffu, (unsigned)(label_next - v0) < (unsigned)VB_N);
+        bool hit_l = false;
+#pragma unroll
+        for (int u = 0; u < NG; ++u) {
+          const float lneg = (label_next[u] >= 0 && n_valid > 0.f) ? log2_inv_n - lse_next[u] * LOG2E
+                                                                    : -INFINITY;
+          sts32f(aNeg + (32 * u + lane) * 4, lneg);
+          asm volatile("st.shared.b32 [%0], %1;" ::"r"(aLab + (32 * u + lane) * 4), "r"(label_next[u]) : "memory");
+          hit_l = hit_l || (unsigned)(label_next[u] - v0) < (unsigned)VB_N;
+        }
+        const bool hit = __any_sync(0xffffffffu, hit_l);
         __syncwarp();
-        {
-          const int nrow = (i + 1) * VB_M + cg * 32 + lane;
-          const bool ok = (i + 1 < nm) && nrow < p.M;
-          label_next = ok ? __ldg(p.labels + nrow) : -1;
-          lse_next = ok ? __ldg(p.lse + nrow) : 0.f;
+#pragma unroll
+        for (int u = 0; u < NG; ++u) {
+          const int nrow = (i + NG) * VB_M + cb + 32 * u + lane;
+          const bool ok = (i + NG < nm) && nrow < p.M;
+          label_next[u] = ok ? __ldg(p.labels + nrow) : -1;
+          lse_next[u] = ok ? __ldg(p.lse + nrow) : 0.f;
         }
         mbar_wait(&s_full[sbuf], (uint32_t)((it / NSB) & 1));
         tc_fence_after();
-        const uint32_t tS = T_S + lane_base + (uint32_t)(sbuf * VB_M + cg * 32);
-        uint32_t r[32];
-        tmem_ld32(tS, r);
-        tmem_ld_wait();
-        tc_fence_before();
-        mbar_arrive_warp(&s_empty[sbuf]);
-        float g[32];
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const float4 n4 = lds128f(aNeg + j * 4);
-          g[j + 0] = ex2(fmaf(__uint_as_float(r[j + 0]), LOG2E, b2 + n4.x));
-          g[j + 1] = ex2(fmaf(__uint_as_float(r[j + 1]), LOG2E, b2 + n4.y));
-          g[j + 2] = ex2(fmaf(__uint_as_float(r[j + 2]), LOG2E, b2 + n4.z));
-          g[j + 3] = ex2(fmaf(__uint_as_float(r[j + 3]), LOG2E, b2 + n4.w));
-        }
-        if (hit) {  // some row of this 32-row group has its label inside this vocabulary tile
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            int lab;
-            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(lab) : "r"(aLab + j * 4) : "memory");
-            if (lab == v) g[j] -= inv_n;
+        for (int u = 0; u < NG; ++u) {
+          const uint32_t tS = T_S + lane_base + (uint32_t)(sbuf * VB_M + cb + 32 * u);
+          uint32_t r[32];
+          tmem_ld32(tS, r);
+          tmem_ld_wait();
+          if (u == NG - 1) {   // the whole accumulator slice of this warp is in registers
+            tc_fence_before();
+            mbar_arrive_warp(&s_empty[sbuf]);
           }
-        }
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-        uint32_t pk[16];
+          float g[32];
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          a0 += g[j + 0];
-          a1 += g[j + 1];
-          a2 += g[j + 2];
-          a3 += g[j + 3];
-          pk[j / 2] = pack_bf16x2(g[j], g[j + 1]);
-          pk[j / 2 + 1] = pack_bf16x2(g[j + 2], g[j + 3]);
+          for (int j = 0; j < 32; j += 4) {
+            const float4 n4 = lds128f(aNeg + (32 * u + j) * 4);
+            g[j + 0] = ex2(fmaf(__uint_as_float(r[j + 0]), LOG2E, b2 + n4.x));
+            g[j + 1] = ex2(fmaf(__uint_as_float(r[j + 1]), LOG2E, b2 + n4.y));
+            g[j + 2] = ex2(fmaf(__uint_as_float(r[j + 2]), LOG2E, b2 + n4.z));
+            g[j + 3] = ex2(fmaf(__uint_as_float(r[j + 3]), LOG2E, b2 + n4.w));
+          }
+          if (hit) {  // some row of this warp's group has its label inside this vocabulary tile
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              int lab;
+              asm volatile("ld.shared.b32 %0, [%1];" : "=r"(lab) : "r"(aLab + (32 * u + j) * 4) : "memory");
+              if (lab == v) g[j] -= inv_n;
+            }
+          }
+          float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+          uint32_t pk[16];
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            a0 += g[j + 0];
+            a1 += g[j + 1];
+            a2 += g[j + 2];
+            a3 += g[j + 3];
+            pk[j / 2] = pack_bf16x2(g[j], g[j + 1]);
+            pk[j / 2 + 1] = pack_bf16x2(g[j + 2], g[j + 3]);
+          }
+          db_acc += (a0 + a1) + (a2 + a3);
+          tmem_st16(tS, pk);
         }
-        db_acc += (a0 + a1) + (a2 + a3);
-        tmem_st16(tS, pk);
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive_warp(&dz_full[sbuf]);  // (its __syncwarp also orders the sNeg/sLab reuse)
@@ -634,7 +656,7 @@ int launch_vocab_fwd_ts(const CUtensorMap& tmX, const CUtensorMap& tmW, const Vo
 }
 
 static size_t bwd_ts_smem(int HB, int xbuf) {
-  return (size_t)2 * HB * 8192 + (size_t)xbuf * HB * VB_M * 128 + 2 * 16 * 32 * 4 + 4 * VB_N * 4 +
+  return (size_t)2 * HB * 8192 + (size_t)xbuf * HB * VB_M * 128 + 2 * 16 * 64 * 4 + 4 * VB_N * 4 +
          256 + 1024;
 }
 
@@ -648,9 +670,16 @@ int launch_vocab_bwd_ts(const CUtensorMap& tmX, const CUtensorMap& tmW, const Vo
   const int grid = std::min(148, p.n_vtiles);
   // two S^T accumulators: a third one (possible at h <= 128) measured slower here (0.84 vs 0.78 ms
   // at the bench shape) - the backward's epilogue is shorter than its two MMAs
-  B4CP_CUDA(cudaFuncSetAttribute(vocab_ce_bwd_ts_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 227 * 1024));
-  vocab_ce_bwd_ts_kernel<2><<<grid, TS_THREADS, bwd_ts_smem(p.HB, xbuf), st>>>(tmX, tmW, p);
+  const char* pp = getenv("B4CP_BWD_GROUPS");
+  if (pp && pp[0] == '1') {
+    B4CP_CUDA(cudaFuncSetAttribute(vocab_ce_bwd_ts_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   227 * 1024));
+    vocab_ce_bwd_ts_kernel<2, 1><<<grid, TS_THREADS, bwd_ts_smem(p.HB, xbuf), st>>>(tmX, tmW, p);
+  } else {
+    B4CP_CUDA(cudaFuncSetAttribute(vocab_ce_bwd_ts_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   227 * 1024));
+    vocab_ce_bwd_ts_kernel<2, 2><<<grid, TS_THREADS, bwd_ts_smem(p.HB, xbuf), st>>>(tmX, tmW, p);
+  }
   return 0;
 }
 
