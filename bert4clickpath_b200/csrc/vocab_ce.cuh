@@ -1,6 +1,5 @@
-// Declarations shared by the two generations of the fused vocabulary-stage kernels
-// (vocab_ce.cu: SS-form, P'/dZ staged in shared memory; vocab_ce_ts.cu: TS-form, P'/dZ fed to the
-// second MMA straight from TMEM).
+// Declarations shared by the host side of the fused vocabulary stage (vocab_ce.cu: C ABI, chunk
+// planner, merge / dX kernels) and its two tcgen05 kernels (vocab_ce_ts.cu).
 #pragma once
 #include "common.cuh"
 
@@ -35,19 +34,13 @@ struct VocabParams {
   const float* loss_stats;  // [2]: (sum, n_valid)
   float* dW;                // [h][V]
   float* db;                // [V]
-  int debug;                // timing experiments only (B4CP_DEBUG_BWD bitmask)
 };
 
-// Warp roles (both kernels, 640 threads): warps 0-15 = epilogue, warp 16 = TMA producer + TMEM
-// owner, warp 17 = MMA issuer, warps 18-19 = bias-gradient column sums (backward only).
-// Epilogue warp w reads TMEM lanes [32*(w%4), +32) (hardware restriction) and owns the 32-column
-// group cg = w/4 of every 128-wide tile, so each scheduler has 4 epilogue warps to hide latency.
-// The single-thread roles sit at the HIGHEST warp ids: the issue arbiter favours high warp ids,
-// and a producer / MMA issuer starved by polling epilogue warps stalls the whole pipeline.
-static constexpr int NUM_THREADS = 640;
+// Warp roles (both kernels, 576 threads): warps 0-15 = epilogue, warp 16 = TMA producer + TMEM
+// owner, warp 17 = MMA issuer.  Epilogue warp w reads TMEM lanes [32*(w%4), +32) (hardware
+// restriction); each scheduler has 4 epilogue warps to hide latency.
 static constexpr int NUM_EPI_WARPS = 16;
-static constexpr int NUM_EPI_THREADS = 512;
-static constexpr int WARP_TMA = 16, WARP_MMA = 17, WARP_DB0 = 18;
+static constexpr int WARP_TMA = 16, WARP_MMA = 17;
 static constexpr float LN2 = 0.6931471805599453f;
 
 // TS-form launchers (vocab_ce_ts.cu)

@@ -1,5 +1,5 @@
 """Times the fused vocabulary-stage kernels: python scripts/time_vocab.py M [h] [V].
-B4CP_VOCAB_IMPL=ss selects the first-generation (shared-memory staged) kernels."""
+B4CP_BWD_GROUPS=1 selects the single-group backward epilogue."""
 import sys, os, torch, numpy as np
 sys.path.insert(0, ".")
 from bert4clickpath_b200 import ops
@@ -18,7 +18,7 @@ def t(fn, n=10):
     for _ in range(n): fn()
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / n
-dxok = h in (128, 256) and not (h == 256 and os.environ.get("B4CP_VOCAB_IMPL", "").startswith("s"))
+dxok = h in (128, 256)
 tf0 = t(lambda: ops.vocab_ce_fwd(xb, M, h, wb, bias, V, labels, lse, tgt, want_dx=False))
 fl = 2.0 * M * h * V
 if not dxok:
@@ -28,4 +28,4 @@ tf = t(lambda: ops.vocab_ce_fwd(xb, M, h, wb, bias, V, labels, lse, tgt, want_dx
 ops.ce_loss_reduce(lse, tgt, labels, stats)
 tb = t(lambda: ops.vocab_ce_bwd(xb, M, h, wb, bias, V, labels, lse, stats, dW, db))
 td = t(lambda: ops.vocab_ce_dx(M, h, V, labels, stats, wb, None, dX, None))
-print(f"impl={os.environ.get('B4CP_VOCAB_IMPL','ts')} M={M} h={h} V={V}: fwd(no dx) {tf0:.3f} ms ({fl/tf0/1e9:.0f} TF/s), fwd+U {tf:.3f} ms ({2*fl/tf/1e9:.0f} TF/s of 2 MMAs), dx {td:.3f} ms, bwd {tb:.3f} ms ({2*fl/tb/1e9:.0f} TF/s of 2 MMAs; {fl/tb/1e9:.0f} algorithmic); total {tf+td+tb:.3f} ms = {3*fl/(tf+td+tb)/1e9:.0f} TF/s useful (6MhV)")
+print(f"M={M} h={h} V={V}: fwd(no dx) {tf0:.3f} ms ({fl/tf0/1e9:.0f} TF/s), fwd+U {tf:.3f} ms ({2*fl/tf/1e9:.0f} TF/s of 2 MMAs), dx {td:.3f} ms, bwd {tb:.3f} ms ({2*fl/tb/1e9:.0f} TF/s of 2 MMAs; {fl/tb/1e9:.0f} algorithmic); total {tf+td+tb:.3f} ms = {3*fl/(tf+td+tb)/1e9:.0f} TF/s useful (6MhV)")
