@@ -1,4 +1,6 @@
-"""Small invocations of the kernels added this round, for compute-sanitizer --tool memcheck."""
+"""Small invocations of the kernels added late in round 1 (TS vocabulary kernels at h = 128 / 256,
+streaming top-k incl. its fallbacks, long-vocabulary fused top-k, tile-based embedding backward,
+S = 202 attention): a quick on-device exercise (compute-sanitizer is closed on this pool)."""
 import sys, numpy as np, torch
 sys.path.insert(0, ".")
 from bert4clickpath_b200 import ops
