@@ -291,6 +291,39 @@ def binary_head_fwd(x, layers, w_out, b_out):
     return 1.0 / (1.0 + np.exp(-z)), z, acts
 
 
+def binary_head_loss_and_grads(x, layers, w_out, b_out, y_true, pos_weight=None, label_pad=LABEL_PAD):
+    """Loss and gradients of BinaryClassificationHead (head.py:13-26) under
+    MaskedLoss(K.binary_crossentropy, pos_weight) (losses.py:31-98) - what TF autodiff derives:
+      l_i = -w_i (y log(pc + e) + (1 - y) log(1 - pc + e)), pc = clip(p, e, 1 - e), e = 1e-7,
+      loss = sum_i mask_i l_i / sum_i mask_i  [/ ((pos_weight + 1) / 2) when pos_weight is given]
+    (the clip passes a gradient only strictly inside (e, 1 - e)).
+    x: (..., in) head input rows; y_true: (...) labels padded with label_pad.
+    Returns loss, dx (same shape as x), [(dW, db) per MLP layer], dW_out, db_out."""
+    x = np.asarray(x, dtype=np.float64)
+    y = np.asarray(y_true, dtype=np.float64)
+    p, z, acts = binary_head_fwd(x, layers, w_out, b_out)
+    mask = (y != label_pad)
+    n = mask.sum()
+    eps = 1e-7
+    pc = np.clip(p, eps, 1 - eps)
+    yy = np.where(mask, y, 0.0)
+    item = -(yy * np.log(pc + eps) + (1 - yy) * np.log(1 - pc + eps))
+    w = np.where(yy == 1, pos_weight, 1.0) if pos_weight is not None else np.ones_like(item)
+    norm = ((pos_weight + 1.0) / 2) if pos_weight is not None else 1.0
+    loss = (item * w * mask).sum() / n / norm if n > 0 else 0.0
+    inside = (p > eps) & (p < 1 - eps)
+    dl_dp = -(yy / (pc + eps) - (1 - yy) / (1 - pc + eps)) * w * inside
+    dz = np.where(mask, dl_dp * p * (1 - p), 0.0) / max(n, 1) / norm       # (...)
+    h = acts[-1]
+    dz2 = dz.reshape(-1, 1)
+    h2 = h.reshape(-1, h.shape[-1])
+    dW_out = h2.T @ dz2
+    db_out = dz2.sum(0)
+    dh = (dz2 @ np.asarray(w_out, dtype=np.float64).T).reshape(h.shape)
+    dx, layer_grads = mlp_bwd(dh, acts, layers)
+    return loss, dx, layer_grads, dW_out, db_out
+
+
 # ------------------------------------------- examples/BERT4Rec/source/utils.py:56-113 (adaptor)
 def cloze_output_adaptor(y_true, y_pred):
     y_pred = y_pred.reshape(-1, y_pred.shape[-1])

@@ -365,6 +365,19 @@ def test_binary_head_training_matches_autograd(cuda_lib, segment, dims):
         g, w = grads[k].astype(np.float64).reshape(t.shape), t.grad.numpy()
         e = np.linalg.norm(g - w) / max(np.linalg.norm(w), 1e-12)
         assert e < 3e-2, (k, e)
+    # ---- and against the NumPy oracle's restatement (exact float64 math, no bf16 rounding):
+    # the stated bf16 tolerance
+    layers = [(Wts[f"head.{i}.w"].astype(np.float64), Wts[f"head.{i}.b"].astype(np.float64)) for i in range(len(dims))]
+    o_loss, _, o_lg, o_dWo, o_dbo = O.binary_head_loss_and_grads(
+        x[:, s0:s1].astype(np.float64), layers, Wts["head.out.w"].astype(np.float64),
+        Wts["head.out.b"].astype(np.float64), y, pos_weight=pw)
+    assert abs(got_loss - o_loss) < 2e-2 * abs(o_loss)
+    want = {"head.out.w": o_dWo, "head.out.b": o_dbo}
+    for i, (dw, db_) in enumerate(o_lg):
+        want[f"head.{i}.w"], want[f"head.{i}.b"] = dw, db_
+    for k, w in want.items():
+        g = grads[k].astype(np.float64).reshape(w.shape)
+        assert np.linalg.norm(g - w) / max(np.linalg.norm(w), 1e-12) < BF16_TOL, k
     enc = [k for k in grads if not k.startswith("head.")]
     assert all(np.isfinite(grads[k]).all() for k in enc) and any(np.abs(grads[k]).max() > 0 for k in enc)
     # ---- Keras-style training: the loss goes down
