@@ -33,6 +33,11 @@ def __getattr__(name):
         "PredictedPositives": ".metrics",
         "F1Score": ".metrics",
         "MaskedMetric": ".metrics",
+        "CustomLRSchedule": ".training_utils",
+        "CustomExponentialDecayLR": ".training_utils",
+        "BestModelSaverCallback": ".training_utils",
+        "ReduceLROnPlateau": ".training_utils",
+        "EarlyStopping": ".training_utils",
     }
     if name in table:
         return getattr(importlib.import_module(table[name], __name__), name)

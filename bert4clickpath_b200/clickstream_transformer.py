@@ -145,6 +145,8 @@ class ClickstreamTransformer:
         self.metrics = []
         self.process_group = None
         self._step_seed = 0
+        self._opt_iterations = 0
+        self.stop_training = False
 
     # ------------------------------------------------------------------ construction helpers
     @staticmethod
@@ -265,9 +267,18 @@ class ClickstreamTransformer:
         self._step_seed += 1
         return self._step_seed
 
+    def _next_lr(self, opt):
+        """Learning rate of this update: a float, or a schedule evaluated at the optimizer's
+        iteration count (Keras passes `iterations`, which is 0 on the first update)."""
+        from .training_utils import current_learning_rate
+        lr = current_learning_rate(opt, self._opt_iterations)
+        self._opt_iterations += 1
+        return lr
+
     # ------------------------------------------------------------------ training (Keras-like)
     def compile(self, optimizer=None, loss=None, metrics=None):
         self.optimizer = optimizer if optimizer is not None else Adam()
+        self._opt_iterations = 0
         self.loss = loss
         self.metrics = list(metrics or [])
 
@@ -378,14 +389,14 @@ class ClickstreamTransformer:
             stats = self.binary_forward_backward(ids_list, y, B, S, (starts, ends), pos_weight=pw,
                                                  seed=self._next_seed())
             opt = self.optimizer or Adam()
-            self.store.adam(opt.learning_rate, opt.beta_1, opt.beta_2, opt.epsilon)
+            self.store.adam(self._next_lr(opt), opt.beta_1, opt.beta_2, opt.epsilon)
             s = stats.cpu().numpy()
             mean = float(s[0] / s[1]) if s[1] > 0 else 0.0
             return {'loss': mean / ((pw + 1.0) / 2) if pw is not None else mean}
         stats = self.cloze_forward_backward(ids_list, y, B, S, n_masked=n_host,
                                             seed=self._next_seed())
         opt = self.optimizer or Adam()
-        self.store.adam(opt.learning_rate, opt.beta_1, opt.beta_2, opt.epsilon)
+        self.store.adam(self._next_lr(opt), opt.beta_1, opt.beta_2, opt.epsilon)
         s = stats.cpu().numpy()
         logs = {'loss': float(s[0] / s[1]) if s[1] > 0 else 0.0}
         for m in self.metrics:
@@ -404,15 +415,33 @@ class ClickstreamTransformer:
             logs[m.name] = float(m.result())
         return logs
 
-    def fit(self, dataset, steps_per_epoch, epochs=1, verbose=0):
-        """Minimal stand-in for Keras Model.fit over an iterator of (inputs, labels)."""
-        history = []
-        it = iter(dataset)
-        for _ in range(epochs):
-            logs = {}
-            for _ in range(steps_per_epoch):
-                logs = self.train_step(next(it))
-            history.append(logs)
-            if verbose:
-                print(logs)
-        return history
+    def fit(self, dataset, steps_per_epoch, epochs=1, verbose=0, validation_data=None,
+            validation_steps=None, callbacks=()):
+        """Keras Model.fit over an iterator of (inputs, labels) (examples/BERT4Rec/source/
+        main.py:159-165): see training_utils.run_fit for the epoch / validation / callback order."""
+        from .training_utils import run_fit
+        return run_fit(self, dataset, steps_per_epoch, epochs=epochs, verbose=verbose,
+                       validation_data=validation_data, validation_steps=validation_steps,
+                       callbacks=callbacks)
+
+    # ------------------------------------------------------------------ weights (N4)
+    def get_weights(self):
+        """{name: float32 ndarray} in the reference's per-layer layout (separate wq / wk / wv)."""
+        from .weights import to_reference_layout
+        return to_reference_layout(self.store.get_weights())
+
+    def set_weights(self, weights):
+        from .weights import to_store_layout
+        self.store.set_weights(to_store_layout(weights))
+
+    def save_weights(self, path):
+        """One .npz keyed by the TF object-checkpoint keys of the reference's variables
+        (weights.tf_checkpoint_key), so the same file can be produced on a TensorFlow box from a
+        reference checkpoint and loaded here, and the other way round."""
+        from .weights import export_reference_variables
+        np.savez(path, **export_reference_variables(self.store.get_weights()))
+
+    def load_weights(self, path):
+        from .weights import import_reference_variables
+        with np.load(path) as z:
+            self.store.set_weights(import_reference_variables({k: z[k] for k in z.files}))

@@ -31,10 +31,18 @@ class ClozeTrainStep:
         self.model = model
         self.opt = optimizer or Adam()
         self.seed = 0
+        self.iterations = 0
         self.use_graph = bool(use_graph)
         self._graphs = {}
         self._dev_ids = self._dev_labels = None
         self._host_stats = torch.empty(2, dtype=F32).pin_memory() if torch.cuda.is_available() else None
+
+    def _lr(self):
+        lr = self.opt.learning_rate
+        if callable(lr):        # training_utils.CustomLRSchedule / CustomExponentialDecayLR
+            lr = lr(self.iterations)
+        self.iterations += 1
+        return float(lr)
 
     def to_device(self, batch):
         """batch: dict from synthetic.make_cloze_batch (host NumPy)."""
@@ -46,7 +54,7 @@ class ClozeTrainStep:
     def _eager(self, db, seed):
         stats = self.model.cloze_forward_backward(db.ids, db.labels, db.B, db.S,
                                                   n_masked=db.n_masked, training=True, seed=seed)
-        self.model.store.adam(self.opt.learning_rate, self.opt.beta_1, self.opt.beta_2,
+        self.model.store.adam(self._lr(), self.opt.beta_1, self.opt.beta_2,
                               self.opt.epsilon)
         return stats
 
@@ -57,19 +65,27 @@ class ClozeTrainStep:
         if st is None:
             st = self._graphs[key] = dict(calls=0, graph=None)
         seed = ops.device_seed(self.model.store.step_dev)
+        if callable(self.opt.learning_rate):
+            raise TypeError("a learning-rate schedule changes Adam's scalar every step: "
+                            "use use_graph=False")
+        hp = (float(self.opt.learning_rate), self.opt.beta_1, self.opt.beta_2, self.opt.epsilon)
+        if st["graph"] is not None and st["hp"] != hp:
+            st["graph"] = None      # Adam's scalars are baked into the captured launches
+                                    # (ReduceLROnPlateau changes lr between epochs): re-capture
         if st["graph"] is None:
             st["calls"] += 1
             if st["calls"] <= self.GRAPH_WARMUP_STEPS:   # real steps; they also size every buffer
                 return self._eager(db, seed)
-            st["ids"] = [torch.empty_like(t) for t in db.ids]
-            st["labels"] = torch.empty_like(db.labels)
+            if "ids" not in st:     # kept across re-captures: step_host copies into them
+                st["ids"] = [torch.empty_like(t) for t in db.ids]
+                st["labels"] = torch.empty_like(db.labels)
             sdb = DeviceBatch(st["ids"], st["labels"], db.B, db.S, db.n_masked)
             timer_was, ops.TIMER.enabled = ops.TIMER.enabled, False
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 st["stats"] = self._eager(sdb, seed)
             ops.TIMER.enabled = timer_was
-            st["graph"] = g
+            st["graph"], st["hp"] = g, hp
         for dst, src in zip(st["ids"], db.ids):
             if dst.data_ptr() != src.data_ptr():
                 dst.copy_(src, non_blocking=True)
@@ -86,7 +102,7 @@ class ClozeTrainStep:
         stats = self.model.cloze_forward_backward(db.ids, db.labels, db.B, db.S,
                                                   n_masked=db.n_masked, training=True,
                                                   seed=self.seed)
-        self.model.store.adam(self.opt.learning_rate, self.opt.beta_1, self.opt.beta_2,
+        self.model.store.adam(self._lr(), self.opt.beta_1, self.opt.beta_2,
                               self.opt.epsilon)
         return stats
 
