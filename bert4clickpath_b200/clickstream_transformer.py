@@ -375,6 +375,65 @@ class ClickstreamTransformer:
         self._last_probs = probs.view(B, Ls)
         return stats
 
+    def multilabel_forward_backward(self, ids_list, y_f32, B, S, segment_bounds, pos_weight=None,
+                                    label_pad=LABEL_PAD, training=True, seed=0):
+        """Segment mode with MultiLabel_MultiClass_classification (head.py:50-69): encoder -> the
+        single row of segment `segment_to_head` (tf.squeeze(axis=1) needs length 1, e.g. [CLS]) ->
+        ReLU MLP -> Dense(V, sigmoid) -> MaskedLoss(binary_crossentropy, pos_weight) over every
+        (row, class) cell, and the whole backward.  y_f32: (B, V) float32, label_pad = ignored
+        cell.  Same contract as binary_forward_backward."""
+        from .head import MultiLabel_MultiClass_classification
+        head = self.head
+        assert isinstance(head, MultiLabel_MultiClass_classification) and self.segment_to_head is not None
+        x = self._encode(ids_list, B, S, training, seed)
+        starts, ends = segment_bounds
+        s0, s1 = int(starts[self.segment_to_head]), int(ends[self.segment_to_head])
+        if s1 - s0 != 1:
+            raise ValueError(f"MultiLabel_MultiClass_classification squeezes axis 1: segment "
+                             f"{self.segment_to_head} has length {s1 - s0}, not 1")
+        M, V, d, h = B, head.output_vocab_size, self.d_model, head.h
+        key = (B, S, s0, s1)
+        if getattr(self, "_seg_rows_key", None) != key:
+            idx = (np.arange(B, dtype=np.int64) * S + s0)
+            self._seg_rows = torch.from_numpy(idx.astype(np.int32)).cuda()
+            self._seg_rows_key = key
+        row_index = self._seg_rows
+        hsel = self.pool.get("hsel_bin", (M, ld8(d)), BF16)
+        ops.gather_rows(x, row_index, None, hsel)
+        ab = head.hidden(hsel, M)
+        W, b = self.store[f"{head.prefix}.out.w"], self.store[f"{head.prefix}.out.b"]
+        z = self.pool.get("z_ml", (M, V))
+        ops.gemm(ab, 0, W.wb, 1, M, V, h, bias=b.w, out_f32=z)
+        probs = ops.sigmoid(z.view(-1), out=self.pool.get("p_ml", (M * V,)))
+        y = y_f32.reshape(-1).contiguous()
+        assert y.numel() == M * V, "labels must be (B, output_vocab_size)"
+        stats = ops.masked_bce(y, probs, label_pad, pos_weight)
+        self._allreduce(stats)
+        dzb = self.pool.get("dz_ml", (M, ld8(V)), BF16)
+        ops.sigmoid_bce_dz(y, probs, M, V, label_pad, pos_weight, stats, dz_bf16=dzb)
+        ops.gemm_splitk(ab, 1, dzb, 1, h, V, M, W.g, ws_name="splitk_vocab")
+        ops.colsum_bf16(dzb, M, V, b.g)
+        # d(ab) = dz W^T: K = V is long and M x h small -> split-K with a (ReLU-gated) reduce
+        splits = ops.gemm_splits_for(M, h, V)
+        part = ops.WS.get("splitk_dx", splits * M * h * 4).view(F32)[: splits * M * h]
+        part = part.view(splits, M, h)
+        ops.gemm(dzb, 0, W.wb, 0, M, h, V, out_f32=part, splits=splits)
+        dsel = self.pool.get("dsel_bin", (M, d))
+        mlp = head.mlp
+        if mlp.dims:
+            dab = self.pool.get("dab_bin", (M, ld8(mlp.out_dim)), BF16)
+            ops.reduce_splits_ex(part, M, h, ab, None, dab)
+            mlp.backward(dab, dsel)
+        else:
+            ops.reduce_splits_ex(part, M, h, None, dsel, None)
+        dx = self.pool.get("dx_top", (B * S, d), zero=True)
+        ops.scatter_rows(dsel, row_index, dx)
+        self.transformer.engine.backward(dx)
+        for run in self.store.replicated_grad_runs():
+            self._allreduce(run)
+        self._last_probs = probs.view(B, V)
+        return stats
+
     def train_step(self, data, n_masked=None):
         """Keras Model.train_step: data = (inputs dict, labels (B, max_n_masked) float32).
         Returns {'loss': float} (+ metric results)."""
@@ -383,11 +442,14 @@ class ClickstreamTransformer:
         y = torch.as_tensor(np.ascontiguousarray(y, dtype=np.float32)) if not torch.is_tensor(y) else y
         n_host = int((y != LABEL_PAD).sum().item())
         y = y.to(device="cuda", dtype=F32).contiguous()
-        from .head import BinaryClassificationHead
-        if isinstance(self.head, BinaryClassificationHead) and self.segment_to_head is not None:
+        from .head import BinaryClassificationHead, MultiLabel_MultiClass_classification
+        sigmoid_head = isinstance(self.head, (BinaryClassificationHead,
+                                              MultiLabel_MultiClass_classification))
+        if sigmoid_head and self.segment_to_head is not None:
             pw = getattr(self.loss, "pos_weight", None)
-            stats = self.binary_forward_backward(ids_list, y, B, S, (starts, ends), pos_weight=pw,
-                                                 seed=self._next_seed())
+            step = (self.binary_forward_backward if isinstance(self.head, BinaryClassificationHead)
+                    else self.multilabel_forward_backward)
+            stats = step(ids_list, y, B, S, (starts, ends), pos_weight=pw, seed=self._next_seed())
             opt = self.optimizer or Adam()
             self.store.adam(self._next_lr(opt), opt.beta_1, opt.beta_2, opt.epsilon)
             s = stats.cpu().numpy()

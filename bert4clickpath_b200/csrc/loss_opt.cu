@@ -364,18 +364,11 @@ namespace b4cp {
 //   w_i = pos_weight where y == 1 (if given), loss = sum l_i / n over labels != label_pad,
 //   divided by (pos_weight + 1) / 2 when pos_weight is given (losses.py:94-96).
 // dz_i = dl/dp * p (1 - p) / n (the clip passes a gradient only strictly inside (e, 1 - e)).
-__global__ void __launch_bounds__(256)
-binary_head_dz_kernel(const float* __restrict__ y_true, const float* __restrict__ p, long n,
-                      float label_pad, float pos_weight, int use_pos_weight,
-                      const float* __restrict__ stats, float* __restrict__ dz) {
-  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
-  if (i >= n) return;
+__device__ __forceinline__ float bce_dz_item(float yt, float pi, float nv, float label_pad,
+                                             float pos_weight, int use_pos_weight) {
   const float eps = 1e-7f;
-  const float nv = stats[1];
-  const float yt = y_true[i];
   float g = 0.f;
   if (yt != label_pad && nv > 0.f) {
-    const float pi = p[i];
     if (pi > eps && pi < 1.f - eps) {
       float dl = -(yt / (pi + eps) - (1.f - yt) / (1.f - pi + eps));
       if (use_pos_weight && yt == 1.f) dl *= pos_weight;
@@ -384,7 +377,40 @@ binary_head_dz_kernel(const float* __restrict__ y_true, const float* __restrict_
       if (use_pos_weight) g *= 2.f / (pos_weight + 1.f);
     }
   }
-  dz[i] = g;
+  return g;
+}
+
+__global__ void __launch_bounds__(256)
+binary_head_dz_kernel(const float* __restrict__ y_true, const float* __restrict__ p, long n,
+                      float label_pad, float pos_weight, int use_pos_weight,
+                      const float* __restrict__ stats, float* __restrict__ dz) {
+  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  dz[i] = bce_dz_item(y_true[i], p[i], stats[1], label_pad, pos_weight, use_pos_weight);
+}
+
+// The same item-wise gradient over a (rows, cols) sigmoid output (MultiLabel_MultiClass_
+// classification, head.py:50-69: every (row, class) cell is one item of the masked mean), written
+// as the bf16 [rows][ld] operand of the dW / dx GEMMs (pad columns zeroed) and/or fp32 [rows][cols].
+__global__ void __launch_bounds__(256)
+sigmoid_bce_dz_kernel(const float* __restrict__ y_true, const float* __restrict__ p, long rows,
+                      int cols, long ld, float label_pad, float pos_weight, int use_pos_weight,
+                      const float* __restrict__ stats, float* __restrict__ dz_f32,
+                      __nv_bfloat16* __restrict__ dz_bf16) {
+  const float nv = stats[1];
+  const long total = rows * ld;
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long)gridDim.x * blockDim.x) {
+    const long r = idx / ld;
+    const int c = (int)(idx - r * ld);
+    float g = 0.f;
+    if (c < cols) {
+      const long i = r * cols + c;
+      g = bce_dz_item(y_true[i], p[i], nv, label_pad, pos_weight, use_pos_weight);
+      if (dz_f32) dz_f32[i] = g;
+    }
+    if (dz_bf16) dz_bf16[idx] = __float2bfloat16_rn(g);
+  }
 }
 
 // d_ab[i][c] = dz_i * w[c] (zeroed where the ReLU output ab[i][c] <= 0 when `gated`)
@@ -452,6 +478,24 @@ extern "C" int b4cp_binary_head_bwd(const float* y_true, const float* probs, lon
   binary_head_dw_kernel<<<ceil_div(h, 32), 256, 0, st>>>(dz, (const __nv_bfloat16*)ab_bf16, ld_ab, M,
                                                          h, dw, db);
   note_launches(3);
+  B4CP_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int b4cp_sigmoid_bce_dz(const float* y_true, const float* probs, long rows, int cols,
+                                   float label_pad, float pos_weight, int use_pos_weight,
+                                   const float* stats, float* dz_f32, void* dz_bf16, long ld_bf16,
+                                   void* stream) {
+  B4CP_CHECK_ARG(y_true && probs && stats && (dz_f32 || dz_bf16), "sigmoid_bce_dz: null argument");
+  B4CP_CHECK_ARG(cols >= 1 && (!dz_bf16 || ld_bf16 >= cols), "sigmoid_bce_dz: cols=%d ld=%ld", cols,
+                 ld_bf16);
+  if (rows == 0) return 0;
+  const long ld = dz_bf16 ? ld_bf16 : cols;
+  const int blocks = (int)std::min<long>(ceil_div(rows * ld, 256), 148L * 16);
+  sigmoid_bce_dz_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
+      y_true, probs, rows, cols, ld, label_pad, pos_weight, use_pos_weight, stats, dz_f32,
+      (__nv_bfloat16*)dz_bf16);
+  note_launches(1);
   B4CP_LAUNCH_CHECK();
   return 0;
 }

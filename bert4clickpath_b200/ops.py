@@ -377,6 +377,15 @@ def binary_head_bwd(y_true, probs, label_pad, pos_weight, stats, ab, h, w_out, g
            L.ptr(db), L.stream_ptr())
 
 
+def sigmoid_bce_dz(y_true, probs, rows, cols, label_pad, pos_weight, stats, dz_f32=None,
+                   dz_bf16=None):
+    """Item-wise gradient of MaskedLoss(binary_crossentropy) through a (rows, cols) sigmoid output."""
+    L.call("b4cp_sigmoid_bce_dz", L.ptr(y_true), L.ptr(probs), L.c_long(rows), L.c_int(cols),
+           L.c_float(label_pad), L.c_float(pos_weight if pos_weight is not None else 1.0),
+           L.c_int(0 if pos_weight is None else 1), L.ptr(stats), L.ptr(dz_f32), L.ptr(dz_bf16),
+           L.c_long(dz_bf16.stride(0) if dz_bf16 is not None else 0), L.stream_ptr())
+
+
 def _vocab_ws(M, V, h):
     fn = L.lib().b4cp_vocab_ce_workspace_bytes
     fn.restype = ctypes.c_long

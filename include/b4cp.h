@@ -240,6 +240,15 @@ int b4cp_binary_head_bwd(const float* y_true, const float* probs, long M, float 
                          float* dz, float* dab_f32, void* dab_bf16, long ld_dab, float* dw,
                          float* db, void* stream);
 
+/* The same item-wise gradient over a (rows, cols) sigmoid output — MultiLabel_MultiClass_
+ * classification (head.py:50-69) under MaskedLoss(binary_crossentropy, pos_weight): every
+ * (row, class) cell whose label != label_pad is one item of the masked mean (losses.py:50-98).
+ * y_true / probs fp32 [rows][cols]; writes dz as fp32 [rows][cols] and/or bf16 [rows][ld_bf16]
+ * (pad columns zeroed) — the operand of the dW = ab^T dz and dx = dz W^T GEMMs. */
+int b4cp_sigmoid_bce_dz(const float* y_true, const float* probs, long rows, int cols,
+                        float label_pad, float pos_weight, int use_pos_weight, const float* stats,
+                        float* dz_f32, void* dz_bf16, long ld_bf16, void* stream);
+
 /* sigmoid output activation of BinaryClassificationHead / MultiLabel_MultiClass_classification
  * (head.py:11, :57) */
 int b4cp_sigmoid(const float* z, float* out, long n, void* stream);

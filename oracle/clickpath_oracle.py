@@ -324,6 +324,44 @@ def binary_head_loss_and_grads(x, layers, w_out, b_out, y_true, pos_weight=None,
     return loss, dx, layer_grads, dW_out, db_out
 
 
+def multilabel_head_fwd(x, layers, w_out, b_out):
+    """MultiLabel_MultiClass_classification.call (head.py:59-69): ReLU MLP, sigmoid(Dense(V)),
+    tf.squeeze(axis=1).  x: (B, 1, in) -> probabilities (B, V), logits (B, 1, V), activations."""
+    assert x.ndim == 3 and x.shape[1] == 1, "tf.squeeze(axis=1) needs a length-1 segment"
+    h, acts = mlp_fwd(x, layers)
+    z = h @ w_out + b_out
+    return (1.0 / (1.0 + np.exp(-z)))[:, 0, :], z, acts
+
+
+def multilabel_head_loss_and_grads(x, layers, w_out, b_out, y_true, pos_weight=None,
+                                   label_pad=LABEL_PAD):
+    """Loss and gradients of MultiLabel_MultiClass_classification (head.py:50-69) under
+    MaskedLoss(K.binary_crossentropy, pos_weight) (losses.py:31-98): every (row, class) cell with
+    y_true != label_pad is one item of the masked mean; same item formula as the binary head.
+    x: (B, 1, in); y_true: (B, V).  Returns loss, dx, [(dW, db) per MLP layer], dW_out, db_out."""
+    x = np.asarray(x, dtype=np.float64)
+    y = np.asarray(y_true, dtype=np.float64)
+    p, z, acts = multilabel_head_fwd(x, layers, w_out, b_out)
+    mask = (y != label_pad)
+    n = mask.sum()
+    eps = 1e-7
+    pc = np.clip(p, eps, 1 - eps)
+    yy = np.where(mask, y, 0.0)
+    item = -(yy * np.log(pc + eps) + (1 - yy) * np.log(1 - pc + eps))
+    w = np.where(yy == 1, pos_weight, 1.0) if pos_weight is not None else np.ones_like(item)
+    norm = ((pos_weight + 1.0) / 2) if pos_weight is not None else 1.0
+    loss = (item * w * mask).sum() / n / norm if n > 0 else 0.0
+    inside = (p > eps) & (p < 1 - eps)
+    dl_dp = -(yy / (pc + eps) - (1 - yy) / (1 - pc + eps)) * w * inside
+    dz = np.where(mask, dl_dp * p * (1 - p), 0.0) / max(n, 1) / norm       # (B, V)
+    h2 = acts[-1].reshape(-1, acts[-1].shape[-1])                           # (B, h)
+    dW_out = h2.T @ dz
+    db_out = dz.sum(0)
+    dh = (dz @ np.asarray(w_out, dtype=np.float64).T).reshape(acts[-1].shape)
+    dx, layer_grads = mlp_bwd(dh, acts, layers)
+    return loss, dx, layer_grads, dW_out, db_out
+
+
 # ------------------------------------------- examples/BERT4Rec/source/utils.py:56-113 (adaptor)
 def cloze_output_adaptor(y_true, y_pred):
     y_pred = y_pred.reshape(-1, y_pred.shape[-1])

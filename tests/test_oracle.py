@@ -271,3 +271,50 @@ def test_binary_head_backward_matches_torch_autograd(dims, pw):
     for (dw, db), (w, b) in zip(lg, tl):
         np.testing.assert_allclose(dw, w.grad.numpy(), rtol=1e-9, atol=1e-14)
         np.testing.assert_allclose(db, b.grad.numpy(), rtol=1e-9, atol=1e-14)
+
+
+@pytest.mark.parametrize("dims,pw", [([6], 2.0), ([], None)])
+def test_multilabel_head_backward_matches_torch_autograd(dims, pw):
+    """oracle.multilabel_head_loss_and_grads (head.py:50-69 + losses.py:31-98) against torch
+    autograd in float64: (B, 1, d) segment rows, (B, V) multi-hot labels with padded cells."""
+    import torch
+    rng = np.random.default_rng(len(dims) + 11)
+    B, d, V = 6, 8, 13
+    x = rng.normal(size=(B, 1, d))
+    y = (rng.random((B, V)) < 0.2).astype(np.float64)
+    y[rng.random((B, V)) < 0.15] = -1.0
+    layers, prev = [], d
+    for hdim in dims:
+        layers.append((rng.normal(size=(prev, hdim)) * 0.5, rng.normal(size=hdim) * 0.1))
+        prev = hdim
+    w_out, b_out = rng.normal(size=(prev, V)) * 0.5, rng.normal(size=V) * 0.1
+    loss, dx, lg, dWo, dbo = O.multilabel_head_loss_and_grads(x, layers, w_out, b_out, y, pos_weight=pw)
+    xt = torch.tensor(x, requires_grad=True)
+    tl = [(torch.tensor(w, requires_grad=True), torch.tensor(b, requires_grad=True)) for w, b in layers]
+    two, tbo = torch.tensor(w_out, requires_grad=True), torch.tensor(b_out, requires_grad=True)
+    a = xt
+    for w, b in tl:
+        a = torch.relu(a @ w + b)
+    p = torch.sigmoid(a @ two + tbo).squeeze(1)
+    yt = torch.tensor(y)
+    mask = yt != -1.0
+    eps = 1e-7
+    pc = torch.clamp(p, eps, 1 - eps)
+    yy = torch.where(mask, yt, torch.zeros_like(yt))
+    item = -(yy * torch.log(pc + eps) + (1 - yy) * torch.log(1 - pc + eps))
+    if pw is not None:
+        item = torch.where(yy == 1, item * pw, item)
+    tloss = (item * mask).sum() / mask.sum()
+    if pw is not None:
+        tloss = tloss / ((pw + 1) / 2)
+    tloss.backward()
+    assert abs(loss - tloss.item()) < 1e-12
+    probs, _, _ = O.multilabel_head_fwd(x, layers, w_out, b_out)
+    assert probs.shape == (B, V)
+    assert abs(loss - O.masked_loss(y, probs, O.binary_crossentropy_probs, pos_weight=pw)) < 1e-12
+    np.testing.assert_allclose(dx, xt.grad.numpy(), rtol=1e-9, atol=1e-14)
+    np.testing.assert_allclose(dWo, two.grad.numpy(), rtol=1e-9, atol=1e-14)
+    np.testing.assert_allclose(dbo, tbo.grad.numpy(), rtol=1e-9, atol=1e-14)
+    for (dw, db), (w, b) in zip(lg, tl):
+        np.testing.assert_allclose(dw, w.grad.numpy(), rtol=1e-9, atol=1e-14)
+        np.testing.assert_allclose(db, b.grad.numpy(), rtol=1e-9, atol=1e-14)
