@@ -119,3 +119,72 @@ class ClozeDataset:
             if drop_remainder and len(idx) < batch_size:
                 return
             yield cloze_batch([self.session_ids[i] for i in idx], mode, rng, masked_percentage, max_masked)
+
+
+class DeviceClozeBuilder:
+    """Sessions resident in HBM (one CSR of input-vocabulary ids) -> Cloze batches built by
+    `b4cp_cloze_build` on the device: masking, label extraction, padding and chaining
+    (input_pipeline.py:21-32, :59-133, :198-214; clickstream_transformer.py:38-63) without host
+    work per step.  The host only chooses the session indices; because the number of masked items
+    is a function of the session length alone, batch shapes and `n_masked` are known on the host
+    without a device round trip.  Mask positions follow the keyed rule stated in include/b4cp.h
+    (the reference's shuffle stream cannot be matched), so a batch is a pure function of
+    (seed, session indices, mode)."""
+
+    def __init__(self, session_ids):
+        import torch
+        self.lengths = np.array([len(s) for s in session_ids], dtype=np.int64)
+        offsets = np.zeros(len(session_ids) + 1, dtype=np.int64)
+        np.cumsum(self.lengths, out=offsets[1:])
+        flat = (np.concatenate([np.asarray(s, dtype=np.int32) for s in session_ids])
+                if len(session_ids) else np.zeros(0, np.int32))
+        self.items = torch.from_numpy(flat).cuda()
+        self.offsets = torch.from_numpy(offsets).cuda()
+        self._status = torch.zeros(1, dtype=torch.int32, device="cuda")
+
+    def __len__(self):
+        return len(self.lengths)
+
+    def shapes(self, session_idx, mode, masked_percentage=MASKED_PERCENTAGE,
+               max_masked=MAX_MASKED_ITEMS):
+        """(L, Mmax, n_masked) of the batch `cloze_batch` would build from these sessions."""
+        lens = self.lengths[np.asarray(session_idx, dtype=np.int64)]
+        if mode == "train":
+            lens = lens - 1
+            counts = [n_masked_for(int(n), masked_percentage, max_masked) for n in lens]
+        elif mode == "eval":
+            counts = [1] * len(lens)
+        else:
+            raise ValueError(f"Unrecognized mode: {mode}")
+        if len(lens) and lens.min() < (0 if mode == "train" else 1):
+            raise ValueError("empty session in the batch")
+        return int(max(1, lens.max())), max(1, max(counts)), int(sum(counts))
+
+    def build(self, session_idx, mode, seed, masked_percentage=MASKED_PERCENTAGE,
+              max_masked=MAX_MASKED_ITEMS, L=None, Mmax=None, check=False):
+        """Returns dict(ids int32 (B, L + 3) device, labels float32 (B, Mmax) device, n_masked
+        int, B, S).  L / Mmax default to the batch's own maxima (what the host builder produces);
+        pass fixed values for shape-stable CUDA-graph steps.  check=True reads the status word
+        back (a device sync) and raises if a row did not fit."""
+        import torch
+        from . import ops
+        idx = np.ascontiguousarray(session_idx, dtype=np.int32)
+        B = len(idx)
+        l_need, m_need, n_masked = self.shapes(idx, mode, masked_percentage, max_masked)
+        L = l_need if L is None else int(L)
+        Mmax = m_need if Mmax is None else int(Mmax)
+        if L < l_need or Mmax < m_need:
+            raise ValueError(f"batch needs L >= {l_need}, Mmax >= {m_need}; got {L}, {Mmax}")
+        idx_dev = torch.from_numpy(idx).cuda()
+        ids = torch.empty((B, L + 3), dtype=torch.int32, device="cuda")
+        labels = torch.empty((B, Mmax), dtype=torch.float32, device="cuda")
+        count = torch.zeros(1, dtype=torch.int32, device="cuda")
+        ops.cloze_build(self.items, self.offsets, idx_dev, B, L, Mmax, mode == "train",
+                        masked_percentage, max_masked, seed,
+                        (CLS, SEP, MASK_ID, 0, NUM_RESERVED_TOKENS), LABEL_PAD, ids, labels, count,
+                        self._status)
+        if check:
+            bad = int(self._status.item())
+            if bad or int(count.item()) != n_masked:
+                raise RuntimeError(f"cloze_build: row {bad - 1} did not fit / count mismatch")
+        return dict(ids=ids, labels=labels, n_masked=n_masked, B=B, S=L + 3)

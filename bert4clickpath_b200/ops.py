@@ -386,6 +386,23 @@ def sigmoid_bce_dz(y_true, probs, rows, cols, label_pad, pos_weight, stats, dz_f
            L.c_long(dz_bf16.stride(0) if dz_bf16 is not None else 0), L.stream_ptr())
 
 
+def cloze_build(items, offsets, session_idx, B, max_items, Mmax, train, masked_percentage,
+                max_masked, seed, special, label_pad, ids, labels, n_masked, status):
+    """On-device Cloze batch builder (include/b4cp.h); special = (cls, sep, mask, pad, label_offset)."""
+    L.call("b4cp_cloze_build", L.ptr(items), L.ptr(offsets), L.ptr(session_idx), L.c_int(B),
+           L.c_int(max_items), L.c_int(Mmax), L.c_int(1 if train else 0),
+           ctypes.c_double(float(masked_percentage)), L.c_int(max_masked), L.c_u64(seed),
+           *[L.c_int(v) for v in special], L.c_float(label_pad), L.ptr(ids), L.ptr(labels),
+           L.ptr(n_masked), L.ptr(status), L.stream_ptr())
+
+
+def cloze_position_key(seed, session, pos):
+    """Host helper: the 64-bit key the builder ranks mask positions by (no GPU needed)."""
+    fn = L.lib().b4cp_cloze_position_key
+    fn.restype = ctypes.c_uint64
+    return int(fn(L.c_u64(seed), L.c_u64(session), L.c_u64(pos)))
+
+
 def _vocab_ws(M, V, h):
     fn = L.lib().b4cp_vocab_ce_workspace_bytes
     fn.restype = ctypes.c_long

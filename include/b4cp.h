@@ -161,6 +161,27 @@ int b4cp_gather_rows(const float* x, int d, const int32_t* row_index, long M, fl
 int b4cp_scatter_rows(const float* src, int d, const int32_t* row_index, long M, float* dst,
                       void* stream);
 
+/* ------------------------------------------------------------------ Cloze batch builder
+ * On-device restatement of examples/BERT4Rec/source/input_pipeline.py:21-32, :59-133, :198-214
+ * and the chaining of clickstream_transformer.py:38-63 over sessions resident in HBM as a CSR
+ * (items int32 input-vocabulary ids, offsets int64 [n_sessions + 1]); batch row b is session
+ * session_idx[b].  train != 0: the last item is dropped and n = clip(int(len * masked_percentage),
+ * 0, max_masked) distinct positions are replaced by mask_id; else only the last position.
+ * Positions = the n smallest keys splitmix64(splitmix64(seed + session) + pos), ties by position
+ * (the reference's tf.random.shuffle stream cannot be matched; oracle/ restates this rule).
+ * Writes ids [B][L + 3] = cls sep items.. pad.. sep, labels [B][Mmax] = (id - label_offset) of the
+ * masked items in ascending position, padded with label_pad; ADDS the number of masked items to
+ * *n_masked (zero it first) and sets *status = b + 1 if row b does not fit (len > L, n > Mmax or an
+ * empty session; that row is written as pads).  L <= 2048. */
+int b4cp_cloze_build(const int32_t* items, const long long* offsets, const int32_t* session_idx,
+                     int B, int L, int Mmax, int train, double masked_percentage, int max_masked,
+                     unsigned long long seed, int cls_id, int sep_id, int mask_id, int pad_id,
+                     int label_offset, float label_pad, int32_t* ids, float* labels,
+                     int32_t* n_masked, int32_t* status, void* stream);
+/* host-side: the key above for one (seed, session, pos); needs no device */
+unsigned long long b4cp_cloze_position_key(unsigned long long seed, unsigned long long session,
+                                           unsigned long long pos);
+
 /* ------------------------------------------------------------------ Cloze loss, materialised
  * Small-vocabulary path of SoftMaxHead + ClozeMaskedLoss (head.py:38-47;
  * examples/BERT4Rec/source/utils.py:56-134; losses.py:31-98) in logits mode.

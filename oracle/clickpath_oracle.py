@@ -362,6 +362,56 @@ def multilabel_head_loss_and_grads(x, layers, w_out, b_out, y_true, pos_weight=N
     return loss, dx, layer_grads, dW_out, db_out
 
 
+# ------------------------------------------- input_pipeline.py:21-32, :59-133 with keyed positions
+_M64 = (1 << 64) - 1
+
+
+def splitmix64(x):
+    """The 64-bit mixer the device builder keys mask positions with (plain Python ints)."""
+    x = (x + 0x9E3779B97F4A7C15) & _M64
+    x = ((x ^ (x >> 30)) * 0xBF58476D1CE4E5B9) & _M64
+    x = ((x ^ (x >> 27)) * 0x94D049BB133111EB) & _M64
+    return x ^ (x >> 31)
+
+
+def keyed_mask_positions(seed, session, length, n):
+    """The n positions of range(length) with the smallest keys splitmix64(splitmix64(seed +
+    session) + pos), ties by position, ascending - the stand-in for
+    `tf.random.shuffle(tf.range(length))[:n]` followed by the sort of input_pipeline.py:77-78."""
+    base = splitmix64((seed + session) & _M64)
+    keys = [(splitmix64((base + i) & _M64), i) for i in range(length)]
+    return sorted(i for _, i in sorted(keys)[:n])
+
+
+def keyed_cloze_batch(sessions_ids, session_idx, mode, seed, masked_percentage, max_masked, L=None,
+                      Mmax=None, num_reserved=10, cls=3, sep=4, mask=1):
+    """Reference batch (input_pipeline.py:59-133, :198-214; clickstream_transformer.py:38-63) for
+    the sessions `session_idx`, with mask positions from keyed_mask_positions.  Pure-Python loops:
+    small cases only.  Returns ids (B, L + 3) int32, labels (B, Mmax) float32, n_masked."""
+    rows, labs = [], []
+    for s in session_idx:
+        ids = [int(v) for v in sessions_ids[s]]
+        if mode == "train":
+            ids = ids[:-1]                                         # :101-104
+            n = max(0, min(int(len(ids) * masked_percentage), max_masked))   # :68-70
+            pos = keyed_mask_positions(seed, int(s), len(ids), n)
+        else:
+            pos = [len(ids) - 1]                                   # :118-121
+        labs.append([float(ids[p] - num_reserved) for p in pos])
+        for p in pos:
+            ids[p] = mask
+        rows.append(ids)
+    L = max(1, max(len(r) for r in rows)) if L is None else L
+    Mmax = max(1, max(len(l) for l in labs)) if Mmax is None else Mmax
+    out = np.zeros((len(rows), L + 3), dtype=np.int32)
+    lab = np.full((len(rows), Mmax), LABEL_PAD, dtype=np.float32)
+    for b, (r, l) in enumerate(zip(rows, labs)):
+        out[b, 0], out[b, 1], out[b, L + 2] = cls, sep, sep
+        out[b, 2:2 + len(r)] = r
+        lab[b, :len(l)] = l
+    return out, lab, sum(len(l) for l in labs)
+
+
 # ------------------------------------------- examples/BERT4Rec/source/utils.py:56-113 (adaptor)
 def cloze_output_adaptor(y_true, y_pred):
     y_pred = y_pred.reshape(-1, y_pred.shape[-1])

@@ -354,3 +354,51 @@ def test_bert4rec_text_reader_and_cloze_batches_follow_the_reference_rules():
     # batches(): every session exactly once per epoch
     seen = sum(b["ids"].shape[0] for b in ds.batches(5, "train", rng))
     assert seen == len(ds)
+
+
+def test_keyed_mask_positions_oracle_matches_library_key_and_reference_rules():
+    """N2: the oracle's position keys are the library's (host export, no GPU), the selected
+    positions are n distinct sorted positions, uniformly spread, and the keyed batch obeys the
+    reference's rules (drop-last, n = clip(int(len p), 0, max), labels = id - 10 in position order,
+    pad-before-chain layout) exactly like data.cloze_batch does for its own draw."""
+    from bert4clickpath_b200 import ops
+    from bert4clickpath_b200.build import build_lib
+    from bert4clickpath_b200.data import cloze_batch
+    build_lib(verbose=False)
+    for seed, sess, pos in [(0, 0, 0), (1234, 17, 5), (2 ** 64 - 1, 3, 9), (99, 2 ** 40, 2047)]:
+        want = O.splitmix64((O.splitmix64((seed + sess) & (2 ** 64 - 1)) + pos) & (2 ** 64 - 1))
+        assert ops.cloze_position_key(seed, sess, pos) == want
+    assert O.splitmix64(0) == 0xE220A8397B1DCDAF          # published SplitMix64 first output
+    # subsets: distinct, sorted, right size, and every position equally likely
+    hits = np.zeros(20)
+    for s in range(4000):
+        p = O.keyed_mask_positions(7, s, 20, 5)
+        assert len(p) == 5 and len(set(p)) == 5 and p == sorted(p) and 0 <= p[0] and p[-1] < 20
+        hits[p] += 1
+    assert np.abs(hits / 4000 - 0.25).max() < 0.03        # 4.4 sigma of a binomial(4000, .25)
+    assert O.keyed_mask_positions(7, 1, 20, 0) == [] and O.keyed_mask_positions(7, 1, 3, 3) == [0, 1, 2]
+    assert O.keyed_mask_positions(7, 1, 20, 5) != O.keyed_mask_positions(8, 1, 20, 5)
+    # batch rules
+    rng = np.random.default_rng(0)
+    sessions = [rng.integers(10, 500, size=n).astype(np.int32) for n in (5, 1, 12, 50, 7, 2)]
+    idx = [3, 0, 5, 1, 2]
+    for mode in ("train", "eval"):
+        use = idx if mode == "train" else [i for i in idx if len(sessions[i]) >= 1]
+        ids, lab, n = O.keyed_cloze_batch(sessions, use, mode, 42, 0.4, 10)
+        ref = cloze_batch([sessions[i] for i in use], mode, np.random.default_rng(1), 0.4, 10)
+        assert ids.shape == ref["ids"].shape and lab.shape == ref["labels"].shape and n == ref["n_masked"]
+        for b, s in enumerate(use):
+            src = sessions[s][:-1] if mode == "train" else sessions[s]
+            row = ids[b]
+            assert row[0] == 3 and row[1] == 4 and row[-1] == 4
+            body = row[2:2 + len(src)]
+            masked = np.nonzero(body == 1)[0]
+            k = int((lab[b] != -1).sum())
+            assert len(masked) == k == int((ref["labels"][b] != -1).sum())
+            assert (body[body != 1] == src[body != 1]).all() and (row[2 + len(src):-1] == 0).all()
+            assert (lab[b, :k] == src[masked] - 10).all() and (lab[b, k:] == -1).all()
+            if mode == "eval":
+                assert list(masked) == [len(src) - 1]
+    # fixed shapes pad further
+    ids2, lab2, _ = O.keyed_cloze_batch(sessions, idx, "train", 42, 0.4, 10, L=60, Mmax=12)
+    assert ids2.shape == (5, 63) and lab2.shape == (5, 12) and (ids2[:, -1] == 4).all()
