@@ -402,3 +402,31 @@ def test_keyed_mask_positions_oracle_matches_library_key_and_reference_rules():
     # fixed shapes pad further
     ids2, lab2, _ = O.keyed_cloze_batch(sessions, idx, "train", 42, 0.4, 10, L=60, Mmax=12)
     assert ids2.shape == (5, 63) and lab2.shape == (5, 12) and (ids2[:, -1] == 4).all()
+
+
+def test_oracle_reproduces_golden_sigmoid_heads_and_keyed_cloze():
+    z = np.load(os.path.join(GOLD, "sigmoid_heads.npz"))
+    layers = [(z["w0"], z["b0"])]
+    loss, dx, lg, dwo, dbo = O.binary_head_loss_and_grads(z["xb"], layers, z["wb"], z["bb"], z["yb"],
+                                                          pos_weight=3.0)
+    assert abs(loss - float(z["b_loss"])) < 1e-13
+    for got, key in [(dx, "b_dx"), (lg[0][0], "b_dw0"), (lg[0][1], "b_db0"), (dwo, "b_dwo"), (dbo, "b_dbo")]:
+        np.testing.assert_allclose(got, z[key], rtol=1e-12, atol=1e-15, err_msg=key)
+    loss, dx, lg, dwo, dbo = O.multilabel_head_loss_and_grads(z["xm"], layers, z["wm"], z["bm"], z["ym"])
+    assert abs(loss - float(z["m_loss"])) < 1e-13
+    for got, key in [(dx, "m_dx"), (lg[0][0], "m_dw0"), (lg[0][1], "m_db0"), (dwo, "m_dwo"), (dbo, "m_dbo")]:
+        np.testing.assert_allclose(got, z[key], rtol=1e-12, atol=1e-15, err_msg=key)
+    k = np.load(os.path.join(GOLD, "keyed_cloze.npz"))
+    offs = k["offsets"]
+    sessions = [k["items"][offs[i]:offs[i + 1]] for i in range(len(offs) - 1)]
+    ids, lab, n = O.keyed_cloze_batch(sessions, k["idx"], "train", 1234, 0.4, 10)
+    assert ids.tobytes() == k["train_ids"].tobytes() and lab.tobytes() == k["train_labels"].tobytes()
+    assert n == int(k["train_n"])
+    ids, lab, n = O.keyed_cloze_batch(sessions, k["idx"], "eval", 1234, 0.4, 10, L=52, Mmax=3)
+    assert ids.tobytes() == k["eval_ids"].tobytes() and lab.tobytes() == k["eval_labels"].tobytes()
+    assert n == int(k["eval_n"]) == len(k["idx"])
+    # the committed keys are also what the library's host export computes
+    from bert4clickpath_b200 import ops
+    from bert4clickpath_b200.build import build_lib
+    build_lib(verbose=False)
+    assert [ops.cloze_position_key(1234, 3, i) for i in range(4)] == [int(v) for v in k["keys_s3"]]

@@ -86,3 +86,19 @@ def test_built_batches_train_the_model(cuda_lib):
         assert s[1] == out["n_masked"]
         losses.append(s[0] / s[1])
     assert losses[-1] < losses[0]
+
+
+def test_device_builder_matches_committed_golden_batches(cuda_lib):
+    import os
+    from bert4clickpath_b200.data import DeviceClozeBuilder
+    k = np.load(os.path.join(os.path.dirname(__file__), "golden", "keyed_cloze.npz"))
+    offs = k["offsets"]
+    builder = DeviceClozeBuilder([k["items"][offs[i]:offs[i + 1]] for i in range(len(offs) - 1)])
+    tr = builder.build(k["idx"], "train", 1234, 0.4, 10, check=True)
+    assert tr["ids"].cpu().numpy().tobytes() == k["train_ids"].tobytes()
+    assert tr["labels"].cpu().numpy().tobytes() == k["train_labels"].tobytes()
+    assert tr["n_masked"] == int(k["train_n"])
+    ev = builder.build(k["idx"], "eval", 1234, 0.4, 10, L=52, Mmax=3, check=True)
+    assert ev["ids"].cpu().numpy().tobytes() == k["eval_ids"].tobytes()
+    assert ev["labels"].cpu().numpy().tobytes() == k["eval_labels"].tobytes()
+    assert ev["n_masked"] == int(k["eval_n"])
