@@ -256,6 +256,9 @@ def run_fit(model, dataset, steps_per_epoch, epochs=1, verbose=0, validation_dat
                 vlast = model.test_step(batch)
                 vsum += vlast.get('loss', 0.0)
                 nv += 1
+            if nv == 0:
+                raise ValueError("validation_data yielded no batches (a generator is exhausted "
+                                 "after one epoch: pass a list or another re-iterable)")
             for k, v in vlast.items():
                 logs['val_' + k] = vsum / nv if k == 'loss' else v
         for cb in callbacks:

@@ -141,6 +141,13 @@ def test_fit_loop_order_reference_callbacks(tmp_path):
         T.run_fit(_FakeModel([1.0], []), _batches(), 1, callbacks=[T.BestModelSaverCallback("x")])
 
 
+def test_fit_rejects_an_exhausted_validation_generator():
+    m = _FakeModel([1.0] * 4, [1.0])
+    gen = (b for b in [None])
+    with pytest.raises(ValueError):
+        T.run_fit(m, _batches(), steps_per_epoch=1, epochs=2, validation_data=gen)
+
+
 def test_lr_schedules_closed_forms():
     s = T.CustomLRSchedule(d_model=64, warmup_steps=4000)
     steps = np.array([1, 100, 4000, 40000], dtype=np.float32)
