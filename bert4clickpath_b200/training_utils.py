@@ -219,6 +219,28 @@ class BestModelSaverCallback(Callback):
             self.best_val_loss = logs['val_loss']
 
 
+# ----------------------------------------------------------------------------- data parallel
+def average_logs(logs, group=None):
+    """Mean over the ranks of every scalar in the epoch logs (one small all-reduce; identity
+    without an initialised process group).  Under MirroredStrategy Keras evaluates on the global
+    batch (main.py:46-57), so every replica's callbacks see the same numbers; with one process per
+    GPU each rank validates its own shard, and without this a plateau or early-stopping decision
+    could differ between ranks and leave them in different collectives."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return logs
+    keys = sorted(k for k, v in logs.items() if isinstance(v, (int, float)))
+    dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+    t = torch.tensor([float(logs[k]) for k in keys], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    t = (t / dist.get_world_size(group)).cpu()
+    out = dict(logs)
+    for k, v in zip(keys, t.tolist()):
+        out[k] = v
+    return out
+
+
 # ----------------------------------------------------------------------------- the loop
 def run_fit(model, dataset, steps_per_epoch, epochs=1, verbose=0, validation_data=None,
             validation_steps=None, callbacks=()):
@@ -226,8 +248,9 @@ def run_fit(model, dataset, steps_per_epoch, epochs=1, verbose=0, validation_dat
     `steps_per_epoch` train steps, then `validation_steps` test steps whose results enter the
     epoch logs as `val_*`, then the callbacks.  Like Keras, the training loss in the logs is the
     running mean of the per-step losses and a metric entry is the metric's own running result;
-    metrics are reset at the start of each epoch and before validation.  Returns the list of
-    epoch logs (`History.history` transposed)."""
+    metrics are reset at the start of each epoch and before validation.  In a data-parallel run
+    the epoch logs are averaged over the ranks before the callbacks see them (average_logs).
+    Returns the list of epoch logs (`History.history` transposed)."""
     callbacks = list(callbacks)
     model.stop_training = False
     for cb in callbacks:
@@ -261,6 +284,7 @@ def run_fit(model, dataset, steps_per_epoch, epochs=1, verbose=0, validation_dat
                                  "after one epoch: pass a list or another re-iterable)")
             for k, v in vlast.items():
                 logs['val_' + k] = vsum / nv if k == 'loss' else v
+        logs = average_logs(logs, getattr(model, 'process_group', None))
         for cb in callbacks:
             cb.on_epoch_end(epoch, logs)
         history.append(logs)

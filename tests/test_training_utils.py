@@ -206,3 +206,45 @@ def test_reference_checkpoint_key_map_round_trips():
         np.testing.assert_array_equal(v, ref[k])
     with pytest.raises(KeyError):
         W.tf_checkpoint_key("decoder.0.w")
+
+
+def _fit_worker(rank, world, port, q):
+    import os
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    # rank 0 sees an improving validation loss, rank 1 a flat one: alone, rank 1 would cut its
+    # learning rate and stop early while rank 0 trains on
+    val = [1.0, 0.8, 0.6, 0.4, 0.2, 0.1] if rank == 0 else [1.0] * 6
+    m = _FakeModel([0.5 + rank] * 6, val)
+    m.process_group = None
+    es = T.EarlyStopping(monitor="val_loss", patience=2)
+    rl = T.ReduceLROnPlateau(monitor="val_loss", patience=1, factor=0.5)
+    hist = T.run_fit(m, _batches(), steps_per_epoch=1, epochs=6, validation_data=[None],
+                     validation_steps=1, callbacks=[es, rl])
+    q.put((rank, [h["val_loss"] for h in hist], [h["loss"] for h in hist],
+           m.optimizer.learning_rate, m.stop_training))
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_fit_keeps_callback_decisions_identical():
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_fit_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (_, v0, l0, lr0, stop0), (_, v1, l1, lr1, stop1) = res
+    assert v0 == v1 == pytest.approx([1.0, 0.9, 0.8, 0.7, 0.6, 0.55])
+    assert l0 == l1 == pytest.approx([1.0] * 6)
+    assert lr0 == lr1 == 1e-3 and stop0 is stop1 is False
+    assert T.average_logs({"a": 1.0, "tag": "x"}) == {"a": 1.0, "tag": "x"}   # no process group
