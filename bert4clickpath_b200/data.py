@@ -98,8 +98,41 @@ class ClozeDataset:
 
     def __init__(self, path, max_seq_len=MAX_SEQ_LEN, vocab=None):
         users, items = read_bert4rec_text_data(path)
-        self.sessions, file_vocab, self.users = prepare_sessions(users, items, max_seq_len)
-        self.vocab = list(vocab) if vocab is not None else file_vocab
+        sessions, file_vocab, users = prepare_sessions(users, items, max_seq_len)
+        self._bind(sessions, users, vocab if vocab is not None else file_vocab)
+
+    @classmethod
+    def from_sessions(cls, sessions, users=None, vocab=None):
+        """Already-prepared sessions (lists of item strings).  `vocab`: list of item strings or
+        the path of an `item_vocab.txt` (one token per line, data_prep/main.py:77-80); default =
+        order of first appearance, which is what data_prep writes."""
+        self = cls.__new__(cls)
+        if isinstance(vocab, str):
+            with open(vocab) as f:
+                vocab = [line.strip() for line in f if line.strip()]
+        if vocab is None:
+            vocab, seen = [], set()
+            for s in sessions:
+                for t in s:
+                    if t not in seen:
+                        seen.add(t)
+                        vocab.append(t)
+        self._bind([list(s) for s in sessions],
+                   list(users) if users is not None else [str(i) for i in range(len(sessions))], vocab)
+        return self
+
+    @classmethod
+    def from_tfrecord(cls, paths, vocab=None, verify_crc=True):
+        """The TFRecord files the reference's data prep writes (one Example per user with
+        `reviewerID` and the `asin` list; data_prep/main.py:86-98, input_pipeline.py:149-156),
+        read without TensorFlow (tfrecord.py)."""
+        from .tfrecord import read_sessions
+        users, sessions = read_sessions(paths, verify_crc=verify_crc)
+        return cls.from_sessions(sessions, users, vocab)
+
+    def _bind(self, sessions, users, vocab):
+        self.sessions, self.users = sessions, users
+        self.vocab = list(vocab)
         index = {t: i for i, t in enumerate(self.vocab)}
         oov = len(self.vocab) + NUM_RESERVED_TOKENS   # StaticVocabularyTable's single OOV bucket
         self.session_ids = [np.array([index[t] + NUM_RESERVED_TOKENS if t in index else oov for t in s],
@@ -107,6 +140,10 @@ class ClozeDataset:
 
     def __len__(self):
         return len(self.session_ids)
+
+    def device_builder(self):
+        """The sessions uploaded once as a CSR for on-device batch building (DeviceClozeBuilder)."""
+        return DeviceClozeBuilder(self.session_ids)
 
     def batches(self, batch_size, mode, rng, masked_percentage=MASKED_PERCENTAGE,
                 max_masked=MAX_MASKED_ITEMS, shuffle=None, drop_remainder=False):
