@@ -3,7 +3,7 @@
 // extraction), :198-214 (padding) and clickstream_transformer.py:38-63 (chaining) on int32 ids
 // held in HBM as one CSR of sessions, so a training step needs no host work beyond choosing
 // which sessions form the batch:
-//   TRAIN: drop the last item; n = clip(int(len * p), 0, max_masked) distinct positions become
+//   TRAIN: drop the last item; n = clip(int(float32(len) * float32(p)), 0, max_masked) distinct positions become
 //          [MASK]; labels (label-vocabulary id = input id - label_offset, as float32) follow in
 //          ascending position; EVAL: only the last position is masked.
 //   ids row = [CLS] [SEP] items... [PAD]... [SEP]  (the sequence is padded BEFORE chaining),
@@ -54,7 +54,9 @@ __global__ void __launch_bounds__(CB_THREADS) cloze_build_kernel(const ClozeBuil
   const long long beg = p.offsets[sess];
   int len = (int)(p.offsets[sess + 1] - beg);
   if (p.train) len -= 1;                                   // input_pipeline.py:101-104
-  int n = p.train ? (int)((double)len * p.masked_percentage) : 1;   // :68-70 / :118-121
+  // :68-70 / :118-121 - the reference multiplies in float32 (tf.cast(size, tf.float32) * p) and
+  // truncates; float32 and float64 disagree for some (len, p), e.g. 90 * 0.7 -> 63 vs 62
+  int n = p.train ? (int)__fmul_rn((float)len, (float)p.masked_percentage) : 1;
   if (p.train) n = max(0, min(n, p.max_masked));
   const int S = p.L + 3;
   int32_t* row = p.ids + (long)b * S;

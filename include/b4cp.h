@@ -165,8 +165,9 @@ int b4cp_scatter_rows(const float* src, int d, const int32_t* row_index, long M,
  * On-device restatement of examples/BERT4Rec/source/input_pipeline.py:21-32, :59-133, :198-214
  * and the chaining of clickstream_transformer.py:38-63 over sessions resident in HBM as a CSR
  * (items int32 input-vocabulary ids, offsets int64 [n_sessions + 1]); batch row b is session
- * session_idx[b].  train != 0: the last item is dropped and n = clip(int(len * masked_percentage),
- * 0, max_masked) distinct positions are replaced by mask_id; else only the last position.
+ * session_idx[b].  train != 0: the last item is dropped and n = clip(int(float32(len) *
+ * float32(masked_percentage)), 0, max_masked) distinct positions (float32 product, truncated, as
+ * input_pipeline.py:68-70 computes it) are replaced by mask_id; else only the last position.
  * Positions = the n smallest keys splitmix64(splitmix64(seed + session) + pos), ties by position
  * (the reference's tf.random.shuffle stream cannot be matched; oracle/ restates this rule).
  * Writes ids [B][L + 3] = cls sep items.. pad.. sep, labels [B][Mmax] = (id - label_offset) of the

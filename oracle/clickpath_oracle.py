@@ -393,7 +393,8 @@ def keyed_cloze_batch(sessions_ids, session_idx, mode, seed, masked_percentage, 
         ids = [int(v) for v in sessions_ids[s]]
         if mode == "train":
             ids = ids[:-1]                                         # :101-104
-            n = max(0, min(int(len(ids) * masked_percentage), max_masked))   # :68-70
+            # :68-70 - a float32 product, truncated (90 * 0.7 gives 63 there, 62 in float64)
+            n = max(0, min(int(np.float32(len(ids)) * np.float32(masked_percentage)), max_masked))
             pos = keyed_mask_positions(seed, int(s), len(ids), n)
         else:
             pos = [len(ids) - 1]                                   # :118-121

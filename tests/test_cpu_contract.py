@@ -399,6 +399,12 @@ def test_keyed_mask_positions_oracle_matches_library_key_and_reference_rules():
             assert (lab[b, :k] == src[masked] - 10).all() and (lab[b, k:] == -1).all()
             if mode == "eval":
                 assert list(masked) == [len(src) - 1]
+    # the mask count is the reference's float32 product (90 * 0.7 -> 63, not float64's 62)
+    from bert4clickpath_b200.synthetic import n_masked_for
+    long = [np.arange(10, 10 + n, dtype=np.int32) for n in (91, 171, 181)]
+    _, lab7, n7 = O.keyed_cloze_batch(long, [0, 1, 2], "train", 1, 0.7, 1000)
+    assert [int((r != -1).sum()) for r in lab7] == [63, 119, 126] == [n_masked_for(n, 0.7, 1000) for n in (90, 170, 180)]
+    assert n7 == 63 + 119 + 126
     # fixed shapes pad further
     ids2, lab2, _ = O.keyed_cloze_batch(sessions, idx, "train", 42, 0.4, 10, L=60, Mmax=12)
     assert ids2.shape == (5, 63) and lab2.shape == (5, 12) and (ids2[:, -1] == 4).all()

@@ -12,17 +12,19 @@ pytestmark = pytest.mark.gpu
 def _sessions(rng, n, max_len, vocab):
     lens = rng.integers(1, max_len + 1, size=n)
     lens[:3] = [1, 2, max_len]
+    lens[3:5] = [min(91, max_len), min(171, max_len)]   # 90 * 0.7 and 170 * 0.7: float32 != float64
     return [rng.integers(10, vocab + 10, size=int(l)).astype(np.int32) for l in lens]
 
 
 @pytest.mark.parametrize("mode", ["train", "eval"])
-@pytest.mark.parametrize("p,max_masked,max_len", [(0.4, 10, 50), (0.15, 30, 200), (1.0, 300, 300)])
+@pytest.mark.parametrize("p,max_masked,max_len", [(0.4, 10, 50), (0.15, 30, 200), (1.0, 300, 300),
+                                                (0.7, 300, 181)])
 def test_device_builder_is_bit_exact_against_the_oracle(cuda_lib, mode, p, max_masked, max_len):
     from bert4clickpath_b200.data import DeviceClozeBuilder
     rng = np.random.default_rng(max_len)
     sessions = _sessions(rng, 300, max_len, 5000)
     builder = DeviceClozeBuilder(sessions)
-    idx = rng.permutation(300)[:97]
+    idx = np.concatenate([np.arange(5), 5 + rng.permutation(295)[:92]])
     for seed, (L, Mmax) in [(5, (None, None)), (2 ** 63 + 11, (max_len + 3, max_masked + 2))]:
         if Mmax is not None and mode == "train":
             Mmax = max(Mmax, builder.shapes(idx, mode, p, max_masked)[1])
