@@ -33,6 +33,9 @@ def __getattr__(name):
         "PredictedPositives": ".metrics",
         "F1Score": ".metrics",
         "MaskedMetric": ".metrics",
+        "create_cloze_dataset": ".data",
+        "ClozeDataset": ".data",
+        "DeviceClozeBuilder": ".data",
         "CustomLRSchedule": ".training_utils",
         "CustomExponentialDecayLR": ".training_utils",
         "BestModelSaverCallback": ".training_utils",

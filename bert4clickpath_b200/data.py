@@ -9,7 +9,8 @@ Not on the timed path and not a tf.data replacement: no TFRecord I/O, no shuffli
 """
 import numpy as np
 
-from .constants import CLS, LABEL_PAD, MASK_ID, NUM_RESERVED_TOKENS, SEP
+from .constants import (CLS, INPUT_MASKING_TOKEN, INPUT_PADDING_TOKEN, LABEL_PAD, MASK_ID,
+                        NUM_RESERVED_TOKENS, SEP)
 from .synthetic import n_masked_for
 
 MASKED_PERCENTAGE = 0.4      # cloze_constants.py:1
@@ -156,6 +157,90 @@ class ClozeDataset:
             if drop_remainder and len(idx) < batch_size:
                 return
             yield cloze_batch([self.session_ids[i] for i in idx], mode, rng, masked_percentage, max_masked)
+
+
+def _shuffled_epochs(load, rng, buffer_size):
+    """dataset.shuffle(buffer_size, reshuffle_each_iteration=True).repeat(None)
+    (input_pipeline.py:183-185): a sliding shuffle buffer per pass over the source, forever."""
+    while True:
+        buf, seen = [], False
+        for ex in load():
+            seen = True
+            if len(buf) < buffer_size:
+                buf.append(ex)
+                continue
+            j = int(rng.integers(len(buf)))
+            out, buf[j] = buf[j], ex
+            yield out
+        if not seen:
+            raise ValueError("create_cloze_dataset: the source yielded no examples")
+        while buf:
+            j = int(rng.integers(len(buf)))
+            buf[j], buf[-1] = buf[-1], buf[j]
+            yield buf.pop()
+
+
+def create_cloze_dataset(source, mode, batch_size, target_vocab_file, rng=None,
+                         masked_percentage=MASKED_PERCENTAGE, max_masked=MAX_MASKED_ITEMS,
+                         shuffle_buffer=20000):
+    """examples/BERT4Rec/source/input_pipeline.py:136-232 with the same arguments: an endless
+    iterator of `(features, labels)` batches in the reference's own contract -
+    features = {'reviewerID': (B,) str, 'asin': (B, L) str padded with '[PAD]', masked positions
+    replaced by '[MASK]'}, labels = (B, M) float32 target-vocabulary indices (one OOV bucket =
+    len(vocab), :189-192) padded with -1 - i.e. what `ClickstreamTransformer.fit / train_step`
+    takes.  `source`: a glob pattern of TFRecord files (read without TensorFlow, tfrecord.py) or a
+    callable returning an iterator of {'reviewerID': str, 'asin': list of str}.  Shuffle buffer,
+    repeat, per-example masking (cloze_example's rules), batches padded to their longest row."""
+    import glob
+    if mode not in ("train", "eval"):
+        raise ValueError(f"Unrecognized mode: {mode}")
+    rng = rng if rng is not None else np.random.default_rng()
+    if isinstance(source, str):
+        files = sorted(glob.glob(source))
+        if not files:
+            raise FileNotFoundError(source)
+
+        def load():
+            from .tfrecord import decode_example, read_records
+            for f in files:
+                for rec in read_records(f):
+                    ex = decode_example(rec)
+                    yield {"reviewerID": ex["reviewerID"][0].decode("utf-8"),
+                           "asin": [v.decode("utf-8") for v in ex.get("asin", [])]}
+    elif callable(source):
+        load = source
+    else:
+        raise TypeError("Source must be either str or callable.")
+    with open(target_vocab_file) as f:
+        label_vocab = [line.strip() for line in f if line.strip()]
+    label_index = {t: i for i, t in enumerate(label_vocab)}
+    oov = len(label_vocab)
+
+    def examples():
+        for ex in _shuffled_epochs(load, rng, shuffle_buffer):
+            items = list(ex["asin"])
+            if mode == "train":
+                items = items[:-1]
+                n = n_masked_for(len(items), masked_percentage, max_masked)
+                pos = np.sort(rng.permutation(len(items))[:n])
+            else:
+                pos = np.array([len(items) - 1])
+            labels = [float(label_index.get(items[p], oov)) for p in pos]
+            for p in pos:
+                items[p] = INPUT_MASKING_TOKEN
+            yield ex["reviewerID"], items, labels
+
+    it = examples()
+    while True:
+        rows = [next(it) for _ in range(batch_size)]
+        L = max(len(r[1]) for r in rows)
+        M = max(len(r[2]) for r in rows)
+        asin = np.full((batch_size, L), INPUT_PADDING_TOKEN, dtype=object)
+        labels = np.full((batch_size, M), LABEL_PAD, dtype=np.float32)
+        for b, (_, items, lab) in enumerate(rows):
+            asin[b, :len(items)] = items
+            labels[b, :len(lab)] = lab
+        yield {"reviewerID": np.array([r[0] for r in rows], dtype=object), "asin": asin}, labels
 
 
 class DeviceClozeBuilder:

@@ -132,3 +132,63 @@ def test_tfrecord_sessions_feed_the_cloze_dataset_like_the_text_reader(tmp_path)
     R.write_records(a, [R.encode_example({"asin": ["x"]})])
     with pytest.raises(ValueError):
         R.read_sessions(a)
+
+
+def test_create_cloze_dataset_yields_the_reference_contract(tmp_path):
+    """input_pipeline.py:136-232: endless (features, labels) batches from TFRecord files or a
+    generator; masked strings, '[PAD]' padding, float32 label indices padded with -1."""
+    from bert4clickpath_b200.clickstream_transformer import StaticVocabularyTable
+    from bert4clickpath_b200.constants import RESERVED_TOKENS
+    from bert4clickpath_b200.data import create_cloze_dataset
+    text = os.path.join(GOLD, "tiny_bert4rec.txt")
+    users, items = read_bert4rec_text_data(text)
+    sessions, vocab, order = prepare_sessions(users, items)
+    by_user = dict(zip(order, sessions))
+    rec = str(tmp_path / "amazon_beauty-0.tfrecord")
+    R.write_sessions(rec, order, sessions)
+    vocab_file = str(tmp_path / "item_vocab.txt")
+    open(vocab_file, "w").writelines("\n".join(vocab))
+    index = {t: i for i, t in enumerate(vocab)}
+    table = StaticVocabularyTable(RESERVED_TOKENS + vocab)
+    B = 4
+    for mode, source in (("train", str(tmp_path / "*.tfrecord")), ("eval", str(tmp_path / "*.tfrecord")),
+                         ("train", lambda: ({"reviewerID": u, "asin": s} for u, s in zip(order, sessions)))):
+        ds = create_cloze_dataset(source, mode, B, vocab_file, rng=np.random.default_rng(1), shuffle_buffer=3)
+        seen = []
+        for _ in range(2 * len(order) // B + 1):          # more than one pass: the dataset repeats
+            feats, labels = next(ds)
+            assert set(feats) == {"reviewerID", "asin"} and labels.dtype == np.float32
+            assert feats["asin"].shape[0] == B == labels.shape[0] == len(feats["reviewerID"])
+            for b in range(B):
+                u = feats["reviewerID"][b]
+                seen.append(u)
+                src = by_user[u][:-1] if mode == "train" else by_user[u]
+                row = list(feats["asin"][b])
+                body, pad = row[:len(src)], row[len(src):]
+                assert all(t == "[PAD]" for t in pad)
+                masked = [i for i, t in enumerate(body) if t == "[MASK]"]
+                assert all(t == s for i, (t, s) in enumerate(zip(body, src)) if i not in masked)
+                k = int((labels[b] != -1).sum())
+                want_k = 1 if mode == "eval" else max(0, min(int(np.float32(len(src)) * np.float32(0.4)), 10))
+                assert len(masked) == k == want_k and (labels[b, k:] == -1).all()
+                assert [index[src[i]] for i in masked] == labels[b, :k].astype(int).tolist()
+                if mode == "eval":
+                    assert masked == [len(src) - 1]
+            # the model's lookup turns the strings into the id layout of the ClozeDataset path
+            ids = table.lookup(feats["asin"])
+            assert ids.dtype == np.int32 and ((ids == 1) == (feats["asin"] == "[MASK]")).all()
+            assert ((ids == 0) == (feats["asin"] == "[PAD]")).all() and ids.max() < len(vocab) + 10
+        assert set(seen) == set(order)                     # every session shows up
+        assert seen[:len(order)] != order                  # shuffled
+    # labels outside the target vocabulary go to the OOV bucket
+    small_vocab = str(tmp_path / "small.txt")
+    open(small_vocab, "w").write(vocab[0] + "\n")
+    _, lab = next(create_cloze_dataset(str(tmp_path / "*.tfrecord"), "eval", B, small_vocab,
+                                       rng=np.random.default_rng(0)))
+    assert set(lab.reshape(-1).tolist()) <= {0.0, 1.0}
+    with pytest.raises(ValueError):
+        next(create_cloze_dataset(rec, "predict", B, vocab_file))
+    with pytest.raises(TypeError):
+        next(create_cloze_dataset(123, "train", B, vocab_file))
+    with pytest.raises(FileNotFoundError):
+        next(create_cloze_dataset(str(tmp_path / "nope*"), "train", B, vocab_file))
