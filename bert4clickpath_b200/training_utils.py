@@ -12,6 +12,7 @@ A callback sees `model.optimizer.learning_rate` (a float, or a schedule called w
 0-based iteration count, as Keras does) and may set `model.stop_training`; `run_fit` is the loop `ClickstreamTransformer.fit`
 delegates to.
 """
+import json
 import math
 import os
 
@@ -202,11 +203,31 @@ class EarlyStopping(Callback):
             print(f'Epoch {self.stopped_epoch + 1:05d}: early stopping')
 
 
+def _jsonable(obj):
+    """Constructor config -> JSON: head units become {class, dense_layer_dims, output_vocab_size},
+    in-memory vocabularies their size."""
+    if isinstance(obj, dict):
+        return {str(k): _jsonable(v) for k, v in obj.items()}
+    if isinstance(obj, (list, tuple)):
+        if len(obj) > 64:
+            return {'len': len(obj)}
+        return [_jsonable(v) for v in obj]
+    if isinstance(obj, (str, int, float, bool)) or obj is None:
+        return obj
+    if isinstance(obj, (np.integer, np.floating)):
+        return obj.item()
+    out = {'class': type(obj).__name__}
+    for attr in ('dense_layer_dims', 'output_vocab_size'):
+        if hasattr(obj, attr):
+            out[attr] = _jsonable(getattr(obj, attr))
+    return out
+
+
 class BestModelSaverCallback(Callback):
     """Writes the model whenever val_loss improves (training_utils.py:63-75).  The reference
-    writes a TF SavedModel with its serving signature; here the artefact is one .npz of the
-    parameters in the reference's per-layer layout (weights.to_reference_layout) plus the
-    serving signature and constructor config as JSON - what INTEGRATION.md's import path reads."""
+    writes a TF SavedModel with its serving signature; here the artefact is `variables.npz` (the
+    parameters under the reference's checkpoint keys, model.save_weights) plus `model.json`
+    (epoch, val_loss, serving signature and constructor config)."""
 
     def __init__(self, savedmodel_path):
         self.savedmodel_path = savedmodel_path
@@ -216,6 +237,13 @@ class BestModelSaverCallback(Callback):
         if logs['val_loss'] < self.best_val_loss:       # KeyError without validation, as upstream
             os.makedirs(self.savedmodel_path, exist_ok=True)
             self.model.save_weights(os.path.join(self.savedmodel_path, 'variables.npz'))
+            meta = {'epoch': epoch, 'val_loss': float(logs['val_loss'])}
+            if hasattr(self.model, 'get_serving_signature'):
+                meta['serving_signature'] = self.model.get_serving_signature()
+            if hasattr(self.model, 'get_config'):
+                meta['config'] = _jsonable(self.model.get_config())
+            with open(os.path.join(self.savedmodel_path, 'model.json'), 'w') as f:
+                json.dump(meta, f, indent=1)
             self.best_val_loss = logs['val_loss']
 
 

@@ -46,6 +46,15 @@ class _FakeModel:
     def save_weights(self, path):
         self.saved.append((path, float(self.weights["w"][0])))
 
+    def get_serving_signature(self):
+        return {"asin": ([None, None], "string")}
+
+    def get_config(self):
+        class _Head:
+            dense_layer_dims, output_vocab_size = [8, 4], 99
+        return {"head_unit": _Head(), "feature_vocabs": {"items": [str(i) for i in range(100)]},
+                "dropout_rate": np.float32(0.5)}
+
 
 def _batches():
     while True:
@@ -132,6 +141,12 @@ def test_fit_loop_order_reference_callbacks(tmp_path):
     assert all(h["loss"] == 1.5 for h in hist)                 # running mean of the step losses
     assert len(hist) == 5 + 30                                 # best at epoch 4, 30 stale epochs
     assert [s[1] for s in m.saved] == [2.0, 4.0, 6.0, 8.0, 10.0]
+    import json
+    meta = json.load(open(tmp_path / "savedmodel" / "model.json"))
+    assert meta["epoch"] == 4 and meta["val_loss"] == pytest.approx(0.6)
+    assert meta["serving_signature"] == {"asin": [[None, None], "string"]}
+    assert meta["config"]["head_unit"] == {"class": "_Head", "dense_layer_dims": [8, 4], "output_vocab_size": 99}
+    assert meta["config"]["feature_vocabs"] == {"items": {"len": 100}}
     f32 = lambda x: float(np.float32(x))
     l1 = f32(f32(1e-3) * 0.317); l2 = f32(l1 * 0.317); l3 = f32(l2 * 0.317)
     # cuts after epochs 14, 24, 34 (0-based); epoch e trains with the lr left by epoch e-1
