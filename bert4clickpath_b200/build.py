@@ -64,7 +64,11 @@ def build_lib(force=False, verbose=True):
         with ThreadPoolExecutor(max_workers=min(8, len(todo))) as ex:
             list(ex.map(lambda s: _compile(s, verbose), todo))
     if todo or not os.path.exists(LIB):
-        cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
+        # shared cudart: the library binds to the CUDA runtime the process already has (torch's)
+        # instead of embedding a second, static copy of it; rpath covers processes without torch
+        cmd = [NVCC, "-shared", "-cudart", "shared", "-o", LIB] + objs + [
+            "-gencode", "arch=compute_100a,code=sm_100a",
+            "-Xlinker", "-rpath,/usr/local/cuda/lib64"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

@@ -106,11 +106,17 @@ class ClickstreamTransformer:
     feature_vocabs values may be a vocabulary file path (reference), a list of tokens, or an int
     vocabulary size (inputs are then integer ids 10..V+9 already).  `encoder_ff_dim` defaults to
     the reference's hard-coded 100 (clickstream_transformer.py:225).
+
+    precision="bf16" (default) feeds the tensor cores bf16 operands (fp32 accumulation, fp32 master
+    weights); precision="fp32" is the parity mode: fp32 activations end to end, Dense layers as
+    bf16 x 3 split products on the same tcgen05 GEMM, fp32 attention, materialised fp32 logits -
+    loss, logits and gradients then match the fp32 reference to ~1e-5.
     """
 
     def __init__(self, sequential_input_config, feature_vocabs, embedding_dims, head_unit,
                  segment_to_head=None, value_to_head=None, num_encoder_layers=1,
-                 num_attention_heads=1, dropout_rate=0.1, *, encoder_ff_dim=100, seed=0, **kwargs):
+                 num_attention_heads=1, dropout_rate=0.1, *, encoder_ff_dim=100, seed=0,
+                 precision="bf16", **kwargs):
         self.sequential_input_config = sequential_input_config
         self.feature_vocabs = feature_vocabs
         self.embedding_dims = embedding_dims
@@ -132,9 +138,12 @@ class ClickstreamTransformer:
             embedding_sizes={k: self.embedding_sizes[k] for k in seq_keys},
             embedding_dims={k: self.embedding_dims[k] for k in seq_keys},
             num_layers=num_encoder_layers, num_attention_heads=num_attention_heads,
-            encoder_ff_dim=encoder_ff_dim, dropout_rate=dropout_rate, store=self.store, seed=seed)
+            encoder_ff_dim=encoder_ff_dim, dropout_rate=dropout_rate, store=self.store, seed=seed,
+            precision=precision)
+        self.precision = precision
+        self.act = self.transformer.engine.act
         self.d_model = self.transformer.d_model
-        self.head.build(self.store, self.d_model, np.random.default_rng(seed + 1))
+        self.head.build(self.store, self.d_model, np.random.default_rng(seed + 1), precision=precision)
         self.store.finalize()
         if self.value_to_head is not None:
             v = self.value_to_head
@@ -207,7 +216,7 @@ class ClickstreamTransformer:
         return x
 
     def forward_ids(self, ids_list, B, S, training=False, seed=0, n_masked=None,
-                    segment_bounds=None):
+                    segment_bounds=None, rows_are_common=False):
         """Hot-path entry on already-chained device ids (int32 [B*S] per feature)."""
         x = self._encode(ids_list, B, S, training, seed)
         state = dict(x=x, ids_first=ids_list[0], B=B, S=S)
@@ -218,10 +227,10 @@ class ClickstreamTransformer:
             return self.head(head_input)
         cap = int(n_masked) if n_masked is not None else B * S
         vocab = getattr(self.head, "vocab", None)
-        if hasattr(vocab, "common_rows"):
+        if hasattr(vocab, "common_rows") and not rows_are_common:
             cap = vocab.common_rows(cap)  # vocabulary-parallel: every rank presents the same rows
         row_index, count = ops.select_masked(ids_list[0], self._value_id, cap)
-        hsel = self.pool.get("hsel", (cap, ld8(self.d_model)), BF16)
+        hsel = self.pool.get("hsel", (cap, ld8(self.d_model)), self.act)
         ops.gather_rows(x, row_index, None, hsel)
         state["value_id"] = self._value_id
         if isinstance(self.head, SoftMaxHead):
@@ -286,20 +295,38 @@ class ClickstreamTransformer:
         """Data-parallel training: gradients / loss statistics are all-reduced over `group`."""
         self.process_group = group
 
-    def _allreduce(self, t):
+    def _allreduce(self, t, async_op=False):
+        """Sum over the data-parallel group.  async_op=True returns the pending work (or None on
+        one rank): the collective runs on NCCL's stream while this stream carries on with the
+        rest of the backward, and `_finish_reduce` makes this stream wait for it."""
         import torch.distributed as dist
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.process_group) > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.process_group)
+            return dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.process_group,
+                                   async_op=async_op)
+        return None
+
+    def _reduce_gradients(self, early=()):
+        """All-reduce every replicated gradient that is not reduced yet (`early`: names whose
+        all-reduce was launched asynchronously when they became final)."""
+        for run in self.store.replicated_grad_runs(exclude=set(early)):
+            self._allreduce(run)
+
+    @staticmethod
+    def _finish_reduce(works):
+        for w in works:
+            if w is not None:
+                w.wait()
 
     def cloze_forward_backward(self, ids_list, labels_f32, B, S, n_masked=None, training=True,
-                               seed=0):
+                               seed=0, rows_are_common=False):
         """One Cloze forward + backward on device-resident inputs.  labels_f32: (B, Mmax) float32
         padded with -1 (the reference contract).  Gradients land in store.flat_g; returns the
         device tensor loss_stats = (sum of per-position losses, valid positions) — already
         all-reduced when a process group is set, so loss = stats[0] / stats[1] is the GLOBAL
         masked mean."""
         assert isinstance(self.head, SoftMaxHead) and self.value_to_head is not None
-        out = self.forward_ids(ids_list, B, S, training, seed, n_masked=n_masked)
+        out = self.forward_ids(ids_list, B, S, training, seed, n_masked=n_masked,
+                               rows_are_common=rows_are_common)
         cap = out.M
         labels, _ = ops.compact_labels(labels_f32, cap)
         stats = self.pool.get("loss_stats", (2,))
@@ -309,17 +336,24 @@ class ClickstreamTransformer:
             self._allreduce(stats)
         d = self.d_model
         dsel = self.pool.get("dsel", (cap, d))
+        # the output kernel's gradient (the largest tensor: 28 of 45 MB at C1) is final as soon as
+        # the vocabulary backward has run: its all-reduce overlaps the head-MLP / encoder backward
+        early = (f"{self.head.prefix}.out.w", f"{self.head.prefix}.out.b")
         if mlp.dims:
-            dzb = self.pool.get("dz_head", (cap, ld8(mlp.out_dim)), BF16)
+            dzb = self.pool.get("dz_head", (cap, ld8(mlp.out_dim)), self.act)
             vocab.loss_backward(stats, out.ab, out_bf16=dzb)
+            works = [self._allreduce(r, async_op=True)
+                     for r in self.store.replicated_grad_runs(only=set(early))]
             mlp.backward(dzb, dsel)
         else:
             vocab.loss_backward(stats, None, out_f32=dsel)
+            works = [self._allreduce(r, async_op=True)
+                     for r in self.store.replicated_grad_runs(only=set(early))]
         dx = self.pool.get("dx_top", (B * S, d), zero=True)
         ops.scatter_rows(dsel, out.row_index, dx)
-        self.transformer.engine.backward(dx)
-        for run in self.store.replicated_grad_runs():
-            self._allreduce(run)
+        self.transformer.engine.backward(dx, self.process_group)
+        self._reduce_gradients(early)
+        self._finish_reduce(works)
         self._last_output = out
         self._last_labels = labels
         return stats
@@ -346,7 +380,7 @@ class ClickstreamTransformer:
             self._seg_rows_key = key
         row_index = self._seg_rows
         d = self.d_model
-        hsel = self.pool.get("hsel_bin", (M, ld8(d)), BF16)
+        hsel = self.pool.get("hsel_bin", (M, ld8(d)), self.act)
         ops.gather_rows(x, row_index, None, hsel)
         head = self.head
         z, ab = head.logits(hsel, M)
@@ -359,7 +393,21 @@ class ClickstreamTransformer:
         dz = self.pool.get("dz_bin", (M,))
         dsel = self.pool.get("dsel_bin", (M, d))
         mlp = head.mlp
-        if mlp.dims:
+        if self.act == F32:
+            # fp32-class mode: the same backward from generic pieces (item-wise dz, then the three
+            # Dense(1) products as fp32-class GEMMs)
+            h = head.h
+            ops.sigmoid_bce_dz(y, probs, M, 1, label_pad, pos_weight, stats, dz_f32=dz)
+            dz2 = dz.view(M, 1)
+            ops.gemm_splitk(ab, 1, dz2, 1, h, 1, M, W.g.view(h, 1))
+            ops.colsum_bf16(dz2, M, 1, b.g)
+            if mlp.dims:
+                dab = self.pool.get("dab_bin", (M, ld8(mlp.out_dim)), F32)
+                ops.gemm(dz2, 0, W.w, 0, M, h, 1, gate=ab, out_f32=dab)
+                mlp.backward(dab, dsel)
+            else:
+                ops.gemm(dz2, 0, W.w, 0, M, h, 1, out_f32=dsel)
+        elif mlp.dims:
             dab = self.pool.get("dab_bin", (M, ld8(mlp.out_dim)), BF16)
             ops.binary_head_bwd(y, probs, label_pad, pos_weight, stats, ab, head.h, W.w, True, dz,
                                 dab_bf16=dab, dw=W.g, db=b.g)
@@ -369,9 +417,8 @@ class ClickstreamTransformer:
                                 dab_f32=dsel, dw=W.g, db=b.g)
         dx = self.pool.get("dx_top", (B * S, d), zero=True)
         ops.scatter_rows(dsel, row_index, dx)
-        self.transformer.engine.backward(dx)
-        for run in self.store.replicated_grad_runs():
-            self._allreduce(run)
+        self.transformer.engine.backward(dx, self.process_group)
+        self._reduce_gradients()
         self._last_probs = probs.view(B, Ls)
         return stats
 
@@ -398,39 +445,40 @@ class ClickstreamTransformer:
             self._seg_rows = torch.from_numpy(idx.astype(np.int32)).cuda()
             self._seg_rows_key = key
         row_index = self._seg_rows
-        hsel = self.pool.get("hsel_bin", (M, ld8(d)), BF16)
+        from .engine import kernel_of
+        fp32 = self.act == F32
+        hsel = self.pool.get("hsel_bin", (M, ld8(d)), self.act)
         ops.gather_rows(x, row_index, None, hsel)
         ab = head.hidden(hsel, M)
         W, b = self.store[f"{head.prefix}.out.w"], self.store[f"{head.prefix}.out.b"]
         z = self.pool.get("z_ml", (M, V))
-        ops.gemm(ab, 0, W.wb, 1, M, V, h, bias=b.w, out_f32=z)
+        ops.gemm(ab, 0, kernel_of(W, ab), 1, M, V, h, bias=b.w, out_f32=z)
         probs = ops.sigmoid(z.view(-1), out=self.pool.get("p_ml", (M * V,)))
         y = y_f32.reshape(-1).contiguous()
         assert y.numel() == M * V, "labels must be (B, output_vocab_size)"
         stats = ops.masked_bce(y, probs, label_pad, pos_weight)
         self._allreduce(stats)
-        dzb = self.pool.get("dz_ml", (M, ld8(V)), BF16)
-        ops.sigmoid_bce_dz(y, probs, M, V, label_pad, pos_weight, stats, dz_bf16=dzb)
+        if fp32:   # fp32-class mode: dz stays fp32, the GEMMs below split it (ops.gemm dispatch)
+            dzb = self.pool.get("dz_ml32", (M, V))
+            ops.sigmoid_bce_dz(y, probs, M, V, label_pad, pos_weight, stats, dz_f32=dzb)
+        else:
+            dzb = self.pool.get("dz_ml", (M, ld8(V)), BF16)
+            ops.sigmoid_bce_dz(y, probs, M, V, label_pad, pos_weight, stats, dz_bf16=dzb)
         ops.gemm_splitk(ab, 1, dzb, 1, h, V, M, W.g, ws_name="splitk_vocab")
         ops.colsum_bf16(dzb, M, V, b.g)
         # d(ab) = dz W^T: K = V is long and M x h small -> split-K with a (ReLU-gated) reduce
-        splits = ops.gemm_splits_for(M, h, V)
-        part = ops.WS.get("splitk_dx", splits * M * h * 4).view(F32)[: splits * M * h]
-        part = part.view(splits, M, h)
-        ops.gemm(dzb, 0, W.wb, 0, M, h, V, out_f32=part, splits=splits)
         dsel = self.pool.get("dsel_bin", (M, d))
         mlp = head.mlp
         if mlp.dims:
-            dab = self.pool.get("dab_bin", (M, ld8(mlp.out_dim)), BF16)
-            ops.reduce_splits_ex(part, M, h, ab, None, dab)
+            dab = self.pool.get("dab_bin", (M, ld8(mlp.out_dim)), self.act)
+            ops.gemm_splitk_ex(dzb, 0, kernel_of(W, dzb), 0, M, h, V, ab, None, dab)
             mlp.backward(dab, dsel)
         else:
-            ops.reduce_splits_ex(part, M, h, None, dsel, None)
+            ops.gemm_splitk_ex(dzb, 0, kernel_of(W, dzb), 0, M, h, V, None, dsel, None)
         dx = self.pool.get("dx_top", (B * S, d), zero=True)
         ops.scatter_rows(dsel, row_index, dx)
-        self.transformer.engine.backward(dx)
-        for run in self.store.replicated_grad_runs():
-            self._allreduce(run)
+        self.transformer.engine.backward(dx, self.process_group)
+        self._reduce_gradients()
         self._last_probs = probs.view(B, V)
         return stats
 
@@ -457,12 +505,15 @@ class ClickstreamTransformer:
             return {'loss': mean / ((pw + 1.0) / 2) if pw is not None else mean}
         stats = self.cloze_forward_backward(ids_list, y, B, S, n_masked=n_host,
                                             seed=self._next_seed())
+        # metrics first: they score the forward pass's hidden rows against the weights that
+        # produced them (Keras computes train metrics on the forward predictions), then Adam
+        for m in self.metrics:
+            m.update_state(y, self._last_output)
         opt = self.optimizer or Adam()
         self.store.adam(self._next_lr(opt), opt.beta_1, opt.beta_2, opt.epsilon)
         s = stats.cpu().numpy()
         logs = {'loss': float(s[0] / s[1]) if s[1] > 0 else 0.0}
         for m in self.metrics:
-            m.update_state(y, self._last_output)
             logs[m.name] = float(m.result())
         return logs
 
@@ -501,9 +552,21 @@ class ClickstreamTransformer:
         (weights.tf_checkpoint_key), so the same file can be produced on a TensorFlow box from a
         reference checkpoint and loaded here, and the other way round."""
         from .weights import export_reference_variables
-        np.savez(path, **export_reference_variables(self.store.get_weights()))
+        import torch.distributed as dist
+        weights = self.store.get_weights()
+        vocab = getattr(self.head, "vocab", None)
+        if hasattr(vocab, "gather_full_weights"):   # vocabulary-parallel: every rank takes part
+            weights.update(vocab.gather_full_weights())
+        if dist.is_available() and dist.is_initialized() and dist.get_rank() != 0:
+            return   # replicas are identical: one writer
+        np.savez(path, **export_reference_variables(weights, self.transformer.engine.features))
 
     def load_weights(self, path):
         from .weights import import_reference_variables
         with np.load(path) as z:
-            self.store.set_weights(import_reference_variables({k: z[k] for k in z.files}))
+            arrays = import_reference_variables({k: z[k] for k in z.files},
+                                                self.transformer.engine.features)
+        vocab = getattr(self.head, "vocab", None)
+        if hasattr(vocab, "shard_full_weights"):
+            arrays = vocab.shard_full_weights(arrays)
+        self.store.set_weights(arrays)

@@ -61,8 +61,12 @@ class ClozeMaskedLoss:
 
 
 class _ClozeRankMetric:
+    MAX_K = 256   # b4cp_topk_rows / b4cp_rank_metrics limit (include/b4cp.h)
+
     def __init__(self, k, name):
         self.k, self.name = int(k), name
+        if not 1 <= self.k <= self.MAX_K:
+            raise ValueError(f"k={k}: ranking metrics support 1 <= k <= {self.MAX_K}")
         self.counters = None
 
     def _counters(self):
@@ -76,12 +80,12 @@ class _ClozeRankMetric:
     def update_state(self, y_true, y_pred, sample_weight=None):
         labels, scores, V = _compact(y_true, y_pred)
         if isinstance(y_pred, ClozeOutput):
-            ids = y_pred.head.vocab.topk(y_pred.ab, y_pred.M, min(self.k, 256))
+            ids = y_pred.head.vocab.topk(y_pred.ab, y_pred.M, self.k)
         else:
             if scores.shape[0] == 0:
                 return
             ids, _ = ops.topk_rows(scores, V, self.k)
-        ops.rank_metrics(ids, self.k, labels, self._counters())
+        ops.rank_metrics(ids, ids.shape[1], labels, self._counters())
 
     def reset_states(self):
         if self.counters is not None:

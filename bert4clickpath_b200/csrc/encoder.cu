@@ -305,7 +305,7 @@ residual_ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x
                        const float* __restrict__ r, long T, int d,
                        const float* __restrict__ gamma, DropSpec dp, float eps,
                        float* __restrict__ dx, __nv_bfloat16* __restrict__ dr_bf16, long ld_bf16,
-                       float* __restrict__ partial) {
+                       float* __restrict__ dr_f32, float* __restrict__ partial) {
   __shared__ float red[8][3][NPL * 32];
   if (dp.thresh24) dp.seed = resolve_seed(dp.seed);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -370,6 +370,7 @@ residual_ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x
         const float drv = dres * keepf[t];
         if (dx) dx[row * d + c] = dres;
         if (dr_bf16) dr_bf16[row * ld_bf16 + c] = __float2bfloat16_rn(drv);
+        if (dr_f32) dr_f32[row * d + c] = drv;
         pr[t] += drv;
       }
     }
@@ -479,7 +480,7 @@ residual_ln_bwd_vec_kernel(const float* __restrict__ dy, const float* __restrict
                            const float* __restrict__ r, long T, const float* __restrict__ gamma,
                            DropSpec dp, float eps, float* __restrict__ dx,
                            __nv_bfloat16* __restrict__ dr_bf16, long ld_bf16,
-                           float* __restrict__ partial) {
+                           float* __restrict__ dr_f32, float* __restrict__ partial) {
   using C = LnVec<D>;
   __shared__ float red[8][3][D];
   if (dp.thresh24) dp.seed = resolve_seed(dp.seed);
@@ -560,6 +561,7 @@ residual_ln_bwd_vec_kernel(const float* __restrict__ dy, const float* __restrict
         }
         if (dx) *reinterpret_cast<float4*>(dx + row * D + c) = make_float4(dres[0], dres[1], dres[2], dres[3]);
         if (dr_bf16) store_bf16x4(dr_bf16 + row * ld_bf16 + c, drv);
+        if (dr_f32) *reinterpret_cast<float4*>(dr_f32 + row * D + c) = make_float4(drv[0], drv[1], drv[2], drv[3]);
       }
     }
   }
@@ -717,6 +719,14 @@ dropout_mask_kernel(float* __restrict__ out, long n, DropSpec dp) {
     out[i] = (!dp.thresh24 || dropout_keep(dp.seed, dp.site, (uint64_t)i, dp.thresh24)) ? dp.inv_keep : 0.f;
 }
 
+__global__ void __launch_bounds__(256)
+dropout_apply_kernel(float* __restrict__ x, long n, DropSpec dp) {
+  dp.seed = resolve_seed(dp.seed);
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n;
+       i += (long)gridDim.x * blockDim.x)
+    x[i] = dropout_keep(dp.seed, dp.site, (uint64_t)i, dp.thresh24) ? x[i] * dp.inv_keep : 0.f;
+}
+
 static DropSpec make_drop(float rate, uint64_t seed, uint32_t site) {
   DropSpec d;
   d.inv_keep = 1.0f / (1.0f - rate);
@@ -822,8 +832,8 @@ extern "C" long b4cp_residual_ln_bwd_workspace_bytes(int d) {
 extern "C" int b4cp_residual_ln_bwd(const float* dy, const float* x, const float* r, long T,
                                     int d, const float* gamma, float dropout_rate, uint64_t seed,
                                     uint32_t site, float* dx, void* dr_bf16, long ld_bf16,
-                                    float* dgamma, float* dbeta, float* dbias, void* workspace,
-                                    void* stream) {
+                                    float* dr_f32, float* dgamma, float* dbeta, float* dbias,
+                                    void* workspace, void* stream) {
   B4CP_CHECK_ARG(d >= 1 && d <= LN_MAX_PER_LANE * 32, "layernorm: d=%d must be <= 256", d);
   B4CP_CHECK_ARG(workspace, "layernorm bwd: workspace required");
   cudaStream_t st = (cudaStream_t)stream;
@@ -831,15 +841,15 @@ extern "C" int b4cp_residual_ln_bwd(const float* dy, const float* x, const float
   const int blocks = (int)std::min<long>(LN_BWD_BLOCKS, std::max<long>(1, ceil_div(T, 8)));
   const DropSpec dsp = make_drop(dropout_rate, seed, site);
   __nv_bfloat16* drb = (__nv_bfloat16*)dr_bf16;
-  const bool vec_ok = (((uintptr_t)x | (uintptr_t)r | (uintptr_t)dy | (uintptr_t)dx | (uintptr_t)gamma) & 15) == 0 &&
+  const bool vec_ok = (((uintptr_t)x | (uintptr_t)r | (uintptr_t)dy | (uintptr_t)dx | (uintptr_t)gamma | (uintptr_t)dr_f32) & 15) == 0 &&
                       ((uintptr_t)dr_bf16 & 7) == 0 && ld_bf16 % 4 == 0;
-  if (vec_ok && d == 64) residual_ln_bwd_vec_kernel<64><<<blocks, 256, 0, st>>>(dy, x, r, T, gamma, dsp, 1e-6f, dx, drb, ld_bf16, partial);
-  else if (vec_ok && d == 128) residual_ln_bwd_vec_kernel<128><<<blocks, 256, 0, st>>>(dy, x, r, T, gamma, dsp, 1e-6f, dx, drb, ld_bf16, partial);
-  else if (vec_ok && d == 256) residual_ln_bwd_vec_kernel<256><<<blocks, 256, 0, st>>>(dy, x, r, T, gamma, dsp, 1e-6f, dx, drb, ld_bf16, partial);
-  else if (d <= 32) residual_ln_bwd_kernel<1><<<blocks, 256, 0, st>>>(dy, x, r, T, d, gamma, dsp, 1e-6f, dx, drb, ld_bf16, partial);
-  else if (d <= 64) residual_ln_bwd_kernel<2><<<blocks, 256, 0, st>>>(dy, x, r, T, d, gamma, dsp, 1e-6f, dx, drb, ld_bf16, partial);
-  else if (d <= 128) residual_ln_bwd_kernel<4><<<blocks, 256, 0, st>>>(dy, x, r, T, d, gamma, dsp, 1e-6f, dx, drb, ld_bf16, partial);
-  else residual_ln_bwd_kernel<8><<<blocks, 256, 0, st>>>(dy, x, r, T, d, gamma, dsp, 1e-6f, dx, drb, ld_bf16, partial);
+  if (vec_ok && d == 64) residual_ln_bwd_vec_kernel<64><<<blocks, 256, 0, st>>>(dy, x, r, T, gamma, dsp, 1e-6f, dx, drb, ld_bf16, dr_f32, partial);
+  else if (vec_ok && d == 128) residual_ln_bwd_vec_kernel<128><<<blocks, 256, 0, st>>>(dy, x, r, T, gamma, dsp, 1e-6f, dx, drb, ld_bf16, dr_f32, partial);
+  else if (vec_ok && d == 256) residual_ln_bwd_vec_kernel<256><<<blocks, 256, 0, st>>>(dy, x, r, T, gamma, dsp, 1e-6f, dx, drb, ld_bf16, dr_f32, partial);
+  else if (d <= 32) residual_ln_bwd_kernel<1><<<blocks, 256, 0, st>>>(dy, x, r, T, d, gamma, dsp, 1e-6f, dx, drb, ld_bf16, dr_f32, partial);
+  else if (d <= 64) residual_ln_bwd_kernel<2><<<blocks, 256, 0, st>>>(dy, x, r, T, d, gamma, dsp, 1e-6f, dx, drb, ld_bf16, dr_f32, partial);
+  else if (d <= 128) residual_ln_bwd_kernel<4><<<blocks, 256, 0, st>>>(dy, x, r, T, d, gamma, dsp, 1e-6f, dx, drb, ld_bf16, dr_f32, partial);
+  else residual_ln_bwd_kernel<8><<<blocks, 256, 0, st>>>(dy, x, r, T, d, gamma, dsp, 1e-6f, dx, drb, ld_bf16, dr_f32, partial);
   if (dgamma || dbeta || dbias)
     reduce_ln_partials_kernel<<<ceil_div(3 * d, 8), 256, 0, st>>>(partial, blocks, d, dgamma, dbeta, dbias);
   note_launches(1 + ((dgamma || dbeta || dbias) ? 1 : 0));
@@ -932,6 +942,18 @@ extern "C" int b4cp_dropout_mask(float* out, long n, float dropout_rate, uint64_
   const int blocks = (int)std::min<long>(ceil_div(n, 256), 148L * 16);
   dropout_mask_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(out, n,
                                                                  make_drop(dropout_rate, seed, site));
+  note_launches(1);
+  B4CP_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int b4cp_dropout_apply(float* x, long n, float dropout_rate, uint64_t seed,
+                                  uint32_t site, void* stream) {
+  if (n == 0 || !(dropout_rate > 0.f)) return 0;
+  const DropSpec dsp = make_drop(dropout_rate, seed, site);
+  if (!dsp.thresh24) return 0;
+  const int blocks = (int)std::min<long>(ceil_div(n, 256), 148L * 16);
+  dropout_apply_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, n, dsp);
   note_launches(1);
   B4CP_LAUNCH_CHECK();
   return 0;

@@ -113,6 +113,22 @@ ce_rows_grad_kernel(const float* __restrict__ logits, long ld, int V,
   }
 }
 
+// the same gradient in fp32, written IN PLACE over the logits (the fp32-class parity path keeps
+// no bf16 copy of dZ): z[row][v] <- (softmax - onehot) / n_valid, pad columns [V, ld) <- 0
+__global__ void __launch_bounds__(256)
+ce_rows_grad_f32_kernel(float* __restrict__ logits, long ld, int V,
+                        const int32_t* __restrict__ labels, const float* __restrict__ lse,
+                        const float* __restrict__ loss_stats) {
+  const long row = blockIdx.x;
+  const float n = loss_stats[1];
+  const int t = labels[row];
+  const float scale = (t >= 0 && n > 0.f) ? 1.f / n : 0.f;
+  const float l = lse[row];
+  float* z = logits + row * ld;
+  for (long v = threadIdx.x; v < ld; v += blockDim.x)
+    z[v] = v < V ? (expf(z[v] - l) - (v == t ? 1.f : 0.f)) * scale : 0.f;
+}
+
 // counters[0] += hits, counters[1] += sum of 1/log2(rank+2) at the hit, counters[2] += n valid
 __global__ void __launch_bounds__(256)
 rank_metrics_kernel(const int32_t* __restrict__ topk_ids, long M, int k, long ld,
@@ -292,6 +308,17 @@ extern "C" int b4cp_ce_rows_grad(const float* logits, long ld, long M, int V,
   if (M == 0) return 0;
   ce_rows_grad_kernel<<<(unsigned)M, 256, 0, (cudaStream_t)stream>>>(
       logits, ld, V, labels, lse, loss_stats, (__nv_bfloat16*)dz_bf16, ld_dz, probs, ld_probs);
+  note_launches(1);
+  B4CP_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int b4cp_ce_rows_grad_f32(float* logits, long ld, long M, int V, const int32_t* labels,
+                                     const float* lse, const float* loss_stats, void* stream) {
+  B4CP_CHECK_ARG(labels && lse && loss_stats, "ce_rows_grad_f32: labels, lse and loss_stats required");
+  if (M == 0) return 0;
+  ce_rows_grad_f32_kernel<<<(unsigned)M, 256, 0, (cudaStream_t)stream>>>(logits, ld, V, labels, lse,
+                                                                         loss_stats);
   note_launches(1);
   B4CP_LAUNCH_CHECK();
   return 0;

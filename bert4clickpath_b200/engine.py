@@ -8,6 +8,13 @@ sequence of kernel launches on one stream (CUDA-graph capturable: no host sync, 
 Numerics: fp32 master weights and residual stream; Dense layers run on tcgen05 tensor cores with
 bf16 operands and fp32 accumulation (bf16 shadows of the weights are refreshed by the Adam
 kernel); attention / LayerNorm / softmax math is fp32.
+
+precision="fp32" (the parity mode) keeps every activation in fp32: Dense layers
+still run on the tcgen05 GEMM, with both operands split into bf16 hi + lo parts along the
+contraction axis (`ops.x3_operands`: hi*hi + hi*lo + lo*hi accumulated in fp32), attention runs in
+the fp32 SIMT kernel and the Cloze output stage on materialised fp32 logits.  The same engine code
+serves both modes: activation buffers are allocated in `act` (bf16 or fp32) and the `ops`
+wrappers dispatch on the dtype they are handed.
 """
 import math
 
@@ -25,7 +32,8 @@ def site(layer, k):
 
 
 class Param:
-    __slots__ = ("name", "shape", "w", "g", "m", "v", "wb", "offset", "numel", "replicated")
+    __slots__ = ("name", "shape", "w", "g", "m", "v", "wb", "offset", "numel", "replicated",
+                 "grad_is_global")
 
     def __init__(self, name, shape):
         self.name, self.shape = name, tuple(shape)
@@ -33,6 +41,7 @@ class Param:
         self.w = self.g = self.m = self.v = self.wb = None
         self.offset = 0
         self.replicated = True  # False: a per-rank shard, excluded from the data-parallel all-reduce
+        self.grad_is_global = False  # True: .g already holds the sum over ranks (row exchange)
 
 
 class ParamStore:
@@ -94,12 +103,16 @@ class ParamStore:
     def get_weights(self):
         return {n: p.w.detach().cpu().numpy().copy() for n, p in self.params.items()}
 
-    def replicated_grad_runs(self):
+    def replicated_grad_runs(self, only=None, exclude=()):
         """Maximal contiguous slices of flat_g that hold replicated parameters (what data
-        parallelism all-reduces; vocabulary-parallel shards are already complete per rank)."""
+        parallelism all-reduces; vocabulary-parallel shards are already complete per rank, and so
+        are tables whose gradient rows were exchanged before the segment sums).  `only` /
+        `exclude`: parameter names, to all-reduce a group as soon as its gradients are final."""
         runs = []
         for p in sorted(self.params.values(), key=lambda q: q.offset):
-            if not p.replicated:
+            if not p.replicated or p.grad_is_global:
+                continue
+            if (only is not None and p.name not in only) or p.name in exclude:
                 continue
             end = p.offset + (p.numel + 63) // 64 * 64
             if runs and runs[-1][1] == p.offset:
@@ -157,11 +170,17 @@ def glorot_uniform(rng, fan_in, fan_out):
 
 
 # =============================================================================== dense layer
+def kernel_of(W, like):
+    """The Dense kernel as a GEMM operand: the bf16 shadow next to bf16 activations, the fp32
+    master weights next to fp32 activations (fp32-class mode)."""
+    return W.w if like.dtype == F32 else W.wb
+
+
 def dense_fwd(xb, K, W, bias, M, *, relu=False, out_f32=None, out_bf16=None):
     """y = act(x W + b).  xb bf16 [M, ld8(K)], W: Param with Keras (K, N) kernel + shadow."""
     N = W.shape[1]
-    ops.gemm(xb, 0, W.wb, 1, M, N, K, bias=bias.w if bias is not None else None, relu=relu,
-             out_f32=out_f32, out_bf16=out_bf16)
+    ops.gemm(xb, 0, kernel_of(W, xb), 1, M, N, K, bias=bias.w if bias is not None else None,
+             relu=relu, out_f32=out_f32, out_bf16=out_bf16)
 
 
 def dense_bwd_weights(xb, dyb, W, bias, M, *, db_from=None):
@@ -175,7 +194,7 @@ def dense_bwd_weights(xb, dyb, W, bias, M, *, db_from=None):
 def dense_bwd_input(dyb, W, M, *, gate=None, addend=None, out_f32=None, out_bf16=None):
     """dx = dy W^T, optionally gated by the ReLU of the layer that produced x / accumulated."""
     K, N = W.shape
-    ops.gemm(dyb, 0, W.wb, 0, M, K, N, gate=gate, addend=addend, out_f32=out_f32,
+    ops.gemm(dyb, 0, kernel_of(W, dyb), 0, M, K, N, gate=gate, addend=addend, out_f32=out_f32,
              out_bf16=out_bf16)
 
 
@@ -184,8 +203,12 @@ class EncoderEngine:
     """Embedding + encoder stack (clickstream_transformer/transformer.py:271-402)."""
 
     def __init__(self, store, embedding_sizes, embedding_dims, num_layers, num_heads, dff,
-                 dropout_rate, rng, max_pos=10000):
+                 dropout_rate, rng, max_pos=10000, precision="bf16"):
         from .transformer import positional_encoding
+        if precision not in ("bf16", "fp32"):
+            raise ValueError("precision must be 'bf16' (fast path) or 'fp32' (parity mode)")
+        self.precision = precision
+        self.act = F32 if precision == "fp32" else BF16
         self.store = store
         self.features = list(embedding_dims.keys())
         self.rows = [int(embedding_sizes[f]) for f in self.features]
@@ -225,33 +248,34 @@ class EncoderEngine:
         """ids_list: per-feature int32 [B*S] device tensors.  Returns fp32 [B*S, d] (+ bf16)."""
         st, pool, d, T = self.store, self.pool, self.d, B * S
         rate = self.rate if training else 0.0
+        act, lowp = self.act, self.act == BF16
         tables = [st[f"emb.{f}"].w for f in range(len(self.features))]
         x = pool.get("x0", (T, d))
-        xb = pool.get("x0b", (T, d), BF16)
+        xb = pool.get("x0b", (T, d), BF16) if lowp else x   # fp32 mode: the fp32 buffer IS the operand
         ops.embed_fwd(ids_list, tables, self._pe(), B, S, dropout_rate=rate, seed=seed,
-                      site=SITE_INPUT, out_f32=x, out_bf16=xb)
+                      site=SITE_INPUT, out_f32=x, out_bf16=xb if lowp else None)
         acts = []
         dffp = ld8(self.dff)
         for l in range(self.L):
             g = lambda n: st[f"enc.{l}.{n}"]
             a = dict(x=x, xb=xb)
-            a["qkvb"] = pool.get(f"qkvb{l}", (T, 3 * d), BF16)
+            a["qkvb"] = pool.get(f"qkvb{l}", (T, 3 * d), act)
             dense_fwd(xb, d, g("wqkv"), g("bqkv"), T, out_bf16=a["qkvb"])
-            a["ob"] = pool.get(f"ob{l}", (T, d), BF16)
+            a["ob"] = pool.get(f"ob{l}", (T, d), act)
             a["lse"] = pool.get(f"lse{l}", (B, self.H, S))
             ops.attention_fwd(a["qkvb"], ids_list[0], B, S, self.H, self.dh, a["ob"], a["lse"])
             a["y1"] = pool.get(f"y1_{l}", (T, d))
             dense_fwd(a["ob"], d, g("wo"), g("bo"), T, out_f32=a["y1"])
             a["x1"] = pool.get(f"x1_{l}", (T, d))
-            a["x1b"] = pool.get(f"x1b{l}", (T, d), BF16)
+            a["x1b"] = pool.get(f"x1b{l}", (T, d), BF16) if lowp else a["x1"]
             ops.residual_ln_fwd(x, a["y1"], g("ln1_g").w, g("ln1_b").w, a["x1"], a["x1b"],
                                 dropout_rate=rate, seed=seed, site=site(l, 1))
-            a["hb"] = pool.get(f"hb{l}", (T, dffp), BF16)
+            a["hb"] = pool.get(f"hb{l}", (T, dffp), act)
             dense_fwd(a["x1b"], d, g("w1"), g("b1"), T, relu=True, out_bf16=a["hb"])
             a["y2"] = pool.get(f"y2_{l}", (T, d))
             dense_fwd(a["hb"], self.dff, g("w2"), g("b2"), T, out_f32=a["y2"])
             x2 = pool.get(f"x2_{l}", (T, d))
-            x2b = pool.get(f"x2b{l}", (T, d), BF16)
+            x2b = pool.get(f"x2b{l}", (T, d), BF16) if lowp else x2
             ops.residual_ln_fwd(a["x1"], a["y2"], g("ln2_g").w, g("ln2_b").w, x2, x2b,
                                 dropout_rate=rate, seed=seed, site=site(l, 2))
             acts.append(a)
@@ -259,46 +283,83 @@ class EncoderEngine:
         self.saved = dict(acts=acts, ids=ids_list, B=B, S=S, rate=rate, seed=seed)
         return x, xb
 
-    def backward(self, dx):
-        """dx: fp32 [T, d] gradient of the encoder output.  Fills every encoder / table .g"""
+    # Data-parallel table gradients.  The reference's MirroredStrategy reduces the IndexedSlices
+    # gradient of tf.gather (examples/BERT4Rec/source/main.py:52).  Here a table's gradient is
+    # either all-reduced dense with the rest of the flat buffer, or - when the table is much
+    # larger than a step's token rows (C3 / C4: 10^5..10^6-row tables) - every rank all-gathers
+    # the (ids, dX rows) of all ranks and runs the same deterministic segment sum over them, so
+    # the 1 GB dense gradient never crosses NVLink and every rank holds the global gradient.
+    ROW_EXCHANGE_RATIO = 2.0   # exchange rows when world * T * d * 4 B < table bytes / ratio
+
+    def plan_table_exchange(self, T, group=None):
+        """Decide (per table) between the dense all-reduce and the row exchange; marks the
+        parameters so that ParamStore.replicated_grad_runs() skips exchanged tables."""
+        import torch.distributed as dist
+        world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        plan = []
+        for f, (R, df) in enumerate(zip(self.rows, self.dims)):
+            rows_bytes = world * T * self.d * 4
+            ex = world > 1 and rows_bytes * self.ROW_EXCHANGE_RATIO < R * df * 4
+            self.store[f"emb.{f}"].grad_is_global = ex
+            plan.append(ex)
+        return plan, world
+
+    def backward(self, dx, group=None):
+        """dx: fp32 [T, d] gradient of the encoder output.  Fills every encoder / table .g
+        (`group`: the data-parallel process group, for the table-gradient row exchange)."""
         sv, st, pool, d = self.saved, self.store, self.pool, self.d
         B, S, rate, seed = sv["B"], sv["S"], sv["rate"], sv["seed"]
         T = B * S
         dffp = ld8(self.dff)
+        act = self.act
         for l in reversed(range(self.L)):
             g = lambda n: st[f"enc.{l}.{n}"]
             a = sv["acts"][l]
             # LN2: dx -> dx1 (residual), dy2 (FFN output grad, bf16) + dgamma/dbeta/db2
             dx1 = pool.get("dxa", (T, d))
-            dy2b = pool.get("dyb", (T, d), BF16)
+            dy2b = pool.get("dyb", (T, d), act)
             ops.residual_ln_bwd(dx, a["x1"], a["y2"], g("ln2_g").w, dx1, dy2b, g("ln2_g").g,
                                 g("ln2_b").g, g("b2").g, dropout_rate=rate, seed=seed,
                                 site=site(l, 2))
             dense_bwd_weights(a["hb"], dy2b, g("w2"), None, T)
-            dhb = pool.get("dhb", (T, dffp), BF16, zero=(dffp != self.dff))
+            dhb = pool.get("dhb", (T, dffp), act, zero=(dffp != self.dff))
             dense_bwd_input(dy2b, g("w2"), T, gate=a["hb"], out_bf16=dhb)
             dense_bwd_weights(a["x1b"], dhb, g("w1"), g("b1"), T)
             dx1b = pool.get("dxb", (T, d))
             dense_bwd_input(dhb, g("w1"), T, addend=dx1, out_f32=dx1b)
             # LN1
             dxr = pool.get("dxa", (T, d))
-            dy1b = pool.get("dyb", (T, d), BF16)
+            dy1b = pool.get("dyb", (T, d), act)
             ops.residual_ln_bwd(dx1b, a["x"], a["y1"], g("ln1_g").w, dxr, dy1b, g("ln1_g").g,
                                 g("ln1_b").g, g("bo").g, dropout_rate=rate, seed=seed,
                                 site=site(l, 1))
             dense_bwd_weights(a["ob"], dy1b, g("wo"), None, T)
-            dob = pool.get("dob", (T, d), BF16)
+            dob = pool.get("dob", (T, d), act)
             dense_bwd_input(dy1b, g("wo"), T, out_bf16=dob)
-            dqkvb = pool.get("dqkvb", (T, 3 * d), BF16)
+            dqkvb = pool.get("dqkvb", (T, 3 * d), act)
             ops.attention_bwd(a["qkvb"], dob, a["lse"], sv["ids"][0], B, S, self.H, self.dh, dqkvb,
                               out=a["ob"])
             dense_bwd_weights(a["xb"], dqkvb, g("wqkv"), g("bqkv"), T)
             dx = pool.get("dxb", (T, d))
             dense_bwd_input(dqkvb, g("wqkv"), T, addend=dxr, out_f32=dx)
+        plan, world = self.plan_table_exchange(T, group)
+        dx_all = None
+        if any(plan):
+            import torch.distributed as dist
+            if rate > 0.0:   # the input-dropout mask is indexed by the LOCAL token: apply it here
+                ops.dropout_apply(dx, rate, seed, SITE_INPUT)
+            dx_all = pool.get("dx_all_ranks", (world * T, d))
+            dist.all_gather_into_tensor(dx_all.view(-1), dx.view(-1), group=group)
         off = 0
         for f, (R, df) in enumerate(zip(self.rows, self.dims)):
-            ops.embed_bwd(dx, d, off, df, sv["ids"][f], R, st[f"emb.{f}"].g, dropout_rate=rate,
-                          seed=seed, site=SITE_INPUT)
+            if plan[f]:
+                ids_all = pool.get(f"ids_all_ranks{f}", (world * T,), I32)
+                dist.all_gather_into_tensor(ids_all, sv["ids"][f], group=group)
+                ops.embed_bwd(dx_all, d, off, df, ids_all, R, st[f"emb.{f}"].g)
+            else:
+                ops.embed_bwd(dx, d, off, df, sv["ids"][f], R, st[f"emb.{f}"].g,
+                              dropout_rate=0.0 if dx_all is not None else rate, seed=seed,
+                              site=SITE_INPUT)
             off += df
         return dx
 
@@ -324,7 +385,7 @@ class MlpEngine:
         prev = self.in_dim
         for i, hd in enumerate(self.dims):
             W, b = self.store[f"{self.prefix}.{i}.w"], self.store[f"{self.prefix}.{i}.b"]
-            out = self.pool.get(f"a{i}", (M, ld8(hd)), BF16)
+            out = self.pool.get(f"a{i}", (M, ld8(hd)), xb.dtype)
             dense_fwd(acts[-1], prev, W, b, M, relu=True, out_bf16=out)
             acts.append(out)
             prev = hd
@@ -339,7 +400,7 @@ class MlpEngine:
             W, b = self.store[f"{self.prefix}.{i}.w"], self.store[f"{self.prefix}.{i}.b"]
             dense_bwd_weights(acts[i], dzb, W, b, M)
             if i > 0:
-                prev = self.pool.get(f"da{i}", (M, ld8(self.dims[i - 1])), BF16)
+                prev = self.pool.get(f"da{i}", (M, ld8(self.dims[i - 1])), dzb.dtype)
                 dense_bwd_input(dzb, W, M, gate=acts[i], out_bf16=prev)
                 dzb = prev
             else:
@@ -410,7 +471,7 @@ class VocabOutputEngine:
         lse = self.pool.get("lse", (M,))
         tgt = self.pool.get("tgt", (M,))
         z = None
-        if self.fused:
+        if self.fused and ab.dtype == BF16:   # fp32-class mode (fp32 rows) is materialised
             t0 = ops.TIMER.begin("vocab_ce")
             ops.vocab_ce_fwd(ab, M, self.h, self.W.wb, self.b.w, self.V, labels, lse, tgt,
                              want_dx=need_grad)
@@ -443,31 +504,32 @@ class VocabOutputEngine:
             return
         chunks = sv["chunks"]
         rows_cap = chunks[0][1] - chunks[0][0]
-        dz_all = self.pool.get("dz", (rows_cap, ld8(V)), BF16)
+        fp32 = ab.dtype == F32
+        dz_all = None if fp32 else self.pool.get("dz", (rows_cap, ld8(V)), BF16)
         db_parts = self.pool.get("db_parts", (len(chunks), V)) if len(chunks) > 1 else None
         for ci, (a, b) in enumerate(chunks):
             rows = b - a
             z = sv["z"] if sv["z"] is not None else self.logits(ab, M, (a, b))
-            dz = dz_all[:rows]
-            ops.ce_rows_grad(z, V, sv["labels"][a:b], sv["lse"][a:b], loss_stats, dz, None)
+            if fp32:   # dZ in fp32, in place over the logits
+                dz = ops.ce_rows_grad_f32(z, V, sv["labels"][a:b], sv["lse"][a:b], loss_stats)
+            else:
+                dz = dz_all[:rows]
+                ops.ce_rows_grad(z, V, sv["labels"][a:b], sv["lse"][a:b], loss_stats, dz, None)
             t0 = ops.TIMER.begin("vocab_gemm")
             if len(chunks) == 1:
                 ops.gemm_splitk(ab, 1, dz, 1, h, V, rows, self.W.g, ws_name="splitk_vocab")
             else:  # dW accumulates over the row ranges in a fixed order (in-place addend)
                 ops.gemm(ab[a:b], 1, dz, 1, h, V, rows, addend=self.W.g if ci else None,
-                         out_f32=self.W.g)
+                         out_f32=self.W.g)   # fp32 rows -> fp32-class product (ops.gemm dispatch)
             ops.TIMER.end("vocab_gemm", t0)
             ops.colsum_bf16(dz, rows, V, self.b.g if db_parts is None else db_parts[ci])
             # dx = dz W^T : K = V is long and rows x h is small -> split-K with a gated reduce
-            splits = ops.gemm_splits_for(rows, h, V)
-            part = ops.WS.get("splitk_dx", splits * rows * h * 4).view(F32)[: splits * rows * h]
-            part = part.view(splits, rows, h)
             t0 = ops.TIMER.begin("vocab_gemm")
-            ops.gemm(dz, 0, self.W.wb, 0, rows, h, V, out_f32=part, splits=splits)
+            ops.gemm_splitk_ex(dz, 0, kernel_of(self.W, dz), 0, rows, h, V,
+                               gate[a:b] if gate is not None else None,
+                               out_f32[a:b] if out_f32 is not None else None,
+                               out_bf16[a:b] if out_bf16 is not None else None)
             ops.TIMER.end("vocab_gemm", t0)
-            ops.reduce_splits_ex(part, rows, h, gate[a:b] if gate is not None else None,
-                                 out_f32[a:b] if out_f32 is not None else None,
-                                 out_bf16[a:b] if out_bf16 is not None else None)
         if db_parts is not None:
             ops.reduce_splits(db_parts, self.b.g)
 
@@ -481,7 +543,8 @@ class VocabOutputEngine:
         the bottleneck.  `prefer_fused_topk = True` selects the fused kernels (they win when HBM
         capacity, not time, is the constraint, and on near-sorted scores)."""
         ids = self.pool.get(f"topk{k}", (M, k), I32)
-        fused_ok = self.h in (64, 128, 256) and k <= 104 and not self.force_materialized
+        fused_ok = (self.h in (64, 128, 256) and k <= 104 and not self.force_materialized
+                    and ab.dtype == BF16)
         if fused_ok and self.prefer_fused_topk:
             t0 = ops.TIMER.begin("score_topk")
             ops.score_topk(ab, M, self.h, self.W.wb, self.b.w, self.V, k, out_ids=ids)
@@ -530,6 +593,32 @@ class VocabParallelOutputEngine(VocabOutputEngine):
         store.add(f"{prefix}.out.b", np.zeros(self.V), replicated=False)
         self.pool = BufferPool()
         self.saved = None
+
+    def gather_full_weights(self):
+        """{name: full (h, V_total) kernel / (V_total,) bias} assembled from every rank's shard
+        (collective: all ranks call it).  Used by save_weights so that one file holds the model."""
+        import torch.distributed as dist
+        per = ld8((self.V_total + self.world - 1) // self.world)
+        wt = torch.zeros((per, self.h), dtype=F32, device="cuda")
+        wt[: self.V] = self.W.w.t()
+        bt = torch.zeros((per,), dtype=F32, device="cuda")
+        bt[: self.V] = self.b.w
+        w_all = torch.empty((self.world * per, self.h), dtype=F32, device="cuda")
+        b_all = torch.empty((self.world * per,), dtype=F32, device="cuda")
+        dist.all_gather_into_tensor(w_all, wt, group=self.group)
+        dist.all_gather_into_tensor(b_all, bt, group=self.group)
+        return {f"{self.prefix}.out.w": w_all[: self.V_total].t().contiguous().cpu().numpy(),
+                f"{self.prefix}.out.b": b_all[: self.V_total].cpu().numpy()}
+
+    def shard_full_weights(self, arrays):
+        """Inverse: replace full output-layer arrays by this rank's columns."""
+        out = dict(arrays)
+        for suffix, cut in (("w", lambda a: a[:, self.v_begin:self.v_end]),
+                            ("b", lambda a: a[self.v_begin:self.v_end])):
+            k = f"{self.prefix}.out.{suffix}"
+            if k in out and np.asarray(out[k]).shape[-1] == self.V_total:
+                out[k] = np.ascontiguousarray(cut(np.asarray(out[k])))
+        return out
 
     def common_rows(self, M):
         """Row capacity shared by all ranks (max over the group); extra rows are padding."""

@@ -5,7 +5,8 @@ import numpy as np
 import torch
 
 from . import ops
-from .engine import MlpEngine, VocabOutputEngine, VocabParallelOutputEngine, glorot_uniform
+from .engine import (MlpEngine, VocabOutputEngine, VocabParallelOutputEngine, glorot_uniform,
+                     kernel_of)
 from .ops import BF16, F32, I32, ld8
 
 
@@ -14,16 +15,22 @@ class _Head:
         self.dense_layer_dims = list(dense_layer_dims)
         self.built = False
 
-    def build(self, store, in_dim, rng, prefix="head"):
+    def build(self, store, in_dim, rng, prefix="head", precision="bf16"):
         assert not self.built, "a Head unit can be attached to one model only"
         self.store, self.in_dim, self.prefix = store, int(in_dim), prefix
+        self.precision = precision
         self.mlp = MlpEngine(store, prefix, in_dim, self.dense_layer_dims, rng)
         self._build_output(store, self.mlp.out_dim, rng)
         self.built = True
 
     def hidden(self, xb, M):
-        """bf16 [M, ld8(in)] -> bf16 [M, ld8(h)]: the ReLU Dense stack (head.py:16-19,41-43)."""
+        """bf16 [M, ld8(in)] -> bf16 [M, ld8(h)]: the ReLU Dense stack (head.py:16-19,41-43).
+        (fp32 in -> fp32 out in the fp32-class mode.)"""
         return self.mlp.forward(xb, M)
+
+    def _operand(self, x_f32):
+        """A fp32 (rows, in_dim) input as the Dense stack's operand in this head's precision."""
+        return x_f32 if self.precision == "fp32" else ops.cast_bf16(x_f32)
 
 
 class ClozeOutput:
@@ -58,7 +65,8 @@ class ClozeOutput:
             idx[b, :len(pos)] = b * S + pos
         row_index = torch.from_numpy(idx.reshape(-1)).cuda()
         M = B * mmax
-        hsel = torch.empty((M, ld8(self.head.in_dim)), dtype=BF16, device="cuda")
+        hsel = torch.empty((M, ld8(self.head.in_dim)), device="cuda",
+                           dtype=F32 if self.head.precision == "fp32" else BF16)
         ops.gather_rows(st["x"], row_index, None, hsel)
         ab = self.head.hidden(hsel, M)
         return self.head.vocab.probabilities(ab, M).view(B, mmax, V)
@@ -88,7 +96,7 @@ class SoftMaxHead(_Head):
         lead = inputs.shape[:-1]
         x = inputs.reshape(-1, self.in_dim).contiguous()
         M = x.shape[0]
-        ab = self.hidden(ops.cast_bf16(x), M)
+        ab = self.hidden(self._operand(x), M)
         return self.vocab.probabilities(ab, M).view(*lead, self.output_vocab_size)
 
     __call__ = call
@@ -107,13 +115,13 @@ class BinaryClassificationHead(_Head):
         ab = self.hidden(xb, M)
         z = torch.empty((M, 1), dtype=F32, device="cuda")
         W, b = self.store[f"{self.prefix}.out.w"], self.store[f"{self.prefix}.out.b"]
-        ops.gemm(ab, 0, W.wb, 1, M, 1, self.h, bias=b.w, out_f32=z)
+        ops.gemm(ab, 0, kernel_of(W, ab), 1, M, 1, self.h, bias=b.w, out_f32=z)
         return z, ab
 
     def call(self, inputs, **kwargs):
         lead = inputs.shape[:-1]
         x = inputs.reshape(-1, self.in_dim).contiguous()
-        z, _ = self.logits(ops.cast_bf16(x), x.shape[0])
+        z, _ = self.logits(self._operand(x), x.shape[0])
         return ops.sigmoid(z.view(-1)).view(*lead)
 
     __call__ = call
@@ -136,10 +144,10 @@ class MultiLabel_MultiClass_classification(_Head):
         lead = inputs.shape[:-1]
         x = inputs.reshape(-1, self.in_dim).contiguous()
         M, V = x.shape[0], self.output_vocab_size
-        ab = self.hidden(ops.cast_bf16(x), M)
+        ab = self.hidden(self._operand(x), M)
         z = torch.empty((M, V), dtype=F32, device="cuda")
         W, b = self.store[f"{self.prefix}.out.w"], self.store[f"{self.prefix}.out.b"]
-        ops.gemm(ab, 0, W.wb, 1, M, V, self.h, bias=b.w, out_f32=z)
+        ops.gemm(ab, 0, kernel_of(W, ab), 1, M, V, self.h, bias=b.w, out_f32=z)
         out = ops.sigmoid(z.view(-1)).view(*lead, V)
         if out.dim() >= 2 and out.shape[1] == 1:
             out = out.squeeze(1)  # tf.squeeze(logits, axis=1)

@@ -84,9 +84,51 @@ TIMER = KernelTimer()
 
 
 # ------------------------------------------------------------------------------------ GEMM
+def split3(x, mn, rows_mn, K, order, ws_name):
+    """fp32 operand -> its bf16 (hi | hi | lo) [order 0] / (hi | lo | hi) [order 1] split along the
+    contraction axis (b4cp_split_bf16x3).  mn = 0: x is [rows_mn][K] (K contiguous) -> bf16
+    [rows_mn][3*ld8(K)]; mn = 1: x is [K][rows_mn] -> bf16 [3*ld8(K)][ld8(rows_mn)]."""
+    kp = ld8(K)
+    if mn == 0:
+        out = WS.get(ws_name, rows_mn * 3 * kp * 2).view(BF16)[: rows_mn * 3 * kp].view(rows_mn, 3 * kp)
+        L.call("b4cp_split_bf16x3", L.ptr(x), L.c_long(rows_mn), L.c_int(K), L.c_long(x.stride(0)),
+               L.ptr(out), L.c_long(3 * kp), L.c_int(0), L.c_int(order), L.stream_ptr())
+    else:
+        ldo = ld8(rows_mn)
+        out = WS.get(ws_name, 3 * kp * ldo * 2).view(BF16)[: 3 * kp * ldo].view(3 * kp, ldo)
+        L.call("b4cp_split_bf16x3", L.ptr(x), L.c_long(K), L.c_int(rows_mn), L.c_long(x.stride(0)),
+               L.ptr(out), L.c_long(ldo), L.c_int(1), L.c_int(order), L.stream_ptr())
+    return out
+
+
+def x3_operands(A, a_mn, B, b_mn, M, N, K):
+    """fp32-class mode: both operands fp32 -> (A3, B3, K3) for ONE bf16 GEMM over K3 = 3*ld8(K)
+    that accumulates hi*hi + hi*lo + lo*hi in fp32."""
+    assert A.dtype == F32 and B.dtype == F32, "fp32-class GEMM needs both operands in fp32"
+    return (split3(A, a_mn, M, K, 0, "x3A"), split3(B, b_mn, N, K, 1, "x3B"), 3 * ld8(K))
+
+
+def _gate_bf16(gate, N):
+    """ReLU-backward gates are tested for > 0 only: a bf16 copy of a fp32 gate is sign-exact."""
+    if gate is None or gate.dtype == BF16:
+        return gate
+    rows = gate.shape[0]
+    buf = WS.get("x3gate", rows * ld8(N) * 2).view(BF16)[: rows * ld8(N)].view(rows, ld8(N))
+    return cast_bf16(gate, N, out=buf)
+
+
 def gemm(A, a_mn, B, b_mn, M, N, K, *, bias=None, relu=False, gate=None, addend=None,
          out_f32=None, out_bf16=None, alpha=1.0, splits=1, lda=None, ldb=None):
-    """C[M,N] = epilogue(alpha * sum_k A(m,k) B(n,k)); see include/b4cp.h."""
+    """C[M,N] = epilogue(alpha * sum_k A(m,k) B(n,k)); see include/b4cp.h.  fp32 operands select
+    the fp32-class product (bf16 x 3 split along K, same tcgen05 kernel); an fp32 tensor passed as
+    `out_bf16` is then simply the fp32 output."""
+    if A.dtype == F32 or B.dtype == F32:
+        A, B, K = x3_operands(A, a_mn, B, b_mn, M, N, K)
+        lda = ldb = None
+    gate = _gate_bf16(gate, N)
+    if out_bf16 is not None and out_bf16.dtype == F32:
+        assert out_f32 is None or out_f32.data_ptr() == out_bf16.data_ptr()
+        out_f32, out_bf16 = out_bf16, None
     ep = L.GemmEpilogue()
     ep.alpha = alpha
     ep.bias = bias.data_ptr() if bias is not None else None
@@ -124,6 +166,8 @@ def reduce_splits(partials, out):
 
 def gemm_splitk(A, a_mn, B, b_mn, M, N, K, out_f32, ws_name="splitk"):
     """Deterministic split-K product into out_f32 [M,N] (used for weight gradients)."""
+    if A.dtype == F32 or B.dtype == F32:
+        A, B, K = x3_operands(A, a_mn, B, b_mn, M, N, K)
     splits = gemm_splits_for(M, N, K)
     if splits <= 1:
         gemm(A, a_mn, B, b_mn, M, N, K, out_f32=out_f32)
@@ -133,7 +177,23 @@ def gemm_splitk(A, a_mn, B, b_mn, M, N, K, out_f32, ws_name="splitk"):
     reduce_splits(buf, out_f32)
 
 
+def gemm_splitk_ex(A, a_mn, B, b_mn, M, N, K, gate=None, out_f32=None, out_bf16=None,
+                   ws_name="splitk_dx"):
+    """Split-K product whose reduction applies a ReLU-backward gate and writes fp32 and/or bf16
+    (dx = dz W^T with K = V long and M x N small)."""
+    if A.dtype == F32 or B.dtype == F32:
+        A, B, K = x3_operands(A, a_mn, B, b_mn, M, N, K)
+    splits = gemm_splits_for(M, N, K)
+    part = WS.get(ws_name, splits * M * N * 4).view(F32)[: splits * M * N].view(splits, M, N)
+    gemm(A, a_mn, B, b_mn, M, N, K, out_f32=part, splits=splits)
+    reduce_splits_ex(part, M, N, gate, out_f32, out_bf16)
+
+
 def reduce_splits_ex(partials, M, N, gate=None, out_f32=None, out_bf16=None):
+    gate = _gate_bf16(gate, N)
+    if out_bf16 is not None and out_bf16.dtype == F32:
+        assert out_f32 is None or out_f32.data_ptr() == out_bf16.data_ptr()
+        out_f32, out_bf16 = out_bf16, None
     splits = partials.shape[0]
     L.call("b4cp_reduce_splits_ex", L.ptr(partials), L.c_int(splits), L.c_long(M), L.c_int(N),
            L.c_long(partials.stride(0)), L.ptr(gate),
@@ -198,18 +258,29 @@ def embed_bwd(dout, d_model, col_offset, dim, ids, rows, table_grad, *, dropout_
 
 # --------------------------------------------------------------------------------- encoder
 def attention_fwd(qkv, ids_first, B, S, H, dh, out, lse):
+    if qkv.dtype == F32:   # fp32-class mode
+        L.call("b4cp_attention_f32_fwd", L.ptr(qkv), L.ptr(ids_first), L.c_int(B), L.c_int(S),
+               L.c_int(H), L.c_int(dh), L.ptr(out), L.ptr(lse), L.stream_ptr())
+        return
     L.call("b4cp_attention_fwd", L.ptr(qkv), L.ptr(ids_first), L.c_int(B), L.c_int(S), L.c_int(H),
            L.c_int(dh), L.ptr(out), L.ptr(lse), L.stream_ptr())
 
 
 def attention_bwd(qkv, dout, lse, ids_first, B, S, H, dh, dqkv, out=None):
     """`out`: the forward output; needed by the tensor-core path for 128 < S <= 256."""
+    if qkv.dtype == F32:
+        L.call("b4cp_attention_f32_bwd", L.ptr(qkv), L.ptr(dout), L.ptr(lse), L.ptr(ids_first),
+               L.c_int(B), L.c_int(S), L.c_int(H), L.c_int(dh), L.ptr(dqkv), L.stream_ptr())
+        return
     L.call("b4cp_attention_bwd", L.ptr(qkv), L.ptr(out), L.ptr(dout), L.ptr(lse), L.ptr(ids_first),
            L.c_int(B), L.c_int(S), L.c_int(H), L.c_int(dh), L.ptr(dqkv), L.stream_ptr())
 
 
 def residual_ln_fwd(x, r, gamma, beta, y_f32, y_bf16, *, dropout_rate=0.0, seed=0, site=0):
     T, d = x.shape
+    if y_bf16 is not None and y_bf16.dtype == F32:   # fp32-class mode: one fp32 output serves both
+        assert y_f32 is None or y_f32.data_ptr() == y_bf16.data_ptr()
+        y_f32, y_bf16 = y_bf16, None
     L.call("b4cp_residual_ln_fwd", L.ptr(x), L.ptr(r), L.c_long(T), L.c_int(d), L.ptr(gamma),
            L.ptr(beta), L.c_float(dropout_rate), L.c_u64(seed), ctypes.c_uint32(site),
            L.ptr(y_f32), L.ptr(y_bf16), L.c_long(y_bf16.stride(0) if y_bf16 is not None else 0),
@@ -222,16 +293,23 @@ def residual_ln_bwd(dy, x, r, gamma, dx, dr_bf16, dgamma, dbeta, dbias, *, dropo
     fn = L.lib().b4cp_residual_ln_bwd_workspace_bytes
     fn.restype = ctypes.c_long
     ws = WS.get("ln_bwd", fn(ctypes.c_int(d)))
+    dr_f32 = None
+    if dr_bf16 is not None and dr_bf16.dtype == F32:   # fp32-class mode
+        dr_f32, dr_bf16 = dr_bf16, None
     L.call("b4cp_residual_ln_bwd", L.ptr(dy), L.ptr(x), L.ptr(r), L.c_long(T), L.c_int(d),
            L.ptr(gamma), L.c_float(dropout_rate), L.c_u64(seed), ctypes.c_uint32(site), L.ptr(dx),
            L.ptr(dr_bf16), L.c_long(dr_bf16.stride(0) if dr_bf16 is not None else 0),
-           L.ptr(dgamma), L.ptr(dbeta), L.ptr(dbias), L.ptr(ws), L.stream_ptr())
+           L.ptr(dr_f32), L.ptr(dgamma), L.ptr(dbeta), L.ptr(dbias), L.ptr(ws), L.stream_ptr())
 
 
 def colsum_bf16(x_bf16, T, n, out):
     fn = L.lib().b4cp_colsum_workspace_bytes
     fn.restype = ctypes.c_long
     ws = WS.get("colsum", fn(ctypes.c_long(T), ctypes.c_int(n)))
+    if x_bf16.dtype == F32:
+        L.call("b4cp_colsum_f32", L.ptr(x_bf16), L.c_long(T), L.c_int(n), L.c_long(x_bf16.stride(0)),
+               L.ptr(out), L.ptr(ws), L.stream_ptr())
+        return
     L.call("b4cp_colsum_bf16", L.ptr(x_bf16), L.c_long(T), L.c_int(n),
            L.c_long(x_bf16.stride(0)), L.ptr(out), L.ptr(ws), L.stream_ptr())
 
@@ -247,6 +325,11 @@ def dropout_mask(n, rate, seed, site):
     L.call("b4cp_dropout_mask", L.ptr(out), L.c_long(n), L.c_float(rate), L.c_u64(seed),
            ctypes.c_uint32(site), L.stream_ptr())
     return out
+
+
+def dropout_apply(x, rate, seed, site):
+    L.call("b4cp_dropout_apply", L.ptr(x), L.c_long(x.numel()), L.c_float(rate), L.c_u64(seed),
+           ctypes.c_uint32(site), L.stream_ptr())
 
 
 # ------------------------------------------------------------------------------- selection
@@ -277,6 +360,9 @@ def compact_labels(labels_f32, capacity, label_pad=-1.0):
 
 def gather_rows(x, row_index, out_f32=None, out_bf16=None):
     M = row_index.numel()
+    if out_bf16 is not None and out_bf16.dtype == F32:
+        assert out_f32 is None and out_bf16.stride(0) == x.shape[1]
+        out_f32, out_bf16 = out_bf16, None
     d = x.shape[1]
     L.call("b4cp_gather_rows", L.ptr(x), L.c_int(d), L.ptr(row_index), L.c_long(M), L.ptr(out_f32),
            L.ptr(out_bf16), L.c_long(out_bf16.stride(0) if out_bf16 is not None else 0),
@@ -307,6 +393,14 @@ def ce_rows_grad(logits, V, labels, lse, loss_stats, dz_bf16=None, probs=None):
            L.ptr(labels), L.ptr(lse), L.ptr(loss_stats), L.ptr(dz_bf16),
            L.c_long(dz_bf16.stride(0) if dz_bf16 is not None else 0), L.ptr(probs),
            L.c_long(probs.stride(0) if probs is not None else 0), L.stream_ptr())
+
+
+def ce_rows_grad_f32(logits, V, labels, lse, loss_stats):
+    """fp32-class mode: dz = (softmax - onehot) / n in place over the fp32 logits [M][ld]."""
+    M = logits.shape[0]
+    L.call("b4cp_ce_rows_grad_f32", L.ptr(logits), L.c_long(logits.stride(0)), L.c_long(M),
+           L.c_int(V), L.ptr(labels), L.ptr(lse), L.ptr(loss_stats), L.stream_ptr())
+    return logits
 
 
 def topk_rows(scores, V, k, out_ids=None, out_scores=None):

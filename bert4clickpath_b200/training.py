@@ -21,18 +21,29 @@ class DeviceBatch:
 
 class ClozeTrainStep:
     """use_graph=True captures the whole step (forward, backward, NCCL gradient all-reduce, Adam)
-    into one CUDA graph per (B, S, masked-row capacity) after two eager steps, and replays it: the
-    ~160 kernel launches of a step cost one host call.  Dropout seeds are then read on the device
-    from the Adam step counter (B4CP_SEED_FROM_DEVICE), so every replay draws new masks."""
+    into one CUDA graph per (B, S, masked-row CAPACITY) after two eager steps, and replays it: the
+    ~140 kernel launches of a step cost one host call.  Dropout seeds are then read on the device
+    from the Adam step counter (B4CP_SEED_FROM_DEVICE), so every replay draws new masks.
+
+    Real Cloze batches have a different total mask count almost every step, so graphs are keyed on
+    a row capacity - the count rounded up to ROW_BUCKET rows - not on the count itself: the
+    selection / label-compaction kernels pad the rows past the true count with -1 and every later
+    kernel treats those rows as dead.  At most MAX_GRAPHS captured graphs are kept (least recently
+    used is dropped).  With a vocabulary-parallel head every rank must present the same capacity:
+    pass `row_capacity` (fixed for the run) or let each step negotiate it (one small all-reduce
+    and host read per step, outside the captured region)."""
 
     GRAPH_WARMUP_STEPS = 2
+    ROW_BUCKET = 128
+    MAX_GRAPHS = 8
 
-    def __init__(self, model, optimizer=None, use_graph=False):
+    def __init__(self, model, optimizer=None, use_graph=False, row_capacity=None):
         self.model = model
         self.opt = optimizer or Adam()
         self.seed = 0
         self.iterations = 0
         self.use_graph = bool(use_graph)
+        self.row_capacity = row_capacity
         self._graphs = {}
         self._dev_ids = self._dev_labels = None
         self._host_stats = torch.empty(2, dtype=F32).pin_memory() if torch.cuda.is_available() else None
@@ -51,19 +62,38 @@ class ClozeTrainStep:
         B, S = batch["ids"].shape
         return DeviceBatch(ids, labels, B, S, batch["n_masked"])
 
-    def _eager(self, db, seed):
+    def capacity(self, n_masked):
+        """Masked-row capacity the step runs at (>= n_masked)."""
+        if self.row_capacity is not None:
+            if n_masked > self.row_capacity:
+                raise ValueError(f"batch has {n_masked} [MASK] rows > row_capacity {self.row_capacity}")
+            return int(self.row_capacity)
+        cap = max(self.ROW_BUCKET, -(-int(n_masked) // self.ROW_BUCKET) * self.ROW_BUCKET)
+        vocab = getattr(self.model.head, "vocab", None)
+        if hasattr(vocab, "common_rows"):
+            cap = vocab.common_rows(cap)      # host read; never inside a capture
+        return cap
+
+    def _eager(self, db, seed, cap=None):
+        cap = self.capacity(db.n_masked) if cap is None else cap
         stats = self.model.cloze_forward_backward(db.ids, db.labels, db.B, db.S,
-                                                  n_masked=db.n_masked, training=True, seed=seed)
+                                                  n_masked=cap, training=True, seed=seed,
+                                                  rows_are_common=True)
         self.model.store.adam(self._lr(), self.opt.beta_1, self.opt.beta_2,
                               self.opt.epsilon)
         return stats
 
     def _step_graph(self, db):
         from . import ops
-        key = (db.B, db.S, int(db.n_masked), len(db.ids))
-        st = self._graphs.get(key)
+        cap = self.capacity(db.n_masked)
+        db = DeviceBatch(db.ids, db.labels, db.B, db.S, cap)
+        key = (db.B, db.S, cap, len(db.ids))
+        st = self._graphs.pop(key, None)
         if st is None:
-            st = self._graphs[key] = dict(calls=0, graph=None)
+            st = dict(calls=0, graph=None)
+            while len(self._graphs) >= self.MAX_GRAPHS:   # LRU: dicts keep insertion order
+                self._graphs.pop(next(iter(self._graphs)))
+        self._graphs[key] = st                            # (re)insert as most recently used
         seed = ops.device_seed(self.model.store.step_dev)
         if callable(self.opt.learning_rate):
             raise TypeError("a learning-rate schedule changes Adam's scalar every step: "
@@ -75,7 +105,7 @@ class ClozeTrainStep:
         if st["graph"] is None:
             st["calls"] += 1
             if st["calls"] <= self.GRAPH_WARMUP_STEPS:   # real steps; they also size every buffer
-                return self._eager(db, seed)
+                return self._eager(db, seed, cap)
             if "ids" not in st:     # kept across re-captures: step_host copies into them
                 st["ids"] = [torch.empty_like(t) for t in db.ids]
                 st["labels"] = torch.empty_like(db.labels)
@@ -83,7 +113,7 @@ class ClozeTrainStep:
             timer_was, ops.TIMER.enabled = ops.TIMER.enabled, False
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                st["stats"] = self._eager(sdb, seed)
+                st["stats"] = self._eager(sdb, seed, cap)
             ops.TIMER.enabled = timer_was
             st["graph"], st["hp"] = g, hp
         for dst, src in zip(st["ids"], db.ids):
@@ -100,8 +130,9 @@ class ClozeTrainStep:
             return self._step_graph(db)
         self.seed += 1
         stats = self.model.cloze_forward_backward(db.ids, db.labels, db.B, db.S,
-                                                  n_masked=db.n_masked, training=True,
-                                                  seed=self.seed)
+                                                  n_masked=self.capacity(db.n_masked),
+                                                  training=True, seed=self.seed,
+                                                  rows_are_common=True)
         self.model.store.adam(self._lr(), self.opt.beta_1, self.opt.beta_2,
                               self.opt.epsilon)
         return stats
@@ -116,7 +147,7 @@ class ClozeTrainStep:
             self._dev_labels = torch.empty(labels_pinned.shape, dtype=F32, device="cuda")
         dev_ids, dev_labels = self._dev_ids.view(-1), self._dev_labels
         if self.use_graph:  # copy straight into the captured graph's input buffers
-            st = self._graphs.get((B, S, int(n_masked), 1))
+            st = self._graphs.get((B, S, self.capacity(n_masked), 1))
             if st is not None and st.get("graph") is not None:
                 dev_ids, dev_labels = st["ids"][0], st["labels"]
         dev_ids.view(B, S).copy_(ids_pinned, non_blocking=True)

@@ -45,7 +45,7 @@ class Transformer:
 
     def __init__(self, num_layers, num_attention_heads, embedding_sizes, embedding_dims,
                  encoder_ff_dim, dropout_rate, item_embedding_weights=None, *, store=None,
-                 seed=0, **kwargs):
+                 seed=0, precision="bf16", **kwargs):
         assert set(embedding_sizes.keys()) == set(embedding_dims.keys()), \
             "embedding_sizes and embedding_dims must have the same set of keys."
         self.num_layers = num_layers
@@ -62,7 +62,8 @@ class Transformer:
         self.store = ParamStore() if store is None else store
         self.engine = EncoderEngine(self.store, embedding_sizes, embedding_dims, num_layers,
                                     num_attention_heads, encoder_ff_dim, dropout_rate,
-                                    np.random.default_rng(seed), self.maximum_position_encoding)
+                                    np.random.default_rng(seed), self.maximum_position_encoding,
+                                    precision=precision)
         self.pos_encoding = self.engine.pe_host[np.newaxis, ...]
         if self._own_store:
             self.store.finalize()

@@ -75,16 +75,37 @@ def tf_checkpoint_key(name):
     raise KeyError(name)
 
 
-def export_reference_variables(store_params):
-    """{TF checkpoint key: float32 array in the Keras layout} for every parameter."""
-    return {tf_checkpoint_key(k): np.asarray(v, dtype=np.float32)
+def _table_name(name, features, to_reference):
+    """The store registers embedding tables by position (`emb.0`, `emb.1`, ... in the key order of
+    sequential_input_config); the reference's `embedding_layers` is a dict keyed by FEATURE NAME
+    (transformer.py:346-355).  `features` (the engine's ordered feature list) converts between
+    the two; without it names pass through unchanged."""
+    parts = name.split(".")
+    if parts[0] != "emb" or features is None:
+        return name
+    tail = ".".join(parts[1:])
+    if to_reference:
+        return f"emb.{features[int(tail)]}" if tail.isdigit() else name
+    if tail in features:
+        return f"emb.{list(features).index(tail)}"
+    if tail.isdigit() and int(tail) < len(features):
+        return name
+    raise KeyError(f"embedding table {tail!r} is not one of the model's features {list(features)}")
+
+
+def export_reference_variables(store_params, features=None):
+    """{TF checkpoint key: float32 array in the Keras layout} for every parameter.  `features`:
+    the model's ordered sequential features (`model.transformer.engine.features`), so that table
+    `emb.<i>` is written under `.../embedding_layers/<feature>/embeddings` as the reference does."""
+    return {tf_checkpoint_key(_table_name(k, features, True)): np.asarray(v, dtype=np.float32)
             for k, v in to_reference_layout(store_params).items()}
 
 
-def import_reference_variables(variables):
+def import_reference_variables(variables, features=None):
     """Inverse of export_reference_variables: a {TF checkpoint key: array} mapping (what
     `tf.train.load_checkpoint(...).get_tensor` yields on a TF box; optimizer slots and
-    bookkeeping keys are ignored) -> the fused store layout, ready for `store.set_weights`."""
+    bookkeeping keys are ignored) -> the fused store layout, ready for `store.set_weights`.
+    `features` maps the reference's feature-named tables onto the store's positional names."""
     import re
     pats = [
         (re.compile(r"^transformer/embedding_layers/(.+)/embeddings$"), lambda m: f"emb.{m[1]}"),
@@ -109,6 +130,6 @@ def import_reference_variables(variables):
         for pat, name in pats:
             m = pat.match(stem)
             if m:
-                ref[name(m)] = np.asarray(arr, dtype=np.float32)
+                ref[_table_name(name(m), features, False)] = np.asarray(arr, dtype=np.float32)
                 break
     return to_store_layout(ref)

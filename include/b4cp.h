@@ -78,6 +78,32 @@ int b4cp_reduce_splits_ex(const float* partials, int splits, long M, int N, long
 int b4cp_cast_f32_bf16(const float* in, long rows, int cols, long ld_in, void* out, long ld_out,
                        void* stream);
 
+/* ------------------------------------------------------------------ fp32-class ("parity") mode
+ * The reference's Dense / attention / softmax arithmetic is fp32 (TensorFlow 2.3.1 kernels behind
+ * clickstream_transformer/transformer.py:64-97, :112-116, :139-167 and head.py:35-45).  These
+ * entry points let the whole path run at fp32-class accuracy (<= 1e-3 of the reference, measured
+ * ~1e-5) on the same tcgen05 GEMM: a fp32 operand is split into bf16 hi + lo parts laid out along
+ * the contraction axis, A as (hi | hi | lo) [order 0] and B as (hi | lo | hi) [order 1], so ONE
+ * b4cp_gemm_bf16 over K' = 3K accumulates hi*hi + hi*lo + lo*hi in fp32.
+ *   k_along_rows = 0: in [rows][ld_in] with `cols` = K valid columns -> out bf16 [rows][3*ld8(K)]
+ *                     (ld_out must equal 3*ld8(K); pad columns are zero);
+ *   k_along_rows = 1: in [K = rows][ld_in] with `cols` valid columns -> out bf16
+ *                     [3*ld8(K)][ld_out], ld_out a multiple of 8 >= cols (pad rows / columns zero).
+ * Either way the contraction length of the product becomes K' = 3*ld8(K).
+ */
+int b4cp_split_bf16x3(const float* in, long rows, int cols, long ld_in, void* out, long ld_out,
+                      int k_along_rows, int order, void* stream);
+/* fp32 masked self-attention (same contract as b4cp_attention_fwd/_bwd with fp32 buffers; exact
+ * division by sqrt(dh), expf; S <= 256 forward, backward while 4 head tiles fit shared memory) */
+int b4cp_attention_f32_fwd(const float* qkv, const int32_t* ids_first, int B, int S, int H, int dh,
+                           float* out, float* lse, void* stream);
+int b4cp_attention_f32_bwd(const float* qkv, const float* dout, const float* lse,
+                           const int32_t* ids_first, int B, int S, int H, int dh, float* dqkv,
+                           void* stream);
+/* column sums of a fp32 [T][ld] matrix (workspace: b4cp_colsum_workspace_bytes) */
+int b4cp_colsum_f32(const float* in, long T, int n, long ld, float* out, void* workspace,
+                    void* stream);
+
 /* ------------------------------------------------------------------ input embedding
  * Replaces Embedding gather x F, tf.concat, * sqrt(d_model), + pos_encoding[:, :S] and the
  * encoder's input Dropout: clickstream_transformer/transformer.py:376-398, :263.
@@ -124,7 +150,8 @@ int b4cp_attention_bwd(const void* qkv, const void* out, const void* dout, const
 
 /* y = LayerNormalization(eps=1e-6)(x + Dropout(r)): transformer.py:204-206, :209-211.
  * Backward returns dx (residual branch, fp32), dr (gradient of the Dense output r, bf16) and the
- * reduced dgamma, dbeta and dbias = column sums of dr.  d <= 256.
+ * reduced dgamma, dbeta and dbias = column sums of dr.  d <= 256.  dr_f32 (fp32 [T][d], optional)
+ * receives the same dr unrounded (fp32-class mode).
  */
 int b4cp_residual_ln_fwd(const float* x, const float* r, long T, int d, const float* gamma,
                          const float* beta, float dropout_rate, uint64_t seed, uint32_t site,
@@ -132,8 +159,8 @@ int b4cp_residual_ln_fwd(const float* x, const float* r, long T, int d, const fl
 long b4cp_residual_ln_bwd_workspace_bytes(int d);
 int b4cp_residual_ln_bwd(const float* dy, const float* x, const float* r, long T, int d,
                          const float* gamma, float dropout_rate, uint64_t seed, uint32_t site,
-                         float* dx, void* dr_bf16, long ld_bf16, float* dgamma, float* dbeta,
-                         float* dbias, void* workspace, void* stream);
+                         float* dx, void* dr_bf16, long ld_bf16, float* dr_f32, float* dgamma,
+                         float* dbeta, float* dbias, void* workspace, void* stream);
 
 /* bias gradients: out[c] = sum over rows of a bf16 [T][ld] matrix (deterministic two-stage) */
 long b4cp_colsum_workspace_bytes(long T, int n);
@@ -143,6 +170,12 @@ int b4cp_colsum_bf16(const void* in, long T, int n, long ld, float* out, void* w
 /* fills out[i] with 1/(1-rate) (kept) or 0 (dropped) for the n elements of a dropout site */
 int b4cp_dropout_mask(float* out, long n, float dropout_rate, uint64_t seed, uint32_t site,
                       void* stream);
+
+/* x[i] <- x[i] / (1-rate) (kept) or 0 (dropped), in place, with the bits of the same site: the
+ * gradient side of a dropout site when the consumer cannot recompute the mask itself (the
+ * data-parallel row exchange of table gradients gathers rows of OTHER ranks' tokens) */
+int b4cp_dropout_apply(float* x, long n, float dropout_rate, uint64_t seed, uint32_t site,
+                       void* stream);
 
 /* ------------------------------------------------------------------ output selection
  * clickstream_transformer/clickstream_transformer.py:260-297 (_gather_output_by_raw_value):
@@ -197,6 +230,11 @@ int b4cp_ce_loss_reduce(const float* lse, const float* tgt, const int32_t* label
 int b4cp_ce_rows_grad(const float* logits, long ld, long M, int V, const int32_t* labels,
                       const float* lse, const float* loss_stats, void* dz_bf16, long ld_dz,
                       float* probs, long ld_probs, void* stream);
+
+/* fp32-class mode: dz = (softmax - onehot) / loss_stats[1] written IN PLACE over the fp32 logits
+ * [M][ld] (columns V..ld-1 zeroed), rows with label -1 -> 0 */
+int b4cp_ce_rows_grad_f32(float* logits, long ld, long M, int V, const int32_t* labels,
+                          const float* lse, const float* loss_stats, void* stream);
 
 /* ------------------------------------------------------------------ Cloze loss, FUSED (tcgen05)
  * SoftMaxHead's Dense(V) + softmax + sparse categorical cross-entropy and its gradient without

@@ -669,6 +669,40 @@ def cloze_train_step(ids_list, labels, P, num_layers, num_heads, pe, dtype=np.fl
     return loss, G, extras
 
 
+def segment_binary_train_step(ids_list, y_true, P, num_layers, num_heads, pe, segment,
+                              pos_weight=None, dtype=np.float64):
+    """Forward + backward of the multi-variable click-path classifier: encoder
+    (transformer.py:376-402) -> rows of segment `segment` (clickstream_transformer.py:317-322)
+    -> BinaryClassificationHead (head.py:4-26) -> MaskedLoss(K.binary_crossentropy, pos_weight)
+    (losses.py:31-98), and what TF autodiff derives from it.  y_true: (B, segment length) padded
+    with LABEL_PAD.  Returns loss, grads dict (same keys as P), extras (probs)."""
+    F = len(ids_list)
+    x, caches = encoder_fwd(ids_list, P, num_layers, num_heads, pe, dtype)
+    starts, ends = segment_bounds(ids_list[0][0])
+    s0, s1 = int(starts[segment]), int(ends[segment])
+    seg = x[:, s0:s1, :]
+    layers = [(w.astype(dtype), b.astype(dtype)) for w, b in head_layers(P)]
+    w_out, b_out = P["head.out.w"].astype(dtype), P["head.out.b"].astype(dtype)
+    loss, dseg, lg, dWo, dbo = binary_head_loss_and_grads(seg, layers, w_out, b_out, y_true,
+                                                          pos_weight=pos_weight)
+    probs, _, _ = binary_head_fwd(seg, layers, w_out, b_out)
+    G = {"head.out.w": dWo, "head.out.b": dbo}
+    for i, (dw, db) in enumerate(lg):
+        G[f"head.{i}.w"], G[f"head.{i}.b"] = dw, db
+    dx = np.zeros_like(x)
+    dx[:, s0:s1, :] = dseg
+    for l in reversed(range(num_layers)):
+        c, p = caches[l]
+        dx, g = encoder_layer_bwd(dx, c, p)
+        for k, v in g.items():
+            G[f"enc.{l}.{k}"] = v
+    dims = [P[f"emb.{f}"].shape[1] for f in range(F)]
+    rows = [P[f"emb.{f}"].shape[0] for f in range(F)]
+    for f, g in enumerate(embed_bwd(dx, ids_list, dims, rows, dtype)):
+        G[f"emb.{f}"] = g
+    return loss, G, dict(probs=probs, enc_out=x)
+
+
 # ------------------------------------------------------------------ binary-task metrics
 def binary_metric_counts(y_true, y_pred, label_pad=-1.0):
     """Accumulators of clickstream_transformer/metrics.py as one vector:

@@ -24,7 +24,7 @@ KERNEL_TOL = 2e-2
 BF16_TOL = 6e-2
 
 
-def build_model(P, dims, L, H, dff, head_dims, V, dropout=0.0, rows2=20):
+def build_model(P, dims, L, H, dff, head_dims, V, dropout=0.0, rows2=20, precision="bf16"):
     import bert4clickpath_b200 as bc
     from bert4clickpath_b200.weights import to_store_layout
     feats = ["items", "events"][:len(dims)]
@@ -34,20 +34,28 @@ def build_model(P, dims, L, H, dff, head_dims, V, dropout=0.0, rows2=20):
         feature_vocabs=dict([("items", V)] + ([("events", rows2 - 11)] if len(dims) > 1 else [])),
         embedding_dims={f: d for f, d in zip(feats, dims)},
         head_unit=head, value_to_head=bc.INPUT_MASKING_TOKEN,
-        num_encoder_layers=L, num_attention_heads=H, dropout_rate=dropout, encoder_ff_dim=dff)
+        num_encoder_layers=L, num_attention_heads=H, dropout_rate=dropout, encoder_ff_dim=dff,
+        precision=precision)
     model.store.set_weights(to_store_layout({k: v for k, v in P.items()}))
     return model
 
 
-def rel_err(got, want, floor=0.0):
-    """Frobenius-norm error relative to the tensor's own RMS scale (or `floor` for tensors whose
-    true gradient is ~0, e.g. the key bias, to which softmax attention is invariant)."""
-    n = np.sqrt(got.size)
-    return (np.linalg.norm(got - want) / n) / max(np.linalg.norm(want) / n, floor, 1e-12)
+def rel_err(got, want, scale=None):
+    """Frobenius-norm error relative to the tensor's OWN norm.  `scale` replaces the denominator
+    for the one tensor family whose true gradient is identically zero - the key bias, to which
+    softmax attention is invariant - and is the query-bias gradient of the same layer."""
+    ref = want if scale is None else scale
+    return np.linalg.norm(got - want) / max(np.linalg.norm(ref), 1e-300)
 
 
 def grad_floor(G):
-    return 3e-2 * max(np.linalg.norm(v) / np.sqrt(v.size) for v in G.values())
+    """{key-bias name: the same layer's query-bias gradient}: the only floored tensors."""
+    return {k: G[k[:-2] + "bq"] for k in G if k.endswith(".bk")}
+
+
+def all_errs(got, want, G):
+    fl = grad_floor(G)
+    return {k: rel_err(got[k], want[k], fl.get(k)) for k in sorted(want)}
 
 
 @pytest.mark.parametrize("dims", [(8,), (8, 8)])
@@ -69,9 +77,9 @@ def test_cloze_forward_backward_matches_oracle(cuda_lib, dims):
     assert abs(s[0] / s[1] - loss) < 2e-2 * abs(loss)
     assert abs(s[0] / s[1] - eloss) < 1e-4 * abs(eloss)
     got = to_reference_layout(model.store.get_grads())
-    for k in sorted(G):
-        assert rel_err(got[k], EG[k], grad_floor(G)) < KERNEL_TOL, (k, rel_err(got[k], EG[k], grad_floor(G)))
-        assert rel_err(got[k], G[k], grad_floor(G)) < BF16_TOL, (k, rel_err(got[k], G[k], grad_floor(G)))
+    ek, eb = all_errs(got, EG, G), all_errs(got, G, G)
+    assert max(ek.values()) < KERNEL_TOL, max(ek.items(), key=lambda kv: kv[1])
+    assert max(eb.values()) < BF16_TOL, max(eb.items(), key=lambda kv: kv[1])
     # PAD rows of the item table get exactly zero gradient (dead compute)
     assert not np.abs(got["emb.0"][0]).any() or (ids_list[0] == 0).any()
 
@@ -132,17 +140,18 @@ def test_dropout_training_step_matches_oracle_with_exported_masks(cuda_lib):
     assert abs(s[0] / s[1] - loss) < 2e-2 * abs(loss)
     assert abs(s[0] / s[1] - eloss) < 1e-4 * abs(eloss)
     got = to_reference_layout(model.store.get_grads())
-    for k in sorted(G):
-        assert rel_err(got[k], EG[k], grad_floor(G)) < KERNEL_TOL, (k, rel_err(got[k], EG[k], grad_floor(G)))
-        assert rel_err(got[k], G[k], grad_floor(G)) < BF16_TOL, (k, rel_err(got[k], G[k], grad_floor(G)))
+    ek, eb = all_errs(got, EG, G), all_errs(got, G, G)
+    assert max(ek.values()) < KERNEL_TOL, max(ek.items(), key=lambda kv: kv[1])
+    assert max(eb.values()) < BF16_TOL, max(eb.items(), key=lambda kv: kv[1])
 
 
-def test_three_adam_steps_track_oracle(cuda_lib):
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+def test_three_adam_steps_track_oracle(cuda_lib, precision):
     import bert4clickpath_b200 as bc
     from bert4clickpath_b200.weights import to_reference_layout
     ids_list, labels, P, L, H, pe, _ = make_tiny_problem(dims=(8,), dff=12, head=(16, 8))
     V = P["head.out.w"].shape[1]
-    model = build_model(P, (8,), L, H, 12, (16, 8), V)
+    model = build_model(P, (8,), L, H, 12, (16, 8), V, precision=precision)
     model.compile(optimizer=bc.Adam(1e-3, 0.9, 0.999, 1e-9))
     Pm = {k: v.copy() for k, v in P.items()}
     M_ = {k: np.zeros_like(v) for k, v in P.items()}
@@ -155,15 +164,25 @@ def test_three_adam_steps_track_oracle(cuda_lib):
             Pm[k], M_[k], V_[k] = O.adam_step(Pm[k], G[k], M_[k], V_[k], t)
         losses.append((logs["loss"], loss))
     for got, want in losses:
-        assert abs(got - want) < 2e-2 * want
+        assert abs(got - want) < (1e-4 if precision == "fp32" else 2e-2) * want
     W = to_reference_layout(model.store.get_weights())
     for k in Pm:
-        # every weight moved by ~lr per step in the same direction as the oracle's
         moved = W[k] - P[k]
         want = Pm[k] - P[k]
-        big = np.abs(want) > 2e-3
-        if big.any():
-            assert (np.sign(moved[big]) == np.sign(want[big])).mean() > 0.97, k
+        if precision == "fp32":
+            # VALUES: three Keras-Adam updates of the oracle, weight by weight.  Adam divides by
+            # sqrt(v): entries whose gradient is itself rounding noise (|g| << the tensor's
+            # scale) move by +-lr in a direction no two implementations agree on, so the
+            # comparison is over the entries the oracle moved by a full-size step.
+            sure = np.abs(want) > 2.5e-3           # 3 steps of lr = 1e-3, consistent sign
+            if sure.any():
+                np.testing.assert_allclose(moved[sure], want[sure], rtol=2e-3, atol=2e-6, err_msg=k)
+            assert np.abs(moved - want).max() < 6.1e-3, k   # nothing moves further than 2 * 3 * lr
+        else:
+            # bf16 operands: every weight moved by ~lr per step in the oracle's direction
+            big = np.abs(want) > 2e-3
+            if big.any():
+                assert (np.sign(moved[big]) == np.sign(want[big])).mean() > 0.97, k
 
 
 @pytest.mark.parametrize("cfg", [
@@ -197,9 +216,8 @@ def test_kernels_match_bf16_emulation_on_c1_like_shapes(cuda_lib, cfg):
     eloss, EG, _ = cloze_train_step_bf16([batch["ids"].astype(np.int64)], batch["labels"], P, L, H, pe)
     assert abs(stats[0] / stats[1] - eloss) < 1e-4 * abs(eloss)
     got = to_reference_layout(model.store.get_grads())
-    floor = grad_floor(EG)
-    for k in sorted(EG):
-        assert rel_err(got[k], EG[k], floor) < KERNEL_TOL, (k, rel_err(got[k], EG[k], floor))
+    ek = all_errs(got, EG, EG)
+    assert max(ek.values()) < KERNEL_TOL, max(ek.items(), key=lambda kv: kv[1])
 
 
 # ------------------------------------------------------------------ committed golden vectors
@@ -236,18 +254,38 @@ def test_gpu_matches_committed_golden_cloze_step(cuda_lib, name, dims):
     lab = torch.from_numpy(z["labels"].astype(np.float32)).cuda()
     n_masked = int((z["labels"] >= 0).sum())
     if has_drop:
-        # the golden step used explicit masks; the forward-only comparison needs dropout off,
-        # so compare the un-dropped forward instead (dropout parity is covered above)
+        # the fixture's step used explicit dropout masks drawn by NumPy, which the device's
+        # counter-based masks cannot reproduce: on the fixture's WEIGHTS AND INPUTS compare (i) the
+        # un-dropped forward with the oracle's un-dropped forward, value by value, and (ii) a
+        # training step under the device's own exported masks with the oracle under those masks
         out = model.forward_ids(dev_ids, B, S, training=False, n_masked=n_masked)
         probs = out.materialize().cpu().numpy()
-        assert probs.shape == z["probs"].shape and np.isfinite(probs).all()
+        P64 = {k: v.astype(np.float64) for k, v in P.items()}
+        pe = O.positional_encoding(10000, sum(dims))
+        x, _ = O.encoder_fwd(ids_list, P64, L, H, pe, np.float64)
+        sel, _ = O.select_masked(ids_list[0], x)
+        want, _, _ = O.softmax_head_fwd(sel, O.head_layers(P64), P64["head.out.w"], P64["head.out.b"])
+        assert probs.shape == z["probs"].shape == want.shape
+        np.testing.assert_allclose(probs, want, rtol=5e-2, atol=1e-4)
+        dmodel = build_model(P, dims, L, H, 12, (16, 8), V, dropout=0.25, rows2=P["emb.1"].shape[0])
+        seed, d = 5, sum(dims)
+        mk = lambda st: ops.dropout_mask(B * S * d, 0.25, seed, st).cpu().numpy().reshape(B, S, d).astype(np.float64)
+        masks = {"in": mk(SITE_INPUT)}
+        for l in range(L):
+            masks[(l, 1)], masks[(l, 2)] = mk(site(l, 1)), mk(site(l, 2))
+        st = dmodel.cloze_forward_backward(dev_ids, lab, B, S, n_masked=n_masked, training=True,
+                                           seed=seed).cpu().numpy()
+        loss, G2, _ = O.cloze_train_step(ids_list, z["labels"], P64, L, H, pe, np.float64, masks)
+        assert abs(st[0] / st[1] - loss) < 2e-2 * abs(loss)
+        eb = all_errs(to_reference_layout(dmodel.store.get_grads()), G2, G2)
+        assert max(eb.values()) < BF16_TOL, max(eb.items(), key=lambda kv: kv[1])
         return
     stats = model.cloze_forward_backward(dev_ids, lab, B, S, n_masked=n_masked, training=False)
     s = stats.cpu().numpy()
     assert abs(s[0] / s[1] - float(z["loss"])) < 2e-2 * float(z["loss"])
     got = to_reference_layout(model.store.get_grads())
-    for k in sorted(G):
-        assert rel_err(got[k], G[k], grad_floor(G)) < BF16_TOL, (k, rel_err(got[k], G[k], grad_floor(G)))
+    eb = all_errs(got, G, G)
+    assert max(eb.values()) < BF16_TOL, max(eb.items(), key=lambda kv: kv[1])
     out = model.forward_ids(dev_ids, B, S, training=False, n_masked=n_masked)
     np.testing.assert_allclose(out.materialize().cpu().numpy(), z["probs"], rtol=5e-2, atol=1e-4)
 

@@ -318,3 +318,43 @@ def test_multilabel_head_backward_matches_torch_autograd(dims, pw):
     for (dw, db), (w, b) in zip(lg, tl):
         np.testing.assert_allclose(dw, w.grad.numpy(), rtol=1e-9, atol=1e-14)
         np.testing.assert_allclose(db, b.grad.numpy(), rtol=1e-9, atol=1e-14)
+
+
+@pytest.mark.parametrize("segment,pw", [(0, None), (2, 3.0)])
+def test_segment_binary_train_step_matches_finite_differences(segment, pw):
+    """The C3 composition (encoder -> segment slice -> sigmoid head -> masked BCE) that the
+    real-configuration GPU parity test is checked against: central differences in float64."""
+    rng = np.random.default_rng(3)
+    B, L1, L2, V = 4, 6, 3, 30
+    P = O.init_params(rng, [V + 11, 9 + 11], (6, 2), 1, 10, (8,), 1, head_kind="binary",
+                      dtype=np.float64)
+    for k in P:
+        if P[k].ndim == 1:
+            P[k] = P[k] + rng.normal(scale=0.1, size=P[k].shape)
+    a = rng.integers(10, V + 10, size=(B, L1)); a[1, 4:] = 0
+    b = rng.integers(10, V + 10, size=(B, L2)); b[2, 2:] = 0
+    ea = np.where(a == 0, 0, rng.integers(10, 19, size=a.shape))
+    eb = np.where(b == 0, 0, rng.integers(10, 19, size=b.shape))
+    ids = [O.chain_sequences([a, b]), O.chain_sequences([ea, eb])]
+    starts, ends = O.segment_bounds(ids[0][0])
+    Ls = int(ends[segment] - starts[segment])
+    y = rng.integers(0, 2, size=(B, Ls)).astype(np.float64)
+    if segment == 2:
+        y[b == 0] = -1.0
+    pe = O.positional_encoding(10000, 8)
+    f = lambda Q: O.segment_binary_train_step(ids, y, Q, 1, 2, pe, segment, pos_weight=pw)[0]
+    loss, G, ex = O.segment_binary_train_step(ids, y, P, 1, 2, pe, segment, pos_weight=pw)
+    assert set(G) == set(P) and ex["probs"].shape == (B, Ls)
+    for k in ["head.out.w", "head.0.w", "head.0.b", "enc.0.wq", "enc.0.wv", "enc.0.w2",
+              "enc.0.ln1_g", "enc.0.bo", "emb.1"]:
+        flat = np.flatnonzero(np.abs(G[k]) > 1e-9)
+        for idx in rng.choice(flat, size=min(3, len(flat)), replace=False):
+            i = np.unravel_index(idx, P[k].shape)
+            Pp = {n: v.copy() for n, v in P.items()}; Pm = {n: v.copy() for n, v in P.items()}
+            h = 1e-5
+            Pp[k][i] += h; Pm[k][i] -= h
+            num = (f(Pp) - f(Pm)) / (2 * h)
+            # tables are embedded in float32 (reference rounding): perturbations below fp32
+            # resolution would vanish, so the table check uses a looser bar
+            tol = 2e-2 if k.startswith("emb.") else 1e-5
+            assert abs(num - G[k][i]) < tol * max(abs(G[k][i]), 1e-6) + 1e-9, (k, i, num, G[k][i])

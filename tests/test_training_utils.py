@@ -221,6 +221,19 @@ def test_reference_checkpoint_key_map_round_trips():
         np.testing.assert_array_equal(v, ref[k])
     with pytest.raises(KeyError):
         W.tf_checkpoint_key("decoder.0.w")
+    # the store registers tables by POSITION (emb.0, emb.1); the reference's checkpoint keys them
+    # by FEATURE NAME: with the model's feature list the round trip lands on the store's names
+    feats = ["items", "events"]
+    pos = {("emb.0" if k == "emb.items" else "emb.1" if k == "emb.events" else k): v
+           for k, v in store.items()}
+    tf2 = W.export_reference_variables(pos, feats)
+    assert set(tf2) == keys                          # same feature-named keys as above
+    back2 = W.import_reference_variables(tf_vars, feats)   # a REAL reference checkpoint's keys
+    assert set(back2) == set(pos)
+    for k in pos:
+        np.testing.assert_array_equal(back2[k], pos[k])
+    with pytest.raises(KeyError):
+        W.import_reference_variables({"transformer/embedding_layers/basket/embeddings" + sfx: np.zeros((2, 2))}, feats)
 
 
 def _fit_worker(rank, world, port, q):

@@ -1,0 +1,176 @@
+"""Parity on BASELINE.json's ACTUAL configurations against the float64 oracle, with the measured
+per-tensor errors written to gpurun_out/parity_*.json (DESIGN.md section 5 quotes them):
+
+  C1 as shipped  V 54,293, d 64, 2 layers, 2 heads, dff 100, head [1024,512,256,128], S 52, B 64
+                 (examples/BERT4Rec/source/main.py:207-211, :262-263)
+  C3             items 500,000 + actions 50, d = 112 + 16, S 103, 2 layers, 4 heads,
+                 BinaryClassificationHead([256, 64]) on segment 0, pos_weight
+  C4-shaped      d 256, 4 layers, 4 heads of 64, S 202, head [] -> V (V reduced to 20,000 so the
+                 float64 oracle finishes in seconds; the V = 1M shape is covered by the
+                 size-independent tests in test_zz_fullsize_gpu.py)
+
+Two bars per configuration:
+  * precision="fp32" (the parity mode: bf16 x 3 split products on the tcgen05 GEMM, fp32 attention,
+    fp32 logits): loss, logits and EVERY gradient tensor within FP32_TOL = 1e-3 of the oracle -
+    north_star's bar - in both the max-norm and the Frobenius norm, relative to the tensor's own
+    scale.  The only floor is on the key bias, whose true gradient is identically zero (softmax is
+    invariant to a per-query constant): its error is measured against the query-bias gradient.
+  * precision="bf16" (the fast path): the stated bf16 tolerances below, per norm.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import clickpath_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL = 1e-3            # north_star: losses, logits, gradients within 1e-3 relative in fp32
+BF16_LOSS_TOL = 2e-3       # fast path, measured <= 6e-4 on these configs
+BF16_FRO_TOL = 3e-2        # per-tensor Frobenius, measured <= 1.6e-2
+BF16_MAX_TOL = 6e-2        # per-tensor max-norm, measured <= 3.5e-2
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def tensor_errors(got, want, G):
+    """{name: (max-norm rel, Frobenius rel)}; key biases are measured against the query bias."""
+    out = {}
+    for k in sorted(want):
+        g, w = got[k].astype(np.float64).reshape(want[k].shape), want[k]
+        ref = G[k[:-2] + "bq"] if k.endswith(".bk") else w
+        out[k] = (float(np.abs(g - w).max() / max(np.abs(ref).max(), 1e-300)),
+                  float(np.linalg.norm(g - w) / max(np.linalg.norm(ref), 1e-300)))
+    return out
+
+
+def report(name, payload):
+    d = os.path.join(ROOT, "gpurun_out")
+    try:
+        os.makedirs(d, exist_ok=True)
+        with open(os.path.join(d, f"parity_{name}.json"), "w") as f:
+            json.dump(payload, f, indent=1, sort_keys=True)
+    except OSError:
+        pass
+
+
+def check(name, precision, loss_err, errs, extra=None):
+    worst_max = max(errs.items(), key=lambda kv: kv[1][0])
+    worst_fro = max(errs.items(), key=lambda kv: kv[1][1])
+    report(f"{name}_{precision}", dict(loss_rel_err=loss_err, worst_max=worst_max, worst_fro=worst_fro,
+                                       per_tensor={k: dict(max=v[0], fro=v[1]) for k, v in errs.items()},
+                                       **(extra or {})))
+    if precision == "fp32":
+        assert loss_err < FP32_TOL, loss_err
+        assert worst_max[1][0] < FP32_TOL, worst_max
+        assert worst_fro[1][1] < FP32_TOL, worst_fro
+    else:
+        assert loss_err < BF16_LOSS_TOL, loss_err
+        assert worst_max[1][0] < BF16_MAX_TOL, worst_max
+        assert worst_fro[1][1] < BF16_FRO_TOL, worst_fro
+
+
+def cloze_case(name, precision, V, d, L, H, dff, hd, B, max_len, mp, max_masked, lengths):
+    import bert4clickpath_b200 as bc
+    from bert4clickpath_b200.synthetic import make_cloze_batch
+    from bert4clickpath_b200.weights import to_reference_layout
+    head = bc.SoftMaxHead(dense_layer_dims=hd, output_vocab_size=V)
+    model = bc.ClickstreamTransformer(
+        sequential_input_config={"items": ["asin"]}, feature_vocabs={"items": V},
+        embedding_dims={"items": d}, head_unit=head, value_to_head=bc.INPUT_MASKING_TOKEN,
+        num_encoder_layers=L, num_attention_heads=H, dropout_rate=0.0, encoder_ff_dim=dff,
+        seed=3, precision=precision)
+    # biases / LayerNorm parameters off their zero / one initial values, so that every term of
+    # the backward is exercised
+    rng = np.random.default_rng(5)
+    w0 = model.store.get_weights()
+    bump = {k: (v + rng.normal(scale=0.02, size=v.shape)).astype(np.float32) for k, v in w0.items()
+            if v.ndim == 1}
+    model.store.set_weights(bump)
+    batch = make_cloze_batch(np.random.default_rng(0), B, V, max_len=max_len, mode="train",
+                             masked_percentage=mp, max_masked=max_masked, lengths=lengths)
+    ids = torch.from_numpy(batch["ids"]).cuda().view(-1)
+    labels = torch.from_numpy(batch["labels"]).cuda()
+    Bq, S = batch["ids"].shape
+    stats = model.cloze_forward_backward([ids], labels, Bq, S, n_masked=batch["n_masked"],
+                                         training=False).cpu().numpy()
+    got = to_reference_layout(model.store.get_grads())
+    P = {k: v.astype(np.float64) for k, v in to_reference_layout(model.store.get_weights()).items()}
+    pe = O.positional_encoding(10000, d)
+    loss, G, ex = O.cloze_train_step([batch["ids"].astype(np.int64)], batch["labels"], P, L, H, pe,
+                                     np.float64)
+    assert stats[1] == ex["n_valid"] == batch["n_masked"]
+    loss_err = abs(stats[0] / stats[1] - loss) / abs(loss)
+    errs = tensor_errors(got, G, G)
+    # logits of the [MASK] rows (compact (b, s) order == the oracle's valid rows in order)
+    out = model.forward_ids([ids], Bq, S, training=False, n_masked=batch["n_masked"])
+    z = out.head.vocab.logits(out.ab, out.M)[:, :V].cpu().numpy().astype(np.float64)
+    want_z = ex["logits"][np.asarray(batch["labels"]).reshape(-1) >= 0]
+    errs["logits"] = (float(np.abs(z - want_z).max() / np.abs(want_z).max()),
+                      float(np.linalg.norm(z - want_z) / np.linalg.norm(want_z)))
+    check(name, precision, loss_err, errs, dict(S=int(S), B=int(Bq), rows=int(batch["n_masked"]),
+                                               loss=float(loss)))
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_c1_as_shipped_matches_float64_oracle(cuda_lib, precision):
+    cloze_case("c1", precision, V=54293, d=64, L=2, H=2, dff=100, hd=[1024, 512, 256, 128], B=64,
+               max_len=50, mp=0.15, max_masked=10, lengths="dense")
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_c1_reference_masking_ragged_sessions(cuda_lib, precision):
+    """The reference's own masking defaults (40 %, at most 10; cloze_constants.py:1-2) on
+    Beauty-shaped ragged sessions: interior pads, rows with different mask counts."""
+    cloze_case("c1_ragged", precision, V=54293, d=64, L=2, H=2, dff=100, hd=[1024, 512, 256, 128],
+               B=48, max_len=50, mp=0.4, max_masked=10, lengths="beauty")
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_c4_shaped_matches_float64_oracle(cuda_lib, precision):
+    cloze_case("c4", precision, V=20000, d=256, L=4, H=4, dff=100, hd=[], B=8, max_len=200,
+               mp=0.15, max_masked=30, lengths="dense")
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_c3_multivariable_binary_head_matches_float64_oracle(cuda_lib, precision):
+    import bert4clickpath_b200 as bc
+    from bert4clickpath_b200.synthetic import zipf_items
+    from bert4clickpath_b200.weights import to_reference_layout
+    Vi, Va, B, Lx, pw = 500_000, 50, 16, 100, 3.0
+    rng = np.random.default_rng(9)
+    items = zipf_items(rng, (B, Lx), Vi)
+    acts = zipf_items(rng, (B, Lx), Va, s=1.0)
+    for b in range(B):                      # ragged sessions: interior pads in both features
+        n = int(rng.integers(5, Lx + 1))
+        items[b, n:] = 0
+        acts[b, n:] = 0
+    head = bc.BinaryClassificationHead(dense_layer_dims=[256, 64])
+    model = bc.ClickstreamTransformer(
+        sequential_input_config={"items": ["s_items"], "events": ["s_ev"]},
+        feature_vocabs={"items": Vi, "events": Va}, embedding_dims={"items": 112, "events": 16},
+        head_unit=head, segment_to_head=0, num_encoder_layers=2, num_attention_heads=4,
+        dropout_rate=0.0, seed=4, precision=precision)
+    w0 = model.store.get_weights()
+    bump = {k: (v + rng.normal(scale=0.02, size=v.shape)).astype(np.float32) for k, v in w0.items()
+            if v.ndim == 1}
+    model.store.set_weights(bump)
+    ids_list, Bq, S, starts, ends = model.prepare_inputs({"s_items": items, "s_ev": acts})
+    assert (Bq, S) == (B, Lx + 3)
+    y = rng.integers(0, 2, size=(B, 1)).astype(np.float32)
+    stats = model.binary_forward_backward(ids_list, torch.from_numpy(y).cuda(), B, S, (starts, ends),
+                                          pos_weight=pw, training=False).cpu().numpy()
+    got = to_reference_layout(model.store.get_grads())
+    probs = model._last_probs.cpu().numpy().astype(np.float64)
+    P = {k: v.astype(np.float64) for k, v in to_reference_layout(model.store.get_weights()).items()}
+    pe = O.positional_encoding(10000, 128)
+    ids64 = [t.view(B, S).cpu().numpy().astype(np.int64) for t in ids_list]
+    loss, G, ex = O.segment_binary_train_step(ids64, y, P, 2, 4, pe, 0, pos_weight=pw)
+    got_loss = stats[0] / stats[1] / ((pw + 1.0) / 2)
+    errs = tensor_errors(got, G, G)
+    errs["probs"] = (float(np.abs(probs - ex["probs"]).max() / np.abs(ex["probs"]).max()),
+                     float(np.linalg.norm(probs - ex["probs"]) / np.linalg.norm(ex["probs"])))
+    check("c3", precision, abs(got_loss - loss) / abs(loss), errs, dict(S=int(S), B=B, loss=float(loss)))
