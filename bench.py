@@ -18,6 +18,12 @@ import sys
 import threading
 import time
 
+if "reference" in sys.argv:
+    # the reference arm runs the CPU restatement on ALL host cores of the box; torchrun pins
+    # OMP_NUM_THREADS=1 for every rank it spawns, which must not reach the BLAS of rank 0
+    for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_v] = str(os.cpu_count() or 1)
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -35,6 +41,15 @@ def peaks():
         return dict(bf16_burst=p["bf16_tflops"], bf16_sustained=p["bf16_tflops_sustained"],
                     hbm=p["hbm_gbs"], source="measured")
     return dict(bf16_burst=1590.0, bf16_sustained=1400.0, hbm=6650.0, source="fallback")
+
+
+def pick_peak(pk, region_seconds):
+    """Tensor-pipe denominator for a kernel timed over `region_seconds` of continuous work:
+    MEASURED_PEAKS' burst figure (clocks still at maximum) for short regions, the sustained one
+    (taken at the power-capped clock) for regions of 2 s and more."""
+    if region_seconds >= 2.0:
+        return pk["bf16_sustained"], pk["source"] + " (sustained: region >= 2 s)"
+    return pk["bf16_burst"], pk["source"] + f" (burst: {region_seconds * 1e3:.0f} ms region)"
 
 
 class ClockSampler:
@@ -178,6 +193,11 @@ def blas_threads():
 def run_reference(args, rank, world):
     if rank != 0:
         return
+    try:    # BLAS pools sized at import time (a launcher's OMP_NUM_THREADS=1) are raised here
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=os.cpu_count() or 1)
+    except Exception:
+        pass
     B = args.cpu_batch
     seqs, n, dt = time_cpu_reference(B, args.steps, min(args.warmup, 1))
     cores = blas_threads()
@@ -203,16 +223,31 @@ def workload_name(B):
 
 
 def finish(world):
-    """Flush and exit 0 without interpreter teardown (every rank calls this exactly once)."""
+    """Leave through the NORMAL interpreter exit (exit hooks run: the driver's record of the
+    native libraries this process loaded is one of them).  Everything that could block a
+    destructor is torn down here, explicitly and while every rank is still alive: captured graphs
+    (they hold NCCL kernels) were dropped by the caller, the device is idle, the process group is
+    destroyed after a last barrier.  A detached killer is the last resort against a hang in a
+    C++ static destructor: it never fires on a healthy exit."""
+    import atexit
     sys.stdout.flush()
     sys.stderr.flush()
+    import torch
+    torch.cuda.synchronize()
     if world > 1:
-        import torch
         import torch.distributed as dist
-        torch.cuda.synchronize()
         dist.barrier()
         torch.cuda.synchronize()
-    os._exit(0)
+        dist.destroy_process_group()
+    try:
+        subprocess.Popen(["sh", "-c", f"sleep 120; kill -9 {os.getpid()} 2>/dev/null"],
+                         stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL,
+                         start_new_session=True)
+    except Exception:
+        pass
+    atexit._run_exitfuncs()     # run the exit hooks now, with the runtime fully alive ...
+    sys.stdout.flush()
+    sys.exit(0)                 # ... and still leave the normal way
 
 
 def arm_watchdog(seconds):
@@ -271,15 +306,15 @@ def c4_vocab_stage(pk, iters=6):
         t += [ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]), ev[2].elapsed_time(ev[3])]
     t /= iters
     mhv = float(M) * h * V
-    peak = pk["bf16_sustained"]
+    peak, peak_src = pick_peak(pk, float(t.sum()) * iters * 1e-3)
 
     def line(ms, flops):
         a = flops / (ms * 1e-3) / 1e12
         return {"ms": float(ms), "achieved": a, "frac": a / peak, "algorithmic_flops": flops}
 
     out = {"workload": f"C4 Cloze output stage: V={V}, h={h}, M={M} [MASK] rows (256 seqs x 29)",
-           "bound": "tensor", "peak": peak, "unit": "TFLOP/s",
-           "peak_source": pk["source"] + " (sustained)",
+           "bound": "tensor", "peak": peak, "unit": "TFLOP/s", "peak_source": peak_src,
+           "frac_of_sustained_peak": 6.0 * mhv / (float(t.sum()) * 1e-3) / 1e12 / pk["bf16_sustained"],
            "vocab_ce_fwd_ts_kernel": line(t[0], 4.0 * mhv),
            "vocab_ce_bwd_ts_kernel": line(t[2], 2.0 * mhv),
            "stage_fwd_dx_bwd": line(float(t.sum()), 6.0 * mhv),
@@ -294,11 +329,17 @@ def c4_vocab_stage(pk, iters=6):
 
 
 # ------------------------------------------------------------------ C5 next-item top-k (kernel leg)
-def c5_topk(pk, B=4096, iters=5):
-    """top-100 over a 1,000,000-item catalogue from 256-wide hidden states (scoring
-    + exact top-k only; the encoder is the C4 one).  Path = what `VocabOutputEngine.topk` runs
-    above 262,144 entries: logits materialised for 2,048 rows at a time (tcgen05 GEMM, fp32) + the
-    single-pass streaming top-k.  HBM-bound: every score is written once and read once."""
+def c5_topk(pk, batches=(1, 16, 256, 1024, 4096, 16384), headline=4096):
+    """SURVEY.md C5 / BASELINE config 5: top-100 over a 1,000,000-item catalogue from 256-wide
+    hidden states, batch sweep 1..16k sessions, with the recall@k / NDCG@k counters fused into the
+    timed region (examples/BERT4Rec/source/utils.py:137-259).  Path = `VocabOutputEngine.topk`'s
+    default above 262,144 entries: logits for 2,048 rows at a time (tcgen05 GEMM, fp32) + the
+    single-pass streaming top-k, then `b4cp_rank_metrics`.
+
+    Roofline per SURVEY.md 8(d): below ~214 rows per pass of W the batch is HBM-bound with
+    ALGORITHMIC bytes V*h*2 (bf16 W read once) + B*h*2 + B*k*4; above it the bound is the tensor
+    pipe with 2*B*h*V flops.  The fp32 scores this path writes and re-reads (2*B*V*4 bytes) are
+    its own traffic, reported as `traffic_bytes`, never as algorithmic work."""
     import torch
     from bert4clickpath_b200 import ops
     V, h, k, RC = 1_000_000, 256, 100, 2048
@@ -306,41 +347,175 @@ def c5_topk(pk, B=4096, iters=5):
     wb = torch.zeros(h, ops.ld8(V), device="cuda", dtype=torch.bfloat16)
     wb[:, :V] = (torch.randn(h, V, device="cuda", generator=g) * 0.05).to(torch.bfloat16)
     bias = torch.zeros(V, device="cuda")
-    xb = (torch.randn(B, h, device="cuda", generator=g) * 0.5).to(torch.bfloat16)
-    ids = torch.empty(B, k, dtype=torch.int32, device="cuda")
+    Bmax = max(batches)
+    xb_all = (torch.randn(Bmax, h, device="cuda", generator=g) * 0.5).to(torch.bfloat16)
+    labels_all = torch.randint(0, V, (Bmax,), device="cuda", dtype=torch.int32, generator=g)
+    ids_all = torch.empty(Bmax, k, dtype=torch.int32, device="cuda")
     z = torch.empty(RC, ops.ld8(V), device="cuda")
+    counters = torch.zeros(3, device="cuda")
+    sustained = pk["bf16_sustained"]
 
-    def run():
+    def run(B):
         for a in range(0, B, RC):
             rows = min(RC, B - a)
-            ops.gemm(xb[a:a + rows], 0, wb, 1, rows, V, h, bias=bias, out_f32=z[:rows])
-            ops.topk_rows(z[:rows], V, k, out_ids=ids[a:a + rows])
+            ops.gemm(xb_all[a:a + rows], 0, wb, 1, rows, V, h, bias=bias, out_f32=z[:rows])
+            ops.topk_rows(z[:rows], V, k, out_ids=ids_all[a:a + rows])
+        ops.rank_metrics(ids_all[:B], k, labels_all[:B], counters)
 
-    for _ in range(2):
-        run()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(iters):
-        run()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / iters
-    nbytes = 2.0 * B * V * 4 + V * h * 2 * (B / RC) + B * k * 4
-    out = {"workload": f"C5 next-item top-{k}: V={V}, h={h}, {B} queries per call (scoring + top-k)",
-           "value": B / (ms * 1e-3), "unit": "queries/s", "ms_per_call": ms, "bound": "hbm",
-           "achieved": nbytes / (ms * 1e-3) / 1e9, "peak": pk["hbm"], "roofline_unit": "GB/s",
-           "frac": nbytes / (ms * 1e-3) / 1e9 / pk["hbm"],
-           "algorithmic_bytes": nbytes,
-           "note": "bytes = scores written once + read once (fp32) + W per 2048-row range + ids; the "
-                   "fused alternative b4cp_score_topk (scores never in HBM) measures 0.41M queries/s "
-                   "at this shape"}
+    sweep = []
+    for B in batches:
+        iters = 3 if B >= 4096 else 10
+        for _ in range(2):
+            run(B)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            run(B)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / iters
+        alg_bytes = float(V) * h * 2 + B * h * 2 + B * k * 4
+        alg_flops = 2.0 * B * h * V
+        # regime by which bound takes longer at the peaks
+        t_hbm, t_tc = alg_bytes / (pk["hbm"] * 1e9), alg_flops / (sustained * 1e12)
+        if t_hbm >= t_tc:
+            ach = alg_bytes / (ms * 1e-3) / 1e9
+            roof = {"bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s",
+                    "frac": ach / pk["hbm"], "algorithmic_bytes": alg_bytes}
+        else:
+            ach = alg_flops / (ms * 1e-3) / 1e12
+            roof = {"bound": "tensor", "achieved": ach, "peak": sustained, "unit": "TFLOP/s",
+                    "frac": ach / sustained, "algorithmic_flops": alg_flops}
+        sweep.append({"batch": B, "queries_per_sec": B / (ms * 1e-3), "ms_per_call": ms,
+                      "roofline": roof,
+                      "traffic_bytes": 2.0 * B * V * 4 + float(V) * h * 2 * -(-B // RC) + B * k * 4})
+    c = counters.cpu().numpy()
+    head = next(r for r in sweep if r["batch"] == headline)
+    out = {"workload": f"C5 next-item top-{k} + recall/NDCG counters: V={V}, h={h}, batch sweep "
+                       f"{list(batches)} (scoring + exact top-k + b4cp_rank_metrics)",
+           "value": head["queries_per_sec"], "unit": "queries/s", "batch": headline,
+           "ms_per_call": head["ms_per_call"], "roofline": head["roofline"],
+           "frac": head["roofline"]["frac"], "sweep": sweep,
+           "recall_at_k": float(c[0] / max(c[2], 1)), "ndcg_at_k": float(c[1] / max(c[2], 1)),
+           "note": "roofline per SURVEY 8(d): algorithmic bytes / flops only (W once, X, ids); the "
+                   "materialised fp32 scores are this path's own traffic (traffic_bytes); labels are "
+                   "random, so recall/NDCG ~ k/V"}
     del wb, z
     torch.cuda.empty_cache()
     return out
 
 
 # ------------------------------------------------------------------------------------- ours
+C4 = dict(vocab=1_000_000, max_len=200, d_model=256, layers=4, heads=4, dff=1024, head_dims=[],
+          mask_rate=0.15, max_masked=30, dropout=0.1, batch=256)
+
+
+def c4_train_leg(args, rank, world):
+    """BASELINE config 4: scaled BERT4Rec - 1M-item vocabulary, d 256, S 202,
+    4 layers, 4 heads, head [] -> V, 29 masks / sequence, 256 sequences per GPU - as a full
+    training step at every N.  N = 1: replicated output layer.  N > 1: the output kernel is
+    sharded V/N per GPU (vocabulary-parallel softmax-CE: all-gather of the hidden rows, per-shard
+    fused kernels, lse / target merge, reduce-scatter of dX), the encoder is data-parallel, and
+    the 1 GB item-table gradient is never all-reduced: ranks exchange (ids, dX rows) and run the
+    same segment sum (EncoderEngine.plan_table_exchange).  Followed by the C5 sharded top-k merge
+    (per-shard fused scoring + top-100, all-to-all of candidates, exact merge)."""
+    import torch
+    import torch.distributed as dist
+    import bert4clickpath_b200 as bc
+    from bert4clickpath_b200 import ops
+    from bert4clickpath_b200.synthetic import make_cloze_batch
+    from bert4clickpath_b200.training import ClozeTrainStep
+    c = C4
+    V, B = c["vocab"], c["batch"]
+    head = bc.SoftMaxHead(dense_layer_dims=c["head_dims"], output_vocab_size=V,
+                          vocab_parallel=world > 1)
+    model = bc.ClickstreamTransformer(
+        sequential_input_config={"items": ["asin"]}, feature_vocabs={"items": V},
+        embedding_dims={"items": c["d_model"]}, head_unit=head, value_to_head=bc.INPUT_MASKING_TOKEN,
+        num_encoder_layers=c["layers"], num_attention_heads=c["heads"], dropout_rate=c["dropout"],
+        encoder_ff_dim=c["dff"], seed=0)
+    rng = np.random.default_rng(4321 + rank)
+    host = [make_cloze_batch(rng, B, V, c["max_len"], "train", c["mask_rate"], c["max_masked"])
+            for _ in range(2)]
+    M = host[0]["n_masked"]
+    assert all(b["n_masked"] == M for b in host)
+    trainer = ClozeTrainStep(model, bc.Adam(1e-3, 0.9, 0.999, 1e-9), use_graph=not args.no_graph,
+                             row_capacity=M)
+    dev = [trainer.to_device(b) for b in host]
+    S = host[0]["ids"].shape[1]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+
+    for i in range(ClozeTrainStep.GRAPH_WARMUP_STEPS + 3):
+        trainer.step_device(dev[i % 2])
+    barrier()
+    n = max(5, args.steps // 2)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(n):
+        stats = trainer.step_device(dev[i % 2])
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1)) / n
+    st = stats.cpu().numpy()
+    plan, _ = model.transformer.engine.plan_table_exchange(B * S, None)
+    out = {"workload": f"C4 scaled BERT4Rec Cloze train step: V_out={V}, S={S}, d={c['d_model']}, "
+                       f"{c['layers']} layers, {c['heads']} heads, dff={c['dff']}, head [] -> V, "
+                       f"{M // B} masks/seq, per-GPU batch {B}, dropout {c['dropout']}",
+           "metric": "c4_cloze_train_seqs_per_sec", "value": world * B / (ms * 1e-3), "unit": "seqs/s",
+           "ms_per_step": ms, "steps": n, "n_gpus": world, "scaling": "weak",
+           "parallelism": (f"dp{world} encoder + vocabulary-parallel output layer (V/{world} = "
+                           f"{head.vocab.V} entries per GPU); item-table gradient by "
+                           f"{'row exchange' if plan[0] else 'dense all-reduce'}") if world > 1
+                          else "single GPU, replicated output layer",
+           "masked_rows_per_gpu": M, "loss": float(st[0] / max(st[1], 1.0)),
+           "hbm_gb_allocated": torch.cuda.max_memory_allocated() / 1e9}
+    # ---- C5: next-item top-100 over the (sharded) 1M catalogue, EVAL masking, per-GPU batch 1024
+    QB, K_TOP = 1024, 100
+    ev = make_cloze_batch(rng, QB, V, c["max_len"], "eval")
+    ids_d = torch.from_numpy(ev["ids"]).cuda().view(-1)
+    lab_d = torch.from_numpy(ev["labels"]).cuda()
+    counters = torch.zeros(3, device="cuda")
+
+    def query():
+        top, _ = model.topk_ids([ids_d], QB, ev["ids"].shape[1], K_TOP, n_masked=QB)
+        labels_c, _ = ops.compact_labels(lab_d, QB)
+        ops.rank_metrics(top, K_TOP, labels_c, counters)
+
+    for _ in range(2):
+        query()
+    barrier()
+    nq = 5
+    e0.record()
+    for _ in range(nq):
+        query()
+    e1.record()
+    barrier()
+    qms = max_over_ranks(e0.elapsed_time(e1)) / nq
+    out["c5_topk"] = {"metric": "c5_next_item_topk_queries_per_sec",
+                      "value": world * QB / (qms * 1e-3), "unit": "queries/s", "k": K_TOP,
+                      "queries_per_step_per_gpu": QB, "ms_per_step": qms,
+                      "includes": "C4 encoder forward + " + (
+                          "per-shard fused scoring/top-k + all-to-all candidate merge" if world > 1
+                          else "scoring + streaming top-k") + " + recall/NDCG counters"}
+    trainer._graphs.clear()
+    del trainer, model, head, dev
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -349,8 +524,9 @@ def run_ours(args, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     import bert4clickpath_b200 as bc
     from bert4clickpath_b200 import _lib, ops
-    from bert4clickpath_b200.synthetic import make_cloze_batch
-    from bert4clickpath_b200.training import ClozeTrainStep
+    from bert4clickpath_b200.constants import CLS, LABEL_PAD, MASK_ID, NUM_RESERVED_TOKENS, SEP
+    from bert4clickpath_b200.synthetic import make_cloze_batch, zipf_items
+    from bert4clickpath_b200.training import ClozeTrainStep, DeviceBatch
     _lib.call("b4cp_device_check")
     V, d, B = CFG["vocab"], CFG["d_model"], args.batch
     head = bc.SoftMaxHead(dense_layer_dims=CFG["head_dims"], output_vocab_size=V)
@@ -382,6 +558,18 @@ def run_ours(args, rank, world, local_rank):
             return float(t.item())
         return ms
 
+    def timed(fn, n):
+        """n calls of fn(i), bracketed by barrier + synchronize, CUDA events, max over ranks."""
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        a.record()
+        r = None
+        for i in range(n):
+            r = fn(i)
+        b.record()
+        barrier()
+        return max_over_ranks(a.elapsed_time(b)), r
+
     # ---- device-resident timing (the step is one CUDA graph replay unless --no-graph; the first
     # ClozeTrainStep.GRAPH_WARMUP_STEPS + 1 calls run eagerly / capture, so warm up past them)
     for i in range(max(args.warmup, ClozeTrainStep.GRAPH_WARMUP_STEPS + 2)):
@@ -390,16 +578,22 @@ def run_ours(args, rank, world, local_rank):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for i in range(args.steps):
-        stats = trainer.step_device(dev[i % n_ring])
-    e1.record()
-    barrier()
-    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    ms_total, stats = timed(lambda i: trainer.step_device(dev[i % n_ring]), args.steps)
     clocks = sampler.stop() if rank == 0 else None
     loss_stats = stats.cpu().numpy()
+
+    # ---- the same step held for >= --sustain-seconds (power-capped clocks): the number that
+    # belongs next to MEASURED_PEAKS' SUSTAINED tensor peak
+    sustained = None
+    if args.sustain_seconds > 0:
+        n_s = max(args.steps, int(args.sustain_seconds * 1e3 / (ms_total / args.steps)) + 1)
+        s_sampler = ClockSampler(local_rank)
+        if rank == 0:
+            s_sampler.start()
+        ms_s, _ = timed(lambda i: trainer.step_device(dev[i % n_ring]), n_s)
+        s_clocks = s_sampler.stop() if rank == 0 else None
+        sustained = {"value": world * B * n_s / (ms_s * 1e-3), "unit": "seqs/s", "steps": n_s,
+                     "seconds": ms_s * 1e-3, "ms_per_step": ms_s / n_s, "clocks": s_clocks}
 
     # ---- per-kernel timing and launch count: the same step launched eagerly with CUDA-event
     # brackets around the vocabulary-stage kernels (events cannot be read back from a graph)
@@ -410,30 +604,103 @@ def run_ours(args, rank, world, local_rank):
     ops.TIMER.reset()
     ops.TIMER.enabled = True
     launches0 = _lib.lib().b4cp_launch_count()
-    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    k0.record()
-    for i in range(n_kt):
-        trainer.step_device(dev[i % n_ring])
-    k1.record()
-    barrier()
+    head_start = int(8e-3 * 1.9e9)   # cycles
+
+    def eager_step(i):
+        # an eagerly launched step issues ~140 kernels + event records from Python: give the host
+        # a head start (the device spins first) so that no event bracket contains a launch gap
+        torch.cuda._sleep(head_start)
+        return trainer.step_device(dev[i % n_ring])
+
+    kt_region_ms, _ = timed(eager_step, n_kt)
     launches_per_step = (_lib.lib().b4cp_launch_count() - launches0) // n_kt
     launches = launches_per_step * args.steps
-    eager_ms_per_step = k0.elapsed_time(k1) / n_kt
     ops.TIMER.enabled = False
     kt = ops.TIMER.totals_ms()
+    kt_ms = sum(v[0] for k, v in kt.items() if k.startswith("k:"))   # device time inside brackets
     trainer.use_graph = graph_mode
 
     # ---- end-to-end timing through the public API (pinned host buffers in, loss out)
     trainer.step_host(*pinned[0])
-    barrier()
-    t0 = time.perf_counter()
-    e0.record()
-    for i in range(args.steps):
-        loss = trainer.step_host(*pinned[i % n_ring])
-    e1.record()
-    barrier()
-    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+    ms_e2e, loss = timed(lambda i: trainer.step_host(*pinned[i % n_ring]), args.steps)
     h2d = ClozeTrainStep.h2d_bytes(pinned[0][0], pinned[0][1])
+
+    # ---- end to end from RAW SESSIONS: the sessions live in HBM (CSR), the host sends B session
+    # indices per step, b4cp_cloze_build masks / chains / labels on the device (N2), then the step
+    e2e_builder = None
+    if not args.no_builder:
+        n_sess, L_items = 1 << 16, CFG["max_len"]
+        items = torch.from_numpy(zipf_items(rng, (n_sess * L_items,), V)).cuda()
+        offsets = torch.arange(0, (n_sess + 1) * L_items, L_items, dtype=torch.int64, device="cuda")
+        Mmax = host[0]["labels"].shape[1]
+        b_ids = torch.empty((B, S), dtype=torch.int32, device="cuda")
+        b_lab = torch.empty((B, Mmax), dtype=torch.float32, device="cuda")
+        b_cnt = torch.zeros(1, dtype=torch.int32, device="cuda")
+        b_status = torch.zeros(1, dtype=torch.int32, device="cuda")
+        idx_dev = torch.empty(B, dtype=torch.int32, device="cuda")
+        idx_host = [torch.from_numpy(rng.integers(0, n_sess, size=B).astype(np.int32)).pin_memory()
+                    for _ in range(n_ring)]
+        host_stats = torch.empty(2, dtype=torch.float32).pin_memory()
+
+        def builder_step(i):
+            idx_dev.copy_(idx_host[i % n_ring], non_blocking=True)
+            b_cnt.zero_()
+            ops.cloze_build(items, offsets, idx_dev, B, S - 3, Mmax, True, CFG["mask_rate"],
+                            CFG["max_masked"], 1000 + i, (CLS, SEP, MASK_ID, 0, NUM_RESERVED_TOKENS),
+                            LABEL_PAD, b_ids, b_lab, b_cnt, b_status)
+            st = trainer.step_device(DeviceBatch([b_ids.view(-1)], b_lab, B, S, M))
+            host_stats.copy_(st, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return float(host_stats[0] / max(float(host_stats[1]), 1.0))
+
+        builder_step(0)
+        ms_b, b_loss = timed(builder_step, args.steps)
+        e2e_builder = {"value": world * B * args.steps / (ms_b * 1e-3), "unit": "seqs/s",
+                       "ms_per_step": ms_b / args.steps, "h2d_bytes_per_step": B * 4,
+                       "d2h_bytes_per_step": 8, "last_loss": b_loss,
+                       "note": "sessions resident in HBM; per step: H2D of the batch's session "
+                               "indices, b4cp_cloze_build on the device, the training step, D2H loss",
+                       "builder_status": int(b_status.item())}
+
+    # ---- the reference's own per-GPU batch (examples/BERT4Rec/source/main.py:186): 512
+    b512 = None
+    if not args.no_b512 and B != 512:
+        h5 = [make_cloze_batch(rng, 512, V, CFG["max_len"], "train", CFG["mask_rate"],
+                               CFG["max_masked"]) for _ in range(n_ring)]
+        d5 = [trainer.to_device(b) for b in h5]
+        for i in range(ClozeTrainStep.GRAPH_WARMUP_STEPS + 3):
+            trainer.step_device(d5[i % n_ring])
+        n5 = max(args.steps, 50)
+        ms5, _ = timed(lambda i: trainer.step_device(d5[i % n_ring]), n5)
+        b512 = {"value": world * 512 * n5 / (ms5 * 1e-3), "unit": "seqs/s", "per_gpu_batch": 512,
+                "global_batch": 512 * world, "steps": n5, "ms_per_step": ms5 / n5,
+                "note": "same model and step at the reference's per-GPU batch (main.py:186)"}
+
+    # ---- the same step in the fp32-class parity mode, batch 512, N = 1
+    fp32_mode = None
+    if world == 1 and not args.no_fp32:
+        head32 = bc.SoftMaxHead(dense_layer_dims=CFG["head_dims"], output_vocab_size=V)
+        model32 = bc.ClickstreamTransformer(
+            sequential_input_config={"items": ["asin"]}, feature_vocabs={"items": V},
+            embedding_dims={"items": d}, head_unit=head32, value_to_head=bc.INPUT_MASKING_TOKEN,
+            num_encoder_layers=CFG["layers"], num_attention_heads=CFG["heads"],
+            dropout_rate=CFG["dropout"], encoder_ff_dim=CFG["dff"], seed=0, precision="fp32")
+        t32 = ClozeTrainStep(model32, bc.Adam(1e-3, 0.9, 0.999, 1e-9), use_graph=False)
+        h32 = [make_cloze_batch(rng, 512, V, CFG["max_len"], "train", CFG["mask_rate"],
+                                CFG["max_masked"]) for _ in range(2)]
+        d32 = [t32.to_device(b) for b in h32]
+        for i in range(3):
+            t32.step_device(d32[i % 2])
+        n32 = 10
+        ms32, st32 = timed(lambda i: t32.step_device(d32[i % 2]), n32)
+        s32 = st32.cpu().numpy()
+        fp32_mode = {"value": 512 * n32 / (ms32 * 1e-3), "unit": "seqs/s", "per_gpu_batch": 512,
+                     "ms_per_step": ms32 / n32, "steps": n32, "loss": float(s32[0] / max(s32[1], 1.0)),
+                     "note": "precision='fp32': fp32 activations, Dense layers as bf16 x 3 split "
+                             "products on the tcgen05 GEMM, fp32 attention, materialised fp32 logits; "
+                             "matches the fp32 reference to ~1e-5 (tests/test_zz_parity_configs_gpu.py)"}
+        del t32, model32, head32, d32
+        torch.cuda.empty_cache()
 
     # ---- next-item top-k inference (EVAL masking: last item of each session), k = 100
     topk = None
@@ -452,15 +719,8 @@ def run_ours(args, rank, world, local_rank):
 
         for i in range(3):
             query(i)
-        barrier()
-        n_q = max(5, args.steps // 2)
-        q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        q0.record()
-        for i in range(n_q):
-            query(i)
-        q1.record()
-        barrier()
-        q_ms = max_over_ranks(q0.elapsed_time(q1))
+        n_q = max(10, args.steps)
+        q_ms, _ = timed(query, n_q)
         c = counters.cpu().numpy()
         topk = {"metric": "next_item_topk_queries_per_sec", "value": world * QB * n_q / (q_ms * 1e-3),
                 "unit": "queries/s", "k": K_TOP, "queries_per_step_per_gpu": QB, "steps": n_q,
@@ -469,15 +729,18 @@ def run_ours(args, rank, world, local_rank):
                             "recall/NDCG counters; synthetic ids are NOT in popularity order",
                 "recall_at_k": float(c[0] / max(c[2], 1)), "ndcg_at_k": float(c[1] / max(c[2], 1))}
 
+    # Captured CUDA graphs hold NCCL kernels: drop them and quiesce before the next model / exit
+    trainer._graphs.clear()
+    torch.cuda.synchronize()
+    del dev
+    torch.cuda.empty_cache()
+
+    c4_train = c4_train_leg(args, rank, world) if not args.no_c4 else None
     c4 = c5 = None
     if world == 1 and not args.no_c4:
         c4 = c4_vocab_stage(peaks())
         c5 = c5_topk(peaks())
 
-    # Captured CUDA graphs hold NCCL kernels: drop them and quiesce BEFORE any teardown, and leave
-    # through os._exit so that no destructor (process group, graph pool) can block the launcher.
-    trainer._graphs.clear()
-    torch.cuda.synchronize()
     if rank != 0:
         finish(world)
     pk = peaks()
@@ -486,33 +749,35 @@ def run_ours(args, rank, world, local_rank):
     # roofline of the dominant kernel, vocab_ce_fwd_kernel: per launch it needs S = X W (2MhV) and
     # U = P' W^T for dX (2MhV) -> 4*M*h*V algorithmic flops; the backward kernel (S recompute is
     # not algorithmic, dW is: 2MhV) and the whole stage (6MhV over fwd + dx + bwd) ride along.
+    # The kernels are event-timed over n_kt eagerly launched steps, each after an idle head start
+    # for the host (device spinning): bursts of a few ms at full clock -> the BURST peak.
     h = CFG["head_dims"][-1]
     step_ms = ms_total / args.steps
-    peak = pk["bf16_sustained"]
+    peak, peak_src = pick_peak(pk, kt_ms * 1e-3)
 
     def kernel_line(tag, flops, per_step=False):
         k_ms, k_n = kt.get(tag, (0.0, 0))
         per = k_ms / max(n_kt if per_step else k_n, 1)
         ach = flops / (per * 1e-3) / 1e12 if per > 0 else 0.0
-        return {"achieved": ach, "frac": ach / peak, "algorithmic_flops_per_launch": flops,
-                "ms_per_launch": per, "launches": k_n,
+        return {"achieved": ach, "frac": ach / peak, "frac_of_sustained_peak": ach / pk["bf16_sustained"],
+                "algorithmic_flops_per_launch": flops, "ms_per_launch": per, "launches": k_n,
                 "kernel_share_of_step": (k_ms / max(n_kt, 1)) / step_ms}
 
     mhv = float(M) * h * V
     traffic = None
     try:
-        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             tj = json.load(f)
         if tj.get("M") == M and tj.get("V") == V:
             traffic = tj["vocab_ce_fwd_ts_kernel"]["dram_bytes_per_launch"]
     except (OSError, KeyError, ValueError):
         pass
     roof = {"bound": "tensor", "kernel": "vocab_ce_fwd_ts_kernel", "peak": peak, "unit": "TFLOP/s",
-            "traffic": traffic,
-            "peak_source": pk["source"] + " (sustained: kernel timed inside a long step)"}
+            "traffic": traffic, "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": float(M) * h * 2 + float(V) * h * 2 + V * 4 + M * 4}
     roof.update(kernel_line("k:vocab_ce_fwd", 4.0 * mhv))
     roof["timed"] = ("CUDA events on the launch stream around b4cp_vocab_ce_fwd (the kernel + its "
-                     "M-row partial merge, < 0.5% of the bracket)")
+                     "M-row partial merge, < 0.5% of the bracket), eagerly launched steps")
     roof["other_kernels"] = {"vocab_ce_bwd_ts_kernel": kernel_line("k:vocab_ce_bwd", 2.0 * mhv),
                              "vocab_stage_fwd_dx_bwd": kernel_line("vocab_ce", 6.0 * mhv, per_step=True)}
     roof["other_kernels"]["vocab_stage_fwd_dx_bwd"]["note"] = \
@@ -522,28 +787,38 @@ def run_ours(args, rank, world, local_rank):
         cpu_base = {"value": cpu_seqs, "unit": "seqs/s", "cores": blas_threads(), "kind": "port",
                     "sample": f"{cpu_n} full oracle training steps at batch {args.cpu_batch}"}
     else:
-        cpu_base = None  # reported at N=1 only (torchrun pins OMP_NUM_THREADS=1)
+        cpu_base = None  # reported at N=1 only
+    metrics = [{"metric": "cloze_train_seqs_per_sec", "value": seqs, "unit": "seqs/s"}]
+    if topk:
+        metrics.append({"metric": topk["metric"], "value": topk["value"], "unit": topk["unit"]})
     line = {
         "metric": "cloze_train_seqs_per_sec", "value": seqs, "unit": "seqs/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic",
+        "metrics": metrics,
+        "topk_queries_per_sec": topk["value"] if topk else None,
         "config": {"workload": workload_name(B), "per_gpu_batch": B, "global_batch": B * world,
                    "seq_len": S, "masked_per_step_per_gpu": M, "parallelism": f"dp{world}",
                    "l2": "per-step working set (activations + 28 MB output kernel + logits) "
                          "exceeds the 126 MB L2; 4 distinct batches cycle",
-                   "precision": "bf16 tensor-core operands, fp32 accumulate / master weights"},
+                   "precision": "bf16 tensor-core operands, fp32 accumulate / master weights "
+                                "(parity of this path and of the fp32-class mode: DESIGN.md section 5)"},
         "clocks": clocks,
         "e2e": {"value": seqs_e2e, "unit": "seqs/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 8, "ms_per_step": ms_e2e / args.steps},
+        "e2e_from_sessions": e2e_builder,
+        "sustained": sustained,
+        "b512": b512,
+        "fp32_mode": fp32_mode,
         "gpu_launches": int(launches),
         "launch_mode": {"cuda_graph": bool(graph_mode), "kernels_per_step": int(launches_per_step),
-                        "eager_ms_per_step_with_event_brackets": eager_ms_per_step,
                         "note": "value/e2e replay one captured graph per step; gpu_launches = "
                                 "kernels per step (counted on eagerly launched steps) x steps"},
         "roofline": roof,
         "cpu_baseline": cpu_base,
         "topk": topk,
+        "c4_train": c4_train,
         "c4_vocab_stage": c4,
         "c5_topk": c5,
         "loss": float(loss_stats[0] / max(loss_stats[1], 1.0)), "e2e_last_loss": loss,
@@ -561,8 +836,13 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=4096, help="per-GPU batch (sequences)")
     ap.add_argument("--cpu-batch", type=int, default=64, help="batch of the CPU reference sample")
+    ap.add_argument("--sustain-seconds", type=float, default=2.5,
+                    help="also hold the step for this long (sustained-clock number); 0 = skip")
     ap.add_argument("--no-topk", action="store_true", help="skip the top-k inference leg")
-    ap.add_argument("--no-c4", action="store_true", help="skip the C4 / C5 (V=1M, h=256) kernel legs")
+    ap.add_argument("--no-b512", action="store_true", help="skip the batch-512 leg")
+    ap.add_argument("--no-fp32", action="store_true", help="skip the fp32-class parity-mode leg")
+    ap.add_argument("--no-builder", action="store_true", help="skip the sessions -> batch -> step leg")
+    ap.add_argument("--no-c4", action="store_true", help="skip the C4 / C5 (V=1M, h=256) legs")
     ap.add_argument("--max-seconds", type=int, default=1200, help="watchdog: hard exit after this long")
     args = ap.parse_args()
     arm_watchdog(args.max_seconds)

@@ -15,11 +15,26 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
+// Forward schedules.  A SEGMENT is a run of consecutive vocabulary tiles of ONE row tile processed
+// by one CTA; it ends with one (max, sum, U) partial per row in slot `slot` of that row tile.
+//   SCHED_GRID   grid = row tiles x vocabulary chunks, one segment per CTA, slot = chunk.  CTAs of
+//                a chunk sweep its W tiles in lock step, so every W tile is fetched from HBM once
+//                however large the vocabulary is (C4: W = 512 MB >> L2).
+//   SCHED_RANGES persistent: <= 148 CTAs, CTA k owns tiles [k Q, (k+1) Q) of the row-major
+//                (row tile, vocabulary tile) space - no wave quantisation, one CTA set-up instead
+//                of ~10, and partials only where a range cuts a row tile (<= 2 per row once
+//                Q >= n_vtiles).  Used when W fits L2 (C1 / C2: 13.9 MB), where the CTAs need not
+//                be aligned on the vocabulary.  slot = k - first_cta(row tile).
+enum { SCHED_GRID = 0, SCHED_RANGES = 1 };
+
 struct VocabParams {
   int M, V, h, HB;          // HB = h / 64
   int n_mtiles, n_vtiles;
-  int tiles_per_chunk;      // forward: vocabulary tiles per CTA
-  int n_chunks;
+  int tiles_per_chunk;      // SCHED_GRID: vocabulary tiles per CTA
+  int n_chunks;             // partial slots per row (both schedules: the workspace stride)
+  int sched;                // SCHED_GRID / SCHED_RANGES
+  long range_q;             // SCHED_RANGES: tiles per CTA
+  long total_tiles;         // n_mtiles * n_vtiles
   const float* bias;
   const int32_t* labels;
   // forward outputs
@@ -29,12 +44,24 @@ struct VocabParams {
   float* part_u;            // [n_chunks][M][h] un-normalised sum_v exp2(z2 - m) W[:,v] (with_dx)
   int with_dx;              // forward also accumulates part_u (h = 128)
   int fwd_stages;
+  int x_bufs;               // forward: X tile buffers in shared memory (1 or 2)
   // backward inputs / outputs
   const float* lse;         // [M]
   const float* loss_stats;  // [2]: (sum, n_valid)
   float* dW;                // [h][V]
   float* db;                // [V]
 };
+
+// number of partial slots row tile m holds, and the CTA that writes its slot 0 (SCHED_RANGES)
+__host__ __device__ inline int ranges_first_cta(long q, int n_vtiles, int m) {
+  return (int)(((long)m * n_vtiles) / q);
+}
+__host__ __device__ inline int ranges_slots(long q, int n_vtiles, int m) {
+  return (int)((((long)(m + 1) * n_vtiles - 1) / q) - ((long)m * n_vtiles) / q) + 1;
+}
+__host__ __device__ inline int vocab_row_slots(const VocabParams& p, int row) {
+  return p.sched == SCHED_RANGES ? ranges_slots(p.range_q, p.n_vtiles, row / VB_M) : p.n_chunks;
+}
 
 // Warp roles (both kernels, 576 threads): warps 0-15 = epilogue, warp 16 = TMA producer + TMEM
 // owner, warp 17 = MMA issuer.  Epilogue warp w reads TMEM lanes [32*(w%4), +32) (hardware

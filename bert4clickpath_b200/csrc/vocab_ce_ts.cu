@@ -40,6 +40,46 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 // packed columns at [32cg, 32cg+16) - inside its own region, so no warp overwrites columns another
 // warp still has to read.  K step k8 (vocabulary entries 16k8..16k8+15 of the tile) therefore
 // reads A at column 32*(k8>>1) + 8*(k8&1).
+//
+// A CTA processes a list of SEGMENTS (vocab_ce.cuh: one under SCHED_GRID, the pieces of its tile
+// range under SCHED_RANGES).  The W ring, the S / P' / U hand-shakes and their phases run on ONE
+// tile counter across segments; per segment there is an X tile (ring of p.x_bufs buffers), a fresh
+// set of row statistics, and at its end a drain of U from TMEM into the segment's partial slot
+// (`u_drained` tells the MMA warp that U may be overwritten by the next segment's first product).
+struct FwdSeg {
+  int m, v0, len, slot;
+};
+
+__device__ __forceinline__ void fwd_range(const VocabParams& p, long& L0, long& L1) {
+  if (p.sched == SCHED_GRID) {
+    const int t_begin = (int)blockIdx.y * p.tiles_per_chunk;
+    const int t_end = min(p.n_vtiles, t_begin + p.tiles_per_chunk);
+    L0 = 0;
+    L1 = t_end - t_begin;
+  } else {
+    L0 = (long)blockIdx.x * p.range_q;
+    L1 = min(p.total_tiles, L0 + p.range_q);
+  }
+}
+
+__device__ __forceinline__ FwdSeg fwd_seg(const VocabParams& p, long L, long L1) {
+  FwdSeg s;
+  if (p.sched == SCHED_GRID) {
+    s.m = (int)blockIdx.x;
+    s.v0 = (int)blockIdx.y * p.tiles_per_chunk + (int)L;
+    s.len = (int)(L1 - L);
+    s.slot = (int)blockIdx.y;
+  } else {
+    s.m = (int)(L / p.n_vtiles);
+    s.v0 = (int)(L - (long)s.m * p.n_vtiles);
+    const long rem = L1 - L;
+    const long left = p.n_vtiles - s.v0;
+    s.len = (int)(rem < left ? rem : left);
+    s.slot = (int)blockIdx.x - ranges_first_cta(p.range_q, p.n_vtiles, s.m);
+  }
+  return s;
+}
+
 template <int NSB>   // S accumulators in TMEM: 3 at h <= 128, 2 at h = 256
 __global__ void __launch_bounds__(TS_THREADS, 1)
 vocab_ce_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmX,
@@ -49,22 +89,25 @@ vocab_ce_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmX,
                                              ~static_cast<uintptr_t>(1023));
   const int HB = p.HB;
   const int NST = p.fwd_stages;
+  const int XB = p.x_bufs;
   const bool with_dx = p.with_dx != 0;
   const int x_bytes = HB * VB_M * 128;
   const int w_bytes = 2 * HB * 64 * 128;
   uint8_t* sX = smem;
-  uint8_t* sW = sX + x_bytes;
+  uint8_t* sW = sX + (size_t)XB * x_bytes;
   float* sBias = reinterpret_cast<float*>(sW + (size_t)NST * w_bytes);  // [16 warps][32]
   float* sMax = sBias + 16 * 32;                                         // [2][4 cg][128 rows]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sMax + 2 * 4 * VB_M);
-  uint64_t* x_full = bars;
-  uint64_t* w_full = bars + 1;          // [4]
+  uint64_t* x_full = bars;              // [2]
+  uint64_t* x_empty = bars + 2;         // [2]
+  uint64_t* w_full = x_empty + 2;       // [4]
   uint64_t* w_empty = w_full + 4;       // [4]
   uint64_t* s_full = w_empty + 4;       // [3]
   uint64_t* s_empty = s_full + 3;       // [3]
   uint64_t* p_full = s_empty + 3;       // [3]
   uint64_t* u_full = p_full + 3;        // [3]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(u_full + 3);
+  uint64_t* u_drained = u_full + 3;     // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(u_drained + 1);
   // S accumulators: three at h <= 128 (columns 0,128,256; U at 384), two at h = 256 (U at 256).
   // With three, S runs two tiles ahead of the epilogue: S(t+3) only has to follow U(t), so an
   // epilogue that takes about as long as the tile's two MMAs no longer stalls on every other tile.
@@ -72,11 +115,8 @@ vocab_ce_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmX,
   // warp index through shfl: provably warp-uniform, so the role branches are uniform control flow
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * VB_M;
-  const int chunk = blockIdx.y;
-  const int t_begin = chunk * p.tiles_per_chunk;
-  const int t_end = min(p.n_vtiles, t_begin + p.tiles_per_chunk);
-  const int ntiles = t_end - t_begin;
+  long L_begin, L_end;
+  fwd_range(p, L_begin, L_end);
 
   if (warp == WARP_TMA) {
     if (lane == 0) {
@@ -86,7 +126,10 @@ vocab_ce_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmX,
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   } else if (warp == WARP_MMA && lane == 0) {
-    mbar_init(x_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&x_full[s], 1);
+      mbar_init(&x_empty[s], 1);
+    }
     for (int s = 0; s < 4; ++s) {
       mbar_init(&w_full[s], 1);
       mbar_init(&w_empty[s], 1);
@@ -97,6 +140,7 @@ vocab_ce_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmX,
       mbar_init(&p_full[b], NUM_EPI_WARPS);
       mbar_init(&u_full[b], 1);
     }
+    mbar_init(u_drained, NUM_EPI_WARPS);
     fence_barrier_init();
   }
   tc_fence_before();
@@ -108,18 +152,26 @@ vocab_ce_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmX,
   if (warp == WARP_TMA) {
     // whole warp, uniform control flow; the TMA instructions are predicated on an elected lane
     const uint32_t aX = smem_u32(sX), aW0 = smem_u32(sW);
-    mbar_expect_tx_el(x_full, (uint32_t)x_bytes);
-    for (int hb = 0; hb < HB; ++hb)
-      tma_load_2d_el(aX + hb * (VB_M * 128), &tmX, x_full, hb * 64, m0);
-    for (int t = 0; t < ntiles; ++t) {
-      const int st = t % NST;
-      mbar_wait_all(&w_empty[st], ((t / NST) & 1) ^ 1);
-      mbar_expect_tx_el(&w_full[st], (uint32_t)w_bytes);
-      const int v0 = (t_begin + t) * VB_N;
-      const uint32_t dst = aW0 + (uint32_t)(st * w_bytes);
-      for (int vb = 0; vb < 2; ++vb)
-        for (int hb = 0; hb < HB; ++hb)
-          tma_load_2d_el(dst + (vb * HB + hb) * 8192, &tmW, &w_full[st], v0 + vb * 64, hb * 64);
+    long t = 0;
+    int sg = 0;
+    for (long L = L_begin; L < L_end; ++sg) {
+      const FwdSeg s = fwd_seg(p, L, L_end);
+      const int xb = sg % XB;
+      mbar_wait_all(&x_empty[xb], (uint32_t)((sg / XB) & 1) ^ 1);
+      mbar_expect_tx_el(&x_full[xb], (uint32_t)x_bytes);
+      for (int hb = 0; hb < HB; ++hb)
+        tma_load_2d_el(aX + xb * x_bytes + hb * (VB_M * 128), &tmX, &x_full[xb], hb * 64, s.m * VB_M);
+      for (int i = 0; i < s.len; ++i, ++t) {
+        const int st = (int)(t % NST);
+        mbar_wait_all(&w_empty[st], (uint32_t)((t / NST) & 1) ^ 1);
+        mbar_expect_tx_el(&w_full[st], (uint32_t)w_bytes);
+        const int v0 = (s.v0 + i) * VB_N;
+        const uint32_t dst = aW0 + (uint32_t)(st * w_bytes);
+        for (int vb = 0; vb < 2; ++vb)
+          for (int hb = 0; hb < HB; ++hb)
+            tma_load_2d_el(dst + (vb * HB + hb) * 8192, &tmW, &w_full[st], v0 + vb * 64, hb * 64);
+      }
+      L += s.len;
     }
   } else if (warp == WARP_MMA) {
     // The WHOLE warp runs this loop in uniform control flow; only the tcgen05 instructions are
@@ -132,24 +184,41 @@ vocab_ce_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmX,
     const uint64_t dX = umma_smem_desc(aX, 16, 1024);                // X, K-major (A of S)
     const uint64_t dWs = umma_smem_desc(aW0, HB * 8192, 1024);       // W, MN-major (B of S)
     const uint64_t dWu = umma_smem_desc(aW0, 16, 1024);              // W, K-major (B of U)
-    auto s_ready = [&](int t) -> bool {
-      return mbar_test_all(&w_full[t % NST], (t / NST) & 1) &&
-             mbar_test_all(&s_empty[t % NSB], ((t / NSB) & 1) ^ 1);
-    };
-    auto issue_s = [&](int t) {
-      const int st = t % NST, buf = t % NSB;
+    // two cursors over the segment list: the S queue and the U queue
+    long Ls = L_begin, Lu = L_begin;
+    int sgs = 0, sgu = 0, is = 0, iu = 0;         // segment index / tile index inside it
+    int len_s = Ls < L_end ? fwd_seg(p, Ls, L_end).len : 0;
+    int len_u = len_s;
+    const long n_total = L_end - L_begin;
+    auto issue_s = [&](long t) {
+      const int st = (int)(t % NST), buf = (int)(t % NSB), xb = sgs % XB;
       tc_fence_after();
       const uint32_t wo = (uint32_t)(st * w_bytes) >> 4;
+      const uint32_t xo = (uint32_t)(xb * x_bytes) >> 4;
       for (int hb = 0; hb < HB; ++hb) {
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk)
-          umma_bf16_el(tmem_base + buf * VB_N, dX + (uint32_t)((hb * (VB_M * 128) + kk * 32) >> 4),
+          umma_bf16_el(tmem_base + buf * VB_N, dX + (xo + (uint32_t)((hb * (VB_M * 128) + kk * 32) >> 4)),
                        dWs + (wo + (uint32_t)((hb * 8192 + kk * 2048) >> 4)), id_s, (hb | kk) ? 1u : 0u);
       }
       umma_commit_el(&s_full[buf]);
+      if (is == len_s - 1) umma_commit_el(&x_empty[xb]);   // last reader of this X tile
     };
-    auto issue_u = [&](int t) {
-      const int st = t % NST, buf = t % NSB;
+    auto advance_s = [&]() {
+      if (++is == len_s) {
+        Ls += len_s;
+        ++sgs;
+        is = 0;
+        len_s = Ls < L_end ? fwd_seg(p, Ls, L_end).len : 0;
+      }
+    };
+    auto s_ready = [&](long t) -> bool {
+      if (is == 0 && !mbar_test_all(&x_full[sgs % XB], (uint32_t)((sgs / XB) & 1))) return false;
+      return mbar_test_all(&w_full[t % NST], (uint32_t)((t / NST) & 1)) &&
+             mbar_test_all(&s_empty[t % NSB], (uint32_t)((t / NSB) & 1) ^ 1);
+    };
+    auto issue_u = [&](long t) {
+      const int st = (int)(t % NST), buf = (int)(t % NSB);
       tc_fence_after();
       const uint32_t wo = (uint32_t)(st * w_bytes) >> 4;
       const uint32_t tP = tmem_base + buf * VB_N;
@@ -157,18 +226,19 @@ vocab_ce_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmX,
       for (int k8 = 0; k8 < 8; ++k8) {
         const int vb = k8 >> 2, kk = k8 & 3;
         umma_bf16_ts_el(T_U, tP + (k8 >> 1) * 32 + (k8 & 1) * 8,
-                        dWu + (wo + (uint32_t)((vb * HB * 8192 + kk * 32) >> 4)), id_u, (t | k8) ? 1u : 0u);
+                        dWu + (wo + (uint32_t)((vb * HB * 8192 + kk * 32) >> 4)), id_u, (iu | k8) ? 1u : 0u);
       }
       umma_commit_el(&u_full[buf]);
       umma_commit_el(&w_empty[st]);
     };
-    mbar_wait_all(x_full, 0);
     if (!with_dx) {
-      for (int t = 0; t < ntiles; ++t) {
-        mbar_wait_all(&w_full[t % NST], (t / NST) & 1);
-        mbar_wait_all(&s_empty[t % NSB], ((t / NSB) & 1) ^ 1);
+      for (long t = 0; t < n_total; ++t) {
+        if (is == 0) mbar_wait_all(&x_full[sgs % XB], (uint32_t)((sgs / XB) & 1));
+        mbar_wait_all(&w_full[t % NST], (uint32_t)((t / NST) & 1));
+        mbar_wait_all(&s_empty[t % NSB], (uint32_t)((t / NSB) & 1) ^ 1);
         issue_s(t);
         umma_commit_el(&w_empty[t % NST]);
+        advance_s();
       }
     } else {
       // Two queues, one issuing warp: S(ts) needs its W stage and a free accumulator, U(tu)
@@ -176,17 +246,25 @@ vocab_ce_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmX,
       // U(t), hence the release of W(t)'s stage, hence the load of W(t+2): loads and tensor
       // work would serialise).  Order constraint: S(t+2) after U(t) - the tensor pipe executes
       // in issue order, so S(t+NSB) then cannot overwrite P'(t) before U(t) has read it.
-      int ts = 0, tu = 0;
-      while (tu < ntiles) {
+      long ts = 0, tu = 0;
+      while (tu < n_total) {
         bool progressed = false;
-        if (tu < ts && mbar_test_all(&p_full[tu % NSB], (tu / NSB) & 1)) {
+        if (tu < ts && mbar_test_all(&p_full[tu % NSB], (uint32_t)((tu / NSB) & 1)) &&
+            (iu != 0 || sgu == 0 || mbar_test_all(u_drained, (uint32_t)((sgu - 1) & 1)))) {
           issue_u(tu);
           ++tu;
+          if (++iu == len_u) {
+            Lu += len_u;
+            ++sgu;
+            iu = 0;
+            len_u = Lu < L_end ? fwd_seg(p, Lu, L_end).len : 0;
+          }
           progressed = true;
         }
-        if (ts < ntiles && ts <= tu + NSB - 1 && s_ready(ts)) {
+        if (ts < n_total && ts <= tu + NSB - 1 && s_ready(ts)) {
           issue_s(ts);
           ++ts;
+          advance_s();
           progressed = true;
         }
         if (!progressed) __nanosleep(20);
@@ -196,139 +274,148 @@ vocab_ce_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmX,
     const int q = warp & 3;
     const int cg = warp >> 2;
     const int r_in_tile = q * 32 + lane;
-    const int row = m0 + r_in_tile;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-    const int label = row < p.M ? p.labels[row] : -1;
     const uint32_t sb = smem_u32(sBias + warp * 32);
     const uint32_t aMax = smem_u32(sMax);
     const int uw = p.h >> 2;  // U columns owned by this warp: [cg*uw, +uw), 32 or 64
-    // statistics in the log2 domain: z2 = (x.w + b) * log2(e); s_run is relative to m_ref
-    float m_run = -INFINITY, m_ref = -INFINITY, s_run = 0.f, tgt2 = 0.f;
-    bool have_tgt = false;
-    auto load_bias = [&](int t) -> float {
-      const int v = (t_begin + t) * VB_N + cg * 32 + lane;
-      return (t < ntiles && v < p.V) ? __ldg(p.bias + v) : -INFINITY;
-    };
-    float bias_next = load_bias(0);
-    for (int t = 0; t < ntiles; ++t) {
-      const int buf = t % NSB, sph = (t / NSB) & 1;   // accumulator buffer and its barrier phase
-      const int vbase = (t_begin + t) * VB_N + cg * 32;
-      sts32f(sb + lane * 4, bias_next * LOG2E);
-      __syncwarp();
-      bias_next = load_bias(t + 1);  // in flight while this tile is processed
-      mbar_wait(&s_full[buf], sph);
-      tc_fence_after();
-      const uint32_t tS = tmem_base + lane_base + (uint32_t)(buf * VB_N + cg * 32);
-      uint32_t r[32];
-      tmem_ld32(tS, r);
-      tmem_ld_wait();
-      tc_fence_before();
-      mbar_arrive_warp(&s_empty[buf]);
-      float z[32];
-      float cmax = -INFINITY;
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        const float4 b4 = lds128f(sb + j * 4);
-        z[j + 0] = fmaf(__uint_as_float(r[j + 0]), LOG2E, b4.x);
-        z[j + 1] = fmaf(__uint_as_float(r[j + 1]), LOG2E, b4.y);
-        z[j + 2] = fmaf(__uint_as_float(r[j + 2]), LOG2E, b4.z);
-        z[j + 3] = fmaf(__uint_as_float(r[j + 3]), LOG2E, b4.w);
-        cmax = fmaxf(cmax, fmaxf(fmaxf(z[j], z[j + 1]), fmaxf(z[j + 2], z[j + 3])));
-      }
-      __syncwarp();  // sb is rewritten for the next tile
-      if (label >= vbase && label < vbase + 32) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (vbase + j == label) tgt2 = z[j];
-        have_tgt = true;
-      }
-      if (with_dx) {
-        // the 4 warps that share these rows agree on one running maximum per row
-        const uint32_t mx = aMax + (uint32_t)((t & 1) * (4 * VB_M) + r_in_tile) * 4;
-        sts32f(mx + cg * VB_M * 4, cmax);
-        asm volatile("bar.sync %0, 128;" ::"r"(2 + q) : "memory");
-        cmax = fmaxf(fmaxf(lds32f(mx), lds32f(mx + VB_M * 4)),
-                     fmaxf(lds32f(mx + 2 * VB_M * 4), lds32f(mx + 3 * VB_M * 4)));
-      }
-      const float m_new = fmaxf(m_run, cmax);
-      if (!with_dx) {
-        const float alpha = m_ref > -INFINITY ? ex2(m_ref - m_new) : 0.f;
-        s_run *= alpha;
-        m_ref = m_new;
-      } else if (t == 0) {
-        m_ref = m_new;  // nothing accumulated yet
-      } else {
-        const bool jump = m_new > m_ref + RESCALE_TH;
-        if (__any_sync(0xffffffffu, jump)) {
-          // rare: U(0..t-1) must have retired before its columns are rescaled in TMEM; U(t)
-          // cannot start before p_full(t), which this warp only signals after the rescale
-          mbar_wait(&u_full[(t - 1) % NSB], ((t - 1) / NSB) & 1);
-          tc_fence_after();
-          const float f = jump ? ex2(m_ref - m_new) : 1.f;
-#pragma unroll 1
-          for (int c = 0; c < uw; c += 8) {  // 8 columns at a time: keeps z[] in registers
-            const uint32_t tU = T_U + lane_base + (uint32_t)(cg * uw + c);
-            uint32_t u[8];
-            tmem_ld8(tU, u);
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 8; ++j) u[j] = __float_as_uint(__uint_as_float(u[j]) * f);
-            tmem_st8(tU, u);
-          }
-          tmem_st_wait();
-          s_run *= f;
-          if (jump) m_ref = m_new;
-        }
-      }
-      m_run = m_new;
-      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        z[j + 0] = ex2(z[j + 0] - m_ref);
-        z[j + 1] = ex2(z[j + 1] - m_ref);
-        z[j + 2] = ex2(z[j + 2] - m_ref);
-        z[j + 3] = ex2(z[j + 3] - m_ref);
-        a0 += z[j + 0];
-        a1 += z[j + 1];
-        a2 += z[j + 2];
-        a3 += z[j + 3];
-      }
-      s_run += (a0 + a1) + (a2 + a3);
-      if (with_dx) {
-        uint32_t pk[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(z[2 * j], z[2 * j + 1]);
-        tmem_st16(tS, pk);
-        tmem_st_wait();
-        tc_fence_before();
-        mbar_arrive_warp(&p_full[buf]);
-      }
-    }
-    if (with_dx && ntiles > 0) {
-      mbar_wait(&u_full[(ntiles - 1) % NSB], ((ntiles - 1) / NSB) & 1);
-      tc_fence_after();
-    }
-    if (row < p.M) {
-      const size_t slot = ((size_t)chunk * 4 + cg) * p.M + row;
-      p.part_max[slot] = m_ref;   // log2 domain; the reference the sums are relative to
-      p.part_sum[slot] = s_run;
-      if (have_tgt) p.tgt[row] = tgt2 * LN2;
-    }
-    if (with_dx) {
-      for (int c = 0; c < uw; c += 32) {
-        uint32_t u[32];
-        tmem_ld32(T_U + lane_base + (uint32_t)(cg * uw + c), u);
+    long t = 0;
+    int sg = 0;
+    for (long L = L_begin; L < L_end; ++sg) {
+      const FwdSeg sgm = fwd_seg(p, L, L_end);
+      const int row = sgm.m * VB_M + r_in_tile;
+      const int label = row < p.M ? p.labels[row] : -1;
+      // statistics in the log2 domain: z2 = (x.w + b) * log2(e); s_run is relative to m_ref
+      float m_run = -INFINITY, m_ref = -INFINITY, s_run = 0.f, tgt2 = 0.f;
+      bool have_tgt = false;
+      auto load_bias = [&](int i) -> float {
+        const int v = (sgm.v0 + i) * VB_N + cg * 32 + lane;
+        return (i < sgm.len && v < p.V) ? __ldg(p.bias + v) : -INFINITY;
+      };
+      float bias_next = load_bias(0);
+      for (int i = 0; i < sgm.len; ++i, ++t) {
+        const int buf = (int)(t % NSB);
+        const uint32_t sph = (uint32_t)((t / NSB) & 1);   // accumulator buffer and its barrier phase
+        const int vbase = (sgm.v0 + i) * VB_N + cg * 32;
+        sts32f(sb + lane * 4, bias_next * LOG2E);
+        __syncwarp();
+        bias_next = load_bias(i + 1);  // in flight while this tile is processed
+        mbar_wait(&s_full[buf], sph);
+        tc_fence_after();
+        const uint32_t tS = tmem_base + lane_base + (uint32_t)(buf * VB_N + cg * 32);
+        uint32_t r[32];
+        tmem_ld32(tS, r);
         tmem_ld_wait();
-        if (row < p.M) {
-          float* dst = p.part_u + ((size_t)chunk * p.M + row) * p.h + cg * uw + c;
+        tc_fence_before();
+        mbar_arrive_warp(&s_empty[buf]);
+        float z[32];
+        float cmax = -INFINITY;
 #pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            *reinterpret_cast<float4*>(dst + j) =
-                make_float4(__uint_as_float(u[j]), __uint_as_float(u[j + 1]),
-                            __uint_as_float(u[j + 2]), __uint_as_float(u[j + 3]));
+        for (int j = 0; j < 32; j += 4) {
+          const float4 b4 = lds128f(sb + j * 4);
+          z[j + 0] = fmaf(__uint_as_float(r[j + 0]), LOG2E, b4.x);
+          z[j + 1] = fmaf(__uint_as_float(r[j + 1]), LOG2E, b4.y);
+          z[j + 2] = fmaf(__uint_as_float(r[j + 2]), LOG2E, b4.z);
+          z[j + 3] = fmaf(__uint_as_float(r[j + 3]), LOG2E, b4.w);
+          cmax = fmaxf(cmax, fmaxf(fmaxf(z[j], z[j + 1]), fmaxf(z[j + 2], z[j + 3])));
+        }
+        __syncwarp();  // sb is rewritten for the next tile
+        if (label >= vbase && label < vbase + 32) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (vbase + j == label) tgt2 = z[j];
+          have_tgt = true;
+        }
+        if (with_dx) {
+          // the 4 warps that share these rows agree on one running maximum per row
+          const uint32_t mx = aMax + (uint32_t)((int)(t & 1) * (4 * VB_M) + r_in_tile) * 4;
+          sts32f(mx + cg * VB_M * 4, cmax);
+          asm volatile("bar.sync %0, 128;" ::"r"(2 + q) : "memory");
+          cmax = fmaxf(fmaxf(lds32f(mx), lds32f(mx + VB_M * 4)),
+                       fmaxf(lds32f(mx + 2 * VB_M * 4), lds32f(mx + 3 * VB_M * 4)));
+        }
+        const float m_new = fmaxf(m_run, cmax);
+        if (!with_dx) {
+          const float alpha = m_ref > -INFINITY ? ex2(m_ref - m_new) : 0.f;
+          s_run *= alpha;
+          m_ref = m_new;
+        } else if (i == 0) {
+          m_ref = m_new;  // nothing accumulated yet in this segment
+        } else {
+          const bool jump = m_new > m_ref + RESCALE_TH;
+          if (__any_sync(0xffffffffu, jump)) {
+            // rare: U(..t-1) must have retired before its columns are rescaled in TMEM; U(t)
+            // cannot start before p_full(t), which this warp only signals after the rescale
+            mbar_wait(&u_full[(t - 1) % NSB], (uint32_t)(((t - 1) / NSB) & 1));
+            tc_fence_after();
+            const float f = jump ? ex2(m_ref - m_new) : 1.f;
+#pragma unroll 1
+            for (int c = 0; c < uw; c += 8) {  // 8 columns at a time: keeps z[] in registers
+              const uint32_t tU = T_U + lane_base + (uint32_t)(cg * uw + c);
+              uint32_t u[8];
+              tmem_ld8(tU, u);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 8; ++j) u[j] = __float_as_uint(__uint_as_float(u[j]) * f);
+              tmem_st8(tU, u);
+            }
+            tmem_st_wait();
+            s_run *= f;
+            if (jump) m_ref = m_new;
+          }
+        }
+        m_run = m_new;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          z[j + 0] = ex2(z[j + 0] - m_ref);
+          z[j + 1] = ex2(z[j + 1] - m_ref);
+          z[j + 2] = ex2(z[j + 2] - m_ref);
+          z[j + 3] = ex2(z[j + 3] - m_ref);
+          a0 += z[j + 0];
+          a1 += z[j + 1];
+          a2 += z[j + 2];
+          a3 += z[j + 3];
+        }
+        s_run += (a0 + a1) + (a2 + a3);
+        if (with_dx) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(z[2 * j], z[2 * j + 1]);
+          tmem_st16(tS, pk);
+          tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive_warp(&p_full[buf]);
         }
       }
-      tc_fence_before();
+      // ---- end of the segment: one (m_ref, sum, U) partial per row into slot sgm.slot
+      if (with_dx && sgm.len > 0) {
+        mbar_wait(&u_full[(t - 1) % NSB], (uint32_t)(((t - 1) / NSB) & 1));
+        tc_fence_after();
+      }
+      if (row < p.M) {
+        const size_t slot = ((size_t)sgm.slot * 4 + cg) * p.M + row;
+        p.part_max[slot] = m_ref;   // log2 domain; the reference the sums are relative to
+        p.part_sum[slot] = s_run;
+        if (have_tgt) p.tgt[row] = tgt2 * LN2;
+      }
+      if (with_dx) {
+        for (int c = 0; c < uw; c += 32) {
+          uint32_t u[32];
+          tmem_ld32(T_U + lane_base + (uint32_t)(cg * uw + c), u);
+          tmem_ld_wait();
+          if (row < p.M) {
+            float* dst = p.part_u + ((size_t)sgm.slot * p.M + row) * p.h + cg * uw + c;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(dst + j) =
+                  make_float4(__uint_as_float(u[j]), __uint_as_float(u[j + 1]),
+                              __uint_as_float(u[j + 2]), __uint_as_float(u[j + 3]));
+          }
+        }
+        tc_fence_before();
+        mbar_arrive_warp(u_drained);   // U may be overwritten by the next segment
+      }
+      L += sgm.len;
     }
   }
   __syncthreads();
@@ -630,27 +717,31 @@ vocab_ce_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmX,
 }
 
 // ------------------------------------------------------------------------------- launchers
-static size_t fwd_ts_smem(int HB, int stages) {
-  return (size_t)HB * VB_M * 128 + (size_t)stages * 2 * HB * 8192 + 16 * 32 * 4 +
+static size_t fwd_ts_smem(int HB, int stages, int xbufs) {
+  return (size_t)xbufs * HB * VB_M * 128 + (size_t)stages * 2 * HB * 8192 + 16 * 32 * 4 +
          2 * 4 * VB_M * 4 + 256 + 1024;
 }
 
 int launch_vocab_fwd_ts(const CUtensorMap& tmX, const CUtensorMap& tmW, const VocabParams& p_in,
                         cudaStream_t st) {
   VocabParams p = p_in;
+  // a CTA with several segments double-buffers the X tile when shared memory allows (h <= 128)
+  p.x_bufs = (p.sched == SCHED_RANGES && p.h <= 128) ? 2 : 1;
   int stages = 4;
-  while (stages > 2 && fwd_ts_smem(p.HB, stages) > 227 * 1024) --stages;
-  B4CP_CHECK_ARG(fwd_ts_smem(p.HB, stages) <= 227 * 1024, "vocab_ce_fwd: h=%d does not fit", p.h);
+  while (stages > 2 && fwd_ts_smem(p.HB, stages, p.x_bufs) > 227 * 1024) --stages;
+  B4CP_CHECK_ARG(fwd_ts_smem(p.HB, stages, p.x_bufs) <= 227 * 1024, "vocab_ce_fwd: h=%d does not fit", p.h);
   p.fwd_stages = stages;
+  const size_t smem = fwd_ts_smem(p.HB, stages, p.x_bufs);
   dim3 grid(p.n_mtiles, p.n_chunks);
+  if (p.sched == SCHED_RANGES) grid = dim3((unsigned)ceil_div(p.total_tiles, p.range_q), 1);
   if (p.h <= 128) {
     B4CP_CUDA(cudaFuncSetAttribute(vocab_ce_fwd_ts_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    227 * 1024));
-    vocab_ce_fwd_ts_kernel<3><<<grid, TS_THREADS, fwd_ts_smem(p.HB, stages), st>>>(tmX, tmW, p);
+    vocab_ce_fwd_ts_kernel<3><<<grid, TS_THREADS, smem, st>>>(tmX, tmW, p);
   } else {
     B4CP_CUDA(cudaFuncSetAttribute(vocab_ce_fwd_ts_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    227 * 1024));
-    vocab_ce_fwd_ts_kernel<2><<<grid, TS_THREADS, fwd_ts_smem(p.HB, stages), st>>>(tmX, tmW, p);
+    vocab_ce_fwd_ts_kernel<2><<<grid, TS_THREADS, smem, st>>>(tmX, tmW, p);
   }
   return 0;
 }

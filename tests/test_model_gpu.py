@@ -267,7 +267,9 @@ def test_gpu_matches_committed_golden_cloze_step(cuda_lib, name, dims):
         want, _, _ = O.softmax_head_fwd(sel, O.head_layers(P64), P64["head.out.w"], P64["head.out.b"])
         assert probs.shape == z["probs"].shape == want.shape
         np.testing.assert_allclose(probs, want, rtol=5e-2, atol=1e-4)
-        dmodel = build_model(P, dims, L, H, 12, (16, 8), V, dropout=0.25, rows2=P["emb.1"].shape[0])
+        # (fp32-class mode: a tiny batch under bf16 operands is dominated by ReLU-gate flips)
+        dmodel = build_model(P, dims, L, H, 12, (16, 8), V, dropout=0.25, rows2=P["emb.1"].shape[0],
+                             precision="fp32")
         seed, d = 5, sum(dims)
         mk = lambda st: ops.dropout_mask(B * S * d, 0.25, seed, st).cpu().numpy().reshape(B, S, d).astype(np.float64)
         masks = {"in": mk(SITE_INPUT)}
@@ -276,9 +278,9 @@ def test_gpu_matches_committed_golden_cloze_step(cuda_lib, name, dims):
         st = dmodel.cloze_forward_backward(dev_ids, lab, B, S, n_masked=n_masked, training=True,
                                            seed=seed).cpu().numpy()
         loss, G2, _ = O.cloze_train_step(ids_list, z["labels"], P64, L, H, pe, np.float64, masks)
-        assert abs(st[0] / st[1] - loss) < 2e-2 * abs(loss)
+        assert abs(st[0] / st[1] - loss) < 1e-4 * abs(loss)
         eb = all_errs(to_reference_layout(dmodel.store.get_grads()), G2, G2)
-        assert max(eb.values()) < BF16_TOL, max(eb.items(), key=lambda kv: kv[1])
+        assert max(eb.values()) < 1e-3, max(eb.items(), key=lambda kv: kv[1])
         return
     stats = model.cloze_forward_backward(dev_ids, lab, B, S, n_masked=n_masked, training=False)
     s = stats.cpu().numpy()

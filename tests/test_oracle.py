@@ -358,3 +358,30 @@ def test_segment_binary_train_step_matches_finite_differences(segment, pw):
             # resolution would vanish, so the table check uses a looser bar
             tol = 2e-2 if k.startswith("emb.") else 1e-5
             assert abs(num - G[k][i]) < tol * max(abs(G[k][i]), 1e-6) + 1e-9, (k, i, num, G[k][i])
+
+
+def test_relu_gate_flips_limit_float32_agreement():
+    """Why the 1e-3 gradient bar is measured at well-conditioned weights (oracle/conditioning.py):
+    the oracle in float32 against itself in float64 on a C1-shaped model at random weights - pure
+    rounding, no implementation difference - already moves gradient entries by more than
+    rounding error wherever a ReLU pre-activation sits inside it; after `condition_relu_gates` the
+    same comparison is at float32 rounding level."""
+    from oracle.conditioning import condition_relu_gates, min_relu_margin
+    from bert4clickpath_b200.synthetic import make_cloze_batch
+    V, d, L, H, dff, hd, B = 3000, 64, 2, 2, 100, [256, 128], 48
+    P = O.init_params(np.random.default_rng(3), [V + 11], [d], L, dff, hd, V, dtype=np.float64)
+    P = {k: v.astype(np.float32).astype(np.float64) for k, v in P.items()}
+    batch = make_cloze_batch(np.random.default_rng(0), B, V, max_len=50, mode="train",
+                             masked_percentage=0.15)
+    ids, pe = [batch["ids"].astype(np.int64)], O.positional_encoding(10000, d)
+
+    def worst(Q):
+        _, G64, _ = O.cloze_train_step(ids, batch["labels"], Q, L, H, pe, np.float64)
+        _, G32, _ = O.cloze_train_step(ids, batch["labels"], Q, L, H, pe, np.float32)
+        return max(np.abs(G32[k] - G64[k]).max() / np.abs(G64[k]).max()
+                   for k in G64 if not k.endswith(".bk"))
+
+    Pc, nudged = condition_relu_gates(P, ids, L, H, pe, tau=1e-4)
+    assert min_relu_margin(Pc, ids, L, H, pe) >= 1e-4 and nudged > 0
+    assert max(np.abs(Pc[k] - P[k]).max() for k in P) < 5e-2     # only biases, by ~1e-2 at most
+    assert worst(Pc) < 2e-4                                       # float32 rounding level

@@ -9,13 +9,25 @@ per-tensor errors written to gpurun_out/parity_*.json (DESIGN.md section 5 quote
                  float64 oracle finishes in seconds; the V = 1M shape is covered by the
                  size-independent tests in test_zz_fullsize_gpu.py)
 
+Weights: the model's own random initial weights with biases / LayerNorm parameters moved off
+their 0 / 1 initial values, then CONDITIONED (oracle/conditioning.py): biases of ReLU units whose
+pre-activation on the test batch lies within 1e-4 of zero are nudged, because the gradient of a
+ReLU network is discontinuous there and ANY two correct fp32 implementations disagree on such
+gates (the oracle in float32 against itself in float64 is off by 1.7e-3 on C1 through one flipped
+gate: tests/test_oracle.py::test_relu_gate_flips_limit_float32_agreement).
+
 Two bars per configuration:
   * precision="fp32" (the parity mode: bf16 x 3 split products on the tcgen05 GEMM, fp32 attention,
     fp32 logits): loss, logits and EVERY gradient tensor within FP32_TOL = 1e-3 of the oracle -
     north_star's bar - in both the max-norm and the Frobenius norm, relative to the tensor's own
     scale.  The only floor is on the key bias, whose true gradient is identically zero (softmax is
     invariant to a per-query constant): its error is measured against the query-bias gradient.
-  * precision="bf16" (the fast path): the stated bf16 tolerances below, per norm.
+  * precision="bf16" (the fast path): the stated bf16 tolerances below, per norm.  They are
+    dominated not by rounding of values but by ReLU gates: a unit whose pre-activation lies within
+    bf16 operand rounding (~4e-3 relative) of zero takes the other branch, ~0.2 % of the units of
+    a layer, and each such layer adds sqrt(0.002) ~ 4.5 % in the Frobenius norm (C1 has four head
+    layers and two feed-forward layers in series).  Against the oracle that applies the SAME bf16
+    roundings (oracle/mixed_precision.py) - same gates - the kernels agree to EMU_TOL.
 """
 import json
 import os
@@ -29,9 +41,12 @@ from oracle import clickpath_oracle as O
 pytestmark = pytest.mark.gpu
 
 FP32_TOL = 1e-3            # north_star: losses, logits, gradients within 1e-3 relative in fp32
-BF16_LOSS_TOL = 2e-3       # fast path, measured <= 6e-4 on these configs
-BF16_FRO_TOL = 3e-2        # per-tensor Frobenius, measured <= 1.6e-2
-BF16_MAX_TOL = 6e-2        # per-tensor max-norm, measured <= 3.5e-2
+BF16_LOSS_TOL = 4e-3       # fast path; measured: C1 2e-8 .. 5e-7, C4 5e-6, C3 1.9e-3
+BF16_FRO_TOL = 0.30        # per-tensor Frobenius; measured worst: C1 0.15, C1 ragged 0.20, C3 0.05, C4 0.07
+BF16_MAX_TOL = 0.45        # per-tensor max-norm;  measured worst: C1 0.16, C1 ragged 0.31, C3 0.08, C4 0.11
+EMU_TOL = 8e-2             # bf16 path vs the oracle with the same bf16 roundings (Frobenius); measured
+                           # 4.4e-3 (C1 ragged) .. 4.7e-2 (C1 dense, C4: one gate of the bf16-rounded
+                           # network inside fp32-vs-float64 accumulation error moves every upstream tensor)
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -73,35 +88,43 @@ def check(name, precision, loss_err, errs, extra=None):
         assert worst_fro[1][1] < BF16_FRO_TOL, worst_fro
 
 
+def conditioned_weights(model, ids64, L, H, pe, head_rows, rng):
+    """Move 1-D parameters off their 0 / 1 initial values, condition the ReLU gates on this batch
+    (module docstring), load the result into the model and return it as float64."""
+    from oracle.conditioning import condition_relu_gates, min_relu_margin
+    from bert4clickpath_b200.weights import to_reference_layout, to_store_layout
+    w0 = to_reference_layout(model.store.get_weights())
+    P = {k: (v + rng.normal(scale=0.02, size=v.shape) if v.ndim == 1 else v).astype(np.float32).astype(np.float64)
+         for k, v in w0.items()}
+    P, nudged = condition_relu_gates(P, ids64, L, H, pe, head_rows=head_rows, tau=1e-4)
+    assert min_relu_margin(P, ids64, L, H, pe, head_rows) >= 1e-4
+    model.store.set_weights(to_store_layout({k: v.astype(np.float32) for k, v in P.items()}))
+    return P, nudged
+
+
 def cloze_case(name, precision, V, d, L, H, dff, hd, B, max_len, mp, max_masked, lengths):
     import bert4clickpath_b200 as bc
     from bert4clickpath_b200.synthetic import make_cloze_batch
     from bert4clickpath_b200.weights import to_reference_layout
+    from oracle.conditioning import masked_rows
     head = bc.SoftMaxHead(dense_layer_dims=hd, output_vocab_size=V)
     model = bc.ClickstreamTransformer(
         sequential_input_config={"items": ["asin"]}, feature_vocabs={"items": V},
         embedding_dims={"items": d}, head_unit=head, value_to_head=bc.INPUT_MASKING_TOKEN,
         num_encoder_layers=L, num_attention_heads=H, dropout_rate=0.0, encoder_ff_dim=dff,
         seed=3, precision=precision)
-    # biases / LayerNorm parameters off their zero / one initial values, so that every term of
-    # the backward is exercised
-    rng = np.random.default_rng(5)
-    w0 = model.store.get_weights()
-    bump = {k: (v + rng.normal(scale=0.02, size=v.shape)).astype(np.float32) for k, v in w0.items()
-            if v.ndim == 1}
-    model.store.set_weights(bump)
     batch = make_cloze_batch(np.random.default_rng(0), B, V, max_len=max_len, mode="train",
                              masked_percentage=mp, max_masked=max_masked, lengths=lengths)
+    ids64 = [batch["ids"].astype(np.int64)]
+    pe = O.positional_encoding(10000, d)
+    P, nudged = conditioned_weights(model, ids64, L, H, pe, masked_rows, np.random.default_rng(5))
     ids = torch.from_numpy(batch["ids"]).cuda().view(-1)
     labels = torch.from_numpy(batch["labels"]).cuda()
     Bq, S = batch["ids"].shape
     stats = model.cloze_forward_backward([ids], labels, Bq, S, n_masked=batch["n_masked"],
                                          training=False).cpu().numpy()
     got = to_reference_layout(model.store.get_grads())
-    P = {k: v.astype(np.float64) for k, v in to_reference_layout(model.store.get_weights()).items()}
-    pe = O.positional_encoding(10000, d)
-    loss, G, ex = O.cloze_train_step([batch["ids"].astype(np.int64)], batch["labels"], P, L, H, pe,
-                                     np.float64)
+    loss, G, ex = O.cloze_train_step(ids64, batch["labels"], P, L, H, pe, np.float64)
     assert stats[1] == ex["n_valid"] == batch["n_masked"]
     loss_err = abs(stats[0] / stats[1] - loss) / abs(loss)
     errs = tensor_errors(got, G, G)
@@ -111,8 +134,20 @@ def cloze_case(name, precision, V, d, L, H, dff, hd, B, max_len, mp, max_masked,
     want_z = ex["logits"][np.asarray(batch["labels"]).reshape(-1) >= 0]
     errs["logits"] = (float(np.abs(z - want_z).max() / np.abs(want_z).max()),
                       float(np.linalg.norm(z - want_z) / np.linalg.norm(want_z)))
-    check(name, precision, loss_err, errs, dict(S=int(S), B=int(Bq), rows=int(batch["n_masked"]),
-                                               loss=float(loss)))
+    extra = dict(S=int(S), B=int(Bq), rows=int(batch["n_masked"]), loss=float(loss),
+                 relu_units_nudged=int(nudged))
+    if precision == "bf16":
+        # the same step with bf16 rounding applied where the pipeline stores bf16: same gates
+        from oracle.mixed_precision import cloze_train_step_bf16
+        eloss, EG, _ = cloze_train_step_bf16(ids64, batch["labels"], P, L, H, pe)
+        emu = {k: v[1] for k, v in tensor_errors(got, EG, EG).items()}
+        extra["vs_bf16_emulating_oracle_fro"] = emu
+        extra["vs_bf16_emulating_oracle_worst"] = max(emu.items(), key=lambda kv: kv[1])
+        extra["vs_bf16_emulating_oracle_loss"] = abs(stats[0] / stats[1] - eloss) / abs(eloss)
+    check(name, precision, loss_err, errs, extra)
+    if precision == "bf16":
+        assert extra["vs_bf16_emulating_oracle_loss"] < 1e-4
+        assert extra["vs_bf16_emulating_oracle_worst"][1] < EMU_TOL, extra["vs_bf16_emulating_oracle_worst"]
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
@@ -154,23 +189,20 @@ def test_c3_multivariable_binary_head_matches_float64_oracle(cuda_lib, precision
         feature_vocabs={"items": Vi, "events": Va}, embedding_dims={"items": 112, "events": 16},
         head_unit=head, segment_to_head=0, num_encoder_layers=2, num_attention_heads=4,
         dropout_rate=0.0, seed=4, precision=precision)
-    w0 = model.store.get_weights()
-    bump = {k: (v + rng.normal(scale=0.02, size=v.shape)).astype(np.float32) for k, v in w0.items()
-            if v.ndim == 1}
-    model.store.set_weights(bump)
+    from oracle.conditioning import segment_rows
     ids_list, Bq, S, starts, ends = model.prepare_inputs({"s_items": items, "s_ev": acts})
     assert (Bq, S) == (B, Lx + 3)
+    ids64 = [t.view(B, S).cpu().numpy().astype(np.int64) for t in ids_list]
+    pe = O.positional_encoding(10000, 128)
+    P, nudged = conditioned_weights(model, ids64, 2, 4, pe, segment_rows(0), rng)
     y = rng.integers(0, 2, size=(B, 1)).astype(np.float32)
     stats = model.binary_forward_backward(ids_list, torch.from_numpy(y).cuda(), B, S, (starts, ends),
                                           pos_weight=pw, training=False).cpu().numpy()
     got = to_reference_layout(model.store.get_grads())
     probs = model._last_probs.cpu().numpy().astype(np.float64)
-    P = {k: v.astype(np.float64) for k, v in to_reference_layout(model.store.get_weights()).items()}
-    pe = O.positional_encoding(10000, 128)
-    ids64 = [t.view(B, S).cpu().numpy().astype(np.int64) for t in ids_list]
     loss, G, ex = O.segment_binary_train_step(ids64, y, P, 2, 4, pe, 0, pos_weight=pw)
     got_loss = stats[0] / stats[1] / ((pw + 1.0) / 2)
     errs = tensor_errors(got, G, G)
     errs["probs"] = (float(np.abs(probs - ex["probs"]).max() / np.abs(ex["probs"]).max()),
                      float(np.linalg.norm(probs - ex["probs"]) / np.linalg.norm(ex["probs"])))
-    check("c3", precision, abs(got_loss - loss) / abs(loss), errs, dict(S=int(S), B=B, loss=float(loss)))
+    check("c3", precision, abs(got_loss - loss) / abs(loss), errs, dict(S=int(S), B=B, loss=float(loss), relu_units_nudged=int(nudged)))
