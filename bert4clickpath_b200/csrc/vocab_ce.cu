@@ -23,10 +23,11 @@ int make_tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64
 // partials are (max, sum) in the log2 domain; lse is returned in natural units
 __global__ void __launch_bounds__(256)
 vocab_ce_merge_kernel(const float* __restrict__ part_max, const float* __restrict__ part_sum,
-                      int n_parts, int M, int V, const int32_t* __restrict__ labels,
+                      const VocabParams p, int M, int V, const int32_t* __restrict__ labels,
                       float* __restrict__ lse, float* __restrict__ tgt) {
   const int row = blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= M) return;
+  const int n_parts = 4 * vocab_row_slots(p, row);
   float m = -INFINITY;
   for (int c = 0; c < n_parts; ++c) m = fmaxf(m, part_max[(size_t)c * M + row]);
   float s = 0.f;
@@ -48,7 +49,7 @@ static constexpr int MAX_FWD_CHUNKS = 24;
 
 __global__ void __launch_bounds__(32 * DX_ROWS_PER_BLOCK)
 vocab_ce_dx_kernel(const float* __restrict__ part_max, const float* __restrict__ part_sum,
-                   const float* __restrict__ part_u, int n_chunks, int M, int h,
+                   const float* __restrict__ part_u, const VocabParams sp, int M, int h,
                    const int32_t* __restrict__ labels, const float* __restrict__ loss_stats,
                    const float* __restrict__ lse_global, int V,
                    const __nv_bfloat16* __restrict__ w, long ldw,
@@ -57,6 +58,7 @@ vocab_ce_dx_kernel(const float* __restrict__ part_max, const float* __restrict__
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * DX_ROWS_PER_BLOCK + (threadIdx.x >> 5);
   if (row >= M) return;
+  const int n_chunks = vocab_row_slots(sp, row);   // partial slots this row's tile holds
   const int label = labels[row];
   const float n_valid = loss_stats[1];
   const bool live = label >= 0 && n_valid > 0.f;
@@ -129,11 +131,10 @@ vocab_ce_dx_kernel(const float* __restrict__ part_max, const float* __restrict__
   }
 }
 
-// Vocabulary chunks per row tile.  One CTA per SM is resident, so the launch runs in waves of 148
-// CTAs and its critical path is waves x tiles-per-chunk tile iterations; every extra chunk adds
-// one more (max, sum, U) partial per row for vocab_ce_dx_kernel to read (~2.5 tile iterations of
-// HBM time).  Pick the count that minimises the sum instead of "about two waves" (448 CTAs = 3.03
-// waves at the bench shape cost a whole extra wave).
+// Vocabulary chunks per row tile (SCHED_GRID).  One CTA per SM is resident, so the launch runs in
+// waves of 148 CTAs and its critical path is waves x tiles-per-chunk tile iterations; every extra
+// chunk adds one more (max, sum, U) partial per row for vocab_ce_dx_kernel to read (~2.5 tile
+// iterations of HBM time).  Pick the count that minimises the sum instead of "about two waves".
 static int fwd_chunks(int n_mtiles, int n_vtiles, int* tiles_per_chunk) {
   int best = 1;
   double best_cost = 1e30;
@@ -149,14 +150,59 @@ static int fwd_chunks(int n_mtiles, int n_vtiles, int* tiles_per_chunk) {
   return best;
 }
 
+// The forward schedule for (M, V, h): fills sched / n_chunks (= partial slots per row, the
+// workspace stride) / tiles_per_chunk / range_q / total_tiles.  SCHED_RANGES (vocab_ce.cuh) when
+// the bf16 kernel fits L2 comfortably; the lock-step chunk grid otherwise.
+static constexpr long RANGES_MAX_W_BYTES = 32L << 20;
+static void plan_forward(long M, int V, int h, VocabParams* p) {
+  p->n_mtiles = ceil_div(M, VB_M);
+  p->n_vtiles = ceil_div(V, VB_N);
+  p->total_tiles = (long)p->n_mtiles * p->n_vtiles;
+  const char* force = getenv("B4CP_FWD_SCHED");   // developer switch: "grid" / "ranges"
+  const bool fits = (long)p->n_vtiles * VB_N * h * 2 <= RANGES_MAX_W_BYTES;
+  const bool ranges = force ? (force[0] == 'r') : fits;
+  if (ranges) {
+    // small M: fill the GPU, but keep a row tile within MAX_FWD_CHUNKS partial slots
+    const long q_min = std::max<long>(1, (p->n_vtiles + MAX_FWD_CHUNKS - 3) / (MAX_FWD_CHUNKS - 2));
+    long ctas = std::min<long>(148, std::max<long>(1, p->total_tiles / q_min));
+    const long q = (p->total_tiles + ctas - 1) / ctas;
+    int slots = 1;
+    for (int m = 0; m < p->n_mtiles; ++m) slots = std::max(slots, ranges_slots(q, p->n_vtiles, m));
+    if (slots <= MAX_FWD_CHUNKS) {
+      p->sched = SCHED_RANGES;
+      p->range_q = q;
+      p->n_chunks = slots;
+      p->tiles_per_chunk = 0;
+      return;
+    }
+  }
+  p->sched = SCHED_GRID;
+  p->range_q = 0;
+  p->n_chunks = fwd_chunks(p->n_mtiles, p->n_vtiles, &p->tiles_per_chunk);
+}
+
 }  // namespace b4cp
 
 using namespace b4cp;
 
 extern "C" long b4cp_vocab_ce_workspace_bytes(long M, int V, int h) {
-  int tpc;
-  const int chunks = fwd_chunks(ceil_div(M, VB_M), ceil_div(V, VB_N), &tpc);
-  return (long)(2 * 4 + h) * chunks * M * sizeof(float) + 256;
+  VocabParams p = {};
+  plan_forward(M, V, h, &p);
+  return (long)(2 * 4 + h) * p.n_chunks * M * sizeof(float) + 256;
+}
+
+// how the forward of (M, V, h) is scheduled: out[0] = schedule (0 grid / 1 ranges), out[1] = CTAs,
+// out[2] = partial slots per row (workspace stride), out[3] = tiles per CTA range (ranges) or per
+// chunk (grid).  Host-only; lets tests pin the planner's invariants without a device.
+extern "C" int b4cp_vocab_ce_plan(long M, int V, int h, long* out) {
+  B4CP_CHECK_ARG(out && M > 0 && V > 0 && h > 0, "vocab_ce_plan: bad argument");
+  VocabParams p = {};
+  plan_forward(M, V, h, &p);
+  out[0] = p.sched;
+  out[1] = p.sched == SCHED_RANGES ? ceil_div(p.total_tiles, p.range_q) : (long)p.n_mtiles * p.n_chunks;
+  out[2] = p.n_chunks;
+  out[3] = p.sched == SCHED_RANGES ? p.range_q : p.tiles_per_chunk;
+  return 0;
 }
 
 static int check_vocab_args(const void* x, long ldx, long M, int h, const void* w, long ldw, int V,
@@ -185,9 +231,7 @@ extern "C" int b4cp_vocab_ce_fwd(const void* x_bf16, long ldx, long M, int h, co
   p.V = V;
   p.h = h;
   p.HB = h / 64;
-  p.n_mtiles = ceil_div(M, VB_M);
-  p.n_vtiles = ceil_div(V, VB_N);
-  p.n_chunks = fwd_chunks(p.n_mtiles, p.n_vtiles, &p.tiles_per_chunk);
+  plan_forward(M, V, h, &p);
   p.bias = bias;
   p.labels = labels;
   p.part_max = (float*)workspace;
@@ -202,8 +246,8 @@ extern "C" int b4cp_vocab_ce_fwd(const void* x_bf16, long ldx, long M, int h, co
   if (rc) return rc;
   rc = launch_vocab_fwd_ts(tmX, tmW, p, st);
   if (rc) return rc;
-  vocab_ce_merge_kernel<<<ceil_div(M, 256), 256, 0, st>>>(p.part_max, p.part_sum, 4 * p.n_chunks,
-                                                          (int)M, V, labels, lse, tgt);
+  vocab_ce_merge_kernel<<<ceil_div(M, 256), 256, 0, st>>>(p.part_max, p.part_sum, p, (int)M, V,
+                                                          labels, lse, tgt);
   note_launches(2);
   B4CP_LAUNCH_CHECK();
   return 0;
@@ -218,14 +262,18 @@ extern "C" int b4cp_vocab_ce_dx(long M, int h, int V, const int32_t* labels,
   B4CP_CHECK_ARG(labels && loss_stats && w_bf16 && workspace && (out_f32 || out_bf16),
                  "vocab_ce_dx: null argument");
   if (M == 0) return 0;
-  int tpc;
-  const int chunks = fwd_chunks(ceil_div(M, VB_M), ceil_div(V, VB_N), &tpc);
+  VocabParams sp = {};
+  sp.M = (int)M;
+  sp.V = V;
+  sp.h = h;
+  plan_forward(M, V, h, &sp);
+  const int chunks = sp.n_chunks;
   const float* part_max = (const float*)workspace;
   const float* part_sum = part_max + (size_t)4 * chunks * M;
   const float* part_u = part_sum + (size_t)4 * chunks * M;
   B4CP_CHECK_ARG(ld_gate % 4 == 0 && ld_bf16 % 4 == 0, "vocab_ce_dx: leading dimensions must be multiples of 4");
   vocab_ce_dx_kernel<<<ceil_div(M, DX_ROWS_PER_BLOCK), 32 * DX_ROWS_PER_BLOCK, 0, (cudaStream_t)stream>>>(
-      part_max, part_sum, part_u, chunks, (int)M, h, labels, loss_stats, lse_global, V,
+      part_max, part_sum, part_u, sp, (int)M, h, labels, loss_stats, lse_global, V,
       (const __nv_bfloat16*)w_bf16, ldw, (const __nv_bfloat16*)gate_bf16, ld_gate, out_f32,
       (__nv_bfloat16*)out_bf16, ld_bf16);
   note_launches(1);

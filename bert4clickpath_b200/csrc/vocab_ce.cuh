@@ -15,6 +15,33 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
+// exp2 of two values on the FMA / ALU pipes (no MUFU): Cody-Waite range reduction with the
+// 1.5 * 2^23 magic constant (t = x + magic holds round(x) in its low mantissa bits, r = x - round(x)
+// in [-0.5, 0.5]), a degree-4 polynomial for 2^r (max relative error 7.2e-6, far inside the bf16
+// rounding of the probabilities it feeds) and the exponent spliced in with one integer
+// multiply-add.  The MUFU unit does 4 ex2 per clock per scheduler; a tile of the fused vocabulary
+// kernels needs 16,384 of them - as long as its two tensor-core products - so a share of the
+// exponentials is computed here instead, in packed fp32x2 arithmetic.
+__device__ __forceinline__ float2 ex2_poly2(float2 x) {
+  const float2 magic = make_float2(12582912.f, 12582912.f);
+  x.x = fmaxf(x.x, -125.f);
+  x.y = fmaxf(x.y, -125.f);
+  const float2 t = __fadd2_rn(x, magic);
+  const float2 n = __fadd2_rn(t, make_float2(-12582912.f, -12582912.f));
+  const float2 r = __fadd2_rn(x, make_float2(-n.x, -n.y));
+  float2 p = __ffma2_rn(r, make_float2(0.009666373953223228f, 0.009666373953223228f),
+                        make_float2(0.055838342756032944f, 0.055838342756032944f));
+  p = __ffma2_rn(p, r, make_float2(0.2402234822511673f, 0.2402234822511673f));
+  p = __ffma2_rn(p, r, make_float2(0.6931367516517639f, 0.6931367516517639f));
+  p = __ffma2_rn(p, r, make_float2(1.f, 1.f));
+  // 2^round(x): (bits(t) << 23) keeps exactly round(x) in the exponent field (the magic constant's
+  // own bits shift out), added to the exponent of p in [0.70, 1.42]
+  float2 y;
+  y.x = __int_as_float(__float_as_int(t.x) * 0x800000 + __float_as_int(p.x));
+  y.y = __int_as_float(__float_as_int(t.y) * 0x800000 + __float_as_int(p.y));
+  return y;
+}
+
 // Forward schedules.  A SEGMENT is a run of consecutive vocabulary tiles of ONE row tile processed
 // by one CTA; it ends with one (max, sum, U) partial per row in slot `slot` of that row tile.
 //   SCHED_GRID   grid = row tiles x vocabulary chunks, one segment per CTA, slot = chunk.  CTAs of

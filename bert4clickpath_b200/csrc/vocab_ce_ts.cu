@@ -28,6 +28,12 @@ namespace b4cp {
 
 static constexpr int TS_THREADS = 576;  // 16 epilogue warps + TMA warp + MMA warp
 static constexpr float RESCALE_TH = 8.f;
+// Forward kernel template parameter PP: one pair in every PP groups of four exponentials is
+// computed by ex2_poly2 instead of MUFU (2: a quarter of them - measured best; 1: half - the FMA
+// pipe then becomes the limiter; 0: none).
+static constexpr int FWD_POLY_DEFAULT = 2;
+// (the backward kernel keeps MUFU for all exponentials: its -inf arguments - padded rows - must
+// give exactly 0, and with two ping-pong epilogue groups the polynomial did not pay: 0.76 vs 0.73 ms)
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
@@ -80,7 +86,9 @@ __device__ __forceinline__ FwdSeg fwd_seg(const VocabParams& p, long L, long L1)
   return s;
 }
 
-template <int NSB>   // S accumulators in TMEM: 3 at h <= 128, 2 at h = 256
+// NSB: S accumulators in TMEM (3 at h <= 128, 2 at h = 256).  OPT: optimistic exponentials (below);
+// they hold the S buffer until the row maxima are agreed, which only pays with three buffers.
+template <int NSB, int PP, bool OPT>
 __global__ void __launch_bounds__(TS_THREADS, 1)
 vocab_ce_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmX,
                        const __grid_constant__ CUtensorMap tmW, const VocabParams p) {
@@ -152,7 +160,7 @@ vocab_ce_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmX,
   if (warp == WARP_TMA) {
     // whole warp, uniform control flow; the TMA instructions are predicated on an elected lane
     const uint32_t aX = smem_u32(sX), aW0 = smem_u32(sW);
-    long t = 0;
+    int t = 0;
     int sg = 0;
     for (long L = L_begin; L < L_end; ++sg) {
       const FwdSeg s = fwd_seg(p, L, L_end);
@@ -162,7 +170,7 @@ vocab_ce_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmX,
       for (int hb = 0; hb < HB; ++hb)
         tma_load_2d_el(aX + xb * x_bytes + hb * (VB_M * 128), &tmX, &x_full[xb], hb * 64, s.m * VB_M);
       for (int i = 0; i < s.len; ++i, ++t) {
-        const int st = (int)(t % NST);
+        const int st = t % NST;
         mbar_wait_all(&w_empty[st], (uint32_t)((t / NST) & 1) ^ 1);
         mbar_expect_tx_el(&w_full[st], (uint32_t)w_bytes);
         const int v0 = (s.v0 + i) * VB_N;
@@ -189,9 +197,9 @@ vocab_ce_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmX,
     int sgs = 0, sgu = 0, is = 0, iu = 0;         // segment index / tile index inside it
     int len_s = Ls < L_end ? fwd_seg(p, Ls, L_end).len : 0;
     int len_u = len_s;
-    const long n_total = L_end - L_begin;
-    auto issue_s = [&](long t) {
-      const int st = (int)(t % NST), buf = (int)(t % NSB), xb = sgs % XB;
+    const int n_total = (int)(L_end - L_begin);
+    auto issue_s = [&](int t) {
+      const int st = t % NST, buf = t % NSB, xb = sgs % XB;
       tc_fence_after();
       const uint32_t wo = (uint32_t)(st * w_bytes) >> 4;
       const uint32_t xo = (uint32_t)(xb * x_bytes) >> 4;
@@ -212,13 +220,13 @@ vocab_ce_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmX,
         len_s = Ls < L_end ? fwd_seg(p, Ls, L_end).len : 0;
       }
     };
-    auto s_ready = [&](long t) -> bool {
+    auto s_ready = [&](int t) -> bool {
       if (is == 0 && !mbar_test_all(&x_full[sgs % XB], (uint32_t)((sgs / XB) & 1))) return false;
       return mbar_test_all(&w_full[t % NST], (uint32_t)((t / NST) & 1)) &&
              mbar_test_all(&s_empty[t % NSB], (uint32_t)((t / NSB) & 1) ^ 1);
     };
-    auto issue_u = [&](long t) {
-      const int st = (int)(t % NST), buf = (int)(t % NSB);
+    auto issue_u = [&](int t) {
+      const int st = t % NST, buf = t % NSB;
       tc_fence_after();
       const uint32_t wo = (uint32_t)(st * w_bytes) >> 4;
       const uint32_t tP = tmem_base + buf * VB_N;
@@ -232,7 +240,7 @@ vocab_ce_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmX,
       umma_commit_el(&w_empty[st]);
     };
     if (!with_dx) {
-      for (long t = 0; t < n_total; ++t) {
+      for (int t = 0; t < n_total; ++t) {
         if (is == 0) mbar_wait_all(&x_full[sgs % XB], (uint32_t)((sgs / XB) & 1));
         mbar_wait_all(&w_full[t % NST], (uint32_t)((t / NST) & 1));
         mbar_wait_all(&s_empty[t % NSB], (uint32_t)((t / NSB) & 1) ^ 1);
@@ -246,7 +254,7 @@ vocab_ce_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmX,
       // U(t), hence the release of W(t)'s stage, hence the load of W(t+2): loads and tensor
       // work would serialise).  Order constraint: S(t+2) after U(t) - the tensor pipe executes
       // in issue order, so S(t+NSB) then cannot overwrite P'(t) before U(t) has read it.
-      long ts = 0, tu = 0;
+      int ts = 0, tu = 0;
       while (tu < n_total) {
         bool progressed = false;
         if (tu < ts && mbar_test_all(&p_full[tu % NSB], (uint32_t)((tu / NSB) & 1)) &&
@@ -278,7 +286,7 @@ vocab_ce_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmX,
     const uint32_t sb = smem_u32(sBias + warp * 32);
     const uint32_t aMax = smem_u32(sMax);
     const int uw = p.h >> 2;  // U columns owned by this warp: [cg*uw, +uw), 32 or 64
-    long t = 0;
+    int t = 0;      // tiles processed by this CTA (< 2^31)
     int sg = 0;
     for (long L = L_begin; L < L_end; ++sg) {
       const FwdSeg sgm = fwd_seg(p, L, L_end);
@@ -293,7 +301,7 @@ vocab_ce_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmX,
       };
       float bias_next = load_bias(0);
       for (int i = 0; i < sgm.len; ++i, ++t) {
-        const int buf = (int)(t % NSB);
+        const int buf = t % NSB;
         const uint32_t sph = (uint32_t)((t / NSB) & 1);   // accumulator buffer and its barrier phase
         const int vbase = (sgm.v0 + i) * VB_N + cg * 32;
         sts32f(sb + lane * 4, bias_next * LOG2E);
@@ -302,81 +310,123 @@ vocab_ce_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmX,
         mbar_wait(&s_full[buf], sph);
         tc_fence_after();
         const uint32_t tS = tmem_base + lane_base + (uint32_t)(buf * VB_N + cg * 32);
-        uint32_t r[32];
-        tmem_ld32(tS, r);
-        tmem_ld_wait();
-        tc_fence_before();
-        mbar_arrive_warp(&s_empty[buf]);
         float z[32];
-        float cmax = -INFINITY;
+        // z2 = s * log2(e) + b2 for this thread's 32 scores (packed fp32x2 FMAs), optional maximum
+        auto load_scores = [&](float& cmax) {
+          uint32_t r[32];
+          tmem_ld32(tS, r);
+          tmem_ld_wait();
+          const float2 l2 = make_float2(LOG2E, LOG2E);
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const float4 b4 = lds128f(sb + j * 4);
-          z[j + 0] = fmaf(__uint_as_float(r[j + 0]), LOG2E, b4.x);
-          z[j + 1] = fmaf(__uint_as_float(r[j + 1]), LOG2E, b4.y);
-          z[j + 2] = fmaf(__uint_as_float(r[j + 2]), LOG2E, b4.z);
-          z[j + 3] = fmaf(__uint_as_float(r[j + 3]), LOG2E, b4.w);
-          cmax = fmaxf(cmax, fmaxf(fmaxf(z[j], z[j + 1]), fmaxf(z[j + 2], z[j + 3])));
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b4 = lds128f(sb + j * 4);
+            const float2 za = __ffma2_rn(make_float2(__uint_as_float(r[j + 0]), __uint_as_float(r[j + 1])), l2,
+                                         make_float2(b4.x, b4.y));
+            const float2 zb = __ffma2_rn(make_float2(__uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])), l2,
+                                         make_float2(b4.z, b4.w));
+            z[j + 0] = za.x; z[j + 1] = za.y; z[j + 2] = zb.x; z[j + 3] = zb.y;
+            cmax = fmaxf(cmax, fmaxf(fmaxf(za.x, za.y), fmaxf(zb.x, zb.y)));
+          }
+        };
+        // z <- exp2(z - ref) in place; returns the sum of the 32 values
+        auto exponentiate = [&](float ref) -> float {
+          const float2 nr = make_float2(-ref, -ref);
+          float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float2 da = __fadd2_rn(make_float2(z[j + 0], z[j + 1]), nr);
+            const float2 db = __fadd2_rn(make_float2(z[j + 2], z[j + 3]), nr);
+            z[j + 0] = ex2(da.x); z[j + 1] = ex2(da.y);
+            if (PP > 0 && (j / 4) % (PP > 0 ? PP : 1) == (PP > 0 ? PP : 1) - 1) {   // this pair on the FMA / ALU pipes
+              const float2 e = ex2_poly2(db);
+              z[j + 2] = e.x; z[j + 3] = e.y;
+            } else {
+              z[j + 2] = ex2(db.x); z[j + 3] = ex2(db.y);
+            }
+            acc0 = __fadd2_rn(acc0, make_float2(z[j + 0], z[j + 1]));
+            acc1 = __fadd2_rn(acc1, make_float2(z[j + 2], z[j + 3]));
+          }
+          return (acc0.x + acc0.y) + (acc1.x + acc1.y);
+        };
+        float cmax = -INFINITY;
+        load_scores(cmax);
+        if (!OPT || !with_dx) {   // scores are in registers for good: release the accumulator now
+          tc_fence_before();
+          mbar_arrive_warp(&s_empty[buf]);
         }
-        __syncwarp();  // sb is rewritten for the next tile
         if (label >= vbase && label < vbase + 32) {
 #pragma unroll
           for (int j = 0; j < 32; ++j)
             if (vbase + j == label) tgt2 = z[j];
           have_tgt = true;
         }
-        if (with_dx) {
-          // the 4 warps that share these rows agree on one running maximum per row
-          const uint32_t mx = aMax + (uint32_t)((int)(t & 1) * (4 * VB_M) + r_in_tile) * 4;
+        float tile_sum;
+        if (!with_dx) {
+          // loss only: every thread keeps its own (max, sum) over its column slices
+          const float m_new = fmaxf(m_run, cmax);
+          const float alpha = m_ref > -INFINITY ? ex2(m_ref - m_new) : 0.f;
+          s_run *= alpha;
+          m_ref = m_run = m_new;
+          tile_sum = exponentiate(m_ref);
+        } else {
+          // OPTIMISTIC exponentials: P' is taken against the reference maximum agreed on earlier
+          // tiles, BEFORE the four warps that share these rows have exchanged this tile's
+          // maxima.  The exchange (a 128-thread barrier) used to sit between the TMEM load and the
+          // exponentials and re-aligned the four warps of a scheduler on every tile, so the TMEM
+          // read phase (64 B/clk: 1,024 clk per tile) and the MUFU phase (1,024 clk) of a tile ran
+          // back to back instead of overlapping across warps.  Only when some row's maximum has
+          // moved past the reference by more than 2^RESCALE_TH (rare), or on the first tile of a
+          // segment (no reference yet), are the scores read from TMEM again and redone.
+          const bool first = (i == 0);
+          const uint32_t mx = aMax + (uint32_t)((t & 1) * (4 * VB_M) + r_in_tile) * 4;
           sts32f(mx + cg * VB_M * 4, cmax);
+          if (OPT && !first) tile_sum = exponentiate(m_ref);
           asm volatile("bar.sync %0, 128;" ::"r"(2 + q) : "memory");
           cmax = fmaxf(fmaxf(lds32f(mx), lds32f(mx + VB_M * 4)),
                        fmaxf(lds32f(mx + 2 * VB_M * 4), lds32f(mx + 3 * VB_M * 4)));
-        }
-        const float m_new = fmaxf(m_run, cmax);
-        if (!with_dx) {
-          const float alpha = m_ref > -INFINITY ? ex2(m_ref - m_new) : 0.f;
-          s_run *= alpha;
-          m_ref = m_new;
-        } else if (i == 0) {
-          m_ref = m_new;  // nothing accumulated yet in this segment
-        } else {
-          const bool jump = m_new > m_ref + RESCALE_TH;
-          if (__any_sync(0xffffffffu, jump)) {
-            // rare: U(..t-1) must have retired before its columns are rescaled in TMEM; U(t)
-            // cannot start before p_full(t), which this warp only signals after the rescale
-            mbar_wait(&u_full[(t - 1) % NSB], (uint32_t)(((t - 1) / NSB) & 1));
-            tc_fence_after();
-            const float f = jump ? ex2(m_ref - m_new) : 1.f;
+          const float m_new = fmaxf(m_run, cmax);
+          m_run = m_new;
+          bool redo = first;
+          if (first) {
+            m_ref = m_new;  // nothing accumulated yet in this segment
+          } else {
+            const bool jump = m_new > m_ref + RESCALE_TH;
+            if (__any_sync(0xffffffffu, jump)) {
+              // U(..t-1) must have retired before its columns are rescaled in TMEM; U(t) cannot
+              // start before p_full(t), which this warp only signals after the rescale
+              mbar_wait(&u_full[(t - 1) % NSB], (uint32_t)(((t - 1) / NSB) & 1));
+              tc_fence_after();
+              const float f = jump ? ex2(m_ref - m_new) : 1.f;
 #pragma unroll 1
-            for (int c = 0; c < uw; c += 8) {  // 8 columns at a time: keeps z[] in registers
-              const uint32_t tU = T_U + lane_base + (uint32_t)(cg * uw + c);
-              uint32_t u[8];
-              tmem_ld8(tU, u);
-              tmem_ld_wait();
+              for (int c = 0; c < uw; c += 8) {  // 8 columns at a time: keeps z[] in registers
+                const uint32_t tU = T_U + lane_base + (uint32_t)(cg * uw + c);
+                uint32_t u[8];
+                tmem_ld8(tU, u);
+                tmem_ld_wait();
 #pragma unroll
-              for (int j = 0; j < 8; ++j) u[j] = __float_as_uint(__uint_as_float(u[j]) * f);
-              tmem_st8(tU, u);
+                for (int j = 0; j < 8; ++j) u[j] = __float_as_uint(__uint_as_float(u[j]) * f);
+                tmem_st8(tU, u);
+              }
+              tmem_st_wait();
+              s_run *= f;
+              if (jump) m_ref = m_new;
+              redo = true;
             }
-            tmem_st_wait();
-            s_run *= f;
-            if (jump) m_ref = m_new;
+          }
+          if (!OPT) {
+            tile_sum = exponentiate(m_ref);   // statistics first, exponentials after the exchange
+          } else if (redo) {   // S(t) is still in TMEM (released below): recompute against the new reference
+            float unused = -INFINITY;
+            load_scores(unused);
+            tile_sum = exponentiate(m_ref);
           }
         }
-        m_run = m_new;
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          z[j + 0] = ex2(z[j + 0] - m_ref);
-          z[j + 1] = ex2(z[j + 1] - m_ref);
-          z[j + 2] = ex2(z[j + 2] - m_ref);
-          z[j + 3] = ex2(z[j + 3] - m_ref);
-          a0 += z[j + 0];
-          a1 += z[j + 1];
-          a2 += z[j + 2];
-          a3 += z[j + 3];
+        if (OPT && with_dx) {
+          tc_fence_before();
+          mbar_arrive_warp(&s_empty[buf]);
         }
-        s_run += (a0 + a1) + (a2 + a3);
+        __syncwarp();   // sb is rewritten for the next tile
+        s_run += tile_sum;
         if (with_dx) {
           uint32_t pk[16];
 #pragma unroll
@@ -734,15 +784,31 @@ int launch_vocab_fwd_ts(const CUtensorMap& tmX, const CUtensorMap& tmW, const Vo
   const size_t smem = fwd_ts_smem(p.HB, stages, p.x_bufs);
   dim3 grid(p.n_mtiles, p.n_chunks);
   if (p.sched == SCHED_RANGES) grid = dim3((unsigned)ceil_div(p.total_tiles, p.range_q), 1);
+  int pp = FWD_POLY_DEFAULT;
+  if (const char* e = getenv("B4CP_FWD_POLY")) pp = atoi(e);   // developer switch: 0 / 2
+  // optimistic exponentials: 0.88 -> 0.837 ms on their own at the C1 shape, but once a
+  // quarter of the exponentials is off the MUFU unit the plain order is as fast (0.78 vs 0.80 ms
+  // at C1, 6.81 vs 6.85 ms at C4) and releases the S accumulator earlier: off by default
+  bool opt = false;
+  if (const char* e = getenv("B4CP_FWD_OPT")) opt = atoi(e) != 0;   // developer switch
+#define B4CP_LAUNCH_FWD(NSB_, PP_, OPT_)                                                            \
+  do {                                                                                              \
+    B4CP_CUDA(cudaFuncSetAttribute(vocab_ce_fwd_ts_kernel<NSB_, PP_, OPT_>,                         \
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));       \
+    vocab_ce_fwd_ts_kernel<NSB_, PP_, OPT_><<<grid, TS_THREADS, smem, st>>>(tmX, tmW, p);           \
+  } while (0)
   if (p.h <= 128) {
-    B4CP_CUDA(cudaFuncSetAttribute(vocab_ce_fwd_ts_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   227 * 1024));
-    vocab_ce_fwd_ts_kernel<3><<<grid, TS_THREADS, smem, st>>>(tmX, tmW, p);
+    if (pp == 2 && opt) B4CP_LAUNCH_FWD(3, 2, true);
+    else if (pp == 2) B4CP_LAUNCH_FWD(3, 2, false);
+    else if (opt) B4CP_LAUNCH_FWD(3, 0, true);
+    else B4CP_LAUNCH_FWD(3, 0, false);
   } else {
-    B4CP_CUDA(cudaFuncSetAttribute(vocab_ce_fwd_ts_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   227 * 1024));
-    vocab_ce_fwd_ts_kernel<2><<<grid, TS_THREADS, smem, st>>>(tmX, tmW, p);
+    if (pp == 2 && opt) B4CP_LAUNCH_FWD(2, 2, true);
+    else if (pp == 2) B4CP_LAUNCH_FWD(2, 2, false);
+    else if (opt) B4CP_LAUNCH_FWD(2, 0, true);
+    else B4CP_LAUNCH_FWD(2, 0, false);
   }
+#undef B4CP_LAUNCH_FWD
   return 0;
 }
 

@@ -253,6 +253,11 @@ int b4cp_ce_rows_grad_f32(float* logits, long ld, long M, int V, const int32_t* 
  *      dZ, with dZ = (softmax - onehot)/n on valid rows recomputed tile by tile.  h must be 128.
  */
 long b4cp_vocab_ce_workspace_bytes(long M, int V, int h);
+/* host-only: how the forward of (M, V, h) is scheduled.  out[0] = 0: grid of (row tile x vocabulary
+ * chunk) CTAs sweeping W in lock step (W larger than L2), 1: <= 148 persistent CTAs over contiguous
+ * ranges of the (row tile, vocabulary tile) space (W fits L2); out[1] = CTAs; out[2] = partial
+ * (max, sum, U) slots per row in the workspace; out[3] = tiles per range / per chunk. */
+int b4cp_vocab_ce_plan(long M, int V, int h, long* out);
 int b4cp_vocab_ce_fwd(const void* x_bf16, long ldx, long M, int h, const void* w_bf16, long ldw,
                       const float* bias, int V, const int32_t* labels, int want_dx, float* lse,
                       float* tgt, void* workspace, void* stream);

@@ -436,3 +436,40 @@ def test_oracle_reproduces_golden_sigmoid_heads_and_keyed_cloze():
     from bert4clickpath_b200.build import build_lib
     build_lib(verbose=False)
     assert [ops.cloze_position_key(1234, 3, i) for i in range(4)] == [int(v) for v in k["keys_s3"]]
+
+
+def test_vocab_forward_planner_invariants():
+    """b4cp_vocab_ce_plan (host-only): under the persistent-range schedule every (row tile,
+    vocabulary tile) is covered exactly once, a CTA's pieces of a row tile land in distinct slots
+    below the reported slot count, and the lock-step grid is kept when W does not fit L2."""
+    import ctypes
+    from bert4clickpath_b200 import _lib
+    L = _lib.lib()
+    out = (ctypes.c_long * 4)()
+    for M, V, h in [(28672, 54293, 128), (448, 54293, 128), (7168, 54293, 128), (232, 20000, 256),
+                    (1, 1, 128), (129, 257, 64), (100000, 54293, 128), (5000, 130000, 128)]:
+        assert L.b4cp_vocab_ce_plan(ctypes.c_long(M), V, h, out) == 0
+        sched, ctas, slots, q = list(out)
+        n_m, n_v = -(-M // 128), -(-V // 128)
+        assert 1 <= slots <= 24
+        if sched == 0:
+            assert ctas == n_m * slots and q * slots >= n_v
+            continue
+        total = n_m * n_v
+        assert ctas == -(-total // q) <= 148
+        seen = {}
+        for k in range(ctas):
+            lo, hi = k * q, min((k + 1) * q, total)
+            while lo < hi:
+                m, v0 = divmod(lo, n_v)
+                ln = min(n_v - v0, hi - lo)
+                slot = k - (m * n_v) // q
+                assert 0 <= slot < slots and (m, slot) not in seen
+                seen[(m, slot)] = (v0, ln)
+                lo += ln
+        for m in range(n_m):     # the slots of a row tile tile its vocabulary range, in order
+            pieces = sorted(v for (mm, s), v in seen.items() if mm == m)
+            assert pieces[0][0] == 0 and sum(p[1] for p in pieces) == n_v
+            n_slots_m = ((m + 1) * n_v - 1) // q - (m * n_v) // q + 1
+            assert len(pieces) == n_slots_m
+    assert L.b4cp_vocab_ce_plan(ctypes.c_long(7424), 1_000_000, 256, out) == 0 and out[0] == 0
