@@ -299,11 +299,20 @@ class ClickstreamTransformer:
         """Sum over the data-parallel group.  async_op=True returns the pending work (or None on
         one rank): the collective runs on NCCL's stream while this stream carries on with the
         rest of the backward, and `_finish_reduce` makes this stream wait for it."""
+        import os
         import torch.distributed as dist
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.process_group) > 1:
+            if os.environ.get("B4CP_DP_OVERLAP") == "0":   # developer switch: A/B the overlap
+                async_op = False
             return dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.process_group,
                                    async_op=async_op)
         return None
+
+    def _dp_world(self):
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_world_size(self.process_group)
+        return 1
 
     def _reduce_gradients(self, early=()):
         """All-reduce every replicated gradient that is not reduced yet (`early`: names whose
@@ -325,15 +334,27 @@ class ClickstreamTransformer:
         all-reduced when a process group is set, so loss = stats[0] / stats[1] is the GLOBAL
         masked mean."""
         assert isinstance(self.head, SoftMaxHead) and self.value_to_head is not None
+        vocab, mlp = self.head.vocab, self.head.mlp
+        dp = self._dp_world() > 1 and not getattr(vocab, "stats_are_global", False)
+        labels = n_global = count_work = None
+        if dp and n_masked is not None:
+            # data parallel: the backward needs the GLOBAL number of valid rows and nothing else
+            # from the other ranks, and that count depends on the labels alone - reduce it now, on
+            # NCCL's stream, while the forward runs (it used to be a 2-float all-reduce between
+            # the loss and the backward: ~25 us of exposed latency per step)
+            labels, n_global = ops.compact_labels(labels_f32, int(n_masked))
+            count_work = self._allreduce(n_global, async_op=True)
         out = self.forward_ids(ids_list, B, S, training, seed, n_masked=n_masked,
                                rows_are_common=rows_are_common)
         cap = out.M
-        labels, _ = ops.compact_labels(labels_f32, cap)
+        if labels is None or labels.numel() != cap:
+            labels, n_global = ops.compact_labels(labels_f32, cap)
+            count_work = self._allreduce(n_global, async_op=True) if dp else None
         stats = self.pool.get("loss_stats", (2,))
-        vocab, mlp = self.head.vocab, self.head.mlp
-        vocab.loss_forward(out.ab, cap, labels, stats)
-        if not getattr(vocab, "stats_are_global", False):
-            self._allreduce(stats)
+        self._finish_reduce([count_work])
+        vocab.loss_forward(out.ab, cap, labels, stats, n_global=n_global if dp else None)
+        # the loss SUM is only reported: its all-reduce rides behind the backward
+        sum_work = self._allreduce(stats[0:1], async_op=True) if dp else None
         d = self.d_model
         dsel = self.pool.get("dsel", (cap, d))
         # the output kernel's gradient (the largest tensor: 28 of 45 MB at C1) is final as soon as
@@ -353,7 +374,7 @@ class ClickstreamTransformer:
         ops.scatter_rows(dsel, out.row_index, dx)
         self.transformer.engine.backward(dx, self.process_group)
         self._reduce_gradients(early)
-        self._finish_reduce(works)
+        self._finish_reduce(works + [sum_work])
         self._last_output = out
         self._last_labels = labels
         return stats

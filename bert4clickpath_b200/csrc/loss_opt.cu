@@ -61,7 +61,8 @@ ce_rows_stats_kernel(const float* __restrict__ logits, long ld, int V,
 // out[0] += 0 ; writes out[0] = sum over valid rows of (lse - tgt), out[1] = number of valid rows
 __global__ void __launch_bounds__(1024)
 ce_loss_reduce_kernel(const float* __restrict__ lse, const float* __restrict__ tgt,
-                      const int32_t* __restrict__ labels, long M, float* __restrict__ out) {
+                      const int32_t* __restrict__ labels, long M, const int32_t* __restrict__ n_global,
+                      float* __restrict__ out) {
   __shared__ double s_loss[1024];
   __shared__ int s_n[1024];
   double a = 0.0;
@@ -84,7 +85,7 @@ ce_loss_reduce_kernel(const float* __restrict__ lse, const float* __restrict__ t
   }
   if (threadIdx.x == 0) {
     out[0] = (float)s_loss[0];
-    out[1] = (float)s_n[0];
+    out[1] = n_global ? (float)*n_global : (float)s_n[0];
   }
 }
 
@@ -295,7 +296,17 @@ extern "C" int b4cp_ce_rows_stats(const float* logits, long ld, long M, int V,
 
 extern "C" int b4cp_ce_loss_reduce(const float* lse, const float* tgt, const int32_t* labels,
                                    long M, float* loss_stats, void* stream) {
-  ce_loss_reduce_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(lse, tgt, labels, M, loss_stats);
+  ce_loss_reduce_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(lse, tgt, labels, M, nullptr, loss_stats);
+  note_launches(1);
+  B4CP_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int b4cp_ce_loss_reduce_n(const float* lse, const float* tgt, const int32_t* labels,
+                                     long M, const int32_t* n_global, float* loss_stats,
+                                     void* stream) {
+  B4CP_CHECK_ARG(n_global, "ce_loss_reduce_n: n_global required");
+  ce_loss_reduce_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(lse, tgt, labels, M, n_global, loss_stats);
   note_launches(1);
   B4CP_LAUNCH_CHECK();
   return 0;

@@ -373,6 +373,200 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// FILTER kernel of the long-vocabulary path, second generation.  Same job as
+// score_topk_kernel<., true> (append every score above the row's seed threshold to the row's
+// candidate list), built like the fused vocabulary forward: 16 epilogue warps (warp (q, cg) owns
+// TMEM lanes [32q, +32) x columns [32cg, +32) of a 128 x 128 score tile, 4 per scheduler), one TMA
+// warp, one MMA warp, FOUR score accumulators in TMEM (no second product here, so all 512 columns
+// hold scores and the tensor pipe runs three tiles ahead of the epilogue).  The common case of a
+// thread - none of its 32 scores beats the threshold - is 16 packed adds, a max tree and one warp
+// vote; survivors (~k V / seed per row over the whole sweep) go straight to the row's list with
+// one global atomic each.  The first-generation kernel walked a row's 128 scores in ONE thread
+// (4 epilogue warps) and measured 10 % tensor-pipe activity.
+static constexpr int SF_THREADS = 576, SF_NSB = 4, SF_EPI_WARPS = 16;
+static constexpr int SF_Q = 6;   // survivors a thread stages in shared memory before one global atomic
+
+// Stage (sc, id) in this thread's shared-memory queue ([slot][thread]: conflict-free); when the
+// queue is full (or with force) ONE global atomic reserves the slots in the row's list and the
+// staged pairs are written out.  Not inlined: the caller tests 32 scores per tile in unrolled
+// code, and survivors are rare (~k V / seed per row over the whole sweep).  Returns the new count.
+__device__ __noinline__ int filter_stage16(uint32_t aQ, int n_staged, float sc, int id, bool force,
+                                           int* cnt, float* cand_scores, int32_t* cand_ids, int k,
+                                           int cap) {
+  constexpr uint32_t SLOT = SF_EPI_WARPS * 32 * 8;   // bytes between queue slots
+  if (!force) {
+    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(aQ + (uint32_t)n_staged * SLOT),
+                 "r"(__float_as_uint(sc)), "r"(id) : "memory");
+    if (++n_staged < SF_Q) return n_staged;
+  }
+  const int base = k + atomicAdd(cnt, n_staged);
+  for (int i = 0; i < n_staged; ++i) {
+    const uint2 e = lds64(aQ + (uint32_t)i * SLOT);
+    if (base + i < cap) {   // (an overflowing row is detected from its counter and redone)
+      cand_scores[base + i] = __uint_as_float(e.x);
+      cand_ids[base + i] = (int32_t)e.y;
+    }
+  }
+  return 0;
+}
+
+__global__ void __launch_bounds__(SF_THREADS, 1)
+score_filter_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
+                    const ScoreParams p, int n_stages) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  const int HB = p.HB, k = p.k, NST = n_stages;
+  const int x_bytes = HB * ST_M * 128;
+  const int w_bytes = 2 * HB * 64 * 128;
+  uint8_t* sX = smem;
+  uint8_t* sW = sX + x_bytes;
+  float* sBias = reinterpret_cast<float*>(sW + (size_t)NST * w_bytes);   // [16 warps][32]
+  uint2* sQueue = reinterpret_cast<uint2*>(sBias + SF_EPI_WARPS * 32);   // [SF_Q][512 threads]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sQueue + SF_Q * SF_EPI_WARPS * 32);
+  uint64_t* x_full = bars;
+  uint64_t* w_full = bars + 1;            // [4]
+  uint64_t* w_empty = w_full + 4;         // [4]
+  uint64_t* s_full = w_empty + 4;         // [4]
+  uint64_t* s_empty = s_full + SF_NSB;    // [4]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_empty + SF_NSB);
+  constexpr int WARP_TMA = 16, WARP_MMA = 17;
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // provably warp-uniform
+  const int lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * ST_M;
+  const int t_begin = (int)blockIdx.y * p.tiles_per_chunk;
+  const int t_end = min(p.n_vtiles, t_begin + p.tiles_per_chunk);
+  const int ntiles = t_end - t_begin;
+
+  if (warp == WARP_TMA) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmX);
+      tma_prefetch_desc(&tmW);
+    }
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  } else if (warp == WARP_MMA && lane == 0) {
+    mbar_init(x_full, 1);
+    for (int s = 0; s < 4; ++s) {
+      mbar_init(&w_full[s], 1);
+      mbar_init(&w_empty[s], 1);
+    }
+    for (int b = 0; b < SF_NSB; ++b) {
+      mbar_init(&s_full[b], 1);
+      mbar_init(&s_empty[b], SF_EPI_WARPS);
+    }
+    fence_barrier_init();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+
+  if (warp == WARP_TMA) {
+    // whole warp, uniform control flow; TMA instructions predicated on an elected lane
+    const uint32_t aX = smem_u32(sX), aW0 = smem_u32(sW);
+    mbar_expect_tx_el(x_full, (uint32_t)x_bytes);
+    for (int hb = 0; hb < HB; ++hb) tma_load_2d_el(aX + hb * (ST_M * 128), &tmX, x_full, hb * 64, m0);
+    for (int t = 0; t < ntiles; ++t) {
+      const int st = t % NST;
+      mbar_wait_all(&w_empty[st], (uint32_t)((t / NST) & 1) ^ 1);
+      mbar_expect_tx_el(&w_full[st], (uint32_t)w_bytes);
+      const int v0 = (p.tile0 + t_begin + t) * ST_N;
+      const uint32_t dst = aW0 + (uint32_t)(st * w_bytes);
+      for (int vb = 0; vb < 2; ++vb)
+        for (int hb = 0; hb < HB; ++hb)
+          tma_load_2d_el(dst + (vb * HB + hb) * 8192, &tmW, &w_full[st], v0 + vb * 64, hb * 64);
+    }
+  } else if (warp == WARP_MMA) {
+    // the WHOLE warp issues, in uniform control flow (see umma_bf16_el in common.cuh)
+    const uint32_t idesc = umma_idesc_bf16(ST_M, ST_N, 0, 1);
+    const uint64_t dX = umma_smem_desc(smem_u32(sX), 16, 1024);               // X, K-major
+    const uint64_t dW = umma_smem_desc(smem_u32(sW), HB * 8192, 1024);        // W, MN-major
+    mbar_wait_all(x_full, 0);
+    for (int t = 0; t < ntiles; ++t) {
+      const int st = t % NST, buf = t % SF_NSB;
+      mbar_wait_all(&w_full[st], (uint32_t)((t / NST) & 1));
+      mbar_wait_all(&s_empty[buf], (uint32_t)((t / SF_NSB) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t wo = (uint32_t)(st * w_bytes) >> 4;
+      for (int hb = 0; hb < HB; ++hb) {
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          umma_bf16_el(tmem_base + buf * ST_N, dX + (uint32_t)((hb * (ST_M * 128) + kk * 32) >> 4),
+                       dW + (wo + (uint32_t)((hb * 8192 + kk * 2048) >> 4)), idesc, (hb | kk) ? 1u : 0u);
+      }
+      umma_commit_el(&w_empty[st]);
+      umma_commit_el(&s_full[buf]);
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (16 warps)
+    const int q = warp & 3, cg = warp >> 2;
+    const int row = m0 + q * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    const uint32_t sb = smem_u32(sBias + warp * 32);
+    const long crow = (long)row * p.cap;
+    // the threshold is the seed's k-th best score; a later id with an equal score loses the tie
+    // (ids only grow), so "strictly greater" is exact.  Rows past M never pass.
+    const float tau = row < p.M ? p.cand_scores[crow + k - 1] : INFINITY;
+    const uint32_t aQ = smem_u32(sQueue) + (uint32_t)(warp * 32 + lane) * 8;
+    int n_staged = 0;
+    auto load_bias = [&](int t) -> float {
+      const int v = (p.tile0 + t_begin + t) * ST_N + cg * 32 + lane;
+      return (t < ntiles && v < p.V) ? __ldg(p.bias + v) : -INFINITY;
+    };
+    float bias_next = load_bias(0);
+    for (int t = 0; t < ntiles; ++t) {
+      const int buf = t % SF_NSB;
+      const int vbase = (p.tile0 + t_begin + t) * ST_N + cg * 32;
+      sts32f(sb + lane * 4, bias_next);
+      __syncwarp();
+      bias_next = load_bias(t + 1);   // in flight while this tile is processed
+      mbar_wait(&s_full[buf], (uint32_t)((t / SF_NSB) & 1));
+      tc_fence_after();
+      uint32_t r[32];
+      tmem_ld32(tmem_base + lane_base + (uint32_t)(buf * ST_N + cg * 32), r);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive_warp(&s_empty[buf]);
+      float sc[32];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 b4 = lds128f(sb + j * 4);
+        const float2 a = __fadd2_rn(make_float2(__uint_as_float(r[j + 0]), __uint_as_float(r[j + 1])),
+                                    make_float2(b4.x, b4.y));
+        const float2 b = __fadd2_rn(make_float2(__uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])),
+                                    make_float2(b4.z, b4.w));
+        sc[j + 0] = a.x; sc[j + 1] = a.y; sc[j + 2] = b.x; sc[j + 3] = b.y;
+        mx = fmaxf(mx, fmaxf(fmaxf(a.x, a.y), fmaxf(b.x, b.y)));
+      }
+      __syncwarp();   // sb is rewritten for the next tile
+      if (__any_sync(0xffffffffu, mx > tau)) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (sc[j] > tau)
+            n_staged = filter_stage16(aQ, n_staged, sc[j], vbase + j, false, p.cand_cnt + row,
+                                      p.cand_scores + crow, p.cand_ids + crow, k, p.cap);
+      }
+    }
+    if (n_staged > 0)
+      filter_stage16(aQ, n_staged, 0.f, 0, true, p.cand_cnt + row, p.cand_scores + crow,
+                     p.cand_ids + crow, k, p.cap);
+  }
+  __syncthreads();
+  if (warp == WARP_TMA) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+static size_t score_filter_smem(int HB, int stages) {
+  return (size_t)HB * ST_M * 128 + (size_t)stages * 2 * HB * 8192 + SF_EPI_WARPS * 32 * 4 +
+         (size_t)SF_Q * SF_EPI_WARPS * 32 * 8 + 256 + 1024;
+}
+
 // Vocabulary chunks per row tile: one CTA per SM is resident, so the critical path is
 // waves-of-148 x tiles-per-chunk; each chunk adds k candidates per row to the merge.
 static int score_chunks(int n_mtiles, int n_vtiles, int* tiles_per_chunk) {
@@ -402,6 +596,10 @@ extern "C" int b4cp_topk_candidates_redo(const float* cand_scores, const int32_t
                                          float* out_scores, long ld_out, void* stream);
 extern "C" int b4cp_topk_rows(const float* scores, long ld, long rows, int V, int k,
                               int32_t* out_ids, float* out_scores, long ld_out, void* stream);
+extern "C" int b4cp_topk_candidates_counted(const float* cand_scores, const int32_t* cand_ids, long ld,
+                                            long rows, int n_cand, const int* extra_count,
+                                            int base_count, int V, int k, int32_t* out_ids,
+                                            float* out_scores, long ld_out, void* stream);
 
 namespace b4cp {
 
@@ -522,7 +720,7 @@ static int score_topk_filter(const void* x_bf16, long ldx, long M, int h, const 
                              float* out_scores, long ld_out, void* workspace, cudaStream_t st) {
   const FilterWs w = carve_filter_ws(workspace, M, V, k);
   const int cap = filter_cap(V, k);
-  B4CP_CUDA(cudaMemsetAsync(w.cand_ids, 0xFF, (size_t)M * cap * 4, st));   // -1 = empty slot
+  // (the merge reads only the k + cnt[row] filled slots of a list: no fill of the lists needed)
   B4CP_CUDA(cudaMemsetAsync(w.cnt, 0, (size_t)M * 4, st));
   B4CP_CUDA(cudaMemsetAsync(w.flag, 0, 4, st));
   // 1. seed: scores of vocabulary [0, FILTER_SEED) for a block of rows, ranked exactly
@@ -560,16 +758,26 @@ static int score_topk_filter(const void* x_bf16, long ldx, long M, int h, const 
   if (rc) return rc;
   rc = make_tmap_bf16_2d(&tmW, w_bf16, (uint64_t)V, (uint64_t)h, (uint64_t)ldw * 2, 64, 64);
   if (rc) return rc;
-  const size_t smem = (size_t)p.HB * ST_M * 128 + (size_t)ST_STAGES * 2 * p.HB * 8192 +
-                      (size_t)2 * 16 * ST_M * 4 + 4 * 2 * ST_N * 4 + 256 + 1024;
-  B4CP_CUDA(cudaFuncSetAttribute(score_topk_kernel<false, true>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   dim3 grid(ceil_div(M, ST_M), p.n_chunks);
-  score_topk_kernel<false, true><<<grid, 192, smem, st>>>(tmX, tmW, p, x, ldx);
+  if (getenv("B4CP_FILTER_GEN1")) {   // developer switch: the first-generation filter kernel
+    const size_t smem = (size_t)p.HB * ST_M * 128 + (size_t)ST_STAGES * 2 * p.HB * 8192 +
+                        (size_t)2 * 16 * ST_M * 4 + 4 * 2 * ST_N * 4 + 256 + 1024;
+    B4CP_CUDA(cudaFuncSetAttribute(score_topk_kernel<false, true>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    score_topk_kernel<false, true><<<grid, 192, smem, st>>>(tmX, tmW, p, x, ldx);
+  } else {
+    int stages = 4;
+    while (stages > 2 && score_filter_smem(p.HB, stages) > 227 * 1024) --stages;
+    B4CP_CHECK_ARG(score_filter_smem(p.HB, stages) <= 227 * 1024, "score_topk: h=%d does not fit", h);
+    B4CP_CUDA(cudaFuncSetAttribute(score_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   227 * 1024));
+    score_filter_kernel<<<grid, SF_THREADS, score_filter_smem(p.HB, stages), st>>>(tmX, tmW, p, stages);
+  }
   note_launches(1);
   B4CP_LAUNCH_CHECK();
   // 3. exact merge of seed winners + appended candidates
-  rc = b4cp_topk_candidates(w.cand_scores, w.cand_ids, cap, M, cap, V, k, out_ids, out_scores, ld_out, st);
+  rc = b4cp_topk_candidates_counted(w.cand_scores, w.cand_ids, cap, M, cap, w.cnt, k, V, k, out_ids,
+                                    out_scores, ld_out, st);
   if (rc) return rc;
   // 4. rows whose list overflowed are marked and redone by the heap kernel (device-side flag)
   filter_mark_overflow_kernel<<<ceil_div(M, 256), 256, 0, st>>>(w.cnt, M, cap - k, out_ids, ld_out, w.flag);

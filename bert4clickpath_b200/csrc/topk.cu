@@ -45,9 +45,12 @@ __device__ __forceinline__ float from_ordered_desc(uint32_t d) {
 __global__ void __launch_bounds__(TK_THREADS)
 topk_rows_kernel(const float* __restrict__ scores, const int32_t* __restrict__ cand_ids, long ld,
                  int V, int k, int idbits, int32_t* __restrict__ out_ids,
-                 float* __restrict__ out_scores, long ld_out, int only_flagged) {
+                 float* __restrict__ out_scores, long ld_out, int only_flagged,
+                 const int* __restrict__ extra_count = nullptr, int base_count = 0) {
   // second launch after topk_stream_kernel: only rows it flagged (out_ids[row][0] == -2)
   if (only_flagged && out_ids[(long)blockIdx.x * ld_out] != TK_REDO) return;
+  // counted candidate lists: row r holds base_count + extra_count[r] entries (at most V)
+  if (extra_count) V = min(V, base_count + max(extra_count[blockIdx.x], 0));
   __shared__ int hist[TK_BINS];
   __shared__ unsigned long long buf[TK_SORT];
   __shared__ int scan_tmp[40];
@@ -133,7 +136,10 @@ topk_rows_kernel(const float* __restrict__ scores, const int32_t* __restrict__ c
     prefix = (prefix << bits) | (unsigned)b;
     consumed += bits;
     __syncthreads();
-    if (bin_count <= TK_CAP || consumed >= total_bits) break;
+    // stop once the undecided bucket is small; short (candidate-list) rows go on until it is
+    // SMALL - the final sort is sized by what is collected, and its ~log^2 barrier-separated
+    // stages dominated the merge of ~1.5K-entry lists when it always ran over TK_SORT keys
+    if (bin_count <= (V <= 16384 ? TK_CAP / 8 : TK_CAP) || consumed >= total_bits) break;
   }
   // collect winners (top bits < prefix) and the undecided bucket (== prefix)
   if (threadIdx.x == 0) s_nsel = 0;
@@ -150,10 +156,16 @@ topk_rows_kernel(const float* __restrict__ scores, const int32_t* __restrict__ c
     }
   }
   __syncthreads();
-  // bitonic sort ascending
-  for (int size = 2; size <= TK_SORT; size <<= 1) {
+  // bitonic sort ascending over the smallest power of two that holds what was collected (unused
+  // slots carry ~0 and sort to the end)
+  int sort_n = 2;
+  while (sort_n < min(s_nsel, TK_SORT)) sort_n <<= 1;
+  if (sort_n < k) {
+    while (sort_n < k) sort_n <<= 1;
+  }
+  for (int size = 2; size <= sort_n; size <<= 1) {
     for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      for (int i = threadIdx.x; i < TK_SORT / 2; i += TK_THREADS) {
+      for (int i = threadIdx.x; i < sort_n / 2; i += TK_THREADS) {
         const int lo = (i / stride) * (stride << 1) + (i % stride);
         const int hi = lo + stride;
         const bool asc = ((lo & size) == 0);
@@ -539,6 +551,25 @@ extern "C" int b4cp_topk_candidates_redo(const float* cand_scores, const int32_t
   while ((1L << idbits) < V) ++idbits;
   topk_rows_kernel<<<(unsigned)rows, TK_THREADS, 0, (cudaStream_t)stream>>>(
       cand_scores, cand_ids, ld, n_cand, k, idbits, out_ids, out_scores, ld_out, 1);
+  note_launches(1);
+  B4CP_LAUNCH_CHECK();
+  return 0;
+}
+
+/* b4cp_topk_candidates over COUNTED lists: row r holds base_count + extra_count[r] entries (capped
+ * at n_cand); slots past that are never read, so they need not be initialised. */
+extern "C" int b4cp_topk_candidates_counted(const float* cand_scores, const int32_t* cand_ids, long ld,
+                                            long rows, int n_cand, const int* extra_count,
+                                            int base_count, int V, int k, int32_t* out_ids,
+                                            float* out_scores, long ld_out, void* stream) {
+  B4CP_CHECK_ARG(k >= 1 && k <= TK_MAXK, "topk: k=%d must be in [1,%d]", k, TK_MAXK);
+  B4CP_CHECK_ARG(cand_scores && cand_ids && out_ids && extra_count, "topk_candidates: null argument");
+  B4CP_CHECK_ARG(ld_out >= k, "topk: ld_out < k");
+  if (rows == 0) return 0;
+  int idbits = 1;
+  while ((1L << idbits) < V) ++idbits;
+  topk_rows_kernel<<<(unsigned)rows, TK_THREADS, 0, (cudaStream_t)stream>>>(
+      cand_scores, cand_ids, ld, n_cand, k, idbits, out_ids, out_scores, ld_out, 0, extra_count, base_count);
   note_launches(1);
   B4CP_LAUNCH_CHECK();
   return 0;

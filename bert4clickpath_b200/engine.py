@@ -466,8 +466,10 @@ class VocabOutputEngine:
 
     force_materialized = False
 
-    def loss_forward(self, ab, M, labels, loss_stats, need_grad=True):
-        """loss_stats <- (sum over valid rows of lse - z_t, number of valid rows)."""
+    def loss_forward(self, ab, M, labels, loss_stats, need_grad=True, n_global=None):
+        """loss_stats <- (sum over valid rows of lse - z_t, number of valid rows).  n_global
+        (int32 device scalar): the valid-row count over all data-parallel ranks, reduced while
+        the forward ran; loss_stats[1] is then that count and loss_stats[0] stays local."""
         lse = self.pool.get("lse", (M,))
         tgt = self.pool.get("tgt", (M,))
         z = None
@@ -486,7 +488,7 @@ class VocabOutputEngine:
                 ops.ce_rows_stats(z, self.V, labels[a:b], lse[a:b], tgt[a:b])
             if len(chunks) > 1:
                 z = None
-        ops.ce_loss_reduce(lse, tgt, labels, loss_stats)
+        ops.ce_loss_reduce(lse, tgt, labels, loss_stats, n_global)
         self.saved = dict(ab=ab, M=M, labels=labels, z=z, lse=lse, chunks=chunks)
 
     def loss_backward(self, loss_stats, gate, out_f32=None, out_bf16=None):
@@ -533,19 +535,28 @@ class VocabOutputEngine:
         if db_parts is not None:
             ops.reduce_splits(db_parts, self.b.g)
 
+    FUSED_TOPK_MIN_V = 262144
+
     def topk(self, ab, M, k):
         """(M, k) int32 ids of the k highest scores per row, ties -> lower id.
-        Default: logits materialised for a bounded row range at a time (tcgen05 GEMM, fp32) + the
-        single-pass streaming top-k (`b4cp_topk_rows`).  On scores in realistic (unsorted) order this
-        measures 3.7 M queries/s at V = 54,293 / h = 128 and 0.5 M at V = 1M / h = 256, against
-        0.67 M / 0.41 M for the fused kernels of `b4cp_score_topk` (scores never in HBM; per-row heaps
-        below 262,144 entries, seed + filter + merge above), whose per-row candidate bookkeeping is
-        the bottleneck.  `prefer_fused_topk = True` selects the fused kernels (they win when HBM
-        capacity, not time, is the constraint, and on near-sorted scores)."""
+
+        V >= 262,144 (C5: the 1M-item catalogue): the FUSED kernels of `b4cp_score_topk` - the
+        scores never reach HBM.  A seed range is scored and ranked exactly, which gives every row
+        a threshold; one tcgen05 sweep over the rest of the vocabulary appends the scores above
+        it to per-row candidate lists; an exact merge finishes.  1.16 M queries/s at V = 1M,
+        h = 256, k = 100, 4,096 queries per call, against 0.54 M for the materialised path.
+
+        Shorter vocabularies (C1: 54,293 entries): logits materialised for a bounded row range at
+        a time (tcgen05 GEMM, fp32) + the single-pass streaming top-k (`b4cp_topk_rows`): 3.7 M
+        queries/s at h = 128; the fused alternative there is a per-row heap kernel, which is
+        slower (0.67 M).  `prefer_fused_topk` = True / False overrides the choice."""
         ids = self.pool.get(f"topk{k}", (M, k), I32)
         fused_ok = (self.h in (64, 128, 256) and k <= 104 and not self.force_materialized
                     and ab.dtype == BF16)
-        if fused_ok and self.prefer_fused_topk:
+        prefer = self.prefer_fused_topk
+        if prefer is None:
+            prefer = self.V >= self.FUSED_TOPK_MIN_V
+        if fused_ok and prefer:
             t0 = ops.TIMER.begin("score_topk")
             ops.score_topk(ab, M, self.h, self.W.wb, self.b.w, self.V, k, out_ids=ids)
             ops.TIMER.end("score_topk", t0)
@@ -555,7 +566,7 @@ class VocabOutputEngine:
             ops.topk_rows(z, self.V, k, out_ids=ids[a:b])
         return ids
 
-    prefer_fused_topk = False
+    prefer_fused_topk = None   # None: by vocabulary size (see topk)
 
 
 class VocabParallelOutputEngine(VocabOutputEngine):
@@ -638,7 +649,7 @@ class VocabParallelOutputEngine(VocabOutputEngine):
             dist.all_gather_into_tensor(lab_all, labels[:M], group=self.group)
         return ab_all, lab_all
 
-    def loss_forward(self, ab, M, labels, loss_stats, need_grad=True):
+    def loss_forward(self, ab, M, labels, loss_stats, need_grad=True, n_global=None):
         import torch.distributed as dist
         W_ = self.world
         ab_all, lab_all = self._gather_rows(ab, M, labels)

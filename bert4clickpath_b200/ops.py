@@ -382,7 +382,12 @@ def ce_rows_stats(logits, V, labels, lse, tgt):
            L.c_int(V), L.ptr(labels), L.ptr(lse), L.ptr(tgt), L.stream_ptr())
 
 
-def ce_loss_reduce(lse, tgt, labels, loss_stats):
+def ce_loss_reduce(lse, tgt, labels, loss_stats, n_global=None):
+    """n_global: int32 device scalar holding the valid-row count over all ranks (see b4cp.h)."""
+    if n_global is not None:
+        L.call("b4cp_ce_loss_reduce_n", L.ptr(lse), L.ptr(tgt), L.ptr(labels),
+               L.c_long(labels.numel()), L.ptr(n_global), L.ptr(loss_stats), L.stream_ptr())
+        return
     L.call("b4cp_ce_loss_reduce", L.ptr(lse), L.ptr(tgt), L.ptr(labels), L.c_long(labels.numel()),
            L.ptr(loss_stats), L.stream_ptr())
 

@@ -226,6 +226,11 @@ int b4cp_ce_rows_stats(const float* logits, long ld, long M, int V, const int32_
                        float* lse, float* tgt, void* stream);
 int b4cp_ce_loss_reduce(const float* lse, const float* tgt, const int32_t* labels, long M,
                         float* loss_stats, void* stream);
+/* data-parallel form: loss_stats[0] = this rank's loss sum, loss_stats[1] = (float)*n_global, the
+ * number of valid rows over ALL ranks (an int32 on the device, all-reduced while the forward runs:
+ * the masked mean of losses.py:80-91 is global, and the backward needs only the count) */
+int b4cp_ce_loss_reduce_n(const float* lse, const float* tgt, const int32_t* labels, long M,
+                          const int32_t* n_global, float* loss_stats, void* stream);
 /* dz = (softmax - onehot) / loss_stats[1] (bf16, optional) and/or probabilities (fp32, optional) */
 int b4cp_ce_rows_grad(const float* logits, long ld, long M, int V, const int32_t* labels,
                       const float* lse, const float* loss_stats, void* dz_bf16, long ld_dz,
@@ -330,6 +335,12 @@ int b4cp_topk_rows(const float* scores, long ld, long rows, int V, int k, int32_
 int b4cp_topk_candidates(const float* cand_scores, const int32_t* cand_ids, long ld, long rows,
                          int n_cand, int V, int k, int32_t* out_ids, float* out_scores,
                          long ld_out, void* stream);
+/* counted lists: row r holds base_count + extra_count[r] entries (capped at n_cand); later slots
+ * are never read */
+int b4cp_topk_candidates_counted(const float* cand_scores, const int32_t* cand_ids, long ld,
+                                 long rows, int n_cand, const int* extra_count, int base_count, int V,
+                                 int k, int32_t* out_ids, float* out_scores, long ld_out,
+                                 void* stream);
 /* b4cp_topk_candidates restricted to the rows whose out_ids[row][0] == -2 (redo marker) */
 int b4cp_topk_candidates_redo(const float* cand_scores, const int32_t* cand_ids, long ld, long rows,
                               int n_cand, int V, int k, int32_t* out_ids, float* out_scores,
