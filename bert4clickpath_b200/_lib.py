@@ -35,6 +35,20 @@ class GemmEpilogue(ctypes.Structure):
     ]
 
 
+class AdamSegment(ctypes.Structure):
+    """Mirror of b4cp_adam_segment (include/b4cp.h)."""
+    _fields_ = [
+        ("begin", ctypes.c_long),
+        ("numel", ctypes.c_long),
+        ("cols", ctypes.c_int),
+        ("ld_shadow", ctypes.c_long),
+        ("shadow_bf16", ctypes.c_void_p),
+    ]
+
+
+ADAM_MAX_SEGS = 48
+
+
 def declared_symbols():
     """Every function name declared in include/b4cp.h."""
     with open(HEADER_PATH) as f:

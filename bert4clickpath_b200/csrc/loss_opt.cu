@@ -230,6 +230,75 @@ adam_vec4_kernel(float4* __restrict__ theta, const float4* __restrict__ grad, fl
   }
 }
 
+// ONE sweep over the whole flat parameter buffer (engine.ParamStore keeps every parameter, its
+// gradient and both Adam moments in four parallel flat arrays): same arithmetic as adam_vec4_kernel,
+// and for the float4s that fall inside a Dense kernel the bf16 shadow is refreshed as well.  The
+// segment table (<= B4CP_ADAM_MAX_SEGS kernels) travels as a kernel parameter.
+struct AdamSegs {
+  int n;
+  b4cp_adam_segment seg[B4CP_ADAM_MAX_SEGS];
+};
+
+__global__ void __launch_bounds__(256)
+adam_flat_kernel(float4* __restrict__ theta, const float4* __restrict__ grad, float4* __restrict__ m,
+                 float4* __restrict__ v, long n4, float lr, float b1, float b2, float eps,
+                 const int* __restrict__ step_dev, int step_host, float grad_scale,
+                 const __grid_constant__ AdamSegs segs) {
+  const int t = step_dev ? *step_dev : step_host;
+  const float lr_t = lr * sqrtf(1.f - powf(b2, (float)t)) / (1.f - powf(b1, (float)t));
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n4;
+       i += (long)gridDim.x * blockDim.x) {
+    const float4 g4 = grad[i];
+    float4 m4 = m[i], v4 = v[i], th4 = theta[i];
+    const float gs[4] = {g4.x * grad_scale, g4.y * grad_scale, g4.z * grad_scale, g4.w * grad_scale};
+    float mm[4] = {m4.x, m4.y, m4.z, m4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w};
+    float th[4] = {th4.x, th4.y, th4.z, th4.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      mm[j] = b1 * mm[j] + (1.f - b1) * gs[j];
+      vv[j] = b2 * vv[j] + (1.f - b2) * gs[j] * gs[j];
+      th[j] = th[j] - lr_t * mm[j] / (sqrtf(vv[j]) + eps);
+    }
+    m[i] = make_float4(mm[0], mm[1], mm[2], mm[3]);
+    v[i] = make_float4(vv[0], vv[1], vv[2], vv[3]);
+    theta[i] = make_float4(th[0], th[1], th[2], th[3]);
+    // segments are sorted by offset and disjoint: find the one that holds element 4i, if any
+    const long e = i * 4;
+    int lo = 0, hi = segs.n;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (segs.seg[mid].begin + segs.seg[mid].numel <= e) lo = mid + 1;
+      else hi = mid;
+    }
+    if (lo < segs.n && segs.seg[lo].begin <= e) {
+      const b4cp_adam_segment& sg = segs.seg[lo];
+      __nv_bfloat16* shadow = (__nv_bfloat16*)sg.shadow_bf16;
+      const long le = e - sg.begin;      // segment offsets are multiples of 4: all 4 lanes inside
+      const long r = le / sg.cols;
+      const int c = (int)(le - r * sg.cols);
+      if ((sg.cols & 3) == 0 && (sg.ld_shadow & 3) == 0) {
+        __nv_bfloat162 a = __floats2bfloat162_rn(th[0], th[1]);
+        __nv_bfloat162 b = __floats2bfloat162_rn(th[2], th[3]);
+        uint2 pk;
+        pk.x = *reinterpret_cast<uint32_t*>(&a);
+        pk.y = *reinterpret_cast<uint32_t*>(&b);
+        *reinterpret_cast<uint2*>(shadow + r * sg.ld_shadow + c) = pk;
+      } else {
+        long rr = r;
+        int cc = c;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (le + j < sg.numel) shadow[rr * sg.ld_shadow + cc] = __float2bfloat16_rn(th[j]);
+          if (++cc == sg.cols) {
+            cc = 0;
+            ++rr;
+          }
+        }
+      }
+    }
+  }
+}
+
 __global__ void step_increment_kernel(int* step) { *step += 1; }
 
 __global__ void __launch_bounds__(256)
@@ -367,6 +436,41 @@ extern "C" int b4cp_adam_step(float* theta, const float* grad, float* m, float* 
                                                         (__nv_bfloat16*)shadow_bf16, cols, ld_shadow);
   note_launches(1);
   B4CP_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int b4cp_adam_flat(float* theta, const float* grad, float* m, float* v, long n,
+                              float lr, float beta1, float beta2, float eps, const int* step_dev,
+                              int step_host, float grad_scale, const b4cp_adam_segment* h_segs,
+                              int n_segs, void* stream) {
+  if (n == 0) return 0;
+  B4CP_CHECK_ARG(step_dev || step_host >= 1, "adam: step must be >= 1");
+  B4CP_CHECK_ARG(n % 4 == 0 && (((uintptr_t)theta | (uintptr_t)grad | (uintptr_t)m | (uintptr_t)v) & 15) == 0,
+                 "adam_flat: buffers must be 16-byte aligned and n a multiple of 4");
+  B4CP_CHECK_ARG(n_segs >= 0 && n_segs <= B4CP_ADAM_MAX_SEGS && (n_segs == 0 || h_segs),
+                 "adam_flat: at most %d shadow segments", B4CP_ADAM_MAX_SEGS);
+  AdamSegs segs;
+  segs.n = n_segs;
+  for (int i = 0; i < n_segs; ++i) {
+    segs.seg[i] = h_segs[i];
+    B4CP_CHECK_ARG(h_segs[i].begin % 4 == 0 && h_segs[i].cols > 0 && h_segs[i].shadow_bf16 &&
+                       h_segs[i].begin + h_segs[i].numel <= n &&
+                       (i == 0 || h_segs[i - 1].begin + h_segs[i - 1].numel <= h_segs[i].begin),
+                   "adam_flat: segment %d is malformed (sorted, disjoint, 4-aligned offsets required)", i);
+  }
+  const int vb = (int)std::min<long>(ceil_div(n / 4, 256), 148L * 8);
+  adam_flat_kernel<<<vb, 256, 0, (cudaStream_t)stream>>>((float4*)theta, (const float4*)grad, (float4*)m,
+                                                         (float4*)v, n / 4, lr, beta1, beta2, eps, step_dev,
+                                                         step_host, grad_scale, segs);
+  note_launches(1);
+  B4CP_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int b4cp_zero(void* ptr, long bytes, void* stream) {
+  if (bytes <= 0) return 0;
+  B4CP_CHECK_ARG(ptr, "zero: null pointer");
+  B4CP_CUDA(cudaMemsetAsync(ptr, 0, (size_t)bytes, (cudaStream_t)stream));
   return 0;
 }
 

@@ -125,7 +125,26 @@ class ParamStore:
         return {n: p.g.detach().cpu().numpy().copy() for n, p in self.params.items()}
 
     def adam(self, lr, beta1=0.9, beta2=0.999, eps=1e-9, grad_scale=1.0):
-        """Keras-semantics Adam over every parameter (tables dense-equivalent), then t += 1."""
+        """Keras-semantics Adam over every parameter (tables dense-equivalent), then t += 1: one
+        sweep over the flat buffers (`b4cp_adam_flat`), which also refreshes the bf16 shadows of
+        the Dense kernels; one launch per shadowed kernel only when there are more kernels than
+        the segment table holds."""
+        from . import _lib
+        shadowed = sorted((p for p in self.params.values() if p.wb is not None), key=lambda q: q.offset)
+        if len(shadowed) <= _lib.ADAM_MAX_SEGS:
+            if getattr(self, "_adam_segs", None) is None:
+                segs = (_lib.AdamSegment * max(len(shadowed), 1))()
+                for i, p in enumerate(shadowed):
+                    segs[i].begin, segs[i].numel = p.offset, p.numel
+                    segs[i].cols, segs[i].ld_shadow = p.shape[1], p.wb.stride(0)
+                    segs[i].shadow_bf16 = p.wb.data_ptr()
+                self._adam_segs = (segs, len(shadowed))
+            segs, n = self._adam_segs
+            ops.adam_flat(self.flat_w, self.flat_g, self.flat_m, self.flat_v, segs, n, lr=lr,
+                          beta1=beta1, beta2=beta2, eps=eps, step_dev=self.step_dev,
+                          grad_scale=grad_scale)
+            ops.step_increment(self.step_dev)
+            return
         plain = [p for p in self.params.values() if p.wb is None]
         # parameters without shadows are swept in maximal contiguous runs of the flat buffers
         runs = []
@@ -160,7 +179,7 @@ class BufferPool:
             t = torch.zeros(shape, dtype=dtype, device="cuda")
             self._b[key] = t
         elif zero:
-            t.zero_()
+            ops.zero_(t)
         return t
 
 
@@ -322,7 +341,8 @@ class EncoderEngine:
                                 g("ln2_b").g, g("b2").g, dropout_rate=rate, seed=seed,
                                 site=site(l, 2))
             dense_bwd_weights(a["hb"], dy2b, g("w2"), None, T)
-            dhb = pool.get("dhb", (T, dffp), act, zero=(dffp != self.dff))
+            # (columns dff..ld8(dff) are zero from allocation and never written: no per-step fill)
+            dhb = pool.get("dhb", (T, dffp), act)
             dense_bwd_input(dy2b, g("w2"), T, gate=a["hb"], out_bf16=dhb)
             dense_bwd_weights(a["x1b"], dhb, g("w1"), g("b1"), T)
             dx1b = pool.get("dxb", (T, d))

@@ -433,6 +433,20 @@ def adam_step(theta, grad, m, v, *, lr, beta1=0.9, beta2=0.999, eps=1e-9, step_d
            L.c_long(shadow.stride(0) if shadow is not None else 0), L.stream_ptr())
 
 
+def adam_flat(theta, grad, m, v, segs, n_segs, *, lr, beta1=0.9, beta2=0.999, eps=1e-9, step_dev=None,
+              step_host=0, grad_scale=1.0):
+    """One Adam sweep over the whole flat parameter buffer (+ the bf16 shadows listed in segs)."""
+    L.call("b4cp_adam_flat", L.ptr(theta), L.ptr(grad), L.ptr(m), L.ptr(v), L.c_long(theta.numel()),
+           L.c_float(lr), L.c_float(beta1), L.c_float(beta2), L.c_float(eps), L.ptr(step_dev),
+           L.c_int(step_host), L.c_float(grad_scale), segs, L.c_int(n_segs), L.stream_ptr())
+
+
+def zero_(t):
+    """Stream-ordered zero fill of a contiguous device tensor (no torch kernel in the hot path)."""
+    L.call("b4cp_zero", L.ptr(t), L.c_long(t.numel() * t.element_size()), L.stream_ptr())
+    return t
+
+
 def step_increment(step_dev):
     L.call("b4cp_step_increment", L.ptr(step_dev), L.stream_ptr())
 

@@ -371,6 +371,23 @@ int b4cp_adam_step(float* theta, const float* grad, float* m, float* v, long n, 
                    float beta1, float beta2, float eps, const int* step_dev, int step_host,
                    float grad_scale, void* shadow_bf16, int cols, long ld_shadow, void* stream);
 int b4cp_step_increment(int* step_dev, void* stream);
+/* The same update as ONE sweep over flat parameter / gradient / moment buffers of n elements that
+ * hold many parameters back to back (gaps must hold zeros in all four buffers).  h_segs (HOST
+ * array, sorted by `begin`, disjoint, `begin` a multiple of 4): the Dense kernels whose bf16
+ * shadow [numel / cols][ld_shadow] is refreshed in the same pass. */
+#define B4CP_ADAM_MAX_SEGS 48
+typedef struct {
+  long begin;         /* first element of the kernel in the flat buffers */
+  long numel;         /* rows * cols */
+  int cols;
+  long ld_shadow;
+  void* shadow_bf16;
+} b4cp_adam_segment;
+int b4cp_adam_flat(float* theta, const float* grad, float* m, float* v, long n, float lr,
+                   float beta1, float beta2, float eps, const int* step_dev, int step_host,
+                   float grad_scale, const b4cp_adam_segment* h_segs, int n_segs, void* stream);
+/* stream-ordered zero fill (cudaMemsetAsync) */
+int b4cp_zero(void* ptr, long bytes, void* stream);
 
 #ifdef __cplusplus
 }
