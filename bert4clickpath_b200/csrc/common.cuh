@@ -261,6 +261,18 @@ __device__ __forceinline__ void tma_load_2d_el(uint32_t smem_dst, const CUtensor
       "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// L2 prefetch of one TMA box (no shared-memory destination): issued a few tiles ahead of the real
+// load it turns that load's HBM miss into an L2 hit.  Matters where the operand stream is larger
+// than L2 and only two stages fit in shared memory (h = 256), so a load's latency is exposed.
+__device__ __forceinline__ void tma_prefetch_2d_el(const CUtensorMap* m, int c0, int c1) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];\n\t}" ::"l"(
+          reinterpret_cast<uint64_t>(m)),
+      "r"(c0), "r"(c1)
+      : "memory");
+}
 // warp-uniform barrier polls (every lane polls; the vote makes the result provably uniform)
 __device__ __forceinline__ bool mbar_test_all(uint64_t* bar, uint32_t parity) {
   return __all_sync(0xffffffffu, mbar_test(bar, parity));

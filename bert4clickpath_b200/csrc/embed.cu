@@ -640,19 +640,10 @@ extern "C" long b4cp_embed_bwd_workspace_bytes(long tokens, int max_dim) {
   return (long)carve_ws(nullptr, tokens, max_dim).bytes;
 }
 
-// Stable sort of (ids, token index) and segment bookkeeping for ONE feature.
-// Outputs live in the workspace; uniq_ids / n_unique are optional exports.
-extern "C" int b4cp_embed_bwd(const float* dout, int d_model, int col_offset, int dim,
-                              const int32_t* ids, long tokens, int rows, float dropout_rate,
-                              uint64_t seed, uint32_t site, float* table_grad, int32_t* uniq_ids,
-                              int32_t* n_unique_out, void* workspace, long workspace_bytes,
-                              void* stream) {
-  cudaStream_t st = (cudaStream_t)stream;
-  B4CP_CHECK_ARG(tokens > 0 && tokens < (1L << 31), "embed_bwd: bad token count %ld", tokens);
-  BwdWorkspace w = carve_ws(workspace, tokens, dim);
-  B4CP_CHECK_ARG(workspace && (long)w.bytes <= workspace_bytes,
-                 "embed_bwd: workspace too small (%ld < %zu)", workspace_bytes, w.bytes);
-  const long T = tokens;
+// Stable LSD radix sort of (id, token index) for ONE feature into the workspace.  It depends on
+// the ids alone - not on any gradient - so callers may run it early (b4cp_embed_sort on a side
+// stream while the backward is still in the encoder layers) and finish with b4cp_embed_bwd_sorted.
+static int embed_sort_impl(const int32_t* ids, long T, int rows, const BwdWorkspace& w, cudaStream_t st) {
   const int nblocks = ceil_div(T, SORT_TILE);
   int bits = 1;
   while ((1L << bits) < rows) ++bits;
@@ -673,6 +664,66 @@ extern "C" int b4cp_embed_bwd(const float* dout, int d_model, int col_offset, in
     kout = (kout == w.keys0) ? w.keys1 : w.keys0;
     vout = (vout == w.vals0) ? w.vals1 : w.vals0;
   }
+  B4CP_LAUNCH_CHECK();
+  return 0;
+}
+// where embed_sort_impl leaves the sorted (keys, tokens): buffer 0 after an odd number of passes
+static void sorted_buffers(int rows, const BwdWorkspace& w, const uint32_t** skeys, const uint32_t** stok) {
+  int bits = 1;
+  while ((1L << bits) < rows) ++bits;
+  const int passes = (bits + 7) / 8;
+  *skeys = (passes & 1) ? w.keys0 : w.keys1;
+  *stok = (passes & 1) ? w.vals0 : w.vals1;
+}
+
+extern "C" int b4cp_embed_sort(const int32_t* ids, long tokens, int rows, int max_dim, void* workspace,
+                               long workspace_bytes, void* stream) {
+  B4CP_CHECK_ARG(tokens > 0 && tokens < (1L << 31), "embed_sort: bad token count %ld", tokens);
+  BwdWorkspace w = carve_ws(workspace, tokens, max_dim);
+  B4CP_CHECK_ARG(workspace && (long)w.bytes <= workspace_bytes,
+                 "embed_sort: workspace too small (%ld < %zu)", workspace_bytes, w.bytes);
+  return embed_sort_impl(ids, tokens, rows, w, (cudaStream_t)stream);
+}
+
+static int embed_bwd_impl(const float* dout, int d_model, int col_offset, int dim, const int32_t* ids,
+                          long tokens, int rows, float dropout_rate, uint64_t seed, uint32_t site,
+                          float* table_grad, int32_t* uniq_ids, int32_t* n_unique_out,
+                          void* workspace, long workspace_bytes, bool presorted, void* stream);
+
+extern "C" int b4cp_embed_bwd(const float* dout, int d_model, int col_offset, int dim,
+                              const int32_t* ids, long tokens, int rows, float dropout_rate,
+                              uint64_t seed, uint32_t site, float* table_grad, int32_t* uniq_ids,
+                              int32_t* n_unique_out, void* workspace, long workspace_bytes,
+                              void* stream) {
+  return embed_bwd_impl(dout, d_model, col_offset, dim, ids, tokens, rows, dropout_rate, seed, site,
+                        table_grad, uniq_ids, n_unique_out, workspace, workspace_bytes, false, stream);
+}
+
+extern "C" int b4cp_embed_bwd_sorted(const float* dout, int d_model, int col_offset, int dim, long tokens,
+                                     int rows, float dropout_rate, uint64_t seed, uint32_t site,
+                                     float* table_grad, void* workspace, long workspace_bytes,
+                                     void* stream) {
+  return embed_bwd_impl(dout, d_model, col_offset, dim, nullptr, tokens, rows, dropout_rate, seed, site,
+                        table_grad, nullptr, nullptr, workspace, workspace_bytes, true, stream);
+}
+
+static int embed_bwd_impl(const float* dout, int d_model, int col_offset, int dim, const int32_t* ids,
+                          long tokens, int rows, float dropout_rate, uint64_t seed, uint32_t site,
+                          float* table_grad, int32_t* uniq_ids, int32_t* n_unique_out,
+                          void* workspace, long workspace_bytes, bool presorted, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  B4CP_CHECK_ARG(tokens > 0 && tokens < (1L << 31), "embed_bwd: bad token count %ld", tokens);
+  BwdWorkspace w = carve_ws(workspace, tokens, dim);
+  B4CP_CHECK_ARG(workspace && (long)w.bytes <= workspace_bytes,
+                 "embed_bwd: workspace too small (%ld < %zu)", workspace_bytes, w.bytes);
+  const long T = tokens;
+  if (!presorted) {
+    const int rc = embed_sort_impl(ids, T, rows, w, st);
+    if (rc) return rc;
+  }
+  const uint32_t* kin;
+  const uint32_t* vin;
+  sorted_buffers(rows, w, &kin, &vin);
   B4CP_LAUNCH_CHECK();
   const uint32_t* skeys = kin;
   const uint32_t* stok = vin;

@@ -46,6 +46,7 @@ struct ScoreParams {
   int* cand_cnt;       // [M] appended so far
   int cap;
   const int* run_if;   // launch is a no-op unless *run_if != 0 (NULL: always run)
+  int l2_prefetch;     // filter kernel: W tiles prefetched into L2 this many tiles ahead (0 = off)
 };
 
 static constexpr int ID24_EMPTY = 0xFFFFFF;
@@ -471,6 +472,11 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     for (int hb = 0; hb < HB; ++hb) tma_load_2d_el(aX + hb * (ST_M * 128), &tmX, x_full, hb * 64, m0);
     for (int t = 0; t < ntiles; ++t) {
       const int st = t % NST;
+      if (p.l2_prefetch && t + p.l2_prefetch < ntiles) {
+        const int vp = (p.tile0 + t_begin + t + p.l2_prefetch) * ST_N;
+        for (int vb = 0; vb < 2; ++vb)
+          for (int hb = 0; hb < HB; ++hb) tma_prefetch_2d_el(&tmW, vp + vb * 64, hb * 64);
+      }
       mbar_wait_all(&w_empty[st], (uint32_t)((t / NST) & 1) ^ 1);
       mbar_expect_tx_el(&w_full[st], (uint32_t)w_bytes);
       const int v0 = (p.tile0 + t_begin + t) * ST_N;
@@ -766,6 +772,8 @@ static int score_topk_filter(const void* x_bf16, long ldx, long M, int h, const 
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     score_topk_kernel<false, true><<<grid, 192, smem, st>>>(tmX, tmW, p, x, ldx);
   } else {
+    p.l2_prefetch = 6;
+    if (const char* e = getenv("B4CP_FILTER_PREFETCH")) p.l2_prefetch = atoi(e);   // developer switch
     int stages = 4;
     while (stages > 2 && score_filter_smem(p.HB, stages) > 227 * 1024) --stages;
     B4CP_CHECK_ARG(score_filter_smem(p.HB, stages) <= 227 * 1024, "score_topk: h=%d does not fit", h);

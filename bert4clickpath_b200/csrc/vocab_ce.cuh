@@ -72,6 +72,9 @@ struct VocabParams {
   int with_dx;              // forward also accumulates part_u (h = 128)
   int fwd_stages;
   int x_bufs;               // forward: X tile buffers in shared memory (1 or 2)
+  int l2_prefetch;          // forward: W tiles prefetched into L2 this many tiles ahead (0 = off)
+  int l2_prefetch_every;    // ... by the CTAs whose row tile index is a multiple of this
+  int grid_stagger;         // SCHED_GRID: row tile m starts its sweep m * grid_stagger tiles in
   // backward inputs / outputs
   const float* lse;         // [M]
   const float* loss_stats;  // [2]: (sum, n_valid)

@@ -54,6 +54,12 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 // (`u_drained` tells the MMA warp that U may be overwritten by the next segment's first product).
 struct FwdSeg {
   int m, v0, len, slot;
+  int rot;   // SCHED_GRID: tile i of the segment is vocabulary tile v0 + (i + rot) % len
+  __device__ __forceinline__ int vtile(int i) const {
+    int j = i + rot;
+    if (j >= len) j -= len;
+    return v0 + j;
+  }
 };
 
 __device__ __forceinline__ void fwd_range(const VocabParams& p, long& L0, long& L1) {
@@ -75,7 +81,13 @@ __device__ __forceinline__ FwdSeg fwd_seg(const VocabParams& p, long L, long L1)
     s.v0 = (int)blockIdx.y * p.tiles_per_chunk + (int)L;
     s.len = (int)(L1 - L);
     s.slot = (int)blockIdx.y;
+    // The CTAs of a chunk sweep the same W tiles.  In exact lock step all of them ask the SAME
+    // few L2 slices for the same 64 KB at the same moment; rotating each row tile's starting
+    // point by a few tiles spreads the requests over the slices while the chunk's working set
+    // (n_mtiles x stagger tiles) still sits in L2, so every W tile is still read from HBM once.
+    s.rot = s.len > 0 ? (int)(((long)blockIdx.x * p.grid_stagger) % s.len) : 0;
   } else {
+    s.rot = 0;
     s.m = (int)(L / p.n_vtiles);
     s.v0 = (int)(L - (long)s.m * p.n_vtiles);
     const long rem = L1 - L;
@@ -88,7 +100,7 @@ __device__ __forceinline__ FwdSeg fwd_seg(const VocabParams& p, long L, long L1)
 
 // NSB: S accumulators in TMEM (3 at h <= 128, 2 at h = 256).  OPT: optimistic exponentials (below);
 // they hold the S buffer until the row maxima are agreed, which only pays with three buffers.
-template <int NSB, int PP, bool OPT>
+template <int NSB, int PP, bool OPT, bool KSPLIT>
 __global__ void __launch_bounds__(TS_THREADS, 1)
 vocab_ce_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmX,
                        const __grid_constant__ CUtensorMap tmW, const VocabParams p) {
@@ -171,13 +183,35 @@ vocab_ce_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmX,
         tma_load_2d_el(aX + xb * x_bytes + hb * (VB_M * 128), &tmX, &x_full[xb], hb * 64, s.m * VB_M);
       for (int i = 0; i < s.len; ++i, ++t) {
         const int st = t % NST;
-        mbar_wait_all(&w_empty[st], (uint32_t)((t / NST) & 1) ^ 1);
-        mbar_expect_tx_el(&w_full[st], (uint32_t)w_bytes);
-        const int v0 = (s.v0 + i) * VB_N;
-        const uint32_t dst = aW0 + (uint32_t)(st * w_bytes);
-        for (int vb = 0; vb < 2; ++vb)
-          for (int hb = 0; hb < HB; ++hb)
-            tma_load_2d_el(dst + (vb * HB + hb) * 8192, &tmW, &w_full[st], v0 + vb * 64, hb * 64);
+        if (p.l2_prefetch && (int)blockIdx.x % p.l2_prefetch_every == 0 &&
+            i + p.l2_prefetch < s.len) {   // W tile i + PF of this segment -> L2
+          const int vp = s.vtile(i + p.l2_prefetch) * VB_N;
+          for (int vb = 0; vb < 2; ++vb)
+            for (int hb = 0; hb < HB; ++hb) tma_prefetch_2d_el(&tmW, vp + vb * 64, hb * 64);
+        }
+        const int v0 = s.vtile(i) * VB_N;
+        if (KSPLIT) {
+          // h = 256: a W tile travels as two K halves (h rows [0,128) and [128,256)) through a
+          // ring of FOUR 32 KB half stages - see the MMA warp
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            const int hi = 2 * t + hh, sl = hi & 3;
+            mbar_wait_all(&w_empty[sl], (uint32_t)((hi >> 2) & 1) ^ 1);
+            mbar_expect_tx_el(&w_full[sl], 32768u);
+            const uint32_t dst = aW0 + (uint32_t)(sl * 32768);
+            for (int vb = 0; vb < 2; ++vb)
+              for (int hb2 = 0; hb2 < 2; ++hb2)
+                tma_load_2d_el(dst + (vb * 2 + hb2) * 8192, &tmW, &w_full[sl], v0 + vb * 64,
+                               (hh * 2 + hb2) * 64);
+          }
+        } else {
+          mbar_wait_all(&w_empty[st], (uint32_t)((t / NST) & 1) ^ 1);
+          mbar_expect_tx_el(&w_full[st], (uint32_t)w_bytes);
+          const uint32_t dst = aW0 + (uint32_t)(st * w_bytes);
+          for (int vb = 0; vb < 2; ++vb)
+            for (int hb = 0; hb < HB; ++hb)
+              tma_load_2d_el(dst + (vb * HB + hb) * 8192, &tmW, &w_full[st], v0 + vb * 64, hb * 64);
+        }
       }
       L += s.len;
     }
@@ -198,16 +232,39 @@ vocab_ce_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmX,
     int len_s = Ls < L_end ? fwd_seg(p, Ls, L_end).len : 0;
     int len_u = len_s;
     const int n_total = (int)(L_end - L_begin);
+    // KSPLIT (h = 256): shared memory holds X (64 KB) and only 128 KB of W.  As two whole-tile
+    // stages, the load of W(t+2) could not start before U(t) had finished with its stage, and
+    // S(t+2) - which the epilogue needs next - waited a full 64 KB L2 -> SM transfer behind it.
+    // The tile is therefore split along K = h into two 32 KB halves in a ring of four: U(t) is
+    // issued as two N = 128 products (U columns [0,128) from half 0, [128,256) from half 1), the
+    // first of which frees half 0 half a product earlier, and each half is a transfer half as long.
+    const uint64_t dWsK = umma_smem_desc(aW0, 2 * 8192, 1024);      // KSPLIT: the vb blocks are 16 KB apart
+    const uint32_t id_u128 = umma_idesc_bf16(VB_M, 128, 0, 0);
     auto issue_s = [&](int t) {
       const int st = t % NST, buf = t % NSB, xb = sgs % XB;
       tc_fence_after();
       const uint32_t wo = (uint32_t)(st * w_bytes) >> 4;
       const uint32_t xo = (uint32_t)(xb * x_bytes) >> 4;
-      for (int hb = 0; hb < HB; ++hb) {
+      if (KSPLIT) {
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk)
-          umma_bf16_el(tmem_base + buf * VB_N, dX + (xo + (uint32_t)((hb * (VB_M * 128) + kk * 32) >> 4)),
-                       dWs + (wo + (uint32_t)((hb * 8192 + kk * 2048) >> 4)), id_s, (hb | kk) ? 1u : 0u);
+        for (int hh = 0; hh < 2; ++hh) {
+          const uint32_t ho = (uint32_t)(((2 * t + hh) & 3) * 32768) >> 4;
+#pragma unroll
+          for (int hb2 = 0; hb2 < 2; ++hb2)
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+              umma_bf16_el(tmem_base + buf * VB_N,
+                           dX + (xo + (uint32_t)(((hh * 2 + hb2) * (VB_M * 128) + kk * 32) >> 4)),
+                           dWsK + (ho + (uint32_t)((hb2 * 8192 + kk * 2048) >> 4)), id_s,
+                           (hh | hb2 | kk) ? 1u : 0u);
+        }
+      } else {
+        for (int hb = 0; hb < HB; ++hb) {
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            umma_bf16_el(tmem_base + buf * VB_N, dX + (xo + (uint32_t)((hb * (VB_M * 128) + kk * 32) >> 4)),
+                         dWs + (wo + (uint32_t)((hb * 8192 + kk * 2048) >> 4)), id_s, (hb | kk) ? 1u : 0u);
+        }
       }
       umma_commit_el(&s_full[buf]);
       if (is == len_s - 1) umma_commit_el(&x_empty[xb]);   // last reader of this X tile
@@ -220,16 +277,38 @@ vocab_ce_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmX,
         len_s = Ls < L_end ? fwd_seg(p, Ls, L_end).len : 0;
       }
     };
+    auto w_ready = [&](int t) -> bool {
+      if (KSPLIT)
+        return mbar_test_all(&w_full[(2 * t) & 3], (uint32_t)(((2 * t) >> 2) & 1)) &&
+               mbar_test_all(&w_full[(2 * t + 1) & 3], (uint32_t)(((2 * t + 1) >> 2) & 1));
+      return mbar_test_all(&w_full[t % NST], (uint32_t)((t / NST) & 1));
+    };
     auto s_ready = [&](int t) -> bool {
       if (is == 0 && !mbar_test_all(&x_full[sgs % XB], (uint32_t)((sgs / XB) & 1))) return false;
-      return mbar_test_all(&w_full[t % NST], (uint32_t)((t / NST) & 1)) &&
-             mbar_test_all(&s_empty[t % NSB], (uint32_t)((t / NSB) & 1) ^ 1);
+      return w_ready(t) && mbar_test_all(&s_empty[t % NSB], (uint32_t)((t / NSB) & 1) ^ 1);
     };
     auto issue_u = [&](int t) {
       const int st = t % NST, buf = t % NSB;
       tc_fence_after();
       const uint32_t wo = (uint32_t)(st * w_bytes) >> 4;
       const uint32_t tP = tmem_base + buf * VB_N;
+      if (KSPLIT) {
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          const int sl = (2 * t + hh) & 3;
+          const uint32_t ho = (uint32_t)(sl * 32768) >> 4;
+#pragma unroll
+          for (int k8 = 0; k8 < 8; ++k8) {
+            const int vb = k8 >> 2, kk = k8 & 3;
+            umma_bf16_ts_el(T_U + hh * 128, tP + (k8 >> 1) * 32 + (k8 & 1) * 8,
+                            dWu + (ho + (uint32_t)((vb * 2 * 8192 + kk * 32) >> 4)), id_u128,
+                            (iu | k8) ? 1u : 0u);
+          }
+          umma_commit_el(&w_empty[sl]);   // this K half is free as soon as its product retires
+        }
+        umma_commit_el(&u_full[buf]);
+        return;
+      }
 #pragma unroll
       for (int k8 = 0; k8 < 8; ++k8) {
         const int vb = k8 >> 2, kk = k8 & 3;
@@ -242,10 +321,20 @@ vocab_ce_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmX,
     if (!with_dx) {
       for (int t = 0; t < n_total; ++t) {
         if (is == 0) mbar_wait_all(&x_full[sgs % XB], (uint32_t)((sgs / XB) & 1));
-        mbar_wait_all(&w_full[t % NST], (uint32_t)((t / NST) & 1));
+        if (KSPLIT) {
+          mbar_wait_all(&w_full[(2 * t) & 3], (uint32_t)(((2 * t) >> 2) & 1));
+          mbar_wait_all(&w_full[(2 * t + 1) & 3], (uint32_t)(((2 * t + 1) >> 2) & 1));
+        } else {
+          mbar_wait_all(&w_full[t % NST], (uint32_t)((t / NST) & 1));
+        }
         mbar_wait_all(&s_empty[t % NSB], (uint32_t)((t / NSB) & 1) ^ 1);
         issue_s(t);
-        umma_commit_el(&w_empty[t % NST]);
+        if (KSPLIT) {
+          umma_commit_el(&w_empty[(2 * t) & 3]);
+          umma_commit_el(&w_empty[(2 * t + 1) & 3]);
+        } else {
+          umma_commit_el(&w_empty[t % NST]);
+        }
         advance_s();
       }
     } else {
@@ -296,14 +385,15 @@ vocab_ce_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmX,
       float m_run = -INFINITY, m_ref = -INFINITY, s_run = 0.f, tgt2 = 0.f;
       bool have_tgt = false;
       auto load_bias = [&](int i) -> float {
-        const int v = (sgm.v0 + i) * VB_N + cg * 32 + lane;
-        return (i < sgm.len && v < p.V) ? __ldg(p.bias + v) : -INFINITY;
+        if (i >= sgm.len) return -INFINITY;
+        const int v = sgm.vtile(i) * VB_N + cg * 32 + lane;
+        return v < p.V ? __ldg(p.bias + v) : -INFINITY;
       };
       float bias_next = load_bias(0);
       for (int i = 0; i < sgm.len; ++i, ++t) {
         const int buf = t % NSB;
         const uint32_t sph = (uint32_t)((t / NSB) & 1);   // accumulator buffer and its barrier phase
-        const int vbase = (sgm.v0 + i) * VB_N + cg * 32;
+        const int vbase = sgm.vtile(i) * VB_N + cg * 32;
         sts32f(sb + lane * 4, bias_next * LOG2E);
         __syncwarp();
         bias_next = load_bias(i + 1);  // in flight while this tile is processed
@@ -784,6 +874,15 @@ int launch_vocab_fwd_ts(const CUtensorMap& tmX, const CUtensorMap& tmW, const Vo
   const size_t smem = fwd_ts_smem(p.HB, stages, p.x_bufs);
   dim3 grid(p.n_mtiles, p.n_chunks);
   if (p.sched == SCHED_RANGES) grid = dim3((unsigned)ceil_div(p.total_tiles, p.range_q), 1);
+  // L2 prefetch of W tiles ahead of their TMA load: measured useless (one CTA per chunk prefetching:
+  // 6.82 vs 6.88 ms at C4) to harmful (every CTA: 10.1 ms) - the exposed latency at h = 256 is the
+  // L2 -> SM transfer of a stage, not an HBM miss.  Off; the switches remain for experiments.
+  p.l2_prefetch = 0;
+  p.l2_prefetch_every = 64;
+  p.grid_stagger = 0;   // measured: 0 / 1 / 3 / 9 tiles all 7.1-7.2 ms at C4, 27 tiles 8.5 ms (HBM re-reads)
+  if (const char* e = getenv("B4CP_FWD_STAGGER")) p.grid_stagger = std::max(0, atoi(e));   // developer switch
+  if (const char* e = getenv("B4CP_FWD_PREFETCH")) p.l2_prefetch = atoi(e);   // developer switches
+  if (const char* e = getenv("B4CP_FWD_PREFETCH_EVERY")) p.l2_prefetch_every = std::max(1, atoi(e));
   int pp = FWD_POLY_DEFAULT;
   if (const char* e = getenv("B4CP_FWD_POLY")) pp = atoi(e);   // developer switch: 0 / 2
   // optimistic exponentials: 0.88 -> 0.837 ms on their own at the C1 shape, but once a
@@ -791,11 +890,19 @@ int launch_vocab_fwd_ts(const CUtensorMap& tmX, const CUtensorMap& tmW, const Vo
   // at C1, 6.81 vs 6.85 ms at C4) and releases the S accumulator earlier: off by default
   bool opt = false;
   if (const char* e = getenv("B4CP_FWD_OPT")) opt = atoi(e) != 0;   // developer switch
+  // K-split half stages: 0.385 -> 0.339 ms at (M 7,424, V 54,293, h 256) where W sits in L2; no
+  // gain under the lock-step grid at V = 1M (7.1 vs 6.9 ms), so only with the range schedule
+  const bool ksplit = p.HB == 4 && stages == 2 && p.sched == SCHED_RANGES && !getenv("B4CP_FWD_NO_KSPLIT");
+#define B4CP_LAUNCH_FWD_K(NSB_, PP_, OPT_, KS_)                                                     \
+  do {                                                                                              \
+    B4CP_CUDA(cudaFuncSetAttribute(vocab_ce_fwd_ts_kernel<NSB_, PP_, OPT_, KS_>,                    \
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));       \
+    vocab_ce_fwd_ts_kernel<NSB_, PP_, OPT_, KS_><<<grid, TS_THREADS, smem, st>>>(tmX, tmW, p);      \
+  } while (0)
 #define B4CP_LAUNCH_FWD(NSB_, PP_, OPT_)                                                            \
   do {                                                                                              \
-    B4CP_CUDA(cudaFuncSetAttribute(vocab_ce_fwd_ts_kernel<NSB_, PP_, OPT_>,                         \
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));       \
-    vocab_ce_fwd_ts_kernel<NSB_, PP_, OPT_><<<grid, TS_THREADS, smem, st>>>(tmX, tmW, p);           \
+    if (NSB_ == 2 && ksplit) B4CP_LAUNCH_FWD_K(NSB_, PP_, OPT_, (NSB_ == 2));                       \
+    else B4CP_LAUNCH_FWD_K(NSB_, PP_, OPT_, false);                                                 \
   } while (0)
   if (p.h <= 128) {
     if (pp == 2 && opt) B4CP_LAUNCH_FWD(3, 2, true);
@@ -809,6 +916,7 @@ int launch_vocab_fwd_ts(const CUtensorMap& tmX, const CUtensorMap& tmW, const Vo
     else B4CP_LAUNCH_FWD(2, 0, false);
   }
 #undef B4CP_LAUNCH_FWD
+#undef B4CP_LAUNCH_FWD_K
   return 0;
 }
 

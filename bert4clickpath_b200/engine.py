@@ -257,6 +257,7 @@ class EncoderEngine:
         self.pe = None
         self.pool = BufferPool()
         self.saved = None
+        self._side = None
 
     def _pe(self):
         if self.pe is None:
@@ -331,6 +332,21 @@ class EncoderEngine:
         T = B * S
         dffp = ld8(self.dff)
         act = self.act
+        plan, world = self.plan_table_exchange(T, group)
+        # The sort of (id, token) that the table gradients need depends on the ids alone: it runs
+        # NOW, on a side stream, under the encoder layers' backward (ten small latency-bound
+        # launches that used to sit at the end of the step's critical path).
+        presorted = not any(plan)
+        if presorted:
+            cur = torch.cuda.current_stream()
+            if self._side is None:
+                self._side = torch.cuda.Stream()
+            for f, df in enumerate(self.dims):      # workspaces belong to the main stream
+                ops._embed_ws(T, df, f"embed_bwd{f}")
+            self._side.wait_stream(cur)
+            with torch.cuda.stream(self._side):
+                for f, (R, df) in enumerate(zip(self.rows, self.dims)):
+                    ops.embed_sort(sv["ids"][f], R, df, f"embed_bwd{f}")
         for l in reversed(range(self.L)):
             g = lambda n: st[f"enc.{l}.{n}"]
             a = sv["acts"][l]
@@ -362,8 +378,15 @@ class EncoderEngine:
             dense_bwd_weights(a["xb"], dqkvb, g("wqkv"), g("bqkv"), T)
             dx = pool.get("dxb", (T, d))
             dense_bwd_input(dqkvb, g("wqkv"), T, addend=dxr, out_f32=dx)
-        plan, world = self.plan_table_exchange(T, group)
         dx_all = None
+        if presorted:
+            torch.cuda.current_stream().wait_stream(self._side)
+            off = 0
+            for f, (R, df) in enumerate(zip(self.rows, self.dims)):
+                ops.embed_bwd_sorted(dx, d, off, df, T, R, st[f"emb.{f}"].g, f"embed_bwd{f}",
+                                     dropout_rate=rate, seed=seed, site=SITE_INPUT)
+                off += df
+            return dx
         if any(plan):
             import torch.distributed as dist
             if rate > 0.0:   # the input-dropout mask is indexed by the LOCAL token: apply it here

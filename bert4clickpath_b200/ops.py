@@ -256,6 +256,28 @@ def embed_bwd(dout, d_model, col_offset, dim, ids, rows, table_grad, *, dropout_
            L.c_long(ws.numel()), L.stream_ptr())
 
 
+def _embed_ws(tokens, dim, name):
+    nbytes = L.lib().b4cp_embed_bwd_workspace_bytes
+    nbytes.restype = ctypes.c_long
+    return WS.get(name, nbytes(ctypes.c_long(tokens), ctypes.c_int(dim)))
+
+
+def embed_sort(ids, rows, dim, ws_name):
+    """First half of embed_bwd: stable sort of (id, token) into the named workspace."""
+    ws = _embed_ws(ids.numel(), dim, ws_name)
+    L.call("b4cp_embed_sort", L.ptr(ids), L.c_long(ids.numel()), L.c_int(rows), L.c_int(dim),
+           L.ptr(ws), L.c_long(ws.numel()), L.stream_ptr())
+
+
+def embed_bwd_sorted(dout, d_model, col_offset, dim, tokens, rows, table_grad, ws_name, *,
+                     dropout_rate=0.0, seed=0, site=0):
+    """Second half: segment sums over the order `embed_sort` left in the named workspace."""
+    ws = _embed_ws(tokens, dim, ws_name)
+    L.call("b4cp_embed_bwd_sorted", L.ptr(dout), L.c_int(d_model), L.c_int(col_offset), L.c_int(dim),
+           L.c_long(tokens), L.c_int(rows), L.c_float(dropout_rate), L.c_u64(seed),
+           ctypes.c_uint32(site), L.ptr(table_grad), L.ptr(ws), L.c_long(ws.numel()), L.stream_ptr())
+
+
 # --------------------------------------------------------------------------------- encoder
 def attention_fwd(qkv, ids_first, B, S, H, dh, out, lse):
     if qkv.dtype == F32:   # fp32-class mode

@@ -133,6 +133,16 @@ int b4cp_embed_bwd(const float* dout, int d_model, int col_offset, int dim, cons
                    float* table_grad, int32_t* uniq_ids, int32_t* n_unique, void* workspace,
                    long workspace_bytes, void* stream);
 
+/* The same backward in two stream-ordered parts: the sort of (id, token) depends on the ids alone,
+ * so it can run EARLY (e.g. on a side stream while the backward is still in the encoder layers);
+ * b4cp_embed_bwd_sorted then only streams the gradient rows through the segment sums.  Both calls
+ * take the same workspace (b4cp_embed_bwd_workspace_bytes(tokens, max_dim), max_dim >= dim). */
+int b4cp_embed_sort(const int32_t* ids, long tokens, int rows, int max_dim, void* workspace,
+                    long workspace_bytes, void* stream);
+int b4cp_embed_bwd_sorted(const float* dout, int d_model, int col_offset, int dim, long tokens,
+                          int rows, float dropout_rate, uint64_t seed, uint32_t site,
+                          float* table_grad, void* workspace, long workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------ encoder layer pieces
  * Fused short-sequence masked self-attention (S <= 256), one CTA per (sequence, head):
  * clickstream_transformer/transformer.py:64-97 (scaled_dot_product_attention, additive -1e9 key
