@@ -86,6 +86,42 @@ __device__ __forceinline__ void stage_tile(const __nv_bfloat16* __restrict__ src
   }
 }
 
+// The Q / K / V (/ dO) slices of one (sequence, head), staged TOGETHER: every thread first issues
+// all of its 128-bit global loads (6 or 8 independent requests at the C1 shape), then stores them.
+// Tile by tile the loads of the next tile waited behind the shared-memory stores of the previous
+// one, so a CTA paid three to four DRAM round trips before its first MMA; these kernels move
+// 0.3 of the HBM roofline and are latency-, not flop-bound (ncu: profiles/r2_ncu_attn_*).
+template <int DH, int SP, int NTILES, int THREADS>
+__device__ __forceinline__ void stage_tiles(const __nv_bfloat16* const (&src)[NTILES],
+                                            const long (&ld)[NTILES], int S,
+                                            __nv_bfloat16* const (&dst)[NTILES], int LDR) {
+  constexpr int W = DH / 8;
+  constexpr int PER = (SP * W + THREADS - 1) / THREADS;   // uint4 per thread per tile
+  if constexpr (PER * NTILES <= 16) {
+    uint4 v[NTILES][PER];
+#pragma unroll
+    for (int k = 0; k < NTILES; ++k)
+#pragma unroll
+      for (int u = 0; u < PER; ++u) {
+        const int i = threadIdx.x + u * THREADS;
+        const int r = i / W, w = i - r * W;
+        v[k][u] = make_uint4(0u, 0u, 0u, 0u);
+        if (i < SP * W && r < S) v[k][u] = __ldg(reinterpret_cast<const uint4*>(src[k] + (size_t)r * ld[k] + 8 * w));
+      }
+#pragma unroll
+    for (int k = 0; k < NTILES; ++k)
+#pragma unroll
+      for (int u = 0; u < PER; ++u) {
+        const int i = threadIdx.x + u * THREADS;
+        const int r = i / W, w = i - r * W;
+        if (i < SP * W) *reinterpret_cast<uint4*>(dst[k] + (size_t)r * LDR + 8 * w) = v[k][u];
+      }
+  } else {
+#pragma unroll
+    for (int k = 0; k < NTILES; ++k) stage_tile<DH, SP>(src[k], ld[k], S, dst[k], LDR);
+  }
+}
+
 template <int NKB, int DH>
 struct AttnCfg {
   static constexpr int SP = 64 * NKB;       // padded sequence length
@@ -113,9 +149,12 @@ attention_mma_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* _
   const int b = blockIdx.x / H, h = blockIdx.x % H;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const __nv_bfloat16* base = qkv + (size_t)b * S * 3 * d + h * DH;
-  stage_tile<DH, C::SP>(base, 3L * d, S, sQ, C::LDR);
-  stage_tile<DH, C::SP>(base + d, 3L * d, S, sK, C::LDR);
-  stage_tile<DH, C::SP>(base + 2 * d, 3L * d, S, sV, C::LDR);
+  {
+    const __nv_bfloat16* const src[3] = {base, base + d, base + 2 * d};
+    const long lds[3] = {3L * d, 3L * d, 3L * d};
+    __nv_bfloat16* const dst[3] = {sQ, sK, sV};
+    stage_tiles<DH, C::SP, 3, 128>(src, lds, S, dst, C::LDR);
+  }
   for (int j = threadIdx.x; j < C::SP; j += blockDim.x)
     sMask[j] = j >= S ? -INFINITY : (ids[(size_t)b * S + j] == 0 ? -1e9f : 0.f);
   __syncthreads();
@@ -219,10 +258,12 @@ attention_mma_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloa
   const int b = blockIdx.x / H, h = blockIdx.x % H;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const __nv_bfloat16* base = qkv + (size_t)b * S * 3 * d + h * DH;
-  stage_tile<DH, C::SP>(base, 3L * d, S, sQ, C::LDR);
-  stage_tile<DH, C::SP>(base + d, 3L * d, S, sK, C::LDR);
-  stage_tile<DH, C::SP>(base + 2 * d, 3L * d, S, sV, C::LDR);
-  stage_tile<DH, C::SP>(dout + (size_t)b * S * d + h * DH, (long)d, S, sDO, C::LDR);
+  {
+    const __nv_bfloat16* const src[4] = {base, base + d, base + 2 * d, dout + (size_t)b * S * d + h * DH};
+    const long lds[4] = {3L * d, 3L * d, 3L * d, (long)d};
+    __nv_bfloat16* const dst[4] = {sQ, sK, sV, sDO};
+    stage_tiles<DH, C::SP, 4, 128>(src, lds, S, dst, C::LDR);
+  }
   for (int j = threadIdx.x; j < C::SP; j += blockDim.x) {
     sMask[j] = j >= S ? -INFINITY : (ids[(size_t)b * S + j] == 0 ? -1e9f : 0.f);
     sLse[j] = j < S ? lse_in[((size_t)b * H + h) * S + j] : INFINITY;  // rows past S: P = 0
