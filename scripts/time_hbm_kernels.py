@@ -72,6 +72,16 @@ for name, B, S, V, d in (("C1", 16384, 52, 54293, 64), ("C4", 1024, 202, 1_000_0
     report("embed_bwd (radix sort + segment sums + table zero-fill)", f"{name}: N={B*S} U={U} d={d} rows={rows}",
            alg, ms, bytes_incl_dense_zero_fill=int(alg + rows * d * 4),
            frac_incl_zero_fill=round((alg + rows * d * 4) / (ms * 1e-3) / 1e9 / PEAK, 3))
+    # the same backward in its two stream-ordered parts: the id sort (gradient-independent: the
+    # engine runs it on a side stream under the encoder backward) and the segment sums alone
+    for j in range(NS):
+        ops.embed_sort(idss[j], rows, d, f"hbm_sort{j}")
+    ms_sort = timed(lambda j: ops.embed_sort(idss[j], rows, d, f"hbm_sort{j}"), sets=NS)
+    report("embed_sort (radix sort of (id, token) only)", f"{name}: N={B*S} rows={rows}", B * S * 4 * 3, ms_sort)
+    ms_seg = timed(lambda j: ops.embed_bwd_sorted(douts[j], d, 0, d, B * S, rows, tg, f"hbm_sort{j}"), sets=NS)
+    report("embed_bwd_sorted (segment sums + table zero-fill, ids pre-sorted)",
+           f"{name}: N={B*S} U={U} d={d} rows={rows}", alg, ms_seg,
+           frac_incl_zero_fill=round((alg + rows * d * 4) / (ms_seg * 1e-3) / 1e9 / PEAK, 3))
     del table, outs, douts, tg
 
 for B, V, k in ((1184, 1_000_000, 100), (9472, 54293, 100), (1184, 1_000_000, 10)):  # whole waves of 2 CTAs x 148 SMs
