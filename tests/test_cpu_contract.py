@@ -473,3 +473,31 @@ def test_vocab_forward_planner_invariants():
             n_slots_m = ((m + 1) * n_v - 1) // q - (m * n_v) // q + 1
             assert len(pieces) == n_slots_m
     assert L.b4cp_vocab_ce_plan(ctypes.c_long(7424), 1_000_000, 256, out) == 0 and out[0] == 0
+
+
+def test_table_exchange_plan_is_by_size(monkeypatch):
+    """EncoderEngine.plan_table_exchange (host logic): a table goes by row exchange only when a
+    step's gathered token rows are much smaller than the table, and the store then leaves it out
+    of the data-parallel all-reduce."""
+    import types
+    import torch.distributed as dist
+    from bert4clickpath_b200 import engine as E
+
+    class FakeParam:
+        def __init__(self):
+            self.grad_is_global = False
+
+    eng = E.EncoderEngine.__new__(E.EncoderEngine)
+    eng.rows, eng.dims, eng.d = [1_000_011, 61], [240, 16], 256
+    eng.store = {"emb.0": FakeParam(), "emb.1": FakeParam()}
+    monkeypatch.setattr(dist, "is_initialized", lambda: True)
+    monkeypatch.setattr(dist, "get_world_size", lambda group=None: 8)
+    plan, world = eng.plan_table_exchange(256 * 202)           # C4: 424 MB of rows vs a 960 MB table
+    assert world == 8 and plan == [True, False]
+    assert eng.store["emb.0"].grad_is_global and not eng.store["emb.1"].grad_is_global
+    eng.rows, eng.dims, eng.d = [54304], [64], 64
+    eng.store = {"emb.0": FakeParam()}
+    assert eng.plan_table_exchange(4096 * 52)[0] == [False]    # C1: 436 MB of rows vs a 13.9 MB table
+    monkeypatch.setattr(dist, "get_world_size", lambda group=None: 1)
+    eng.rows, eng.dims, eng.d = [1_000_011], [256], 256
+    assert eng.plan_table_exchange(256 * 202)[0] == [False]    # one rank: nothing to exchange

@@ -189,6 +189,39 @@ def test_embed_bwd_sorted_scatter_add(cuda_lib, B, S, rows):
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])  # reproducible
 
 
+@pytest.mark.parametrize("rate", [0.0, 0.25])
+def test_embed_sort_then_sorted_sums_equal_the_one_call_backward(cuda_lib, rate):
+    """b4cp_embed_sort (gradient-independent, run early on a side stream by the engine) followed
+    by b4cp_embed_bwd_sorted is bit-identical to b4cp_embed_bwd, dropout mask included; and
+    b4cp_dropout_apply produces the masked gradient the data-parallel row exchange gathers."""
+    from bert4clickpath_b200 import ops
+    rng = np.random.default_rng(3)
+    B, S, rows, d = 96, 52, 54304, 64
+    ids = np.minimum(rng.zipf(1.3, size=(B, S)) + 9, rows - 1).astype(np.int32)
+    ids[rng.random((B, S)) < 0.15] = 1
+    dout = dev(rng.normal(size=(B * S, d)).astype(np.float32))
+    idd = dev(ids.reshape(-1))
+    g_one, g_two, g_three = (torch.empty((rows, d), device="cuda") for _ in range(3))
+    ops.embed_bwd(dout, d, 0, d, idd, rows, g_one, dropout_rate=rate, seed=5, site=1)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        ops.embed_sort(idd, rows, d, "test_sorted")
+    torch.cuda.current_stream().wait_stream(side)
+    ops.embed_bwd_sorted(dout, d, 0, d, B * S, rows, g_two, "test_sorted", dropout_rate=rate, seed=5, site=1)
+    torch.cuda.synchronize()
+    assert torch.equal(g_one, g_two)
+    # mask applied up front (what the row exchange does before gathering), then no dropout inside
+    masked = dout.clone()
+    ops.dropout_apply(masked, rate, 5, 1)
+    if rate > 0:
+        m = ops.dropout_mask(B * S * d, rate, 5, 1).view(B * S, d)
+        assert torch.equal(masked, dout * m)
+    ops.embed_bwd(masked, d, 0, d, idd, rows, g_three)
+    torch.cuda.synchronize()
+    assert torch.equal(g_one, g_three)
+
+
 # ------------------------------------------------------------------------------- attention
 @pytest.mark.parametrize("B,S,H,dh", [(4, 53, 2, 32), (3, 5, 1, 8), (2, 103, 4, 32), (2, 203, 4, 64),
                                       (3, 202, 2, 32), (2, 256, 1, 64), (2, 129, 2, 32),
