@@ -624,16 +624,25 @@ def run_ours(args, rank, world, local_rank):
     ops.TIMER.reset()
     ops.TIMER.enabled = True
     launches0 = _lib.lib().b4cp_launch_count()
-    head_start = int(8e-3 * 1.9e9)   # cycles
+    head_start = int(25e-3 * 1.9e9)   # cycles
 
+    # An eagerly launched step issues ~110 kernels + event records from Python, more slowly than a
+    # graph replay but faster than the device executes them: ONE head start (the device spins 25 ms
+    # first) keeps the host ahead for all n_kt + 1 steps, so no event bracket contains a launch gap
+    # and every step but the first runs in the steady state of the graph-replayed loop.  (Round 2
+    # span before EVERY step: the tensor-heavy kernels then started ~1 ms after an idle period and
+    # measured 7-10 % slower than in steady state - scripts/probe_fwd_context.py: 0.89 ms after a
+    # 10 ms spin against 0.83 ms otherwise.)  The first step's brackets are dropped.
     def eager_step(i):
-        # an eagerly launched step issues ~140 kernels + event records from Python: give the host
-        # a head start (the device spins first) so that no event bracket contains a launch gap
-        torch.cuda._sleep(head_start)
-        return trainer.step_device(dev[i % n_ring])
+        if i == 0:
+            torch.cuda._sleep(head_start)
+        r = trainer.step_device(dev[i % n_ring])
+        if i == 0:
+            ops.TIMER.reset()
+        return r
 
-    kt_region_ms, _ = timed(eager_step, n_kt)
-    launches_per_step = (_lib.lib().b4cp_launch_count() - launches0) // n_kt
+    kt_region_ms, _ = timed(eager_step, n_kt + 1)
+    launches_per_step = (_lib.lib().b4cp_launch_count() - launches0) // (n_kt + 1)
     launches = launches_per_step * args.steps
     ops.TIMER.enabled = False
     kt = ops.TIMER.totals_ms()
@@ -769,8 +778,8 @@ def run_ours(args, rank, world, local_rank):
     # roofline of the dominant kernel, vocab_ce_fwd_kernel: per launch it needs S = X W (2MhV) and
     # U = P' W^T for dX (2MhV) -> 4*M*h*V algorithmic flops; the backward kernel (S recompute is
     # not algorithmic, dW is: 2MhV) and the whole stage (6MhV over fwd + dx + bwd) ride along.
-    # The kernels are event-timed over n_kt eagerly launched steps, each after an idle head start
-    # for the host (device spinning): bursts of a few ms at full clock -> the BURST peak.
+    # The kernels are event-timed over n_kt eagerly launched steps issued back to back behind one
+    # head start for the host: a region of a few tens of ms at full clock -> the BURST peak.
     h = CFG["head_dims"][-1]
     step_ms = ms_total / args.steps
     peak, peak_src = pick_peak(pk, kt_ms * 1e-3)

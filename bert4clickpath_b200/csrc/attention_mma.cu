@@ -822,8 +822,14 @@ static int launch_bwd(const void* qkv, const void* dout, const float* lse, const
 
 bool attention_mma_supported(int S, int dh) { return S <= LSP && (dh == 32 || dh == 64); }
 
+// tcgen05 / TMEM / TMA kernels (attention_umma.cu): head depth 32, S <= 128
+bool attention_umma_supported(int S, int H, int dh);
+int attention_umma_fwd(const void* qkv, const int32_t* ids, int B, int S, int H, void* out,
+                       float* lse, cudaStream_t st);
+
 int attention_mma_fwd(const void* qkv, const int32_t* ids, int B, int S, int H, int dh, void* out,
                       float* lse, cudaStream_t st) {
+  if (attention_umma_supported(S, H, dh)) return attention_umma_fwd(qkv, ids, B, S, H, out, lse, st);
   if (S > 128)
     return dh == 32 ? launch_fwd_long<32>(qkv, ids, B, S, H, out, lse, st)
                     : launch_fwd_long<64>(qkv, ids, B, S, H, out, lse, st);

@@ -1,0 +1,480 @@
+// tcgen05 / TMEM / TMA path of the fused short-sequence masked self-attention, head depth 32:
+// clickstream_transformer/transformer.py:64-97 (scaled_dot_product_attention with the additive
+// -1e9 key padding mask of create_padding_mask :38-41) and :130-156 (split / merge heads).
+//
+// The per-(sequence, head) products of the reference's configurations are 52x52x32 - far below a
+// 128-row UMMA tile - so a work ITEM packs them: for S <= 64, two sequences (64 TMEM lanes each)
+// and the two heads that share a 64-column (128-byte) slice of the fused (q | k | v) rows; for
+// 64 < S <= 128, one sequence and the same two heads.  The item's Q, K and V tiles (128 rows x 128
+// bytes each, 128-byte swizzle) arrive with one 3-D TMA box per operand straight from the
+// [B][S][3d] activation - rows past S and sequences past B are zero-filled by the TMA unit - into
+// a 2-stage ring.
+//
+//   S_h  = Q_h K_h^T        tcgen05.mma, A and B K-major from shared memory (K = 32: two steps at
+//                           byte offset 64 h inside the swizzled rows), 128 x 128 fp32 in TMEM.
+//                           With two sequences per tile only the two diagonal 64 x 64 blocks are
+//                           meaningful; the off-diagonal blocks are never read.
+//   P_h  = exp2(S_h c + mask - max)   one thread per (query row, head) reads its row from TMEM
+//                           (tcgen05.ld), and writes the un-normalised bf16 probabilities back to
+//                           TMEM IN PLACE of the scores (tcgen05.st), zeros in the off-diagonal
+//                           block: P never touches shared memory.
+//   O_h  = P_h V            tcgen05.mma, A from TMEM (TS form), B = the V tile read MN-major.
+//   out  = O_h / rowsum     read back with tcgen05.ld, scaled, packed to bf16, 64-byte row stores.
+//
+// Warp roles (320 threads, 2 CTAs per SM so that one CTA's softmax overlaps the other's tensor and
+// TMA phases): warps 0-7 epilogue (warp w: TMEM lanes 32 (w % 4), head slot w / 4), warp 8 TMA
+// producer + TMEM owner, warp 9 MMA issuer.  TMEM: 256 columns per CTA, per head [P (64 packed
+// columns) | O (64 columns)] over the 128 columns S occupied.
+//
+// The backward kernel (same items, Q / K / V / dO tiles) computes both orientations on the tensor
+// cores - S, dP = dO V^T with queries on lanes for dQ = dZ K, and S^T, dP^T = V dO^T with keys on
+// lanes for dV = P^T dO and dK = dZ^T Q - so no transposition and no atomics are needed.
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+
+#include "../../include/b4cp.h"
+#include "common.cuh"
+
+namespace b4cp {
+
+static constexpr int AU_THREADS = 320;
+static constexpr int AU_WARP_TMA = 8, AU_WARP_MMA = 9;
+static constexpr int AU_EPI_WARPS = 8;
+static constexpr int AU_NST = 2;                      // stages of the operand ring
+static constexpr int AU_TILE = 128 * 128;             // bytes: 128 rows x 64 bf16
+static constexpr float AU_LOG2E = 1.4426950408889634f;
+static constexpr float AU_LN2 = 0.6931471805599453f;
+static constexpr float AU_PAD2 = -1.0e9f * 1.4426950408889634f;   // the -1e9 mask in log2 units
+
+__device__ __forceinline__ float au_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ uint32_t au_pack(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ void tma_load_3d_el(uint32_t smem_dst, const CUtensorMap* m,
+                                               uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];\n\t}" ::"r"(smem_dst),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
+// 32 lanes x 32 columns <- one register (zero fill without 32 live registers)
+__device__ __forceinline__ void tmem_st32_same(uint32_t taddr, uint32_t v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, "
+      "%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr),
+      "r"(v)
+      : "memory");
+}
+
+struct AttnUmmaParams {
+  const int32_t* ids;     // [B][S] ids of the first feature (0 = pad)
+  __nv_bfloat16* out;     // forward: [B*S][d]
+  float* lse;             // [B][H][S]
+  __nv_bfloat16* dqkv;    // backward: [B*S][3d]
+  int B, S, H, d;
+  int n_boxes;            // d / 64
+  int n_items;            // ceil(B / SEQS) * n_boxes
+  float scale2;           // log2(e) / sqrt(dh)
+  float scale;            // 1 / sqrt(dh)
+};
+
+// mask value (log2 units) of key j of a row whose 32-key group has validity bits `len` and pad
+// bits `pad`
+__device__ __forceinline__ float au_mask(uint32_t len, uint32_t pad, int j) {
+  return ((len >> j) & 1u) ? (((pad >> j) & 1u) ? AU_PAD2 : 0.f) : -INFINITY;
+}
+
+// ================================================================================= forward
+// SEQS = 2: S <= 64, lanes [0,64) hold sequence 2p, lanes [64,128) sequence 2p+1; a row's keys are
+//           the 64 columns of its own diagonal block.
+// SEQS = 1: 64 < S <= 128, all 128 columns are the row's keys.
+template <int SEQS>
+__global__ void __launch_bounds__(AU_THREADS, 2)
+attention_umma_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnUmmaParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AU_NST * 3 * AU_TILE);
+  uint64_t* full = bars;             // [2] TMA -> MMA
+  uint64_t* empty = bars + 2;        // [2] MMA (P V retired) -> TMA
+  uint64_t* s_full = bars + 4;       // S of both heads in TMEM
+  uint64_t* p_full = bars + 5;       // 8 warps: P written
+  uint64_t* o_full = bars + 6;       // O of both heads in TMEM
+  uint64_t* o_read = bars + 7;       // 8 warps: O read, TMEM free for the next item
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  // per stage: keep bits of the item's keys [4 x 32] (SEQS = 2: sequence slot s, group g at 2s+g)
+  // and, per sequence slot, whether every key of the sequence is a pad
+  uint32_t* masks = reinterpret_cast<uint32_t*>(bars + 10);   // [AU_NST][8]
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const int n_mine = ((int)blockIdx.x < p.n_items)
+                         ? (p.n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x
+                         : 0;
+
+  if (warp == AU_WARP_TMA) {
+    if (lane == 0) tma_prefetch_desc(&tmQKV);
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  } else if (warp == AU_WARP_MMA && lane == 0) {
+    for (int s = 0; s < AU_NST; ++s) {
+      mbar_init(&full[s], 2);   // the TMA bytes (expect_tx arrival) + the key masks
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(p_full, AU_EPI_WARPS);
+    mbar_init(o_full, 1);
+    mbar_init(o_read, AU_EPI_WARPS);
+    fence_barrier_init();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+
+  if (warp == AU_WARP_TMA) {
+    const uint32_t a0 = smem_u32(smem);
+    for (int i = 0; i < n_mine; ++i) {
+      const int item = (int)blockIdx.x + i * (int)gridDim.x;
+      const int grp = item / p.n_boxes, box = item - grp * p.n_boxes;
+      const int st = i % AU_NST;
+      mbar_wait_all(&empty[st], (uint32_t)((i / AU_NST) & 1) ^ 1);
+      mbar_expect_tx_el(&full[st], 3u * AU_TILE);
+      const uint32_t dst = a0 + (uint32_t)(st * 3 * AU_TILE);
+#pragma unroll
+      for (int o = 0; o < 3; ++o)
+        tma_load_3d_el(dst + o * AU_TILE, &tmQKV, &full[st], o * p.d + box * 64, 0, grp * SEQS);
+      // Key masks of the item, while its tiles are in flight.  keep: keys that take part in the
+      // softmax.  A pad key's additive -1e9 (create_padding_mask) gives it exactly zero
+      // probability next to any unpadded key, so it is simply left out; if EVERY key of the
+      // sequence is a pad, fp32 absorbs the scores into the -1e9 and the reference's softmax is
+      // uniform over the S keys: keep = all S keys, flagged so that the scores are ignored.
+      uint32_t keep[4], len[4];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int b = SEQS == 2 ? grp * 2 + (g >> 1) : grp;
+        const int j = (SEQS == 2 ? (g & 1) : g) * 32 + lane;
+        const bool in = b < p.B && j < p.S;
+        const int id = in ? __ldg(p.ids + (size_t)b * p.S + j) : 1;
+        len[g] = __ballot_sync(0xffffffffu, in);
+        keep[g] = __ballot_sync(0xffffffffu, in && id != 0);
+      }
+      uint32_t allpad[2];
+      if (SEQS == 2) {
+        allpad[0] = (keep[0] | keep[1]) == 0u;
+        allpad[1] = (keep[2] | keep[3]) == 0u;
+      } else {
+        allpad[0] = allpad[1] = (keep[0] | keep[1] | keep[2] | keep[3]) == 0u;
+      }
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+        if (allpad[SEQS == 2 ? (g >> 1) : 0]) keep[g] = len[g];
+      // a sequence past B: one kept key keeps the arithmetic of its (never stored) rows finite
+      if (SEQS == 2) {
+        if ((keep[0] | keep[1]) == 0u) keep[0] = 1u;
+        if ((keep[2] | keep[3]) == 0u) keep[2] = 1u;
+      } else if ((keep[0] | keep[1] | keep[2] | keep[3]) == 0u) {
+        keep[0] = 1u;
+      }
+      if (lane < 4) masks[st * 8 + lane] = lane == 0 ? keep[0] : lane == 1 ? keep[1] : lane == 2 ? keep[2] : keep[3];
+      if (lane >= 4 && lane < 6) masks[st * 8 + lane] = allpad[lane - 4];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full[st]);
+    }
+  } else if (warp == AU_WARP_MMA) {
+    const uint32_t id_s = umma_idesc_bf16(128, 128, 0, 0);
+    const uint32_t id_o = umma_idesc_bf16(128, 64, 0, 1);
+    const uint32_t a0 = smem_u32(smem);
+    const uint64_t dK0 = umma_smem_desc(a0, 16, 1024);       // K-major tiles (Q, K)
+    const uint64_t dV0 = umma_smem_desc(a0, 8192, 1024);     // MN-major tile (V)
+    for (int i = 0; i < n_mine; ++i) {
+      const int st = i % AU_NST;
+      const uint32_t so = (uint32_t)(st * 3 * AU_TILE);
+      mbar_wait_all(&full[st], (uint32_t)((i / AU_NST) & 1));
+      if (i > 0) mbar_wait_all(o_read, (uint32_t)((i - 1) & 1));
+      tc_fence_after();
+#pragma unroll
+      for (int hs = 0; hs < 2; ++hs)
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk)
+          umma_bf16_el(tmem_base + hs * 128, dK0 + ((so + (uint32_t)(hs * 64 + kk * 32)) >> 4),
+                       dK0 + ((so + (uint32_t)(AU_TILE + hs * 64 + kk * 32)) >> 4), id_s,
+                       kk ? 1u : 0u);
+      umma_commit_el(s_full);
+      mbar_wait_all(p_full, (uint32_t)(i & 1));
+      tc_fence_after();
+#pragma unroll
+      for (int hs = 0; hs < 2; ++hs)
+#pragma unroll
+        for (int k8 = 0; k8 < 8; ++k8)
+          umma_bf16_ts_el(tmem_base + hs * 128 + 64, tmem_base + hs * 128 + k8 * 8,
+                          dV0 + ((so + (uint32_t)(2 * AU_TILE + k8 * 2048)) >> 4), id_o,
+                          k8 ? 1u : 0u);
+      umma_commit_el(o_full);
+      umma_commit_el(&empty[st]);
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue: thread = (row, head)
+    const int q = warp & 3, hs = warp >> 2;
+    const int row = 32 * q + lane;
+    const int sq = SEQS == 2 ? (q >> 1) : 0;            // sequence slot of this row
+    const int si = SEQS == 2 ? (row & 63) : row;        // query position
+    const uint32_t t_head = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(hs * 128);
+    constexpr int NG = SEQS == 2 ? 2 : 4;               // 32-key groups of a row
+    const uint32_t t_keys = t_head + (uint32_t)(SEQS == 2 ? sq * 64 : 0);   // the row's scores
+    const uint32_t t_p = t_head + (uint32_t)(SEQS == 2 ? sq * 32 : 0);      // its packed P
+    for (int i = 0; i < n_mine; ++i) {
+      const int item = (int)blockIdx.x + i * (int)gridDim.x;
+      const int grp = item / p.n_boxes, box = item - grp * p.n_boxes;
+      const int b = grp * SEQS + sq;
+      const int head = box * 2 + hs;
+      const bool seq_ok = b < p.B;
+      // the producer's key masks of this stage (its arrival on full[st] released them)
+      const int st = i % AU_NST;
+      mbar_wait(&full[st], (uint32_t)((i / AU_NST) & 1));
+      uint32_t keep[NG];
+#pragma unroll
+      for (int g = 0; g < NG; ++g) keep[g] = masks[st * 8 + (SEQS == 2 ? sq * 2 : 0) + g];
+      const bool allpad = masks[st * 8 + 4 + sq] != 0u;
+      const float sc = allpad ? 0.f : p.scale2;
+      const float bias = allpad ? AU_PAD2 : 0.f;
+      mbar_wait(s_full, (uint32_t)(i & 1));
+      tc_fence_after();
+      float sum;
+      float m2;
+      if constexpr (SEQS == 2) {
+        // the row's 64 scores stay in registers: one TMEM read
+        uint32_t ra[32], rb[32];
+        tmem_ld32(t_keys, ra);
+        tmem_ld32(t_keys + 32, rb);
+        tmem_ld_wait();
+        float m = -INFINITY;
+        if (keep[0] == 0xffffffffu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) m = fmaxf(m, __uint_as_float(ra[j]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            m = fmaxf(m, ((keep[0] >> j) & 1u) ? __uint_as_float(ra[j]) : -INFINITY);
+        }
+        if (keep[1] == 0xffffffffu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) m = fmaxf(m, __uint_as_float(rb[j]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            m = fmaxf(m, ((keep[1] >> j) & 1u) ? __uint_as_float(rb[j]) : -INFINITY);
+        }
+        m2 = fmaf(m, sc, bias);
+        const float2 sc2 = make_float2(sc, sc), nb2 = make_float2(bias - m2, bias - m2);
+        float2 acc = make_float2(0.f, 0.f);
+        // 8 packed columns (16 keys) per store: the packed values never need more than 8
+        // registers next to the 64 scores
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t pk[8];
+          const bool lo = c < 2;
+          const uint32_t kp = lo ? keep[0] : keep[1];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int j = (c & 1) * 16 + 2 * u;
+            const float2 z = __ffma2_rn(lo ? make_float2(__uint_as_float(ra[j]), __uint_as_float(ra[j + 1]))
+                                           : make_float2(__uint_as_float(rb[j]), __uint_as_float(rb[j + 1])),
+                                        sc2, nb2);
+            float e0 = au_ex2(z.x), e1 = au_ex2(z.y);
+            if (kp != 0xffffffffu) {
+              e0 = ((kp >> j) & 1u) ? e0 : 0.f;
+              e1 = ((kp >> (j + 1)) & 1u) ? e1 : 0.f;
+            }
+            acc = __fadd2_rn(acc, make_float2(e0, e1));
+            pk[u] = au_pack(e0, e1);
+          }
+          tmem_st8(t_p + c * 8, pk);
+        }
+        sum = acc.x + acc.y;
+        tmem_st32_same(t_head + (uint32_t)((1 - sq) * 32), 0u);   // the other sequence's keys
+      } else {
+        // 128 scores per row: two sweeps over TMEM (maximum, then probabilities)
+        float m = -INFINITY;
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+          uint32_t r[32];
+          tmem_ld32(t_keys + g * 32, r);
+          tmem_ld_wait();
+          if (keep[g] == 0xffffffffu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) m = fmaxf(m, __uint_as_float(r[j]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              m = fmaxf(m, ((keep[g] >> j) & 1u) ? __uint_as_float(r[j]) : -INFINITY);
+          }
+        }
+        m2 = fmaf(m, sc, bias);
+        const float2 sc2 = make_float2(sc, sc), nb2 = make_float2(bias - m2, bias - m2);
+        float2 acc = make_float2(0.f, 0.f);
+        // In-place is safe inside a thread: group g is read from columns [32g, 32g+32) before its
+        // 16 packed columns [16g, 16g+16) are written, and those lie below every group still to
+        // be read.
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+          uint32_t r[32], pk[16];
+          tmem_ld32(t_keys + g * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            const float2 z = __ffma2_rn(make_float2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])), sc2, nb2);
+            float e0 = au_ex2(z.x), e1 = au_ex2(z.y);
+            if (keep[g] != 0xffffffffu) {
+              e0 = ((keep[g] >> j) & 1u) ? e0 : 0.f;
+              e1 = ((keep[g] >> (j + 1)) & 1u) ? e1 : 0.f;
+            }
+            acc = __fadd2_rn(acc, make_float2(e0, e1));
+            pk[j >> 1] = au_pack(e0, e1);
+          }
+          tmem_st16(t_p + g * 16, pk);
+        }
+        sum = acc.x + acc.y;
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive_warp(p_full);
+      const bool row_ok = seq_ok && si < p.S;
+      if (row_ok && p.lse)
+        p.lse[((size_t)b * p.H + head) * p.S + si] = (m2 + __log2f(sum)) * AU_LN2;
+      const float inv = 1.f / sum;
+      const float2 inv2 = make_float2(inv, inv);
+      mbar_wait(o_full, (uint32_t)(i & 1));
+      tc_fence_after();
+      uint32_t o[32];
+      tmem_ld32(t_head + 64 + hs * 32, o);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive_warp(o_read);
+      if (row_ok) {
+        uint4* dst = reinterpret_cast<uint4*>(p.out + ((size_t)b * p.S + si) * p.d + box * 64 + hs * 32);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          float2 v[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            v[u] = __fmul2_rn(make_float2(__uint_as_float(o[8 * c + 2 * u]), __uint_as_float(o[8 * c + 2 * u + 1])), inv2);
+          dst[c] = make_uint4(au_pack(v[0].x, v[0].y), au_pack(v[1].x, v[1].y),
+                              au_pack(v[2].x, v[2].y), au_pack(v[3].x, v[3].y));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == AU_WARP_TMA) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+// ================================================================================= host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn au_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) ==
+            cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+// bf16 [B][S][width] activation (row stride ld elements) as a 3-D tensor: box = 64 columns x
+// `box_rows` positions x `box_seqs` sequences, 128-byte swizzle, zero fill out of bounds
+static int make_tmap_seq3d(CUtensorMap* map, const void* base, int width, int ld, int S, int B,
+                           int box_rows, int box_seqs) {
+  EncodeTiledFn fn = au_encode_fn();
+  if (!fn) {
+    set_last_error("cuTensorMapEncodeTiled entry point not available");
+    return -2;
+  }
+  cuuint64_t dims[3] = {(cuuint64_t)width, (cuuint64_t)S, (cuuint64_t)B};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)S * ld * 2};
+  cuuint32_t box[3] = {64u, (cuuint32_t)box_rows, (cuuint32_t)box_seqs};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("attention: cuTensorMapEncodeTiled failed (%d): base=%p width=%d ld=%d S=%d B=%d",
+                   (int)r, base, width, ld, S, B);
+    return -3;
+  }
+  return 0;
+}
+
+static int au_num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+bool attention_umma_supported(int S, int H, int dh) {
+  static const bool off = getenv("B4CP_ATTN_MMA_SYNC") != nullptr;
+  return !off && dh == 32 && (H % 2) == 0 && S >= 1 && S <= 128;
+}
+
+int attention_umma_fwd(const void* qkv, const int32_t* ids, int B, int S, int H, void* out,
+                       float* lse, cudaStream_t st) {
+  const int d = H * 32;
+  const int seqs = S <= 64 ? 2 : 1;
+  CUtensorMap tm;
+  int rc = make_tmap_seq3d(&tm, qkv, 3 * d, 3 * d, S, B, seqs == 2 ? 64 : 128, seqs);
+  if (rc) return rc;
+  AttnUmmaParams p{};
+  p.ids = ids;
+  p.out = (__nv_bfloat16*)out;
+  p.lse = lse;
+  p.B = B;
+  p.S = S;
+  p.H = H;
+  p.d = d;
+  p.n_boxes = d / 64;
+  p.n_items = ((B + seqs - 1) / seqs) * p.n_boxes;
+  p.scale = 1.f / sqrtf(32.f);
+  p.scale2 = AU_LOG2E / sqrtf(32.f);
+  const int smem = AU_NST * 3 * AU_TILE + 1024 + 256;
+  static const int grid_cap = getenv("B4CP_ATTN_GRID") ? atoi(getenv("B4CP_ATTN_GRID")) : 0;   // experiments
+  const int grid = std::min(p.n_items, grid_cap > 0 ? grid_cap : 2 * au_num_sms());
+  if (seqs == 2) {
+    B4CP_CUDA(cudaFuncSetAttribute(attention_umma_fwd_kernel<2>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attention_umma_fwd_kernel<2><<<grid, AU_THREADS, smem, st>>>(tm, p);
+  } else {
+    B4CP_CUDA(cudaFuncSetAttribute(attention_umma_fwd_kernel<1>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attention_umma_fwd_kernel<1><<<grid, AU_THREADS, smem, st>>>(tm, p);
+  }
+  return 0;
+}
+
+}  // namespace b4cp

@@ -22,4 +22,6 @@ tf = t(lambda: ops.attention_fwd(qkv, ids, B, S, H, dh, out, lse))
 tb = t(lambda: ops.attention_bwd(qkv, do, lse, ids, B, S, H, dh, dqkv, out=out))
 tbs = t(lambda: ops.attention_bwd(qkv, do, lse, ids, B, S, H, dh, dqkv))
 fl = 4.0 * B * H * S * S * dh
+by_f = B * S * d * 2 * 4.0; by_b = B * S * d * 2 * 7.0
+print(f"  HBM bytes (algorithmic): fwd {by_f/1e6:.0f} MB -> {by_f/tf/1e6:.0f} GB/s, bwd {by_b/1e6:.0f} MB -> {by_b/tb/1e6:.0f} GB/s")
 print(f"B={B} S={S} H={H} dh={dh}: fwd {tf:.3f} ms ({fl/tf/1e9:.1f} TF/s), bwd(tensor) {tb:.3f} ms ({2.5*fl/tb/1e9:.1f} TF/s), bwd(out=None -> {'SIMT' if S > 128 else 'tensor'}) {tbs:.3f} ms")

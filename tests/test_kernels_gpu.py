@@ -225,7 +225,12 @@ def test_embed_sort_then_sorted_sums_equal_the_one_call_backward(cuda_lib, rate)
 # ------------------------------------------------------------------------------- attention
 @pytest.mark.parametrize("B,S,H,dh", [(4, 53, 2, 32), (3, 5, 1, 8), (2, 103, 4, 32), (2, 203, 4, 64),
                                       (3, 202, 2, 32), (2, 256, 1, 64), (2, 129, 2, 32),
-                                      (2, 114, 2, 64)])
+                                      (2, 114, 2, 64),
+                                      # tcgen05 path (head depth 32, S <= 128): odd batch (half-empty
+                                      # tile), full 64 / 128 rows, two column boxes, several items per CTA
+                                      (5, 52, 2, 32), (3, 64, 2, 32), (2, 33, 4, 32), (1, 7, 2, 32),
+                                      (701, 52, 2, 32), (3, 128, 2, 32), (2, 65, 6, 32),
+                                      (311, 100, 2, 32)])
 def test_attention_fwd_bwd(cuda_lib, B, S, H, dh):
     from bert4clickpath_b200 import ops
     rng = np.random.default_rng(S)
