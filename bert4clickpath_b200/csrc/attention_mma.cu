@@ -840,8 +840,14 @@ int attention_mma_fwd(const void* qkv, const int32_t* ids, int B, int S, int H, 
   return launch_fwd<2, 64>(qkv, ids, B, S, H, out, lse, st);
 }
 
+bool attention_umma_bwd_supported(int S, int H, int dh);
+int attention_umma_bwd(const void* qkv, const void* dout, const float* lse, const int32_t* ids,
+                       int B, int S, int H, void* dqkv, cudaStream_t st);
+
 int attention_mma_bwd(const void* qkv, const void* fwd_out, const void* dout, const float* lse,
                       const int32_t* ids, int B, int S, int H, int dh, void* dqkv, cudaStream_t st) {
+  if (attention_umma_bwd_supported(S, H, dh))
+    return attention_umma_bwd(qkv, dout, lse, ids, B, S, H, dqkv, st);
   if (S > 128) {
     if (!fwd_out) {
       set_last_error("attention_bwd: S=%d > 128 needs the forward output (delta = rowsum(dO o O))", S);

@@ -77,6 +77,24 @@ __device__ __forceinline__ void tmem_st32_same(uint32_t taddr, uint32_t v) {
       : "memory");
 }
 
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, uint32_t smem_src, int c0, int c1,
+                                             int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+// the 256 threads of the 8 epilogue warps
+__device__ __forceinline__ void au_epi_sync() {
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+}
+
 struct AttnUmmaParams {
   const int32_t* ids;     // [B][S] ids of the first feature (0 = pad)
   __nv_bfloat16* out;     // forward: [B*S][d]
@@ -384,6 +402,303 @@ attention_umma_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnU
   }
 }
 
+// ================================================================================= backward
+// S <= 64: an item is the forward's - two sequences x the two heads of a 64-column box - with the
+// Q, K, V and dO tiles in a 2-stage ring (64 KB per stage).  One CTA per SM, all 512 TMEM columns:
+//
+//   phase 1 (tensor):  S_h = Q_h K_h^T and dP_h = dO_h V_h^T for both heads, lanes = (sequence,
+//                      query), four 128-column accumulators.
+//   phase 2 (threads): thread (row, head) reads its 64 scores and 64 dP values, forms
+//                      P = exp2(S c - lse), delta = sum_j P dP, dZ = P (dP - delta) / sqrt(dh) and
+//                      writes the bf16 rows of P and dZ into shared memory, 128-byte swizzled, as
+//                      per-sequence tiles [head][query][key] (16 KB each).
+//   phase 3 (tensor):  the SAME bytes are read through two descriptors (as the vocabulary kernels
+//                      read a W tile both ways): K-major, rows = (head, query), for
+//                      dQ_s = dZ_s K_s; MN-major, rows = (head, key), for dK_s = dZ_s^T Q_s and
+//                      dV_s = P_s^T dO_s - the transposed products need no transposition, no
+//                      second orientation of the scores and no atomics.  B operands are the stage
+//                      tiles of sequence s read MN-major over all 64 columns (a head's lanes use
+//                      its own 32).  Six 64-column accumulators reuse the score columns.
+//   phase 4 (threads): accumulators -> bf16 -> dqkv (64-byte row stores).
+static constexpr int AB_STAGE = 4 * AU_TILE;          // Q, K, V, dO
+static constexpr int AB_PZ = 4 * AU_TILE;             // P[2 sequences], dZ[2 sequences]
+
+__global__ void __launch_bounds__(AU_THREADS, 1)
+attention_umma_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV,
+                          const __grid_constant__ CUtensorMap tmDO,
+                          const __grid_constant__ CUtensorMap tmDQKV, const AttnUmmaParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* sPZ = smem + AU_NST * AB_STAGE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sPZ + AB_PZ);
+  uint64_t* full = bars;             // [2] TMA bytes + key masks
+  uint64_t* empty = bars + 2;        // [2] phase 3 retired
+  uint64_t* s_full = bars + 4;       // phase 1 retired
+  uint64_t* pz_full = bars + 5;      // 8 warps: P / dZ in shared memory, scores consumed
+  uint64_t* acc_full = bars + 6;     // phase 3 retired
+  uint64_t* acc_read = bars + 7;     // 8 warps: accumulators drained
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint32_t* masks = reinterpret_cast<uint32_t*>(bars + 10);   // [AU_NST][8]
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const int n_mine = ((int)blockIdx.x < p.n_items)
+                         ? (p.n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x
+                         : 0;
+
+  if (warp == AU_WARP_TMA) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmQKV);
+      tma_prefetch_desc(&tmDO);
+      tma_prefetch_desc(&tmDQKV);
+    }
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  } else if (warp == AU_WARP_MMA && lane == 0) {
+    for (int s = 0; s < AU_NST; ++s) {
+      mbar_init(&full[s], 2);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(pz_full, AU_EPI_WARPS);
+    mbar_init(acc_full, 1);
+    mbar_init(acc_read, AU_EPI_WARPS);
+    fence_barrier_init();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+
+  if (warp == AU_WARP_TMA) {
+    const uint32_t a0 = smem_u32(smem);
+    for (int i = 0; i < n_mine; ++i) {
+      const int item = (int)blockIdx.x + i * (int)gridDim.x;
+      const int grp = item / p.n_boxes, box = item - grp * p.n_boxes;
+      const int st = i % AU_NST;
+      mbar_wait_all(&empty[st], (uint32_t)((i / AU_NST) & 1) ^ 1);
+      mbar_expect_tx_el(&full[st], 4u * AU_TILE);
+      const uint32_t dst = a0 + (uint32_t)(st * AB_STAGE);
+#pragma unroll
+      for (int o = 0; o < 3; ++o)
+        tma_load_3d_el(dst + o * AU_TILE, &tmQKV, &full[st], o * p.d + box * 64, 0, grp * 2);
+      tma_load_3d_el(dst + 3 * AU_TILE, &tmDO, &full[st], box * 64, 0, grp * 2);
+      // key masks (see the forward kernel): [2 s + g] keep bits, [4 + s] all-pad flag
+      uint32_t keep[4], len[4];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int b = grp * 2 + (g >> 1);
+        const int j = (g & 1) * 32 + lane;
+        const bool in = b < p.B && j < p.S;
+        const int id = in ? __ldg(p.ids + (size_t)b * p.S + j) : 1;
+        len[g] = __ballot_sync(0xffffffffu, in);
+        keep[g] = __ballot_sync(0xffffffffu, in && id != 0);
+      }
+      uint32_t allpad[2];
+      allpad[0] = (keep[0] | keep[1]) == 0u;
+      allpad[1] = (keep[2] | keep[3]) == 0u;
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+        if (allpad[g >> 1]) keep[g] = len[g];
+      if (lane < 4) masks[st * 8 + lane] = lane == 0 ? keep[0] : lane == 1 ? keep[1] : lane == 2 ? keep[2] : keep[3];
+      if (lane >= 4 && lane < 6) masks[st * 8 + lane] = allpad[lane - 4];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full[st]);
+    }
+  } else if (warp == AU_WARP_MMA) {
+    const uint32_t id_s = umma_idesc_bf16(128, 128, 0, 0);
+    const uint32_t id_q = umma_idesc_bf16(128, 64, 0, 1);    // dQ: A K-major, B MN-major
+    const uint32_t id_t = umma_idesc_bf16(128, 64, 1, 1);    // dK, dV: A MN-major, B MN-major
+    const uint32_t a0 = smem_u32(smem);
+    const uint32_t aPZ = smem_u32(sPZ);
+    const uint64_t dKm = umma_smem_desc(a0, 16, 1024);        // K-major view of a stage tile
+    const uint64_t dMn = umma_smem_desc(a0, 8192, 1024);      // MN-major view of a stage tile
+    const uint64_t dPZk = umma_smem_desc(aPZ, 16, 1024);      // P / dZ tiles, rows = (head, query)
+    const uint64_t dPZm = umma_smem_desc(aPZ, 8192, 1024);    // P / dZ tiles, rows = (head, key)
+    for (int i = 0; i < n_mine; ++i) {
+      const int st = i % AU_NST;
+      const uint32_t so = (uint32_t)(st * AB_STAGE);
+      mbar_wait_all(&full[st], (uint32_t)((i / AU_NST) & 1));
+      if (i > 0) mbar_wait_all(acc_read, (uint32_t)((i - 1) & 1));
+      tc_fence_after();
+      // ---- phase 1
+#pragma unroll
+      for (int hs = 0; hs < 2; ++hs)
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk) {
+          const uint32_t ko = (uint32_t)(hs * 64 + kk * 32);
+          umma_bf16_el(tmem_base + hs * 128, dKm + ((so + ko) >> 4),
+                       dKm + ((so + AU_TILE + ko) >> 4), id_s, kk ? 1u : 0u);
+          umma_bf16_el(tmem_base + 256 + hs * 128, dKm + ((so + 3 * AU_TILE + ko) >> 4),
+                       dKm + ((so + 2 * AU_TILE + ko) >> 4), id_s, kk ? 1u : 0u);
+        }
+      umma_commit_el(s_full);
+      mbar_wait_all(pz_full, (uint32_t)(i & 1));
+      tc_fence_after();
+      // ---- phase 3 (P[s] at aPZ + s * 16 KB, dZ[s] at aPZ + 32 KB + s * 16 KB)
+#pragma unroll
+      for (int sq = 0; sq < 2; ++sq) {
+        const uint32_t rows = (uint32_t)(sq * 8192);              // sequence sq's 64 rows of a tile
+        const uint32_t pP = (uint32_t)(sq * AU_TILE), pZ = (uint32_t)(2 * AU_TILE + sq * AU_TILE);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          // dQ_s = dZ_s K_s           (K = keys)
+          umma_bf16_el(tmem_base + sq * 64, dPZk + ((pZ + (uint32_t)(kk * 32)) >> 4),
+                       dMn + ((so + AU_TILE + rows + (uint32_t)(kk * 2048)) >> 4), id_q, kk ? 1u : 0u);
+          // dK_s = dZ_s^T Q_s         (K = queries)
+          umma_bf16_el(tmem_base + 128 + sq * 64, dPZm + ((pZ + (uint32_t)(kk * 2048)) >> 4),
+                       dMn + ((so + rows + (uint32_t)(kk * 2048)) >> 4), id_t, kk ? 1u : 0u);
+          // dV_s = P_s^T dO_s         (K = queries)
+          umma_bf16_el(tmem_base + 256 + sq * 64, dPZm + ((pP + (uint32_t)(kk * 2048)) >> 4),
+                       dMn + ((so + 3 * AU_TILE + rows + (uint32_t)(kk * 2048)) >> 4), id_t, kk ? 1u : 0u);
+        }
+      }
+      umma_commit_el(acc_full);
+      umma_commit_el(&empty[st]);
+    }
+  } else {
+    // ------------------------------------------------------------ threads: (row, head slot)
+    const int q = warp & 3, hs = warp >> 2;
+    const int row = 32 * q + lane;
+    const int sq = q >> 1;              // phase 2: sequence slot of this row
+    const int qi = row & 63;            //          query position
+    const uint32_t t_lane = tmem_base + ((uint32_t)(32 * q) << 16);
+    const uint32_t aPZ = smem_u32(sPZ);
+    // phase 4: TMEM lane = (head q >> 1, position (q & 1) * 32 + lane); warp group hs drains the
+    // accumulators of sequence hs
+    const int h4 = q >> 1, pos4 = (q & 1) * 32 + lane;
+    // -lse (log2 units) of this thread's row, fetched one item ahead; -inf for rows that do not
+    // exist -> P = 0
+    auto fetch_nb = [&](int i) -> float {
+      const int item = (int)blockIdx.x + i * (int)gridDim.x;
+      const int grp = item / p.n_boxes, box = item - grp * p.n_boxes;
+      const int b = grp * 2 + sq;
+      return (b < p.B && qi < p.S)
+                 ? -__ldg(p.lse + ((size_t)b * p.H + box * 2 + hs) * p.S + qi) * AU_LOG2E
+                 : -INFINITY;
+    };
+    float nb_next = n_mine > 0 ? fetch_nb(0) : 0.f;
+    for (int i = 0; i < n_mine; ++i) {
+      const int item = (int)blockIdx.x + i * (int)gridDim.x;
+      const int grp = item / p.n_boxes, box = item - grp * p.n_boxes;
+      const int st = i % AU_NST;
+      float nb = nb_next;
+      mbar_wait(&full[st], (uint32_t)((i / AU_NST) & 1));
+      const uint32_t keep0 = masks[st * 8 + sq * 2], keep1 = masks[st * 8 + sq * 2 + 1];
+      float sc = p.scale2;
+      if (masks[st * 8 + 4 + sq] != 0u) {   // every key a pad: uniform over the S keys
+        sc = 0.f;
+        if (nb != -INFINITY) nb = -__log2f((float)(__popc(keep0) + __popc(keep1)));
+      }
+      mbar_wait(s_full, (uint32_t)(i & 1));
+      tc_fence_after();
+      uint32_t ra[32], rb[32], da[32], db[32];
+      tmem_ld32(t_lane + hs * 128 + sq * 64, ra);
+      tmem_ld32(t_lane + hs * 128 + sq * 64 + 32, rb);
+      tmem_ld32(t_lane + 256 + hs * 128 + sq * 64, da);
+      tmem_ld32(t_lane + 256 + hs * 128 + sq * 64 + 32, db);
+      // the previous item's gradient tiles leave through TMA stores out of the P / dZ region:
+      // their reads of shared memory must be over before it is written again
+      if (i > 0) {
+        if (threadIdx.x == 0) tma_store_wait_read();
+        au_epi_sync();
+      }
+      tmem_ld_wait();
+      // P (kept in place of the scores) and delta = sum_j P_j dP_j
+      const float2 sc2 = make_float2(sc, sc), nb2 = make_float2(nb, nb);
+      float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int j = 0; j < 32; j += 2) {
+        float2 z = __ffma2_rn(make_float2(__uint_as_float(ra[j]), __uint_as_float(ra[j + 1])), sc2, nb2);
+        float e0 = au_ex2(z.x), e1 = au_ex2(z.y);
+        if (keep0 != 0xffffffffu) {
+          e0 = ((keep0 >> j) & 1u) ? e0 : 0.f;
+          e1 = ((keep0 >> (j + 1)) & 1u) ? e1 : 0.f;
+        }
+        ra[j] = __float_as_uint(e0);
+        ra[j + 1] = __float_as_uint(e1);
+        acc = __ffma2_rn(make_float2(e0, e1), make_float2(__uint_as_float(da[j]), __uint_as_float(da[j + 1])), acc);
+        z = __ffma2_rn(make_float2(__uint_as_float(rb[j]), __uint_as_float(rb[j + 1])), sc2, nb2);
+        e0 = au_ex2(z.x), e1 = au_ex2(z.y);
+        if (keep1 != 0xffffffffu) {
+          e0 = ((keep1 >> j) & 1u) ? e0 : 0.f;
+          e1 = ((keep1 >> (j + 1)) & 1u) ? e1 : 0.f;
+        }
+        rb[j] = __float_as_uint(e0);
+        rb[j + 1] = __float_as_uint(e1);
+        acc = __ffma2_rn(make_float2(e0, e1), make_float2(__uint_as_float(db[j]), __uint_as_float(db[j + 1])), acc);
+      }
+      const float delta = acc.x + acc.y;
+      // rows of P and dZ = P (dP - delta) / sqrt(dh) -> shared memory, 128-byte swizzle:
+      // tile [head][query][key], 16-byte chunk c of row r at chunk position c ^ (r & 7)
+      const uint32_t rowP = aPZ + (uint32_t)(sq * AU_TILE + hs * 8192 + (qi >> 3) * 1024 + (qi & 7) * 128);
+      const uint32_t rowZ = rowP + 2 * AU_TILE;
+      const float2 nd2 = make_float2(-delta, -delta), s2 = make_float2(p.scale, p.scale);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        uint32_t pw[4], zw[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int j = (c & 3) * 8 + 2 * u;
+          const float2 pv = c < 4 ? make_float2(__uint_as_float(ra[j]), __uint_as_float(ra[j + 1]))
+                                  : make_float2(__uint_as_float(rb[j]), __uint_as_float(rb[j + 1]));
+          const float2 dv = c < 4 ? make_float2(__uint_as_float(da[j]), __uint_as_float(da[j + 1]))
+                                  : make_float2(__uint_as_float(db[j]), __uint_as_float(db[j + 1]));
+          const float2 dz = __fmul2_rn(__fmul2_rn(pv, __fadd2_rn(dv, nd2)), s2);
+          pw[u] = au_pack(pv.x, pv.y);
+          zw[u] = au_pack(dz.x, dz.y);
+        }
+        const uint32_t off = (uint32_t)((c ^ (qi & 7)) << 4);
+        sts128(rowP + off, pw[0], pw[1], pw[2], pw[3]);
+        sts128(rowZ + off, zw[0], zw[1], zw[2], zw[3]);
+      }
+      fence_proxy_async_smem();     // generic-proxy stores -> visible to the tensor core's reads
+      tc_fence_before();
+      mbar_arrive_warp(pz_full);
+      if (i + 1 < n_mine) nb_next = fetch_nb(i + 1);
+      // ---- phase 4: accumulators -> bf16 tiles [sequence][position][64 columns] in the (now
+      // free) P / dZ region -> three TMA stores (rows past S and sequences past B are clipped)
+      mbar_wait(acc_full, (uint32_t)(i & 1));
+      tc_fence_after();
+      uint32_t gq[32], gk[32], gv[32];
+      tmem_ld32(t_lane + hs * 64 + h4 * 32, gq);
+      tmem_ld32(t_lane + 128 + hs * 64 + h4 * 32, gk);
+      tmem_ld32(t_lane + 256 + hs * 64 + h4 * 32, gv);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive_warp(acc_read);
+      const uint32_t rowO = aPZ + (uint32_t)(hs * 8192 + (pos4 >> 3) * 1024 + (pos4 & 7) * 128);
+#pragma unroll
+      for (int o = 0; o < 3; ++o) {
+        const uint32_t(&g)[32] = o == 0 ? gq : (o == 1 ? gk : gv);
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          sts128(rowO + (uint32_t)(o * AU_TILE) + (uint32_t)(((h4 * 4 + c) ^ (pos4 & 7)) << 4),
+                 au_pack(__uint_as_float(g[8 * c + 0]), __uint_as_float(g[8 * c + 1])),
+                 au_pack(__uint_as_float(g[8 * c + 2]), __uint_as_float(g[8 * c + 3])),
+                 au_pack(__uint_as_float(g[8 * c + 4]), __uint_as_float(g[8 * c + 5])),
+                 au_pack(__uint_as_float(g[8 * c + 6]), __uint_as_float(g[8 * c + 7])));
+      }
+      fence_proxy_async_smem();
+      au_epi_sync();
+      if (threadIdx.x == 0) {
+#pragma unroll
+        for (int o = 0; o < 3; ++o)
+          tma_store_3d(&tmDQKV, aPZ + (uint32_t)(o * AU_TILE), o * p.d + box * 64, 0, grp * 2);
+        tma_store_commit();
+      }
+    }
+    if (threadIdx.x == 0) tma_store_wait_read();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == AU_WARP_TMA) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 // ================================================================================= host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
@@ -474,6 +789,41 @@ int attention_umma_fwd(const void* qkv, const int32_t* ids, int B, int S, int H,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attention_umma_fwd_kernel<1><<<grid, AU_THREADS, smem, st>>>(tm, p);
   }
+  return 0;
+}
+
+bool attention_umma_bwd_supported(int S, int H, int dh) {
+  return attention_umma_supported(S, H, dh) && S <= 64;
+}
+
+int attention_umma_bwd(const void* qkv, const void* dout, const float* lse, const int32_t* ids,
+                       int B, int S, int H, void* dqkv, cudaStream_t st) {
+  const int d = H * 32;
+  CUtensorMap tmQ, tmD;
+  int rc = make_tmap_seq3d(&tmQ, qkv, 3 * d, 3 * d, S, B, 64, 2);
+  if (rc) return rc;
+  rc = make_tmap_seq3d(&tmD, dout, d, d, S, B, 64, 2);
+  if (rc) return rc;
+  CUtensorMap tmG;
+  rc = make_tmap_seq3d(&tmG, dqkv, 3 * d, 3 * d, S, B, 64, 2);
+  if (rc) return rc;
+  AttnUmmaParams p{};
+  p.ids = ids;
+  p.lse = const_cast<float*>(lse);
+  p.dqkv = (__nv_bfloat16*)dqkv;
+  p.B = B;
+  p.S = S;
+  p.H = H;
+  p.d = d;
+  p.n_boxes = d / 64;
+  p.n_items = ((B + 1) / 2) * p.n_boxes;
+  p.scale = 1.f / sqrtf(32.f);
+  p.scale2 = AU_LOG2E / sqrtf(32.f);
+  const int smem = AU_NST * AB_STAGE + AB_PZ + 1024 + 256;
+  const int grid = std::min(p.n_items, au_num_sms());
+  B4CP_CUDA(cudaFuncSetAttribute(attention_umma_bwd_kernel,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  attention_umma_bwd_kernel<<<grid, AU_THREADS, smem, st>>>(tmQ, tmD, tmG, p);
   return 0;
 }
 

@@ -8,6 +8,8 @@
 // memory as bf16 with an odd word stride, scores never touch HBM.
 #include <algorithm>
 
+#include <cstdlib>
+
 #include "common.cuh"
 #include "../../include/b4cp.h"
 
@@ -636,9 +638,61 @@ reduce_partials_wide_kernel(const float* __restrict__ partial, int P, long n, lo
   if (lane == 0) out[c] = s;
 }
 
+// The same sums for MANY partials (split-K over ~148 CTAs, one LayerNorm partial row per CTA of a
+// 2,368-CTA grid): the one-thread-per-column loop above is a chain of P dependent-latency loads
+// (13-14 us for a few KB of output).  Block = TX consecutive columns (coalesced) x TY partial
+// lanes; lane ty adds partials ty, ty+TY, ... eight independent loads at a time, then the TY lane
+// sums are added in lane order: a fixed association, deterministic.  Column c of segment
+// c / seg goes to out0 / out1 / out2 (LayerNorm: dgamma | dbeta | dbias; plain sums: seg = n).
+template <int TX, int TY>
+__global__ void __launch_bounds__(TX * TY)
+reduce_partials_2d_kernel(const float* __restrict__ partial, int P, long n, long stride, long seg,
+                          float* __restrict__ out0, float* __restrict__ out1,
+                          float* __restrict__ out2) {
+  __shared__ float red[TY][TX + 1];
+  const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
+  const long c = (long)blockIdx.x * TX + tx;
+  float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (c < n) {
+    const float* src = partial + c;
+    int p = ty;
+    for (; p + 7 * TY < P; p += 8 * TY) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = __ldg(src + (size_t)(p + u * TY) * stride);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) a[u] += v[u];
+    }
+    for (int u = 0; p < P; p += TY, ++u) a[u & 7] += __ldg(src + (size_t)p * stride);
+  }
+  red[ty][tx] = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+  __syncthreads();
+  if (ty == 0 && c < n) {
+    float t = 0.f;
+#pragma unroll 8
+    for (int y = 0; y < TY; ++y) t += red[y][tx];
+    const long k = c / seg;
+    float* out = k == 0 ? out0 : (k == 1 ? out1 : out2);
+    if (out) out[c - k * seg] = t;
+  }
+}
+
+static void launch_reduce_partials_seg(const float* partial, int P, long n, long stride, long seg,
+                                       float* out0, float* out1, float* out2, cudaStream_t st) {
+  if (P >= 512)
+    reduce_partials_2d_kernel<16, 64><<<ceil_div(n, 16), 1024, 0, st>>>(partial, P, n, stride, seg, out0, out1, out2);
+  else if (n <= 8192)
+    reduce_partials_2d_kernel<32, 32><<<ceil_div(n, 32), 1024, 0, st>>>(partial, P, n, stride, seg, out0, out1, out2);
+  else
+    reduce_partials_2d_kernel<32, 8><<<ceil_div(n, 32), 256, 0, st>>>(partial, P, n, stride, seg, out0, out1, out2);
+}
+
 static void launch_reduce_partials(const float* partial, int P, long n, long stride, float* out,
                                    cudaStream_t st) {
-  if (P >= 64 && n <= 4096)
+  static const bool old = getenv("B4CP_REDUCE_1D") != nullptr;   // the round-1 kernels (comparison)
+  if (P >= 16 && !old)
+    launch_reduce_partials_seg(partial, P, n, stride, n, out, nullptr, nullptr, st);
+  else if (P >= 64 && n <= 4096)
     reduce_partials_wide_kernel<<<ceil_div(n, 8), 256, 0, st>>>(partial, P, n, stride, out);
   else
     reduce_partials_kernel<<<ceil_div(n, 256), 256, 0, st>>>(partial, P, n, stride, out);
@@ -851,7 +905,10 @@ extern "C" int b4cp_residual_ln_bwd(const float* dy, const float* x, const float
   else if (d <= 128) residual_ln_bwd_kernel<4><<<blocks, 256, 0, st>>>(dy, x, r, T, d, gamma, dsp, 1e-6f, dx, drb, ld_bf16, dr_f32, partial);
   else residual_ln_bwd_kernel<8><<<blocks, 256, 0, st>>>(dy, x, r, T, d, gamma, dsp, 1e-6f, dx, drb, ld_bf16, dr_f32, partial);
   if (dgamma || dbeta || dbias)
-    reduce_ln_partials_kernel<<<ceil_div(3 * d, 8), 256, 0, st>>>(partial, blocks, d, dgamma, dbeta, dbias);
+    if (blocks >= 16 && !getenv("B4CP_REDUCE_1D"))
+      launch_reduce_partials_seg(partial, blocks, 3L * d, 3L * d, d, dgamma, dbeta, dbias, st);
+    else
+      reduce_ln_partials_kernel<<<ceil_div(3 * d, 8), 256, 0, st>>>(partial, blocks, d, dgamma, dbeta, dbias);
   note_launches(1 + ((dgamma || dbeta || dbias) ? 1 : 0));
   B4CP_LAUNCH_CHECK();
   return 0;
