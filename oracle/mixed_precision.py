@@ -26,11 +26,26 @@ def _tensor_core_attention(S, dh):
     return S <= 128 and dh in (32, 64)
 
 
+def _umma_attention_fwd(S, H, dh):
+    """csrc/attention_umma.cu (tcgen05): head depth 32, an even number of heads, S <= 128.  Its
+    probabilities go to the tensor core UN-normalised (exp(z - max) in bf16) and the output is
+    divided by the fp32 row sum afterwards."""
+    return dh == 32 and H % 2 == 0 and S <= 128
+
+
+def _umma_attention_bwd(S, H, dh):
+    """... and its backward for S <= 64: dZ is rounded to bf16 AFTER the 1/sqrt(dh) scale."""
+    return dh == 32 and H % 2 == 0 and S <= 64
+
+
 def _mha_fwd(qm, km, vm, pad, H):
     o, att = O.mha_core_fwd(qm, km, vm, pad, H)
     B, S, d = qm.shape
-    if _tensor_core_attention(S, d // H):
-        dh = d // H
+    dh = d // H
+    if _umma_attention_fwd(S, H, dh):
+        e = att["a"] / att["a"].max(-1, keepdims=True)      # exp(z - max)
+        o = ((bf16(e) @ att["vh"]) / e.sum(-1, keepdims=True)).transpose(0, 2, 1, 3).reshape(B, S, d)
+    elif _tensor_core_attention(S, dh):
         o = (bf16(att["a"]) @ att["vh"]).transpose(0, 2, 1, 3).reshape(B, S, d)
     return o, att
 
@@ -44,10 +59,15 @@ def _mha_bwd(do_merged, att):
     do = do_merged.reshape(B, S, H, dh).transpose(0, 2, 1, 3)
     dv = bf16(a).transpose(0, 1, 3, 2) @ do
     da = do @ vh.transpose(0, 1, 3, 2)
-    dz = bf16(a * (da - (da * a).sum(-1, keepdims=True)))
     inv = 1.0 / np.sqrt(np.float32(dh)).astype(np.float64)
-    dq = (dz @ kh) * inv
-    dk = (dz.transpose(0, 1, 3, 2) @ qh) * inv
+    if _umma_attention_bwd(S, H, dh):
+        dz = bf16(a * (da - (da * a).sum(-1, keepdims=True)) * inv)
+        dq = dz @ kh
+        dk = dz.transpose(0, 1, 3, 2) @ qh
+    else:
+        dz = bf16(a * (da - (da * a).sum(-1, keepdims=True)))
+        dq = (dz @ kh) * inv
+        dk = (dz.transpose(0, 1, 3, 2) @ qh) * inv
     merge = lambda t: t.transpose(0, 2, 1, 3).reshape(B, S, d)
     return merge(dq), merge(dk), merge(dv)
 
