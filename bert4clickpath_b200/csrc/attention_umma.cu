@@ -105,7 +105,17 @@ struct AttnUmmaParams {
   int n_items;            // ceil(B / SEQS) * n_boxes
   float scale2;           // log2(e) / sqrt(dh)
   float scale;            // 1 / sqrt(dh)
+  int spin;               // experiments: epilogue warps poll their barriers without suspending
 };
+
+__device__ __forceinline__ void au_wait(uint64_t* bar, uint32_t parity, int spin) {
+  if (spin) {
+    while (!mbar_test(bar, parity)) {
+    }
+  } else {
+    mbar_wait(bar, parity);
+  }
+}
 
 // mask value (log2 units) of key j of a row whose 32-key group has validity bits `len` and pad
 // bits `pad`
@@ -260,14 +270,14 @@ attention_umma_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnU
       const bool seq_ok = b < p.B;
       // the producer's key masks of this stage (its arrival on full[st] released them)
       const int st = i % AU_NST;
-      mbar_wait(&full[st], (uint32_t)((i / AU_NST) & 1));
+      au_wait(&full[st], (uint32_t)((i / AU_NST) & 1), p.spin);
       uint32_t keep[NG];
 #pragma unroll
       for (int g = 0; g < NG; ++g) keep[g] = masks[st * 8 + (SEQS == 2 ? sq * 2 : 0) + g];
       const bool allpad = masks[st * 8 + 4 + sq] != 0u;
       const float sc = allpad ? 0.f : p.scale2;
       const float bias = allpad ? AU_PAD2 : 0.f;
-      mbar_wait(s_full, (uint32_t)(i & 1));
+      au_wait(s_full, (uint32_t)(i & 1), p.spin);
       tc_fence_after();
       float sum;
       float m2;
@@ -373,7 +383,7 @@ attention_umma_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnU
         p.lse[((size_t)b * p.H + head) * p.S + si] = (m2 + __log2f(sum)) * AU_LN2;
       const float inv = 1.f / sum;
       const float2 inv2 = make_float2(inv, inv);
-      mbar_wait(o_full, (uint32_t)(i & 1));
+      au_wait(o_full, (uint32_t)(i & 1), p.spin);
       tc_fence_after();
       uint32_t o[32];
       tmem_ld32(t_head + 64 + hs * 32, o);
@@ -584,14 +594,14 @@ attention_umma_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV,
       const int grp = item / p.n_boxes, box = item - grp * p.n_boxes;
       const int st = i % AU_NST;
       float nb = nb_next;
-      mbar_wait(&full[st], (uint32_t)((i / AU_NST) & 1));
+      au_wait(&full[st], (uint32_t)((i / AU_NST) & 1), p.spin);
       const uint32_t keep0 = masks[st * 8 + sq * 2], keep1 = masks[st * 8 + sq * 2 + 1];
       float sc = p.scale2;
       if (masks[st * 8 + 4 + sq] != 0u) {   // every key a pad: uniform over the S keys
         sc = 0.f;
         if (nb != -INFINITY) nb = -__log2f((float)(__popc(keep0) + __popc(keep1)));
       }
-      mbar_wait(s_full, (uint32_t)(i & 1));
+      au_wait(s_full, (uint32_t)(i & 1), p.spin);
       tc_fence_after();
       uint32_t ra[32], rb[32], da[32], db[32];
       tmem_ld32(t_lane + hs * 128 + sq * 64, ra);
@@ -659,7 +669,7 @@ attention_umma_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV,
       if (i + 1 < n_mine) nb_next = fetch_nb(i + 1);
       // ---- phase 4: accumulators -> bf16 tiles [sequence][position][64 columns] in the (now
       // free) P / dZ region -> three TMA stores (rows past S and sequences past B are clipped)
-      mbar_wait(acc_full, (uint32_t)(i & 1));
+      au_wait(acc_full, (uint32_t)(i & 1), p.spin);
       tc_fence_after();
       uint32_t gq[32], gk[32], gv[32];
       tmem_ld32(t_lane + hs * 64 + h4 * 32, gq);
@@ -742,6 +752,11 @@ static int make_tmap_seq3d(CUtensorMap* map, const void* base, int width, int ld
   return 0;
 }
 
+static int au_spin() {
+  static const int v = getenv("B4CP_ATTN_SPIN") ? atoi(getenv("B4CP_ATTN_SPIN")) : 0;
+  return v;
+}
+
 static int au_num_sms() {
   static int n = 0;
   if (!n) {
@@ -777,6 +792,7 @@ int attention_umma_fwd(const void* qkv, const int32_t* ids, int B, int S, int H,
   p.n_items = ((B + seqs - 1) / seqs) * p.n_boxes;
   p.scale = 1.f / sqrtf(32.f);
   p.scale2 = AU_LOG2E / sqrtf(32.f);
+  p.spin = au_spin();
   const int smem = AU_NST * 3 * AU_TILE + 1024 + 256;
   static const int grid_cap = getenv("B4CP_ATTN_GRID") ? atoi(getenv("B4CP_ATTN_GRID")) : 0;   // experiments
   const int grid = std::min(p.n_items, grid_cap > 0 ? grid_cap : 2 * au_num_sms());
@@ -819,6 +835,7 @@ int attention_umma_bwd(const void* qkv, const void* dout, const float* lse, cons
   p.n_items = ((B + 1) / 2) * p.n_boxes;
   p.scale = 1.f / sqrtf(32.f);
   p.scale2 = AU_LOG2E / sqrtf(32.f);
+  p.spin = au_spin();
   const int smem = AU_NST * AB_STAGE + AB_PZ + 1024 + 256;
   const int grid = std::min(p.n_items, au_num_sms());
   B4CP_CUDA(cudaFuncSetAttribute(attention_umma_bwd_kernel,

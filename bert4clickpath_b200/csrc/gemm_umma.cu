@@ -573,7 +573,14 @@ __device__ __forceinline__ void tma_store_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
-__global__ void __launch_bounds__(320, 1)
+// Epilogue warps of the persistent kernel.  The skinny products are bound by their epilogue (scale /
+// bias / activation / pack / staging of 24 K outputs per 128 x 192 tile: ncu shows the 8-warp
+// version at IPC 1.3 with its warps waiting on each other's latencies), so each TMEM lane quadrant
+// gets PE_WARPS / 4 warps that split the tile's 32-column chunks.
+static constexpr int PE_WARPS = 16;
+static constexpr int PE_THREADS = 64 + 32 * PE_WARPS;
+
+__global__ void __launch_bounds__(PE_THREADS, 1)
 gemm_umma_persistent_kernel(const __grid_constant__ CUtensorMap tmA,
                             const __grid_constant__ CUtensorMap tmB,
                             const __grid_constant__ CUtensorMap tmOutB,
@@ -589,8 +596,8 @@ gemm_umma_persistent_kernel(const __grid_constant__ CUtensorMap tmA,
   // per-epilogue-warp staging tiles for the TMA stores: fp32 32x32 (4 KB, 128B swizzle) and bf16
   // 32x32 (2 KB, 64B swizzle)
   uint8_t* sStageF = sA + 2 * (size_t)a_stage_bytes;
-  uint8_t* sStageB = sStageF + (p.tma_out_f32 ? 8 * 4096 : 0);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sStageB + (p.tma_out_bf16 ? 8 * 2048 : 0));
+  uint8_t* sStageB = sStageF + (p.tma_out_f32 ? PE_WARPS * 4096 : 0);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStageB + (p.tma_out_bf16 ? PE_WARPS * 2048 : 0));
   uint64_t* b_full = bars;
   uint64_t* a_full = bars + 1;    // [2]
   uint64_t* a_empty = bars + 3;   // [2]
@@ -604,7 +611,7 @@ gemm_umma_persistent_kernel(const __grid_constant__ CUtensorMap tmA,
   const int n_my = (n_mtiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   uint32_t tmem_cols = 32;
   while ((int)tmem_cols < 2 * BN) tmem_cols <<= 1;
-  constexpr int WARP_TMA = 8, WARP_MMA = 9;  // single-thread roles at the highest warp ids
+  constexpr int WARP_TMA = PE_WARPS, WARP_MMA = PE_WARPS + 1;  // single-thread roles at the highest warp ids
 
   if (warp == WARP_TMA) {
     if (lane == 0) {
@@ -619,7 +626,7 @@ gemm_umma_persistent_kernel(const __grid_constant__ CUtensorMap tmA,
       mbar_init(&a_full[i], 1);
       mbar_init(&a_empty[i], 1);
       mbar_init(&t_full[i], 1);
-      mbar_init(&t_empty[i], 8);
+      mbar_init(&t_empty[i], PE_WARPS);
     }
     fence_barrier_init();
   }
@@ -683,10 +690,11 @@ gemm_umma_persistent_kernel(const __grid_constant__ CUtensorMap tmA,
       }
     }
   } else {
-    const int q = warp & 3, half = warp >> 2;  // 8 epilogue warps
+    const int q = warp & 3, part = warp >> 2;  // PE_WARPS / 4 warps per lane quadrant
     const b4cp_gemm_epilogue& ep = p.ep;
     const int chunks = BN / 32;
-    const int c_begin = half * ((chunks + 1) / 2), c_end = half ? chunks : (chunks + 1) / 2;
+    constexpr int NP = PE_WARPS / 4;
+    const int c_begin = (part * chunks) / NP, c_end = ((part + 1) * chunks) / NP;
     uint8_t* stgF = sStageF + warp * 4096;
     uint8_t* stgB = sStageB + warp * 2048;
     const bool staged = p.tma_out_bf16 || p.tma_out_f32;
@@ -922,7 +930,7 @@ extern "C" int b4cp_gemm_bf16(const void* A, int a_mn, long lda, const void* B, 
     }
     const size_t psmem = (size_t)p.k_tiles_total * (p.BN * BK * 2) +
                          2 * (size_t)p.k_tiles_total * A_STAGE_BYTES +
-                         (p.tma_out_f32 ? 8 * 4096 : 0) + (p.tma_out_bf16 ? 8 * 2048 : 0) + 128 +
+                         (p.tma_out_f32 ? PE_WARPS * 4096 : 0) + (p.tma_out_bf16 ? PE_WARPS * 2048 : 0) + 128 +
                          p.BN * 4 + 1024;
     if (psmem <= 227 * 1024) {
       static bool pattr = false;
@@ -932,7 +940,7 @@ extern "C" int b4cp_gemm_bf16(const void* A, int a_mn, long lda, const void* B, 
         pattr = true;
       }
       const int grid = std::min(n_mtiles, 148);
-      gemm_umma_persistent_kernel<<<grid, 320, psmem, (cudaStream_t)stream>>>(tmA, tmB, tmOutB,
+      gemm_umma_persistent_kernel<<<grid, PE_THREADS, psmem, (cudaStream_t)stream>>>(tmA, tmB, tmOutB,
                                                                               tmOutF, p);
       note_launches(1);
       B4CP_LAUNCH_CHECK();
