@@ -681,7 +681,7 @@ static void launch_reduce_partials_seg(const float* partial, int P, long n, long
                                        float* out0, float* out1, float* out2, cudaStream_t st) {
   if (P >= 512)
     reduce_partials_2d_kernel<16, 64><<<ceil_div(n, 16), 1024, 0, st>>>(partial, P, n, stride, seg, out0, out1, out2);
-  else if (n <= 8192)
+  else if (n <= 8192 || P >= 64)
     reduce_partials_2d_kernel<32, 32><<<ceil_div(n, 32), 1024, 0, st>>>(partial, P, n, stride, seg, out0, out1, out2);
   else
     reduce_partials_2d_kernel<32, 8><<<ceil_div(n, 32), 256, 0, st>>>(partial, P, n, stride, seg, out0, out1, out2);

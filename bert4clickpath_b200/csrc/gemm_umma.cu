@@ -377,7 +377,7 @@ __device__ __forceinline__ TileCoord tile_coord(const GemmKernelParams& p, int t
   return c;
 }
 
-static constexpr int TILES_EPI_WARPS = 8;  // two per TMEM lane quadrant, interleaved column chunks
+static constexpr int TILES_EPI_WARPS = 16;  // four per TMEM lane quadrant, interleaved column chunks
 static constexpr int TILES_THREADS = 64 + 32 * TILES_EPI_WARPS;
 
 __global__ void __launch_bounds__(TILES_THREADS, 1)
@@ -495,7 +495,8 @@ gemm_umma_tiles_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       }
     }
   } else {
-    // ---- epilogue warps 2..9: TMEM lane quadrant warp % 4, column chunks half, half + 2, ...
+    // ---- epilogue warps 2..: TMEM lane quadrant warp % 4, column chunks half, half + NPQ, ...
+    constexpr int NPQ = TILES_EPI_WARPS / 4;   // warps per quadrant
     const int q = warp & 3, half = (warp - 2) >> 2;
     const int n_chunks = BN / 32;
     const int etid = threadIdx.x - 64;
@@ -516,12 +517,12 @@ gemm_umma_tiles_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       const uint32_t stg = smem_u32(sStage + (warp - 2) * 4096);
       float* out_f32 = ep.out_f32 ? ep.out_f32 + (size_t)c.z * ep.split_stride : nullptr;
       bool released = false;
-      for (int ci = half; ci < n_chunks; ci += 2) {
+      for (int ci = half; ci < n_chunks; ci += NPQ) {
         const int c0 = ci * 32;
         uint32_t r[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), r);
         tmem_ld_wait();
-        if (ci + 2 >= n_chunks) {  // this warp's last read: hand the accumulator back early
+        if (ci + NPQ >= n_chunks) {  // this warp's last read: hand the accumulator back early
           tc_fence_before();
           mbar_arrive_warp(&acc_empty[acc]);
           released = true;
