@@ -698,6 +698,63 @@ static void launch_reduce_partials(const float* partial, int P, long n, long str
     reduce_partials_kernel<<<ceil_div(n, 256), 256, 0, st>>>(partial, P, n, stride, out);
 }
 
+// Column sums with the thread shape fitted to the matrix: CGP column groups of 8 columns x
+// 256 / CGP row lanes per CTA, `rows` rows per CTA chosen by the host so that the grid is ~8 CTAs
+// per SM whatever T and n are (the fixed 32-group x 512-row shape left 19 of 32 column lanes idle
+// at n = 104 and launched 56 CTAs for the head's 28,672 rows: ~20 us for 7-58 MB).
+template <int CGP>
+__global__ void __launch_bounds__(256)
+colsum_partial_fit_kernel(const __nv_bfloat16* __restrict__ in, long T, int n, long ld, int rows,
+                          float* __restrict__ partial) {
+  constexpr int RL = 256 / CGP;
+  __shared__ float red[RL][CGP][9];
+  const int cx = threadIdx.x % CGP, ry = threadIdx.x / CGP;
+  const int c0 = (blockIdx.y * CGP + cx) * 8;
+  const long r0 = (long)blockIdx.x * rows;
+  const long r1 = min(T, r0 + rows);
+  float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (c0 < n) {
+#pragma unroll 4
+    for (long r = r0 + ry; r < r1; r += RL) {
+      const uint4 q = __ldg(reinterpret_cast<const uint4*>(in + r * ld + c0));
+      const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        s[2 * k] += __uint_as_float(w[k] << 16);            // low half = even column
+        s[2 * k + 1] += __uint_as_float(w[k] & 0xFFFF0000u);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) red[ry][cx][k] = s[k];
+  __syncthreads();
+  const int g = threadIdx.x >> 3, k = threadIdx.x & 7;
+  const int c = (blockIdx.y * CGP + g) * 8 + k;
+  if (g < CGP && c < n) {
+    float t = 0.f;
+#pragma unroll 8
+    for (int y = 0; y < RL; ++y) t += red[y][g][k];   // fixed order: deterministic
+    partial[(size_t)blockIdx.x * n + c] = t;
+  }
+}
+
+struct ColsumPlan {
+  int cgp, grid_y, rows, chunks;
+};
+static ColsumPlan colsum_plan(long T, int n) {
+  ColsumPlan p;
+  const int groups = ceil_div(n, 8);
+  p.cgp = groups <= 8 ? 8 : (groups <= 16 ? 16 : 32);
+  p.grid_y = ceil_div(groups, p.cgp);
+  const int rl = 256 / p.cgp;
+  long chunks = std::max(1L, (long)(148 * 8) / p.grid_y);
+  long rows = std::max((long)std::max(64, 4 * rl), (T + chunks - 1) / chunks);
+  rows = (rows + rl - 1) / rl * rl;
+  p.rows = (int)rows;
+  p.chunks = ceil_div(T, rows);
+  return p;
+}
+
 // column sums of a bf16 matrix [T][ld] over rows -> partial[chunk][n]
 static constexpr int CS_ROWS = 512;
 __global__ void __launch_bounds__(256)
@@ -915,7 +972,8 @@ extern "C" int b4cp_residual_ln_bwd(const float* dy, const float* x, const float
 }
 
 extern "C" long b4cp_colsum_workspace_bytes(long T, int n) {
-  return (long)ceil_div(T, CS_ROWS) * n * sizeof(float);
+  const long fit = T > 0 ? colsum_plan(T, n).chunks : 1;
+  return std::max((long)ceil_div(T, CS_ROWS), fit) * n * sizeof(float);
 }
 
 extern "C" int b4cp_colsum_bf16(const void* in, long T, int n, long ld, float* out,
@@ -926,8 +984,17 @@ extern "C" int b4cp_colsum_bf16(const void* in, long T, int n, long ld, float* o
     B4CP_CUDA(cudaMemsetAsync(out, 0, (size_t)n * 4, st));
     return 0;
   }
-  const int chunks = ceil_div(T, CS_ROWS);
-  if (ld % 8 == 0 && ((uintptr_t)in & 15) == 0 && ld >= (long)ceil_div(n, 8) * 8) {
+  int chunks = ceil_div(T, CS_ROWS);
+  static const bool old_shape = getenv("B4CP_COLSUM_FIXED") != nullptr;   // comparison
+  if (ld % 8 == 0 && ((uintptr_t)in & 15) == 0 && ld >= (long)ceil_div(n, 8) * 8 && !old_shape) {
+    const ColsumPlan cp = colsum_plan(T, n);
+    chunks = cp.chunks;
+    dim3 grid(cp.chunks, cp.grid_y);
+    const __nv_bfloat16* src = (const __nv_bfloat16*)in;
+    if (cp.cgp == 8) colsum_partial_fit_kernel<8><<<grid, 256, 0, st>>>(src, T, n, ld, cp.rows, (float*)workspace);
+    else if (cp.cgp == 16) colsum_partial_fit_kernel<16><<<grid, 256, 0, st>>>(src, T, n, ld, cp.rows, (float*)workspace);
+    else colsum_partial_fit_kernel<32><<<grid, 256, 0, st>>>(src, T, n, ld, cp.rows, (float*)workspace);
+  } else if (ld % 8 == 0 && ((uintptr_t)in & 15) == 0 && ld >= (long)ceil_div(n, 8) * 8) {
     dim3 grid(chunks, ceil_div(n, 256));
     colsum_partial_vec_kernel<<<grid, 256, 0, st>>>((const __nv_bfloat16*)in, T, n, ld, (float*)workspace);
   } else {
