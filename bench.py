@@ -651,7 +651,20 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- end-to-end timing through the public API (pinned host buffers in, loss out)
     trainer.step_host(*pinned[0])
-    ms_e2e, loss = timed(lambda i: trainer.step_host(*pinned[i % n_ring]), args.steps)
+    ms_blocking, _ = timed(lambda i: trainer.step_host(*pinned[i % n_ring]), args.steps)
+    # the loop a user runs (ClozeTrainStep.run_host = the reference's prefetching fit loop): every
+    # step's inputs are copied from pinned host memory and every step's loss is read back on the
+    # host inside the timed region, one step behind the launches
+    for _ in trainer.run_host(pinned[i % n_ring] for i in range(4)):
+        pass
+    e2e_losses = []
+
+    def e2e_loop(_):
+        e2e_losses.extend(trainer.run_host(pinned[i % n_ring] for i in range(args.steps)))
+        return e2e_losses[-1]
+
+    ms_e2e, loss = timed(e2e_loop, 1)
+    assert len(e2e_losses) == args.steps
     h2d = ClozeTrainStep.h2d_bytes(pinned[0][0], pinned[0][1])
 
     # ---- end to end from RAW SESSIONS: the sessions live in HBM (CSR), the host sends B session
@@ -811,7 +824,7 @@ def run_ours(args, rank, world, local_rank):
                              "vocab_stage_fwd_dx_bwd": kernel_line("vocab_ce", 6.0 * mhv, per_step=True)}
     roof["other_kernels"]["vocab_stage_fwd_dx_bwd"]["note"] = \
         "fwd + merge + dx + bwd kernels of one step; ms_per_launch is per step"
-    if world == 1:
+    if world == 1 and not args.no_cpu:
         cpu_seqs, cpu_n, cpu_dt = time_cpu_reference(args.cpu_batch, 6, 1, budget_s=20.0)
         cpu_base = {"value": cpu_seqs, "unit": "seqs/s", "cores": blas_threads(), "kind": "port",
                     "sample": f"{cpu_n} full oracle training steps at batch {args.cpu_batch}"}
@@ -835,7 +848,15 @@ def run_ours(args, rank, world, local_rank):
                                 "(parity of this path and of the fp32-class mode: DESIGN.md section 5)"},
         "clocks": clocks,
         "e2e": {"value": seqs_e2e, "unit": "seqs/s", "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": 8, "ms_per_step": ms_e2e / args.steps},
+                "d2h_bytes_per_step": 8, "ms_per_step": ms_e2e / args.steps,
+                "blocking_call_per_step": {
+                    "value": world * B * args.steps / (ms_blocking * 1e-3),
+                    "ms_per_step": ms_blocking / args.steps,
+                    "note": "ClozeTrainStep.step_host: copy, step and loss read strictly one "
+                            "after the other"},
+                "note": "ClozeTrainStep.run_host: per step the H2D copy of its inputs from pinned "
+                        "memory (copy stream, two landing buffers) and the D2H read of its loss, "
+                        "read on the host one step behind the launches"},
         "e2e_from_sessions": e2e_builder,
         "sustained": sustained,
         "b512": b512,
@@ -871,6 +892,8 @@ def main():
     ap.add_argument("--no-b512", action="store_true", help="skip the batch-512 leg")
     ap.add_argument("--no-fp32", action="store_true", help="skip the fp32-class parity-mode leg")
     ap.add_argument("--no-builder", action="store_true", help="skip the sessions -> batch -> step leg")
+    ap.add_argument("--no-cpu", action="store_true",
+                    help="skip the CPU oracle baseline leg (profiling runs; the line is then incomplete)")
     ap.add_argument("--no-c4", action="store_true", help="skip the C4 / C5 (V=1M, h=256) legs")
     ap.add_argument("--max-seconds", type=int, default=1200, help="watchdog: hard exit after this long")
     args = ap.parse_args()

@@ -47,6 +47,8 @@ class ClozeTrainStep:
         self._graphs = {}
         self._dev_ids = self._dev_labels = None
         self._host_stats = torch.empty(2, dtype=F32).pin_memory() if torch.cuda.is_available() else None
+        self._copy_stream = None
+        self._slots = {}
 
     def _lr(self):
         lr = self.opt.learning_rate
@@ -158,6 +160,54 @@ class ClozeTrainStep:
         torch.cuda.current_stream().synchronize()
         s0, s1 = float(self._host_stats[0]), float(self._host_stats[1])
         return s0 / s1 if s1 > 0 else 0.0
+
+    def run_host(self, batches):
+        """The end-to-end loop a `model.fit(dataset.prefetch(...))` of the reference runs
+        (examples/BERT4Rec/source/main.py:140-165): for every (ids_pinned, labels_pinned,
+        n_masked) of `batches` the H2D copy of its inputs from pinned memory, the training step,
+        and the D2H read of its loss statistics.  Yields the global mean loss of every step, ONE
+        STEP BEHIND the launches: step k+1 is copied (on a copy stream, into the other of two
+        landing buffers) and enqueued while step k runs, so neither the copy nor the host's launch
+        work leaves the device idle.  `step_host` is the same thing strictly one step at a time."""
+        cur = torch.cuda.current_stream()
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream()
+        cs = self._copy_stream
+        pending = None
+
+        def read(slot):
+            slot["done"].synchronize()
+            s0, s1 = float(slot["stats"][0]), float(slot["stats"][1])
+            return s0 / s1 if s1 > 0 else 0.0
+
+        for k, (ids_pinned, labels_pinned, n_masked) in enumerate(batches):
+            key = (k & 1, tuple(ids_pinned.shape), tuple(labels_pinned.shape))
+            slot = self._slots.get(key)
+            if slot is None:
+                slot = dict(ids=torch.empty(ids_pinned.shape, dtype=I32, device="cuda"),
+                            labels=torch.empty(labels_pinned.shape, dtype=F32, device="cuda"),
+                            stats=torch.empty(2, dtype=F32).pin_memory(),
+                            copied=torch.cuda.Event(), consumed=None, done=torch.cuda.Event())
+                self._slots[key] = slot
+            B, S = ids_pinned.shape
+            with torch.cuda.stream(cs):
+                if slot["consumed"] is not None:     # the step that last read this landing buffer
+                    cs.wait_event(slot["consumed"])
+                slot["ids"].copy_(ids_pinned, non_blocking=True)
+                slot["labels"].copy_(labels_pinned, non_blocking=True)
+                slot["copied"].record(cs)
+            cur.wait_event(slot["copied"])
+            stats = self.step_device(DeviceBatch([slot["ids"].view(-1)], slot["labels"], B, S, n_masked))
+            if slot["consumed"] is None:
+                slot["consumed"] = torch.cuda.Event()
+            slot["consumed"].record(cur)
+            slot["stats"].copy_(stats, non_blocking=True)
+            slot["done"].record(cur)
+            if pending is not None:
+                yield read(pending)
+            pending = slot
+        if pending is not None:
+            yield read(pending)
 
     @staticmethod
     def h2d_bytes(ids_pinned, labels_pinned):

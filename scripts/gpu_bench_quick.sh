@@ -1,0 +1,9 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 600 python bench.py --steps 20 --warmup 5 --no-c4 --no-topk --no-fp32 --sustain-seconds 0 --no-cpu > gpurun_out/q_bench.json 2> gpurun_out/q_bench.err; echo "bench rc=$?"; tail -3 gpurun_out/q_bench.err
+python - <<'PY'
+import json
+d=json.load(open('gpurun_out/q_bench.json'))
+print('value',d['value'],d['ms_per_step'],'e2e',d['e2e']['value'],d['e2e']['ms_per_step'],'blocking',d['e2e']['blocking_call_per_step']['value'],'sessions',(d.get('e2e_from_sessions') or {}).get('value'),'b512',(d.get('b512') or {}).get('value'))
+r=d['roofline']; print('fwd',r['ms_per_launch'],r['frac'],'bwd',r['other_kernels']['vocab_ce_bwd_ts_kernel']['ms_per_launch'],'stage',r['other_kernels']['vocab_stage_fwd_dx_bwd']['ms_per_launch'],'launches',d['launch_mode']['kernels_per_step'], 'loss', d['loss'], d['e2e_last_loss'])
+PY

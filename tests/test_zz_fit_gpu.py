@@ -120,3 +120,27 @@ def test_graph_step_recaptures_when_the_learning_rate_changes(cuda_lib):
     assert st["graph"] is not None and st["hp"][0] == 1e-4
     wg, we = mg.store.get_weights(), me.store.get_weights()
     assert all(np.array_equal(wg[k], we[k]) for k in wg)
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_pipelined_host_loop_equals_the_blocking_one(cuda_lib, use_graph):
+    """run_host (copies on a second stream, losses read one step late) must train exactly like
+    step_host called once per batch: same losses, same weights, with batches of different mask
+    counts and a partial last pair of landing buffers."""
+    import bert4clickpath_b200 as bc
+    from bert4clickpath_b200.synthetic import make_cloze_batch
+    from bert4clickpath_b200.training import ClozeTrainStep
+    rng = np.random.default_rng(3)
+    host = [make_cloze_batch(rng, 32, V, max_len=30, mode="train", lengths="beauty") for _ in range(3)]
+    pinned = [(torch.from_numpy(b["ids"]).pin_memory(), torch.from_numpy(b["labels"]).pin_memory(),
+               b["n_masked"]) for b in host]
+    order = [0, 1, 2, 1, 0, 2, 2]
+    ma, mb = _model(dropout=0.0), _model(dropout=0.0)
+    ta = ClozeTrainStep(ma, bc.Adam(1e-3), use_graph=use_graph)
+    tb = ClozeTrainStep(mb, bc.Adam(1e-3), use_graph=use_graph)
+    blocking = [ta.step_host(*pinned[i]) for i in order]
+    piped = list(tb.run_host(pinned[i] for i in order))
+    assert piped == blocking
+    wa, wb = ma.store.get_weights(), mb.store.get_weights()
+    assert all(np.array_equal(wa[k], wb[k]) for k in wa)
+    assert list(tb.run_host(iter(()))) == []
