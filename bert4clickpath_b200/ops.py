@@ -324,10 +324,10 @@ def residual_ln_bwd(dy, x, r, gamma, dx, dr_bf16, dgamma, dbeta, dbias, *, dropo
            L.ptr(dr_f32), L.ptr(dgamma), L.ptr(dbeta), L.ptr(dbias), L.ptr(ws), L.stream_ptr())
 
 
-def colsum_bf16(x_bf16, T, n, out):
+def colsum_bf16(x_bf16, T, n, out, ws_name="colsum"):
     fn = L.lib().b4cp_colsum_workspace_bytes
     fn.restype = ctypes.c_long
-    ws = WS.get("colsum", fn(ctypes.c_long(T), ctypes.c_int(n)))
+    ws = WS.get(ws_name, fn(ctypes.c_long(T), ctypes.c_int(n)))
     if x_bf16.dtype == F32:
         L.call("b4cp_colsum_f32", L.ptr(x_bf16), L.c_long(T), L.c_int(n), L.c_long(x_bf16.stride(0)),
                L.ptr(out), L.ptr(ws), L.stream_ptr())
