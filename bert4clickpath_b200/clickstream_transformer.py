@@ -11,7 +11,7 @@ import torch
 from . import ops
 from .constants import (CLASSIFICATION_TOKEN, CLS, INPUT_MASKING_TOKEN, LABEL_PAD, RESERVED_TOKENS,
                         SEP, SEPARATOR_TOKEN)
-from .engine import BufferPool, ParamStore
+from .engine import WSTREAM, BufferPool, ParamStore
 from .head import ClozeOutput, SoftMaxHead
 from .ops import BF16, F32, I32, ld8
 from .transformer import Transformer
@@ -218,9 +218,8 @@ class ClickstreamTransformer:
     def forward_ids(self, ids_list, B, S, training=False, seed=0, n_masked=None,
                     segment_bounds=None, rows_are_common=False):
         """Hot-path entry on already-chained device ids (int32 [B*S] per feature)."""
-        x = self._encode(ids_list, B, S, training, seed)
-        state = dict(x=x, ids_first=ids_list[0], B=B, S=S)
         if self.segment_to_head is not None:
+            x = self._encode(ids_list, B, S, training, seed)
             starts, ends = segment_bounds
             s0, s1 = int(starts[self.segment_to_head]), int(ends[self.segment_to_head])
             head_input = x.view(B, S, self.d_model)[:, s0:s1, :]
@@ -229,7 +228,15 @@ class ClickstreamTransformer:
         vocab = getattr(self.head, "vocab", None)
         if hasattr(vocab, "common_rows") and not rows_are_common:
             cap = vocab.common_rows(cap)  # vocabulary-parallel: every rank presents the same rows
-        row_index, count = ops.select_masked(ids_list[0], self._value_id, cap)
+        # which rows go to the head depends on the ids alone: the five small launches of the
+        # selection run on the second stream under the encoder
+        row_buf = self.pool.get("row_index", (max(cap, 1),), I32)
+        count = self.pool.get("row_count", (1,), I32)
+        row_index = row_buf[:cap]
+        selected = WSTREAM.run(lambda: ops.select_masked(ids_list[0], self._value_id, cap, row_buf, count))
+        x = self._encode(ids_list, B, S, training, seed)
+        state = dict(x=x, ids_first=ids_list[0], B=B, S=S)
+        WSTREAM.wait(selected)
         hsel = self.pool.get("hsel", (cap, ld8(self.d_model)), self.act)
         ops.gather_rows(x, row_index, None, hsel)
         state["value_id"] = self._value_id
@@ -344,9 +351,20 @@ class ClickstreamTransformer:
             # the loss and the backward: ~25 us of exposed latency per step)
             labels, n_global = ops.compact_labels(labels_f32, int(n_masked))
             count_work = self._allreduce(n_global, async_op=True)
+        compacted = None
+        if (not dp and n_masked is not None
+                and (rows_are_common or not hasattr(vocab, "common_rows"))):
+            # single process: the label compaction (a function of the labels alone) runs on the
+            # second stream under the encoder forward
+            cap0 = int(n_masked)
+            lab_buf = self.pool.get("labels_compact", (max(cap0, 1),), I32)
+            n_global = self.pool.get("labels_count", (1,), I32)
+            labels = lab_buf[:cap0]
+            compacted = WSTREAM.run(lambda: ops.compact_labels(labels_f32, cap0, out=lab_buf, count=n_global))
         out = self.forward_ids(ids_list, B, S, training, seed, n_masked=n_masked,
                                rows_are_common=rows_are_common)
         cap = out.M
+        WSTREAM.wait(compacted)
         if labels is None or labels.numel() != cap:
             labels, n_global = ops.compact_labels(labels_f32, cap)
             count_work = self._allreduce(n_global, async_op=True) if dp else None

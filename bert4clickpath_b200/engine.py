@@ -210,9 +210,11 @@ class WeightStream:
         self.enabled = os.environ.get("B4CP_WEIGHT_STREAM", "1") != "0"
 
     def run(self, fn, *reads):
+        """Run fn on the weight stream after everything queued on the current stream so far.
+        Returns the event that marks its completion (None when it ran inline)."""
         if not self.enabled:
             fn()
-            return
+            return None
         cur = torch.cuda.current_stream()
         if self.stream is None:
             self.stream = torch.cuda.Stream()
@@ -223,6 +225,13 @@ class WeightStream:
             done.record(self.stream)
         for t in reads:
             self.readers[t.data_ptr()] = done
+        return done
+
+    @staticmethod
+    def wait(done):
+        """The current stream waits for side work started with run()."""
+        if done is not None:
+            torch.cuda.current_stream().wait_event(done)
 
     def before_write(self, *tensors):
         for t in tensors:

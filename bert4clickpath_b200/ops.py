@@ -355,26 +355,29 @@ def dropout_apply(x, rate, seed, site):
 
 
 # ------------------------------------------------------------------------------- selection
-def select_masked(ids_first, value, capacity):
+def select_masked(ids_first, value, capacity, row_index=None, count=None):
+    """`row_index` (int32 [>= max(capacity, 1)]) / `count` (int32 [1]): optional caller-owned
+    outputs (a caller that runs this on a second stream must not let it allocate there)."""
     tokens = ids_first.numel()
     fn = L.lib().b4cp_select_workspace_bytes
     fn.restype = ctypes.c_long
     ws = WS.get("select", fn(ctypes.c_long(tokens)))
-    row_index = empty((max(capacity, 1),), I32)
-    count = empty((1,), I32)
+    row_index = empty((max(capacity, 1),), I32) if row_index is None else row_index
+    count = empty((1,), I32) if count is None else count
     L.call("b4cp_select_masked", L.ptr(ids_first), L.c_long(tokens), L.c_int(value),
            L.ptr(row_index), L.c_long(capacity), L.ptr(count), L.ptr(ws), L.stream_ptr())
     return row_index[:capacity], count
 
 
-def compact_labels(labels_f32, capacity, label_pad=-1.0):
-    """(B, Mmax) float32 labels padded with -1 -> int32 [capacity] valid labels, -1 padded."""
+def compact_labels(labels_f32, capacity, label_pad=-1.0, out=None, count=None):
+    """(B, Mmax) float32 labels padded with -1 -> int32 [capacity] valid labels, -1 padded.
+    `out` / `count`: optional caller-owned outputs (see select_masked)."""
     n = labels_f32.numel()
     fn = L.lib().b4cp_select_workspace_bytes
     fn.restype = ctypes.c_long
     ws = WS.get("select", fn(ctypes.c_long(max(n, 1))))
-    out = empty((max(capacity, 1),), I32)
-    count = empty((1,), I32)
+    out = empty((max(capacity, 1),), I32) if out is None else out
+    count = empty((1,), I32) if count is None else count
     L.call("b4cp_compact_labels", L.ptr(labels_f32), L.c_long(n), L.c_float(label_pad), L.ptr(out),
            L.c_long(capacity), L.ptr(count), L.ptr(ws), L.stream_ptr())
     return out[:capacity], count
