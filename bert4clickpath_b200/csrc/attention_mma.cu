@@ -829,7 +829,9 @@ int attention_umma_fwd(const void* qkv, const int32_t* ids, int B, int S, int H,
 
 int attention_mma_fwd(const void* qkv, const int32_t* ids, int B, int S, int H, int dh, void* out,
                       float* lse, cudaStream_t st) {
-  if (attention_umma_supported(S, H, dh)) return attention_umma_fwd(qkv, ids, B, S, H, out, lse, st);
+  // (TMA needs 16-byte aligned base addresses; an offset view falls back to the kernels below)
+  if (attention_umma_supported(S, H, dh) && (((uintptr_t)qkv | (uintptr_t)out) & 15) == 0)
+    return attention_umma_fwd(qkv, ids, B, S, H, out, lse, st);
   if (S > 128)
     return dh == 32 ? launch_fwd_long<32>(qkv, ids, B, S, H, out, lse, st)
                     : launch_fwd_long<64>(qkv, ids, B, S, H, out, lse, st);
@@ -846,7 +848,7 @@ int attention_umma_bwd(const void* qkv, const void* dout, const float* lse, cons
 
 int attention_mma_bwd(const void* qkv, const void* fwd_out, const void* dout, const float* lse,
                       const int32_t* ids, int B, int S, int H, int dh, void* dqkv, cudaStream_t st) {
-  if (attention_umma_bwd_supported(S, H, dh))
+  if (attention_umma_bwd_supported(S, H, dh) && (((uintptr_t)qkv | (uintptr_t)dout | (uintptr_t)dqkv) & 15) == 0)
     return attention_umma_bwd(qkv, dout, lse, ids, B, S, H, dqkv, st);
   if (S > 128) {
     if (!fwd_out) {

@@ -709,6 +709,271 @@ attention_umma_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV,
   }
 }
 
+// ------------------------------------------------------------------ backward, 64 < S <= 128
+// One sequence per item; its two heads are processed one after the other ("sub-items" j = 2 i + h)
+// because a 128-row sequence needs all 128 key columns of S_h and dP_h (256 TMEM columns per head)
+// and 32 KB each for the P_h / dZ_h tiles.  TMEM: scores [0,256), accumulators dQ | dK | dV at
+// [256,448) - separate, so phase 1 of sub-item j+1 runs under phase 4 of sub-item j.  The 8 thread
+// warps all work on the same head: thread (query row, key half) owns 64 of the row's 128 keys;
+// delta = sum_j P dP needs both halves, exchanged through shared memory.  P_h / dZ_h tiles are two
+// 64-key blocks of [128 queries][64 keys] (16 KB each): K-major that is a 128 x 128 A operand for
+// dQ_h = dZ_h K (the K steps 4..7 live in the second block), MN-major a 128-key x 128-query A
+// operand (two 64-wide M blocks) for dK_h = dZ_h^T Q and dV_h = P_h^T dO.
+__global__ void __launch_bounds__(AU_THREADS, 1)
+attention_umma_bwd1_kernel(const __grid_constant__ CUtensorMap tmQKV,
+                           const __grid_constant__ CUtensorMap tmDO, const AttnUmmaParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* sPZ = smem + AU_NST * AB_STAGE;          // P_h: [0, 32 KB), dZ_h: [32 KB, 64 KB)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sPZ + AB_PZ);
+  uint64_t* full = bars;             // [2] TMA bytes + key masks
+  uint64_t* empty = bars + 2;        // [2] phase 3 of the item's second head retired
+  uint64_t* s_full = bars + 4;       // phase 1 retired
+  uint64_t* pz_full = bars + 5;      // 8 warps: P / dZ in shared memory, scores consumed
+  uint64_t* acc_full = bars + 6;     // phase 3 retired
+  uint64_t* acc_read = bars + 7;     // 8 warps: accumulators drained
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint32_t* masks = reinterpret_cast<uint32_t*>(bars + 10);   // [AU_NST][8]
+  float* sDelta = reinterpret_cast<float*>(masks + AU_NST * 8);   // [2 halves][128 rows]
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const int n_mine = ((int)blockIdx.x < p.n_items)
+                         ? (p.n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x
+                         : 0;
+  const int n_sub = 2 * n_mine;
+
+  if (warp == AU_WARP_TMA) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmQKV);
+      tma_prefetch_desc(&tmDO);
+    }
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  } else if (warp == AU_WARP_MMA && lane == 0) {
+    for (int s = 0; s < AU_NST; ++s) {
+      mbar_init(&full[s], 2);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(pz_full, AU_EPI_WARPS);
+    mbar_init(acc_full, 1);
+    mbar_init(acc_read, AU_EPI_WARPS);
+    fence_barrier_init();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+
+  if (warp == AU_WARP_TMA) {
+    const uint32_t a0 = smem_u32(smem);
+    for (int i = 0; i < n_mine; ++i) {
+      const int item = (int)blockIdx.x + i * (int)gridDim.x;
+      const int b = item / p.n_boxes, box = item - b * p.n_boxes;
+      const int st = i % AU_NST;
+      mbar_wait_all(&empty[st], (uint32_t)((i / AU_NST) & 1) ^ 1);
+      mbar_expect_tx_el(&full[st], 4u * AU_TILE);
+      const uint32_t dst = a0 + (uint32_t)(st * AB_STAGE);
+#pragma unroll
+      for (int o = 0; o < 3; ++o)
+        tma_load_3d_el(dst + o * AU_TILE, &tmQKV, &full[st], o * p.d + box * 64, 0, b);
+      tma_load_3d_el(dst + 3 * AU_TILE, &tmDO, &full[st], box * 64, 0, b);
+      uint32_t keep[4], len[4];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int j = g * 32 + lane;
+        const bool in = j < p.S;
+        const int id = in ? __ldg(p.ids + (size_t)b * p.S + j) : 1;
+        len[g] = __ballot_sync(0xffffffffu, in);
+        keep[g] = __ballot_sync(0xffffffffu, in && id != 0);
+      }
+      const uint32_t allpad = (keep[0] | keep[1] | keep[2] | keep[3]) == 0u;
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+        if (allpad) keep[g] = len[g];
+      if (lane < 4) masks[st * 8 + lane] = lane == 0 ? keep[0] : lane == 1 ? keep[1] : lane == 2 ? keep[2] : keep[3];
+      if (lane == 4) masks[st * 8 + 4] = allpad;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full[st]);
+    }
+  } else if (warp == AU_WARP_MMA) {
+    const uint32_t id_s = umma_idesc_bf16(128, 128, 0, 0);
+    const uint32_t id_q = umma_idesc_bf16(128, 64, 0, 1);
+    const uint32_t id_t = umma_idesc_bf16(128, 64, 1, 1);
+    const uint32_t a0 = smem_u32(smem);
+    const uint32_t aPZ = smem_u32(sPZ);
+    const uint64_t dKm = umma_smem_desc(a0, 16, 1024);
+    const uint64_t dMn = umma_smem_desc(a0, 8192, 1024);
+    const uint64_t dPZk = umma_smem_desc(aPZ, 16, 1024);        // rows = queries, K = keys
+    const uint64_t dPZm = umma_smem_desc(aPZ, 16384, 1024);     // rows = keys (2 x 64), K = queries
+    auto phase1 = [&](int j) {
+      const int i = j >> 1, hs = j & 1, st = i % AU_NST;
+      const uint32_t so = (uint32_t)(st * AB_STAGE);
+      if (hs == 0) mbar_wait_all(&full[st], (uint32_t)((i / AU_NST) & 1));
+      tc_fence_after();
+#pragma unroll
+      for (int kk = 0; kk < 2; ++kk) {
+        const uint32_t ko = (uint32_t)(hs * 64 + kk * 32);
+        umma_bf16_el(tmem_base, dKm + ((so + ko) >> 4), dKm + ((so + AU_TILE + ko) >> 4), id_s,
+                     kk ? 1u : 0u);
+        umma_bf16_el(tmem_base + 128, dKm + ((so + 3 * AU_TILE + ko) >> 4),
+                     dKm + ((so + 2 * AU_TILE + ko) >> 4), id_s, kk ? 1u : 0u);
+      }
+      umma_commit_el(s_full);
+    };
+    if (n_sub > 0) phase1(0);
+    for (int j = 0; j < n_sub; ++j) {
+      const int i = j >> 1, hs = j & 1, st = i % AU_NST;
+      const uint32_t so = (uint32_t)(st * AB_STAGE);
+      mbar_wait_all(pz_full, (uint32_t)(j & 1));
+      if (j > 0) mbar_wait_all(acc_read, (uint32_t)((j - 1) & 1));
+      tc_fence_after();
+#pragma unroll
+      for (int kk = 0; kk < 8; ++kk) {
+        const uint32_t kq = (uint32_t)((kk >> 2) * 16384 + (kk & 3) * 32);   // K-major A: key step
+        const uint32_t rows = (uint32_t)(kk * 2048);                          // 16 rows of a tile
+        // dQ_h = dZ_h K
+        umma_bf16_el(tmem_base + 256, dPZk + ((2u * AU_TILE + kq) >> 4),
+                     dMn + ((so + AU_TILE + rows) >> 4), id_q, kk ? 1u : 0u);
+        // dK_h = dZ_h^T Q
+        umma_bf16_el(tmem_base + 320, dPZm + ((2u * AU_TILE + rows) >> 4),
+                     dMn + ((so + rows) >> 4), id_t, kk ? 1u : 0u);
+        // dV_h = P_h^T dO
+        umma_bf16_el(tmem_base + 384, dPZm + (rows >> 4),
+                     dMn + ((so + 3 * AU_TILE + rows) >> 4), id_t, kk ? 1u : 0u);
+      }
+      umma_commit_el(acc_full);
+      if (hs == 1) umma_commit_el(&empty[st]);
+      if (j + 1 < n_sub) phase1(j + 1);   // (its s_full arrives after the products above retire)
+    }
+  } else {
+    const int q = warp & 3, half = warp >> 2;
+    const int row = 32 * q + lane;                     // query row (phase 2) / TMEM lane (phase 4)
+    const uint32_t t_lane = tmem_base + ((uint32_t)(32 * q) << 16);
+    const uint32_t aPZ = smem_u32(sPZ);
+    auto fetch_nb = [&](int j) -> float {
+      const int item = (int)blockIdx.x + (j >> 1) * (int)gridDim.x;
+      const int b = item / p.n_boxes, box = item - b * p.n_boxes;
+      return row < p.S ? -__ldg(p.lse + ((size_t)b * p.H + box * 2 + (j & 1)) * p.S + row) * AU_LOG2E
+                       : -INFINITY;
+    };
+    float nb_next = n_sub > 0 ? fetch_nb(0) : 0.f;
+    for (int j = 0; j < n_sub; ++j) {
+      const int i = j >> 1, hs = j & 1, st = i % AU_NST;
+      const int item = (int)blockIdx.x + i * (int)gridDim.x;
+      const int b = item / p.n_boxes, box = item - b * p.n_boxes;
+      float nb = nb_next;
+      au_wait(&full[st], (uint32_t)((i / AU_NST) & 1), p.spin);
+      const uint32_t keep0 = masks[st * 8 + half * 2], keep1 = masks[st * 8 + half * 2 + 1];
+      float sc = p.scale2;
+      if (masks[st * 8 + 4] != 0u) {   // every key a pad: uniform over the S keys
+        sc = 0.f;
+        if (nb != -INFINITY) nb = -__log2f((float)p.S);
+      }
+      au_wait(s_full, (uint32_t)(j & 1), p.spin);
+      tc_fence_after();
+      uint32_t ra[32], rb[32], da[32], db[32];
+      tmem_ld32(t_lane + half * 64, ra);
+      tmem_ld32(t_lane + half * 64 + 32, rb);
+      tmem_ld32(t_lane + 128 + half * 64, da);
+      tmem_ld32(t_lane + 128 + half * 64 + 32, db);
+      tmem_ld_wait();
+      const float2 sc2 = make_float2(sc, sc), nb2 = make_float2(nb, nb);
+      float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int jj = 0; jj < 32; jj += 2) {
+        float2 z = __ffma2_rn(make_float2(__uint_as_float(ra[jj]), __uint_as_float(ra[jj + 1])), sc2, nb2);
+        float e0 = au_ex2(z.x), e1 = au_ex2(z.y);
+        if (keep0 != 0xffffffffu) {
+          e0 = ((keep0 >> jj) & 1u) ? e0 : 0.f;
+          e1 = ((keep0 >> (jj + 1)) & 1u) ? e1 : 0.f;
+        }
+        ra[jj] = __float_as_uint(e0);
+        ra[jj + 1] = __float_as_uint(e1);
+        acc = __ffma2_rn(make_float2(e0, e1), make_float2(__uint_as_float(da[jj]), __uint_as_float(da[jj + 1])), acc);
+        z = __ffma2_rn(make_float2(__uint_as_float(rb[jj]), __uint_as_float(rb[jj + 1])), sc2, nb2);
+        e0 = au_ex2(z.x), e1 = au_ex2(z.y);
+        if (keep1 != 0xffffffffu) {
+          e0 = ((keep1 >> jj) & 1u) ? e0 : 0.f;
+          e1 = ((keep1 >> (jj + 1)) & 1u) ? e1 : 0.f;
+        }
+        rb[jj] = __float_as_uint(e0);
+        rb[jj + 1] = __float_as_uint(e1);
+        acc = __ffma2_rn(make_float2(e0, e1), make_float2(__uint_as_float(db[jj]), __uint_as_float(db[jj + 1])), acc);
+      }
+      // delta over both key halves (the other half's thread sits in warp +-4)
+      sDelta[half * 128 + row] = acc.x + acc.y;
+      au_epi_sync();
+      const float delta = sDelta[row] + sDelta[128 + row];
+      const uint32_t rowP = aPZ + (uint32_t)(half * 16384 + (row >> 3) * 1024 + (row & 7) * 128);
+      const uint32_t rowZ = rowP + 2 * AU_TILE;
+      const float2 nd2 = make_float2(-delta, -delta), s2 = make_float2(p.scale, p.scale);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        uint32_t pw[4], zw[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int jj = (c & 3) * 8 + 2 * u;
+          const float2 pv = c < 4 ? make_float2(__uint_as_float(ra[jj]), __uint_as_float(ra[jj + 1]))
+                                  : make_float2(__uint_as_float(rb[jj]), __uint_as_float(rb[jj + 1]));
+          const float2 dv = c < 4 ? make_float2(__uint_as_float(da[jj]), __uint_as_float(da[jj + 1]))
+                                  : make_float2(__uint_as_float(db[jj]), __uint_as_float(db[jj + 1]));
+          const float2 dz = __fmul2_rn(__fmul2_rn(pv, __fadd2_rn(dv, nd2)), s2);
+          pw[u] = au_pack(pv.x, pv.y);
+          zw[u] = au_pack(dz.x, dz.y);
+        }
+        const uint32_t off = (uint32_t)((c ^ (row & 7)) << 4);
+        sts128(rowP + off, pw[0], pw[1], pw[2], pw[3]);
+        sts128(rowZ + off, zw[0], zw[1], zw[2], zw[3]);
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive_warp(pz_full);
+      if (j + 1 < n_sub) nb_next = fetch_nb(j + 1);
+      // ---- phase 4: this head's 32 columns of the accumulators (lane = query for dQ, key for
+      // dK / dV); warp half 0 drains dQ and dK, half 1 dV
+      au_wait(acc_full, (uint32_t)(j & 1), p.spin);
+      tc_fence_after();
+      uint32_t g0[32], g1[32];
+      if (half == 0) {
+        tmem_ld32(t_lane + 256 + hs * 32, g0);
+        tmem_ld32(t_lane + 320 + hs * 32, g1);
+      } else {
+        tmem_ld32(t_lane + 384 + hs * 32, g0);
+      }
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive_warp(acc_read);
+      if (row < p.S) {
+        __nv_bfloat16* dst = p.dqkv + ((size_t)b * p.S + row) * 3 * p.d + box * 64 + hs * 32;
+        auto put = [&](const uint32_t(&g)[32], int o) {
+          uint4* d4 = reinterpret_cast<uint4*>(dst + o * p.d);
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            d4[c] = make_uint4(au_pack(__uint_as_float(g[8 * c + 0]), __uint_as_float(g[8 * c + 1])),
+                               au_pack(__uint_as_float(g[8 * c + 2]), __uint_as_float(g[8 * c + 3])),
+                               au_pack(__uint_as_float(g[8 * c + 4]), __uint_as_float(g[8 * c + 5])),
+                               au_pack(__uint_as_float(g[8 * c + 6]), __uint_as_float(g[8 * c + 7])));
+        };
+        if (half == 0) {
+          put(g0, 0);
+          put(g1, 1);
+        } else {
+          put(g0, 2);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == AU_WARP_TMA) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 // ================================================================================= host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
@@ -809,13 +1074,38 @@ int attention_umma_fwd(const void* qkv, const int32_t* ids, int B, int S, int H,
 }
 
 bool attention_umma_bwd_supported(int S, int H, int dh) {
-  return attention_umma_supported(S, H, dh) && S <= 64;
+  return attention_umma_supported(S, H, dh);
 }
 
 int attention_umma_bwd(const void* qkv, const void* dout, const float* lse, const int32_t* ids,
                        int B, int S, int H, void* dqkv, cudaStream_t st) {
   const int d = H * 32;
   CUtensorMap tmQ, tmD;
+  if (S > 64) {   // one sequence per item, heads in turn
+    int rc1 = make_tmap_seq3d(&tmQ, qkv, 3 * d, 3 * d, S, B, 128, 1);
+    if (rc1) return rc1;
+    rc1 = make_tmap_seq3d(&tmD, dout, d, d, S, B, 128, 1);
+    if (rc1) return rc1;
+    AttnUmmaParams p1{};
+    p1.ids = ids;
+    p1.lse = const_cast<float*>(lse);
+    p1.dqkv = (__nv_bfloat16*)dqkv;
+    p1.B = B;
+    p1.S = S;
+    p1.H = H;
+    p1.d = d;
+    p1.n_boxes = d / 64;
+    p1.n_items = B * p1.n_boxes;
+    p1.scale = 1.f / sqrtf(32.f);
+    p1.scale2 = AU_LOG2E / sqrtf(32.f);
+    p1.spin = au_spin();
+    const int smem1 = AU_NST * AB_STAGE + AB_PZ + 1024 + 256 + 1024;
+    const int grid1 = std::min(p1.n_items, au_num_sms());
+    B4CP_CUDA(cudaFuncSetAttribute(attention_umma_bwd1_kernel,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, smem1));
+    attention_umma_bwd1_kernel<<<grid1, AU_THREADS, smem1, st>>>(tmQ, tmD, p1);
+    return 0;
+  }
   int rc = make_tmap_seq3d(&tmQ, qkv, 3 * d, 3 * d, S, B, 64, 2);
   if (rc) return rc;
   rc = make_tmap_seq3d(&tmD, dout, d, d, S, B, 64, 2);

@@ -34,8 +34,8 @@ def _umma_attention_fwd(S, H, dh):
 
 
 def _umma_attention_bwd(S, H, dh):
-    """... and its backward for S <= 64: dZ is rounded to bf16 AFTER the 1/sqrt(dh) scale."""
-    return dh == 32 and H % 2 == 0 and S <= 64
+    """... and its backward: dZ is rounded to bf16 AFTER the 1/sqrt(dh) scale."""
+    return dh == 32 and H % 2 == 0 and S <= 128
 
 
 def _mha_fwd(qm, km, vm, pad, H):
