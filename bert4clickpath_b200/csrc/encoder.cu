@@ -498,7 +498,29 @@ residual_ln_bwd_vec_kernel(const float* __restrict__ dy, const float* __restrict
     for (int j = 0; j < 4; ++j) pg[i][j] = pb[i][j] = pr[i][j] = 0.f;
   }
   const long groups = (T + C::RPW - 1) / C::RPW;
-  for (long grp = (long)blockIdx.x * nwarps + warp; grp < groups; grp += (long)gridDim.x * nwarps) {
+  // The loads of the NEXT row group are issued before this group's arithmetic.  With one group
+  // per iteration a warp had 1.5 KB in flight and, at 76 registers (3 CTAs per SM), an SM 36 KB -
+  // about half of what 1/148 of the HBM bandwidth needs at DRAM latency, which is where the
+  // kernel sat (0.63 of the roofline; the 27-register forward kernel: 64 KB in flight, 0.98).
+  const long gstride = (long)gridDim.x * nwarps;
+  auto load_group = [&](long grp, float4 (&X)[C::VPL], float4 (&R)[C::VPL], float4 (&DY)[C::VPL]) {
+    const long row = grp * C::RPW + sub;
+    const bool live = grp < groups && row < T;
+#pragma unroll
+    for (int i = 0; i < C::VPL; ++i) {
+      const int c = (lr + i * C::LPR) * 4;
+      X[i] = R[i] = DY[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (live) {
+        X[i] = *reinterpret_cast<const float4*>(x + row * D + c);
+        R[i] = *reinterpret_cast<const float4*>(r + row * D + c);
+        DY[i] = *reinterpret_cast<const float4*>(dy + row * D + c);
+      }
+    }
+  };
+  float4 Xc[C::VPL], Rc[C::VPL], DYc[C::VPL], Xn[C::VPL], Rn[C::VPL], DYn[C::VPL];
+  load_group((long)blockIdx.x * nwarps + warp, Xc, Rc, DYc);
+  for (long grp = (long)blockIdx.x * nwarps + warp; grp < groups; grp += gstride) {
+    load_group(grp + gstride, Xn, Rn, DYn);
     const long row = grp * C::RPW + sub;
     const bool live = row < T;
     float v[C::VPL][4], g[C::VPL][4], keepf[C::VPL][4], dyv[C::VPL][4];
@@ -506,12 +528,7 @@ residual_ln_bwd_vec_kernel(const float* __restrict__ dy, const float* __restrict
 #pragma unroll
     for (int i = 0; i < C::VPL; ++i) {
       const int c = (lr + i * C::LPR) * 4;
-      float4 xv = make_float4(0.f, 0.f, 0.f, 0.f), rv = xv, dv = xv;
-      if (live) {
-        xv = *reinterpret_cast<const float4*>(x + row * D + c);
-        rv = *reinterpret_cast<const float4*>(r + row * D + c);
-        dv = *reinterpret_cast<const float4*>(dy + row * D + c);
-      }
+      const float4 xv = Xc[i], rv = Rc[i], dv = DYc[i];
       const float xx[4] = {xv.x, xv.y, xv.z, xv.w}, rr[4] = {rv.x, rv.y, rv.z, rv.w};
       dyv[i][0] = dv.x; dyv[i][1] = dv.y; dyv[i][2] = dv.z; dyv[i][3] = dv.w;
 #pragma unroll
@@ -565,6 +582,12 @@ residual_ln_bwd_vec_kernel(const float* __restrict__ dy, const float* __restrict
         if (dr_bf16) store_bf16x4(dr_bf16 + row * ld_bf16 + c, drv);
         if (dr_f32) *reinterpret_cast<float4*>(dr_f32 + row * D + c) = make_float4(drv[0], drv[1], drv[2], drv[3]);
       }
+    }
+#pragma unroll
+    for (int i = 0; i < C::VPL; ++i) {
+      Xc[i] = Xn[i];
+      Rc[i] = Rn[i];
+      DYc[i] = DYn[i];
     }
   }
   // sub-rows of a warp hold the same columns: fold them (fixed order), then one writer per column

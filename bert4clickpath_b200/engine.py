@@ -207,6 +207,7 @@ class WeightStream:
     def __init__(self):
         self.stream = None
         self.readers = {}
+        self.forked = False     # side work queued since the last join
         self.enabled = os.environ.get("B4CP_WEIGHT_STREAM", "1") != "0"
 
     def run(self, fn, *reads):
@@ -219,6 +220,7 @@ class WeightStream:
         if self.stream is None:
             self.stream = torch.cuda.Stream()
         self.stream.wait_stream(cur)
+        self.forked = True
         with torch.cuda.stream(self.stream):
             fn()
             done = torch.cuda.Event()
@@ -240,8 +242,11 @@ class WeightStream:
                 torch.cuda.current_stream().wait_event(ev)
 
     def join(self):
-        if self.stream is not None:
+        # only a stream that was forked from the current one since the last join: waiting on an
+        # idle side stream inside a graph capture is a dependency on uncaptured work
+        if self.forked:
             torch.cuda.current_stream().wait_stream(self.stream)
+            self.forked = False
         self.readers.clear()
 
 

@@ -1,0 +1,13 @@
+#!/bin/bash
+# LayerNorm backward: prefetching loop (tree) against the previous kernel (scratch_ab/libb4cp_old.so)
+mkdir -p gpurun_out
+timeout 300 python -m pytest tests/test_zz_fit_gpu.py -m gpu -q --timeout 300 -rf -x > gpurun_out/ab_pytest.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/ab_pytest.log
+for i in 1 2; do
+  echo "--- new"; timeout 200 python scripts/time_ln.py 2>&1 | grep bwd | cut -c1-60,150-260
+  echo "--- old"; timeout 200 python scripts/with_lib.py scratch_ab/libb4cp_old.so scripts/time_ln.py 2>&1 | grep bwd | cut -c1-60,150-260
+done
+B="bench.py --steps 40 --warmup 10 --no-c4 --no-topk --no-fp32 --sustain-seconds 0 --no-cpu --no-builder"
+for i in 1 2; do
+  timeout 300 python $B 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('new', d['ms_per_step'], (d.get('b512') or {}).get('ms_per_step'))"
+  timeout 300 python scripts/with_lib.py scratch_ab/libb4cp_old.so $B 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('old', d['ms_per_step'], (d.get('b512') or {}).get('ms_per_step'))"
+done

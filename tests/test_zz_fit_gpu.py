@@ -144,3 +144,34 @@ def test_pipelined_host_loop_equals_the_blocking_one(cuda_lib, use_graph):
     wa, wb = ma.store.get_weights(), mb.store.get_weights()
     assert all(np.array_equal(wa[k], wb[k]) for k in wa)
     assert list(tb.run_host(iter(()))) == []
+
+
+def test_weight_stream_schedule_is_bit_identical(cuda_lib):
+    """Weight gradients on the second stream (engine.WeightStream) are the same kernels in the
+    same order per tensor: every gradient and the loss must equal the single-stream schedule
+    bit for bit, eagerly and through the captured graph, with dropout on."""
+    import bert4clickpath_b200 as bc
+    from bert4clickpath_b200 import engine
+    from bert4clickpath_b200.synthetic import make_cloze_batch
+    from bert4clickpath_b200.training import ClozeTrainStep
+    rng = np.random.default_rng(11)
+    batches = [make_cloze_batch(rng, 32, V, max_len=30, mode="train") for _ in range(2)]
+    results = []
+    was = engine.WSTREAM.enabled
+    try:
+        for enabled in (True, False):
+            engine.WSTREAM.enabled = enabled
+            m = _model(dropout=0.1)
+            t = ClozeTrainStep(m, bc.Adam(1e-3), use_graph=True)
+            losses = []
+            for i in range(6):     # 2 eager warm-up steps, capture, replays
+                st = t.step_device(t.to_device(batches[i % 2])).clone()
+                torch.cuda.synchronize()
+                losses.append(st.cpu().numpy().copy())
+            results.append((losses, m.store.get_grads(), m.store.get_weights()))
+    finally:
+        engine.WSTREAM.enabled = was
+    (la, ga, wa), (lb, gb, wb) = results
+    assert all(np.array_equal(x, y) for x, y in zip(la, lb))
+    assert all(np.array_equal(ga[k], gb[k]) for k in ga)
+    assert all(np.array_equal(wa[k], wb[k]) for k in wa)
