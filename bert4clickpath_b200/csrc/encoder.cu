@@ -1043,8 +1043,8 @@ namespace b4cp {
 __global__ void __launch_bounds__(256)
 reduce_splits_ex_kernel(const float* __restrict__ partials, int splits, long M, int N,
                         long split_stride, const __nv_bfloat16* __restrict__ gate, long ld_gate,
-                        float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16,
-                        long ld_bf16) {
+                        float* __restrict__ out_f32, long ld_f32,
+                        __nv_bfloat16* __restrict__ out_bf16, long ld_bf16) {
   const long total = M * N;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total;
        i += (long)gridDim.x * blockDim.x) {
@@ -1053,7 +1053,7 @@ reduce_splits_ex_kernel(const float* __restrict__ partials, int splits, long M, 
     float s = 0.f;
     for (int p = 0; p < splits; ++p) s += partials[(size_t)p * split_stride + i];
     if (gate && !(bf2f(gate[r * ld_gate + c]) > 0.f)) s = 0.f;
-    if (out_f32) out_f32[i] = s;
+    if (out_f32) out_f32[r * ld_f32 + c] = s;
     if (out_bf16) out_bf16[r * ld_bf16 + c] = __float2bfloat16_rn(s);
   }
 }
@@ -1061,11 +1061,13 @@ reduce_splits_ex_kernel(const float* __restrict__ partials, int splits, long M, 
 
 extern "C" int b4cp_reduce_splits_ex(const float* partials, int splits, long M, int N,
                                      long split_stride, const void* gate, long ld_gate,
-                                     float* out_f32, void* out_bf16, long ld_bf16, void* stream) {
+                                     float* out_f32, long ld_f32, void* out_bf16, long ld_bf16,
+                                     void* stream) {
   if (M * N == 0) return 0;
+  B4CP_CHECK_ARG(out_f32 == nullptr || ld_f32 >= N, "reduce_splits_ex: ld_f32=%ld < N=%d", ld_f32, N);
   const int blocks = (int)std::min<long>(ceil_div(M * N, 256), 148L * 16);
   reduce_splits_ex_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
-      partials, splits, M, N, split_stride, (const __nv_bfloat16*)gate, ld_gate, out_f32,
+      partials, splits, M, N, split_stride, (const __nv_bfloat16*)gate, ld_gate, out_f32, ld_f32,
       (__nv_bfloat16*)out_bf16, ld_bf16);
   note_launches(1);
   B4CP_LAUNCH_CHECK();

@@ -197,8 +197,10 @@ def reduce_splits_ex(partials, M, N, gate=None, out_f32=None, out_bf16=None):
     splits = partials.shape[0]
     L.call("b4cp_reduce_splits_ex", L.ptr(partials), L.c_int(splits), L.c_long(M), L.c_int(N),
            L.c_long(partials.stride(0)), L.ptr(gate),
-           L.c_long(gate.stride(0) if gate is not None else 0), L.ptr(out_f32), L.ptr(out_bf16),
-           L.c_long(out_bf16.stride(0) if out_bf16 is not None else 0), L.stream_ptr())
+           L.c_long(gate.stride(0) if gate is not None else 0), L.ptr(out_f32),
+           L.c_long(out_f32.stride(0) if out_f32 is not None and out_f32.dim() == 2 else N),
+           L.ptr(out_bf16), L.c_long(out_bf16.stride(0) if out_bf16 is not None else 0),
+           L.stream_ptr())
 
 
 def cast_bf16(x_f32, cols=None, out=None):

@@ -101,11 +101,12 @@ def export_reference_variables(store_params, features=None):
             for k, v in to_reference_layout(store_params).items()}
 
 
-def import_reference_variables(variables, features=None):
+def import_reference_variables(variables, features=None, dtype=np.float32):
     """Inverse of export_reference_variables: a {TF checkpoint key: array} mapping (what
     `tf.train.load_checkpoint(...).get_tensor` yields on a TF box; optimizer slots and
     bookkeeping keys are ignored) -> the fused store layout, ready for `store.set_weights`.
-    `features` maps the reference's feature-named tables onto the store's positional names."""
+    `features` maps the reference's feature-named tables onto the store's positional names.
+    `dtype=None` keeps the arrays' own type (float64 gradients keyed like the variables)."""
     import re
     pats = [
         (re.compile(r"^transformer/embedding_layers/(.+)/embeddings$"), lambda m: f"emb.{m[1]}"),
@@ -130,6 +131,6 @@ def import_reference_variables(variables, features=None):
         for pat, name in pats:
             m = pat.match(stem)
             if m:
-                ref[_table_name(name(m), features, False)] = np.asarray(arr, dtype=np.float32)
+                ref[_table_name(name(m), features, False)] = np.asarray(arr, dtype=dtype)
                 break
     return to_store_layout(ref)

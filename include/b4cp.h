@@ -70,10 +70,10 @@ int b4cp_gemm_splits_for(int M, int N, int K);
 int b4cp_reduce_splits(const float* partials, int splits, long n, long split_stride, float* out,
                        void* stream);
 /* same, over a dense [M][N] matrix, with an optional ReLU-backward gate (bf16, zero where
- * gate <= 0) and fp32 and/or bf16 outputs */
+ * gate <= 0) and fp32 (row stride ld_f32 >= N) and/or bf16 (row stride ld_bf16) outputs */
 int b4cp_reduce_splits_ex(const float* partials, int splits, long M, int N, long split_stride,
-                          const void* gate, long ld_gate, float* out_f32, void* out_bf16,
-                          long ld_bf16, void* stream);
+                          const void* gate, long ld_gate, float* out_f32, long ld_f32,
+                          void* out_bf16, long ld_bf16, void* stream);
 /* fp32 [rows][ld_in] -> bf16 [rows][ld_out], columns >= cols are zero-filled */
 int b4cp_cast_f32_bf16(const float* in, long rows, int cols, long ld_in, void* out, long ld_out,
                        void* stream);

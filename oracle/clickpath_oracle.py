@@ -378,9 +378,15 @@ def keyed_mask_positions(seed, session, length, n):
     """The n positions of range(length) with the smallest keys splitmix64(splitmix64(seed +
     session) + pos), ties by position, ascending - the stand-in for
     `tf.random.shuffle(tf.range(length))[:n]` followed by the sort of input_pipeline.py:77-78."""
+    return sorted(keyed_mask_positions_order(seed, session, length)[:n])
+
+
+def keyed_mask_positions_order(seed, session, length):
+    """All positions of range(length) by ascending key (ties by position): the permutation that
+    stands in for tf.random.shuffle(tf.range(length)) (input_pipeline.py:28)."""
     base = splitmix64((seed + session) & _M64)
     keys = [(splitmix64((base + i) & _M64), i) for i in range(length)]
-    return sorted(i for _, i in sorted(keys)[:n])
+    return [i for _, i in sorted(keys)]
 
 
 def keyed_cloze_batch(sessions_ids, session_idx, mode, seed, masked_percentage, max_masked, L=None,
@@ -606,12 +612,17 @@ def head_layers(P):
     return out
 
 
-def encoder_fwd(ids_list, P, num_layers, num_heads, pe, dtype=np.float64, masks=None):
+def encoder_fwd(ids_list, P, num_layers, num_heads, pe, dtype=np.float64, masks=None,
+                embed_dtype=np.float32):
     """Transformer.call (transformer.py:376-402): embed, (dropout), encoder stack.
-    masks: optional dict {'in': m, (l,1): m, (l,2): m} of scaled dropout masks."""
+    masks: optional dict {'in': m, (l,1): m, (l,2): m} of scaled dropout masks.
+    embed_dtype: the scale-and-add of the embedding is a float32 computation in the reference and
+    stays one by default even when the rest runs in float64 (the device kernel is byte-exact to
+    it); np.float64 evaluates that step in double as well (the all-float64 graph of
+    tests/golden/reference_*_f64.npz)."""
     F = len(ids_list)
     tables = [P[f"emb.{f}"] for f in range(F)]
-    x0 = embed_fwd(ids_list, tables, pe, dtype=np.float32).astype(dtype)
+    x0 = embed_fwd(ids_list, tables, pe, dtype=embed_dtype).astype(dtype)
     x = x0 * masks["in"] if masks and masks.get("in") is not None else x0
     pad = create_padding_mask(ids_list[0])
     caches = []
@@ -625,12 +636,12 @@ def encoder_fwd(ids_list, P, num_layers, num_heads, pe, dtype=np.float64, masks=
 
 
 def cloze_train_step(ids_list, labels, P, num_layers, num_heads, pe, dtype=np.float64,
-                     masks=None):
+                     masks=None, embed_dtype=np.float32):
     """Forward + backward of the BERT4Rec Cloze model (value_to_head='[MASK]', SoftMaxHead,
     ClozeMaskedLoss) in logits mode.  labels: (B, Mmax) float/ints padded with -1, aligned with
     the (b,s)-ordered [MASK] positions.  Returns loss, grads dict (same keys as P), extras."""
     F = len(ids_list)
-    x, caches = encoder_fwd(ids_list, P, num_layers, num_heads, pe, dtype, masks)
+    x, caches = encoder_fwd(ids_list, P, num_layers, num_heads, pe, dtype, masks, embed_dtype)
     B, S, d = x.shape
     sel, index = select_masked(ids_list[0], x)
     Mmax = sel.shape[1]
@@ -670,22 +681,26 @@ def cloze_train_step(ids_list, labels, P, num_layers, num_heads, pe, dtype=np.fl
 
 
 def segment_binary_train_step(ids_list, y_true, P, num_layers, num_heads, pe, segment,
-                              pos_weight=None, dtype=np.float64):
+                              pos_weight=None, dtype=np.float64, embed_dtype=np.float32,
+                              head_kind="binary"):
     """Forward + backward of the multi-variable click-path classifier: encoder
     (transformer.py:376-402) -> rows of segment `segment` (clickstream_transformer.py:317-322)
     -> BinaryClassificationHead (head.py:4-26) -> MaskedLoss(K.binary_crossentropy, pos_weight)
     (losses.py:31-98), and what TF autodiff derives from it.  y_true: (B, segment length) padded
-    with LABEL_PAD.  Returns loss, grads dict (same keys as P), extras (probs)."""
+    with LABEL_PAD.  Returns loss, grads dict (same keys as P), extras (probs).
+    head_kind='multilabel': MultiLabel_MultiClass_classification (head.py:50-69) on a length-1
+    segment instead, y_true (B, classes)."""
     F = len(ids_list)
-    x, caches = encoder_fwd(ids_list, P, num_layers, num_heads, pe, dtype)
+    x, caches = encoder_fwd(ids_list, P, num_layers, num_heads, pe, dtype, None, embed_dtype)
     starts, ends = segment_bounds(ids_list[0][0])
     s0, s1 = int(starts[segment]), int(ends[segment])
     seg = x[:, s0:s1, :]
     layers = [(w.astype(dtype), b.astype(dtype)) for w, b in head_layers(P)]
     w_out, b_out = P["head.out.w"].astype(dtype), P["head.out.b"].astype(dtype)
-    loss, dseg, lg, dWo, dbo = binary_head_loss_and_grads(seg, layers, w_out, b_out, y_true,
-                                                          pos_weight=pos_weight)
-    probs, _, _ = binary_head_fwd(seg, layers, w_out, b_out)
+    loss_and_grads, fwd = ((binary_head_loss_and_grads, binary_head_fwd) if head_kind == "binary"
+                           else (multilabel_head_loss_and_grads, multilabel_head_fwd))
+    loss, dseg, lg, dWo, dbo = loss_and_grads(seg, layers, w_out, b_out, y_true, pos_weight=pos_weight)
+    probs, _, _ = fwd(seg, layers, w_out, b_out)
     G = {"head.out.w": dWo, "head.out.b": dbo}
     for i, (dw, db) in enumerate(lg):
         G[f"head.{i}.w"], G[f"head.{i}.b"] = dw, db
