@@ -5,13 +5,24 @@ reference file:line each block follows (paths relative to the reference reposito
 `tests/`, `__graft_entry__.smoke()` and `bench.py`'s cpu_baseline / `--impl reference` legs may
 import this module, and only as the checker or the timed CPU baseline.
 
-PARITY UNPINNED: the reference's arithmetic lives in TensorFlow 2.3.1 (requirements.txt:33),
-which cannot be installed here, and the reference ships no tests or golden vectors.  The oracle
-is pinned only by (i) the two known answers in the reference's `__main__` blocks
-(losses.py:101-123 -> 2.9957323; examples/BERT4Rec/source/utils.py:262-272 -> 0.81546488),
-(ii) the docstring example of transformer.py:8-19, and (iii) an independent torch-autograd
-restatement in tests/test_oracle.py.  TensorFlow-library behaviours it assumes are listed in
-SURVEY.md Appendix C and selectable here where they matter (`ce_mode`).
+PARITY PIN: the reference's arithmetic lives in TensorFlow 2.3.1 (requirements.txt:33), which
+cannot be installed here, and the reference ships no tests or golden vectors.  The oracle is
+pinned by OUTPUTS OF THE REFERENCE'S OWN SOURCE RUN IN THIS CONTAINER: its modules are imported
+unmodified from /root/reference on top of tests/golden/tf_shim/tensorflow (a small eager
+implementation of the TensorFlow calls they make, torch autograd as the tape) by
+tests/golden/make_reference_golden.py, and the results are committed as
+tests/golden/reference_*.npz.  tests/test_reference_golden.py holds this file to them: loss,
+probabilities and every gradient of the Cloze model (inference and with recorded dropout masks),
+of the two-feature segment / BinaryClassificationHead model and of the multi-label head within
+1e-12 in float64 (measured 2e-15) and 2e-5 in float32 (measured 1e-6); NDCG / recall / the binary
+metrics; the masking pipeline under keyed permutations; the float32 mask-count rule.  What that
+does NOT pin is TensorFlow's own kernels (summation order, its softmax / rsqrt implementations):
+the float32 run is "float32 with torch's summation order".  Also held: (i) the two known answers
+in the reference's `__main__` blocks (losses.py:101-123 -> 2.9957323;
+examples/BERT4Rec/source/utils.py:262-272 -> 0.81546488), (ii) the docstring example of
+transformer.py:8-19, (iii) an independent torch-autograd restatement in tests/test_oracle.py.
+TensorFlow-library behaviours assumed are listed in SURVEY.md Appendix C and selectable here
+where they matter (`ce_mode`).
 
 All functions take a `dtype` (np.float64 = "truth", np.float32 = TF-like rounding).
 """

@@ -224,3 +224,25 @@ def test_learning_rate_schedules_return_the_reference_values():
                        ("exp_decay:1e-3_1e-5_1000_0.9", CustomExponentialDecayLR(1e-3, 1e-5, 1000, 0.9))):
         got = np.array([np.float32(sched(float(s))) for s in steps], dtype=np.float32)
         assert np.allclose(got, d[key], rtol=3e-7, atol=0), (key, got, d[key])
+
+
+def test_host_input_prep_and_lookup_give_the_reference_ids():
+    """The drop-in's host side (TransformerInputPrep + StaticVocabularyTable) on the reference's
+    string features -> the ids the reference's own prep + tf.lookup tables produced, and the same
+    segment bounds."""
+    from bert4clickpath_b200.clickstream_transformer import StaticVocabularyTable, TransformerInputPrep
+    from bert4clickpath_b200.constants import RESERVED_TOKENS
+    d = load("cloze", "f32")
+    table = StaticVocabularyTable(list(RESERVED_TOKENS) + [str(v) for v in d["vocab"]])
+    raw, starts, ends = TransformerInputPrep({"items": ["asin"]})(features={"asin": d["train0:asin"].astype(object)})
+    assert np.array_equal(table.lookup(raw["items"]), d["train0:ids"])
+    assert table.size() == O.NUM_RESERVED_TOKENS + len(d["vocab"]) + 1
+    d = load("segment", "f32")
+    feats = {k[len("feature:"):]: d[k].astype(object) for k in d.files if k.startswith("feature:")}
+    prep = TransformerInputPrep({"items": ["s_items", "b_items"], "events": ["s_events", "b_events"]})
+    raw, starts, ends = prep(features=feats)
+    assert set(raw) == {"items", "events"}
+    assert np.array_equal(starts, d["segment_starts"]) and np.array_equal(ends, d["segment_ends"])
+    for f, vocab in (("items", d["item_vocab"]), ("events", d["event_vocab"])):
+        table = StaticVocabularyTable(list(RESERVED_TOKENS) + [str(v) for v in vocab])
+        assert np.array_equal(table.lookup(raw[f]), d["ids:" + f])
