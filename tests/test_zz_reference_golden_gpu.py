@@ -32,9 +32,9 @@ from .test_zz_parity_configs_gpu import FP32_TOL, report, tensor_errors
 pytestmark = pytest.mark.gpu
 
 G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-BF16_LOSS_TOL = 2e-2       # measured: see gpurun_out/parity_reference_*_bf16.json
-BF16_FRO_TOL = 0.30
-BF16_PROB_TOL = 5e-2
+BF16_LOSS_TOL = 1e-2       # measured worst 2.6e-3 (segment, pos_weight None)
+BF16_FRO_TOL = 0.25        # measured worst 0.11 (cloze train1, head.0.w: 24 units, one gate)
+BF16_PROB_TOL = 2e-2       # measured worst 3.9e-3
 
 
 def load(case):
