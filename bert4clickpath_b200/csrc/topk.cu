@@ -42,20 +42,17 @@ __device__ __forceinline__ float from_ordered_desc(uint32_t d) {
   return __uint_as_float(u);
 }
 
-__global__ void __launch_bounds__(TK_THREADS)
-topk_rows_kernel(const float* __restrict__ scores, const int32_t* __restrict__ cand_ids, long ld,
-                 int V, int k, int idbits, int32_t* __restrict__ out_ids,
-                 float* __restrict__ out_scores, long ld_out, int only_flagged,
-                 const int* __restrict__ extra_count = nullptr, int base_count = 0) {
-  // second launch after topk_stream_kernel: only rows it flagged (out_ids[row][0] == -2)
-  if (only_flagged && out_ids[(long)blockIdx.x * ld_out] != TK_REDO) return;
+// One row, whole CTA (every thread calls it with the same row).
+__device__ __forceinline__ void
+topk_row(const long row, const float* __restrict__ scores, const int32_t* __restrict__ cand_ids, long ld,
+         int V, int k, int idbits, int32_t* __restrict__ out_ids, float* __restrict__ out_scores,
+         long ld_out, const int* __restrict__ extra_count, int base_count) {
   // counted candidate lists: row r holds base_count + extra_count[r] entries (at most V)
-  if (extra_count) V = min(V, base_count + max(extra_count[blockIdx.x], 0));
+  if (extra_count) V = min(V, base_count + max(extra_count[row], 0));
   __shared__ int hist[TK_BINS];
   __shared__ unsigned long long buf[TK_SORT];
   __shared__ int scan_tmp[40];
   __shared__ int s_bin, s_below, s_nsel;
-  const long row = blockIdx.x;
   const float* z = scores + row * ld;
   // candidate mode: element v carries the id cand[v] (negative = empty slot, skipped)
   const int32_t* cand = cand_ids ? cand_ids + row * ld : nullptr;
@@ -185,6 +182,46 @@ topk_rows_kernel(const float* __restrict__ scores, const int32_t* __restrict__ c
     out_ids[row * ld_out + r] = ok ? (int32_t)(K & idmask) : -1;
     if (out_scores)
       out_scores[row * ld_out + r] = ok ? from_ordered_desc((uint32_t)(K >> idbits)) : -INFINITY;
+  }
+}
+
+__global__ void __launch_bounds__(TK_THREADS)
+topk_rows_kernel(const float* __restrict__ scores, const int32_t* __restrict__ cand_ids, long ld,
+                 int V, int k, int idbits, int32_t* __restrict__ out_ids,
+                 float* __restrict__ out_scores, long ld_out, int only_flagged,
+                 const int* __restrict__ extra_count = nullptr, int base_count = 0) {
+  // second launch after a single-pass kernel: only rows it flagged (out_ids[row][0] == -2)
+  if (only_flagged && out_ids[(long)blockIdx.x * ld_out] != TK_REDO) return;
+  topk_row(blockIdx.x, scores, cand_ids, ld, V, k, idbits, out_ids, out_scores, ld_out, extra_count,
+           base_count);
+}
+
+// The redo pass after a single-pass kernel as a FIXED small grid: one CTA per row costs a CTA
+// launch (1,024 threads, 50 KB of shared memory) per row just to find the flag clear - ~60 us for
+// the 9,472 rows of a C1 ranking batch, a tenth of the whole top-k.  Here every CTA reads the
+// flags of its rows with one parallel load, lists the flagged ones (almost always none) and
+// redoes those.
+static constexpr int TK_REDO_CHUNK = 64;   // rows whose flags one CTA inspects at a time
+
+__global__ void __launch_bounds__(TK_THREADS)
+topk_redo_kernel(const float* __restrict__ scores, long ld, long rows, int V, int k, int idbits,
+                 int32_t* __restrict__ out_ids, float* __restrict__ out_scores, long ld_out) {
+  __shared__ int s_n;
+  __shared__ int s_rows[TK_REDO_CHUNK];
+  for (long base = (long)blockIdx.x * TK_REDO_CHUNK; base < rows; base += (long)gridDim.x * TK_REDO_CHUNK) {
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    const long mine = base + threadIdx.x;
+    if (threadIdx.x < TK_REDO_CHUNK && mine < rows && out_ids[mine * ld_out] == TK_REDO)
+      s_rows[atomicAdd(&s_n, 1)] = (int)(mine - base);
+    __syncthreads();
+    const int n = s_n;
+    for (int i = 0; i < n; ++i) {
+      const long row = base + s_rows[i];
+      __syncthreads();
+      topk_row(row, scores, nullptr, ld, V, k, idbits, out_ids, out_scores, ld_out, nullptr, 0);
+    }
+    __syncthreads();
   }
 }
 
@@ -484,6 +521,181 @@ topk_sample_kernel(const float* __restrict__ scores, long ld, int V, int k, int 
   }
 }
 
+
+// ------------------------------------------------------ sampled threshold, rows of 16K..128K scores
+// Same algorithm as topk_sample_kernel, re-shaped for rows that take only ~10 us to stream (the
+// C1 vocabulary: 54,293 scores = 217 KB), where everything that is not streaming shows:
+//   * 256 threads and 34 KB of shared memory per CTA -> FOUR rows per SM, so the threshold and
+//     finish phases of one row hide under the streaming of three others (the 512-thread kernel
+//     keeps two, and sat at 0.34 of the HBM roofline at V = 54K against 0.77 at V = 1M);
+//   * the sample is 512 float4 (2,048 scores in 512 sectors instead of 2,048);
+//   * the r-th best sample key is found WITHOUT block-wide rounds: every warp peels the r best
+//     distinct keys of its own 256 samples with warp reductions only, one barrier, then warp 0
+//     peels the r best distinct keys of those 8 r candidates (the r-th best of the whole sample is
+//     among them).  The 512-thread kernel pays two block barriers per round, ~3 us per row.
+// The threshold only has to be roughly right: too few (< k) or too many (> SS_CAP) admitted scores
+// flag the row for the exact radix-select redo, as before.
+static constexpr int SS_THREADS = 256;
+static constexpr int SS_CAP = 2048;
+static constexpr int SS_V4 = 2;                       // float4 samples per thread
+static constexpr int SS_RMAX = 64;                    // rounds_target is clamped to [8, 64]
+static constexpr int SS_NS = SS_THREADS * SS_V4 * 4;  // 2,048 sampled scores
+
+__global__ void __launch_bounds__(SS_THREADS, 4)
+topk_sample_small_kernel(const float* __restrict__ scores, long ld, int V, int k, int idbits,
+                         int rounds_tight, int rounds_loose, int32_t* __restrict__ out_ids,
+                         float* __restrict__ out_scores, long ld_out) {
+  extern __shared__ __align__(16) unsigned long long sm_buf[];  // [2 * SS_CAP] (second half: scratch)
+  constexpr int NW = SS_THREADS / 32;
+  __shared__ uint32_t s_cand[NW * SS_RMAX];
+  __shared__ uint32_t s_tau;
+  __shared__ int s_count;
+  const long row = blockIdx.x;
+  const float* z = scores + row * ld;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  auto load_batch = [&](int base, float (&x)[4][4]) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int idx = base + (u * SS_THREADS + tid) * 4;
+      if (idx + 3 < V) {
+        const float4 v4 = __ldg(reinterpret_cast<const float4*>(z + idx));
+        x[u][0] = v4.x; x[u][1] = v4.y; x[u][2] = v4.z; x[u][3] = v4.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) x[u][j] = idx + j < V ? __ldg(z + idx + j) : -INFINITY;
+      }
+    }
+  };
+  // Two attempts.  The first aims the threshold at population rank ~2k: ~2k admitted scores fit
+  // the one-key-per-thread rank count (two barriers) instead of a 512-key bitonic sort (45), and
+  // the search peels half as many keys.  It admits fewer than k scores on a few percent of the
+  // rows; those run once more at rank ~6k, reading the row from L2.  Only a row that fails both
+  // (or overflows the buffer) is left to the radix-select redo.
+  int c = 0;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    const int R = attempt == 0 ? rounds_tight : rounds_loose;
+    // ---- 1. threshold = (about) the sample's R-th best distinct key (ordered_desc: smaller = better)
+    uint32_t key[SS_V4 * 4];
+    {
+      const long V4 = V >> 2;
+      constexpr int NV = SS_THREADS * SS_V4;
+#pragma unroll
+      for (int q = 0; q < SS_V4; ++q) {
+        const long j4 = (long)(tid + SS_THREADS * q) * V4 / NV;
+        const float4 v4 = __ldg(reinterpret_cast<const float4*>(z) + j4);
+        key[4 * q + 0] = ordered_desc(v4.x);
+        key[4 * q + 1] = ordered_desc(v4.y);
+        key[4 * q + 2] = ordered_desc(v4.z);
+        key[4 * q + 3] = ordered_desc(v4.w);
+      }
+    }
+    if (tid == 0) s_count = 0;
+    // the first batch of the streaming pass is requested now: its DRAM latency runs under the
+    // threshold search instead of after it
+    float x[4][4];
+    load_batch(0, x);
+    for (int r = 0; r < R; ++r) {
+      uint32_t m = 0xFFFFFFFFu;
+#pragma unroll
+      for (int q = 0; q < SS_V4 * 4; ++q) m = min(m, key[q]);
+      m = __reduce_min_sync(0xffffffffu, m);
+      if (lane == 0) s_cand[warp * R + r] = m;
+#pragma unroll
+      for (int q = 0; q < SS_V4 * 4; ++q)
+        if (key[q] == m) key[q] = 0xFFFFFFFFu;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      constexpr int PER_LANE = NW * SS_RMAX / 32;
+      uint32_t cd[PER_LANE];
+#pragma unroll
+      for (int i = 0; i < PER_LANE; ++i) {
+        const int idx = lane + 32 * i;
+        cd[i] = idx < NW * R ? s_cand[idx] : 0xFFFFFFFFu;
+      }
+      uint32_t tau = 0xFFFFFFFFu;
+      for (int r = 0; r < R; ++r) {
+        uint32_t m = 0xFFFFFFFFu;
+#pragma unroll
+        for (int i = 0; i < PER_LANE; ++i) m = min(m, cd[i]);
+        m = __reduce_min_sync(0xffffffffu, m);
+        if (m == 0xFFFFFFFFu) break;   // fewer than R distinct sample keys (e.g. an all-ties row)
+        tau = m;
+#pragma unroll
+        for (int i = 0; i < PER_LANE; ++i)
+          if (cd[i] == m) cd[i] = 0xFFFFFFFFu;
+      }
+      if (lane == 0) s_tau = tau;
+    }
+    __syncthreads();
+    const float tau_f = from_ordered_desc(s_tau);
+    // ---- 2. one pass: admit every score >= tau
+    constexpr int BATCH = SS_THREADS * 16;
+    float xn[4][4];
+    for (int base = 0; base < V; base += BATCH) {
+      if (base + BATCH < V) load_batch(base + BATCH, xn);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (x[u][j] >= tau_f) {
+            const int v = base + (u * SS_THREADS + tid) * 4 + j;
+            if (v < V) {
+              const int slot = atomicAdd(&s_count, 1);
+              if (slot < SS_CAP)
+                sm_buf[slot] = ((unsigned long long)ordered_desc(x[u][j]) << idbits) | (unsigned)v;
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) x[u][j] = xn[u][j];
+    }
+    __syncthreads();
+    c = s_count;
+    if (c >= k || rounds_loose <= rounds_tight) break;   // enough (or too many: decided below)
+    __syncthreads();                                      // s_count is reset by the next attempt
+  }
+  if (c > SS_CAP || c < k) {   // threshold too loose / too tight: exact redo by the radix kernel
+    if (tid == 0) out_ids[row * ld_out] = TK_REDO;
+    return;
+  }
+  // ---- 3. exact top-k of the admitted candidates (sorted into sm_buf[0..k)).  Up to 256: rank by
+  // counting, one key per thread.  More (second attempts, k > 128): counting ranks of 400 keys is
+  // 160 K 64-bit comparisons - more issue slots than the whole streaming pass (0.40 of the HBM
+  // roofline at k = 100 when every row did that) - so those take a bitonic sort, 45 barrier steps
+  // but a fifth of the instructions (0.53).
+  {
+    unsigned long long* buf = sm_buf;
+    if (c <= SS_THREADS) {   // rank by counting, one key per thread: c^2 comparisons
+      unsigned long long* dst = buf + SS_CAP;
+      const unsigned long long my = tid < c ? buf[tid] : ~0ull;
+      int rk = 0;
+#pragma unroll 4
+      for (int i = 0; i < c; ++i) rk += buf[i] < my ? 1 : 0;
+      __syncthreads();
+      if (tid < c && rk < k) dst[rk] = my;
+      __syncthreads();
+      for (int i = tid; i < k; i += SS_THREADS) buf[i] = dst[i];
+    } else {
+      int logn = 1;
+      while ((1 << logn) < c) ++logn;
+      for (int i = c + tid; i < (1 << logn); i += SS_THREADS) buf[i] = ~0ull;
+      __syncthreads();
+      block_bitonic_sort(buf, logn);
+    }
+    __syncthreads();
+  }
+  const unsigned long long idmask = (1ull << idbits) - 1ull;
+  for (int r = tid; r < k; r += SS_THREADS) {
+    const unsigned long long K = sm_buf[r];
+    out_ids[row * ld_out + r] = (int32_t)(K & idmask);
+    if (out_scores) out_scores[row * ld_out + r] = from_ordered_desc((uint32_t)(K >> idbits));
+  }
+}
+
 }  // namespace b4cp
 
 using namespace b4cp;
@@ -510,7 +722,16 @@ extern "C" int b4cp_topk_rows(const float* scores, long ld, long rows, int V, in
       int r = (int)((4L * k * ns + V - 1) / V);
       r = std::max(8, std::min(r, 64));
       const size_t smem = (size_t)2 * SM_CAP * sizeof(unsigned long long);
-      if (big) {
+      static const bool small_ok = !(getenv("B4CP_TOPK_SMALL") && getenv("B4CP_TOPK_SMALL")[0] == '0');
+      if (!big && small_ok) {
+        // four rows per SM, warp-local threshold search, two attempts (ranks ~2k, then ~6k)
+        static_assert(SS_NS == SM_THREADS * 4, "the small kernel samples as many scores");
+        const int r_tight = std::max(8, std::min((int)((2L * k * ns + V - 1) / V), SS_RMAX));
+        const int r_loose = std::max(r_tight, std::min((int)((6L * k * ns + V - 1) / V), SS_RMAX));
+        const size_t smem_s = (size_t)2 * SS_CAP * sizeof(unsigned long long);
+        topk_sample_small_kernel<<<(unsigned)rows, SS_THREADS, smem_s, (cudaStream_t)stream>>>(
+            scores, ld, V, k, idbits, r_tight, r_loose, out_ids, out_scores, ld_out);
+      } else if (big) {
         B4CP_CUDA(cudaFuncSetAttribute(topk_sample_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         topk_sample_kernel<16><<<(unsigned)rows, SM_THREADS, smem, (cudaStream_t)stream>>>(
             scores, ld, V, k, idbits, r, out_ids, out_scores, ld_out);
@@ -526,8 +747,9 @@ extern "C" int b4cp_topk_rows(const float* scores, long ld, long rows, int V, in
       topk_stream_kernel<<<(unsigned)rows, ST_THREADS, smem, (cudaStream_t)stream>>>(
           scores, ld, V, k, idbits, out_ids, out_scores, ld_out);
     }
-    topk_rows_kernel<<<(unsigned)rows, TK_THREADS, 0, (cudaStream_t)stream>>>(
-        scores, nullptr, ld, V, k, idbits, out_ids, out_scores, ld_out, 1);
+    const unsigned redo_grid = (unsigned)std::min<long>(ceil_div(rows, (long)TK_REDO_CHUNK), 2 * 148L);
+    topk_redo_kernel<<<redo_grid, TK_THREADS, 0, (cudaStream_t)stream>>>(
+        scores, ld, rows, V, k, idbits, out_ids, out_scores, ld_out);
     note_launches(2);
     B4CP_LAUNCH_CHECK();
     return 0;
