@@ -691,6 +691,46 @@ def run_ours(args, rank, world, local_rank):
                                "indices, b4cp_cloze_build on the device, the training step, D2H loss",
                        "builder_status": int(b_status.item())}
 
+    # ---- end to end from the reference-shaped batch: {raw feature: (B, L) STRING array}, padded
+    # float labels (what input_pipeline.py:198-214 yields and model.fit consumes).  Per step, inside
+    # the timed region: chaining + vocabulary lookup on the host (native table, host threads,
+    # straight into pinned memory), H2D, the step, D2H loss - pipelined by run_host like `e2e`
+    e2e_strings = None
+    if not args.no_strings:
+        try:
+            from bert4clickpath_b200.constants import RESERVED_TOKENS
+            tok = np.asarray(list(RESERVED_TOKENS) + [f"item_{j}" for j in range(V)], dtype=np.str_)
+            str_batches = [({"asin": tok[b["ids"][:, 2:-1]]}, b["labels"]) for b in host]
+            chk = trainer.encode_host(*str_batches[0], parity=0)
+            assert np.array_equal(chk[0].numpy(), host[0]["ids"]) and chk[2] == host[0]["n_masked"]
+
+            def encoded(n):
+                return (trainer.encode_host(*str_batches[i % n_ring], parity=i) for i in range(n))
+
+            for _ in trainer.run_host(encoded(4)):
+                pass
+            s_losses = []
+
+            def strings_loop(_):
+                s_losses.extend(trainer.run_host(encoded(args.steps)))
+                return s_losses[-1]
+
+            ms_s, s_loss = timed(strings_loop, 1)
+            t0 = time.perf_counter()
+            for i in range(8):
+                trainer.encode_host(*str_batches[i % n_ring], parity=i)
+            enc_ms = (time.perf_counter() - t0) * 1e3 / 8
+            e2e_strings = {"value": world * B * args.steps / (ms_s * 1e-3), "unit": "seqs/s",
+                           "ms_per_step": ms_s / args.steps, "host_encode_ms_per_batch": enc_ms,
+                           "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8, "last_loss": s_loss,
+                           "string_dtype": str(str_batches[0][0]["asin"].dtype),
+                           "note": "reference-shaped input: per step TransformerInputPrep chaining + "
+                                   "b4cp_vocab_table_lookup of the (B, L) string array into pinned "
+                                   "memory, H2D, training step, D2H loss; ClozeTrainStep.run_host "
+                                   "overlaps the host encode of batch k+1 with step k"}
+        except Exception as e:   # the leg must not take the bench line down
+            e2e_strings = {"error": repr(e)}
+
     # ---- (after the burst-regime legs above, so that they all run in the thermal state of the
     # headline timed region)
     # ---- the same step held for >= --sustain-seconds (power-capped clocks): the number that
@@ -860,6 +900,7 @@ def run_ours(args, rank, world, local_rank):
                         "memory (copy stream, two landing buffers) and the D2H read of its loss, "
                         "read on the host one step behind the launches"},
         "e2e_from_sessions": e2e_builder,
+        "e2e_strings": e2e_strings,
         "sustained": sustained,
         "b512": b512,
         "fp32_mode": fp32_mode,
@@ -894,6 +935,7 @@ def main():
     ap.add_argument("--no-b512", action="store_true", help="skip the batch-512 leg")
     ap.add_argument("--no-fp32", action="store_true", help="skip the fp32-class parity-mode leg")
     ap.add_argument("--no-builder", action="store_true", help="skip the sessions -> batch -> step leg")
+    ap.add_argument("--no-strings", action="store_true", help="skip the string batch -> step leg")
     ap.add_argument("--no-cpu", action="store_true",
                     help="skip the CPU oracle baseline leg (profiling runs; the line is then incomplete)")
     ap.add_argument("--no-c4", action="store_true", help="skip the C4 / C5 (V=1M, h=256) legs")

@@ -5,9 +5,13 @@ Host side (this file): token chaining `[CLS] [SEP] seq_1 [SEP] seq_2 [SEP] ...`,
 lookup (10 reserved tokens + vocab + 1 OOV bucket), segment bookkeeping.  Device side: everything
 from int ids to the head output / loss / gradients / metrics.
 """
+import ctypes
+import os
+
 import numpy as np
 import torch
 
+from . import _lib as L
 from . import ops
 from .constants import (CLASSIFICATION_TOKEN, CLS, INPUT_MASKING_TOKEN, LABEL_PAD, RESERVED_TOKENS,
                         SEP, SEPARATOR_TOKEN)
@@ -25,28 +29,70 @@ def load_vocabulary(vocab_file):
 
 class StaticVocabularyTable:
     """tf.lookup.StaticVocabularyTable(KeyValueTensorInitializer(keys, range), num_oov_buckets=1)
-    as used at clickstream_transformer.py:247-258: known keys -> their index, anything else ->
-    len(keys); size() counts the OOV bucket."""
+    as used at clickstream_transformer.py:247-258: known keys -> their index (the first occurrence
+    of a duplicated key), anything else -> len(keys); size() counts the OOV bucket.
+
+    The table lives in libb4cp (`b4cp_vocab_table_*`, csrc/vocab_table.cu: open addressing over
+    UCS4 code points, a few host threads): the reference runs this lookup inside its TensorFlow
+    graph on string tensors, and per token in Python it costs ten times the training step it
+    feeds.  String arrays are passed in NumPy's '<U' layout; byte strings are decoded and object
+    arrays converted first (pass '<U' arrays to skip that)."""
+
+    THREADS = max(1, min(8, os.cpu_count() or 1))
 
     def __init__(self, keys):
         self.keys = list(keys)
-        self.table = {}
-        for i, k in enumerate(self.keys):
-            self.table.setdefault(k, i)
         self.oov = len(self.keys)
+        arr = (np.asarray(self.keys, dtype=np.str_) if self.keys else np.zeros((0,), dtype="<U1"))
+        arr = np.ascontiguousarray(arr)
+        width = max(1, arr.dtype.itemsize // 4)
+        if arr.dtype.itemsize == 0:
+            arr = arr.astype("<U1")
+        fn = L.lib().b4cp_vocab_table_create
+        fn.restype = ctypes.c_void_p
+        self._handle = fn(arr.ctypes.data_as(ctypes.c_void_p), ctypes.c_long(len(self.keys)),
+                          ctypes.c_int(width))
+        if not self._handle:
+            raise L.B4cpError(f"b4cp_vocab_table_create failed: {L.lib().b4cp_last_error().decode()}")
+
+    def __del__(self):
+        h, self._handle = getattr(self, "_handle", None), None
+        if h:
+            try:
+                L.lib().b4cp_vocab_table_destroy(ctypes.c_void_p(h))
+            except Exception:      # interpreter shutdown
+                pass
 
     def size(self):
         return len(self.keys) + 1
 
-    def lookup(self, tokens):
+    def lookup(self, tokens, out=None):
+        """ids (int32, same shape) of a string array; integer arrays pass through as ids.
+        `out`: optional C-contiguous int32 array of the same shape to fill (e.g. pinned memory)."""
         arr = np.asarray(tokens)
         if arr.dtype.kind in "iu":
-            return arr.astype(np.int32)  # already ids
+            ids = arr.astype(np.int32)  # already ids
+            if out is not None:
+                out[...] = ids
+                return out
+            return ids
         if arr.dtype.kind == "S":
             arr = np.char.decode(arr, "utf-8")
-        flat = np.fromiter((self.table.get(t, self.oov) for t in arr.reshape(-1).tolist()),
-                           dtype=np.int32, count=arr.size)
-        return flat.reshape(arr.shape)
+        elif arr.dtype.kind != "U":
+            arr = arr.astype(np.str_)
+        if arr.dtype.itemsize == 0:
+            arr = arr.astype("<U1")
+        arr = np.ascontiguousarray(arr)
+        if not arr.dtype.isnative:
+            arr = arr.astype(arr.dtype.newbyteorder("="))
+        if out is None:
+            out = np.empty(arr.shape, dtype=np.int32)
+        assert out.dtype == np.int32 and out.shape == arr.shape and out.flags.c_contiguous
+        L.call("b4cp_vocab_table_lookup", ctypes.c_void_p(self._handle),
+               arr.ctypes.data_as(ctypes.c_void_p), ctypes.c_long(arr.size),
+               ctypes.c_int(arr.dtype.itemsize // 4), out.ctypes.data_as(ctypes.c_void_p),
+               ctypes.c_int(self.THREADS))
+        return out
 
 
 class TransformerInputPrep:
@@ -65,6 +111,10 @@ class TransformerInputPrep:
         sep_v = SEPARATOR_TOKEN if is_str else SEP
         shape = (first.shape[0], 1) + tuple(first.shape[2:])
         dtype = object if is_str else first.dtype
+        if is_str and all(np.asarray(q).dtype.kind == "U" for q in sequences):
+            # fixed-width unicode stays fixed-width (no per-token Python objects on the way to
+            # the native lookup): wide enough for the longest input and for the two tokens
+            dtype = np.result_type(*[np.asarray(q).dtype for q in sequences], np.dtype("<U5"))
         cls_token = np.full(shape, cls_v, dtype=dtype)
         sep_token = np.full(shape, sep_v, dtype=dtype)
         seqs = [cls_token] + [np.asarray(s).astype(dtype) for s in sequences]
@@ -194,15 +244,40 @@ class ClickstreamTransformer:
         return {f: ([None, None], 'string') for f in feats}
 
     # ------------------------------------------------------------------ input preparation
+    def prepare_host(self, inputs, out=None):
+        """dict of raw (B, L_i) string / id arrays -> ({sequential feature: chained int32 (B, S)
+        ids}, segment starts, segment ends), all on the host.
+
+        The reference chains the STRING sequences and looks the chained tensor up
+        (clickstream_transformer.py:38-63, :307-308); the id of a token does not depend on where
+        it stands, so here every raw sequence is looked up first (native table, '<U' arrays are
+        never turned into Python objects) and the int32 pieces are chained with the ids of
+        [CLS] / [SEP] - the same tensor.  `out`: optional {feature: int32 (B, S) array} to fill
+        (pinned staging memory)."""
+        chained = {}
+        for name, chain in self.sequential_input_config.items():
+            table = self.vocab_lookup_tables[name]
+            pieces = []
+            for raw_name in chain:
+                v = inputs[raw_name]
+                pieces.append(table.lookup(v.cpu().numpy() if torch.is_tensor(v) else np.asarray(v)))
+            ids = TransformerInputPrep._chain_sequences(pieces)
+            if out is not None and name in out:
+                out[name][...] = ids
+                ids = out[name]
+            chained[name] = ids
+        first = chained[list(self.sequential_input_config.keys())[0]]
+        sample = first[0, :] if first.shape[0] > 0 else np.asarray([], dtype=np.int32)
+        ends = np.nonzero(sample == SEP)[0]
+        starts = np.concatenate([[0], ends[:-1] + 1]).astype(np.int64)
+        return chained, starts, ends
+
     def prepare_inputs(self, inputs):
         """dict of raw (B, L_i) string / id arrays -> chained device ids per sequential feature."""
-        host = {}
-        for k, v in inputs.items():
-            host[k] = v.cpu().numpy() if torch.is_tensor(v) else np.asarray(v)
-        raw, starts, ends = self.transformer_input_prep(features=host)
+        chained, starts, ends = self.prepare_host(inputs)
         ids_list, shape = [], None
         for name in self.sequential_input_config.keys():
-            ids = self.vocab_lookup_tables[name].lookup(raw[name])
+            ids = chained[name]
             if shape is None:
                 self._host_ids_first = ids
             shape = ids.shape

@@ -49,6 +49,7 @@ class ClozeTrainStep:
         self._host_stats = torch.empty(2, dtype=F32).pin_memory() if torch.cuda.is_available() else None
         self._copy_stream = None
         self._slots = {}
+        self._staging = {}
 
     def _lr(self):
         lr = self.opt.learning_rate
@@ -160,6 +161,30 @@ class ClozeTrainStep:
         torch.cuda.current_stream().synchronize()
         s0, s1 = float(self._host_stats[0]), float(self._host_stats[1])
         return s0 / s1 if s1 > 0 else 0.0
+
+    def encode_host(self, features, labels, parity=0):
+        """A batch as the reference's dataset yields it - {raw feature: (B, L) string array},
+        (B, max_n_masked) float labels padded with -1 (input_pipeline.py:198-214) - to what
+        `step_host` / `run_host` take: (ids_pinned int32 (B, S), labels_pinned, n_masked).  The
+        chaining and the vocabulary lookup (native table, host threads) write straight into pinned
+        staging memory; two staging sets alternate by `parity`, which is what `run_host` needs
+        (it copies batch k while the caller encodes batch k + 1)."""
+        m = self.model
+        name = list(m.sequential_input_config.keys())[0]
+        assert len(m.sequential_input_config) == 1, "the Cloze step takes one sequential feature"
+        first_raw = np.asarray(features[m.sequential_input_config[name][0]])
+        B = first_raw.shape[0]
+        S = 1 + sum(np.asarray(features[r]).shape[1] + 1 for r in m.sequential_input_config[name]) + 1
+        labels = np.asarray(labels, dtype=np.float32)
+        key = (parity & 1, B, S, labels.shape)
+        st = self._staging.get(key)
+        if st is None:
+            st = (torch.empty((B, S), dtype=I32).pin_memory(), torch.empty(labels.shape, dtype=F32).pin_memory())
+            self._staging[key] = st
+        ids_pinned, labels_pinned = st
+        m.prepare_host(features, out={name: ids_pinned.numpy()})
+        labels_pinned.numpy()[...] = labels
+        return ids_pinned, labels_pinned, int((labels != -1.0).sum())
 
     def run_host(self, batches):
         """The end-to-end loop a `model.fit(dataset.prefetch(...))` of the reference runs

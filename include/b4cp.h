@@ -226,6 +226,19 @@ int b4cp_cloze_build(const int32_t* items, const long long* offsets, const int32
 unsigned long long b4cp_cloze_position_key(unsigned long long seed, unsigned long long session,
                                            unsigned long long pos);
 
+/* ------------------------------------------------------------------ host: vocabulary lookup
+ * tf.lookup.StaticVocabularyTable(KeyValueTensorInitializer(keys, range(len(keys))),
+ * num_oov_buckets=1) as clickstream_transformer/clickstream_transformer.py:247-258 builds it, on
+ * the host (the reference runs it inside its graph on string tensors): key j -> j (first
+ * occurrence of a duplicate), any other string -> n_keys.  Strings are fixed-width UCS4 code
+ * points, NUL padded (NumPy's '<U<width>' layout).  No device is needed.  lookup fills
+ * out_ids[n_tokens] with up to n_threads host threads. */
+void* b4cp_vocab_table_create(const uint32_t* keys_ucs4, long n_keys, int width);
+void b4cp_vocab_table_destroy(void* table);
+long b4cp_vocab_table_size(const void* table);
+int b4cp_vocab_table_lookup(const void* table, const uint32_t* tokens_ucs4, long n_tokens, int width,
+                            int32_t* out_ids, int n_threads);
+
 /* ------------------------------------------------------------------ Cloze loss, materialised
  * Small-vocabulary path of SoftMaxHead + ClozeMaskedLoss (head.py:38-47;
  * examples/BERT4Rec/source/utils.py:56-134; losses.py:31-98) in logits mode.

@@ -501,3 +501,52 @@ def test_table_exchange_plan_is_by_size(monkeypatch):
     monkeypatch.setattr(dist, "get_world_size", lambda group=None: 1)
     eng.rows, eng.dims, eng.d = [1_000_011], [256], 256
     assert eng.plan_table_exchange(256 * 202)[0] == [False]    # one rank: nothing to exchange
+
+
+def test_native_vocabulary_table_equals_a_dict_lookup():
+    """b4cp_vocab_table_* (host code in libb4cp, csrc/vocab_table.cu) against the Python dict
+    semantics of tf.lookup.StaticVocabularyTable with one OOV bucket
+    (clickstream_transformer.py:247-258): first occurrence of a duplicated key, every unknown
+    string -> len(keys), any string width, unicode, empty strings, bytes, ids passed through."""
+    from bert4clickpath_b200.clickstream_transformer import StaticVocabularyTable
+    from bert4clickpath_b200.constants import RESERVED_TOKENS
+    rng = np.random.default_rng(5)
+    alphabet = list("abcXYZ019_-[]") + ["é", "ü", "項", "𝄞"]
+    keys = list(RESERVED_TOKENS)
+    for _ in range(3000):
+        keys.append("".join(rng.choice(alphabet, size=int(rng.integers(0, 14)))))
+    keys += keys[100:120]                                    # duplicates: first occurrence wins
+    table = StaticVocabularyTable(keys)
+    want = {}
+    for i, k in enumerate(keys):
+        want.setdefault(k, i)
+    assert table.size() == len(keys) + 1
+    probes = list(rng.choice(keys, size=5000)) + [k + "?" for k in rng.choice(keys, size=500)] + \
+        ["", "a-much-longer-token-than-any-key-in-the-table", "[MASK]", "[PAD]"]
+    for dtype in (np.str_, object):
+        arr = np.asarray(probes, dtype=dtype).reshape(-1, 4)
+        got = table.lookup(arr)
+        assert got.dtype == np.int32 and got.shape == arr.shape
+        assert got.reshape(-1).tolist() == [want.get(p, len(keys)) for p in probes]
+    ascii_probes = [p for p in probes if p.isascii()]
+    got = table.lookup(np.asarray([p.encode() for p in ascii_probes]))
+    assert got.tolist() == [want.get(p, len(keys)) for p in ascii_probes]
+    assert table.lookup(np.array([[3, 7]])).tolist() == [[3, 7]]          # ids pass through
+    assert table.lookup(np.zeros((0, 5), dtype="<U3")).shape == (0, 5)
+    out = np.full((2, 2), -7, dtype=np.int32)
+    assert table.lookup(np.array([["[CLS]", "[SEP]"], ["nope", "[NA]"]]), out=out) is out
+    assert out.tolist() == [[3, 4], [len(keys), 5]]
+    # many tokens: the multi-threaded split covers every element exactly once
+    big = np.asarray(rng.choice(keys[:2000], size=200_000), dtype=np.str_)
+    assert np.array_equal(table.lookup(big), np.array([want[p] for p in big.tolist()], dtype=np.int32))
+
+
+def test_chaining_fixed_width_strings_stays_fixed_width():
+    from bert4clickpath_b200.clickstream_transformer import TransformerInputPrep
+    a = np.array([["x1", "[PAD]"], ["a-long-token", "y"]])
+    b = np.array([["q"], ["r"]])
+    raw, starts, ends = TransformerInputPrep({"items": ["a", "b"]})(features={"a": a, "b": b})
+    assert raw["items"].dtype.kind == "U"
+    assert raw["items"].tolist() == [["[CLS]", "[SEP]", "x1", "[PAD]", "[SEP]", "q", "[SEP]"],
+                                     ["[CLS]", "[SEP]", "a-long-token", "y", "[SEP]", "r", "[SEP]"]]
+    assert starts.tolist() == [0, 2, 5] and ends.tolist() == [1, 4, 6]

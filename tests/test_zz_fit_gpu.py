@@ -175,3 +175,34 @@ def test_weight_stream_schedule_is_bit_identical(cuda_lib):
     assert all(np.array_equal(x, y) for x, y in zip(la, lb))
     assert all(np.array_equal(ga[k], gb[k]) for k in ga)
     assert all(np.array_equal(wa[k], wb[k]) for k in wa)
+
+
+def test_string_batches_through_encode_host_train_like_the_id_batches(cuda_lib):
+    """The reference-shaped input ({raw feature: (B, L) strings}, padded labels) through
+    encode_host (chaining + native vocabulary lookup into pinned memory) + run_host must give the
+    ids of the pre-chained batch and train identically: same losses, same weights - for '<U'
+    arrays and for object arrays, including an out-of-vocabulary string."""
+    import bert4clickpath_b200 as bc
+    from bert4clickpath_b200.constants import RESERVED_TOKENS
+    from bert4clickpath_b200.synthetic import make_cloze_batch
+    from bert4clickpath_b200.training import ClozeTrainStep
+    rng = np.random.default_rng(8)
+    host = [make_cloze_batch(rng, 32, V, max_len=30, mode="train", lengths="beauty") for _ in range(3)]
+    tok = np.asarray(list(RESERVED_TOKENS) + [f"item_{j}" for j in range(V)] + ["never-seen"], dtype=np.str_)
+    host[1]["ids"][0, 2] = len(tok) - 1                      # the OOV bucket = 10 + V
+    strings = [({"asin": tok[b["ids"][:, 2:-1]]}, b["labels"]) for b in host]
+    strings[2] = ({"asin": strings[2][0]["asin"].astype(object)}, strings[2][1])
+    pinned = [(torch.from_numpy(b["ids"]).pin_memory(), torch.from_numpy(b["labels"]).pin_memory(),
+               b["n_masked"]) for b in host]
+    order = [0, 1, 2, 1, 0]
+    ma, mb = _model(dropout=0.0), _model(dropout=0.0)
+    ta, tb = ClozeTrainStep(ma, bc.Adam(1e-3), use_graph=True), ClozeTrainStep(mb, bc.Adam(1e-3), use_graph=True)
+    for i in range(3):
+        ids_p, lab_p, n = tb.encode_host(*strings[i], parity=i)
+        assert np.array_equal(ids_p.numpy(), host[i]["ids"]) and n == host[i]["n_masked"]
+        assert np.array_equal(lab_p.numpy(), host[i]["labels"])
+    want = list(ta.run_host(pinned[i] for i in order))
+    got = list(tb.run_host(tb.encode_host(*strings[i], parity=k) for k, i in enumerate(order)))
+    assert got == want
+    wa, wb = ma.store.get_weights(), mb.store.get_weights()
+    assert all(np.array_equal(wa[k], wb[k]) for k in wa)
