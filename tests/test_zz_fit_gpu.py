@@ -189,7 +189,8 @@ def test_string_batches_through_encode_host_train_like_the_id_batches(cuda_lib):
     rng = np.random.default_rng(8)
     host = [make_cloze_batch(rng, 32, V, max_len=30, mode="train", lengths="beauty") for _ in range(3)]
     tok = np.asarray(list(RESERVED_TOKENS) + [f"item_{j}" for j in range(V)] + ["never-seen"], dtype=np.str_)
-    host[1]["ids"][0, 2] = len(tok) - 1                      # the OOV bucket = 10 + V
+    col = int(np.nonzero(host[1]["ids"][0] >= 10)[0][0])     # an ordinary item (not [MASK] / [PAD])
+    host[1]["ids"][0, col] = len(tok) - 1                    # -> the OOV bucket = 10 + V
     strings = [({"asin": tok[b["ids"][:, 2:-1]]}, b["labels"]) for b in host]
     strings[2] = ({"asin": strings[2][0]["asin"].astype(object)}, strings[2][1])
     pinned = [(torch.from_numpy(b["ids"]).pin_memory(), torch.from_numpy(b["labels"]).pin_memory(),
