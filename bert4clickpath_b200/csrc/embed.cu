@@ -361,7 +361,7 @@ static constexpr int SEG_NV = 8;      // columns per lane: dim <= 256
 static constexpr int SEG_LONG = 16;   // tiles
 
 template <int NV>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, NV <= 2 ? 3 : 1)   // d <= 64: <= 85 registers, 3 CTAs per SM
 segment_tile_sum_kernel(const float* __restrict__ dout, int d_model, int off, int dim,
                         const uint32_t* __restrict__ skeys, const uint32_t* __restrict__ stok,
                         long n, int rows, float scale, float inv_keep, uint32_t thresh24,
@@ -403,29 +403,68 @@ segment_tile_sum_kernel(const float* __restrict__ dout, int d_model, int off, in
       for (int v = 0; v < NV; ++v) acc[v] = 0.f;
     };
     // G tokens per step: all their row loads are issued before the first add (one warp keeps
-    // G * NV 128-byte requests in flight instead of one row at a time)
+    // G * NV 128-byte requests in flight instead of one row at a time).  The loads carry NO
+    // branch: with `if (i < cnt && c < dim) x = load` every load sat in its own divergence region
+    // and ncu showed 73 % of the stall samples on the first use of each loaded value, one DRAM
+    // latency after another (82 us for the 213k tokens of a C1 batch, 8 % of the DRAM
+    // throughput).  Lanes past the tile's end hold token 0 and columns past `dim` read column 0 -
+    // valid addresses - and the values are zeroed afterwards.  (d <= 64 only: at 4 or 8 columns
+    // per lane the same form needs 128 registers or spills, and measured 6 % slower at d = 256.)
     constexpr int G = NV <= 4 ? 8 : 4;
     for (int i0 = 0; i0 < cnt; i0 += G) {
       uint32_t kk[G];
       float g[G][NV];
+      if constexpr (NV <= 2) {
+        uint32_t tt[G];
 #pragma unroll
-      for (int j = 0; j < G; ++j) {
-        const int i = i0 + j;   // i0 is a multiple of G, G divides 32: one branch per step
-        kk[j] = i0 < 32 ? __shfl_sync(0xffffffffu, k0, i & 31) : __shfl_sync(0xffffffffu, k1, i & 31);
-        const uint32_t ti = i0 < 32 ? __shfl_sync(0xffffffffu, t0, i & 31) : __shfl_sync(0xffffffffu, t1, i & 31);
-        const float* src = dout + (size_t)ti * d_model + off;
+        for (int j = 0; j < G; ++j) {
+          const int i = i0 + j;   // i0 is a multiple of G, G divides 32: one branch per step
+          kk[j] = i0 < 32 ? __shfl_sync(0xffffffffu, k0, i & 31) : __shfl_sync(0xffffffffu, k1, i & 31);
+          tt[j] = i0 < 32 ? __shfl_sync(0xffffffffu, t0, i & 31) : __shfl_sync(0xffffffffu, t1, i & 31);
+        }
 #pragma unroll
-        for (int v = 0; v < NV; ++v) {
-          const int c = lane + 32 * v;
-          float x = 0.f;
-          if (i < cnt && c < dim) {
-            x = __ldg(src + c);
+        for (int j = 0; j < G; ++j) {
+          const float* src = dout + (size_t)tt[j] * d_model + off;
+#pragma unroll
+          for (int v = 0; v < NV; ++v) {
+            const int c = lane + 32 * v;
+            g[j][v] = __ldg(src + (c < dim ? c : 0));
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < G; ++j) {
+          const bool live = i0 + j < cnt;
+#pragma unroll
+          for (int v = 0; v < NV; ++v) {
+            const int c = lane + 32 * v;
+            float x = g[j][v];
             if (thresh24) {
-              const bool keep = dropout_keep(seed, site, (uint64_t)ti * d_model + off + c, thresh24);
+              const bool keep = dropout_keep(seed, site, (uint64_t)tt[j] * d_model + off + c, thresh24);
               x = keep ? __fmul_rn(x, inv_keep) : 0.f;
             }
+            g[j][v] = (live && c < dim) ? x : 0.f;
           }
-          g[j][v] = x;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < G; ++j) {
+          const int i = i0 + j;   // i0 is a multiple of G, G divides 32: one branch per step
+          kk[j] = i0 < 32 ? __shfl_sync(0xffffffffu, k0, i & 31) : __shfl_sync(0xffffffffu, k1, i & 31);
+          const uint32_t ti = i0 < 32 ? __shfl_sync(0xffffffffu, t0, i & 31) : __shfl_sync(0xffffffffu, t1, i & 31);
+          const float* src = dout + (size_t)ti * d_model + off;
+#pragma unroll
+          for (int v = 0; v < NV; ++v) {
+            const int c = lane + 32 * v;
+            float x = 0.f;
+            if (i < cnt && c < dim) {
+              x = __ldg(src + c);
+              if (thresh24) {
+                const bool keep = dropout_keep(seed, site, (uint64_t)ti * d_model + off + c, thresh24);
+                x = keep ? __fmul_rn(x, inv_keep) : 0.f;
+              }
+            }
+            g[j][v] = x;
+          }
         }
       }
 #pragma unroll
