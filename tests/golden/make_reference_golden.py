@@ -308,6 +308,42 @@ def case_schedules_and_masking(tf, tmp):
         assert (masked == "[MASK]").sum() == len(labels)
         counts[f"{n}|{p}|{cap}"] = int(len(labels))
     out["n_masked"] = np.array(json.dumps(counts))
+    out.update(_clipped_losses(tf))
+    return out
+
+
+def _clipped_losses(tf):
+    """ClozeMaskedLoss / MaskedLoss on PROBABILITIES where TF 2.3's clip to [1e-7, 1 - 1e-7] is
+    active (peaked rows: the label's probability far below 1e-7, or above 1 - 1e-7) - the regime
+    where K.sparse_categorical_crossentropy's clip -> log -> softmax-CE differs from -log p_t
+     - and MaskedLoss(K.binary_crossentropy) at saturated sigmoids."""
+    from clickstream_transformer.constants import LABEL_PAD
+    from clickstream_transformer.losses import MaskedLoss
+    from source.utils import ClozeMaskedLoss
+    rng = np.random.default_rng(SEED + 9)
+    B, M, V = 5, 4, 23
+    z = rng.normal(size=(B, M, V)) * np.array([1.0, 8.0, 30.0, 60.0])[None, :, None]
+    p = np.exp(z - z.max(-1, keepdims=True))
+    p = (p / p.sum(-1, keepdims=True)).astype(np.float32)
+    y = rng.integers(0, V, size=(B, M)).astype(np.float32)
+    y[0, 2:] = LABEL_PAD
+    y[3, :] = LABEL_PAD
+    y[1, 3] = float(np.argmax(p[1, 3]))          # a label whose probability is clipped from above
+    out = {"clip:probs": p, "clip:labels": y}
+    out["clip:cloze_loss"] = ClozeMaskedLoss(tf.keras.backend.sparse_categorical_crossentropy,
+                                             label_pad=LABEL_PAD)(y, p).numpy()
+    flat_y, flat_p = y.reshape(-1), p.reshape(-1, V)
+    out["clip:masked_scc_loss"] = MaskedLoss(tf.keras.backend.sparse_categorical_crossentropy)(
+        flat_y, flat_p).numpy()
+    q = (1.0 / (1.0 + np.exp(-rng.normal(size=(B, M)) * 25.0))).astype(np.float32)   # many exact 0 / 1
+    t = rng.integers(0, 2, size=(B, M)).astype(np.float32)
+    t[2, 1:] = LABEL_PAD
+    out["clip:sigmoid_probs"], out["clip:binary_labels"] = q, t
+    out["clip:masked_bce_loss"] = MaskedLoss(tf.keras.backend.binary_crossentropy)(t, q).numpy()
+    out["clip:masked_bce_loss_pw"] = MaskedLoss(tf.keras.backend.binary_crossentropy, pos_weight=4.0)(t, q).numpy()
+    # an empty batch: the reference returns 0.0 instead of 0 / 0 (losses.py:89-91)
+    out["clip:empty_loss"] = np.float32(MaskedLoss(tf.keras.backend.binary_crossentropy)(
+        np.zeros((0, 3), np.float32), np.zeros((0, 3), np.float32)))
     return out
 
 
@@ -327,8 +363,6 @@ def main():
         return child(sys.argv[2], sys.argv[3])
     for case in CASES:
         for mode in ("f32", "f64"):
-            if case == "misc" and mode == "f64":
-                continue
             path = os.path.join(HERE, f"reference_{case}_{mode}.npz")
             env = dict(os.environ, TFSHIM_FLOAT64="1" if mode == "f64" else "0")
             subprocess.run([sys.executable, os.path.abspath(__file__), "--child", case, path],

@@ -101,6 +101,8 @@ def _t(x, dtype=None):
         t = _torch.from_numpy(_np.ascontiguousarray(x)).clone()
         if t.dtype == _torch.float64 and dtype == float32:
             t = _round_f32(t)
+        elif t.dtype == _torch.float32:
+            t = t.to(float32)      # a NumPy float32 array is a tf.float32 tensor (float64 mode: widened)
     elif isinstance(x, _b.range):
         t = _torch.tensor(list(x), dtype=_torch.int32)
     else:

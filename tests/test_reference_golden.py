@@ -246,3 +246,28 @@ def test_host_input_prep_and_lookup_give_the_reference_ids():
     for f, vocab in (("items", d["item_vocab"]), ("events", d["event_vocab"])):
         table = StaticVocabularyTable(list(RESERVED_TOKENS) + [str(v) for v in vocab])
         assert np.array_equal(table.lookup(raw[f]), d["ids:" + f])
+
+
+@pytest.mark.parametrize("mode", ["f64", "f32"])
+def test_losses_where_the_tf_clip_is_active_match_the_reference_run(mode):
+    """K.sparse_categorical_crossentropy / K.binary_crossentropy on PROBABILITIES with the label's
+    probability far outside [1e-7, 1 - 1e-7]: the oracle's 'exact_tf23' forms
+    (clip -> log -> softmax-CE; clip -> log(p + eps)) against ClozeMaskedLoss / MaskedLoss of the
+    reference, and the logits-mode value must DIFFER there (that is the regime the two part)."""
+    d = load("misc", mode)
+    dt = np.float64 if mode == "f64" else np.float32
+    tol = 1e-12 if mode == "f64" else 2e-6
+    p, y = d["clip:probs"].astype(dt), d["clip:labels"]
+    assert (p[np.arange(5)[:, None], np.arange(4)[None, :], np.maximum(y, 0).astype(int)] < 1e-7).any()
+    got = O.cloze_masked_loss(y, p, ce_mode="exact_tf23")
+    assert rel(got, d["clip:cloze_loss"]) < tol
+    assert rel(O.cloze_masked_loss(y, p, ce_mode="logits"), d["clip:cloze_loss"]) > 1e-2
+    flat = O.masked_loss(y.reshape(-1).astype(dt), p.reshape(-1, p.shape[-1]),
+                         lambda yy, pp: O.sparse_categorical_crossentropy_probs(yy, pp, "exact_tf23"))
+    assert rel(flat, d["clip:masked_scc_loss"]) < tol
+    q, t = d["clip:sigmoid_probs"].astype(dt), d["clip:binary_labels"].astype(dt)
+    assert ((q == 0) | (q == 1)).any()
+    assert rel(O.masked_loss(t, q, O.binary_crossentropy_probs), d["clip:masked_bce_loss"]) < tol
+    assert rel(O.masked_loss(t, q, O.binary_crossentropy_probs, pos_weight=4.0), d["clip:masked_bce_loss_pw"]) < tol
+    assert float(d["clip:empty_loss"]) == 0.0
+    assert float(O.masked_loss(np.zeros((0, 3), dt), np.zeros((0, 3), dt), O.binary_crossentropy_probs)) == 0.0
