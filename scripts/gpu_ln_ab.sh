@@ -1,5 +1,8 @@
 #!/bin/bash
-# LayerNorm backward: prefetching loop (tree) against the previous kernel (scratch_ab/libb4cp_old.so)
+# LayerNorm backward: prefetching loop (tree) against the previous kernel.  Build the other side first:
+#   git show <rev>:bert4clickpath_b200/csrc/encoder.cu > /tmp/e.cu && nvcc <build.py FLAGS> -c /tmp/e.cu -o /tmp/e.o
+#   nvcc -shared -cudart shared -o scratch_ab/libb4cp_old.so $(ls bert4clickpath_b200/csrc/build/*.o | grep -v /encoder.o) /tmp/e.o
+# (scratch_ab/ is not tracked; *.so files travel to the GPU box with the tree)
 mkdir -p gpurun_out
 timeout 300 python -m pytest tests/test_zz_fit_gpu.py -m gpu -q --timeout 300 -rf -x > gpurun_out/ab_pytest.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/ab_pytest.log
 for i in 1 2; do
