@@ -178,3 +178,24 @@ def test_multilabel_step_matches_the_reference_run(cuda_lib, tmp_path, precision
     errs = tensor_errors(W.to_reference_layout(model.store.get_grads()), want, want)
     probs = model.call(feats, training=False).cpu().numpy().reshape(d["probs"].shape)
     judge("multilabel", precision, abs(loss - want_loss) / want_loss, errs, rel_pair(probs, d["probs"]))
+
+
+def test_materialised_losses_in_the_clip_regime_match_the_reference_run(cuda_lib):
+    """ClozeMaskedLoss / MaskedLoss of the drop-in on materialised PROBABILITIES, where TF 2.3's
+    clip to [1e-7, 1 - 1e-7] is active (labels with probability far below 1e-7, saturated
+    sigmoids): `b4cp_clip_log` + the row CE kernels and `b4cp_masked_bce` against the values the
+    reference's own loss classes returned (tests/golden/reference_misc_f32.npz)."""
+    import bert4clickpath_b200 as bc
+    d = np.load(os.path.join(G, "reference_misc_f32.npz"))
+    p, y = d["clip:probs"], d["clip:labels"]
+    V = p.shape[-1]
+    got = bc.ClozeMaskedLoss(bc.sparse_categorical_crossentropy)(y, p)
+    assert abs(got - float(d["clip:cloze_loss"])) < 2e-5 * float(d["clip:cloze_loss"])
+    got = bc.MaskedLoss(bc.sparse_categorical_crossentropy)(y.reshape(-1), p.reshape(-1, V))
+    assert abs(got - float(d["clip:masked_scc_loss"])) < 2e-5 * float(d["clip:masked_scc_loss"])
+    q, t = d["clip:sigmoid_probs"], d["clip:binary_labels"]
+    got = bc.MaskedLoss(bc.binary_crossentropy)(t, q)
+    assert abs(got - float(d["clip:masked_bce_loss"])) < 2e-5 * float(d["clip:masked_bce_loss"])
+    got = bc.MaskedLoss(bc.binary_crossentropy, pos_weight=4.0)(t, q)
+    assert abs(got - float(d["clip:masked_bce_loss_pw"])) < 2e-5 * float(d["clip:masked_bce_loss_pw"])
+    assert bc.MaskedLoss(bc.binary_crossentropy)(np.zeros((0, 3), np.float32), np.zeros((0, 3), np.float32)) == 0.0
